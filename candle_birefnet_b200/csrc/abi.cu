@@ -1,0 +1,293 @@
+// extern "C" surface of libbirefnet_b200.so (include/birefnet_b200.h).  Nothing throws across this boundary.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "model.h"
+
+using namespace brn;
+
+static thread_local std::string g_err;
+
+template <class F>
+static brn_status guard(F&& f) {
+  try {
+    f();
+    return BRN_OK;
+  } catch (const Error& e) {
+    g_err = e.what();
+    return (brn_status)e.status;
+  } catch (const std::exception& e) {
+    g_err = std::string("internal error: ") + e.what();
+    return BRN_ERR_INVALID;
+  } catch (...) {
+    g_err = "unknown internal error";
+    return BRN_ERR_INVALID;
+  }
+}
+
+struct brn_model {
+  Model impl;
+  brn_model(const brn_config& c, int dev) : impl(c, dev) {}
+};
+
+extern "C" {
+
+const char* brn_last_error(void) { return g_err.c_str(); }
+const char* brn_version(void) { return "birefnet_b200 0.1 (sm_100a)"; }
+
+void brn_config_swin_l(brn_config* cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->embed_dim = 192;
+  const int d[4] = {2, 2, 18, 2}, h[4] = {6, 12, 24, 48};
+  for (int i = 0; i < 4; ++i) { cfg->depths[i] = d[i]; cfg->num_heads[i] = h[i]; }
+  cfg->window_size = 12; cfg->mlp_ratio = 4; cfg->patch_size = 4;
+  cfg->precision = BRN_PREC_BF16; cfg->deform_mode = BRN_DEFORM_DEFORMABLE; cfg->micro_batch = 0;
+}
+
+brn_status brn_model_create(const brn_config* cfg, int device, brn_model** out) {
+  return guard([&] {
+    BRN_CHECK(cfg && out, 1, "brn_model_create: null argument");
+    *out = new brn_model(*cfg, device);
+  });
+}
+
+void brn_model_destroy(brn_model* m) { delete m; }
+
+brn_status brn_model_set_tensor(brn_model* m, const char* key, const void* data, int dtype, const int64_t* shape,
+                                int rank) {
+  return guard([&] {
+    BRN_CHECK(m, 1, "null model");
+    std::lock_guard<std::mutex> lk(m->impl.mu);
+    m->impl.set_tensor(key, data, dtype, shape, rank);
+  });
+}
+
+int32_t brn_model_num_tensors(const brn_model* m) { return m ? (int32_t)m->impl.keys.size() : 0; }
+
+brn_status brn_model_tensor_info(const brn_model* m, int32_t i, const char** key, int64_t shape[4], int32_t* rank) {
+  return guard([&] {
+    BRN_CHECK(m && key && shape && rank, 1, "null argument");
+    BRN_CHECK(i >= 0 && i < (int32_t)m->impl.keys.size(), 1, "tensor index out of range");
+    *key = m->impl.keys[i].c_str();
+    const auto& s = m->impl.tensors[i].shape;
+    *rank = (int32_t)s.size();
+    for (size_t d = 0; d < 4; ++d) shape[d] = d < s.size() ? s[d] : 1;
+  });
+}
+
+brn_status brn_model_finalize(brn_model* m) {
+  return guard([&] {
+    BRN_CHECK(m, 1, "null model");
+    std::lock_guard<std::mutex> lk(m->impl.mu);
+    m->impl.finalize();
+  });
+}
+
+brn_status brn_model_set_precision(brn_model* m, int precision) {
+  return guard([&] {
+    BRN_CHECK(m, 1, "null model");
+    BRN_CHECK(precision == BRN_PREC_FP32 || precision == BRN_PREC_BF16, 1, "bad precision");
+    std::lock_guard<std::mutex> lk(m->impl.mu);
+    m->impl.cfg.precision = precision;
+  });
+}
+
+brn_status brn_model_set_deform_mode(brn_model* m, int mode) {
+  return guard([&] {
+    BRN_CHECK(m, 1, "null model");
+    BRN_CHECK(mode == BRN_DEFORM_CPU_FALLBACK || mode == BRN_DEFORM_DEFORMABLE, 1, "bad deform mode");
+    std::lock_guard<std::mutex> lk(m->impl.mu);
+    m->impl.cfg.deform_mode = mode;
+  });
+}
+
+brn_status brn_forward_logits(brn_model* m, const float* x, int32_t B, int32_t H, int32_t W, int x_is_device,
+                              float* out, int out_is_device, void* stream) {
+  return guard([&] {
+    BRN_CHECK(m, 1, "null model");
+    m->impl.forward(x, B, H, W, x_is_device != 0, out, out_is_device != 0, (cudaStream_t)stream, false);
+  });
+}
+
+brn_status brn_forward(brn_model* m, const float* x, int32_t B, int32_t H, int32_t W, int x_is_device, float* out,
+                       int out_is_device, void* stream) {
+  return guard([&] {
+    BRN_CHECK(m, 1, "null model");
+    m->impl.forward(x, B, H, W, x_is_device != 0, out, out_is_device != 0, (cudaStream_t)stream, true);
+  });
+}
+
+brn_status brn_backbone_forward(brn_model* m, const float* x, int32_t B, int32_t H, int32_t W, int x_is_device,
+                                float* const outs[4], int out_is_device, void* stream) {
+  return guard([&] {
+    BRN_CHECK(m && x && outs, 1, "null argument");
+    m->impl.backbone_api(x, B, H, W, x_is_device != 0, outs, out_is_device != 0, (cudaStream_t)stream);
+  });
+}
+
+brn_status brn_decoder_forward(brn_model* m, const float* x, const float* x1, const float* x2, const float* x3,
+                               const float* x4, int32_t B, int32_t H, int32_t W, int is_device, float* out,
+                               void* stream) {
+  return guard([&] {
+    BRN_CHECK(m && x && x1 && x2 && x3 && x4 && out, 1, "null argument");
+    m->impl.decoder_api(x, x1, x2, x3, x4, B, H, W, is_device != 0, out, (cudaStream_t)stream);
+  });
+}
+
+int64_t brn_launch_count(const brn_model* m) { return m ? m->impl.launches : 0; }
+void brn_launch_count_reset(brn_model* m) { if (m) m->impl.launches = 0; }
+void brn_profile_enable(brn_model* m, int on) { if (m) m->impl.prof_on = on != 0; }
+int32_t brn_profile_get(const brn_model* m, const char*** names, const float** ms, const double** flops) {
+  if (!m) return 0;
+  if (names) *names = const_cast<const char**>(m->impl.prof_names.data());
+  if (ms) *ms = m->impl.prof_ms.data();
+  if (flops) *flops = m->impl.prof_flops.data();
+  return (int32_t)m->impl.prof_names.size();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// operator level: host buffers in, host buffers out; device scratch is allocated per call
+// ---------------------------------------------------------------------------------------------------------------
+struct Scratch {
+  std::vector<void*> ptrs;
+  cudaStream_t stream = nullptr;
+  explicit Scratch(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    BRN_CHECK(e == cudaSuccess && n > 0, 2, "no CUDA device available (this library has no CPU fallback)");
+    BRN_CUDA(cudaSetDevice(device));
+    BRN_CUDA(cudaStreamCreate(&stream));
+  }
+  ~Scratch() {
+    for (void* p : ptrs) cudaFree(p);
+    if (stream) cudaStreamDestroy(stream);
+  }
+  void* alloc(size_t bytes) {
+    void* p = nullptr;
+    BRN_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+    ptrs.push_back(p);
+    return p;
+  }
+  float* put(const float* h, size_t n) {
+    float* d = (float*)alloc(n * 4);
+    BRN_CUDA(cudaMemcpyAsync(d, h, n * 4, cudaMemcpyHostToDevice, stream));
+    return d;
+  }
+};
+
+static LaunchCtx make_ctx(Scratch& s, int precision) {
+  LaunchCtx c; c.stream = s.stream; c.precision = precision; c.dry = false; c.launches = nullptr;
+  const char* v = getenv("BRN_FORCE_SIMT");
+  c.force_simt = v && v[0] && v[0] != '0';
+  return c;
+}
+
+brn_status brn_linear(int device, int precision, const float* a, const float* w, const float* bias,
+                      const float* residual, int32_t M, int32_t N, int32_t K, int32_t act, float* out) {
+  return guard([&] {
+    BRN_CHECK(a && w && out && M > 0 && N > 0 && K > 0, 1, "brn_linear: bad argument");
+    Scratch s(device);
+    LaunchCtx ctx = make_ctx(s, precision);
+    const int AD = precision == BRN_PREC_BF16 ? BF16 : F32;
+    LayerW L = make_layer_standalone(N, K, 1, 1, w, bias, s.ptrs);
+    View a32 = make_view(s.put(a, (size_t)M * K), F32, 1, 1, M, K);
+    View ax = a32;
+    if (AD == BF16) { ax = make_view(s.alloc((size_t)M * K * 2), BF16, 1, 1, M, K); glue_copy_cast(ctx, a32, ax); }
+    View o = make_view(s.alloc((size_t)M * N * 4), F32, 1, 1, M, N);
+    GemmArgs g; g.x = ax; g.w = &L; g.act = act; g.out = o;
+    if (residual) g.res = make_view(s.put(residual, (size_t)M * N), F32, 1, 1, M, N);
+    op_gemm(ctx, g);
+    BRN_CUDA(cudaMemcpyAsync(out, o.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost, s.stream));
+    BRN_CUDA(cudaStreamSynchronize(s.stream));
+  });
+}
+
+brn_status brn_conv2d(int device, int precision, const float* x, const float* weight, const float* bias, int32_t B,
+                      int32_t C, int32_t H, int32_t W, int32_t O, int32_t k, int32_t act, float* out) {
+  return guard([&] {
+    BRN_CHECK(x && weight && out && B > 0 && C > 0 && H > 0 && W > 0 && O > 0 && (k & 1), 1, "brn_conv2d: bad argument");
+    Scratch s(device);
+    LaunchCtx ctx = make_ctx(s, precision);
+    const int AD = precision == BRN_PREC_BF16 ? BF16 : F32;
+    LayerW L = make_layer_standalone(O, C, k, k, weight, bias, s.ptrs);
+    float* dx = s.put(x, (size_t)B * C * H * W);
+    View xv = make_view(s.alloc((size_t)B * C * H * W * dsize(AD)), AD, B, H, W, C);
+    glue_nchw_to_nhwc(ctx, dx, B, C, H, W, xv);
+    View o = make_view(s.alloc((size_t)B * O * H * W * 4), F32, B, H, W, O);
+    GemmArgs g; g.x = xv; g.w = &L; g.pad = k / 2; g.act = act; g.out = o;
+    op_gemm(ctx, g);
+    float* on = (float*)s.alloc((size_t)B * O * H * W * 4);
+    glue_nhwc_to_nchw(ctx, o, on);
+    BRN_CUDA(cudaMemcpyAsync(out, on, (size_t)B * O * H * W * 4, cudaMemcpyDeviceToHost, s.stream));
+    BRN_CUDA(cudaStreamSynchronize(s.stream));
+  });
+}
+
+brn_status brn_deform_conv2d(int device, int precision, const float* x, const float* offset, const float* mask,
+                             const float* weight, const float* bias, int32_t B, int32_t C, int32_t H, int32_t W,
+                             int32_t O, int32_t k, float* out) {
+  return guard([&] {
+    BRN_CHECK(x && offset && mask && weight && out && (k & 1), 1, "brn_deform_conv2d: bad argument");
+    Scratch s(device);
+    LaunchCtx ctx = make_ctx(s, precision);
+    const int AD = precision == BRN_PREC_BF16 ? BF16 : F32;
+    const int taps = k * k;
+    LayerW L = make_layer_standalone(O, C, k, k, weight, bias, s.ptrs);
+    float* dx = s.put(x, (size_t)B * C * H * W);
+    View xv = make_view(s.alloc((size_t)B * C * H * W * dsize(AD)), AD, B, H, W, C);
+    glue_nchw_to_nhwc(ctx, dx, B, C, H, W, xv);
+    // offsets (2*taps channels) and modulators (taps channels) -> one NHWC fp32 tensor [.., 3*taps]
+    View om = make_view(s.alloc((size_t)B * H * W * 3 * taps * 4), F32, B, H, W, 3 * taps);
+    glue_nchw_to_nhwc(ctx, s.put(offset, (size_t)B * 2 * taps * H * W), B, 2 * taps, H, W, om.slice(0, 2 * taps));
+    glue_nchw_to_nhwc(ctx, s.put(mask, (size_t)B * taps * H * W), B, taps, H, W, om.slice(2 * taps, taps));
+    View o = make_view(s.alloc((size_t)B * O * H * W * 4), F32, B, H, W, O);
+    DeformArgs d; d.x = xv; d.om = om; d.w = &L; d.out = o;
+    op_deform(ctx, d);
+    float* on = (float*)s.alloc((size_t)B * O * H * W * 4);
+    glue_nhwc_to_nchw(ctx, o, on);
+    BRN_CUDA(cudaMemcpyAsync(out, on, (size_t)B * O * H * W * 4, cudaMemcpyDeviceToHost, s.stream));
+    BRN_CUDA(cudaStreamSynchronize(s.stream));
+  });
+}
+
+brn_status brn_window_attention(int device, int precision, const float* qkv, const float* bias, int32_t n_windows,
+                                int32_t heads, int32_t hp, int32_t wp, int32_t shift, float* out) {
+  return guard([&] {
+    BRN_CHECK(qkv && bias && out && n_windows > 0 && heads > 0, 1, "brn_window_attention: bad argument");
+    BRN_CHECK(hp % 12 == 0 && wp % 12 == 0 && (shift == 0 || shift == 6), 5, "hp, wp must be multiples of 12; shift 0|6");
+    const int nw = (hp / 12) * (wp / 12);
+    BRN_CHECK(n_windows % nw == 0, 5, "n_windows must be a multiple of (hp/12)*(wp/12)");
+    Scratch s(device);
+    LaunchCtx ctx = make_ctx(s, precision);
+    const int AD = precision == BRN_PREC_BF16 ? BF16 : F32;
+    const int C = heads * 32;
+    const size_t rows = (size_t)n_windows * 144;
+    // fold the q scale the way finalize does (src/swin.rs:278)
+    std::vector<float> hq(qkv, qkv + rows * 3 * C);
+    const float sc = 0.17677669529663687f;
+    for (size_t r = 0; r < rows; ++r)
+      for (int c = 0; c < C; ++c) hq[r * 3 * C + c] *= sc;
+    View q32 = make_view(s.put(hq.data(), hq.size()), F32, 1, 1, (int)rows, 3 * C);
+    View qx = q32;
+    if (AD == BF16) { qx = make_view(s.alloc(rows * 3 * C * 2), BF16, 1, 1, (int)rows, 3 * C); glue_copy_cast(ctx, q32, qx); }
+    float* b32 = s.put(bias, (size_t)heads * 144 * 144);
+    // bf16 padded copy [heads][144][152]
+    std::vector<float> padded((size_t)heads * 144 * 152, 0.f);
+    for (size_t r = 0; r < (size_t)heads * 144; ++r) memcpy(&padded[r * 152], &bias[r * 144], 144 * 4);
+    View p32 = make_view(s.put(padded.data(), padded.size()), F32, 1, 1, heads * 144, 152);
+    View p16 = make_view(s.alloc(padded.size() * 2), BF16, 1, 1, heads * 144, 152);
+    glue_copy_cast(ctx, p32, p16);
+    View o = make_view(s.alloc(rows * C * dsize(AD)), AD, 1, 1, (int)rows, C);
+    AttnArgs a; a.qkv = qx; a.bias32 = b32; a.bias16 = (const __nv_bfloat16*)p16.p; a.n_windows = n_windows;
+    a.heads = heads; a.nwh = hp / 12; a.nww = wp / 12; a.shift = shift; a.out = o;
+    op_attention(ctx, a);
+    View o32 = o;
+    if (AD == BF16) { o32 = make_view(s.alloc(rows * C * 4), F32, 1, 1, (int)rows, C); glue_copy_cast(ctx, o, o32); }
+    BRN_CUDA(cudaMemcpyAsync(out, o32.p, rows * C * 4, cudaMemcpyDeviceToHost, s.stream));
+    BRN_CUDA(cudaStreamSynchronize(s.stream));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// Shared host-side declarations for libbirefnet_b200 (private; the public ABI is include/birefnet_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+
+namespace brn {
+
+struct Error : std::runtime_error {
+  int status;
+  Error(int s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+
+#define BRN_CUDA(call)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      throw ::brn::Error(2, std::string(#call) + " failed: " + cudaGetErrorString(e__) + " at " +   \
+                                __FILE__ + ":" + std::to_string(__LINE__));                         \
+  } while (0)
+
+#define BRN_CHECK(cond, status, msg)                        \
+  do {                                                      \
+    if (!(cond)) throw ::brn::Error((status), (msg));       \
+  } while (0)
+
+enum DType { F32 = 0, BF16 = 1 };
+inline size_t dsize(int dt) { return dt == F32 ? 4 : 2; }
+
+// NHWC activation view.  Element (b,y,x,c) lives at p + (((b*H+y)*W+x)*ld + c) elements.  Token matrices
+// [rows, C] are views with B=1,H=1,W=rows.  `ld` >= C lets a producer write into a channel slice of a wider
+// (concatenated) buffer, which is how every Tensor::cat of the reference disappears.
+struct View {
+  void* p = nullptr;
+  int dt = F32;
+  int B = 1, H = 1, W = 1, C = 0;
+  int ld = 0;
+  long long rows() const { return (long long)B * H * W; }
+  View slice(int c0, int c) const {
+    View v = *this;
+    v.p = (char*)p + (size_t)c0 * dsize(dt);
+    v.C = c;
+    return v;
+  }
+};
+
+inline View make_view(void* p, int dt, int B, int H, int W, int C, int ld = 0) {
+  View v;
+  v.p = p; v.dt = dt; v.B = B; v.H = H; v.W = W; v.C = C; v.ld = ld ? ld : C;
+  return v;
+}
+
+// Weights of one conv / linear layer after finalize (BN folded, tap-major K order).
+struct LayerW {
+  int N = 0;        // output channels
+  int Cin = 0;      // input channels
+  int kh = 1, kw = 1;
+  int cin_pad = 0;  // Cin rounded up to 64 (K pitch per tap of the bf16 matrix)
+  float* w32 = nullptr;          // [N][kh*kw][Cin]      fp32 (SIMT path)
+  __nv_bfloat16* w16 = nullptr;  // [N][kh*kw][cin_pad]  bf16, zero padded (tcgen05 path)
+  float* bias = nullptr;         // [N] fp32 or null
+  int taps() const { return kh * kw; }
+};
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_2SIGMOID_TAIL = 3 };
+
+// window-reverse row map of the proj GEMM epilogue (src/swin.rs:387-401): window-ordered padded row -> token row
+struct RowMap {
+  int enabled = 0;
+  int h = 0, w = 0, hp = 0, wp = 0, shift = 0;
+};
+
+// One implicit-GEMM problem: out[m, n] = act(sum_k A[m,k] W[n,k] + bias) (+ res[m,n]).
+// A is the conv patch matrix of `x` (NHWC, stride 1, zero padding `pad`), K order (tap, channel).
+struct GemmArgs {
+  View x;                 // input activation
+  const LayerW* w = nullptr;
+  int pad = 0;
+  const float* bias = nullptr;   // overrides w->bias when non-null
+  int bias_bstride = 0;          // >0: bias is [B][N] (per-image bias; ASPP global-pool branch)
+  int act = ACT_NONE;
+  int act_from = 0;              // ACT_2SIGMOID_TAIL: columns >= act_from get 2*sigmoid (modulator, src/aspp.rs:174)
+  View res;                      // optional residual (res.p == nullptr: none); indexed like out
+  View out;                      // output view (dtype decides conversion)
+  RowMap rowmap;                 // optional output row scatter
+  double flops = 0;
+};
+
+struct DeformArgs {
+  View x;                 // [B,H,W,C] input
+  View om;                // [B,H,W,3*taps] fp32: 2*taps offsets (dy,dx interleaved) then taps modulators
+  const LayerW* w = nullptr;
+  const float* bias = nullptr;
+  int act = ACT_NONE;
+  View out;
+};
+
+struct AttnArgs {
+  View qkv;               // [rows = nWin*144, 3C], window order, q pre-scaled
+  const float* bias32 = nullptr;          // [heads][144][144] fp32
+  const __nv_bfloat16* bias16 = nullptr;  // [heads][144][152] bf16 (row padded to 304 B)
+  int n_windows = 0;      // total windows (B * nW)
+  int heads = 0;
+  int nwh = 0, nww = 0;   // windows per image along h / w
+  int shift = 0;          // 0: no mask at all (src/swin.rs:383)
+  View out;               // [rows, C]
+};
+
+struct LaunchCtx {
+  cudaStream_t stream = nullptr;
+  int precision = 0;
+  bool dry = false;        // plan pass: no launches
+  long long* launches = nullptr;
+  bool force_simt = false;
+};
+
+// ---- SIMT (fp32 FMA) kernels: kernels_simt.cu ----
+void simt_gemm(const LaunchCtx&, const GemmArgs&);
+void simt_deform(const LaunchCtx&, const DeformArgs&);
+void simt_attention(const LaunchCtx&, const AttnArgs&);
+
+// ---- tcgen05 kernels ----
+bool tc_gemm_supported(const GemmArgs&);
+void tc_gemm(const LaunchCtx&, const GemmArgs&);
+void tc_attention(const LaunchCtx&, const AttnArgs&);
+bool tc_deform_supported(const DeformArgs&);
+void tc_deform(const LaunchCtx&, const DeformArgs&);
+
+// ---- HBM-bound glue kernels: kernels_glue.cu ----
+enum LnMode { LN_PLAIN = 0, LN_WINDOW = 1, LN_MERGE = 2 };
+struct LnArgs {
+  View x;                  // source rows [B,h,w,C] (fp32 stream) -- for LN_MERGE the pre-merge grid
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  View out;                // destination rows
+  int mode = LN_PLAIN;
+  int hp = 0, wp = 0, shift = 0;  // LN_WINDOW
+};
+void glue_layernorm(const LaunchCtx&, const LnArgs&);
+void glue_patch_im2col(const LaunchCtx&, const float* x_nchw, int B, int H, int W, int patch, View out);
+void glue_resize_nchw(const LaunchCtx&, const float* x, int B, int C, int H, int W, float* out, int Ho, int Wo);
+void glue_resize_nhwc(const LaunchCtx&, View in, View out);                      // bilinear, align_corners=true
+void glue_image2patches(const LaunchCtx&, const float* x_nchw, int B, int H, int W, int th, int tw, View out);
+void glue_nchw_to_nhwc(const LaunchCtx&, const float* x, int B, int C, int H, int W, View out);
+void glue_nhwc_to_nchw(const LaunchCtx&, View in, float* out);
+void glue_gap_sum(const LaunchCtx&, View x, float* sums /*[B][C], zeroed here*/);
+void glue_aspp_pool_bias(const LaunchCtx&, const float* sums, int B, int HW, const LayerW* gap_conv,
+                         const float* conv1_tail /*[64][256] fp32, bn1-scaled*/, const float* bn1_shift /*[64]*/,
+                         float* out /*[B][64]*/);
+void glue_gate(const LaunchCtx&, View p, View g16, const float* w16, float b0);
+void glue_dot1(const LaunchCtx&, View p, const float* w, float* out /*[rows]*/);
+void glue_final(const LaunchCtx&, const float* x_nchw, int B, int H, int W, const float* w1 /*[64][27]*/,
+                const float* b1 /*[64]*/, const float* wc /*[64][9]*/, float bc, const float* q, int qh, int qw,
+                float* out, int apply_sigmoid);
+void glue_copy_cast(const LaunchCtx&, View in, View out);
+void glue_sigmoid(const LaunchCtx&, float* p, long long n);
+
+}  // namespace brn

@@ -1,0 +1,43 @@
+// Small device helpers shared by every kernel file.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include "brn_common.h"
+
+namespace brn {
+
+// Window-ordered padded row m (batch-major, window id, token ti*12+tj; src/swin.rs:446-459) -> token row of the
+// un-shifted, un-padded [B,h,w] grid, or -1 for a pad position.  Inverse of pad -> roll(-shift) -> partition
+// (src/swin.rs:359-380) == window_reverse -> roll(+shift) -> crop (src/swin.rs:387-401).
+__host__ __device__ __forceinline__ long long window_row_to_token(long long m, int h, int w, int hp, int wp,
+                                                                  int shift) {
+  const int nww = wp / 12;
+  const int nw = (hp / 12) * nww;
+  const long long b = m / ((long long)nw * 144);
+  const int rem = (int)(m - b * (long long)nw * 144);
+  const int wid = rem / 144, t = rem - wid * 144;
+  const int wi = wid / nww, wj = wid - wi * nww;
+  const int ti = t / 12, tj = t - ti * 12;
+  int r = wi * 12 + ti + shift, c = wj * 12 + tj + shift;
+  if (r >= hp) r -= hp;
+  if (c >= wp) c -= wp;
+  if (r >= h || c >= w) return -1;
+  return (b * h + r) * (long long)w + c;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float apply_act(float v, int act, int n, int act_from) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_GELU) return gelu_erf(v);
+  if (act == ACT_2SIGMOID_TAIL) return n >= act_from ? 2.f / (1.f + expf(-v)) : v;
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace brn

@@ -1,0 +1,353 @@
+// tcgen05 implicit-GEMM kernel (sm_100a): every linear layer and every stride-1 convolution of the model.
+//
+//   out[m, n] = act( sum_{tap, c} X[pixel(m) + tap, c] * W[n, tap, c] + bias ) (+ residual)
+//
+// * A operand: NHWC bf16 activations through a 4-D TMA tensor map {C, W, H, B}; one M tile is a TH x TW pixel
+//   patch (TH*TW = 128) of one image, so a conv tap is just a shifted box and TMA's out-of-bounds zero fill is the
+//   conv's zero padding (and the channel tail when C % 64 != 0).  Linear layers are the 1-tap case on {K, rows,1,1}.
+// * B operand: weights [N][taps][cin_pad] bf16 (K-major) through a 2-D map, box {64, BN}.
+// * 128B-swizzled K-major smem tiles, 4-stage mbarrier ring, warp-specialised: warp 0 = TMA producer,
+//   warp 1 = MMA issuer (one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128, N=BN<=256, K=16),
+//   warps 2-5 = epilogue (tcgen05.ld 32x32b, bias / ReLU / erf-GELU / 2*sigmoid / residual / window-reverse row
+//   scatter, bf16 or fp32 stores).  Two TMEM accumulator stages (2 x 256 columns) overlap the epilogue of tile i
+//   with the MMAs of tile i+1; the kernel is persistent (grid = min(tiles, #SM)).
+// Roofline: tensor pipe (2*M*N*K flop per launch) for K >= 384, HBM (A read + out write) below that.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "brn_common.h"
+#include "device_utils.cuh"
+#include "tc_ptx.cuh"
+
+namespace brn {
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4, TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+constexpr int TC_B_BYTES = 256 * TC_BK * 2;     // 32 KB (BN <= 256)
+constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 256 + 1024;
+
+struct TcGemmP {
+  int B, H, W;
+  int tw_log2, tiles_x, tiles_y;
+  int m_tiles, n_tiles, BN;
+  int taps, kw, pad, cblocks, cin_pad;
+  int N;
+  const float* bias; int bias_bstride;
+  int act, act_from;
+  const void* res; int resdt; int ldres; int vec_res;
+  void* out; int odt; int ldo; int vec_out;
+  RowMap rm;
+};
+
+// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 2 MUFU + ~10 FMA instead of erff's ~40 instructions.  The
+// epilogue evaluates ~0.5 G GELUs per 1024^2 image, so this is what keeps fc1 MMA-paced rather than epilogue-paced.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  const float erf_abs = 1.f - poly * __expf(-z * z);
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + TC_STAGES * TC_A_BYTES;
+  uint64_t* full = (uint64_t*)(sB + TC_STAGES * TC_B_BYTES);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* tfull = empty + TC_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int kblocks = p.taps * p.cblocks;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int TW = 1 << p.tw_log2, TH = TC_BM >> p.tw_log2;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      // ===== TMA producer =====
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_bytes = TC_A_BYTES + p.BN * TC_BK * 2;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const int b = m_tile / tiles_per_img, r = m_tile - b * tiles_per_img;
+        const int y0 = (r / p.tiles_x) * TH, x0 = (r % p.tiles_x) * TW;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full[stage], tx_bytes);
+          const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+          ptx::tma_load_4d(sA + stage * TC_A_BYTES, &tmA, &full[stage], cb * TC_BK, x0 + kx - p.pad, y0 + ky - p.pad, b);
+          ptx::tma_load_2d(sB + stage * TC_B_BYTES, &tmB, &full[stage], tap * p.cin_pad + cb * TC_BK, n_tile * p.BN);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = ptx::make_idesc_bf16(TC_BM, p.BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ptx::make_smem_desc(ptx::smem_u32(sA + stage * TC_A_BYTES), 16, 1024, ptx::SW_128B);
+          const uint64_t b_desc = ptx::make_smem_desc(ptx::smem_u32(sB + stage * TC_B_BYTES), 16, 1024, ptx::SW_128B);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)   // +32 B (= 2 in the >>4 address field) per K=16 step inside the 128B atom
+            ptx::umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          ptx::umma_commit(&empty[stage]);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull[acc]);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue: 4 warps, warp%4 selects the TMEM lane quadrant =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int esz = p.odt == F32 ? 4 : 2;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int b = m_tile / tiles_per_img, r = m_tile - b * tiles_per_img;
+      const int y = (r / p.tiles_x) * TH + (row >> p.tw_log2), x = (r % p.tiles_x) * TW + (row & (TW - 1));
+      bool valid = y < p.H && x < p.W;
+      long long orow = ((long long)b * p.H + y) * p.W + x;
+      if (valid && p.rm.enabled) {
+        orow = window_row_to_token(orow, p.rm.h, p.rm.w, p.rm.hp, p.rm.wp, p.rm.shift);
+        valid = orow >= 0;
+      }
+      const int n0 = n_tile * p.BN;
+      const float* bias = p.bias ? p.bias + (long long)b * p.bias_bstride : nullptr;
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
+      for (int c = 0; c < p.BN / 16; ++c) {
+        const int nb = n0 + c * 16;
+        if (nb >= p.N) break;
+        uint32_t v[16];
+        ptx::tmem_ld16(taddr + c * 16, v);
+        ptx::tmem_ld_wait();
+        if (!valid) continue;
+        const bool full16 = nb + 16 <= p.N;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (bias) {
+          if (full16) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 bv = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
+              f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (nb + j < p.N) f[j] += __ldg(bias + nb + j);
+          }
+        }
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = gelu_fast(f[j]);
+        } else if (p.act == ACT_2SIGMOID_TAIL) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (nb + j >= p.act_from) f[j] = 2.f / (1.f + __expf(-f[j]));
+        }
+        if (p.res) {
+          if (p.vec_res && full16) {
+            if (p.resdt == F32) {
+              const float4* rp = reinterpret_cast<const float4*>((const float*)p.res + orow * p.ldres + nb);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { float4 rv = rp[j]; f[4 * j] += rv.x; f[4 * j + 1] += rv.y; f[4 * j + 2] += rv.z; f[4 * j + 3] += rv.w; }
+            } else {
+              const uint4* rp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)p.res + orow * p.ldres + nb);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                uint4 rv = rp[j];
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { float2 ff = __bfloat1622float2(h[t]); f[8 * j + 2 * t] += ff.x; f[8 * j + 2 * t + 1] += ff.y; }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nb + j < p.N)
+                f[j] += p.resdt == F32 ? ((const float*)p.res)[orow * p.ldres + nb + j]
+                                       : __bfloat162float(((const __nv_bfloat16*)p.res)[orow * p.ldres + nb + j]);
+          }
+        }
+        char* op = (char*)p.out + (orow * p.ldo + nb) * esz;
+        if (p.vec_out && full16) {
+          if (p.odt == F32) {
+            float4* o4 = reinterpret_cast<float4*>(op);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                 pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.N) {
+              if (p.odt == F32) ((float*)op)[j] = f[j]; else ((__nv_bfloat16*)op)[j] = __float2bfloat16(f[j]);
+            }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty[acc]);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)f;
+  });
+  BRN_CHECK(fn != nullptr, 2, "cuTensorMapEncodeTiled is not available from the driver");
+  return fn;
+}
+
+// rank-`rank` bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides[0] is implicit.
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, CUtensorMapSwizzle swz) {
+  CUtensorMap m;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BRN_CHECK(r == CUDA_SUCCESS, 2, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return m;
+}
+
+int device_sm_count() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+  return n;
+}
+
+bool tc_gemm_supported(const GemmArgs& a) {
+  if (!a.w || !a.w->w16) return false;
+  if (a.x.dt != BF16) return false;
+  if (a.x.C % 8 != 0 || a.x.ld % 8 != 0 || ((uintptr_t)a.x.p & 15)) return false;
+  if (a.rowmap.enabled && !(a.x.B == 1 && a.x.H == 1)) return false;
+  if (a.bias_bstride && a.x.H * a.x.W < 1) return false;
+  return true;
+}
+
+static int pick_bn(int N) {
+  if (N <= 256) return (N + 15) / 16 * 16;
+  int best = 256, best_pad = (N + 255) / 256 * 256;
+  const int cands[2] = {192, 128};
+  for (int c : cands) {
+    int padded = (N + c - 1) / c * c;
+    if (padded < best_pad) { best = c; best_pad = padded; }
+  }
+  return best;
+}
+
+void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
+  if (ctx.launches) ++*ctx.launches;
+  if (ctx.dry) return;
+  const LayerW& w = *a.w;
+  BRN_CHECK(w.Cin == a.x.C, 5, "tc_gemm: weight/input channel mismatch");
+  TcGemmP p{};
+  p.B = a.x.B; p.H = a.x.H; p.W = a.x.W;
+  int tw = 1, lg = 0;
+  while (tw < std::min(a.x.W, TC_BM)) { tw <<= 1; ++lg; }
+  p.tw_log2 = lg;
+  const int TH = TC_BM / tw;
+  p.tiles_x = (a.x.W + tw - 1) / tw;
+  p.tiles_y = (a.x.H + TH - 1) / TH;
+  p.m_tiles = a.x.B * p.tiles_x * p.tiles_y;
+  p.BN = pick_bn(w.N);
+  p.n_tiles = (w.N + p.BN - 1) / p.BN;
+  p.taps = w.taps(); p.kw = w.kw; p.pad = a.pad; p.cin_pad = w.cin_pad; p.cblocks = w.cin_pad / TC_BK;
+  p.N = w.N;
+  p.bias = a.bias ? a.bias : w.bias; p.bias_bstride = a.bias_bstride;
+  p.act = a.act; p.act_from = a.act_from;
+  p.res = a.res.p; p.resdt = a.res.dt; p.ldres = a.res.ld;
+  p.vec_res = a.res.p && (((uintptr_t)a.res.p & 15) == 0) && ((a.res.ld * dsize(a.res.dt)) % 16 == 0);
+  p.out = a.out.p; p.odt = a.out.dt; p.ldo = a.out.ld;
+  p.vec_out = (((uintptr_t)a.out.p & 15) == 0) && ((a.out.ld * dsize(a.out.dt)) % 16 == 0);
+  p.rm = a.rowmap;
+
+  const uint64_t ld2 = (uint64_t)a.x.ld * 2;
+  uint64_t adims[4] = {(uint64_t)a.x.C, (uint64_t)a.x.W, (uint64_t)a.x.H, (uint64_t)a.x.B};
+  uint64_t astr[3] = {ld2, ld2 * a.x.W, ld2 * a.x.W * a.x.H};
+  uint32_t abox[4] = {(uint32_t)TC_BK, (uint32_t)tw, (uint32_t)TH, 1};
+  CUtensorMap tmA = make_tmap_bf16(a.x.p, 4, adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_128B);
+  const uint64_t ktot = (uint64_t)w.taps() * w.cin_pad;
+  uint64_t bdims[2] = {ktot, (uint64_t)w.N};
+  uint64_t bstr[1] = {ktot * 2};
+  uint32_t bbox[2] = {(uint32_t)TC_BK, (uint32_t)p.BN};
+  CUtensorMap tmB = make_tmap_bf16(w.w16, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B);
+
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  });
+  const int grid = std::min(p.m_tiles * p.n_tiles, device_sm_count());
+  tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM, ctx.stream>>>(tmA, tmB, p);
+  BRN_CUDA(cudaGetLastError());
+}
+
+}  // namespace brn

@@ -1,0 +1,431 @@
+// HBM-bound glue kernels: LayerNorm (+ window gather / patch-merge gather), bilinear resampling, image2patches,
+// global average pool, GDT gate, the fused final layer.  All are bandwidth-bound; threads map to the contiguous
+// (channel) dimension of NHWC so every warp access is a run of consecutive addresses.
+#include "brn_common.h"
+#include "device_utils.cuh"
+
+namespace brn {
+
+__device__ __forceinline__ float g_ld(const void* p, int dt, long long i) {
+  return dt == F32 ? ((const float*)p)[i] : __bfloat162float(((const __nv_bfloat16*)p)[i]);
+}
+__device__ __forceinline__ void g_st(void* p, int dt, long long i, float v) {
+  if (dt == F32) ((float*)p)[i] = v; else ((__nv_bfloat16*)p)[i] = __float2bfloat16(v);
+}
+
+#define GLUE_LAUNCH_PROLOGUE(ctx)        \
+  if ((ctx).launches) ++*(ctx).launches; \
+  if ((ctx).dry) return;
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm, one warp per destination row (candle_nn::layer_norm, eps 1e-5, biased variance).
+//  LN_PLAIN : row m <- row m                                     (norm2, patch_embed.norm, norm{i})
+//  LN_WINDOW: window-ordered padded row m <- token row, zeros for pad rows (norm1 -> pad -> roll -> partition,
+//             src/swin.rs:355-380; pad rows are zeros AFTER the norm)
+//  LN_MERGE : row (b,i,j) <- [x(2i,2j) | x(2i+1,2j) | x(2i,2j+1) | x(2i+1,2j+1)], LN over 4C (src/swin.rs:505-525)
+// ------------------------------------------------------------------------------------------------
+struct LnP {
+  const void* x; int xdt; int ldx; int B, h, w, C;
+  const float* gamma; const float* beta;
+  void* out; int odt; int ldo;
+  int mode, hp, wp, shift;
+  long long rows;
+};
+
+__global__ void __launch_bounds__(256) ln_kernel(LnP p) {
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= p.rows) return;
+  const int n = p.mode == LN_MERGE ? 4 * p.C : p.C;
+  long long src[4] = {-1, -1, -1, -1};
+  if (p.mode == LN_PLAIN) {
+    src[0] = m * p.ldx;
+  } else if (p.mode == LN_WINDOW) {
+    long long tok = window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift);
+    if (tok < 0) {
+      for (int e = lane; e < n; e += 32) g_st(p.out, p.odt, m * p.ldo + e, 0.f);
+      return;
+    }
+    src[0] = tok * p.ldx;
+  } else {
+    const int h2 = (p.h + 1) / 2, w2 = (p.w + 1) / 2;
+    long long b = m / ((long long)h2 * w2);
+    int r = (int)(m - b * (long long)h2 * w2);
+    int i = r / w2, j = r - i * w2;
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+      int y = 2 * i + (part & 1), xx = 2 * j + (part >> 1);
+      if (y < p.h && xx < p.w) src[part] = ((b * p.h + y) * (long long)p.w + xx) * p.ldx;
+    }
+  }
+  auto load = [&](int e) -> float {
+    if (p.mode == LN_MERGE) {
+      int part = e / p.C, c = e - part * p.C;
+      return src[part] < 0 ? 0.f : g_ld(p.x, p.xdt, src[part] + c);
+    }
+    return g_ld(p.x, p.xdt, src[0] + e);
+  };
+  float s = 0.f;
+  for (int e = lane; e < n; e += 32) s += load(e);
+  const float mean = warp_sum(s) / n;
+  float v = 0.f;
+  for (int e = lane; e < n; e += 32) { float d = load(e) - mean; v += d * d; }
+  const float rstd = rsqrtf(warp_sum(v) / n + 1e-5f);
+  for (int e = lane; e < n; e += 32)
+    g_st(p.out, p.odt, m * p.ldo + e, (load(e) - mean) * rstd * p.gamma[e] + p.beta[e]);
+}
+
+void glue_layernorm(const LaunchCtx& ctx, const LnArgs& a) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  LnP p{};
+  p.x = a.x.p; p.xdt = a.x.dt; p.ldx = a.x.ld; p.B = a.x.B; p.h = a.x.H; p.w = a.x.W; p.C = a.x.C;
+  p.gamma = a.gamma; p.beta = a.beta;
+  p.out = a.out.p; p.odt = a.out.dt; p.ldo = a.out.ld;
+  p.mode = a.mode; p.hp = a.hp; p.wp = a.wp; p.shift = a.shift;
+  p.rows = a.out.rows();
+  ln_kernel<<<(unsigned)((p.rows + 7) / 8), 256, 0, ctx.stream>>>(p);
+  BRN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// PatchEmbed im2col (src/swin.rs:692-704): row (b,py,px), k = c*P*P + ky*P + kx  <-  x[b,c,py*P+ky,px*P+kx]
+// ------------------------------------------------------------------------------------------------
+__global__ void patch_im2col_kernel(const float* x, int B, int H, int W, int P, void* out, int odt, int ldo,
+                                    long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int K = 3 * P * P;
+  long long row = i / K; int k = (int)(i - row * K);
+  int c = k / (P * P), r = k - c * P * P, ky = r / P, kx = r - ky * P;
+  int Wp = W / P, Hp = H / P;
+  long long b = row / ((long long)Hp * Wp); int rr = (int)(row - b * (long long)Hp * Wp);
+  int py = rr / Wp, px = rr - py * Wp;
+  float v = x[((b * 3 + c) * H + (py * P + ky)) * (long long)W + px * P + kx];
+  g_st(out, odt, row * ldo + k, v);
+}
+
+void glue_patch_im2col(const LaunchCtx& ctx, const float* x, int B, int H, int W, int P, View out) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  long long total = (long long)B * (H / P) * (W / P) * 3 * P * P;
+  patch_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(x, B, H, W, P, out.p, out.dt, out.ld,
+                                                                              total);
+  BRN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bilinear resample, align_corners = true (Tensor::upsample_bilinear2d(h,w,true), src/birefnet.rs x16; also used
+// to down-sample, point-sampled, no antialias).  src = dst * (in-1)/(out-1).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilin_coord(int dst, int in, int out, int& i0, int& i1, float& l) {
+  float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  float s = scale * dst;
+  i0 = min((int)s, in - 1);
+  i1 = min(i0 + 1, in - 1);
+  l = s - (float)i0;
+}
+
+__global__ void resize_nchw_kernel(const float* x, int C, int H, int W, float* out, int Ho, int Wo, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int ox = (int)(i % Wo); long long t = i / Wo; int oy = (int)(t % Ho); long long bc = t / Ho;
+  int y0, y1, x0, x1; float ly, lx;
+  bilin_coord(oy, H, Ho, y0, y1, ly);
+  bilin_coord(ox, W, Wo, x0, x1, lx);
+  const float* s = x + bc * (long long)H * W;
+  float v = (1.f - ly) * ((1.f - lx) * s[(long long)y0 * W + x0] + lx * s[(long long)y0 * W + x1]) +
+            ly * ((1.f - lx) * s[(long long)y1 * W + x0] + lx * s[(long long)y1 * W + x1]);
+  out[i] = v;
+}
+
+void glue_resize_nchw(const LaunchCtx& ctx, const float* x, int B, int C, int H, int W, float* out, int Ho, int Wo) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  long long total = (long long)B * C * Ho * Wo;
+  resize_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(x, C, H, W, out, Ho, Wo, total);
+  BRN_CUDA(cudaGetLastError());
+}
+
+struct ResizeP {
+  const void* x; int xdt; int ldx; int H, W, C;
+  void* out; int odt; int ldo; int Ho, Wo;
+  long long total;
+};
+
+__global__ void resize_nhwc_kernel(ResizeP p) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.total) return;
+  int c = (int)(i % p.C); long long t = i / p.C;
+  int ox = (int)(t % p.Wo); t /= p.Wo; int oy = (int)(t % p.Ho); long long b = t / p.Ho;
+  int y0, y1, x0, x1; float ly, lx;
+  bilin_coord(oy, p.H, p.Ho, y0, y1, ly);
+  bilin_coord(ox, p.W, p.Wo, x0, x1, lx);
+  long long base = b * p.H * p.W;
+  float v00 = g_ld(p.x, p.xdt, (base + (long long)y0 * p.W + x0) * p.ldx + c);
+  float v01 = g_ld(p.x, p.xdt, (base + (long long)y0 * p.W + x1) * p.ldx + c);
+  float v10 = g_ld(p.x, p.xdt, (base + (long long)y1 * p.W + x0) * p.ldx + c);
+  float v11 = g_ld(p.x, p.xdt, (base + (long long)y1 * p.W + x1) * p.ldx + c);
+  float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  g_st(p.out, p.odt, ((b * p.Ho + oy) * (long long)p.Wo + ox) * p.ldo + c, v);
+}
+
+void glue_resize_nhwc(const LaunchCtx& ctx, View in, View out) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  ResizeP p{in.p, in.dt, in.ld, in.H, in.W, in.C, out.p, out.dt, out.ld, out.H, out.W, 0};
+  p.total = (long long)in.B * out.H * out.W * in.C;
+  resize_nhwc_kernel<<<(unsigned)((p.total + 255) / 256), 256, 0, ctx.stream>>>(p);
+  BRN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// image2patches (src/birefnet.rs:288-300): out[b,ty,tx, c*gh*gw + gy*gw + gx] = x[b,c,gy*th+ty,gx*tw+tx]
+// ------------------------------------------------------------------------------------------------
+__global__ void image2patches_kernel(const float* x, int H, int W, int th, int tw, void* out, int odt, int ldo,
+                                     long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int gh = H / th, gw = W / tw, Cn = 3 * gh * gw;
+  int ch = (int)(i % Cn); long long t = i / Cn;
+  int tx = (int)(t % tw); t /= tw; int ty = (int)(t % th); long long b = t / th;
+  int c = ch / (gh * gw), r = ch - c * gh * gw, gy = r / gw, gx = r - gy * gw;
+  float v = x[((b * 3 + c) * H + (gy * th + ty)) * (long long)W + gx * tw + tx];
+  g_st(out, odt, ((b * th + ty) * (long long)tw + tx) * ldo + ch, v);
+}
+
+void glue_image2patches(const LaunchCtx& ctx, const float* x, int B, int H, int W, int th, int tw, View out) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  long long total = (long long)B * 3 * H * W;
+  image2patches_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(x, H, W, th, tw, out.p, out.dt,
+                                                                               out.ld, total);
+  BRN_CUDA(cudaGetLastError());
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* x, int C, int H, int W, void* out, int odt, int ldo, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C); long long t = i / C;
+  int xx = (int)(t % W); t /= W; int y = (int)(t % H); long long b = t / H;
+  g_st(out, odt, ((b * H + y) * (long long)W + xx) * ldo + c, x[((b * C + c) * H + y) * (long long)W + xx]);
+}
+void glue_nchw_to_nhwc(const LaunchCtx& ctx, const float* x, int B, int C, int H, int W, View out) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  long long total = (long long)B * C * H * W;
+  nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(x, C, H, W, out.p, out.dt, out.ld, total);
+  BRN_CUDA(cudaGetLastError());
+}
+
+__global__ void nhwc_to_nchw_kernel(const void* x, int xdt, int ldx, int C, int H, int W, float* out, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int xx = (int)(i % W); long long t = i / W;
+  int y = (int)(t % H); t /= H; int c = (int)(t % C); long long b = t / C;
+  out[i] = g_ld(x, xdt, ((b * H + y) * (long long)W + xx) * ldx + c);
+}
+void glue_nhwc_to_nchw(const LaunchCtx& ctx, View in, float* out) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  long long total = (long long)in.B * in.C * in.H * in.W;
+  nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(in.p, in.dt, in.ld, in.C, in.H, in.W,
+                                                                              out, total);
+  BRN_CUDA(cudaGetLastError());
+}
+
+__global__ void copy_cast_kernel(const void* x, int xdt, int ldx, void* out, int odt, int ldo, int C, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long row = i / C; int c = (int)(i - row * C);
+  g_st(out, odt, row * ldo + c, g_ld(x, xdt, row * ldx + c));
+}
+void glue_copy_cast(const LaunchCtx& ctx, View in, View out) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  long long total = in.rows() * in.C;
+  copy_cast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(in.p, in.dt, in.ld, out.p, out.dt, out.ld,
+                                                                           in.C, total);
+  BRN_CUDA(cudaGetLastError());
+}
+
+__global__ void sigmoid_kernel(float* p, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 1.f / (1.f + expf(-p[i]));
+}
+void glue_sigmoid(const LaunchCtx& ctx, float* p, long long n) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  sigmoid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx.stream>>>(p, n);
+  BRN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Global average pool partial sums (src/aspp.rs:314) and the pooled branch folded to a per-image bias of conv1:
+//   x5 = relu(bn(conv1x1(mean)))  (src/aspp.rs:315-317), broadcast over H,W (:318), then its 256 channels times
+//   conv1.weight[:, 1024:1280] (:327-329) is a constant 64-vector per image.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gap_sum_kernel(const void* x, int xdt, int ldx, int C, int HW, int chunk,
+                                                      float* sums) {
+  __shared__ float part[256];
+  const int b = blockIdx.y;
+  const int lanes = 256 / C;   // pixel lanes (C divides 256: C = 64)
+  const int c = threadIdx.x % C, pl = threadIdx.x / C;
+  const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, HW);
+  float s = 0.f;
+  if (pl < lanes)
+    for (int px = p0 + pl; px < p1; px += lanes) s += g_ld(x, xdt, ((long long)b * HW + px) * ldx + c);
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += part[l * C + threadIdx.x];
+    atomicAdd(&sums[b * C + threadIdx.x], t);
+  }
+}
+
+void glue_gap_sum(const LaunchCtx& ctx, View x, float* sums) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  BRN_CHECK(x.C <= 256 && 256 % x.C == 0, 5, "gap_sum: C must divide 256");
+  BRN_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * x.B * x.C, ctx.stream));
+  const int HW = x.H * x.W, chunk = 1024;
+  dim3 grid((HW + chunk - 1) / chunk, x.B);
+  gap_sum_kernel<<<grid, 256, 0, ctx.stream>>>(x.p, x.dt, x.ld, x.C, HW, chunk, sums);
+  BRN_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) aspp_pool_bias_kernel(const float* sums, int HW, const float* wg /*[256][64]*/,
+                                                             const float* bg /*[256]*/, const float* tail /*[64][256]*/,
+                                                             const float* shift /*[64]*/, float* out) {
+  __shared__ float mean[64];
+  __shared__ float x5[256];
+  const int b = blockIdx.x, t = threadIdx.x;
+  if (t < 64) mean[t] = sums[b * 64 + t] / (float)HW;
+  __syncthreads();
+  float s = bg[t];
+  for (int c = 0; c < 64; ++c) s = fmaf(wg[t * 64 + c], mean[c], s);
+  x5[t] = fmaxf(s, 0.f);
+  __syncthreads();
+  if (t < 64) {
+    float o = shift[t];
+    for (int j = 0; j < 256; ++j) o = fmaf(tail[t * 256 + j], x5[j], o);
+    out[b * 64 + t] = o;
+  }
+}
+
+void glue_aspp_pool_bias(const LaunchCtx& ctx, const float* sums, int B, int HW, const LayerW* gap_conv,
+                         const float* conv1_tail, const float* bn1_shift, float* out) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  aspp_pool_bias_kernel<<<B, 256, 0, ctx.stream>>>(sums, HW, gap_conv->w32, gap_conv->bias, conv1_tail, bn1_shift, out);
+  BRN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// GDT gate (src/birefnet.rs:327-329): p *= sigmoid(conv1x1_{16->1}(g) + b)
+// ------------------------------------------------------------------------------------------------
+__global__ void gate_kernel(void* p, int pdt, int ldp, int C, const void* g, int gdt, int ldg, const float* w, float b0,
+                            long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long row = i / C; int c = (int)(i - row * C);
+  float s = b0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s = fmaf(w[j], g_ld(g, gdt, row * ldg + j), s);
+  float gate = 1.f / (1.f + expf(-s));
+  g_st(p, pdt, row * ldp + c, g_ld(p, pdt, row * ldp + c) * gate);
+}
+void glue_gate(const LaunchCtx& ctx, View p, View g16, const float* w16, float b0) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  long long total = p.rows() * p.C;
+  gate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(p.p, p.dt, p.ld, p.C, g16.p, g16.dt, g16.ld, w16,
+                                                                      b0, total);
+  BRN_CUDA(cudaGetLastError());
+}
+
+// out[row] = sum_c w[c] * p[row, c]   (the p1 half of conv_out1)
+__global__ void __launch_bounds__(256) dot1_kernel(const void* p, int pdt, int ldp, int C, const float* w, float* out,
+                                                   long long rows) {
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s = fmaf(w[c], g_ld(p, pdt, m * ldp + c), s);
+  s = warp_sum(s);
+  if (lane == 0) out[m] = s;
+}
+void glue_dot1(const LaunchCtx& ctx, View p, const float* w, float* out) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  long long rows = p.rows();
+  dot1_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ctx.stream>>>(p.p, p.dt, p.ld, p.C, w, out, rows);
+  BRN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused final layer (src/birefnet.rs:320,372-375 + src/decoder.rs:50-56), exact algebraic rewrite:
+//   conv_out1(cat(up(p1), ipt_blk1(x))) = up(w_p . p1) + conv3x3_{64->1}(conv3x3_{3->64}(x); Wc) + bc
+// where Wc[c,i,j] = sum_o w_i[o] ipt_blk1.conv_out.weight[o,c,i,j]; the inner conv's zero padding is kept (the
+// 64-channel intermediate is zero outside the image).  The 240-channel full-resolution tensor never exists.
+// ------------------------------------------------------------------------------------------------
+constexpr int FT = 16;  // output tile
+__global__ void __launch_bounds__(256) final_kernel(const float* __restrict__ x, int H, int W,
+                                                    const float* __restrict__ w1, const float* __restrict__ b1,
+                                                    const float* __restrict__ wc, float bc,
+                                                    const float* __restrict__ q, int qh, int qw, float* out,
+                                                    int apply_sigmoid) {
+  __shared__ float xin[3][FT + 4][FT + 4];
+  __shared__ float tmid[16][FT + 2][FT + 2 + 1];
+  __shared__ float sw1[64 * 27], sb1[64], swc[64 * 9];
+  const int b = blockIdx.z, ty0 = blockIdx.y * FT, tx0 = blockIdx.x * FT, tid = threadIdx.x;
+  for (int i = tid; i < 64 * 27; i += 256) sw1[i] = w1[i];
+  for (int i = tid; i < 64 * 9; i += 256) swc[i] = wc[i];
+  if (tid < 64) sb1[tid] = b1[tid];
+  for (int i = tid; i < 3 * (FT + 4) * (FT + 4); i += 256) {
+    int c = i / ((FT + 4) * (FT + 4)), r = i % ((FT + 4) * (FT + 4)), yy = r / (FT + 4), xx = r % (FT + 4);
+    int gy = ty0 + yy - 2, gx = tx0 + xx - 2;
+    xin[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[((long long)(b * 3 + c) * H + gy) * W + gx] : 0.f;
+  }
+  __syncthreads();
+  const int ly = tid / FT, lx = tid % FT;
+  float acc = 0.f;
+  for (int cc = 0; cc < 64; cc += 16) {
+    for (int i = tid; i < 16 * (FT + 2) * (FT + 2); i += 256) {
+      int c = i / ((FT + 2) * (FT + 2)), r = i % ((FT + 2) * (FT + 2)), yy = r / (FT + 2), xx = r % (FT + 2);
+      int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
+      float v = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        v = sb1[cc + c];
+        const float* wr = &sw1[(cc + c) * 27];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) v = fmaf(wr[ci * 9 + ky * 3 + kx], xin[ci][yy + ky][xx + kx], v);
+      }
+      tmid[c][yy][xx] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int c = 0; c < 16; ++c) {
+      const float* wr = &swc[(cc + c) * 9];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) acc = fmaf(wr[ky * 3 + kx], tmid[c][ly + ky][lx + kx], acc);
+    }
+    __syncthreads();
+  }
+  const int gy = ty0 + ly, gx = tx0 + lx;
+  if (gy < H && gx < W) {
+    int y0, y1, x0, x1; float fy, fx;
+    bilin_coord(gy, qh, H, y0, y1, fy);
+    bilin_coord(gx, qw, W, x0, x1, fx);
+    const float* qb = q + (long long)b * qh * qw;
+    float up = (1.f - fy) * ((1.f - fx) * qb[y0 * qw + x0] + fx * qb[y0 * qw + x1]) +
+               fy * ((1.f - fx) * qb[y1 * qw + x0] + fx * qb[y1 * qw + x1]);
+    float v = acc + bc + up;
+    if (apply_sigmoid) v = 1.f / (1.f + expf(-v));
+    out[((long long)b * H + gy) * W + gx] = v;
+  }
+}
+
+void glue_final(const LaunchCtx& ctx, const float* x, int B, int H, int W, const float* w1, const float* b1,
+                const float* wc, float bc, const float* q, int qh, int qw, float* out, int apply_sigmoid) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  dim3 grid((W + FT - 1) / FT, (H + FT - 1) / FT, B);
+  final_kernel<<<grid, 256, 0, ctx.stream>>>(x, H, W, w1, b1, wc, bc, q, qh, qw, out, apply_sigmoid);
+  BRN_CUDA(cudaGetLastError());
+}
+
+}  // namespace brn

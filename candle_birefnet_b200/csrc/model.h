@@ -1,0 +1,155 @@
+// Model handle: weight schema, finalize (folding + upload) and the forward graph.  Private to the library.
+#pragma once
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/birefnet_b200.h"
+#include "brn_common.h"
+
+namespace brn {
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  bool set = false;
+  size_t numel() const { size_t n = 1; for (auto d : shape) n *= (size_t)d; return n; }
+};
+
+// Bump allocator over one device buffer, reset per forward.  A dry "plan" pass measures the peak first.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;
+  void* alloc(size_t bytes) {
+    off = (off + 1023) & ~(size_t)1023;
+    size_t o = off;
+    off += bytes;
+    if (off > peak) peak = off;
+    if (dry) return (void*)(uintptr_t)(0x10000 + o);
+    if (off > cap) throw Error(2, "arena overflow (plan pass under-estimated the workspace)");
+    return base + o;
+  }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+struct BlockW {
+  float *n1g, *n1b, *n2g, *n2b;
+  LayerW qkv, proj, fc1, fc2;
+  float* bias32;           // [heads][144][144]
+  __nv_bfloat16* bias16;   // [heads][144][152]
+};
+struct StageW {
+  std::vector<BlockW> blocks;
+  bool has_down = false;
+  float *dng = nullptr, *dnb = nullptr;
+  LayerW red;
+  float *ng = nullptr, *nb = nullptr;
+};
+struct AsppBranchW {
+  int k = 1;
+  LayerW om;   // offset_conv ++ modulator_conv -> [3k^2, 64, k, k] (+bias)
+  LayerW reg;  // regular_conv with BatchNorm folded -> [256, 64, k, k] (+bias = bn shift)
+};
+struct DecBlkW {
+  LayerW conv_in;        // + bn_in folded
+  AsppBranchW br[4];     // aspp1, aspp_deforms[0..2]
+  LayerW gap;            // global_avg_pool.1 + .2 folded: [256][64]
+  LayerW conv1;          // conv1[:, :1024] * bn1 scale, no bias
+  float* conv1_tail = nullptr;  // [64][256] = conv1[:, 1024:1280] * bn1 scale
+  float* bn1_shift = nullptr;   // [64]
+  LayerW conv_out;       // + bn_out folded
+};
+struct DecoderW {
+  LayerW ipt_conv1[5], ipt_out[5];   // index n-1 for ipt_blk{n}; [0] unused (fused final kernel)
+  DecBlkW squeeze, dec[4];           // dec[0] = decoder_block4 ... dec[3] = decoder_block1
+  LayerW lat[3];                     // lateral_block4,3,2
+  LayerW gdt[3];                     // gdt_convs_{4,3,2}.0 + .1 folded
+  float* gdt_attn_w[3] = {nullptr, nullptr, nullptr};
+  float gdt_attn_b[3] = {0, 0, 0};
+  float* out_wp = nullptr;           // conv_out1 weights on p1 channels
+  float *fin_w1 = nullptr, *fin_b1 = nullptr, *fin_wc = nullptr;
+  float fin_bc = 0.f;
+};
+
+struct ProfEntry {
+  std::string name;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double flops = 0;
+};
+
+struct Model {
+  brn_config cfg{};
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  std::mutex mu;
+  std::vector<std::string> keys;
+  std::unordered_map<std::string, int> index;
+  std::vector<HostTensor> tensors;
+  bool finalized = false;
+  std::vector<void*> allocs;
+
+  StageW stages[4];
+  LayerW patch_embed;
+  float *pe_g = nullptr, *pe_b = nullptr;
+  DecoderW dw;
+
+  Arena arena;
+  long long launches = 0;
+
+  bool prof_on = false;
+  std::vector<ProfEntry> prof;
+  std::vector<const char*> prof_names;
+  std::vector<float> prof_ms;
+  std::vector<double> prof_flops;
+
+  // derived
+  int C(int i) const { return cfg.embed_dim << i; }
+  int lat(int i) const { return 2 * C(i); }
+  int x4_channels() const { return lat(0) + lat(1) + lat(2) + lat(3); }
+
+  explicit Model(const brn_config& c, int dev);
+  ~Model();
+  void build_schema();
+  void set_tensor(const char* key, const void* data, int dtype, const int64_t* shape, int rank);
+  void finalize();
+
+  // graph
+  void forward(const float* x, int B, int H, int W, bool x_dev, float* out, bool out_dev, cudaStream_t s,
+               bool apply_sigmoid);
+  void backbone_api(const float* x, int B, int H, int W, bool x_dev, float* const outs[4], bool out_dev,
+                    cudaStream_t s);
+  void decoder_api(const float* x, const float* x1, const float* x2, const float* x3, const float* x4, int B, int H,
+                   int W, bool is_dev, float* out, cudaStream_t s);
+
+ private:
+  void run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, float* out, bool apply_sigmoid);
+  void run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, View feats[4]);
+  void run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out);
+  void run_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, View X1, View X2, View X3, View D4in,
+                   float* out, bool apply_sigmoid);
+  void run_squeeze_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, View X1, View X2, View X3,
+                           View X4cat, float* out, bool apply_sigmoid);
+  void ensure_arena(size_t bytes);
+  int micro_batch(int B, int H, int W) const;
+  int act_dtype() const { return cfg.precision == BRN_PREC_BF16 ? BF16 : F32; }
+  void prof_begin(LaunchCtx& ctx, const char* name);
+  void prof_end(LaunchCtx& ctx);
+
+  const HostTensor& T(const std::string& k) const;
+  float* upload(const std::vector<float>& v);
+  LayerW make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w_oihw, const std::vector<float>* bias);
+};
+
+// generic dispatchers (precision + support -> tcgen05 or SIMT)
+void op_gemm(const LaunchCtx&, const GemmArgs&);
+void op_deform(const LaunchCtx&, const DeformArgs&);
+void op_attention(const LaunchCtx&, const AttnArgs&);
+
+// standalone layer upload for the operator-level ABI
+LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w_oihw, const float* bias,
+                             std::vector<void*>& allocs);
+
+}  // namespace brn

@@ -1,0 +1,63 @@
+"""Operator-level entry points (host numpy in / out) -- the reference's native boundaries, used by parity tests."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+_PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def linear(a, w, bias=None, residual=None, act: int = 0, precision: str = "bf16", device: int = 0) -> np.ndarray:
+    """candle_nn::linear (+ activation / residual epilogue): act 0 none, 1 relu, 2 exact-erf gelu."""
+    a, w, bias, residual = _f32(a), _f32(w), _f32(bias), _f32(residual)
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape == (N, K)
+    out = np.empty((M, N), dtype=np.float32)
+    check(lib().brn_linear(device, _PREC[precision], _p(a), _p(w), _p(bias), _p(residual), M, N, K, act, _p(out)))
+    return out
+
+
+def conv2d(x, weight, bias=None, act: int = 0, precision: str = "bf16", device: int = 0) -> np.ndarray:
+    """candle_nn::conv2d, stride 1, padding k//2, NCHW."""
+    x, weight, bias = _f32(x), _f32(weight), _f32(bias)
+    B, Cin, H, W = x.shape
+    O, _, k, _ = weight.shape
+    out = np.empty((B, O, H, W), dtype=np.float32)
+    check(lib().brn_conv2d(device, _PREC[precision], _p(x), _p(weight), _p(bias), B, Cin, H, W, O, k, act, _p(out)))
+    return out
+
+
+def deform_conv2d(x, offset, mask, weight, bias=None, precision: str = "bf16", device: int = 0) -> np.ndarray:
+    """DeformableConv2d / DeformConvASPP Metal math (src/deform_conv.rs:102-215, src/aspp.rs:58-165); stride 1."""
+    x, offset, mask, weight, bias = _f32(x), _f32(offset), _f32(mask), _f32(weight), _f32(bias)
+    B, Cin, H, W = x.shape
+    O, _, k, _ = weight.shape
+    assert offset.shape == (B, 2 * k * k, H, W) and mask.shape == (B, k * k, H, W)
+    out = np.empty((B, O, H, W), dtype=np.float32)
+    check(lib().brn_deform_conv2d(device, _PREC[precision], _p(x), _p(offset), _p(mask), _p(weight), _p(bias), B, Cin,
+                                  H, W, O, k, _p(out)))
+    return out
+
+
+def window_attention(qkv, bias, hp: int, wp: int, shift: int, precision: str = "bf16", device: int = 0) -> np.ndarray:
+    """WindowAttention::forward_standard (src/swin.rs:266-311) on window-ordered qkv [n_windows,144,3*heads*32]."""
+    qkv, bias = _f32(qkv), _f32(bias)
+    nwin, n, c3 = qkv.shape
+    heads = bias.shape[0]
+    assert n == 144 and c3 == 3 * heads * 32 and bias.shape == (heads, 144, 144)
+    out = np.empty((nwin, 144, heads * 32), dtype=np.float32)
+    check(lib().brn_window_attention(device, _PREC[precision], _p(qkv), _p(bias), nwin, heads, hp, wp, shift, _p(out)))
+    return out

@@ -1,0 +1,178 @@
+/*
+ * birefnet_b200.h -- C ABI of libbirefnet_b200.so
+ *
+ * B200-native (sm_100a) replacement for the forward path of the Rust crate
+ * imperatormk/candle-birefnet.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference repo).  No torch /
+ * candle types cross this boundary: plain pointers, sizes and an opaque handle.
+ *
+ * Data layout at the boundary is the reference's: NCHW, fp32, contiguous
+ * (`Tensor[B,3,H,W]` in, `Tensor[B,1,H,W]` out, src/birefnet.rs:412-461).
+ * H and W must be multiples of 32 (the reference's image2patches uses integer
+ * division, src/birefnet.rs:290-299, and fails in reshape otherwise; here it is
+ * BRN_ERR_SHAPE).  Internal layouts (NHWC bf16, window-ordered tokens) are private.
+ *
+ * Errors: every function returns brn_status; brn_last_error() gives the
+ * thread-local message (mirrors candle_core::Result / bail!, src/aspp.rs:101,117).
+ * Nothing throws or aborts across the ABI.
+ *
+ * Threading: a handle is thread-compatible, not thread-safe: calls on one
+ * handle are serialised by an internal mutex (the reference's `&self` forward
+ * is immutable; here the workspace arena is per handle).  Use one handle per
+ * GPU for image sharding.
+ */
+#ifndef BIREFNET_B200_H
+#define BIREFNET_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define BRN_API __attribute__((visibility("default")))
+#else
+#define BRN_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct brn_model brn_model;
+
+typedef enum {
+  BRN_OK = 0,
+  BRN_ERR_INVALID = 1,        /* bad argument / null pointer                         */
+  BRN_ERR_CUDA = 2,           /* CUDA runtime/driver error (message names the call)  */
+  BRN_ERR_MISSING_TENSOR = 3, /* finalize: a key of the schema was never set         */
+  BRN_ERR_UNKNOWN_TENSOR = 4, /* set_tensor: key not in the schema                   */
+  BRN_ERR_SHAPE = 5,          /* shape / dtype mismatch, H or W not a multiple of 32 */
+  BRN_ERR_STATE = 6,          /* call order (forward before finalize, ...)           */
+  BRN_ERR_UNSUPPORTED = 7     /* config outside window 12 / head_dim 32              */
+} brn_status;
+
+typedef enum { BRN_F32 = 0, BRN_BF16 = 1, BRN_F16 = 2 } brn_dtype;
+
+/* precision of the arithmetic (north_star): FP32 = SIMT fp32 FMA path (max |dlogit| <= 1e-3 vs the
+ * reference's fp32 CPU forward); BF16 = tcgen05 tensor-core path, fp32 accumulate, fp32 residual
+ * stream / LN / softmax (max |dsigmoid| <= 1e-2, IoU@0.5 >= 0.999). */
+typedef enum { BRN_PREC_FP32 = 0, BRN_PREC_BF16 = 1 } brn_precision;
+
+/* What `DeformConvASPP::forward` computes (src/aspp.rs:168-187):
+ *   CPU_FALLBACK: regular_conv(x), offsets/modulator discarded -- the reference's behaviour on Device::Cpu
+ *                 (src/aspp.rs:183-185, src/deform_conv.rs:95-98);
+ *   DEFORMABLE:   modulated deformable conv, torchvision DCNv2 semantics -- the reference's Metal path
+ *                 (src/aspp.rs:58-165). */
+typedef enum { BRN_DEFORM_CPU_FALLBACK = 0, BRN_DEFORM_DEFORMABLE = 1 } brn_deform_mode;
+
+/* Mirror of SwinConfig (src/swin.rs:13-23) + the BiRefNetConfig fields that are read (src/birefnet.rs:13-30).
+ * window_size must be 12 and embed_dim/num_heads[0] must be 32. */
+typedef struct {
+  int32_t embed_dim;      /* 192 for swin_l                      */
+  int32_t depths[4];      /* {2,2,18,2}                          */
+  int32_t num_heads[4];   /* {6,12,24,48}                        */
+  int32_t window_size;    /* 12                                  */
+  int32_t mlp_ratio;      /* 4                                   */
+  int32_t patch_size;     /* 4                                   */
+  int32_t precision;      /* brn_precision (initial; changeable) */
+  int32_t deform_mode;    /* brn_deform_mode (initial)           */
+  int32_t micro_batch;    /* images per internal pass; 0 = auto  */
+} brn_config;
+
+/* BiRefNetConfig::swin_l() (src/birefnet.rs:64-66) + SwinConfig::swin_l() (src/swin.rs:69-80). */
+BRN_API void brn_config_swin_l(brn_config* cfg);
+
+/* ---- model lifetime: replaces BiRefNet::new(config, vb) (src/birefnet.rs:389-409) ------------------------- */
+
+/* Allocates a handle on CUDA device `device`.  Fails loudly (BRN_ERR_CUDA) when no sm_100 device is present:
+ * there is no CPU fallback. */
+BRN_API brn_status brn_model_create(const brn_config* cfg, int device, brn_model** out);
+
+/* Replaces `vb.get(shape, key)` / candle_core::safetensors::load (examples/infer_image.rs:35-40).  `key` is the
+ * HF safetensors name, `data` a HOST pointer to a contiguous tensor of `dtype`.
+ * Unknown key -> BRN_ERR_UNKNOWN_TENSOR; wrong shape -> BRN_ERR_SHAPE (candle's `vb.get` shape check). */
+BRN_API brn_status brn_model_set_tensor(brn_model* m, const char* key, const void* data, int dtype,
+                                const int64_t* shape, int rank);
+
+/* Number of tensors in the schema and the i-th key/shape (for loaders and tests). */
+BRN_API int32_t brn_model_num_tensors(const brn_model* m);
+BRN_API brn_status brn_model_tensor_info(const brn_model* m, int32_t index, const char** key, int64_t shape[4], int32_t* rank);
+
+/* Folds eval-BatchNorm into the preceding convs, pre-gathers the relative-position bias to [heads,144,144]
+ * (WindowAttention::new, src/swin.rs:143-152), re-lays conv weights out tap-major and uploads fp32 + bf16 copies.
+ * Missing key -> BRN_ERR_MISSING_TENSOR (mirrors `vb.get` failing inside BiRefNet::new). */
+BRN_API brn_status brn_model_finalize(brn_model* m);
+
+BRN_API brn_status brn_model_set_precision(brn_model* m, int precision);
+BRN_API brn_status brn_model_set_deform_mode(brn_model* m, int deform_mode);
+
+BRN_API void brn_model_destroy(brn_model* m);
+
+/* ---- the hot path ------------------------------------------------------------------------------------------- */
+
+/* BiRefNet::forward_logits (src/birefnet.rs:412-461).  x: [B,3,H,W] fp32 NCHW; out: [B,1,H,W] fp32.
+ * x_is_device / out_is_device: 0 = host pointer (copied inside the call), 1 = device pointer on the handle's GPU.
+ * `stream` is a cudaStream_t (NULL = the handle's own stream).  The call returns after the work is enqueued when
+ * both pointers are device pointers, and after completion otherwise. */
+BRN_API brn_status brn_forward_logits(brn_model* m, const float* x, int32_t B, int32_t H, int32_t W, int x_is_device,
+                              float* out, int out_is_device, void* stream);
+
+/* BiRefNet::forward / impl Module (src/birefnet.rs:466-476): sigmoid(forward_logits). */
+BRN_API brn_status brn_forward(brn_model* m, const float* x, int32_t B, int32_t H, int32_t W, int x_is_device,
+                       float* out, int out_is_device, void* stream);
+
+/* SwinTransformer::forward (src/swin.rs:768-797): 4 NCHW fp32 maps [B,C_i,H/4>>i,W/4>>i] (BASELINE config 2). */
+BRN_API brn_status brn_backbone_forward(brn_model* m, const float* x, int32_t B, int32_t H, int32_t W, int x_is_device,
+                                float* const outs[4], int out_is_device, void* stream);
+
+/* SqueezeModule::forward + BiRefNetDecoder::forward (src/birefnet.rs:86-94, 278-376) on caller-provided
+ * multi-scale features (BASELINE config 4).  x1..x3: [B,2C_i,...] NCHW fp32 as produced by forward_logits lines
+ * 435-443; x4: the cxt-concatenated [B,x4_channels,H/32,W/32] (line 453), before the squeeze module. */
+BRN_API brn_status brn_decoder_forward(brn_model* m, const float* x, const float* x1, const float* x2, const float* x3,
+                               const float* x4, int32_t B, int32_t H, int32_t W, int is_device, float* out,
+                               void* stream);
+
+/* ---- operator level (kernel parity tests; the reference's native boundaries) ---------------------------------- */
+
+/* Plain-chain window attention: out = softmax(scale*q k^T + bias[h] (+ mask[w % nW])) v, the computation of
+ * WindowAttention::forward_standard (src/swin.rs:266-311) == what flash_attention_with_[repeating_]bias replaces
+ * (src/swin.rs:243,252; examples/test_flash_bias.rs:30-36).  qkv: HOST fp32 [n_windows,144,3*heads*32] (channel =
+ * s*C + head*32 + d, src/swin.rs:218-223), bias: HOST fp32 [heads,144,144]; shift geometry (hp,wp in tokens, shift
+ * 0 or 6) selects the analytic -100 mask of create_attention_mask (src/swin.rs:603-655).
+ * out: HOST fp32 [n_windows,144,heads*32]. */
+BRN_API brn_status brn_window_attention(int device, int precision, const float* qkv, const float* bias, int32_t n_windows,
+                                int32_t heads, int32_t hp, int32_t wp, int32_t shift, float* out);
+
+/* Modulated deformable conv == call_deformable_im2col + weight matmul (src/aspp.rs:138-164,
+ * src/deform_conv.rs:177-214).  x: HOST fp32 NCHW [B,C,H,W]; offset [B,2k^2,H,W] (dy,dx interleaved per tap),
+ * mask [B,k^2,H,W], weight [O,C,k,k], bias [O] or NULL; stride 1, padding k/2, dilation 1, one offset group.
+ * out: HOST fp32 NCHW [B,O,H,W]. */
+BRN_API brn_status brn_deform_conv2d(int device, int precision, const float* x, const float* offset, const float* mask,
+                             const float* weight, const float* bias, int32_t B, int32_t C, int32_t H, int32_t W,
+                             int32_t O, int32_t k, float* out);
+
+/* D[M,N] = act(A[M,K] W[N,K]^T + bias[N]) (+ residual[M,N]); candle_nn::linear (src/swin.rs:98-107,130-131).
+ * act: 0 none, 1 relu, 2 exact-erf gelu.  All HOST fp32 row-major. */
+BRN_API brn_status brn_linear(int device, int precision, const float* a, const float* w, const float* bias,
+                      const float* residual, int32_t M, int32_t N, int32_t K, int32_t act, float* out);
+
+/* conv2d, stride 1, zero padding k/2, NCHW fp32 HOST tensors (candle_nn::conv2d; src/decoder.rs:44-45,104,113). */
+BRN_API brn_status brn_conv2d(int device, int precision, const float* x, const float* weight, const float* bias, int32_t B,
+                      int32_t C, int32_t H, int32_t W, int32_t O, int32_t k, int32_t act, float* out);
+
+/* ---- introspection --------------------------------------------------------------------------------------------- */
+
+/* Kernels launched by this handle since creation / since the last reset (bench.py's `gpu_launches`). */
+BRN_API int64_t brn_launch_count(const brn_model* m);
+BRN_API void brn_launch_count_reset(brn_model* m);
+
+/* Per-stage device time of the last forward, CUDA events on the launch stream (needs brn_profile_enable(m,1)).
+ * names/ms arrays are owned by the handle; returns the number of entries. */
+BRN_API void brn_profile_enable(brn_model* m, int on);
+BRN_API int32_t brn_profile_get(const brn_model* m, const char*** names, const float** ms, const double** flops);
+
+BRN_API const char* brn_last_error(void);
+BRN_API const char* brn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIREFNET_B200_H */
