@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
     L.brn_profile_enable.restype = None
     L.brn_profile_get.argtypes = [vp, C.POINTER(C.POINTER(C.c_char_p)), C.POINTER(fp), C.POINTER(C.POINTER(C.c_double))]
     L.brn_profile_get.restype = i32
+    L.brn_kernel_class_times.argtypes = [vp, fp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32), i32]
+    L.brn_kernel_class_times.restype = i32
     _lib = L
     return L
 

@@ -138,7 +138,18 @@ brn_status brn_decoder_forward(brn_model* m, const float* x, const float* x1, co
 
 int64_t brn_launch_count(const brn_model* m) { return m ? m->impl.launches : 0; }
 void brn_launch_count_reset(brn_model* m) { if (m) m->impl.launches = 0; }
-void brn_profile_enable(brn_model* m, int on) { if (m) m->impl.prof_on = on != 0; }
+void brn_profile_enable(brn_model* m, int on) { if (m) m->impl.prof_on = on; }
+int32_t brn_kernel_class_times(const brn_model* m, float* ms, double* flops, double* bytes, int32_t* counts, int32_t cap) {
+  if (!m) return 0;
+  const int n = cap < (int)KC_COUNT ? cap : (int)KC_COUNT;
+  for (int c = 0; c < n; ++c) {
+    if (ms) ms[c] = m->impl.kc_ms[c];
+    if (flops) flops[c] = m->impl.kc_flops[c];
+    if (bytes) bytes[c] = m->impl.kc_bytes[c];
+    if (counts) counts[c] = m->impl.kc_count[c];
+  }
+  return (int32_t)KC_COUNT;
+}
 int32_t brn_profile_get(const brn_model* m, const char*** names, const float** ms, const double** flops) {
   if (!m) return 0;
   if (names) *names = const_cast<const char**>(m->impl.prof_names.data());

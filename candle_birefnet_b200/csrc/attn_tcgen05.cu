@@ -280,6 +280,7 @@ void tc_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   const int sms = device_sm_count();
   int per_head = std::max(1, sms / a.heads);
   per_head = std::min(per_head, a.n_windows);
+  KScope ks(ctx, KC_ATTN_TC, 4.0 * 144 * 144 * 32 * (double)a.n_windows * a.heads);
   tc_attn_kernel<<<a.heads * per_head, AT_THREADS, AT_SMEM, ctx.stream>>>(tm, p);
   BRN_CUDA(cudaGetLastError());
 }

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace brn {
 
@@ -108,12 +109,35 @@ struct AttnArgs {
   View out;               // [rows, C]
 };
 
+// Per-kernel-class device timing (CUDA events on the launch stream around every launch of the class); used by
+// bench.py for the roofline of the dominant kernel and the kernel-time shares.  Off on the timed throughput path.
+enum KClass { KC_GEMM_TC = 0, KC_ATTN_TC, KC_DEFORM_TC, KC_GEMM_SIMT, KC_ATTN_SIMT, KC_LN, KC_GLUE, KC_COUNT };
+struct KTimer {
+  struct Rec { int cls; cudaEvent_t e0, e1; double flops; double bytes; };
+  std::vector<Rec> recs;
+};
+
 struct LaunchCtx {
   cudaStream_t stream = nullptr;
   int precision = 0;
   bool dry = false;        // plan pass: no launches
   long long* launches = nullptr;
   bool force_simt = false;
+  KTimer* kt = nullptr;
+};
+
+struct KScope {
+  const LaunchCtx& c;
+  cudaEvent_t e1 = nullptr;
+  KScope(const LaunchCtx& ctx, int cls, double flops, double bytes = 0) : c(ctx) {
+    if (!c.kt || c.dry) return;
+    KTimer::Rec r{cls, nullptr, nullptr, flops, bytes};
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, c.stream);
+    e1 = r.e1;
+    c.kt->recs.push_back(r);
+  }
+  ~KScope() { if (e1) cudaEventRecord(e1, c.stream); }
 };
 
 // ---- SIMT (fp32 FMA) kernels: kernels_simt.cu ----

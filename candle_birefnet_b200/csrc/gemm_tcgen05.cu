@@ -19,6 +19,7 @@
 #include "brn_common.h"
 #include "device_utils.cuh"
 #include "tc_ptx.cuh"
+#include "tc_epilogue.cuh"
 
 namespace brn {
 
@@ -32,32 +33,9 @@ struct TcGemmP {
   int tw_log2, tiles_x, tiles_y;
   int m_tiles, n_tiles, BN;
   int taps, kw, pad, cblocks, cin_pad;
-  int N;
-  const float* bias; int bias_bstride;
-  int act, act_from;
-  const void* res; int resdt; int ldres; int vec_res;
-  void* out; int odt; int ldo; int vec_out;
+  EpiP epi;
   RowMap rm;
 };
-
-// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 2 MUFU + ~10 FMA instead of erff's ~40 instructions.  The
-// epilogue evaluates ~0.5 G GELUs per 1024^2 image, so this is what keeps fc1 MMA-paced rather than epilogue-paced.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  poly *= t;
-  const float erf_abs = 1.f - poly * __expf(-z * z);
-  return 0.5f * x * (1.f + copysignf(erf_abs, x));
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmP p) {
@@ -139,7 +117,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
-    const int esz = p.odt == F32 ? 4 : 2;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
       const int b = m_tile / tiles_per_img, r = m_tile - b * tiles_per_img;
@@ -151,87 +128,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         valid = orow >= 0;
       }
       const int n0 = n_tile * p.BN;
-      const float* bias = p.bias ? p.bias + (long long)b * p.bias_bstride : nullptr;
+      const float* bias = p.epi.bias ? p.epi.bias + (long long)b * p.epi.bias_bstride : nullptr;
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
       for (int c = 0; c < p.BN / 16; ++c) {
         const int nb = n0 + c * 16;
-        if (nb >= p.N) break;
+        if (nb >= p.epi.N) break;
         uint32_t v[16];
         ptx::tmem_ld16(taddr + c * 16, v);
         ptx::tmem_ld_wait();
         if (!valid) continue;
-        const bool full16 = nb + 16 <= p.N;
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        if (bias) {
-          if (full16) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 bv = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
-              f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (nb + j < p.N) f[j] += __ldg(bias + nb + j);
-          }
-        }
-        if (p.act == ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-        } else if (p.act == ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = gelu_fast(f[j]);
-        } else if (p.act == ACT_2SIGMOID_TAIL) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) if (nb + j >= p.act_from) f[j] = 2.f / (1.f + __expf(-f[j]));
-        }
-        if (p.res) {
-          if (p.vec_res && full16) {
-            if (p.resdt == F32) {
-              const float4* rp = reinterpret_cast<const float4*>((const float*)p.res + orow * p.ldres + nb);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) { float4 rv = rp[j]; f[4 * j] += rv.x; f[4 * j + 1] += rv.y; f[4 * j + 2] += rv.z; f[4 * j + 3] += rv.w; }
-            } else {
-              const uint4* rp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)p.res + orow * p.ldres + nb);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                uint4 rv = rp[j];
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) { float2 ff = __bfloat1622float2(h[t]); f[8 * j + 2 * t] += ff.x; f[8 * j + 2 * t + 1] += ff.y; }
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (nb + j < p.N)
-                f[j] += p.resdt == F32 ? ((const float*)p.res)[orow * p.ldres + nb + j]
-                                       : __bfloat162float(((const __nv_bfloat16*)p.res)[orow * p.ldres + nb + j]);
-          }
-        }
-        char* op = (char*)p.out + (orow * p.ldo + nb) * esz;
-        if (p.vec_out && full16) {
-          if (p.odt == F32) {
-            float4* o4 = reinterpret_cast<float4*>(op);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(op);
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                 pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.N) {
-              if (p.odt == F32) ((float*)op)[j] = f[j]; else ((__nv_bfloat16*)op)[j] = __float2bfloat16(f[j]);
-            }
-        }
+        epilogue_store16(p.epi, v, nb, orow, bias);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[acc]);
@@ -293,6 +201,16 @@ bool tc_gemm_supported(const GemmArgs& a) {
   return true;
 }
 
+EpiP make_epi(int N, const float* bias, int bias_bstride, int act, int act_from, const View& res, const View& out) {
+  EpiP e{};
+  e.N = N; e.bias = bias; e.bias_bstride = bias_bstride; e.act = act; e.act_from = act_from;
+  e.res = res.p; e.resdt = res.dt; e.ldres = res.ld;
+  e.vec_res = res.p && (((uintptr_t)res.p & 15) == 0) && ((res.ld * dsize(res.dt)) % 16 == 0);
+  e.out = out.p; e.odt = out.dt; e.ldo = out.ld;
+  e.vec_out = (((uintptr_t)out.p & 15) == 0) && ((out.ld * dsize(out.dt)) % 16 == 0);
+  return e;
+}
+
 static int pick_bn(int N) {
   if (N <= 256) return (N + 15) / 16 * 16;
   int best = 256, best_pad = (N + 255) / 256 * 256;
@@ -321,13 +239,7 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   p.BN = pick_bn(w.N);
   p.n_tiles = (w.N + p.BN - 1) / p.BN;
   p.taps = w.taps(); p.kw = w.kw; p.pad = a.pad; p.cin_pad = w.cin_pad; p.cblocks = w.cin_pad / TC_BK;
-  p.N = w.N;
-  p.bias = a.bias ? a.bias : w.bias; p.bias_bstride = a.bias_bstride;
-  p.act = a.act; p.act_from = a.act_from;
-  p.res = a.res.p; p.resdt = a.res.dt; p.ldres = a.res.ld;
-  p.vec_res = a.res.p && (((uintptr_t)a.res.p & 15) == 0) && ((a.res.ld * dsize(a.res.dt)) % 16 == 0);
-  p.out = a.out.p; p.odt = a.out.dt; p.ldo = a.out.ld;
-  p.vec_out = (((uintptr_t)a.out.p & 15) == 0) && ((a.out.ld * dsize(a.out.dt)) % 16 == 0);
+  p.epi = make_epi(w.N, a.bias ? a.bias : w.bias, a.bias_bstride, a.act, a.act_from, a.res, a.out);
   p.rm = a.rowmap;
 
   const uint64_t ld2 = (uint64_t)a.x.ld * 2;
@@ -341,11 +253,11 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   uint32_t bbox[2] = {(uint32_t)TC_BK, (uint32_t)p.BN};
   CUtensorMap tmB = make_tmap_bf16(w.w16, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B);
 
-  static std::once_flag once;
-  std::call_once(once, [] {
-    cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-  });
+  cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
   const int grid = std::min(p.m_tiles * p.n_tiles, device_sm_count());
+  const double rows = (double)a.x.rows();
+  KScope ks(ctx, KC_GEMM_TC, 2.0 * rows * w.N * w.taps() * w.Cin,
+            rows * a.x.C * 2 + rows * w.N * dsize(a.out.dt) + (double)w.N * w.taps() * w.cin_pad * 2);
   tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM, ctx.stream>>>(tmA, tmB, p);
   BRN_CUDA(cudaGetLastError());
 }

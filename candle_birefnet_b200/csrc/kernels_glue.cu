@@ -15,7 +15,8 @@ __device__ __forceinline__ void g_st(void* p, int dt, long long i, float v) {
 
 #define GLUE_LAUNCH_PROLOGUE(ctx)        \
   if ((ctx).launches) ++*(ctx).launches; \
-  if ((ctx).dry) return;
+  if ((ctx).dry) return;                 \
+  KScope ks__((ctx), KC_GLUE, 0.0);
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm, one warp per destination row (candle_nn::layer_norm, eps 1e-5, biased variance).
@@ -76,7 +77,9 @@ __global__ void __launch_bounds__(256) ln_kernel(LnP p) {
 }
 
 void glue_layernorm(const LaunchCtx& ctx, const LnArgs& a) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  if (ctx.launches) ++*ctx.launches;
+  if (ctx.dry) return;
+  KScope ks__(ctx, KC_LN, 0.0, (double)a.out.rows() * a.out.C * (4 + dsize(a.out.dt)));
   LnP p{};
   p.x = a.x.p; p.xdt = a.x.dt; p.ldx = a.x.ld; p.B = a.x.B; p.h = a.x.H; p.w = a.x.W; p.C = a.x.C;
   p.gamma = a.gamma; p.beta = a.beta;

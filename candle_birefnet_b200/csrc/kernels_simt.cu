@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtGemmP p) {
 static void launch_simt_gemm(const LaunchCtx& ctx, SimtGemmP& p) {
   if (ctx.launches) ++*ctx.launches;
   if (ctx.dry) return;
+  KScope ks(ctx, KC_GEMM_SIMT, 2.0 * (double)p.M * p.N * p.kh * p.kw * p.Cin);
   dim3 grid((unsigned)((p.M + SG_BM - 1) / SG_BM), (unsigned)((p.N + SG_BN - 1) / SG_BN));
   simt_gemm_kernel<<<grid, 256, 0, ctx.stream>>>(p);
   BRN_CUDA(cudaGetLastError());
@@ -234,6 +235,7 @@ void simt_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   p.bias = a.bias32; p.heads = a.heads; p.nwh = a.nwh; p.nww = a.nww; p.shift = a.shift;
   p.out = a.out.p; p.odt = a.out.dt; p.ldo = a.out.ld;
   dim3 grid(a.n_windows, a.heads);
+  KScope ks(ctx, KC_ATTN_SIMT, 4.0 * 144 * 144 * 32 * (double)a.n_windows * a.heads);
   simt_attn_kernel<<<grid, 160, 0, ctx.stream>>>(p);
   BRN_CUDA(cudaGetLastError());
 }

@@ -649,6 +649,7 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
   run_forward(ctx, (const float*)0x10000, mb, H, W, (float*)0x10000, apply_sigmoid);
   ensure_arena(arena.peak);
   arena.dry = false; ctx.dry = false; ctx.launches = &launches;
+  if (prof_on >= 2) { ctx.kt = &ktimer; ktimer.recs.clear(); }
   if (prof_on) {
     for (auto& pe : prof) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
     prof.clear();
@@ -665,6 +666,15 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
     if (!out_dev) BRN_CUDA(cudaMemcpyAsync(oi, dout, (size_t)nb * H * W * 4, cudaMemcpyDeviceToHost, st));
   }
   if (!x_dev || !out_dev || prof_on) BRN_CUDA(cudaStreamSynchronize(st));
+  if (prof_on >= 2) {
+    for (int c = 0; c < KC_COUNT; ++c) { kc_ms[c] = 0; kc_flops[c] = 0; kc_bytes[c] = 0; kc_count[c] = 0; }
+    for (auto& r : ktimer.recs) {
+      float ms = 0; cudaEventElapsedTime(&ms, r.e0, r.e1);
+      kc_ms[r.cls] += ms; kc_flops[r.cls] += r.flops; kc_bytes[r.cls] += r.bytes; kc_count[r.cls]++;
+      cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    ktimer.recs.clear();
+  }
   if (prof_on) {
     prof_names.clear(); prof_ms.clear(); prof_flops.clear();
     for (auto& pe : prof) {

@@ -99,7 +99,12 @@ struct Model {
   Arena arena;
   long long launches = 0;
 
-  bool prof_on = false;
+  int prof_on = 0;          // 1: per-stage events, 2: + per-kernel-class events (KTimer)
+  KTimer ktimer;
+  float kc_ms[KC_COUNT] = {0};
+  double kc_flops[KC_COUNT] = {0};
+  double kc_bytes[KC_COUNT] = {0};
+  int kc_count[KC_COUNT] = {0};
   std::vector<ProfEntry> prof;
   std::vector<const char*> prof_names;
   std::vector<float> prof_ms;

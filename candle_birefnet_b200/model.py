@@ -112,6 +112,34 @@ class BiRefNet:
             raise
         return m
 
+    @staticmethod
+    def new_synthetic(config: BiRefNetConfig, seed: int = 0, weight_set: str = "B", offset_sigma: float = 2.0,
+                      device: int = 0) -> "BiRefNet":
+        """BiRefNet::new on seeded random-init weights (no network for the HF checkpoint): the schema comes from the
+        handle itself, the values from `synth.synthetic_weights`."""
+        from .synth import synthetic_weights
+        L = lib()
+        probe = BiRefNet._create(config, device)
+        try:
+            sc = probe.tensor_schema()
+        finally:
+            probe.close()
+        return BiRefNet.new(config, synthetic_weights(sc, seed, weight_set, offset_sigma), device)
+
+    @staticmethod
+    def _create(config: BiRefNetConfig, device: int) -> "BiRefNet":
+        L = lib()
+        c = BrnConfig()
+        c.embed_dim = config.swin.embed_dim
+        for i in range(4):
+            c.depths[i] = config.swin.depths[i]
+            c.num_heads[i] = config.swin.num_heads[i]
+        c.window_size, c.mlp_ratio, c.patch_size = config.swin.window_size, config.swin.mlp_ratio, config.swin.patch_size
+        c.precision, c.deform_mode, c.micro_batch = _PREC[config.precision], _DEF[config.deform_mode], config.micro_batch
+        h = C.c_void_p()
+        check(L.brn_model_create(C.byref(c), device, C.byref(h)))
+        return BiRefNet(h, config, device)
+
     def tensor_keys(self) -> List[str]:
         L = lib()
         out = []
@@ -209,8 +237,22 @@ class BiRefNet:
     def reset_launch_count(self) -> None:
         lib().brn_launch_count_reset(self._h)
 
-    def profile(self, on: bool = True) -> None:
-        lib().brn_profile_enable(self._h, 1 if on else 0)
+    KERNEL_CLASSES = ("gemm_tcgen05", "attn_tcgen05", "deform_tcgen05", "gemm_simt", "attn_simt", "layernorm", "glue")
+
+    def profile(self, on=True) -> None:
+        """on = 1/True: per-stage CUDA events; on = 2: also events around every kernel launch (per-class sums)."""
+        lib().brn_profile_enable(self._h, int(on))
+
+    def kernel_class_times(self):
+        """{class: dict(ms, flops, bytes, launches)} of the last forward run with profile(2)."""
+        n = len(self.KERNEL_CLASSES)
+        ms = (C.c_float * n)()
+        fl = (C.c_double * n)()
+        by = (C.c_double * n)()
+        cnt = (C.c_int32 * n)()
+        lib().brn_kernel_class_times(self._h, ms, fl, by, cnt, n)
+        return {k: dict(ms=float(ms[i]), flops=float(fl[i]), bytes=float(by[i]), launches=int(cnt[i]))
+                for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def profile_get(self) -> List[Tuple[str, float]]:
         names = C.POINTER(C.c_char_p)()

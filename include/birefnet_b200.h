@@ -166,7 +166,13 @@ BRN_API void brn_launch_count_reset(brn_model* m);
 
 /* Per-stage device time of the last forward, CUDA events on the launch stream (needs brn_profile_enable(m,1)).
  * names/ms arrays are owned by the handle; returns the number of entries. */
+/* on = 1: per-stage events; on = 2: additionally CUDA events around EVERY kernel launch, summed per kernel class
+ * (0 gemm_tcgen05, 1 attn_tcgen05, 2 deform_tcgen05, 3 gemm_simt, 4 attn_simt, 5 layernorm, 6 glue). */
 BRN_API void brn_profile_enable(brn_model* m, int on);
+/* Per-class device time (ms), algorithmic flops and bytes, and launch counts of the last forward (mode 2).
+ * Arrays of capacity `cap`; returns the number of classes. */
+BRN_API int32_t brn_kernel_class_times(const brn_model* m, float* ms, double* flops, double* bytes, int32_t* counts,
+                                       int32_t cap);
 BRN_API int32_t brn_profile_get(const brn_model* m, const char*** names, const float** ms, const double** flops);
 
 BRN_API const char* brn_last_error(void);

@@ -105,49 +105,11 @@ def schema(cfg: Config) -> "OrderedDict[str, Tuple[Tuple[int, ...], str]]":
     return s
 
 
-def make_weights(cfg: Config, seed: int = 0, weight_set: str = "A", offset_sigma: float = 2.0,
-                 gain: float = 1.0) -> Dict[str, np.ndarray]:
-    """float32 numpy tensors for every key of `schema(cfg)`."""
-    assert weight_set in ("A", "B")
-    out: Dict[str, np.ndarray] = {}
-    for name, (shape, kind) in schema(cfg).items():
-        rng = np.random.Generator(np.random.PCG64([seed, zlib.crc32(name.encode())]))
-        fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
-        is_off = ".offset_conv." in name or ".modulator_conv." in name
-        if kind == "w":
-            v = rng.standard_normal(shape) * (gain * np.sqrt(1.0 / fan_in))
-        elif kind == "b":
-            # U(+-1/sqrt(fan_in)) with the fan_in of the matching weight
-            wshape = schema_cache(cfg)[name[:-5] + ".weight"][0]
-            v = rng.uniform(-1.0, 1.0, shape) / (1.0 if is_off else np.sqrt(float(np.prod(wshape[1:]))))
-        elif kind == "ln_g" or kind == "bn_g":
-            v = 1.0 + 0.1 * rng.standard_normal(shape)
-        elif kind == "ln_b" or kind == "bn_b" or kind == "bn_m":
-            v = 0.1 * rng.standard_normal(shape)
-        elif kind == "bn_v":
-            v = rng.uniform(0.5, 1.5, shape)
-        elif kind == "table":
-            v = 0.5 * rng.standard_normal(shape)
-        else:
-            raise AssertionError(kind)
-        if is_off:
-            if weight_set == "A":
-                v = np.zeros(shape)
-            elif ".offset_conv." in name:
-                # inputs to the ASPP are post-ReLU O(1); fan-in normalised weights give O(1) outputs
-                v = v * offset_sigma if kind == "w" else v * 0.5 * offset_sigma
-        out[name] = np.ascontiguousarray(v, dtype=np.float32)
-    return out
-
-
-_SCHEMA_CACHE: Dict[str, "OrderedDict"] = {}
-
-
-def schema_cache(cfg: Config):
-    key = f"{cfg.name}:{cfg.embed_dim}:{cfg.depths}:{cfg.num_heads}"
-    if key not in _SCHEMA_CACHE:
-        _SCHEMA_CACHE[key] = schema(cfg)
-    return _SCHEMA_CACHE[key]
+def make_weights(cfg: Config, seed: int = 0, weight_set: str = "A", offset_sigma: float = 2.0) -> Dict[str, np.ndarray]:
+    """float32 numpy tensors for every key of `schema(cfg)`; values from the package's seeded generator
+    (candle_birefnet_b200/synth.py) so tests, bench and smoke runs share one definition of "random-init"."""
+    from candle_birefnet_b200.synth import synthetic_weights
+    return synthetic_weights({k: v[0] for k, v in schema(cfg).items()}, seed, weight_set, offset_sigma)
 
 
 def as_torch(weights: Dict[str, np.ndarray], dtype=None):
@@ -156,9 +118,8 @@ def as_torch(weights: Dict[str, np.ndarray], dtype=None):
 
 
 def make_input(b: int, h: int, w: int, seed: int = 1234) -> np.ndarray:
-    """x ~ N(0,1), the distribution the reference's benches use (examples/bench_inference.rs:30)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    return rng.standard_normal((b, 3, h, w)).astype(np.float32)
+    from candle_birefnet_b200.synth import synthetic_input
+    return synthetic_input(b, h, w, seed)
 
 
 def count_params(cfg: Config) -> Tuple[int, int]:

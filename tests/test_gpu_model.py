@@ -1,0 +1,160 @@
+"""GPU parity tests of the whole path through the C ABI: backbone, decoder and forward_logits against the oracle.
+
+Tolerances are the north_star's: fp32 path max |dlogit| <= 1e-3; bf16 path max |dsigmoid| <= 1e-2 and IoU@0.5 >= 0.999.
+"""
+import numpy as np
+import pytest
+import torch
+
+import candle_birefnet_b200 as cb
+from oracle import birefnet_ref as R
+from oracle.make_weights import as_torch, make_input, make_weights
+
+pytestmark = pytest.mark.gpu
+
+
+def py_cfg(cfg: R.Config, precision: str, deform_mode: str) -> cb.BiRefNetConfig:
+    return cb.BiRefNetConfig(swin=cb.SwinConfig(embed_dim=cfg.embed_dim, depths=tuple(cfg.depths),
+                                               num_heads=tuple(cfg.num_heads)),
+                             precision=precision, deform_mode=deform_mode)
+
+
+def iou(a, b):
+    a, b = a > 0.5, b > 0.5
+    u = np.logical_or(a, b).sum()
+    return 1.0 if u == 0 else float(np.logical_and(a, b).sum() / u)
+
+
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+@pytest.fixture(scope="module")
+def mini_models(mini_cfg, mini_weights_A, mini_weights_B):
+    ms = {k: cb.BiRefNet.new(py_cfg(mini_cfg, "fp32", "deformable"), w) for k, w in (("A", mini_weights_A), ("B", mini_weights_B))}
+    yield ms
+    for m in ms.values():
+        m.close()
+
+
+def check_logits(got, exp, precision):
+    if precision == "fp32":
+        err = np.abs(got - exp).max()
+        assert err <= 1e-3, f"fp32 path max |dlogit| = {err}"
+    else:
+        ds = np.abs(sigmoid(got) - sigmoid(exp)).max()
+        i = iou(sigmoid(got), sigmoid(exp))
+        assert ds <= 1e-2 and i >= 0.999, f"bf16 path max |dsigmoid| = {ds}, IoU = {i}"
+
+
+def test_schema_matches_oracle(mini_models, mini_cfg):
+    from oracle.make_weights import schema
+    sc = {k: tuple(v[0]) for k, v in schema(mini_cfg).items()}
+    assert mini_models["A"].tensor_schema() == sc
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("hw", [(128, 160), (256, 256)])
+def test_backbone_mini(mini_models, mini_cfg, mini_weights_A, precision, hw):
+    m = mini_models["A"]
+    m.set_precision(precision)
+    x = make_input(2, hw[0], hw[1], seed=5)
+    got = m.backbone_forward(x)
+    exp = R.swin_forward(torch.from_numpy(x), as_torch(mini_weights_A), mini_cfg)
+    for i in range(4):
+        e = exp[i].numpy()
+        err = np.abs(got[i] - e).max()
+        assert got[i].shape == e.shape
+        assert err < (1e-3 if precision == "fp32" else 0.15), (i, err)   # LN-normalised features, |x| ~ 3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("wset,mode", [("A", "cpu_fallback"), ("A", "deformable"), ("B", "deformable"), ("B", "cpu_fallback")])
+def test_forward_logits_mini(mini_models, mini_cfg, mini_weights_A, mini_weights_B, precision, wset, mode):
+    """weight-set A: deformable == cpu_fallback == the reference's candle-CPU forward;
+    weight-set B: random offsets, each mode against the same mode of the oracle."""
+    m = mini_models[wset]
+    m.set_precision(precision)
+    m.set_deform_mode(mode)
+    x = make_input(2, 128, 192, seed=11)
+    got = m.forward_logits(x)
+    w = as_torch(mini_weights_A if wset == "A" else mini_weights_B)
+    exp = R.forward_logits(torch.from_numpy(x), w, mini_cfg, mode).numpy()
+    check_logits(got, exp, precision)
+    prob = m.forward(x)
+    assert np.abs(prob - sigmoid(got)).max() < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_golden_fixture(mini_models, precision):
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "mini_64x96.npz")
+    m = mini_models["B"]
+    m.set_precision(precision)
+    x = make_input(1, 64, 96, seed=7)
+    for mode in ("cpu_fallback", "deformable"):
+        m.set_deform_mode(mode)
+        check_logits(m.forward_logits(x), g["logits_" + mode], precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_decoder_mini(mini_models, mini_cfg, mini_weights_B, precision):
+    m = mini_models["B"]
+    m.set_precision(precision)
+    m.set_deform_mode("deformable")
+    x = torch.from_numpy(make_input(1, 128, 128, seed=2))
+    w = as_torch(mini_weights_B)
+    x1, x2, x3, x4 = R.features(x, w, mini_cfg)
+    exp = R.decoder_forward(x, x1, x2, x3, R.basic_dec_blk(x4, w, "squeeze_module.0", "deformable"), w, "deformable").numpy()
+    got = m.decoder_forward(x.numpy(), x1.numpy(), x2.numpy(), x3.numpy(), x4.numpy())
+    check_logits(got, exp, precision)
+
+
+def test_batch_independence_and_microbatch(mini_models):
+    """Image sharding contract: a batch result equals the per-image results bit for bit."""
+    m = mini_models["A"]
+    m.set_precision("bf16")
+    m.set_deform_mode("deformable")
+    x = make_input(3, 64, 64, seed=9)
+    full = m.forward_logits(x)
+    for b in range(3):
+        assert np.array_equal(full[b:b + 1], m.forward_logits(x[b:b + 1]))
+
+
+def test_device_pointer_entry(mini_models):
+    m = mini_models["A"]
+    m.set_precision("bf16")
+    x = make_input(2, 64, 96, seed=4)
+    host = m.forward_logits(x)
+    xd = torch.from_numpy(x).cuda()
+    out = m.forward_logits(xd)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), host)
+
+
+def test_rejects_bad_shapes(mini_models):
+    m = mini_models["A"]
+    with pytest.raises(cb.BrnError) as e:
+        m.forward_logits(np.zeros((1, 3, 100, 128), np.float32))
+    assert e.value.status == 5
+
+
+def test_missing_and_unknown_tensor(mini_cfg, mini_weights_A):
+    w = dict(mini_weights_A)
+    w.pop("bb.norm2.weight")
+    with pytest.raises(cb.BrnError) as e:
+        cb.BiRefNet.new(py_cfg(mini_cfg, "bf16", "deformable"), w)
+    assert e.value.status == 3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_logits_swin_l_512(precision):
+    """The real architecture (Swin-L, 220 M params) at 512x512, weight-set A: == the reference's candle-CPU forward."""
+    cfg = R.Config.swin_l()
+    wnp = make_weights(cfg, seed=0, weight_set="A")
+    m = cb.BiRefNet.new(py_cfg(cfg, precision, "deformable"), wnp)
+    x = make_input(1, 512, 512, seed=1234)
+    got = m.forward_logits(x)
+    exp = R.forward_logits(torch.from_numpy(x), as_torch(wnp), cfg, "cpu_fallback").numpy()
+    m.close()
+    check_logits(got, exp, precision)

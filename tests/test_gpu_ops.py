@@ -1,0 +1,115 @@
+"""GPU parity tests, operator level, through the C ABI (ctypes) against the oracle's statement of each op.
+
+fp32 path (SIMT FMA): tolerance 1e-4 relative to the output scale.
+bf16 path (tcgen05): the oracle is evaluated on bf16-rounded operands in fp64, so what remains is accumulation
+order (fp32) and the bf16 rounding of stored activations; tolerances are written at each test.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import candle_birefnet_b200 as cb
+from oracle import birefnet_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def bf16r(a):
+    return torch.from_numpy(np.asarray(a, dtype=np.float32)).bfloat16().float().numpy()
+
+
+def relerr(got, exp):
+    return float(np.abs(got - exp).max() / (np.abs(exp).max() + 1e-12))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 192, 192), (1000, 576, 192), (257, 48, 96), (144, 3, 64),
+                                    (5184, 2304, 768)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_linear(M, N, K, precision):
+    rng = np.random.default_rng(M + N + K)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    got = cb.ops.linear(a, w, b, precision=precision)
+    if precision == "bf16":
+        exp = bf16r(a).astype(np.float64) @ bf16r(w).astype(np.float64).T + b
+        tol = 2e-5
+    else:
+        exp = a.astype(np.float64) @ w.astype(np.float64).T + b
+        tol = 2e-5
+    assert relerr(got, exp) < tol
+
+
+@pytest.mark.parametrize("act", [1, 2])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_linear_epilogues(act, precision):
+    rng = np.random.default_rng(act)
+    M, N, K = 500, 256, 128
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    res = rng.standard_normal((M, N)).astype(np.float32)
+    got = cb.ops.linear(a, w, b, residual=res, act=act, precision=precision)
+    aa, ww = (bf16r(a), bf16r(w)) if precision == "bf16" else (a, w)
+    z = torch.from_numpy(aa.astype(np.float64) @ ww.astype(np.float64).T + b)
+    z = F.relu(z) if act == 1 else F.gelu(z)      # exact-erf GELU (src/swin.rs:105)
+    exp = z.numpy() + res
+    assert relerr(got, exp) < 2e-5
+
+
+@pytest.mark.parametrize("C,O,k,H,W", [(64, 64, 3, 32, 32), (64, 256, 1, 16, 24), (64, 147, 7, 16, 16), (224, 64, 3, 64, 64),
+                                        (48, 64, 3, 20, 12), (128, 16, 3, 8, 8)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv2d(C, O, k, H, W, precision):
+    rng = np.random.default_rng(C + O + k)
+    x = rng.standard_normal((2, C, H, W)).astype(np.float32)
+    w = (rng.standard_normal((O, C, k, k)) / np.sqrt(C * k * k)).astype(np.float32)
+    b = rng.standard_normal(O).astype(np.float32)
+    got = cb.ops.conv2d(x, w, b, act=1, precision=precision)
+    xx, ww = (bf16r(x), bf16r(w)) if precision == "bf16" else (x, w)
+    exp = F.relu(F.conv2d(torch.from_numpy(xx).double(), torch.from_numpy(ww).double(), torch.from_numpy(b).double(),
+                          padding=k // 2)).numpy()
+    assert relerr(got, exp) < 2e-5
+
+
+@pytest.mark.parametrize("k,sigma", [(1, 0.0), (1, 2.0), (3, 0.5), (3, 8.0), (7, 2.0)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_deform_conv2d(k, sigma, precision):
+    import torchvision
+    rng = np.random.default_rng(k * 10 + int(sigma))
+    B, C, H, W, O = 2, 64, 20, 28, 256
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = (rng.standard_normal((O, C, k, k)) / np.sqrt(C * k * k)).astype(np.float32)
+    off = (rng.standard_normal((B, 2 * k * k, H, W)) * sigma).astype(np.float32)   # incl. far out-of-bounds samples
+    msk = rng.uniform(0, 2, (B, k * k, H, W)).astype(np.float32)
+    got = cb.ops.deform_conv2d(x, off, msk, w, precision=precision)
+    xx, ww = (bf16r(x), bf16r(w)) if precision == "bf16" else (x, w)
+    exp = torchvision.ops.deform_conv2d(torch.from_numpy(xx).double(), torch.from_numpy(off).double(),
+                                        torch.from_numpy(ww).double(), None, padding=k // 2,
+                                        mask=torch.from_numpy(msk).double()).numpy()
+    # bf16 path: the gathered, modulated samples are rounded to bf16 before the MMA
+    assert relerr(got, exp) < (1e-2 if precision == "bf16" else 1e-4)
+
+
+@pytest.mark.parametrize("nimg,hp,wp,heads,shift", [(1, 24, 36, 2, 0), (2, 24, 36, 2, 6), (1, 12, 12, 6, 6), (1, 72, 72, 24, 6),
+                                                     (1, 264, 264, 6, 6)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_window_attention(nimg, hp, wp, heads, shift, precision):
+    """softmax(scale q k^T + bias (+ -100 region mask)) v, the plain chain of examples/test_flash_bias.rs:30-36."""
+    rng = np.random.default_rng(hp + heads + shift)
+    nw = (hp // 12) * (wp // 12)
+    C = heads * 32
+    qkv = rng.standard_normal((nimg * nw, 144, 3 * C)).astype(np.float32)
+    bias = (rng.standard_normal((heads, 144, 144)) * 0.5).astype(np.float32)
+    got = cb.ops.window_attention(qkv, bias, hp, wp, shift, precision=precision)
+    t = torch.from_numpy(bf16r(qkv) if precision == "bf16" else qkv).double()
+    q, k, v = [t[..., i * C:(i + 1) * C].reshape(nimg * nw, 144, heads, 32).permute(0, 2, 1, 3) for i in range(3)]
+    s = (q * 32 ** -0.5) @ k.transpose(-1, -2) + torch.from_numpy(bias).double()
+    if shift:
+        m = R.create_attention_mask(hp, wp, 12, 6, torch.float64)
+        s = (s.reshape(nimg, nw, heads, 144, 144) + m[None, :, None]).reshape(nimg * nw, heads, 144, 144)
+    exp = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(nimg * nw, 144, C).numpy()
+    err = np.abs(got - exp).max()
+    # bf16: q (scaled), bias, P and the output are rounded to bf16 (8 mantissa bits); |out| <= ~1
+    assert err < (3e-2 if precision == "bf16" else 2e-5), err
