@@ -14,7 +14,7 @@ LIB_PATH = HERE / "libbirefnet_b200.so"
 HEADER = HERE.parent / "include" / "birefnet_b200.h"
 
 OK = 0
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 DEFORM_CPU_FALLBACK, DEFORM_DEFORMABLE = 0, 1
 F32, BF16, F16 = 0, 1, 2
 
@@ -22,7 +22,8 @@ F32, BF16, F16 = 0, 1, 2
 class BrnConfig(C.Structure):
     _fields_ = [("embed_dim", C.c_int32), ("depths", C.c_int32 * 4), ("num_heads", C.c_int32 * 4),
                 ("window_size", C.c_int32), ("mlp_ratio", C.c_int32), ("patch_size", C.c_int32),
-                ("precision", C.c_int32), ("deform_mode", C.c_int32), ("micro_batch", C.c_int32)]
+                ("precision", C.c_int32), ("deform_mode", C.c_int32), ("micro_batch", C.c_int32),
+                ("decoder_fp16", C.c_int32)]
 
 
 class BrnError(RuntimeError):

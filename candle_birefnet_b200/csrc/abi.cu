@@ -44,6 +44,7 @@ void brn_config_swin_l(brn_config* cfg) {
   for (int i = 0; i < 4; ++i) { cfg->depths[i] = d[i]; cfg->num_heads[i] = h[i]; }
   cfg->window_size = 12; cfg->mlp_ratio = 4; cfg->patch_size = 4;
   cfg->precision = BRN_PREC_BF16; cfg->deform_mode = BRN_DEFORM_DEFORMABLE; cfg->micro_batch = 0;
+  cfg->decoder_fp16 = 1;
 }
 
 brn_status brn_model_create(const brn_config* cfg, int device, brn_model** out) {
@@ -189,7 +190,7 @@ struct Scratch {
 };
 
 static LaunchCtx make_ctx(Scratch& s, int precision) {
-  LaunchCtx c; c.stream = s.stream; c.precision = precision; c.dry = false; c.launches = nullptr;
+  LaunchCtx c; c.stream = s.stream; c.precision = precision ? BRN_PREC_BF16 : BRN_PREC_FP32; c.dry = false; c.launches = nullptr;
   const char* v = getenv("BRN_FORCE_SIMT");
   c.force_simt = v && v[0] && v[0] != '0';
   return c;
@@ -201,8 +202,8 @@ brn_status brn_linear(int device, int precision, const float* a, const float* w,
     BRN_CHECK(a && w && out && M > 0 && N > 0 && K > 0, 1, "brn_linear: bad argument");
     Scratch s(device);
     LaunchCtx ctx = make_ctx(s, precision);
-    const int AD = precision == BRN_PREC_BF16 ? BF16 : F32;
-    LayerW L = make_layer_standalone(N, K, 1, 1, w, bias, s.ptrs);
+    const int AD = precision == BRN_PREC_FP16 ? F16 : precision == BRN_PREC_BF16 ? BF16 : F32;
+    LayerW L = make_layer_standalone(N, K, 1, 1, w, bias, s.ptrs, AD == F16 ? F16 : BF16);
     View a32 = make_view(s.put(a, (size_t)M * K), F32, 1, 1, M, K);
     View ax = a32;
     if (AD == BF16) { ax = make_view(s.alloc((size_t)M * K * 2), BF16, 1, 1, M, K); glue_copy_cast(ctx, a32, ax); }
@@ -221,8 +222,8 @@ brn_status brn_conv2d(int device, int precision, const float* x, const float* we
     BRN_CHECK(x && weight && out && B > 0 && C > 0 && H > 0 && W > 0 && O > 0 && (k & 1), 1, "brn_conv2d: bad argument");
     Scratch s(device);
     LaunchCtx ctx = make_ctx(s, precision);
-    const int AD = precision == BRN_PREC_BF16 ? BF16 : F32;
-    LayerW L = make_layer_standalone(O, C, k, k, weight, bias, s.ptrs);
+    const int AD = precision == BRN_PREC_FP16 ? F16 : precision == BRN_PREC_BF16 ? BF16 : F32;
+    LayerW L = make_layer_standalone(O, C, k, k, weight, bias, s.ptrs, AD == F16 ? F16 : BF16);
     float* dx = s.put(x, (size_t)B * C * H * W);
     View xv = make_view(s.alloc((size_t)B * C * H * W * dsize(AD)), AD, B, H, W, C);
     glue_nchw_to_nhwc(ctx, dx, B, C, H, W, xv);
@@ -243,9 +244,9 @@ brn_status brn_deform_conv2d(int device, int precision, const float* x, const fl
     BRN_CHECK(x && offset && mask && weight && out && (k & 1), 1, "brn_deform_conv2d: bad argument");
     Scratch s(device);
     LaunchCtx ctx = make_ctx(s, precision);
-    const int AD = precision == BRN_PREC_BF16 ? BF16 : F32;
+    const int AD = precision == BRN_PREC_FP16 ? F16 : precision == BRN_PREC_BF16 ? BF16 : F32;
     const int taps = k * k;
-    LayerW L = make_layer_standalone(O, C, k, k, weight, bias, s.ptrs);
+    LayerW L = make_layer_standalone(O, C, k, k, weight, bias, s.ptrs, AD == F16 ? F16 : BF16);
     float* dx = s.put(x, (size_t)B * C * H * W);
     View xv = make_view(s.alloc((size_t)B * C * H * W * dsize(AD)), AD, B, H, W, C);
     glue_nchw_to_nhwc(ctx, dx, B, C, H, W, xv);
@@ -272,7 +273,7 @@ brn_status brn_window_attention(int device, int precision, const float* qkv, con
     BRN_CHECK(n_windows % nw == 0, 5, "n_windows must be a multiple of (hp/12)*(wp/12)");
     Scratch s(device);
     LaunchCtx ctx = make_ctx(s, precision);
-    const int AD = precision == BRN_PREC_BF16 ? BF16 : F32;
+    const int AD = precision == BRN_PREC_FP16 ? F16 : precision == BRN_PREC_BF16 ? BF16 : F32;
     const int C = heads * 32;
     const size_t rows = (size_t)n_windows * 144;
     // fold the q scale the way finalize does (src/swin.rs:278)

@@ -16,14 +16,16 @@
 // Bound: MUFU (144*144 exp per unit) -- see DESIGN.md; tensor work per unit is ~600 cycles vs ~1300 of exp.
 #include <cuda.h>
 
+#include <cstdio>
+
 #include "brn_common.h"
 #include "device_utils.cuh"
 #include "tc_ptx.cuh"
 
 namespace brn {
 
-CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                           const uint32_t* box, CUtensorMapSwizzle swz);
+CUtensorMap make_tmap_16(const void* base, int dt, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, CUtensorMapSwizzle swz);
 int device_sm_count();
 
 constexpr int AT_THREADS = 192;
@@ -275,12 +277,14 @@ void tc_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   uint64_t dims[2] = {(uint64_t)3 * p.C, rows};
   uint64_t str[1] = {(uint64_t)a.qkv.ld * 2};
   uint32_t box[2] = {32, 144};
-  CUtensorMap tm = make_tmap_bf16(a.qkv.p, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+  CUtensorMap tm = make_tmap_16(a.qkv.p, BF16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
   cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
   const int sms = device_sm_count();
   int per_head = std::max(1, sms / a.heads);
   per_head = std::min(per_head, a.n_windows);
-  KScope ks(ctx, KC_ATTN_TC, 4.0 * 144 * 144 * 32 * (double)a.n_windows * a.heads);
+  char desc[96] = "";
+  if (ctx.kt) snprintf(desc, sizeof desc, "windows=%d heads=%d shift=%d grid=%d", a.n_windows, a.heads, a.shift, a.heads * per_head);
+  KScope ks(ctx, KC_ATTN_TC, 4.0 * 144 * 144 * 32 * (double)a.n_windows * a.heads, 0, desc);
   tc_attn_kernel<<<a.heads * per_head, AT_THREADS, AT_SMEM, ctx.stream>>>(tm, p);
   BRN_CUDA(cudaGetLastError());
 }

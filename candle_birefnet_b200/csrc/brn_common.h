@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdexcept>
 #include <string>
@@ -27,7 +28,10 @@ struct Error : std::runtime_error {
     if (!(cond)) throw ::brn::Error((status), (msg));       \
   } while (0)
 
-enum DType { F32 = 0, BF16 = 1 };
+// Activation / operand element types.  The 16-bit tensor-core path uses bf16 in the backbone (fp32 residual stream,
+// wide dynamic range) and fp16 in the squeeze module + decoder (BN-normalised, O(1) activations; 3 more mantissa
+// bits are what the IoU >= 0.999 tolerance on near-zero logits needs, see DESIGN.md "precision").
+enum DType { F32 = 0, BF16 = 1, F16 = 2 };
 inline size_t dsize(int dt) { return dt == F32 ? 4 : 2; }
 
 // NHWC activation view.  Element (b,y,x,c) lives at p + (((b*H+y)*W+x)*ld + c) elements.  Token matrices
@@ -60,7 +64,8 @@ struct LayerW {
   int kh = 1, kw = 1;
   int cin_pad = 0;  // Cin rounded up to 64 (K pitch per tap of the bf16 matrix)
   float* w32 = nullptr;          // [N][kh*kw][Cin]      fp32 (SIMT path)
-  __nv_bfloat16* w16 = nullptr;  // [N][kh*kw][cin_pad]  bf16, zero padded (tcgen05 path)
+  void* w16 = nullptr;           // [N][kh*kw][cin_pad]  bf16 or fp16 (w16_dt), zero padded (tcgen05 path)
+  int w16_dt = BF16;
   float* bias = nullptr;         // [N] fp32 or null
   int taps() const { return kh * kw; }
 };
@@ -113,8 +118,15 @@ struct AttnArgs {
 // bench.py for the roofline of the dominant kernel and the kernel-time shares.  Off on the timed throughput path.
 enum KClass { KC_GEMM_TC = 0, KC_ATTN_TC, KC_DEFORM_TC, KC_GEMM_SIMT, KC_ATTN_SIMT, KC_LN, KC_GLUE, KC_COUNT };
 struct KTimer {
-  struct Rec { int cls; cudaEvent_t e0, e1; double flops; double bytes; };
+  struct Rec { int cls; cudaEvent_t e0, e1; double flops; double bytes; std::string desc; };
   std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;   // events are created once and reused: no cudaEventCreate on the launch path
+  size_t next = 0;
+  cudaEvent_t get() {
+    if (next == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[next++];
+  }
+  void reset() { recs.clear(); next = 0; }
 };
 
 struct LaunchCtx {
@@ -129,10 +141,9 @@ struct LaunchCtx {
 struct KScope {
   const LaunchCtx& c;
   cudaEvent_t e1 = nullptr;
-  KScope(const LaunchCtx& ctx, int cls, double flops, double bytes = 0) : c(ctx) {
+  KScope(const LaunchCtx& ctx, int cls, double flops, double bytes = 0, const char* desc = nullptr) : c(ctx) {
     if (!c.kt || c.dry) return;
-    KTimer::Rec r{cls, nullptr, nullptr, flops, bytes};
-    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    KTimer::Rec r{cls, c.kt->get(), c.kt->get(), flops, bytes, desc ? desc : ""};
     cudaEventRecord(r.e0, c.stream);
     e1 = r.e1;
     c.kt->recs.push_back(r);
@@ -175,9 +186,10 @@ void glue_aspp_pool_bias(const LaunchCtx&, const float* sums, int B, int HW, con
                          float* out /*[B][64]*/);
 void glue_gate(const LaunchCtx&, View p, View g16, const float* w16, float b0);
 void glue_dot1(const LaunchCtx&, View p, const float* w, float* out /*[rows]*/);
-void glue_final(const LaunchCtx&, const float* x_nchw, int B, int H, int W, const float* w1 /*[64][27]*/,
-                const float* b1 /*[64]*/, const float* wc /*[64][9]*/, float bc, const float* q, int qh, int qw,
-                float* out, int apply_sigmoid);
+void glue_final(const LaunchCtx&, const float* x_nchw, int B, int H, int W, const float* tab /*final_kernel.cu*/,
+                const float* q, int qh, int qw, float* out, int apply_sigmoid);
+void build_final_table(const float* w1 /*[64][27]*/, const float* b1 /*[64]*/, const double* wc /*[64][9]*/, double bc,
+                       float* tab /*[336]*/);
 void glue_copy_cast(const LaunchCtx&, View in, View out);
 void glue_sigmoid(const LaunchCtx&, float* p, long long n);
 

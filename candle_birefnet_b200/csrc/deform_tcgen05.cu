@@ -14,6 +14,8 @@
 // Bound: gather (L1/L2 bandwidth of 4 corners x 128 B per pixel-tap) vs tensor pipe 512 cycles per tap-tile.
 #include <cuda.h>
 
+#include <cstdio>
+
 #include "brn_common.h"
 #include "device_utils.cuh"
 #include "tc_epilogue.cuh"
@@ -21,8 +23,8 @@
 
 namespace brn {
 
-CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                           const uint32_t* box, CUtensorMapSwizzle swz);
+CUtensorMap make_tmap_16(const void* base, int dt, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, CUtensorMapSwizzle swz);
 int device_sm_count();
 EpiP make_epi(int N, const float* bias, int bias_bstride, int act, int act_from, const View& res, const View& out);
 
@@ -34,18 +36,19 @@ constexpr int DF_B_BYTES = 256 * 128;
 constexpr int DF_SMEM = DF_STAGES * (DF_A_BYTES + DF_B_BYTES) + 256 + 1024;
 
 struct DeformP {
-  const __nv_bfloat16* x; int ldx; int B, H, W;
+  const uint16_t* x; int ldx; int B, H, W;   // bf16 or fp16 elements (xdt)
+  int xdt;
   const float* om; int ldom;
   int k, pad, taps;
   long long M; int m_tiles; int BN;
   EpiP epi;
 };
 
-__device__ __forceinline__ void fma_bf16x8(float (&acc)[8], const uint4& v, float w) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+__device__ __forceinline__ void fma_16x8(float (&acc)[8], const uint4& v, float w, int dt) {
+  const uint32_t* h = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    float2 f = __bfloat1622float2(h[t]);
+    float2 f = unpack16x2(h[t], dt);
     acc[2 * t] = fmaf(w, f.x, acc[2 * t]);
     acc[2 * t + 1] = fmaf(w, f.y, acc[2 * t + 1]);
   }
@@ -85,7 +88,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
       const bool row_ok = m < p.M;
       int b = 0, y = 0, x = 0;
       if (row_ok) { b = (int)(m / HW); int rem = (int)(m - (long long)b * HW); y = rem / p.W; x = rem - y * p.W; }
-      const __nv_bfloat16* xb = p.x + (long long)b * HW * p.ldx + half * 32;
+      const uint16_t* xb = p.x + (long long)b * HW * p.ldx + half * 32;
       const float* o = p.om + m * p.ldom;
       for (int tap = 0; tap < p.taps; ++tap) {
         float acc[4][8];
@@ -113,7 +116,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[j] = __ldg(src + j);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) fma_bf16x8(acc[j], v[j], wgt[cnr]);
+              for (int j = 0; j < 4; ++j) fma_16x8(acc[j], v[j], wgt[cnr], p.xdt);
             }
           }
         }
@@ -123,8 +126,8 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
         for (int j = 0; j < 4; ++j) {
           const int chunk = (half * 4 + j) ^ (r & 7);
           *reinterpret_cast<uint4*>(rowp + chunk * 16) =
-              make_uint4(pack_bf16x2(acc[j][0], acc[j][1]), pack_bf16x2(acc[j][2], acc[j][3]),
-                         pack_bf16x2(acc[j][4], acc[j][5]), pack_bf16x2(acc[j][6], acc[j][7]));
+              make_uint4(pack16x2(acc[j][0], acc[j][1], p.xdt), pack16x2(acc[j][2], acc[j][3], p.xdt),
+                         pack16x2(acc[j][4], acc[j][5], p.xdt), pack16x2(acc[j][6], acc[j][7], p.xdt));
         }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&full[stage]);
@@ -135,7 +138,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
     if (ptx::elect_one()) {
       // ===== weight TMA + MMA issuer =====
       ptx::prefetch_tmap(&tmB);
-      const uint32_t idesc = ptx::make_idesc_bf16(128, p.BN, 0, 0);
+      const uint32_t idesc = ptx::make_idesc_16(128, p.BN, 0, 0, p.xdt == BF16 ? 1u : 0u);
       const uint32_t b_bytes = p.BN * 128;
       const int n_my_tiles = blockIdx.x < p.m_tiles ? (p.m_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
       const long long total = (long long)n_my_tiles * p.taps;
@@ -202,7 +205,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
 }
 
 bool tc_deform_supported(const DeformArgs& a) {
-  return a.w && a.w->w16 && a.x.dt == BF16 && a.x.C == 64 && a.w->cin_pad == 64 && a.x.ld % 8 == 0 &&
+  return a.w && a.w->w16 && (a.x.dt == BF16 || a.x.dt == F16) && a.x.dt == a.w->w16_dt && a.x.C == 64 && a.w->cin_pad == 64 && a.x.ld % 8 == 0 &&
          (((uintptr_t)a.x.p) & 15) == 0 && a.w->N <= 256 && a.om.dt == F32;
 }
 
@@ -211,7 +214,7 @@ void tc_deform(const LaunchCtx& ctx, const DeformArgs& a) {
   if (ctx.dry) return;
   const LayerW& w = *a.w;
   DeformP p{};
-  p.x = (const __nv_bfloat16*)a.x.p; p.ldx = a.x.ld; p.B = a.x.B; p.H = a.x.H; p.W = a.x.W;
+  p.x = (const uint16_t*)a.x.p; p.xdt = a.x.dt; p.ldx = a.x.ld; p.B = a.x.B; p.H = a.x.H; p.W = a.x.W;
   p.om = (const float*)a.om.p; p.ldom = a.om.ld;
   p.k = w.kh; p.pad = w.kh / 2; p.taps = w.taps();
   p.M = a.x.rows(); p.m_tiles = (int)((p.M + 127) / 128);
@@ -222,10 +225,12 @@ void tc_deform(const LaunchCtx& ctx, const DeformArgs& a) {
   uint64_t bdims[2] = {ktot, (uint64_t)w.N};
   uint64_t bstr[1] = {ktot * 2};
   uint32_t bbox[2] = {64, (uint32_t)p.BN};
-  CUtensorMap tmB = make_tmap_bf16(w.w16, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tmB = make_tmap_16(w.w16, w.w16_dt, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B);
   cudaFuncSetAttribute(tc_deform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM);
   const int grid = std::min(p.m_tiles, device_sm_count());
-  KScope ks(ctx, KC_DEFORM_TC, 2.0 * (double)p.M * w.N * w.taps() * 64, (double)p.M * w.taps() * 4 * 128);
+  char desc[96] = "";
+  if (ctx.kt) snprintf(desc, sizeof desc, "M=%lld N=%d k=%d", p.M, w.N, p.k);
+  KScope ks(ctx, KC_DEFORM_TC, 2.0 * (double)p.M * w.N * w.taps() * 64, (double)p.M * w.taps() * 4 * 128, desc);
   tc_deform_kernel<<<grid, DF_THREADS, DF_SMEM, ctx.stream>>>(tmB, p);
   BRN_CUDA(cudaGetLastError());
 }

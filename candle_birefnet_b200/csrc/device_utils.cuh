@@ -25,6 +25,18 @@ __host__ __device__ __forceinline__ long long window_row_to_token(long long m, i
   return (b * h + r) * (long long)w + c;
 }
 
+// element load / store by runtime dtype tag (F32 / BF16 / F16)
+__device__ __forceinline__ float ld_elem(const void* p, int dt, long long i) {
+  if (dt == F32) return ((const float*)p)[i];
+  if (dt == BF16) return __bfloat162float(((const __nv_bfloat16*)p)[i]);
+  return __half2float(((const __half*)p)[i]);
+}
+__device__ __forceinline__ void st_elem(void* p, int dt, long long i, float v) {
+  if (dt == F32) ((float*)p)[i] = v;
+  else if (dt == BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16(v);
+  else ((__half*)p)[i] = __float2half_rn(v);
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 __device__ __forceinline__ float apply_act(float v, int act, int n, int act_from) {

@@ -1,0 +1,123 @@
+// Fused final layer of BiRefNetDecoder::forward (src/birefnet.rs:320,372-375 + SimpleConvs, src/decoder.rs:50-56):
+//
+//   logits = conv_out1( cat( up(p1), ipt_blk1(x) ) )
+//          = up( w_p . p1 )  +  sum_o w_i[o] * conv_out_o( conv1(x) )  +  b          (bilinear up-sampling is linear)
+//
+// ipt_blk1 is two stacked 3x3 convs with NO activation in between, so for a pixel whose 3x3 neighbourhood lies inside
+// the image the second term collapses exactly to one 5x5 convolution of the 3-channel input (75 MACs instead of
+// 9*64*27 + 64*9 = 16,128).  On the 1-pixel image border the intermediate 64-channel map is ZERO-padded (it is not
+// the conv of a padded input), so there the sum runs over the valid intermediate taps only:
+//   out(y,x) = b + up(q)(y,x) + sum_{(i,j) valid} ( Bt[i,j] + sum_{ci,ky,kx} M[i,j][ci,ky,kx] x~[ci, y+i+ky-2, x+j+kx-2] )
+// with M[i,j] = sum_c Wc[c,i,j] w1[c], Bt[i,j] = sum_c Wc[c,i,j] b1[c], Wc = sum_o w_i[o] conv_out.weight[o] -- all
+// folded on the host in double at finalize.  The 240-channel full-resolution tensor (960 MiB fp32 per image) and the
+// 64-channel intermediate never exist.  HBM-bound: 12 B in + 4 B out per pixel.
+#include "brn_common.h"
+#include "device_utils.cuh"
+
+namespace brn {
+
+// table layout (floats): [0,75) K5[ci][u][v] | [75,318) M[ij][ci*9+ky*3+kx] | [318,327) Bt[ij] | 327 b | 328 b + sum Bt
+constexpr int FIN_TAB = 336;
+constexpr int FT_W = 32, FT_H = 8;
+
+__device__ __forceinline__ void fin_bilin(int dst, int in, int out, int& i0, int& i1, float& l) {
+  float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  float s = scale * dst;
+  i0 = min((int)s, in - 1);
+  i1 = min(i0 + 1, in - 1);
+  l = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(FT_W * FT_H) final_kernel(const float* __restrict__ x, int H, int W,
+                                                            const float* __restrict__ tab, const float* __restrict__ q,
+                                                            int qh, int qw, float* __restrict__ out, int apply_sigmoid) {
+  __shared__ float xin[3][FT_H + 4][FT_W + 4];
+  __shared__ float st[FIN_TAB];
+  const int b = blockIdx.z, ty0 = blockIdx.y * FT_H, tx0 = blockIdx.x * FT_W, tid = threadIdx.x;
+  for (int i = tid; i < FIN_TAB; i += FT_W * FT_H) st[i] = tab[i];
+  for (int i = tid; i < 3 * (FT_H + 4) * (FT_W + 4); i += FT_W * FT_H) {
+    const int c = i / ((FT_H + 4) * (FT_W + 4)), r = i % ((FT_H + 4) * (FT_W + 4)), yy = r / (FT_W + 4), xx = r % (FT_W + 4);
+    const int gy = ty0 + yy - 2, gx = tx0 + xx - 2;
+    xin[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(x + ((long long)(b * 3 + c) * H + gy) * W + gx) : 0.f;
+  }
+  __syncthreads();
+  const int ly = tid / FT_W, lx = tid % FT_W;
+  const int gy = ty0 + ly, gx = tx0 + lx;
+  if (gy >= H || gx >= W) return;
+  float acc;
+  if (gy >= 1 && gy <= H - 2 && gx >= 1 && gx <= W - 2) {
+    acc = st[328];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int u = 0; u < 5; ++u)
+#pragma unroll
+        for (int v = 0; v < 5; ++v) acc = fmaf(st[ci * 25 + u * 5 + v], xin[ci][ly + u][lx + v], acc);
+  } else {
+    acc = st[327];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        const int py = gy + i - 1, px = gx + j - 1;
+        if (py < 0 || py >= H || px < 0 || px >= W) continue;
+        const float* m = &st[75 + (i * 3 + j) * 27];
+        float s = st[318 + i * 3 + j];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) s = fmaf(m[ci * 9 + ky * 3 + kx], xin[ci][ly + i + ky][lx + j + kx], s);
+        acc += s;
+      }
+  }
+  int y0, y1, x0, x1; float fy, fx;
+  fin_bilin(gy, qh, H, y0, y1, fy);
+  fin_bilin(gx, qw, W, x0, x1, fx);
+  const float* qb = q + (long long)b * qh * qw;
+  const float up = (1.f - fy) * ((1.f - fx) * __ldg(qb + y0 * qw + x0) + fx * __ldg(qb + y0 * qw + x1)) +
+                   fy * ((1.f - fx) * __ldg(qb + y1 * qw + x0) + fx * __ldg(qb + y1 * qw + x1));
+  float v = acc + up;
+  if (apply_sigmoid) v = 1.f / (1.f + expf(-v));
+  out[((long long)b * H + gy) * W + gx] = v;
+}
+
+void glue_final(const LaunchCtx& ctx, const float* x, int B, int H, int W, const float* tab, const float* q, int qh,
+                int qw, float* out, int apply_sigmoid) {
+  if (ctx.launches) ++*ctx.launches;
+  if (ctx.dry) return;
+  KScope ks(ctx, KC_GLUE, 2.0 * 75 * (double)B * H * W, 16.0 * B * H * W, "final");
+  dim3 grid((W + FT_W - 1) / FT_W, (H + FT_H - 1) / FT_H, B);
+  final_kernel<<<grid, FT_W * FT_H, 0, ctx.stream>>>(x, H, W, tab, q, qh, qw, out, apply_sigmoid);
+  BRN_CUDA(cudaGetLastError());
+}
+
+// host-side fold (double): w1 [64][27], b1 [64], wc [64][9] (c; i*3+j), bc -> table
+void build_final_table(const float* w1, const float* b1, const double* wc, double bc, float* tab) {
+  double M[9][27] = {}, Bt[9] = {}, K5[3][5][5] = {};
+  for (int ij = 0; ij < 9; ++ij) {
+    for (int c = 0; c < 64; ++c) {
+      Bt[ij] += wc[c * 9 + ij] * (double)b1[c];
+      for (int t = 0; t < 27; ++t) M[ij][t] += wc[c * 9 + ij] * (double)w1[c * 27 + t];
+    }
+  }
+  double bsum = bc;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      bsum += Bt[i * 3 + j];
+      for (int ci = 0; ci < 3; ++ci)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) K5[ci][i + ky][j + kx] += M[i * 3 + j][ci * 9 + ky * 3 + kx];
+    }
+  for (int i = 0; i < FIN_TAB; ++i) tab[i] = 0.f;
+  for (int ci = 0; ci < 3; ++ci)
+    for (int u = 0; u < 5; ++u)
+      for (int v = 0; v < 5; ++v) tab[ci * 25 + u * 5 + v] = (float)K5[ci][u][v];
+  for (int ij = 0; ij < 9; ++ij) {
+    for (int t = 0; t < 27; ++t) tab[75 + ij * 27 + t] = (float)M[ij][t];
+    tab[318 + ij] = (float)Bt[ij];
+  }
+  tab[327] = (float)bc;
+  tab[328] = (float)bsum;
+}
+
+}  // namespace brn

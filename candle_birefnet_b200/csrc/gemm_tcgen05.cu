@@ -14,6 +14,7 @@
 // Roofline: tensor pipe (2*M*N*K flop per launch) for K >= 384, HBM (A read + out write) below that.
 #include <cuda.h>
 
+#include <cstdio>
 #include <mutex>
 
 #include "brn_common.h"
@@ -33,6 +34,7 @@ struct TcGemmP {
   int tw_log2, tiles_x, tiles_y;
   int m_tiles, n_tiles, BN;
   int taps, kw, pad, cblocks, cin_pad;
+  int in_bf16;   // operand format: 1 = bf16, 0 = fp16
   EpiP epi;
   RowMap rm;
 };
@@ -90,7 +92,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (ptx::elect_one()) {
       // ===== MMA issuer =====
-      const uint32_t idesc = ptx::make_idesc_bf16(TC_BM, p.BN, 0, 0);
+      const uint32_t idesc = ptx::make_idesc_16(TC_BM, p.BN, 0, 0, p.in_bf16);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -171,15 +173,15 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// rank-`rank` bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides[0] is implicit.
-CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                           const uint32_t* box, CUtensorMapSwizzle swz) {
+// rank-`rank` bf16/fp16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides[0] is implicit.
+CUtensorMap make_tmap_16(const void* base, int dt, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, CUtensorMapSwizzle swz) {
   CUtensorMap m;
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = get_encode()(&m, dt == F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BRN_CHECK(r == CUDA_SUCCESS, 2, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
@@ -194,7 +196,7 @@ int device_sm_count() {
 
 bool tc_gemm_supported(const GemmArgs& a) {
   if (!a.w || !a.w->w16) return false;
-  if (a.x.dt != BF16) return false;
+  if ((a.x.dt != BF16 && a.x.dt != F16) || a.x.dt != a.w->w16_dt) return false;
   if (a.x.C % 8 != 0 || a.x.ld % 8 != 0 || ((uintptr_t)a.x.p & 15)) return false;
   if (a.rowmap.enabled && !(a.x.B == 1 && a.x.H == 1)) return false;
   if (a.bias_bstride && a.x.H * a.x.W < 1) return false;
@@ -241,23 +243,27 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   p.taps = w.taps(); p.kw = w.kw; p.pad = a.pad; p.cin_pad = w.cin_pad; p.cblocks = w.cin_pad / TC_BK;
   p.epi = make_epi(w.N, a.bias ? a.bias : w.bias, a.bias_bstride, a.act, a.act_from, a.res, a.out);
   p.rm = a.rowmap;
+  p.in_bf16 = a.x.dt == BF16 ? 1 : 0;
 
   const uint64_t ld2 = (uint64_t)a.x.ld * 2;
   uint64_t adims[4] = {(uint64_t)a.x.C, (uint64_t)a.x.W, (uint64_t)a.x.H, (uint64_t)a.x.B};
   uint64_t astr[3] = {ld2, ld2 * a.x.W, ld2 * a.x.W * a.x.H};
   uint32_t abox[4] = {(uint32_t)TC_BK, (uint32_t)tw, (uint32_t)TH, 1};
-  CUtensorMap tmA = make_tmap_bf16(a.x.p, 4, adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tmA = make_tmap_16(a.x.p, a.x.dt, 4, adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_128B);
   const uint64_t ktot = (uint64_t)w.taps() * w.cin_pad;
   uint64_t bdims[2] = {ktot, (uint64_t)w.N};
   uint64_t bstr[1] = {ktot * 2};
   uint32_t bbox[2] = {(uint32_t)TC_BK, (uint32_t)p.BN};
-  CUtensorMap tmB = make_tmap_bf16(w.w16, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tmB = make_tmap_16(w.w16, w.w16_dt, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B);
 
   cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
   const int grid = std::min(p.m_tiles * p.n_tiles, device_sm_count());
   const double rows = (double)a.x.rows();
+  char desc[128] = "";
+  if (ctx.kt) snprintf(desc, sizeof desc, "M=%lld N=%d K=%dx%d BN=%d tiles=%d act=%d res=%d odt=%d", (long long)a.x.rows(),
+                       w.N, w.taps(), w.Cin, p.BN, p.m_tiles * p.n_tiles, a.act, a.res.p ? 1 : 0, a.out.dt);
   KScope ks(ctx, KC_GEMM_TC, 2.0 * rows * w.N * w.taps() * w.Cin,
-            rows * a.x.C * 2 + rows * w.N * dsize(a.out.dt) + (double)w.N * w.taps() * w.cin_pad * 2);
+            rows * a.x.C * 2 + rows * w.N * dsize(a.out.dt) + (double)w.N * w.taps() * w.cin_pad * 2, desc);
   tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM, ctx.stream>>>(tmA, tmB, p);
   BRN_CUDA(cudaGetLastError());
 }

@@ -1,94 +1,18 @@
-// HBM-bound glue kernels: LayerNorm (+ window gather / patch-merge gather), bilinear resampling, image2patches,
-// global average pool, GDT gate, the fused final layer.  All are bandwidth-bound; threads map to the contiguous
+// HBM-bound glue kernels: bilinear resampling, image2patches, layout converts, global average pool, GDT gate
+// (LayerNorm lives in ln_kernels.cu, the fused final layer in final_kernel.cu).  All are bandwidth-bound; threads map to the contiguous
 // (channel) dimension of NHWC so every warp access is a run of consecutive addresses.
 #include "brn_common.h"
 #include "device_utils.cuh"
 
 namespace brn {
 
-__device__ __forceinline__ float g_ld(const void* p, int dt, long long i) {
-  return dt == F32 ? ((const float*)p)[i] : __bfloat162float(((const __nv_bfloat16*)p)[i]);
-}
-__device__ __forceinline__ void g_st(void* p, int dt, long long i, float v) {
-  if (dt == F32) ((float*)p)[i] = v; else ((__nv_bfloat16*)p)[i] = __float2bfloat16(v);
-}
+__device__ __forceinline__ float g_ld(const void* p, int dt, long long i) { return ld_elem(p, dt, i); }
+__device__ __forceinline__ void g_st(void* p, int dt, long long i, float v) { st_elem(p, dt, i, v); }
 
 #define GLUE_LAUNCH_PROLOGUE(ctx)        \
   if ((ctx).launches) ++*(ctx).launches; \
   if ((ctx).dry) return;                 \
-  KScope ks__((ctx), KC_GLUE, 0.0);
-
-// ------------------------------------------------------------------------------------------------
-// LayerNorm, one warp per destination row (candle_nn::layer_norm, eps 1e-5, biased variance).
-//  LN_PLAIN : row m <- row m                                     (norm2, patch_embed.norm, norm{i})
-//  LN_WINDOW: window-ordered padded row m <- token row, zeros for pad rows (norm1 -> pad -> roll -> partition,
-//             src/swin.rs:355-380; pad rows are zeros AFTER the norm)
-//  LN_MERGE : row (b,i,j) <- [x(2i,2j) | x(2i+1,2j) | x(2i,2j+1) | x(2i+1,2j+1)], LN over 4C (src/swin.rs:505-525)
-// ------------------------------------------------------------------------------------------------
-struct LnP {
-  const void* x; int xdt; int ldx; int B, h, w, C;
-  const float* gamma; const float* beta;
-  void* out; int odt; int ldo;
-  int mode, hp, wp, shift;
-  long long rows;
-};
-
-__global__ void __launch_bounds__(256) ln_kernel(LnP p) {
-  const int lane = threadIdx.x & 31;
-  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (m >= p.rows) return;
-  const int n = p.mode == LN_MERGE ? 4 * p.C : p.C;
-  long long src[4] = {-1, -1, -1, -1};
-  if (p.mode == LN_PLAIN) {
-    src[0] = m * p.ldx;
-  } else if (p.mode == LN_WINDOW) {
-    long long tok = window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift);
-    if (tok < 0) {
-      for (int e = lane; e < n; e += 32) g_st(p.out, p.odt, m * p.ldo + e, 0.f);
-      return;
-    }
-    src[0] = tok * p.ldx;
-  } else {
-    const int h2 = (p.h + 1) / 2, w2 = (p.w + 1) / 2;
-    long long b = m / ((long long)h2 * w2);
-    int r = (int)(m - b * (long long)h2 * w2);
-    int i = r / w2, j = r - i * w2;
-#pragma unroll
-    for (int part = 0; part < 4; ++part) {
-      int y = 2 * i + (part & 1), xx = 2 * j + (part >> 1);
-      if (y < p.h && xx < p.w) src[part] = ((b * p.h + y) * (long long)p.w + xx) * p.ldx;
-    }
-  }
-  auto load = [&](int e) -> float {
-    if (p.mode == LN_MERGE) {
-      int part = e / p.C, c = e - part * p.C;
-      return src[part] < 0 ? 0.f : g_ld(p.x, p.xdt, src[part] + c);
-    }
-    return g_ld(p.x, p.xdt, src[0] + e);
-  };
-  float s = 0.f;
-  for (int e = lane; e < n; e += 32) s += load(e);
-  const float mean = warp_sum(s) / n;
-  float v = 0.f;
-  for (int e = lane; e < n; e += 32) { float d = load(e) - mean; v += d * d; }
-  const float rstd = rsqrtf(warp_sum(v) / n + 1e-5f);
-  for (int e = lane; e < n; e += 32)
-    g_st(p.out, p.odt, m * p.ldo + e, (load(e) - mean) * rstd * p.gamma[e] + p.beta[e]);
-}
-
-void glue_layernorm(const LaunchCtx& ctx, const LnArgs& a) {
-  if (ctx.launches) ++*ctx.launches;
-  if (ctx.dry) return;
-  KScope ks__(ctx, KC_LN, 0.0, (double)a.out.rows() * a.out.C * (4 + dsize(a.out.dt)));
-  LnP p{};
-  p.x = a.x.p; p.xdt = a.x.dt; p.ldx = a.x.ld; p.B = a.x.B; p.h = a.x.H; p.w = a.x.W; p.C = a.x.C;
-  p.gamma = a.gamma; p.beta = a.beta;
-  p.out = a.out.p; p.odt = a.out.dt; p.ldo = a.out.ld;
-  p.mode = a.mode; p.hp = a.hp; p.wp = a.wp; p.shift = a.shift;
-  p.rows = a.out.rows();
-  ln_kernel<<<(unsigned)((p.rows + 7) / 8), 256, 0, ctx.stream>>>(p);
-  BRN_CUDA(cudaGetLastError());
-}
+  KScope ks__((ctx), KC_GLUE, 0.0, 0.0, __func__);
 
 // ------------------------------------------------------------------------------------------------
 // PatchEmbed im2col (src/swin.rs:692-704): row (b,py,px), k = c*P*P + ky*P + kx  <-  x[b,c,py*P+ky,px*P+kx]
@@ -351,83 +275,6 @@ void glue_dot1(const LaunchCtx& ctx, View p, const float* w, float* out) {
   GLUE_LAUNCH_PROLOGUE(ctx);
   long long rows = p.rows();
   dot1_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ctx.stream>>>(p.p, p.dt, p.ld, p.C, w, out, rows);
-  BRN_CUDA(cudaGetLastError());
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fused final layer (src/birefnet.rs:320,372-375 + src/decoder.rs:50-56), exact algebraic rewrite:
-//   conv_out1(cat(up(p1), ipt_blk1(x))) = up(w_p . p1) + conv3x3_{64->1}(conv3x3_{3->64}(x); Wc) + bc
-// where Wc[c,i,j] = sum_o w_i[o] ipt_blk1.conv_out.weight[o,c,i,j]; the inner conv's zero padding is kept (the
-// 64-channel intermediate is zero outside the image).  The 240-channel full-resolution tensor never exists.
-// ------------------------------------------------------------------------------------------------
-constexpr int FT = 16;  // output tile
-__global__ void __launch_bounds__(256) final_kernel(const float* __restrict__ x, int H, int W,
-                                                    const float* __restrict__ w1, const float* __restrict__ b1,
-                                                    const float* __restrict__ wc, float bc,
-                                                    const float* __restrict__ q, int qh, int qw, float* out,
-                                                    int apply_sigmoid) {
-  __shared__ float xin[3][FT + 4][FT + 4];
-  __shared__ float tmid[16][FT + 2][FT + 2 + 1];
-  __shared__ float sw1[64 * 27], sb1[64], swc[64 * 9];
-  const int b = blockIdx.z, ty0 = blockIdx.y * FT, tx0 = blockIdx.x * FT, tid = threadIdx.x;
-  for (int i = tid; i < 64 * 27; i += 256) sw1[i] = w1[i];
-  for (int i = tid; i < 64 * 9; i += 256) swc[i] = wc[i];
-  if (tid < 64) sb1[tid] = b1[tid];
-  for (int i = tid; i < 3 * (FT + 4) * (FT + 4); i += 256) {
-    int c = i / ((FT + 4) * (FT + 4)), r = i % ((FT + 4) * (FT + 4)), yy = r / (FT + 4), xx = r % (FT + 4);
-    int gy = ty0 + yy - 2, gx = tx0 + xx - 2;
-    xin[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[((long long)(b * 3 + c) * H + gy) * W + gx] : 0.f;
-  }
-  __syncthreads();
-  const int ly = tid / FT, lx = tid % FT;
-  float acc = 0.f;
-  for (int cc = 0; cc < 64; cc += 16) {
-    for (int i = tid; i < 16 * (FT + 2) * (FT + 2); i += 256) {
-      int c = i / ((FT + 2) * (FT + 2)), r = i % ((FT + 2) * (FT + 2)), yy = r / (FT + 2), xx = r % (FT + 2);
-      int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
-      float v = 0.f;
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        v = sb1[cc + c];
-        const float* wr = &sw1[(cc + c) * 27];
-#pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) v = fmaf(wr[ci * 9 + ky * 3 + kx], xin[ci][yy + ky][xx + kx], v);
-      }
-      tmid[c][yy][xx] = v;
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int c = 0; c < 16; ++c) {
-      const float* wr = &swc[(cc + c) * 9];
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) acc = fmaf(wr[ky * 3 + kx], tmid[c][ly + ky][lx + kx], acc);
-    }
-    __syncthreads();
-  }
-  const int gy = ty0 + ly, gx = tx0 + lx;
-  if (gy < H && gx < W) {
-    int y0, y1, x0, x1; float fy, fx;
-    bilin_coord(gy, qh, H, y0, y1, fy);
-    bilin_coord(gx, qw, W, x0, x1, fx);
-    const float* qb = q + (long long)b * qh * qw;
-    float up = (1.f - fy) * ((1.f - fx) * qb[y0 * qw + x0] + fx * qb[y0 * qw + x1]) +
-               fy * ((1.f - fx) * qb[y1 * qw + x0] + fx * qb[y1 * qw + x1]);
-    float v = acc + bc + up;
-    if (apply_sigmoid) v = 1.f / (1.f + expf(-v));
-    out[((long long)b * H + gy) * W + gx] = v;
-  }
-}
-
-void glue_final(const LaunchCtx& ctx, const float* x, int B, int H, int W, const float* w1, const float* b1,
-                const float* wc, float bc, const float* q, int qh, int qw, float* out, int apply_sigmoid) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
-  dim3 grid((W + FT - 1) / FT, (H + FT - 1) / FT, B);
-  final_kernel<<<grid, 256, 0, ctx.stream>>>(x, H, W, w1, b1, wc, bc, q, qh, qw, out, apply_sigmoid);
   BRN_CUDA(cudaGetLastError());
 }
 

@@ -24,12 +24,8 @@ struct SimtGemmP {
 
 constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
 
-__device__ __forceinline__ float ld_act(const void* p, int dt, long long i) {
-  return dt == F32 ? ((const float*)p)[i] : __bfloat162float(((const __nv_bfloat16*)p)[i]);
-}
-__device__ __forceinline__ void st_act(void* p, int dt, long long i, float v) {
-  if (dt == F32) ((float*)p)[i] = v; else ((__nv_bfloat16*)p)[i] = __float2bfloat16(v);
-}
+__device__ __forceinline__ float ld_act(const void* p, int dt, long long i) { return ld_elem(p, dt, i); }
+__device__ __forceinline__ void st_act(void* p, int dt, long long i, float v) { st_elem(p, dt, i, v); }
 
 // torchvision deform_conv2d bilinear_interpolate semantics (zero outside (-1,H)x(-1,W))
 __device__ __forceinline__ float deform_sample(const SimtGemmP& p, long long base_b, float py, float px, int c) {

@@ -1,0 +1,184 @@
+// LayerNorm kernels (candle_nn::layer_norm, eps 1e-5, biased variance), HBM-bound: one warp per destination row, the
+// row held in registers as float4 vectors (one global read of the fp32 residual stream, one 16-bit write).
+//  LN_PLAIN : row m <- row m                                     (norm2, patch_embed.norm, norm{i})
+//  LN_WINDOW: window-ordered padded row m <- token row, zeros for pad rows: norm1 -> pad -> roll -> window_partition
+//             (src/swin.rs:355-380) as one gather; pad rows are zeros AFTER the norm
+//  LN_MERGE : row (b,i,j) <- [x(2i,2j) | x(2i+1,2j) | x(2i,2j+1) | x(2i+1,2j+1)], LN over 4C (src/swin.rs:505-525)
+// Algorithmic bytes per row: 4*n read + esize*n written (n = C or 4C).
+#include "brn_common.h"
+#include "device_utils.cuh"
+
+namespace brn {
+
+struct LnP {
+  const void* x; int xdt; int ldx; int B, h, w, C;
+  const float* gamma; const float* beta;
+  void* out; int odt; int ldo;
+  int mode, hp, wp, shift;
+  long long rows;
+};
+
+__device__ __forceinline__ void ln_store4(void* out, int odt, long long idx, float4 v) {
+  if (odt == F32) {
+    *reinterpret_cast<float4*>((float*)out + idx) = v;
+  } else if (odt == BF16) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    *reinterpret_cast<uint2*>((__nv_bfloat16*)out + idx) = u;
+  } else {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    *reinterpret_cast<uint2*>((__half*)out + idx) = u;
+  }
+}
+
+// fp32 source, n % 4 == 0, NV = ceil(n / 128) float4 per lane
+template <int NV>
+__global__ void __launch_bounds__(256) ln_vec_kernel(LnP p) {
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= p.rows) return;
+  const int n = p.mode == LN_MERGE ? 4 * p.C : p.C;
+  const int n4 = n >> 2;
+  const float* xs = (const float*)p.x;
+  long long src[4] = {-1, -1, -1, -1};
+  if (p.mode == LN_PLAIN) {
+    src[0] = m * p.ldx;
+  } else if (p.mode == LN_WINDOW) {
+    const long long tok = window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift);
+    if (tok < 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int e4 = lane + 32 * i;
+        if (e4 < n4) ln_store4(p.out, p.odt, m * p.ldo + 4 * e4, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+      return;
+    }
+    src[0] = tok * p.ldx;
+  } else {
+    const int h2 = (p.h + 1) / 2, w2 = (p.w + 1) / 2;
+    const long long b = m / ((long long)h2 * w2);
+    const int r = (int)(m - b * (long long)h2 * w2);
+    const int i = r / w2, j = r - i * w2;
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+      const int y = 2 * i + (part & 1), xx = 2 * j + (part >> 1);
+      if (y < p.h && xx < p.w) src[part] = ((b * p.h + y) * (long long)p.w + xx) * p.ldx;
+    }
+  }
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e4 = lane + 32 * i;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e4 < n4) {
+      if (p.mode == LN_MERGE) {
+        const int e = 4 * e4, part = e / p.C, c = e - part * p.C;
+        if (src[part] >= 0) v[i] = __ldg(reinterpret_cast<const float4*>(xs + src[part] + c));
+      } else {
+        v[i] = __ldg(reinterpret_cast<const float4*>(xs + src[0] + 4 * e4));
+      }
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / n;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + 32 * i < n4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / n + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e4 = lane + 32 * i;
+    if (e4 < n4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + e4);
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.beta) + e4);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + bb.x;
+      o.y = (v[i].y - mean) * rstd * g.y + bb.y;
+      o.z = (v[i].z - mean) * rstd * g.z + bb.z;
+      o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+      ln_store4(p.out, p.odt, m * p.ldo + 4 * e4, o);
+    }
+  }
+}
+
+// generic fallback (any dtype / alignment): three passes over the row
+__global__ void __launch_bounds__(256) ln_generic_kernel(LnP p) {
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= p.rows) return;
+  const int n = p.mode == LN_MERGE ? 4 * p.C : p.C;
+  long long src[4] = {-1, -1, -1, -1};
+  if (p.mode == LN_PLAIN) {
+    src[0] = m * p.ldx;
+  } else if (p.mode == LN_WINDOW) {
+    long long tok = window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift);
+    if (tok < 0) {
+      for (int e = lane; e < n; e += 32) st_elem(p.out, p.odt, m * p.ldo + e, 0.f);
+      return;
+    }
+    src[0] = tok * p.ldx;
+  } else {
+    const int h2 = (p.h + 1) / 2, w2 = (p.w + 1) / 2;
+    long long b = m / ((long long)h2 * w2);
+    int r = (int)(m - b * (long long)h2 * w2);
+    int i = r / w2, j = r - i * w2;
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+      int y = 2 * i + (part & 1), xx = 2 * j + (part >> 1);
+      if (y < p.h && xx < p.w) src[part] = ((b * p.h + y) * (long long)p.w + xx) * p.ldx;
+    }
+  }
+  auto load = [&](int e) -> float {
+    if (p.mode == LN_MERGE) {
+      int part = e / p.C, c = e - part * p.C;
+      return src[part] < 0 ? 0.f : ld_elem(p.x, p.xdt, src[part] + c);
+    }
+    return ld_elem(p.x, p.xdt, src[0] + e);
+  };
+  float s = 0.f;
+  for (int e = lane; e < n; e += 32) s += load(e);
+  const float mean = warp_sum(s) / n;
+  float v = 0.f;
+  for (int e = lane; e < n; e += 32) { float d = load(e) - mean; v += d * d; }
+  const float rstd = rsqrtf(warp_sum(v) / n + 1e-5f);
+  for (int e = lane; e < n; e += 32)
+    st_elem(p.out, p.odt, m * p.ldo + e, (load(e) - mean) * rstd * p.gamma[e] + p.beta[e]);
+}
+
+void glue_layernorm(const LaunchCtx& ctx, const LnArgs& a) {
+  if (ctx.launches) ++*ctx.launches;
+  if (ctx.dry) return;
+  LnP p{};
+  p.x = a.x.p; p.xdt = a.x.dt; p.ldx = a.x.ld; p.B = a.x.B; p.h = a.x.H; p.w = a.x.W; p.C = a.x.C;
+  p.gamma = a.gamma; p.beta = a.beta;
+  p.out = a.out.p; p.odt = a.out.dt; p.ldo = a.out.ld;
+  p.mode = a.mode; p.hp = a.hp; p.wp = a.wp; p.shift = a.shift;
+  p.rows = a.out.rows();
+  const int n = a.mode == LN_MERGE ? 4 * a.x.C : a.x.C;
+  KScope ks(ctx, KC_LN, 0.0, (double)p.rows * n * (4 + dsize(a.out.dt)),
+            a.mode == LN_WINDOW ? "ln_window" : a.mode == LN_MERGE ? "ln_merge" : "ln_plain");
+  const unsigned grid = (unsigned)((p.rows + 7) / 8);
+  const bool vec = a.x.dt == F32 && a.x.C % 4 == 0 && a.x.ld % 4 == 0 && (((uintptr_t)a.x.p) & 15) == 0 &&
+                   (a.out.ld * dsize(a.out.dt)) % (4 * dsize(a.out.dt)) == 0 && a.out.ld % 4 == 0 &&
+                   (((uintptr_t)a.out.p) & (4 * dsize(a.out.dt) - 1)) == 0 && (((uintptr_t)a.gamma | (uintptr_t)a.beta) & 15) == 0;
+  const int nv = (n + 127) / 128;
+  if (vec && nv <= 24) {
+#define LN_CASE(NV) ln_vec_kernel<NV><<<grid, 256, 0, ctx.stream>>>(p)
+    if (nv <= 1) LN_CASE(1); else if (nv <= 2) LN_CASE(2); else if (nv <= 3) LN_CASE(3); else if (nv <= 4) LN_CASE(4);
+    else if (nv <= 6) LN_CASE(6); else if (nv <= 8) LN_CASE(8); else if (nv <= 12) LN_CASE(12);
+    else if (nv <= 16) LN_CASE(16); else LN_CASE(24);
+#undef LN_CASE
+  } else {
+    ln_generic_kernel<<<grid, 256, 0, ctx.stream>>>(p);
+  }
+  BRN_CUDA(cudaGetLastError());
+}
+
+}  // namespace brn

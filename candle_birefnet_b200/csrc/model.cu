@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 
 #include "device_utils.cuh"
@@ -57,6 +58,7 @@ Model::~Model() {
   for (void* p : allocs) cudaFree(p);
   if (arena.base) cudaFree(arena.base);
   for (auto& pe : prof) { if (pe.e0) cudaEventDestroy(pe.e0); if (pe.e1) cudaEventDestroy(pe.e1); }
+  for (auto e : ktimer.pool) cudaEventDestroy(e);
   if (own_stream) cudaStreamDestroy(own_stream);
 }
 
@@ -186,10 +188,16 @@ static uint16_t f2bf(float f) {  // round-to-nearest-even
   return (uint16_t)(u >> 16);
 }
 
+static uint16_t f2h(float f) {
+  __half h = __float2half_rn(f);
+  uint16_t u; memcpy(&u, &h, 2);
+  return u;
+}
+
 LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w, const float* bias,
-                             std::vector<void*>& allocs) {
+                             std::vector<void*>& allocs, int w16_dt) {
   LayerW L;
-  L.N = N; L.Cin = Cin; L.kh = kh; L.kw = kw;
+  L.N = N; L.Cin = Cin; L.kh = kh; L.kw = kw; L.w16_dt = w16_dt;
   L.cin_pad = (Cin + 63) / 64 * 64;
   const int taps = kh * kw;
   std::vector<float> w32((size_t)N * taps * Cin);
@@ -199,7 +207,7 @@ LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w, con
       for (int t = 0; t < taps; ++t) {
         float v = w[((size_t)n * Cin + c) * taps + t];
         w32[((size_t)n * taps + t) * Cin + c] = v;
-        w16[((size_t)n * taps + t) * L.cin_pad + c] = f2bf(v);
+        w16[((size_t)n * taps + t) * L.cin_pad + c] = w16_dt == F16 ? f2h(v) : f2bf(v);
       }
   BRN_CUDA(cudaMalloc(&L.w32, w32.size() * 4)); allocs.push_back(L.w32);
   BRN_CUDA(cudaMemcpy(L.w32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice));
@@ -212,9 +220,10 @@ LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w, con
   return L;
 }
 
-LayerW Model::make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w, const std::vector<float>* bias) {
+LayerW Model::make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w, const std::vector<float>* bias,
+                         int w16_dt) {
   BRN_CHECK(w.size() == (size_t)N * Cin * kh * kw, 5, "internal: make_layer size");
-  return make_layer_standalone(N, Cin, kh, kw, w.data(), bias ? bias->data() : nullptr, allocs);
+  return make_layer_standalone(N, Cin, kh, kw, w.data(), bias ? bias->data() : nullptr, allocs, w16_dt);
 }
 
 // eval BatchNorm as (scale, shift): y = x*scale + shift  (candle batch_norm(C,1e-5).forward_t(x,false))
@@ -234,6 +243,7 @@ void Model::finalize() {
     BRN_CHECK(tensors[i].set, 3, "missing tensor: " + keys[i]);
   BRN_CUDA(cudaSetDevice(device));
 
+  const int dec16 = cfg.decoder_fp16 ? F16 : BF16;   // 16-bit operand type of the squeeze module + decoder
   // conv (+ optional BN fold) -> LayerW
   auto conv_bn = [&](const std::string& cp, bool has_bias, const std::string& bnp) -> LayerW {
     const HostTensor& w = T(cp + ".weight");
@@ -252,7 +262,7 @@ void Model::finalize() {
       }
       any_bias = true;
     }
-    return make_layer(N, Cin, k, k, wf, any_bias ? &bf : nullptr);
+    return make_layer(N, Cin, k, k, wf, any_bias ? &bf : nullptr, dec16);
   };
   auto linear = [&](const std::string& p, bool bias) -> LayerW {
     const HostTensor& w = T(p + ".weight");
@@ -332,7 +342,7 @@ void Model::finalize() {
       const HostTensor &mw = T(bp + ".atrous_conv.modulator_conv.weight"), &mb = T(bp + ".atrous_conv.modulator_conv.bias");
       std::vector<float> w = ow.data; w.insert(w.end(), mw.data.begin(), mw.data.end());
       std::vector<float> bb = ob.data; bb.insert(bb.end(), mb.data.begin(), mb.data.end());
-      D.br[b].om = make_layer(3 * k * k, 64, k, k, w, &bb);
+      D.br[b].om = make_layer(3 * k * k, 64, k, k, w, &bb, dec16);
       D.br[b].reg = conv_bn(bp + ".atrous_conv.regular_conv", false, bp + ".bn");
     }
     D.gap = conv_bn(a + ".global_avg_pool.1", false, a + ".global_avg_pool.2");
@@ -346,7 +356,7 @@ void Model::finalize() {
         for (int c = 0; c < 256; ++c) tail[(size_t)o * 256 + c] = (float)((double)w.data[(size_t)o * 1280 + 1024 + c] * sc[o]);
         shift[o] = (float)sh[o];
       }
-      D.conv1 = make_layer(64, 1024, 1, 1, head, nullptr);
+      D.conv1 = make_layer(64, 1024, 1, 1, head, nullptr, dec16);
       D.conv1_tail = upload(tail);
       D.bn1_shift = upload(shift);
     }
@@ -375,19 +385,18 @@ void Model::finalize() {
     const HostTensor& c1 = T("decoder.ipt_blk1.conv1.weight");     // [64,3,3,3]
     const HostTensor& co = T("decoder.ipt_blk1.conv_out.weight");  // [48,64,3,3]
     const HostTensor& cob = T("decoder.ipt_blk1.conv_out.bias");
-    dw.fin_w1 = upload(c1.data);
-    dw.fin_b1 = upload(T("decoder.ipt_blk1.conv1.bias").data);
-    std::vector<float> wc((size_t)64 * 9);
+    std::vector<double> wc((size_t)64 * 9);
     for (int c = 0; c < 64; ++c)
       for (int t = 0; t < 9; ++t) {
         double s = 0;
         for (int o = 0; o < 48; ++o) s += (double)wo.data[P + o] * (double)co.data[((size_t)o * 64 + c) * 9 + t];
-        wc[(size_t)c * 9 + t] = (float)s;
+        wc[(size_t)c * 9 + t] = s;
       }
-    dw.fin_wc = upload(wc);
     double bc = T("decoder.conv_out1.0.bias").data[0];
     for (int o = 0; o < 48; ++o) bc += (double)wo.data[P + o] * (double)cob.data[o];
-    dw.fin_bc = (float)bc;
+    std::vector<float> tab(336);
+    build_final_table(c1.data.data(), T("decoder.ipt_blk1.conv1.bias").data.data(), wc.data(), bc, tab.data());
+    dw.fin_tab = upload(tab);
   }
   // host copies are no longer needed
   for (auto& t : tensors) { std::vector<float>().swap(t.data); }
@@ -492,7 +501,7 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
 
 // BasicDecBlk::forward (src/decoder.rs:126-141) with ASPPDeformable (src/aspp.rs:303-333)
 void Model::run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out) {
-  const int AD = act_dtype();
+  const int AD = dec_dtype();
   const size_t m0 = arena.mark();
   const int B = in.B, H = in.H, W = in.W;
   const size_t px = (size_t)B * H * W;
@@ -526,7 +535,7 @@ void Model::run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out) {
 // BiRefNetDecoder::forward (src/birefnet.rs:278-376).  D4in[:, :lat3] already holds the squeezed x4.
 void Model::run_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, View X1, View X2, View X3, View D4in,
                         float* out, bool apply_sigmoid) {
-  const int AD = act_dtype();
+  const int AD = dec_dtype();
   const int dec_out[4] = {lat(2), lat(1), lat(0), lat(0) / 2};
   View lat_src[3] = {X3, X2, X1};
   View din = D4in;
@@ -547,7 +556,9 @@ void Model::run_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, V
         op_gemm(ctx, g); }
       arena.release(m1);
     }
-    p = make_view(arena.alloc(px * dec_out[d] * dsize(AD)), AD, B, hh, ww, dec_out[d]);
+    // p1 (the last block's output) only feeds the 1x1 output conv: keep it in fp32 (no 16-bit rounding before the dot)
+    const int PD = d == 3 ? F32 : AD;
+    p = make_view(arena.alloc(px * dec_out[d] * dsize(PD)), PD, B, hh, ww, dec_out[d]);
     run_decblk(ctx, dw.dec[d], din, p);
     if (d == 3) break;
     // GDT gate (src/birefnet.rs:327-329)
@@ -570,12 +581,12 @@ void Model::run_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, V
   // final: conv_out1(cat(up(p1), ipt_blk1(x))) (src/birefnet.rs:372-375), rewritten (Appendix F.9)
   float* q = (float*)arena.alloc((size_t)B * p.H * p.W * 4);
   glue_dot1(ctx, p, dw.out_wp, q);
-  glue_final(ctx, img, B, H, W, dw.fin_w1, dw.fin_b1, dw.fin_wc, dw.fin_bc, q, p.H, p.W, out, apply_sigmoid ? 1 : 0);
+  glue_final(ctx, img, B, H, W, dw.fin_tab, q, p.H, p.W, out, apply_sigmoid ? 1 : 0);
 }
 
 void Model::run_squeeze_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, View X1, View X2, View X3,
                                 View X4cat, float* out, bool apply_sigmoid) {
-  const int AD = act_dtype();
+  const int AD = dec_dtype();
   const int h4 = H / 32, w4 = W / 32;
   const int c4 = lat(3) + kIptOut[4];
   View D4in = make_view(arena.alloc((size_t)B * h4 * w4 * c4 * dsize(AD)), AD, B, h4, w4, c4);
@@ -589,7 +600,7 @@ void Model::run_squeeze_decoder(LaunchCtx& ctx, const float* img, int B, int H, 
 
 // BiRefNet::forward_logits (src/birefnet.rs:412-461)
 void Model::run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, float* out, bool apply_sigmoid) {
-  const int AD = act_dtype();
+  const int AD = dec_dtype();
   const size_t m0 = arena.mark();
   int hs[4], ws[4];
   for (int i = 0; i < 4; ++i) { hs[i] = H / (4 << i); ws[i] = W / (4 << i); }
@@ -649,7 +660,7 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
   run_forward(ctx, (const float*)0x10000, mb, H, W, (float*)0x10000, apply_sigmoid);
   ensure_arena(arena.peak);
   arena.dry = false; ctx.dry = false; ctx.launches = &launches;
-  if (prof_on >= 2) { ctx.kt = &ktimer; ktimer.recs.clear(); }
+  if (prof_on >= 2) { ctx.kt = &ktimer; ktimer.reset(); }
   if (prof_on) {
     for (auto& pe : prof) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
     prof.clear();
@@ -671,9 +682,17 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
     for (auto& r : ktimer.recs) {
       float ms = 0; cudaEventElapsedTime(&ms, r.e0, r.e1);
       kc_ms[r.cls] += ms; kc_flops[r.cls] += r.flops; kc_bytes[r.cls] += r.bytes; kc_count[r.cls]++;
-      cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
     }
-    ktimer.recs.clear();
+    if (const char* path = getenv("BRN_KERNEL_LOG")) {
+      if (FILE* f = fopen(path, "w")) {
+        fprintf(f, "class,ms,gflop,mbytes,desc\n");
+        for (auto& r : ktimer.recs) {
+          float ms = 0; cudaEventElapsedTime(&ms, r.e0, r.e1);
+          fprintf(f, "%d,%.5f,%.4f,%.3f,%s\n", r.cls, ms, r.flops / 1e9, r.bytes / 1e6, r.desc.c_str());
+        }
+        fclose(f);
+      }
+    }
   }
   if (prof_on) {
     prof_names.clear(); prof_ms.clear(); prof_flops.clear();
@@ -727,7 +746,7 @@ void Model::decoder_api(const float* x, const float* x1, const float* x2, const 
   std::lock_guard<std::mutex> lk(mu);
   BRN_CUDA(cudaSetDevice(device));
   cudaStream_t st = s ? s : own_stream;
-  const int AD = act_dtype();
+  const int AD = dec_dtype();
   LaunchCtx ctx; ctx.stream = st; ctx.precision = cfg.precision; ctx.force_simt = env_flag("BRN_FORCE_SIMT");
   long long dummy = 0;
   const cudaMemcpyKind kin = is_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;

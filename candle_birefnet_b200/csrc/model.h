@@ -70,8 +70,7 @@ struct DecoderW {
   float* gdt_attn_w[3] = {nullptr, nullptr, nullptr};
   float gdt_attn_b[3] = {0, 0, 0};
   float* out_wp = nullptr;           // conv_out1 weights on p1 channels
-  float *fin_w1 = nullptr, *fin_b1 = nullptr, *fin_wc = nullptr;
-  float fin_bc = 0.f;
+  float* fin_tab = nullptr;          // folded final-layer table (final_kernel.cu)
 };
 
 struct ProfEntry {
@@ -139,13 +138,15 @@ struct Model {
                            View X4cat, float* out, bool apply_sigmoid);
   void ensure_arena(size_t bytes);
   int micro_batch(int B, int H, int W) const;
-  int act_dtype() const { return cfg.precision == BRN_PREC_BF16 ? BF16 : F32; }
+  int act_dtype() const { return cfg.precision == BRN_PREC_BF16 ? BF16 : F32; }   // backbone activations
+  int dec_dtype() const { return cfg.precision == BRN_PREC_BF16 ? (cfg.decoder_fp16 ? F16 : BF16) : F32; }  // decoder
   void prof_begin(LaunchCtx& ctx, const char* name);
   void prof_end(LaunchCtx& ctx);
 
   const HostTensor& T(const std::string& k) const;
   float* upload(const std::vector<float>& v);
-  LayerW make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w_oihw, const std::vector<float>* bias);
+  LayerW make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w_oihw, const std::vector<float>* bias,
+                    int w16_dt = BF16);
 };
 
 // generic dispatchers (precision + support -> tcgen05 or SIMT)
@@ -155,6 +156,6 @@ void op_attention(const LaunchCtx&, const AttnArgs&);
 
 // standalone layer upload for the operator-level ABI
 LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w_oihw, const float* bias,
-                             std::vector<void*>& allocs);
+                             std::vector<void*>& allocs, int w16_dt = BF16);
 
 }  // namespace brn

@@ -31,6 +31,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// two 16-bit elements (bf16 or fp16 by tag) <-> two floats
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, int dt) { return dt == BF16 ? pack_bf16x2(a, b) : pack_f16x2(a, b); }
+__device__ __forceinline__ float2 unpack16x2(uint32_t u, int dt) {
+  if (dt == BF16) return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
 
 // v: 16 fp32 accumulators (as raw bits) of output row `orow`, columns [nb, nb+16).  `bias` already points at the
 // row's image (per-image bias) or at the shared bias vector.
@@ -74,17 +84,16 @@ __device__ __forceinline__ void epilogue_store16(const EpiP& p, const uint32_t (
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           uint4 rv = rp[j];
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+          const uint32_t* h = reinterpret_cast<const uint32_t*>(&rv);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) { float2 ff = __bfloat1622float2(h[t]); f[8 * j + 2 * t] += ff.x; f[8 * j + 2 * t + 1] += ff.y; }
+          for (int t = 0; t < 4; ++t) { float2 ff = unpack16x2(h[t], p.resdt); f[8 * j + 2 * t] += ff.x; f[8 * j + 2 * t + 1] += ff.y; }
         }
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (nb + j < p.N)
-          f[j] += p.resdt == F32 ? ((const float*)p.res)[orow * p.ldres + nb + j]
-                                 : __bfloat162float(((const __nv_bfloat16*)p.res)[orow * p.ldres + nb + j]);
+          f[j] += ld_elem(p.res, p.resdt, orow * p.ldres + nb + j);
     }
   }
   char* op = (char*)p.out + (orow * p.ldo + nb) * esz;
@@ -97,14 +106,14 @@ __device__ __forceinline__ void epilogue_store16(const EpiP& p, const uint32_t (
       uint4* o4 = reinterpret_cast<uint4*>(op);
 #pragma unroll
       for (int j = 0; j < 2; ++j)
-        o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        o4[j] = make_uint4(pack16x2(f[8 * j], f[8 * j + 1], p.odt), pack16x2(f[8 * j + 2], f[8 * j + 3], p.odt),
+                           pack16x2(f[8 * j + 4], f[8 * j + 5], p.odt), pack16x2(f[8 * j + 6], f[8 * j + 7], p.odt));
     }
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
       if (nb + j < p.N) {
-        if (p.odt == F32) ((float*)op)[j] = f[j]; else ((__nv_bfloat16*)op)[j] = __float2bfloat16(f[j]);
+        st_elem(op, p.odt, j, f[j]);
       }
   }
 }

@@ -157,12 +157,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // instruction descriptor, kind::f16: fp32 accumulate, bf16 A and B
-//  [4,6) D format (1 = f32) | [7,10) A format (1 = bf16) | [10,13) B format | [15] A major (0 = K) | [16] B major |
+//  [4,6) D format (1 = f32) | [7,10) A format (0 = f16, 1 = bf16) | [10,13) B format | [15] A major (0 = K) | [16] B major |
 //  [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ __forceinline__ uint32_t make_idesc_16(uint32_t M, uint32_t N, uint32_t a_mn_major,
+                                                           uint32_t b_mn_major, uint32_t is_bf16) {
+  return (1u << 4) | (is_bf16 << 7) | (is_bf16 << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
+         ((M >> 4) << 24);
+}
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major,
                                                              uint32_t b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
-         ((M >> 4) << 24);
+  return make_idesc_16(M, N, a_mn_major, b_mn_major, 1u);
 }
 
 }  // namespace ptx

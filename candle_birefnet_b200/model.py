@@ -54,6 +54,7 @@ class BiRefNetConfig:
     precision: str = "bf16"            # "bf16" (tcgen05) | "fp32" (SIMT)
     deform_mode: str = "deformable"    # "deformable" (Metal path semantics) | "cpu_fallback" (candle CPU semantics)
     micro_batch: int = 0
+    decoder_dtype: str = "fp16"        # 16-bit path: operand type of squeeze module + decoder ("fp16" | "bf16")
 
     @staticmethod
     def swin_l() -> "BiRefNetConfig":
@@ -85,6 +86,7 @@ class BiRefNet:
             c.num_heads[i] = config.swin.num_heads[i]
         c.window_size, c.mlp_ratio, c.patch_size = config.swin.window_size, config.swin.mlp_ratio, config.swin.patch_size
         c.precision, c.deform_mode, c.micro_batch = _PREC[config.precision], _DEF[config.deform_mode], config.micro_batch
+        c.decoder_fp16 = 1 if config.decoder_dtype == "fp16" else 0
         h = C.c_void_p()
         check(L.brn_model_create(C.byref(c), device, C.byref(h)))
         m = BiRefNet(h, config, device)
@@ -136,6 +138,7 @@ class BiRefNet:
             c.num_heads[i] = config.swin.num_heads[i]
         c.window_size, c.mlp_ratio, c.patch_size = config.swin.window_size, config.swin.mlp_ratio, config.swin.patch_size
         c.precision, c.deform_mode, c.micro_batch = _PREC[config.precision], _DEF[config.deform_mode], config.micro_batch
+        c.decoder_fp16 = 1 if config.decoder_dtype == "fp16" else 0
         h = C.c_void_p()
         check(L.brn_model_create(C.byref(c), device, C.byref(h)))
         return BiRefNet(h, config, device)
@@ -190,6 +193,8 @@ class BiRefNet:
             if out is None:
                 out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
             s = stream if stream is not None else torch.cuda.current_stream(x.device).cuda_stream
+            if not s:
+                s = 1   # cudaStreamLegacy: torch's default stream, explicitly (NULL would mean the handle's own stream)
             check(fn(self._h, C.c_void_p(x.data_ptr()), B, H, W, 1, C.c_void_p(out.data_ptr()), 1, C.c_void_p(s)))
             return out
         x = np.ascontiguousarray(x, dtype=np.float32)

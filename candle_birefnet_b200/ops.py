@@ -8,7 +8,7 @@ import numpy as np
 from . import _lib
 from ._lib import check, lib
 
-_PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+_PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
 
 
 def _p(a):

@@ -54,7 +54,7 @@ typedef enum { BRN_F32 = 0, BRN_BF16 = 1, BRN_F16 = 2 } brn_dtype;
 /* precision of the arithmetic (north_star): FP32 = SIMT fp32 FMA path (max |dlogit| <= 1e-3 vs the
  * reference's fp32 CPU forward); BF16 = tcgen05 tensor-core path, fp32 accumulate, fp32 residual
  * stream / LN / softmax (max |dsigmoid| <= 1e-2, IoU@0.5 >= 0.999). */
-typedef enum { BRN_PREC_FP32 = 0, BRN_PREC_BF16 = 1 } brn_precision;
+typedef enum { BRN_PREC_FP32 = 0, BRN_PREC_BF16 = 1, BRN_PREC_FP16 = 2 /* operator-level calls only */ } brn_precision;
 
 /* What `DeformConvASPP::forward` computes (src/aspp.rs:168-187):
  *   CPU_FALLBACK: regular_conv(x), offsets/modulator discarded -- the reference's behaviour on Device::Cpu
@@ -75,6 +75,7 @@ typedef struct {
   int32_t precision;      /* brn_precision (initial; changeable) */
   int32_t deform_mode;    /* brn_deform_mode (initial)           */
   int32_t micro_batch;    /* images per internal pass; 0 = auto  */
+  int32_t decoder_fp16;   /* 16-bit path: 1 = fp16 operands in the squeeze module + decoder (default), 0 = bf16 */
 } brn_config;
 
 /* BiRefNetConfig::swin_l() (src/birefnet.rs:64-66) + SwinConfig::swin_l() (src/swin.rs:69-80). */

@@ -110,6 +110,21 @@ def test_decoder_mini(mini_models, mini_cfg, mini_weights_B, precision):
     check_logits(got, exp, precision)
 
 
+def test_bf16_decoder_variant(mini_cfg, mini_weights_B):
+    """decoder_dtype="bf16" (all-bf16 operands): inside the sigmoid tolerance; the IoU criterion on random-init
+    logits (not bimodal) is what the default fp16 decoder operands are for (DESIGN.md "precision")."""
+    c = py_cfg(mini_cfg, "bf16", "deformable")
+    c.decoder_dtype = "bf16"
+    m = cb.BiRefNet.new(c, mini_weights_B)
+    x = make_input(2, 128, 192, seed=11)
+    got = m.forward_logits(x)
+    m.close()
+    exp = R.forward_logits(torch.from_numpy(x), as_torch(mini_weights_B), mini_cfg, "deformable").numpy()
+    ds = np.abs(sigmoid(got) - sigmoid(exp)).max()
+    assert ds <= 1e-2, ds
+    assert iou(sigmoid(got), sigmoid(exp)) >= 0.995
+
+
 def test_batch_independence_and_microbatch(mini_models):
     """Image sharding contract: a batch result equals the per-image results bit for bit."""
     m = mini_models["A"]

@@ -19,30 +19,35 @@ def bf16r(a):
     return torch.from_numpy(np.asarray(a, dtype=np.float32)).bfloat16().float().numpy()
 
 
+def r16(a, precision):
+    """operands as the 16-bit tensor-core path sees them"""
+    t = torch.from_numpy(np.asarray(a, dtype=np.float32))
+    if precision == "bf16":
+        return t.bfloat16().float().numpy()
+    if precision == "fp16":
+        return t.half().float().numpy()
+    return t.numpy()
+
+
 def relerr(got, exp):
     return float(np.abs(got - exp).max() / (np.abs(exp).max() + 1e-12))
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 192, 192), (1000, 576, 192), (257, 48, 96), (144, 3, 64),
                                     (5184, 2304, 768)])
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_linear(M, N, K, precision):
     rng = np.random.default_rng(M + N + K)
     a = rng.standard_normal((M, K)).astype(np.float32)
     w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     b = rng.standard_normal(N).astype(np.float32)
     got = cb.ops.linear(a, w, b, precision=precision)
-    if precision == "bf16":
-        exp = bf16r(a).astype(np.float64) @ bf16r(w).astype(np.float64).T + b
-        tol = 2e-5
-    else:
-        exp = a.astype(np.float64) @ w.astype(np.float64).T + b
-        tol = 2e-5
-    assert relerr(got, exp) < tol
+    exp = r16(a, precision).astype(np.float64) @ r16(w, precision).astype(np.float64).T + b
+    assert relerr(got, exp) < 2e-5
 
 
 @pytest.mark.parametrize("act", [1, 2])
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_linear_epilogues(act, precision):
     rng = np.random.default_rng(act)
     M, N, K = 500, 256, 128
@@ -51,7 +56,7 @@ def test_linear_epilogues(act, precision):
     b = rng.standard_normal(N).astype(np.float32)
     res = rng.standard_normal((M, N)).astype(np.float32)
     got = cb.ops.linear(a, w, b, residual=res, act=act, precision=precision)
-    aa, ww = (bf16r(a), bf16r(w)) if precision == "bf16" else (a, w)
+    aa, ww = r16(a, precision), r16(w, precision)
     z = torch.from_numpy(aa.astype(np.float64) @ ww.astype(np.float64).T + b)
     z = F.relu(z) if act == 1 else F.gelu(z)      # exact-erf GELU (src/swin.rs:105)
     exp = z.numpy() + res
@@ -60,21 +65,21 @@ def test_linear_epilogues(act, precision):
 
 @pytest.mark.parametrize("C,O,k,H,W", [(64, 64, 3, 32, 32), (64, 256, 1, 16, 24), (64, 147, 7, 16, 16), (224, 64, 3, 64, 64),
                                         (48, 64, 3, 20, 12), (128, 16, 3, 8, 8)])
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_conv2d(C, O, k, H, W, precision):
     rng = np.random.default_rng(C + O + k)
     x = rng.standard_normal((2, C, H, W)).astype(np.float32)
     w = (rng.standard_normal((O, C, k, k)) / np.sqrt(C * k * k)).astype(np.float32)
     b = rng.standard_normal(O).astype(np.float32)
     got = cb.ops.conv2d(x, w, b, act=1, precision=precision)
-    xx, ww = (bf16r(x), bf16r(w)) if precision == "bf16" else (x, w)
+    xx, ww = r16(x, precision), r16(w, precision)
     exp = F.relu(F.conv2d(torch.from_numpy(xx).double(), torch.from_numpy(ww).double(), torch.from_numpy(b).double(),
                           padding=k // 2)).numpy()
     assert relerr(got, exp) < 2e-5
 
 
 @pytest.mark.parametrize("k,sigma", [(1, 0.0), (1, 2.0), (3, 0.5), (3, 8.0), (7, 2.0)])
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_deform_conv2d(k, sigma, precision):
     import torchvision
     rng = np.random.default_rng(k * 10 + int(sigma))
@@ -84,12 +89,12 @@ def test_deform_conv2d(k, sigma, precision):
     off = (rng.standard_normal((B, 2 * k * k, H, W)) * sigma).astype(np.float32)   # incl. far out-of-bounds samples
     msk = rng.uniform(0, 2, (B, k * k, H, W)).astype(np.float32)
     got = cb.ops.deform_conv2d(x, off, msk, w, precision=precision)
-    xx, ww = (bf16r(x), bf16r(w)) if precision == "bf16" else (x, w)
+    xx, ww = r16(x, precision), r16(w, precision)
     exp = torchvision.ops.deform_conv2d(torch.from_numpy(xx).double(), torch.from_numpy(off).double(),
                                         torch.from_numpy(ww).double(), None, padding=k // 2,
                                         mask=torch.from_numpy(msk).double()).numpy()
-    # bf16 path: the gathered, modulated samples are rounded to bf16 before the MMA
-    assert relerr(got, exp) < (1e-2 if precision == "bf16" else 1e-4)
+    # 16-bit paths: the gathered, modulated samples are rounded once to bf16 / fp16 before the MMA
+    assert relerr(got, exp) < {"bf16": 1e-2, "fp16": 2e-3, "fp32": 1e-4}[precision]
 
 
 @pytest.mark.parametrize("nimg,hp,wp,heads,shift", [(1, 24, 36, 2, 0), (2, 24, 36, 2, 6), (1, 12, 12, 6, 6), (1, 72, 72, 24, 6),
