@@ -157,7 +157,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=1024)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--deform-mode", default="deformable", choices=["deformable", "cpu_fallback"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
@@ -316,7 +316,7 @@ def main():
             "metric": "images/s BiRefNet Swin-L @1024^2", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"fp16": "fp16", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"BiRefNet {args.model} forward_logits {H}x{W}, batch {B} per GPU "
                                    f"(BASELINE.json configs[2])",
                        "global_batch": B * world, "parallelism": f"image-sharded x{world}, no collective",

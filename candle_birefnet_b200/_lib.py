@@ -22,8 +22,7 @@ F32, BF16, F16 = 0, 1, 2
 class BrnConfig(C.Structure):
     _fields_ = [("embed_dim", C.c_int32), ("depths", C.c_int32 * 4), ("num_heads", C.c_int32 * 4),
                 ("window_size", C.c_int32), ("mlp_ratio", C.c_int32), ("patch_size", C.c_int32),
-                ("precision", C.c_int32), ("deform_mode", C.c_int32), ("micro_batch", C.c_int32),
-                ("decoder_fp16", C.c_int32)]
+                ("precision", C.c_int32), ("deform_mode", C.c_int32), ("micro_batch", C.c_int32)]
 
 
 class BrnError(RuntimeError):
@@ -70,6 +69,7 @@ def lib() -> C.CDLL:
     L.brn_deform_conv2d.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.brn_linear.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.brn_conv2d.argtypes = [C.c_int, C.c_int, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.brn_bench_op.argtypes = [C.c_int, C.c_int, C.c_int] + [i32] * 10 + [fp]
     L.brn_launch_count.argtypes = [vp]
     L.brn_launch_count.restype = i64
     L.brn_launch_count_reset.argtypes = [vp]

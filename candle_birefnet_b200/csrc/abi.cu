@@ -1,5 +1,7 @@
 // extern "C" surface of libbirefnet_b200.so (include/birefnet_b200.h).  Nothing throws across this boundary.
+#include <cmath>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -43,8 +45,7 @@ void brn_config_swin_l(brn_config* cfg) {
   const int d[4] = {2, 2, 18, 2}, h[4] = {6, 12, 24, 48};
   for (int i = 0; i < 4; ++i) { cfg->depths[i] = d[i]; cfg->num_heads[i] = h[i]; }
   cfg->window_size = 12; cfg->mlp_ratio = 4; cfg->patch_size = 4;
-  cfg->precision = BRN_PREC_BF16; cfg->deform_mode = BRN_DEFORM_DEFORMABLE; cfg->micro_batch = 0;
-  cfg->decoder_fp16 = 1;
+  cfg->precision = BRN_PREC_FP16; cfg->deform_mode = BRN_DEFORM_DEFORMABLE; cfg->micro_batch = 0;
 }
 
 brn_status brn_model_create(const brn_config* cfg, int device, brn_model** out) {
@@ -89,7 +90,7 @@ brn_status brn_model_finalize(brn_model* m) {
 brn_status brn_model_set_precision(brn_model* m, int precision) {
   return guard([&] {
     BRN_CHECK(m, 1, "null model");
-    BRN_CHECK(precision == BRN_PREC_FP32 || precision == BRN_PREC_BF16, 1, "bad precision");
+    BRN_CHECK(precision == BRN_PREC_FP32 || precision == BRN_PREC_BF16 || precision == BRN_PREC_FP16, 1, "bad precision");
     std::lock_guard<std::mutex> lk(m->impl.mu);
     m->impl.cfg.precision = precision;
   });
@@ -190,7 +191,7 @@ struct Scratch {
 };
 
 static LaunchCtx make_ctx(Scratch& s, int precision) {
-  LaunchCtx c; c.stream = s.stream; c.precision = precision ? BRN_PREC_BF16 : BRN_PREC_FP32; c.dry = false; c.launches = nullptr;
+  LaunchCtx c; c.stream = s.stream; c.precision = precision; c.dry = false; c.launches = nullptr;
   const char* v = getenv("BRN_FORCE_SIMT");
   c.force_simt = v && v[0] && v[0] != '0';
   return c;
@@ -203,10 +204,10 @@ brn_status brn_linear(int device, int precision, const float* a, const float* w,
     Scratch s(device);
     LaunchCtx ctx = make_ctx(s, precision);
     const int AD = precision == BRN_PREC_FP16 ? F16 : precision == BRN_PREC_BF16 ? BF16 : F32;
-    LayerW L = make_layer_standalone(N, K, 1, 1, w, bias, s.ptrs, AD == F16 ? F16 : BF16);
+    LayerW L = make_layer_standalone(N, K, 1, 1, w, bias, s.ptrs);
     View a32 = make_view(s.put(a, (size_t)M * K), F32, 1, 1, M, K);
     View ax = a32;
-    if (AD == BF16) { ax = make_view(s.alloc((size_t)M * K * 2), BF16, 1, 1, M, K); glue_copy_cast(ctx, a32, ax); }
+    if (AD != F32) { ax = make_view(s.alloc((size_t)M * K * 2), AD, 1, 1, M, K); glue_copy_cast(ctx, a32, ax); }
     View o = make_view(s.alloc((size_t)M * N * 4), F32, 1, 1, M, N);
     GemmArgs g; g.x = ax; g.w = &L; g.act = act; g.out = o;
     if (residual) g.res = make_view(s.put(residual, (size_t)M * N), F32, 1, 1, M, N);
@@ -223,7 +224,7 @@ brn_status brn_conv2d(int device, int precision, const float* x, const float* we
     Scratch s(device);
     LaunchCtx ctx = make_ctx(s, precision);
     const int AD = precision == BRN_PREC_FP16 ? F16 : precision == BRN_PREC_BF16 ? BF16 : F32;
-    LayerW L = make_layer_standalone(O, C, k, k, weight, bias, s.ptrs, AD == F16 ? F16 : BF16);
+    LayerW L = make_layer_standalone(O, C, k, k, weight, bias, s.ptrs);
     float* dx = s.put(x, (size_t)B * C * H * W);
     View xv = make_view(s.alloc((size_t)B * C * H * W * dsize(AD)), AD, B, H, W, C);
     glue_nchw_to_nhwc(ctx, dx, B, C, H, W, xv);
@@ -246,7 +247,7 @@ brn_status brn_deform_conv2d(int device, int precision, const float* x, const fl
     LaunchCtx ctx = make_ctx(s, precision);
     const int AD = precision == BRN_PREC_FP16 ? F16 : precision == BRN_PREC_BF16 ? BF16 : F32;
     const int taps = k * k;
-    LayerW L = make_layer_standalone(O, C, k, k, weight, bias, s.ptrs, AD == F16 ? F16 : BF16);
+    LayerW L = make_layer_standalone(O, C, k, k, weight, bias, s.ptrs);
     float* dx = s.put(x, (size_t)B * C * H * W);
     View xv = make_view(s.alloc((size_t)B * C * H * W * dsize(AD)), AD, B, H, W, C);
     glue_nchw_to_nhwc(ctx, dx, B, C, H, W, xv);
@@ -283,22 +284,102 @@ brn_status brn_window_attention(int device, int precision, const float* qkv, con
       for (int c = 0; c < C; ++c) hq[r * 3 * C + c] *= sc;
     View q32 = make_view(s.put(hq.data(), hq.size()), F32, 1, 1, (int)rows, 3 * C);
     View qx = q32;
-    if (AD == BF16) { qx = make_view(s.alloc(rows * 3 * C * 2), BF16, 1, 1, (int)rows, 3 * C); glue_copy_cast(ctx, q32, qx); }
+    if (AD != F32) { qx = make_view(s.alloc(rows * 3 * C * 2), AD, 1, 1, (int)rows, 3 * C); glue_copy_cast(ctx, q32, qx); }
     float* b32 = s.put(bias, (size_t)heads * 144 * 144);
     // bf16 padded copy [heads][144][152]
     std::vector<float> padded((size_t)heads * 144 * 152, 0.f);
     for (size_t r = 0; r < (size_t)heads * 144; ++r) memcpy(&padded[r * 152], &bias[r * 144], 144 * 4);
     View p32 = make_view(s.put(padded.data(), padded.size()), F32, 1, 1, heads * 144, 152);
-    View p16 = make_view(s.alloc(padded.size() * 2), BF16, 1, 1, heads * 144, 152);
+    View p16 = make_view(s.alloc(padded.size() * 2), AD == F16 ? F16 : BF16, 1, 1, heads * 144, 152);
     glue_copy_cast(ctx, p32, p16);
     View o = make_view(s.alloc(rows * C * dsize(AD)), AD, 1, 1, (int)rows, C);
-    AttnArgs a; a.qkv = qx; a.bias32 = b32; a.bias16 = (const __nv_bfloat16*)p16.p; a.n_windows = n_windows;
+    AttnArgs a; a.qkv = qx; a.bias32 = b32; a.bias16 = p16.p; a.n_windows = n_windows;
     a.heads = heads; a.nwh = hp / 12; a.nww = wp / 12; a.shift = shift; a.out = o;
     op_attention(ctx, a);
     View o32 = o;
-    if (AD == BF16) { o32 = make_view(s.alloc(rows * C * 4), F32, 1, 1, (int)rows, C); glue_copy_cast(ctx, o, o32); }
+    if (AD != F32) { o32 = make_view(s.alloc(rows * C * 4), F32, 1, 1, (int)rows, C); glue_copy_cast(ctx, o, o32); }
     BRN_CUDA(cudaMemcpyAsync(out, o32.p, rows * C * 4, cudaMemcpyDeviceToHost, s.stream));
     BRN_CUDA(cudaStreamSynchronize(s.stream));
+  });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel micro-benchmarks on device-resident synthetic data (scripts/kernel_bench.py; ncu -k targets)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void fill_kernel(void* p, int dt, long long n, unsigned seed, float scale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned h = (unsigned)(i * 2654435761u) ^ seed;
+  h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+  float v = ((h & 0xffffff) / 8388608.0f - 1.0f) * scale;
+  if (dt == F32) ((float*)p)[i] = v;
+  else if (dt == BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16(v);
+  else ((__half*)p)[i] = __float2half_rn(v);
+}
+static void fill(Scratch& s, void* p, int dt, long long n, unsigned seed, float scale) {
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s.stream>>>(p, dt, n, seed, scale);
+}
+
+// kind 0: conv/linear GEMM  x[B,H,W,C] * w[N,k,k,C] (act, optional fp32 residual, out dtype odt: 0 f32 / 1 = act dtype)
+// kind 1: window attention   (B = n_windows, C = heads)
+// kind 2: deformable conv    x[B,H,W,64] -> N, kernel k (offsets ~ N(0, 2 px))
+// Returns the mean device time per launch in *ms_out (CUDA events around `iters` back-to-back launches).
+brn_status brn_bench_op(int device, int precision, int kind, int32_t B, int32_t H, int32_t W, int32_t C, int32_t N,
+                        int32_t k, int32_t act, int32_t with_res, int32_t out_f32, int32_t iters, float* ms_out) {
+  return guard([&] {
+    BRN_CHECK(ms_out && iters > 0, 1, "brn_bench_op: bad argument");
+    Scratch s(device);
+    LaunchCtx ctx = make_ctx(s, precision);
+    const int AD = precision == BRN_PREC_FP16 ? F16 : precision == BRN_PREC_BF16 ? BF16 : F32;
+    cudaEvent_t e0, e1;
+    BRN_CUDA(cudaEventCreate(&e0)); BRN_CUDA(cudaEventCreate(&e1));
+    std::function<void()> launch;
+    LayerW L{}; GemmArgs g; AttnArgs at; DeformArgs d;
+    const size_t px = (size_t)B * H * W;
+    if (kind == 0 || kind == 2) {
+      const int taps = k * k;
+      std::vector<float> hw((size_t)N * C * taps), hb(N);
+      for (size_t i = 0; i < hw.size(); ++i) hw[i] = (float)((int)((i * 2654435761u) >> 20 & 1023) - 512) / (512.0f * sqrtf((float)C * taps));
+      for (int i = 0; i < N; ++i) hb[i] = 0.01f * (i % 7);
+      L = make_layer_standalone(N, C, k, k, hw.data(), hb.data(), s.ptrs);
+      View x = make_view(s.alloc(px * C * dsize(AD)), AD, B, H, W, C);
+      fill(s, x.p, AD, (long long)px * C, 1u, 1.0f);
+      const int OD = out_f32 ? F32 : AD;
+      View o = make_view(s.alloc(px * N * dsize(OD)), OD, B, H, W, N);
+      if (kind == 0) {
+        g.x = x; g.w = &L; g.pad = k / 2; g.act = act; g.out = o;
+        if (with_res) { g.res = make_view(s.alloc(px * N * 4), F32, B, H, W, N); fill(s, g.res.p, F32, (long long)px * N, 2u, 1.0f);
+                        g.out = make_view(g.res.p, F32, B, H, W, N); }
+        launch = [&] { op_gemm(ctx, g); };
+      } else {
+        View om = make_view(s.alloc(px * 3 * taps * 4), F32, B, H, W, 3 * taps);
+        fill(s, om.p, F32, (long long)px * 3 * taps, 3u, 2.0f);
+        d.x = x; d.om = om; d.w = &L; d.act = act; d.out = o;
+        launch = [&] { op_deform(ctx, d); };
+      }
+    } else {
+      const int heads = C, Cc = heads * 32, nwin = B;
+      const size_t rows = (size_t)nwin * 144;
+      View q = make_view(s.alloc(rows * 3 * Cc * dsize(AD)), AD, 1, 1, (int)rows, 3 * Cc);
+      fill(s, q.p, AD, (long long)rows * 3 * Cc, 5u, 1.0f);
+      void* b16 = s.alloc((size_t)heads * 144 * 152 * 2);
+      fill(s, b16, AD == F32 ? BF16 : AD, (long long)heads * 144 * 152, 6u, 0.5f);
+      float* b32 = (float*)s.alloc((size_t)heads * 144 * 144 * 4);
+      fill(s, b32, F32, (long long)heads * 144 * 144, 7u, 0.5f);
+      View o = make_view(s.alloc(rows * Cc * dsize(AD)), AD, 1, 1, (int)rows, Cc);
+      at.qkv = q; at.bias32 = b32; at.bias16 = b16; at.n_windows = nwin; at.heads = heads;
+      at.nwh = H; at.nww = W; at.shift = k; at.out = o;
+      launch = [&] { op_attention(ctx, at); };
+    }
+    for (int i = 0; i < 3; ++i) launch();
+    BRN_CUDA(cudaStreamSynchronize(s.stream));
+    BRN_CUDA(cudaEventRecord(e0, s.stream));
+    for (int i = 0; i < iters; ++i) launch();
+    BRN_CUDA(cudaEventRecord(e1, s.stream));
+    BRN_CUDA(cudaStreamSynchronize(s.stream));
+    float ms = 0; BRN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
   });
 }
 

@@ -21,6 +21,7 @@
 #include "brn_common.h"
 #include "device_utils.cuh"
 #include "tc_ptx.cuh"
+#include "tc_epilogue.cuh"
 
 namespace brn {
 
@@ -40,10 +41,11 @@ constexpr int AT_SMEM = AT_BIAS_REGION + 2 * AT_STAGE_BYTES + AT_P_REGION + 256 
 constexpr uint32_t AT_COL_S0 = 0, AT_COL_S1 = 144, AT_COL_O0 = 288, AT_COL_O1 = 320;
 
 struct AttnP {
-  const __nv_bfloat16* bias16;   // [heads][144][152]
+  const uint16_t* bias16;        // [heads][144][152], bf16 or fp16 (dt)
+  int dt;                        // operand / output element type: BF16 or F16
   int n_windows, heads, C;
   int nwh, nww, shift;
-  __nv_bfloat16* out; int ldo;
+  uint16_t* out; int ldo;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -97,8 +99,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         ptx::tma_load_2d(st + AT_TILE_BYTES, &tmQKV, &qkv_full[s], p.C + head * 32, win * 144);
         ptx::tma_load_2d(st + 2 * AT_TILE_BYTES, &tmQKV, &qkv_full[s], 2 * p.C + head * 32, win * 144);
       };
-      const uint32_t idesc_s = ptx::make_idesc_bf16(128, 144, 0, 0);   // S = Q K^T : both K-major
-      const uint32_t idesc_o = ptx::make_idesc_bf16(128, 32, 0, 1);    // O = P V   : V is MN-major
+      const uint32_t idesc_s = ptx::make_idesc_16(128, 144, 0, 0, p.dt == BF16 ? 1u : 0u);   // S = Q K^T : both K-major
+      const uint32_t idesc_o = ptx::make_idesc_16(128, 32, 0, 1, p.dt == BF16 ? 1u : 0u);    // O = P V   : V is MN-major
       if (w_first < p.n_windows) load_unit(w_first, 0);
       uint32_t full_ph[2] = {0, 0}, empty_ph[2] = {0, 0}, pf_ph = 0;
       int i = 0;
@@ -182,10 +184,10 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
 #pragma unroll
         for (int j8 = 0; j8 < ncol / 8; ++j8) {
           uint4 bq = *reinterpret_cast<const uint4*>(brow + (c * 32 + j8 * 8) * 2);
-          const __nv_bfloat162* bh = reinterpret_cast<const __nv_bfloat162*>(&bq);
+          const uint32_t* bh = reinterpret_cast<const uint32_t*>(&bq);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            float2 bf = __bfloat1622float2(bh[t]);
+            float2 bf = unpack16x2(bh[t], p.dt);
             const int k0 = c * 32 + j8 * 8 + 2 * t, k1 = k0 + 1;
             float s0 = __uint_as_float(v[j8 * 8 + 2 * t]) + bf.x + mk[((k0 / 12 >= 6) ? 2 : 0) + ((k0 % 12 >= 6) ? 1 : 0)];
             float s1 = __uint_as_float(v[j8 * 8 + 2 * t + 1]) + bf.y + mk[((k1 / 12 >= 6) ? 2 : 0) + ((k1 % 12 >= 6) ? 1 : 0)];
@@ -208,18 +210,17 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
 #pragma unroll
         for (int j8 = 0; j8 < ncol / 8; ++j8) {
           uint4 bq = *reinterpret_cast<const uint4*>(brow + (c * 32 + j8 * 8) * 2);
-          const __nv_bfloat162* bh = reinterpret_cast<const __nv_bfloat162*>(&bq);
+          const uint32_t* bh = reinterpret_cast<const uint32_t*>(&bq);
           uint32_t packed[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            float2 bf = __bfloat1622float2(bh[t]);
+            float2 bf = unpack16x2(bh[t], p.dt);
             const int k0 = c * 32 + j8 * 8 + 2 * t, k1 = k0 + 1;
             float s0 = __uint_as_float(v[j8 * 8 + 2 * t]) + bf.x + mk[((k0 / 12 >= 6) ? 2 : 0) + ((k0 % 12 >= 6) ? 1 : 0)];
             float s1 = __uint_as_float(v[j8 * 8 + 2 * t + 1]) + bf.y + mk[((k1 / 12 >= 6) ? 2 : 0) + ((k1 % 12 >= 6) ? 1 : 0)];
             float p0 = ex2(fmaf(s0, LOG2E, -moff)), p1 = ex2(fmaf(s1, LOG2E, -moff));
             sum += p0 + p1;
-            __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-            packed[t] = *reinterpret_cast<uint32_t*>(&h);
+            packed[t] = pack16x2(p0, p1, p.dt);
           }
           if (row_ok) {
             // keys [8*g, 8*g+8): K step j16 = g/2, 16-byte chunk (g&1) of the row's 32 B, XOR-swizzled with row bit 2
@@ -247,9 +248,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
             uint32_t w4[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * t]) * inv,
-                                                       __uint_as_float(v[j * 8 + 2 * t + 1]) * inv);
-              w4[t] = *reinterpret_cast<uint32_t*>(&h);
+              w4[t] = pack16x2(__uint_as_float(v[j * 8 + 2 * t]) * inv, __uint_as_float(v[j * 8 + 2 * t + 1]) * inv, p.dt);
             }
             dst[j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
@@ -266,18 +265,18 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
 void tc_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   if (ctx.launches) ++*ctx.launches;
   if (ctx.dry) return;
-  BRN_CHECK(a.qkv.dt == BF16 && a.out.dt == BF16, 5, "tc_attention: bf16 only");
+  BRN_CHECK((a.qkv.dt == BF16 || a.qkv.dt == F16) && a.out.dt == a.qkv.dt, 5, "tc_attention: bf16 or fp16 only");
   BRN_CHECK(a.qkv.ld % 8 == 0 && a.out.ld % 8 == 0 && (((uintptr_t)a.qkv.p | (uintptr_t)a.out.p) & 15) == 0, 5,
             "tc_attention: alignment");
   AttnP p{};
-  p.bias16 = a.bias16; p.n_windows = a.n_windows; p.heads = a.heads; p.C = a.heads * 32;
+  p.bias16 = (const uint16_t*)a.bias16; p.dt = a.qkv.dt; p.n_windows = a.n_windows; p.heads = a.heads; p.C = a.heads * 32;
   p.nwh = a.nwh; p.nww = a.nww; p.shift = a.shift;
-  p.out = (__nv_bfloat16*)a.out.p; p.ldo = a.out.ld;
+  p.out = (uint16_t*)a.out.p; p.ldo = a.out.ld;
   const uint64_t rows = (uint64_t)a.n_windows * 144;
   uint64_t dims[2] = {(uint64_t)3 * p.C, rows};
   uint64_t str[1] = {(uint64_t)a.qkv.ld * 2};
   uint32_t box[2] = {32, 144};
-  CUtensorMap tm = make_tmap_16(a.qkv.p, BF16, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+  CUtensorMap tm = make_tmap_16(a.qkv.p, a.qkv.dt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
   cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
   const int sms = device_sm_count();
   int per_head = std::max(1, sms / a.heads);

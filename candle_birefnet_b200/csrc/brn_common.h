@@ -64,8 +64,9 @@ struct LayerW {
   int kh = 1, kw = 1;
   int cin_pad = 0;  // Cin rounded up to 64 (K pitch per tap of the bf16 matrix)
   float* w32 = nullptr;          // [N][kh*kw][Cin]      fp32 (SIMT path)
-  void* w16 = nullptr;           // [N][kh*kw][cin_pad]  bf16 or fp16 (w16_dt), zero padded (tcgen05 path)
-  int w16_dt = BF16;
+  void* w_bf16 = nullptr;        // [N][kh*kw][cin_pad]  bf16, zero padded (tcgen05 path, precision bf16)
+  void* w_fp16 = nullptr;        // same, fp16 (precision fp16)
+  const void* w16(int dt) const { return dt == F16 ? w_fp16 : w_bf16; }
   float* bias = nullptr;         // [N] fp32 or null
   int taps() const { return kh * kw; }
 };
@@ -106,7 +107,7 @@ struct DeformArgs {
 struct AttnArgs {
   View qkv;               // [rows = nWin*144, 3C], window order, q pre-scaled
   const float* bias32 = nullptr;          // [heads][144][144] fp32
-  const __nv_bfloat16* bias16 = nullptr;  // [heads][144][152] bf16 (row padded to 304 B)
+  const void* bias16 = nullptr;           // [heads][144][152] bf16 or fp16 matching qkv.dt (rows padded to 304 B)
   int n_windows = 0;      // total windows (B * nW)
   int heads = 0;
   int nwh = 0, nww = 0;   // windows per image along h / w

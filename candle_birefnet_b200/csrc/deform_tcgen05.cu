@@ -186,14 +186,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      for (int c = 0; c < p.BN / 16; ++c) {
-        const int nb = c * 16;
-        if (nb >= p.epi.N) break;
-        uint32_t v[16];
-        ptx::tmem_ld16(taddr + c * 16, v);
-        ptx::tmem_ld_wait();
-        if (valid) epilogue_store16(p.epi, v, nb, orow, p.epi.bias);
-      }
+      epi_row(p.epi, taddr, 0, (p.epi.N + 15) >> 4, 0, 1, valid ? orow : 0, p.epi.bias, valid);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -205,7 +198,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
 }
 
 bool tc_deform_supported(const DeformArgs& a) {
-  return a.w && a.w->w16 && (a.x.dt == BF16 || a.x.dt == F16) && a.x.dt == a.w->w16_dt && a.x.C == 64 && a.w->cin_pad == 64 && a.x.ld % 8 == 0 &&
+  return a.w && (a.x.dt == BF16 || a.x.dt == F16) && a.w->w16(a.x.dt) && a.x.C == 64 && a.w->cin_pad == 64 && a.x.ld % 8 == 0 &&
          (((uintptr_t)a.x.p) & 15) == 0 && a.w->N <= 256 && a.om.dt == F32;
 }
 
@@ -225,7 +218,7 @@ void tc_deform(const LaunchCtx& ctx, const DeformArgs& a) {
   uint64_t bdims[2] = {ktot, (uint64_t)w.N};
   uint64_t bstr[1] = {ktot * 2};
   uint32_t bbox[2] = {64, (uint32_t)p.BN};
-  CUtensorMap tmB = make_tmap_16(w.w16, w.w16_dt, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tmB = make_tmap_16(w.w16(a.x.dt), a.x.dt, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B);
   cudaFuncSetAttribute(tc_deform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM);
   const int grid = std::min(p.m_tiles, device_sm_count());
   char desc[96] = "";

@@ -24,7 +24,9 @@
 
 namespace brn {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;
+constexpr int TC_EPI_WARPS = 8;                               // two per TMEM lane quadrant, interleaved column chunks
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;            // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 constexpr int TC_B_BYTES = 256 * TC_BK * 2;     // 32 KB (BN <= 256)
 constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 256 + 1024;
@@ -39,6 +41,11 @@ struct TcGemmP {
   RowMap rm;
 };
 
+// CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs own M tiles 2j and 2j+1 of the same N tile: each loads
+// half of the shared B (weight) tile and TMA-multicasts it into both CTAs' shared memory, so the L2 -> SMEM bytes per
+// 128x256x64 MMA block drop from 48 KB to 32 KB (the kernel is L2-bandwidth bound at 48 KB: ~42 B/clk/SM of L2 vs
+// 94 B/clk/SM needed to keep the tensor pipe busy).
+template <int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -52,19 +59,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
+    for (int s = 0; s < TC_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], CL); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 32 * TC_EPI_WARPS); }
     ptx::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();     // peers' barriers are initialised before any multicast can land
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // work items: (m_group, n_tile); this CTA's M tile is m_group * CL + rank
+  const int m_groups = (p.m_tiles + CL - 1) / CL;
+  const int num_items = m_groups * p.n_tiles;
+  const int item0 = blockIdx.x / CL, item_step = gridDim.x / CL;
   const int kblocks = p.taps * p.cblocks;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int TW = 1 << p.tw_log2, TH = TC_BM >> p.tw_log2;
@@ -74,9 +86,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx_bytes = TC_A_BYTES + p.BN * TC_BK * 2;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-        const int b = m_tile / tiles_per_img, r = m_tile - b * tiles_per_img;
+      const int b_rows = p.BN / CL;                           // rows of B this CTA loads (and multicasts)
+      for (int item = item0; item < num_items; item += item_step) {
+        const int m_tile = (item / p.n_tiles) * CL + rank, n_tile = item % p.n_tiles;
+        const int b = m_tile / tiles_per_img, r = m_tile - b * tiles_per_img;   // b >= B for the odd tail: TMA zero-fills
         const int y0 = (r / p.tiles_x) * TH, x0 = (r % p.tiles_x) * TW;
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
@@ -84,7 +97,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
           ptx::tma_load_4d(sA + stage * TC_A_BYTES, &tmA, &full[stage], cb * TC_BK, x0 + kx - p.pad, y0 + ky - p.pad, b);
-          ptx::tma_load_2d(sB + stage * TC_B_BYTES, &tmB, &full[stage], tap * p.cin_pad + cb * TC_BK, n_tile * p.BN);
+          uint8_t* bdst = sB + stage * TC_B_BYTES + rank * b_rows * (TC_BK * 2);
+          const int bk = tap * p.cin_pad + cb * TC_BK, bn = n_tile * p.BN + rank * b_rows;
+          if (CL > 1) ptx::tma_load_2d_mc(bdst, &tmB, &full[stage], bk, bn, (uint16_t)((1u << CL) - 1));
+          else ptx::tma_load_2d(bdst, &tmB, &full[stage], bk, bn);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -95,7 +111,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc = ptx::make_idesc_16(TC_BM, p.BN, 0, 0, p.in_bf16);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = item0; item < num_items; item += item_step) {
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
@@ -107,7 +123,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)   // +32 B (= 2 in the >>4 address field) per K=16 step inside the 128B atom
             ptx::umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          ptx::umma_commit(&empty[stage]);
+          // the stage is free once the MMAs of EVERY CTA that received the multicast have read it
+          if (CL > 1) ptx::umma_commit_mc(&empty[stage], (uint16_t)((1u << CL) - 1));
+          else ptx::umma_commit(&empty[stage]);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(&tfull[acc]);
@@ -115,34 +133,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===== epilogue: 4 warps, warp%4 selects the TMEM lane quadrant =====
+    // ===== epilogue: 8 warps; warp % 4 selects the TMEM lane quadrant, (warp - 2) / 4 the odd / even column chunks =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+    for (int item = item0; item < num_items; item += item_step) {
+      const int m_tile = (item / p.n_tiles) * CL + rank, n_tile = item % p.n_tiles;
       const int b = m_tile / tiles_per_img, r = m_tile - b * tiles_per_img;
       const int y = (r / p.tiles_x) * TH + (row >> p.tw_log2), x = (r % p.tiles_x) * TW + (row & (TW - 1));
-      bool valid = y < p.H && x < p.W;
+      bool valid = m_tile < p.m_tiles && y < p.H && x < p.W;
       long long orow = ((long long)b * p.H + y) * p.W + x;
       if (valid && p.rm.enabled) {
         orow = window_row_to_token(orow, p.rm.h, p.rm.w, p.rm.hp, p.rm.wp, p.rm.shift);
         valid = orow >= 0;
       }
+      if (!valid) orow = 0;
       const int n0 = n_tile * p.BN;
-      const float* bias = p.epi.bias ? p.epi.bias + (long long)b * p.epi.bias_bstride : nullptr;
+      const float* bias = p.epi.bias ? p.epi.bias + (long long)(valid ? b : 0) * p.epi.bias_bstride : nullptr;
+      const int nchunks = min(p.BN, p.epi.N - n0 + 15) >> 4;
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      for (int c = 0; c < p.BN / 16; ++c) {
-        const int nb = n0 + c * 16;
-        if (nb >= p.epi.N) break;
-        uint32_t v[16];
-        ptx::tmem_ld16(taddr + c * 16, v);
-        ptx::tmem_ld_wait();
-        if (!valid) continue;
-        epilogue_store16(p.epi, v, nb, orow, bias);
-      }
+      epi_row(p.epi, taddr, n0, nchunks, half, 2, orow, bias, valid);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -150,6 +163,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();     // no CTA leaves while a peer may still multicast into it / arrive on its barriers
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
@@ -195,8 +209,8 @@ int device_sm_count() {
 }
 
 bool tc_gemm_supported(const GemmArgs& a) {
-  if (!a.w || !a.w->w16) return false;
-  if ((a.x.dt != BF16 && a.x.dt != F16) || a.x.dt != a.w->w16_dt) return false;
+  if (!a.w) return false;
+  if ((a.x.dt != BF16 && a.x.dt != F16) || !a.w->w16(a.x.dt)) return false;
   if (a.x.C % 8 != 0 || a.x.ld % 8 != 0 || ((uintptr_t)a.x.p & 15)) return false;
   if (a.rowmap.enabled && !(a.x.B == 1 && a.x.H == 1)) return false;
   if (a.bias_bstride && a.x.H * a.x.W < 1) return false;
@@ -253,18 +267,38 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   const uint64_t ktot = (uint64_t)w.taps() * w.cin_pad;
   uint64_t bdims[2] = {ktot, (uint64_t)w.N};
   uint64_t bstr[1] = {ktot * 2};
-  uint32_t bbox[2] = {(uint32_t)TC_BK, (uint32_t)p.BN};
-  CUtensorMap tmB = make_tmap_16(w.w16, w.w16_dt, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B);
+  // 2-CTA clusters (B multicast) whenever there is enough work for every SM pair and BN splits into two swizzle-
+  // aligned halves; BRN_GEMM_CLUSTER=1 forces single-CTA launches (A/B testing)
+  static const bool no_cluster = [] { const char* v = getenv("BRN_GEMM_CLUSTER"); return v && v[0] == '1'; }();
+  const int sms = device_sm_count();
+  const int CL = (!no_cluster && p.BN % 32 == 0 && p.m_tiles >= 2 && (long long)p.m_tiles * p.n_tiles >= sms) ? 2 : 1;
+  uint32_t bbox[2] = {(uint32_t)TC_BK, (uint32_t)(p.BN / CL)};
+  CUtensorMap tmB = make_tmap_16(w.w16(a.x.dt), a.x.dt, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B);
 
-  cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-  const int grid = std::min(p.m_tiles * p.n_tiles, device_sm_count());
   const double rows = (double)a.x.rows();
   char desc[128] = "";
-  if (ctx.kt) snprintf(desc, sizeof desc, "M=%lld N=%d K=%dx%d BN=%d tiles=%d act=%d res=%d odt=%d", (long long)a.x.rows(),
-                       w.N, w.taps(), w.Cin, p.BN, p.m_tiles * p.n_tiles, a.act, a.res.p ? 1 : 0, a.out.dt);
+  if (ctx.kt) snprintf(desc, sizeof desc, "M=%lld N=%d K=%dx%d BN=%d tiles=%d act=%d res=%d odt=%d cl=%d", (long long)a.x.rows(),
+                       w.N, w.taps(), w.Cin, p.BN, p.m_tiles * p.n_tiles, a.act, a.res.p ? 1 : 0, a.out.dt, CL);
   KScope ks(ctx, KC_GEMM_TC, 2.0 * rows * w.N * w.taps() * w.Cin,
             rows * a.x.C * 2 + rows * w.N * dsize(a.out.dt) + (double)w.N * w.taps() * w.cin_pad * 2, desc);
-  tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM, ctx.stream>>>(tmA, tmB, p);
+  if (CL == 2) {
+    BRN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    const int items = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * std::min(items, sms / 2));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM;
+    cfg.stream = ctx.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    BRN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<2>, tmA, tmB, p));
+  } else {
+    BRN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    const int grid = std::min(p.m_tiles * p.n_tiles, sms);
+    tc_gemm_kernel<1><<<grid, TC_THREADS, TC_SMEM, ctx.stream>>>(tmA, tmB, p);
+  }
   BRN_CUDA(cudaGetLastError());
 }
 

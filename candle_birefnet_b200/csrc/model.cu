@@ -18,15 +18,16 @@ static const int kIptOut[5] = {48, 96, 192, 384, 384};    // src/birefnet.rs:180
 // dispatch
 // ------------------------------------------------------------------------------------------------
 void op_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
-  if (ctx.precision == BRN_PREC_BF16 && !ctx.force_simt && tc_gemm_supported(a)) tc_gemm(ctx, a);
+  if (ctx.precision != BRN_PREC_FP32 && !ctx.force_simt && tc_gemm_supported(a)) tc_gemm(ctx, a);
   else simt_gemm(ctx, a);
 }
 void op_deform(const LaunchCtx& ctx, const DeformArgs& a) {
-  if (ctx.precision == BRN_PREC_BF16 && !ctx.force_simt && tc_deform_supported(a)) tc_deform(ctx, a);
+  if (ctx.precision != BRN_PREC_FP32 && !ctx.force_simt && tc_deform_supported(a)) tc_deform(ctx, a);
   else simt_deform(ctx, a);
 }
 void op_attention(const LaunchCtx& ctx, const AttnArgs& a) {
-  if (ctx.precision == BRN_PREC_BF16 && !ctx.force_simt && a.qkv.dt == BF16 && a.out.dt == BF16) tc_attention(ctx, a);
+  if (ctx.precision != BRN_PREC_FP32 && !ctx.force_simt && (a.qkv.dt == BF16 || a.qkv.dt == F16) && a.out.dt == a.qkv.dt)
+    tc_attention(ctx, a);
   else simt_attention(ctx, a);
 }
 
@@ -195,24 +196,27 @@ static uint16_t f2h(float f) {
 }
 
 LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w, const float* bias,
-                             std::vector<void*>& allocs, int w16_dt) {
+                             std::vector<void*>& allocs) {
   LayerW L;
-  L.N = N; L.Cin = Cin; L.kh = kh; L.kw = kw; L.w16_dt = w16_dt;
+  L.N = N; L.Cin = Cin; L.kh = kh; L.kw = kw;
   L.cin_pad = (Cin + 63) / 64 * 64;
   const int taps = kh * kw;
   std::vector<float> w32((size_t)N * taps * Cin);
-  std::vector<uint16_t> w16((size_t)N * taps * L.cin_pad, 0);
+  std::vector<uint16_t> wbf((size_t)N * taps * L.cin_pad, 0), wfp((size_t)N * taps * L.cin_pad, 0);
   for (int n = 0; n < N; ++n)
     for (int c = 0; c < Cin; ++c)
       for (int t = 0; t < taps; ++t) {
         float v = w[((size_t)n * Cin + c) * taps + t];
         w32[((size_t)n * taps + t) * Cin + c] = v;
-        w16[((size_t)n * taps + t) * L.cin_pad + c] = w16_dt == F16 ? f2h(v) : f2bf(v);
+        wbf[((size_t)n * taps + t) * L.cin_pad + c] = f2bf(v);
+        wfp[((size_t)n * taps + t) * L.cin_pad + c] = f2h(v);
       }
   BRN_CUDA(cudaMalloc(&L.w32, w32.size() * 4)); allocs.push_back(L.w32);
   BRN_CUDA(cudaMemcpy(L.w32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice));
-  BRN_CUDA(cudaMalloc(&L.w16, w16.size() * 2)); allocs.push_back(L.w16);
-  BRN_CUDA(cudaMemcpy(L.w16, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+  BRN_CUDA(cudaMalloc(&L.w_bf16, wbf.size() * 2)); allocs.push_back(L.w_bf16);
+  BRN_CUDA(cudaMemcpy(L.w_bf16, wbf.data(), wbf.size() * 2, cudaMemcpyHostToDevice));
+  BRN_CUDA(cudaMalloc(&L.w_fp16, wfp.size() * 2)); allocs.push_back(L.w_fp16);
+  BRN_CUDA(cudaMemcpy(L.w_fp16, wfp.data(), wfp.size() * 2, cudaMemcpyHostToDevice));
   if (bias) {
     BRN_CUDA(cudaMalloc(&L.bias, (size_t)N * 4)); allocs.push_back(L.bias);
     BRN_CUDA(cudaMemcpy(L.bias, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
@@ -220,10 +224,9 @@ LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w, con
   return L;
 }
 
-LayerW Model::make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w, const std::vector<float>* bias,
-                         int w16_dt) {
+LayerW Model::make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w, const std::vector<float>* bias) {
   BRN_CHECK(w.size() == (size_t)N * Cin * kh * kw, 5, "internal: make_layer size");
-  return make_layer_standalone(N, Cin, kh, kw, w.data(), bias ? bias->data() : nullptr, allocs, w16_dt);
+  return make_layer_standalone(N, Cin, kh, kw, w.data(), bias ? bias->data() : nullptr, allocs);
 }
 
 // eval BatchNorm as (scale, shift): y = x*scale + shift  (candle batch_norm(C,1e-5).forward_t(x,false))
@@ -243,7 +246,6 @@ void Model::finalize() {
     BRN_CHECK(tensors[i].set, 3, "missing tensor: " + keys[i]);
   BRN_CUDA(cudaSetDevice(device));
 
-  const int dec16 = cfg.decoder_fp16 ? F16 : BF16;   // 16-bit operand type of the squeeze module + decoder
   // conv (+ optional BN fold) -> LayerW
   auto conv_bn = [&](const std::string& cp, bool has_bias, const std::string& bnp) -> LayerW {
     const HostTensor& w = T(cp + ".weight");
@@ -262,7 +264,7 @@ void Model::finalize() {
       }
       any_bias = true;
     }
-    return make_layer(N, Cin, k, k, wf, any_bias ? &bf : nullptr, dec16);
+    return make_layer(N, Cin, k, k, wf, any_bias ? &bf : nullptr);
   };
   auto linear = [&](const std::string& p, bool bias) -> LayerW {
     const HostTensor& w = T(p + ".weight");
@@ -302,7 +304,7 @@ void Model::finalize() {
         // index[(i,j),(k,l)] = (i-k+11)*23 + (j-l+11)  (src/swin.rs:182-184)
         const HostTensor& tb = T(p + ".attn.relative_position_bias_table");
         std::vector<float> b32((size_t)heads * 144 * 144);
-        std::vector<uint16_t> b16((size_t)heads * 144 * 152, 0);
+        std::vector<uint16_t> b16((size_t)heads * 144 * 152, 0), h16((size_t)heads * 144 * 152, 0);
         for (int h = 0; h < heads; ++h)
           for (int q = 0; q < 144; ++q)
             for (int k = 0; k < 144; ++k) {
@@ -310,10 +312,13 @@ void Model::finalize() {
               float v = tb.data[(size_t)idx * heads + h];
               b32[((size_t)h * 144 + q) * 144 + k] = v;
               b16[((size_t)h * 144 + q) * 152 + k] = f2bf(v);
+              h16[((size_t)h * 144 + q) * 152 + k] = f2h(v);
             }
         B.bias32 = upload(b32);
-        BRN_CUDA(cudaMalloc(&B.bias16, b16.size() * 2)); allocs.push_back(B.bias16);
-        BRN_CUDA(cudaMemcpy(B.bias16, b16.data(), b16.size() * 2, cudaMemcpyHostToDevice));
+        BRN_CUDA(cudaMalloc(&B.bias_bf16, b16.size() * 2)); allocs.push_back(B.bias_bf16);
+        BRN_CUDA(cudaMemcpy(B.bias_bf16, b16.data(), b16.size() * 2, cudaMemcpyHostToDevice));
+        BRN_CUDA(cudaMalloc(&B.bias_fp16, h16.size() * 2)); allocs.push_back(B.bias_fp16);
+        BRN_CUDA(cudaMemcpy(B.bias_fp16, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice));
       }
       S.blocks.push_back(B);
     }
@@ -342,7 +347,7 @@ void Model::finalize() {
       const HostTensor &mw = T(bp + ".atrous_conv.modulator_conv.weight"), &mb = T(bp + ".atrous_conv.modulator_conv.bias");
       std::vector<float> w = ow.data; w.insert(w.end(), mw.data.begin(), mw.data.end());
       std::vector<float> bb = ob.data; bb.insert(bb.end(), mb.data.begin(), mb.data.end());
-      D.br[b].om = make_layer(3 * k * k, 64, k, k, w, &bb, dec16);
+      D.br[b].om = make_layer(3 * k * k, 64, k, k, w, &bb);
       D.br[b].reg = conv_bn(bp + ".atrous_conv.regular_conv", false, bp + ".bn");
     }
     D.gap = conv_bn(a + ".global_avg_pool.1", false, a + ".global_avg_pool.2");
@@ -356,7 +361,7 @@ void Model::finalize() {
         for (int c = 0; c < 256; ++c) tail[(size_t)o * 256 + c] = (float)((double)w.data[(size_t)o * 1280 + 1024 + c] * sc[o]);
         shift[o] = (float)sh[o];
       }
-      D.conv1 = make_layer(64, 1024, 1, 1, head, nullptr, dec16);
+      D.conv1 = make_layer(64, 1024, 1, 1, head, nullptr);
       D.conv1_tail = upload(tail);
       D.bn1_shift = upload(shift);
     }
@@ -417,7 +422,7 @@ void Model::ensure_arena(size_t bytes) {
 int Model::micro_batch(int B, int H, int W) const {
   if (cfg.micro_batch > 0) return std::min(B, (int)cfg.micro_batch);
   // ~2.6 GB of workspace per 1024^2 image in bf16, twice that in fp32; keep well inside 180 GB
-  double per = 3.0e9 * ((double)H * W / (1024.0 * 1024.0)) * (cfg.precision == BRN_PREC_BF16 ? 1.0 : 2.0);
+  double per = 3.0e9 * ((double)H * W / (1024.0 * 1024.0)) * (cfg.precision != BRN_PREC_FP32 ? 1.0 : 2.0);
   int mb = (int)std::max(1.0, std::floor(100.0e9 / per));
   return std::min(B, std::min(mb, 16));
 }
@@ -465,7 +470,7 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
       View qkv = make_view(arena.alloc((size_t)Tp * 3 * Ci * dsize(AD)), AD, 1, 1, (int)Tp, 3 * Ci);
       { GemmArgs g; g.x = xw; g.w = &bw.qkv; g.out = qkv; op_gemm(ctx, g); }
       View ao = make_view(xw.p, AD, 1, 1, (int)Tp, Ci);   // reuse the xw buffer (qkv GEMM has consumed it)
-      { AttnArgs a; a.qkv = qkv; a.bias32 = bw.bias32; a.bias16 = bw.bias16; a.n_windows = (int)(Tp / 144);
+      { AttnArgs a; a.qkv = qkv; a.bias32 = bw.bias32; a.bias16 = AD == F16 ? bw.bias_fp16 : bw.bias_bf16; a.n_windows = (int)(Tp / 144);
         a.heads = heads; a.nwh = hp / 12; a.nww = wp / 12; a.shift = shift; a.out = ao; op_attention(ctx, a); }
       // proj + window_reverse + roll back + crop + residual (src/swin.rs:310,387-406)
       { GemmArgs g; g.x = ao; g.w = &bw.proj; g.out = xt; g.res = xt;

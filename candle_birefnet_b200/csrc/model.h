@@ -39,7 +39,8 @@ struct BlockW {
   float *n1g, *n1b, *n2g, *n2b;
   LayerW qkv, proj, fc1, fc2;
   float* bias32;           // [heads][144][144]
-  __nv_bfloat16* bias16;   // [heads][144][152]
+  uint16_t* bias_bf16;     // [heads][144][152] bf16
+  uint16_t* bias_fp16;     // same, fp16
 };
 struct StageW {
   std::vector<BlockW> blocks;
@@ -138,15 +139,15 @@ struct Model {
                            View X4cat, float* out, bool apply_sigmoid);
   void ensure_arena(size_t bytes);
   int micro_batch(int B, int H, int W) const;
-  int act_dtype() const { return cfg.precision == BRN_PREC_BF16 ? BF16 : F32; }   // backbone activations
-  int dec_dtype() const { return cfg.precision == BRN_PREC_BF16 ? (cfg.decoder_fp16 ? F16 : BF16) : F32; }  // decoder
+  // element type of stored activations / GEMM operands for the current precision (fp32 | bf16 | fp16)
+  int act_dtype() const { return cfg.precision == BRN_PREC_BF16 ? BF16 : cfg.precision == BRN_PREC_FP16 ? F16 : F32; }
+  int dec_dtype() const { return act_dtype(); }
   void prof_begin(LaunchCtx& ctx, const char* name);
   void prof_end(LaunchCtx& ctx);
 
   const HostTensor& T(const std::string& k) const;
   float* upload(const std::vector<float>& v);
-  LayerW make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w_oihw, const std::vector<float>* bias,
-                    int w16_dt = BF16);
+  LayerW make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w_oihw, const std::vector<float>* bias);
 };
 
 // generic dispatchers (precision + support -> tcgen05 or SIMT)
@@ -156,6 +157,6 @@ void op_attention(const LaunchCtx&, const AttnArgs&);
 
 // standalone layer upload for the operator-level ABI
 LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w_oihw, const float* bias,
-                             std::vector<void*>& allocs, int w16_dt = BF16);
+                             std::vector<void*>& allocs);
 
 }  // namespace brn

@@ -51,17 +51,16 @@ class BiRefNetConfig:
     ms_supervision: bool = True
     dec_ipt: bool = True
     use_aspp_deformable: bool = True
-    precision: str = "bf16"            # "bf16" (tcgen05) | "fp32" (SIMT)
+    precision: str = "fp16"            # tcgen05 path with "fp16" | "bf16" operands, or "fp32" (SIMT FMA path)
     deform_mode: str = "deformable"    # "deformable" (Metal path semantics) | "cpu_fallback" (candle CPU semantics)
     micro_batch: int = 0
-    decoder_dtype: str = "fp16"        # 16-bit path: operand type of squeeze module + decoder ("fp16" | "bf16")
 
     @staticmethod
     def swin_l() -> "BiRefNetConfig":
         return BiRefNetConfig()
 
 
-_PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+_PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
 _DEF = {"cpu_fallback": _lib.DEFORM_CPU_FALLBACK, "deformable": _lib.DEFORM_DEFORMABLE}
 
 
@@ -86,7 +85,6 @@ class BiRefNet:
             c.num_heads[i] = config.swin.num_heads[i]
         c.window_size, c.mlp_ratio, c.patch_size = config.swin.window_size, config.swin.mlp_ratio, config.swin.patch_size
         c.precision, c.deform_mode, c.micro_batch = _PREC[config.precision], _DEF[config.deform_mode], config.micro_batch
-        c.decoder_fp16 = 1 if config.decoder_dtype == "fp16" else 0
         h = C.c_void_p()
         check(L.brn_model_create(C.byref(c), device, C.byref(h)))
         m = BiRefNet(h, config, device)
@@ -138,7 +136,6 @@ class BiRefNet:
             c.num_heads[i] = config.swin.num_heads[i]
         c.window_size, c.mlp_ratio, c.patch_size = config.swin.window_size, config.swin.mlp_ratio, config.swin.patch_size
         c.precision, c.deform_mode, c.micro_batch = _PREC[config.precision], _DEF[config.deform_mode], config.micro_batch
-        c.decoder_fp16 = 1 if config.decoder_dtype == "fp16" else 0
         h = C.c_void_p()
         check(L.brn_model_create(C.byref(c), device, C.byref(h)))
         return BiRefNet(h, config, device)

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+from ctypes import c_float as C_float
 
 import numpy as np
 
@@ -61,3 +62,13 @@ def window_attention(qkv, bias, hp: int, wp: int, shift: int, precision: str = "
     out = np.empty((nwin, 144, heads * 32), dtype=np.float32)
     check(lib().brn_window_attention(device, _PREC[precision], _p(qkv), _p(bias), nwin, heads, hp, wp, shift, _p(out)))
     return out
+
+
+def bench_op(kind: str, B: int, H: int, W: int, C: int, N: int = 0, k: int = 1, act: int = 0, with_res: bool = False,
+             out_f32: bool = False, iters: int = 20, precision: str = "fp16", device: int = 0) -> float:
+    """Mean device ms per launch of one kernel on synthetic device-resident data (kind: gemm | attn | deform)."""
+    ms = C_float()
+    kid = {"gemm": 0, "attn": 1, "deform": 2}[kind]
+    check(lib().brn_bench_op(device, _PREC[precision], kid, B, H, W, C, N, k, act, int(with_res), int(out_f32), iters,
+                             C.byref(ms)))
+    return float(ms.value)

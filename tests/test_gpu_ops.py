@@ -99,7 +99,7 @@ def test_deform_conv2d(k, sigma, precision):
 
 @pytest.mark.parametrize("nimg,hp,wp,heads,shift", [(1, 24, 36, 2, 0), (2, 24, 36, 2, 6), (1, 12, 12, 6, 6), (1, 72, 72, 24, 6),
                                                      (1, 264, 264, 6, 6)])
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_window_attention(nimg, hp, wp, heads, shift, precision):
     """softmax(scale q k^T + bias (+ -100 region mask)) v, the plain chain of examples/test_flash_bias.rs:30-36."""
     rng = np.random.default_rng(hp + heads + shift)
@@ -108,7 +108,7 @@ def test_window_attention(nimg, hp, wp, heads, shift, precision):
     qkv = rng.standard_normal((nimg * nw, 144, 3 * C)).astype(np.float32)
     bias = (rng.standard_normal((heads, 144, 144)) * 0.5).astype(np.float32)
     got = cb.ops.window_attention(qkv, bias, hp, wp, shift, precision=precision)
-    t = torch.from_numpy(bf16r(qkv) if precision == "bf16" else qkv).double()
+    t = torch.from_numpy(r16(qkv, precision)).double()
     q, k, v = [t[..., i * C:(i + 1) * C].reshape(nimg * nw, 144, heads, 32).permute(0, 2, 1, 3) for i in range(3)]
     s = (q * 32 ** -0.5) @ k.transpose(-1, -2) + torch.from_numpy(bias).double()
     if shift:
@@ -116,5 +116,5 @@ def test_window_attention(nimg, hp, wp, heads, shift, precision):
         s = (s.reshape(nimg, nw, heads, 144, 144) + m[None, :, None]).reshape(nimg * nw, heads, 144, 144)
     exp = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(nimg * nw, 144, C).numpy()
     err = np.abs(got - exp).max()
-    # bf16: q (scaled), bias, P and the output are rounded to bf16 (8 mantissa bits); |out| <= ~1
-    assert err < (3e-2 if precision == "bf16" else 2e-5), err
+    # 16-bit paths: q (scaled), bias, P and the output are rounded to bf16 / fp16; |out| <= ~1
+    assert err < {"bf16": 3e-2, "fp16": 4e-3, "fp32": 2e-5}[precision], err
