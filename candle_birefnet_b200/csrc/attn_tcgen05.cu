@@ -5,15 +5,22 @@
 // relative-position bias of WindowAttention::new (src/swin.rs:143-152) and the analytic -100 region mask of
 // BasicLayer::create_attention_mask (src/swin.rs:603-655).  The [nW,heads,144,144] score tensor never leaves the SM.
 //
-// Work unit = (window, head).  A persistent CTA owns ONE head (its 144x144 bias stays resident in shared memory as
-// bf16, rows padded to 304 B so row-per-thread 16-byte reads are bank-conflict free) and walks the windows.
-//   warp 5   : one elected thread issues TMA (Q,K,V tiles of the window-ordered qkv matrix, 64B-swizzled, 2 stages)
-//              and all tcgen05.mma:  S = Q K^T (two M=128 tiles for the 144 queries, N=144, K=32) into TMEM,
-//              then O = P V (M=128 x2, N=32, K=144; V is the MN-major B operand straight from the TMA tile).
-//   warps 0-3: softmax for query rows 0..127 (one row per thread: TMEM lane == query), warp 4: rows 128..143.
-//              Two passes over the S row (tcgen05.ld 32 columns at a time): max, then exp2 / sum / bf16 P written
-//              to shared memory in the 32B-swizzled K-major layout the P V MMA reads.  1/sum is applied to O.
-// Bound: MUFU (144*144 exp per unit) -- see DESIGN.md; tensor work per unit is ~600 cycles vs ~1300 of exp.
+// Work unit = (window, head).  A persistent CTA owns ONE head (its 144x144 bias stays resident in shared memory,
+// rows padded to 304 B so row-per-thread 16-byte reads are bank-conflict free) and walks the windows.
+//   warp 10  : one elected thread issues TMA (Q,K,V tiles of the window-ordered qkv matrix, 64B-swizzled, 3 stages)
+//              and all tcgen05.mma:  S = Q K^T (M=128 tiles over the 144 queries, N=144, K=32) into TMEM, then
+//              O = P V (M=128 x2, N=32, K=144; V is the MN-major B operand straight from the TMA tile).
+//   warps 0-9: softmax.  Every query row is split between TWO threads (keys 0-71 / 72-143), so a thread keeps its 72
+//              scores in registers: S is read from TMEM once and released immediately, which lets the MMA warp
+//              compute S of the NEXT window while this one is in its exp phase.  warps 0-3 / 4-7: rows 0-127
+//              (TMEM lane quadrant = warp % 4), warps 8 / 9: rows 128-143.  Row max and row sum are combined
+//              through shared memory; P (bf16/fp16) goes to shared memory in the 32B-swizzled K-major layout the
+//              P V MMA reads; 1/sum is applied to O in the epilogue, which is deferred into the next unit's softmax
+//              so the P V latency is hidden.
+//   TMEM   : S0 [0,144) rows 0-127 | S1a [144,288) rows 128-143 in lanes 0-15 (for warp 8) | S1b [288,432) the same
+//            rows in lanes 32-47 (A tile started 32 rows earlier; for warp 9, whose quadrant is lanes 32-63) |
+//            O0 [432,464) | O1 [464,496).
+// Bound: MUFU (144*144 exp per unit = 1296 clk at 16/clk/SM) vs ~650 clk of tensor work per unit.
 #include <cuda.h>
 
 #include <cstdio>
@@ -29,16 +36,20 @@ CUtensorMap make_tmap_16(const void* base, int dt, int rank, const uint64_t* dim
                          const uint32_t* box, CUtensorMapSwizzle swz);
 int device_sm_count();
 
-constexpr int AT_THREADS = 192;
-constexpr int AT_BIAS_LD = 152;                          // bf16 elements per bias row (304 B)
+constexpr int AT_SOFT_WARPS = 10;
+constexpr int AT_SOFT_THREADS = 32 * AT_SOFT_WARPS;      // 320
+constexpr int AT_THREADS = AT_SOFT_THREADS + 32;         // + control warp
+constexpr int AT_BIAS_LD = 152;                          // 16-bit elements per bias row (304 B)
 constexpr int AT_BIAS_BYTES = 144 * AT_BIAS_LD * 2;      // 43,776
-constexpr int AT_BIAS_REGION = 44 * 1024;                // 45,056 (1 KB aligned)
+constexpr int AT_BIAS_REGION = 44 * 1024;
 constexpr int AT_TILE_BYTES = 144 * 64;                  // one of Q/K/V: 9,216
-constexpr int AT_STAGE_BYTES = 3 * AT_TILE_BYTES;        // 27,648 = 27 KB
+constexpr int AT_STAGE_BYTES = 3 * AT_TILE_BYTES;        // 27,648
+constexpr int AT_STAGES = 3;
 constexpr int AT_P_BLOCK = 144 * 32;                     // one K=16 step of P: 4,608
 constexpr int AT_P_REGION = 44 * 1024;                   // 9 blocks (41,472) + over-read slack of the 16-row tile
-constexpr int AT_SMEM = AT_BIAS_REGION + 2 * AT_STAGE_BYTES + AT_P_REGION + 256 + 1024;
-constexpr uint32_t AT_COL_S0 = 0, AT_COL_S1 = 144, AT_COL_O0 = 288, AT_COL_O1 = 320;
+constexpr int AT_STAT_BYTES = 2 * 2 * 2 * 144 * 4;       // {max,sum} x parity x half x row
+constexpr int AT_SMEM = AT_BIAS_REGION + AT_STAGES * AT_STAGE_BYTES + AT_P_REGION + AT_STAT_BYTES + 256 + 1024;
+constexpr uint32_t AT_COL_S0 = 0, AT_COL_S1A = 144, AT_COL_S1B = 288, AT_COL_O0 = 432, AT_COL_O1 = 464;
 
 struct AttnP {
   const uint16_t* bias16;        // [heads][144][152], bf16 or fp16 (dt)
@@ -54,80 +65,100 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// tcgen05.wait::ld tied to the destination registers (keeps uses below the wait)
+__device__ __forceinline__ void tmem_wait32(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait8(uint32_t (&v)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void soft_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(AT_SOFT_THREADS) : "memory"); }
+
 __global__ void __launch_bounds__(AT_THREADS, 1)
 tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sBias = smem;
   uint8_t* sQKV = smem + AT_BIAS_REGION;
-  uint8_t* sP = sQKV + 2 * AT_STAGE_BYTES;
-  uint64_t* bars = (uint64_t*)(sP + AT_P_REGION);
-  uint64_t* qkv_full = bars;        // [2]
-  uint64_t* qkv_empty = bars + 2;   // [2]
-  uint64_t* s_full = bars + 4;
-  uint64_t* p_full = bars + 5;
-  uint64_t* o_full = bars + 6;
-  uint64_t* bias_bar = bars + 7;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+  uint8_t* sP = sQKV + AT_STAGES * AT_STAGE_BYTES;
+  float* sStat = (float*)(sP + AT_P_REGION);                 // smax[par][half][row], then ssum[par][half][row]
+  uint64_t* bars = (uint64_t*)((uint8_t*)sStat + AT_STAT_BYTES);
+  uint64_t* qkv_full = bars;        // [3]
+  uint64_t* qkv_empty = bars + 3;   // [3]
+  uint64_t* s_full = bars + 6;
+  uint64_t* s_empty = bars + 7;
+  uint64_t* p_full = bars + 8;
+  uint64_t* o_full = bars + 9;
+  uint64_t* bias_bar = bars + 10;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x % p.heads;
   const int w_first = blockIdx.x / p.heads, w_step = gridDim.x / p.heads;
+  const int n_units = w_first < p.n_windows ? (p.n_windows - w_first + w_step - 1) / w_step : 0;
 
-  if (threadIdx.x == 160) {
-    ptx::mbar_init(&qkv_full[0], 1); ptx::mbar_init(&qkv_full[1], 1);
-    ptx::mbar_init(&qkv_empty[0], 1); ptx::mbar_init(&qkv_empty[1], 1);
-    ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, 160); ptx::mbar_init(o_full, 1);
+  if (threadIdx.x == AT_SOFT_THREADS) {
+    for (int s = 0; s < AT_STAGES; ++s) { ptx::mbar_init(&qkv_full[s], 1); ptx::mbar_init(&qkv_empty[s], 1); }
+    ptx::mbar_init(s_full, 1); ptx::mbar_init(s_empty, AT_SOFT_THREADS);
+    ptx::mbar_init(p_full, AT_SOFT_THREADS); ptx::mbar_init(o_full, 1);
     ptx::mbar_init(bias_bar, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 5) ptx::tmem_alloc(tmem_slot, 512);
+  if (warp == AT_SOFT_WARPS) ptx::tmem_alloc(tmem_slot, 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 5) {
-    if (ptx::elect_one()) {
+  if (warp == AT_SOFT_WARPS) {
+    if (ptx::elect_one() && n_units > 0) {
+      // ===== TMA + MMA issuer =====
       ptx::prefetch_tmap(&tmQKV);
       ptx::mbar_expect_tx(bias_bar, AT_BIAS_BYTES);
       ptx::bulk_load(sBias, p.bias16 + (size_t)head * 144 * AT_BIAS_LD, AT_BIAS_BYTES, bias_bar);
-      auto load_unit = [&](int win, int s) {
+      const uint32_t is_bf = p.dt == BF16 ? 1u : 0u;
+      const uint32_t idesc_s = ptx::make_idesc_16(128, 144, 0, 0, is_bf);   // S = Q K^T : both K-major
+      const uint32_t idesc_o = ptx::make_idesc_16(128, 32, 0, 1, is_bf);    // O = P V   : V is MN-major
+      auto load_unit = [&](int i) {
+        const int s = i % AT_STAGES, win = w_first + i * w_step;
         uint8_t* st = sQKV + s * AT_STAGE_BYTES;
         ptx::mbar_expect_tx(&qkv_full[s], AT_STAGE_BYTES);
         ptx::tma_load_2d(st, &tmQKV, &qkv_full[s], head * 32, win * 144);
         ptx::tma_load_2d(st + AT_TILE_BYTES, &tmQKV, &qkv_full[s], p.C + head * 32, win * 144);
         ptx::tma_load_2d(st + 2 * AT_TILE_BYTES, &tmQKV, &qkv_full[s], 2 * p.C + head * 32, win * 144);
       };
-      const uint32_t idesc_s = ptx::make_idesc_16(128, 144, 0, 0, p.dt == BF16 ? 1u : 0u);   // S = Q K^T : both K-major
-      const uint32_t idesc_o = ptx::make_idesc_16(128, 32, 0, 1, p.dt == BF16 ? 1u : 0u);    // O = P V   : V is MN-major
-      if (w_first < p.n_windows) load_unit(w_first, 0);
-      uint32_t full_ph[2] = {0, 0}, empty_ph[2] = {0, 0}, pf_ph = 0;
-      int i = 0;
-      for (int win = w_first; win < p.n_windows; win += w_step, ++i) {
-        const int s = i & 1;
-        const uint32_t q_addr = ptx::smem_u32(sQKV + s * AT_STAGE_BYTES);
-        const uint32_t k_addr = q_addr + AT_TILE_BYTES, v_addr = q_addr + 2 * AT_TILE_BYTES;
-        ptx::mbar_wait(&qkv_full[s], full_ph[s]); full_ph[s] ^= 1;
-        ptx::tc_fence_after();
-        // S tiles: K-major, 64B swizzle: 8-row groups 512 B apart; +32 B per K=16 step
+      auto issue_s = [&](int i) {
+        const uint32_t q_addr = ptx::smem_u32(sQKV + (i % AT_STAGES) * AT_STAGE_BYTES), k_addr = q_addr + AT_TILE_BYTES;
+        // K-major, 64B swizzle: 8-row groups 512 B apart; +32 B per K=16 step.  A tiles start at query rows 0 / 128 / 96.
+        const uint32_t a_row[3] = {0, 128, 96};
+        const uint32_t d_col[3] = {AT_COL_S0, AT_COL_S1A, AT_COL_S1B};
+        const uint64_t b = ptx::make_smem_desc(k_addr, 16, 512, ptx::SW_64B);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const uint64_t a = ptx::make_smem_desc(q_addr + t * 128 * 64, 16, 512, ptx::SW_64B);
-          const uint64_t b = ptx::make_smem_desc(k_addr, 16, 512, ptx::SW_64B);
+        for (int t = 0; t < 3; ++t) {
+          const uint64_t a = ptx::make_smem_desc(q_addr + a_row[t] * 64, 16, 512, ptx::SW_64B);
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            ptx::umma_f16_ss(tmem_base + (t ? AT_COL_S1 : AT_COL_S0), a + 2 * k, b + 2 * k, idesc_s, k);
+          for (int k = 0; k < 2; ++k) ptx::umma_f16_ss(tmem_base + d_col[t], a + 2 * k, b + 2 * k, idesc_s, k);
         }
         ptx::umma_commit(s_full);
-        // prefetch the next window's tiles into the other stage
-        if (win + w_step < p.n_windows) {
-          if (i >= 1) { ptx::mbar_wait(&qkv_empty[s ^ 1], empty_ph[s ^ 1]); empty_ph[s ^ 1] ^= 1; }
-          load_unit(win + w_step, s ^ 1);
-        }
-        // O tiles once P is in shared memory
-        ptx::mbar_wait(p_full, pf_ph); pf_ph ^= 1;
-        ptx::tc_fence_after();
+      };
+      auto issue_pv = [&](int i) {
+        const int s = i % AT_STAGES;
+        const uint32_t v_addr = ptx::smem_u32(sQKV + s * AT_STAGE_BYTES) + 2 * AT_TILE_BYTES;
         const uint32_t p_addr = ptx::smem_u32(sP);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -142,124 +173,155 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         }
         ptx::umma_commit(o_full);
         ptx::umma_commit(&qkv_empty[s]);
+      };
+      load_unit(0);
+      if (n_units > 1) load_unit(1);
+      ptx::mbar_wait(&qkv_full[0], 0);
+      ptx::tc_fence_after();
+      issue_s(0);
+      for (int i = 0; i < n_units; ++i) {
+        if (i + 1 < n_units) {      // S of the next unit as soon as this unit's scores sit in registers
+          ptx::mbar_wait(&qkv_full[(i + 1) % AT_STAGES], ((i + 1) / AT_STAGES) & 1);
+          ptx::mbar_wait(s_empty, i & 1);
+          ptx::tc_fence_after();
+          issue_s(i + 1);
+        }
+        if (i + 2 < n_units) {      // prefetch two units ahead; that stage held unit i-1
+          if (i >= 1) ptx::mbar_wait(&qkv_empty[(i + 2) % AT_STAGES], ((i - 1) / AT_STAGES) & 1);
+          load_unit(i + 2);
+        }
+        ptx::mbar_wait(p_full, i & 1);
+        ptx::tc_fence_after();
+        issue_pv(i);
       }
     }
-  } else {
-    // ===== softmax + epilogue: warps 0-3 -> rows 0..127, warp 4 -> rows 128..143 =====
-    const int tile = warp == 4 ? 1 : 0;
-    const int r = tile ? 128 + lane : warp * 32 + lane;      // query row (>= 144 for the idle lanes of warp 4)
+  } else if (n_units > 0) {
+    // ===== softmax + epilogue =====
+    const int tile = warp >= 8 ? 1 : 0;
+    const int half = tile ? warp - 8 : warp >> 2;              // keys [72*half, 72*half + 72)
+    const int quad = warp & 3;
+    const int r = tile ? 128 + lane : quad * 32 + lane;        // query row (>= 144 for the idle lanes of warps 8, 9)
     const bool row_ok = r < 144;
     const int rr = row_ok ? r : 143;
-    const uint32_t lane_base = tmem_base + ((uint32_t)((tile ? 0 : warp) * 32) << 16);
-    const uint32_t s_col = tile ? AT_COL_S1 : AT_COL_S0, o_col = tile ? AT_COL_O1 : AT_COL_O0;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t s_col = (tile ? (half ? AT_COL_S1B : AT_COL_S1A) : AT_COL_S0) + half * 72;
     const int qi = rr / 12, qj = rr % 12;
     const float LOG2E = 1.4426950408889634f;
-    ptx::mbar_wait(bias_bar, 0);
-    const uint8_t* brow = sBias + (size_t)rr * AT_BIAS_LD * 2;
-    uint32_t ph = 0;
+    float* smax = sStat;
+    float* ssum = sStat + 2 * 2 * 144;
     const int nw = p.nwh * p.nww;
-    for (int win = w_first; win < p.n_windows; win += w_step) {
-      // analytic shift mask (src/swin.rs:603-655): only the last window row / column mixes regions
+    ptx::mbar_wait(bias_bar, 0);
+    const uint8_t* brow = sBias + (size_t)rr * AT_BIAS_LD * 2 + half * 144;
+
+    auto epilogue = [&](int j) {   // O(j) / sum(j) -> 16-bit, head-major channel (src/swin.rs:306-307)
+      const int par = j & 1, win = w_first + j * w_step;
+      ptx::mbar_wait(o_full, par);
+      ptx::tc_fence_after();
+      const float inv = 1.f / (ssum[(par * 2 + 0) * 144 + rr] + ssum[(par * 2 + 1) * 144 + rr]);
+      if (!tile) {
+        uint32_t v[16];
+        ptx::tmem_ld16(lane_base + AT_COL_O0 + half * 16, v);
+        tmem_wait_dep(v);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)win * 144 + r) * p.ldo + head * 32 + half * 16);
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          dst[g] = make_uint4(pack16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv, p.dt),
+                              pack16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv, p.dt),
+                              pack16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv, p.dt),
+                              pack16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv, p.dt));
+      } else if (half == 0) {       // rows 128-143 live in lanes 0-15 of quadrant 0: warp 8 writes all 32 dims
+        uint32_t v[32];
+        ptx::tmem_ld32(lane_base + AT_COL_O1, v);
+        tmem_wait32(v);
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)win * 144 + r) * p.ldo + head * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            dst[g] = make_uint4(pack16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv, p.dt),
+                                pack16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv, p.dt),
+                                pack16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv, p.dt),
+                                pack16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv, p.dt));
+        }
+      }
+    };
+
+    for (int i = 0; i < n_units; ++i) {
+      const int par = i & 1, win = w_first + i * w_step;
+      // analytic shift mask (src/swin.rs:603-655): only the last window row / column mixes regions.  This thread's
+      // keys all have (ki >= 6) == half; kj >= 6 depends on the key column.
       const int wl = win % nw, wi = wl / p.nww, wj = wl - wi * p.nww;
       const bool last_r = p.shift > 0 && wi == p.nwh - 1, last_c = p.shift > 0 && wj == p.nww - 1;
-      float mk[4];   // index = (ki>=6)*2 + (kj>=6)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const bool kih = c >> 1, kjh = c & 1;
-        mk[c] = ((last_r && (kih != (qi >= 6))) || (last_c && (kjh != (qj >= 6)))) ? -100.0f : 0.0f;
-      }
-      ptx::mbar_wait(s_full, ph);
+      const bool rmask = last_r && ((half != 0) != (qi >= 6));
+      float mk[2];   // index = (kj >= 6)
+      mk[0] = (rmask || (last_c && (qj >= 6))) ? -100.0f : 0.0f;
+      mk[1] = (rmask || (last_c && (qj < 6))) ? -100.0f : 0.0f;
+
+      // ---- scores: TMEM -> registers once, then hand the S region back to the MMA warp ----
+      uint32_t v0[32], v1[32], v2[8];
+      ptx::mbar_wait(s_full, par);
       ptx::tc_fence_after();
-      // ---- pass 1: row max of s + bias + mask ----
+      ptx::tmem_ld32(lane_base + s_col, v0);
+      ptx::tmem_ld32(lane_base + s_col + 32, v1);
+      tmem_ld8(lane_base + s_col + 64, v2);
+      tmem_wait32(v0); tmem_wait32(v1); tmem_wait8(v2);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(s_empty);
+
+      // ---- pass 1: s + bias + mask (kept in registers), partial row max ----
+      float sc[72];
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        uint32_t v[32];
-        if (c < 4) ptx::tmem_ld32(lane_base + s_col + c * 32, v);
-        else { uint32_t u[16]; ptx::tmem_ld16(lane_base + s_col + 128, u);
+      for (int g = 0; g < 9; ++g) {
+        const uint4 bq = *reinterpret_cast<const uint4*>(brow + g * 16);
+        const uint32_t* bh = reinterpret_cast<const uint32_t*>(&bq);
 #pragma unroll
-               for (int j = 0; j < 16; ++j) v[j] = u[j]; }
-        ptx::tmem_ld_wait();
-        const int ncol = c < 4 ? 32 : 16;
-#pragma unroll
-        for (int j8 = 0; j8 < ncol / 8; ++j8) {
-          uint4 bq = *reinterpret_cast<const uint4*>(brow + (c * 32 + j8 * 8) * 2);
-          const uint32_t* bh = reinterpret_cast<const uint32_t*>(&bq);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float2 bf = unpack16x2(bh[t], p.dt);
-            const int k0 = c * 32 + j8 * 8 + 2 * t, k1 = k0 + 1;
-            float s0 = __uint_as_float(v[j8 * 8 + 2 * t]) + bf.x + mk[((k0 / 12 >= 6) ? 2 : 0) + ((k0 % 12 >= 6) ? 1 : 0)];
-            float s1 = __uint_as_float(v[j8 * 8 + 2 * t + 1]) + bf.y + mk[((k1 / 12 >= 6) ? 2 : 0) + ((k1 % 12 >= 6) ? 1 : 0)];
-            mx = fmaxf(mx, fmaxf(s0, s1));
-          }
+        for (int t = 0; t < 4; ++t) {
+          const float2 bf = unpack16x2(bh[t], p.dt);
+          const int c0 = g * 8 + 2 * t, c1 = c0 + 1;       // key column within this half; 72 = 6 * 12 so kj = c % 12
+          const float a0 = __uint_as_float(c0 < 32 ? v0[c0 & 31] : c0 < 64 ? v1[c0 & 31] : v2[c0 & 7]);
+          const float a1 = __uint_as_float(c1 < 32 ? v0[c1 & 31] : c1 < 64 ? v1[c1 & 31] : v2[c1 & 7]);
+          sc[c0] = a0 + bf.x + mk[(c0 % 12) >= 6 ? 1 : 0];
+          sc[c1] = a1 + bf.y + mk[(c1 % 12) >= 6 ? 1 : 0];
+          mx = fmaxf(mx, fmaxf(sc[c0], sc[c1]));
         }
       }
-      const float moff = mx * LOG2E;
-      // ---- pass 2: p = exp2((s - max) * log2e), row sum, bf16 P -> shared memory (K-major, 32B swizzle) ----
+      if (row_ok) smax[(par * 2 + half) * 144 + r] = mx;
+      soft_bar_sync();
+      const float m = fmaxf(smax[(par * 2 + 0) * 144 + rr], smax[(par * 2 + 1) * 144 + rr]);
+      const float moff = m * LOG2E;
+
+      // ---- deferred epilogue of the previous unit (its P V finished long ago); also frees the P buffer ----
+      if (i > 0) epilogue(i - 1);
+
+      // ---- pass 2: p = exp2((s - max) * log2e), partial row sum, 16-bit P -> shared (K-major, 32B swizzle) ----
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        uint32_t v[32];
-        if (c < 4) ptx::tmem_ld32(lane_base + s_col + c * 32, v);
-        else { uint32_t u[16]; ptx::tmem_ld16(lane_base + s_col + 128, u);
+      for (int g = 0; g < 9; ++g) {
+        uint32_t packed[4];
 #pragma unroll
-               for (int j = 0; j < 16; ++j) v[j] = u[j]; }
-        ptx::tmem_ld_wait();
-        const int ncol = c < 4 ? 32 : 16;
-#pragma unroll
-        for (int j8 = 0; j8 < ncol / 8; ++j8) {
-          uint4 bq = *reinterpret_cast<const uint4*>(brow + (c * 32 + j8 * 8) * 2);
-          const uint32_t* bh = reinterpret_cast<const uint32_t*>(&bq);
-          uint32_t packed[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float2 bf = unpack16x2(bh[t], p.dt);
-            const int k0 = c * 32 + j8 * 8 + 2 * t, k1 = k0 + 1;
-            float s0 = __uint_as_float(v[j8 * 8 + 2 * t]) + bf.x + mk[((k0 / 12 >= 6) ? 2 : 0) + ((k0 % 12 >= 6) ? 1 : 0)];
-            float s1 = __uint_as_float(v[j8 * 8 + 2 * t + 1]) + bf.y + mk[((k1 / 12 >= 6) ? 2 : 0) + ((k1 % 12 >= 6) ? 1 : 0)];
-            float p0 = ex2(fmaf(s0, LOG2E, -moff)), p1 = ex2(fmaf(s1, LOG2E, -moff));
-            sum += p0 + p1;
-            packed[t] = pack16x2(p0, p1, p.dt);
-          }
-          if (row_ok) {
-            // keys [8*g, 8*g+8): K step j16 = g/2, 16-byte chunk (g&1) of the row's 32 B, XOR-swizzled with row bit 2
-            const int g = c * 4 + j8, j16 = g >> 1, ch = (g & 1) ^ ((r >> 2) & 1);
-            *reinterpret_cast<uint4*>(sP + j16 * AT_P_BLOCK + r * 32 + ch * 16) =
-                make_uint4(packed[0], packed[1], packed[2], packed[3]);
-          }
+        for (int t = 0; t < 4; ++t) {
+          const float p0 = ex2(fmaf(sc[g * 8 + 2 * t], LOG2E, -moff)), p1 = ex2(fmaf(sc[g * 8 + 2 * t + 1], LOG2E, -moff));
+          sum += p0 + p1;
+          packed[t] = pack16x2(p0, p1, p.dt);
+        }
+        if (row_ok) {
+          // keys [8*G, 8*G+8), G = 9*half + g: K step G/2, 16-byte chunk (G&1) of the row's 32 B, XOR row bit 2
+          const int G = 9 * half + g, j16 = G >> 1, ch = (G & 1) ^ ((r >> 2) & 1);
+          *reinterpret_cast<uint4*>(sP + j16 * AT_P_BLOCK + r * 32 + ch * 16) =
+              make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
       }
+      if (row_ok) ssum[(par * 2 + half) * 144 + r] = sum;
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
-      // ---- epilogue: O / sum -> bf16, head-major channel (src/swin.rs:306-307) ----
-      ptx::mbar_wait(o_full, ph);
-      ptx::tc_fence_after();
-      {
-        uint32_t v[32];
-        ptx::tmem_ld32(lane_base + o_col, v);
-        ptx::tmem_ld_wait();
-        if (row_ok) {
-          const float inv = 1.f / sum;
-          uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)win * 144 + r) * p.ldo + head * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t w4[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              w4[t] = pack16x2(__uint_as_float(v[j * 8 + 2 * t]) * inv, __uint_as_float(v[j * 8 + 2 * t + 1]) * inv, p.dt);
-            }
-            dst[j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-          }
-        }
-      }
-      ph ^= 1;
     }
+    soft_bar_sync();               // every thread's sum of the last unit is visible
+    epilogue(n_units - 1);
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) ptx::tmem_dealloc(tmem_base, 512);
+  if (warp == AT_SOFT_WARPS) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 void tc_attention(const LaunchCtx& ctx, const AttnArgs& a) {

@@ -94,9 +94,59 @@ __global__ void resize_nhwc_kernel(ResizeP p) {
   g_st(p.out, p.odt, ((b * p.Ho + oy) * (long long)p.Wo + ox) * p.ldo + c, v);
 }
 
+// vector variant: 16-bit in == 16-bit out, 8 channels (16 bytes) per thread
+__device__ __forceinline__ float2 up16(uint32_t u, int dt) {
+  if (dt == BF16) return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+__device__ __forceinline__ uint32_t pk16(float a, float b, int dt) {
+  if (dt == BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+  __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256) resize_nhwc_vec8_kernel(ResizeP p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C8 = p.C >> 3;
+  if (i >= p.total) return;
+  const int c8 = (int)(i % C8); long long t = i / C8;
+  const int ox = (int)(t % p.Wo); t /= p.Wo; const int oy = (int)(t % p.Ho); const long long b = t / p.Ho;
+  int y0, y1, x0, x1; float ly, lx;
+  bilin_coord(oy, p.H, p.Ho, y0, y1, ly);
+  bilin_coord(ox, p.W, p.Wo, x0, x1, lx);
+  const long long base = b * p.H * p.W;
+  const uint16_t* xs = (const uint16_t*)p.x + c8 * 8;
+  const uint4 a00 = __ldg(reinterpret_cast<const uint4*>(xs + (base + (long long)y0 * p.W + x0) * p.ldx));
+  const uint4 a01 = __ldg(reinterpret_cast<const uint4*>(xs + (base + (long long)y0 * p.W + x1) * p.ldx));
+  const uint4 a10 = __ldg(reinterpret_cast<const uint4*>(xs + (base + (long long)y1 * p.W + x0) * p.ldx));
+  const uint4 a11 = __ldg(reinterpret_cast<const uint4*>(xs + (base + (long long)y1 * p.W + x1) * p.ldx));
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const uint32_t *p00 = reinterpret_cast<const uint32_t*>(&a00), *p01 = reinterpret_cast<const uint32_t*>(&a01),
+                 *p10 = reinterpret_cast<const uint32_t*>(&a10), *p11 = reinterpret_cast<const uint32_t*>(&a11);
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f00 = up16(p00[j], p.xdt), f01 = up16(p01[j], p.xdt), f10 = up16(p10[j], p.xdt), f11 = up16(p11[j], p.xdt);
+    // same association as the scalar kernel / F.interpolate: (1-ly)*((1-lx)*v00 + lx*v01) + ly*(...)
+    const float ax = (1.f - ly) * ((1.f - lx) * f00.x + lx * f01.x) + ly * ((1.f - lx) * f10.x + lx * f11.x);
+    const float ay = (1.f - ly) * ((1.f - lx) * f00.y + lx * f01.y) + ly * ((1.f - lx) * f10.y + lx * f11.y);
+    o[j] = pk16(ax, ay, p.odt);
+  }
+  (void)w00; (void)w01; (void)w10; (void)w11;
+  *reinterpret_cast<uint4*>((uint16_t*)p.out + ((b * p.Ho + oy) * (long long)p.Wo + ox) * p.ldo + c8 * 8) =
+      make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 void glue_resize_nhwc(const LaunchCtx& ctx, View in, View out) {
   GLUE_LAUNCH_PROLOGUE(ctx);
   ResizeP p{in.p, in.dt, in.ld, in.H, in.W, in.C, out.p, out.dt, out.ld, out.H, out.W, 0};
+  const bool vec = in.dt != F32 && in.dt == out.dt && in.C % 8 == 0 && in.ld % 8 == 0 && out.ld % 8 == 0 &&
+                   (((uintptr_t)in.p | (uintptr_t)out.p) & 15) == 0;
+  if (vec) {
+    p.total = (long long)in.B * out.H * out.W * (in.C / 8);
+    resize_nhwc_vec8_kernel<<<(unsigned)((p.total + 255) / 256), 256, 0, ctx.stream>>>(p);
+    BRN_CUDA(cudaGetLastError());
+    return;
+  }
   p.total = (long long)in.B * out.H * out.W * in.C;
   resize_nhwc_kernel<<<(unsigned)((p.total + 255) / 256), 256, 0, ctx.stream>>>(p);
   BRN_CUDA(cudaGetLastError());
@@ -252,8 +302,39 @@ __global__ void gate_kernel(void* p, int pdt, int ldp, int C, const void* g, int
   float gate = 1.f / (1.f + expf(-s));
   g_st(p, pdt, row * ldp + c, g_ld(p, pdt, row * ldp + c) * gate);
 }
+__global__ void __launch_bounds__(256) gate_vec8_kernel(uint16_t* p, int dt, int ldp, int C8, const uint16_t* g, int ldg,
+                                                        const float* w, float b0, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long row = i / C8; const int c8 = (int)(i - row * C8);
+  const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(g + row * ldg)), g1 = __ldg(reinterpret_cast<const uint4*>(g + row * ldg + 8));
+  const uint32_t* gp0 = reinterpret_cast<const uint32_t*>(&g0); const uint32_t* gp1 = reinterpret_cast<const uint32_t*>(&g1);
+  float s = b0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = up16(gp0[j], dt), b = up16(gp1[j], dt);
+    s = fmaf(__ldg(w + 2 * j), a.x, s); s = fmaf(__ldg(w + 2 * j + 1), a.y, s);
+    s = fmaf(__ldg(w + 8 + 2 * j), b.x, s); s = fmaf(__ldg(w + 8 + 2 * j + 1), b.y, s);
+  }
+  const float gate = 1.f / (1.f + expf(-s));
+  uint4* pp = reinterpret_cast<uint4*>(p + row * ldp + c8 * 8);
+  uint4 v = *pp;
+  uint32_t* vp = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 f = up16(vp[j], dt); vp[j] = pk16(f.x * gate, f.y * gate, dt); }
+  *pp = v;
+}
+
 void glue_gate(const LaunchCtx& ctx, View p, View g16, const float* w16, float b0) {
   GLUE_LAUNCH_PROLOGUE(ctx);
+  if (p.dt != F32 && g16.dt == p.dt && p.C % 8 == 0 && p.ld % 8 == 0 && g16.ld % 8 == 0 && g16.C == 16 &&
+      (((uintptr_t)p.p | (uintptr_t)g16.p) & 15) == 0) {
+    const long long tot = p.rows() * (p.C / 8);
+    gate_vec8_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx.stream>>>((uint16_t*)p.p, p.dt, p.ld, p.C / 8,
+                                                                           (const uint16_t*)g16.p, g16.ld, w16, b0, tot);
+    BRN_CUDA(cudaGetLastError());
+    return;
+  }
   long long total = p.rows() * p.C;
   gate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(p.p, p.dt, p.ld, p.C, g16.p, g16.dt, g16.ld, w16,
                                                                       b0, total);

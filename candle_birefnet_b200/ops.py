@@ -64,11 +64,11 @@ def window_attention(qkv, bias, hp: int, wp: int, shift: int, precision: str = "
     return out
 
 
-def bench_op(kind: str, B: int, H: int, W: int, C: int, N: int = 0, k: int = 1, act: int = 0, with_res: bool = False,
+def bench_op(kind: str, B: int, H: int, W: int, Cin: int, N: int = 0, k: int = 1, act: int = 0, with_res: bool = False,
              out_f32: bool = False, iters: int = 20, precision: str = "fp16", device: int = 0) -> float:
     """Mean device ms per launch of one kernel on synthetic device-resident data (kind: gemm | attn | deform)."""
     ms = C_float()
     kid = {"gemm": 0, "attn": 1, "deform": 2}[kind]
-    check(lib().brn_bench_op(device, _PREC[precision], kid, B, H, W, C, N, k, act, int(with_res), int(out_f32), iters,
+    check(lib().brn_bench_op(device, _PREC[precision], kid, B, H, W, Cin, N, k, act, int(with_res), int(out_f32), iters,
                              C.byref(ms)))
     return float(ms.value)

@@ -16,6 +16,10 @@ def gemm(tag, M, N, K, k=1, act=0, res=False, f32=False, H=None, W=None, B=1, pr
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "one":   # one <M> <N> <K> <act> <res> <f32>
+        M, N, K, act, res, f32 = [int(v) for v in sys.argv[2:8]]
+        gemm("one", M, N, K, act=act, res=bool(res), f32=bool(f32))
+        return
     if which in ("all", "gemm"):
         gemm("s2 fc1 gelu", 65536, 3072, 768, act=2)
         gemm("s2 qkv", 82944, 2304, 768)
