@@ -92,12 +92,16 @@ struct GemmArgs {
   View res;                      // optional residual (res.p == nullptr: none); indexed like out
   View out;                      // output view (dtype decides conversion)
   RowMap rowmap;                 // optional output row scatter
+  int tile_w = 0;                // conv M tile = tile_w x (128 / tile_w) pixels (power of two); 0 = widest that fits W
+  int out_tiled = 0;             // 1: fp32 out is [m_tile][N][128] (tile-major, row-in-tile fastest): the layout the
+                                 //    deformable gather reads its offsets from with coalesced loads
   double flops = 0;
 };
 
 struct DeformArgs {
   View x;                 // [B,H,W,C] input
   View om;                // [B,H,W,3*taps] fp32: 2*taps offsets (dy,dx interleaved) then taps modulators
+  int om_tiled = 0;       // 1: om.p is [m_tile][3*taps][128] over 16x8-pixel tiles (tc_gemm out_tiled, tile_w 16)
   const LayerW* w = nullptr;
   const float* bias = nullptr;
   int act = ACT_NONE;

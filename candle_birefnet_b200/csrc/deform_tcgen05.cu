@@ -28,21 +28,30 @@ CUtensorMap make_tmap_16(const void* base, int dt, int rank, const uint64_t* dim
 int device_sm_count();
 EpiP make_epi(int N, const float* bias, int bias_bstride, int act, int act_from, const View& res, const View& out);
 
-constexpr int DF_STAGES = 4;
+constexpr int DF_STAGES = 3;                      // 3 x 48 KB: leaves ~70 KB of L1 for the gathered neighbourhood
 constexpr int DF_PRODUCERS = 256;                 // 8 warps
 constexpr int DF_THREADS = DF_PRODUCERS + 32 + 128;
 constexpr int DF_A_BYTES = 128 * 128;             // 128 pixels x 64 ch bf16
 constexpr int DF_B_BYTES = 256 * 128;
-constexpr int DF_SMEM = DF_STAGES * (DF_A_BYTES + DF_B_BYTES) + 256 + 1024;
+constexpr int DF_BIAS_LD = 288;
+constexpr int DF_EPI_BYTES = 4 * EPI_STAGE_BYTES + DF_BIAS_LD * 4;
+constexpr int DF_SMEM = DF_STAGES * (DF_A_BYTES + DF_B_BYTES) + DF_EPI_BYTES + 256 + 1024;
+constexpr int DF_TW = 16, DF_TH = 8;              // an M tile is a 16 x 8 pixel patch of one image (2-D gather locality)
 
 struct DeformP {
   const uint16_t* x; int ldx; int B, H, W;   // bf16 or fp16 elements (xdt)
   int xdt;
-  const float* om; int ldom;
+  const float* om; int ldom; int om_tiled;   // om_tiled: [m_tile][3*taps][128] (written by tc_gemm with out_tiled)
   int k, pad, taps;
-  long long M; int m_tiles; int BN;
+  int tiles_x, tiles_y, m_tiles; int BN;
   EpiP epi;
 };
+
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 
 __device__ __forceinline__ void fma_16x8(float (&acc)[8], const uint4& v, float w, int dt) {
   const uint32_t* h = reinterpret_cast<const uint32_t*>(&v);
@@ -60,7 +69,9 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + DF_STAGES * DF_A_BYTES;
-  uint64_t* full = (uint64_t*)(sB + DF_STAGES * DF_B_BYTES);
+  uint8_t* sStage = sB + DF_STAGES * DF_B_BYTES;                 // epilogue staging, 2 KB per epilogue warp
+  float* sBias = (float*)(sStage + 4 * EPI_STAGE_BYTES);
+  uint64_t* full = (uint64_t*)((uint8_t*)sBias + DF_BIAS_LD * 4);
   uint64_t* empty = full + DF_STAGES;
   uint64_t* tfull = empty + DF_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -68,7 +79,8 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < DF_STAGES; ++s) { ptx::mbar_init(&full[s], DF_PRODUCERS + 1); ptx::mbar_init(&empty[s], 1); }
+    // full: one arrival per producer warp (after its lanes' proxy fences) + the weight TMA's expect_tx arrival
+    for (int s = 0; s < DF_STAGES; ++s) { ptx::mbar_init(&full[s], DF_PRODUCERS / 32 + 1); ptx::mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
     ptx::fence_barrier_init();
   }
@@ -77,49 +89,61 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp < 8) {
-    // ===== gather producers =====
+    // ===== gather producers: 2 threads per pixel, 32 channels (4 x 16 B) each =====
     const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const int HW = p.H * p.W;
+    const int ncols = 3 * p.taps;
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-      const long long m = (long long)tile * 128 + r;
-      const bool row_ok = m < p.M;
-      int b = 0, y = 0, x = 0;
-      if (row_ok) { b = (int)(m / HW); int rem = (int)(m - (long long)b * HW); y = rem / p.W; x = rem - y * p.W; }
-      const uint16_t* xb = p.x + (long long)b * HW * p.ldx + half * 32;
-      const float* o = p.om + m * p.ldom;
+      const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
+      const int y = (t2 / p.tiles_x) * DF_TH + (r >> 4), x = (t2 % p.tiles_x) * DF_TW + (r & 15);
+      const bool row_ok = y < p.H && x < p.W;
+      const uint16_t* xb = p.x + (long long)b * p.H * p.W * p.ldx + half * 32;
+      // offsets / modulator of tap t: o[t*os2], o[t*os2 + os1] and o[(2*taps + t) * os1]  (os1 = stride between columns)
+      const float* o; long long os1;
+      if (p.om_tiled) { o = p.om + (long long)tile * ncols * 128 + r; os1 = 128; }
+      else { o = p.om + (((long long)b * p.H + min(y, p.H - 1)) * p.W + min(x, p.W - 1)) * p.ldom; os1 = 1; }
+      float ndy = ldg_stream(o), ndx = ldg_stream(o + os1), nmk = ldg_stream(o + 2 * p.taps * os1);
       for (int tap = 0; tap < p.taps; ++tap) {
+        const float dy = ndy, dx = ndx, mk = row_ok ? nmk : 0.f;
+        if (tap + 1 < p.taps) {      // next tap's offsets while this tap's corners are in flight
+          ndy = ldg_stream(o + (2 * tap + 2) * os1); ndx = ldg_stream(o + (2 * tap + 3) * os1);
+          nmk = ldg_stream(o + (2 * p.taps + tap + 1) * os1);
+        }
+        const int ky = tap / p.k, kx = tap - ky * p.k;
+        const float py = (float)(y - p.pad + ky) + dy, px = (float)(x - p.pad + kx) + dx;
+        // torchvision semantics: zero outside (-1,H)x(-1,W), per-corner validity; folded into the corner weights so
+        // that all 16 loads are issued unconditionally (clamped addresses) and back to back
+        const bool inb = py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W;
+        const float fy = floorf(py), fx = floorf(px);
+        const int y0 = (int)fy, x0 = (int)fx;
+        const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+        const float m0 = inb ? mk : 0.f;
+        const float wy0 = (y0 >= 0) ? hy * m0 : 0.f, wy1 = (y0 + 1 <= p.H - 1) ? ly * m0 : 0.f;
+        const float wx0 = (x0 >= 0) ? hx : 0.f, wx1 = (x0 + 1 <= p.W - 1) ? lx : 0.f;
+        const float wgt[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
+        const int yc0 = min(max(y0, 0), p.H - 1), yc1 = min(max(y0 + 1, 0), p.H - 1);
+        const int xc0 = min(max(x0, 0), p.W - 1), xc1 = min(max(x0 + 1, 0), p.W - 1);
+        const uint4* src[4] = {reinterpret_cast<const uint4*>(xb + ((long long)yc0 * p.W + xc0) * p.ldx),
+                               reinterpret_cast<const uint4*>(xb + ((long long)yc0 * p.W + xc1) * p.ldx),
+                               reinterpret_cast<const uint4*>(xb + ((long long)yc1 * p.W + xc0) * p.ldx),
+                               reinterpret_cast<const uint4*>(xb + ((long long)yc1 * p.W + xc1) * p.ldx)};
+        uint4 v[4][4];
+#pragma unroll
+        for (int cnr = 0; cnr < 4; ++cnr)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[cnr][j] = __ldg(src[cnr] + j);
         float acc[4][8];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
-        if (row_ok) {
-          const int ky = tap / p.k, kx = tap - ky * p.k;
-          const float py = (float)(y - p.pad + ky) + __ldg(o + 2 * tap);
-          const float px = (float)(x - p.pad + kx) + __ldg(o + 2 * tap + 1);
-          const float mk = __ldg(o + 2 * p.taps + tap);
-          if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
-            const int y0 = (int)floorf(py), x0 = (int)floorf(px);
-            const float ly = py - y0, lx = px - x0, hy = 1.f - ly, hx = 1.f - lx;
-            const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= p.H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= p.W - 1;
-            const float wgt[4] = {hy * hx * mk, hy * lx * mk, ly * hx * mk, ly * lx * mk};
-            const bool ok[4] = {y0ok && x0ok, y0ok && x1ok, y1ok && x0ok, y1ok && x1ok};
-            const int cy[4] = {y0, y0, y0 + 1, y0 + 1}, cx[4] = {x0, x0 + 1, x0, x0 + 1};
 #pragma unroll
-            for (int cnr = 0; cnr < 4; ++cnr) {
-              if (!ok[cnr]) continue;
-              const uint4* src = reinterpret_cast<const uint4*>(xb + ((long long)cy[cnr] * p.W + cx[cnr]) * p.ldx);
-              uint4 v[4];
+        for (int cnr = 0; cnr < 4; ++cnr)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = __ldg(src + j);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) fma_16x8(acc[j], v[j], wgt[cnr], p.xdt);
-            }
-          }
-        }
+          for (int j = 0; j < 4; ++j) fma_16x8(acc[j], v[cnr][j], wgt[cnr], p.xdt);
         ptx::mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* rowp = sA + stage * DF_A_BYTES + r * 128;
 #pragma unroll
@@ -130,7 +154,8 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
                          pack16x2(acc[j][4], acc[j][5], p.xdt), pack16x2(acc[j][6], acc[j][7], p.xdt));
         }
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&full[stage]);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&full[stage]);
         if (++stage == DF_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -176,17 +201,26 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
       }
     }
   } else {
-    // ===== epilogue =====
+    // ===== epilogue (4 warps, one TMEM lane quadrant each, all BN columns) =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int eth = threadIdx.x - (DF_PRODUCERS + 32);
+    const uint32_t stage = ptx::smem_u32(sStage) + (warp - 9) * EPI_STAGE_BYTES;
+    const uint32_t sb = ptx::smem_u32(sBias);
+    if (p.epi.bias) {
+      for (int t = eth; t < DF_BIAS_LD; t += 128) ptx::sts32(sb + t * 4, t < p.epi.N ? __ldg(p.epi.bias + t) : 0.f);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    const int c1 = ((p.epi.N + 15) >> 4) * 16;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-      const long long orow = (long long)tile * 128 + row;
-      const bool valid = orow < p.M;
+      const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
+      const int y = (t2 / p.tiles_x) * DF_TH + (row >> 4), x = (t2 % p.tiles_x) * DF_TW + (row & 15);
+      const long long orow = (y < p.H && x < p.W) ? ((long long)b * p.H + y) * p.W + x : -1;
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      epi_row(p.epi, taddr, 0, (p.epi.N + 15) >> 4, 0, 1, valid ? orow : 0, p.epi.bias, valid);
+      epi_warp_dyn(p.epi, taddr, 0, 0, c1, orow, p.epi.bias ? sb : 0u, stage, lane);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -208,9 +242,10 @@ void tc_deform(const LaunchCtx& ctx, const DeformArgs& a) {
   const LayerW& w = *a.w;
   DeformP p{};
   p.x = (const uint16_t*)a.x.p; p.xdt = a.x.dt; p.ldx = a.x.ld; p.B = a.x.B; p.H = a.x.H; p.W = a.x.W;
-  p.om = (const float*)a.om.p; p.ldom = a.om.ld;
+  p.om = (const float*)a.om.p; p.ldom = a.om.ld; p.om_tiled = a.om_tiled;
   p.k = w.kh; p.pad = w.kh / 2; p.taps = w.taps();
-  p.M = a.x.rows(); p.m_tiles = (int)((p.M + 127) / 128);
+  p.tiles_x = (p.W + DF_TW - 1) / DF_TW; p.tiles_y = (p.H + DF_TH - 1) / DF_TH;
+  p.m_tiles = p.B * p.tiles_x * p.tiles_y;
   p.BN = (w.N + 15) / 16 * 16;
   View none{};
   p.epi = make_epi(w.N, a.bias ? a.bias : w.bias, 0, a.act, 0, none, a.out);
@@ -222,8 +257,9 @@ void tc_deform(const LaunchCtx& ctx, const DeformArgs& a) {
   cudaFuncSetAttribute(tc_deform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM);
   const int grid = std::min(p.m_tiles, device_sm_count());
   char desc[96] = "";
-  if (ctx.kt) snprintf(desc, sizeof desc, "M=%lld N=%d k=%d", p.M, w.N, p.k);
-  KScope ks(ctx, KC_DEFORM_TC, 2.0 * (double)p.M * w.N * w.taps() * 64, (double)p.M * w.taps() * 4 * 128, desc);
+  const double M = (double)a.x.rows();
+  if (ctx.kt) snprintf(desc, sizeof desc, "M=%lld N=%d k=%d", (long long)a.x.rows(), w.N, p.k);
+  KScope ks(ctx, KC_DEFORM_TC, 2.0 * M * w.N * w.taps() * 64, M * w.taps() * 4 * 128, desc);
   tc_deform_kernel<<<grid, DF_THREADS, DF_SMEM, ctx.stream>>>(tmB, p);
   BRN_CUDA(cudaGetLastError());
 }

@@ -29,7 +29,9 @@ constexpr int TC_EPI_WARPS = 8;                               // two per TMEM la
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;            // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 constexpr int TC_B_BYTES = 256 * TC_BK * 2;     // 32 KB (BN <= 256)
-constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 256 + 1024;
+constexpr int TC_BIAS_LD = 288;                                // floats per accumulator stage (BN <= 256, padded to 32)
+constexpr int TC_EPI_BYTES = TC_EPI_WARPS * EPI_STAGE_BYTES + 2 * TC_BIAS_LD * 4;
+constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_EPI_BYTES + 256 + 1024;
 
 struct TcGemmP {
   int B, H, W;
@@ -37,6 +39,7 @@ struct TcGemmP {
   int m_tiles, n_tiles, BN;
   int taps, kw, pad, cblocks, cin_pad;
   int in_bf16;   // operand format: 1 = bf16, 0 = fp16
+  int out_tiled; // fp32 out is [m_tile][N][128]
   EpiP epi;
   RowMap rm;
 };
@@ -52,7 +55,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + TC_STAGES * TC_A_BYTES;
-  uint64_t* full = (uint64_t*)(sB + TC_STAGES * TC_B_BYTES);
+  uint8_t* sStage = sB + TC_STAGES * TC_B_BYTES;                 // epilogue staging, 2 KB per epilogue warp
+  float* sBias = (float*)(sStage + TC_EPI_WARPS * EPI_STAGE_BYTES);
+  uint64_t* full = (uint64_t*)((uint8_t*)sBias + 2 * TC_BIAS_LD * 4);
   uint64_t* empty = full + TC_STAGES;
   uint64_t* tfull = empty + TC_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -92,7 +97,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int b = m_tile / tiles_per_img, r = m_tile - b * tiles_per_img;   // b >= B for the odd tail: TMA zero-fills
         const int y0 = (r / p.tiles_x) * TH, x0 = (r % p.tiles_x) * TW;
         for (int kb = 0; kb < kblocks; ++kb) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_wait_backoff(&empty[stage], phase ^ 1);
           ptx::mbar_expect_tx(&full[stage], tx_bytes);
           const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
@@ -112,7 +117,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int item = item0; item < num_items; item += item_step) {
-        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        ptx::mbar_wait_backoff(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kb = 0; kb < kblocks; ++kb) {
@@ -133,29 +138,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===== epilogue: 8 warps; warp % 4 selects the TMEM lane quadrant, (warp - 2) / 4 the odd / even column chunks =====
+    // ===== epilogue: 8 warps; warp % 4 selects the TMEM lane quadrant, (warp - 2) / 4 the column half =====
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    const int eth = threadIdx.x - 64;
+    const uint32_t stage = ptx::smem_u32(sStage) + (warp - 2) * EPI_STAGE_BYTES;
+    const bool o32 = p.epi.odt == F32;
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = item0; item < num_items; item += item_step) {
       const int m_tile = (item / p.n_tiles) * CL + rank, n_tile = item % p.n_tiles;
       const int b = m_tile / tiles_per_img, r = m_tile - b * tiles_per_img;
       const int y = (r / p.tiles_x) * TH + (row >> p.tw_log2), x = (r % p.tiles_x) * TW + (row & (TW - 1));
-      bool valid = m_tile < p.m_tiles && y < p.H && x < p.W;
-      long long orow = ((long long)b * p.H + y) * p.W + x;
-      if (valid && p.rm.enabled) {
-        orow = window_row_to_token(orow, p.rm.h, p.rm.w, p.rm.hp, p.rm.wp, p.rm.shift);
-        valid = orow >= 0;
-      }
-      if (!valid) orow = 0;
+      const bool valid = m_tile < p.m_tiles && y < p.H && x < p.W;
+      long long orow = valid ? ((long long)b * p.H + y) * p.W + x : -1;
+      if (valid && p.rm.enabled) orow = window_row_to_token(orow, p.rm.h, p.rm.w, p.rm.hp, p.rm.wp, p.rm.shift);
       const int n0 = n_tile * p.BN;
-      const float* bias = p.epi.bias ? p.epi.bias + (long long)(valid ? b : 0) * p.epi.bias_bstride : nullptr;
-      const int nchunks = min(p.BN, p.epi.N - n0 + 15) >> 4;
+      const int nch = min(p.BN, p.epi.N - n0 + 15) >> 4;     // 16-column chunks of this tile that hold real columns
+      int h0 = (nch + 1) >> 1;
+      if (!o32) h0 = min((h0 + 1) & ~1, nch);                // 16-bit output: keep the split on a 32-column granule
+      const int c0 = half ? h0 * 16 : 0, c1 = half ? nch * 16 : h0 * 16;
+      const uint32_t sb = ptx::smem_u32(sBias) + acc * TC_BIAS_LD * 4;
+      if (p.epi.bias) {
+        // this tile's bias -> shared (double buffered with the accumulator stage; an M tile lies inside one image)
+        const float* bias = p.epi.bias + (long long)(m_tile < p.m_tiles ? b : 0) * p.epi.bias_bstride;
+        for (int t = eth; t < TC_BIAS_LD; t += 32 * TC_EPI_WARPS)
+          ptx::sts32(sb + t * 4, (t < p.BN && n0 + t < p.epi.N) ? __ldg(bias + n0 + t) : 0.f);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+      }
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      epi_row(p.epi, taddr, n0, nchunks, half, 2, orow, bias, valid);
+      if (p.out_tiled) {
+        if (m_tile < p.m_tiles) epi_warp_tiled_dyn(p.epi, taddr, n0, c0, c1, m_tile, row, p.epi.bias ? sb : 0u);
+      } else {
+        epi_warp_dyn(p.epi, taddr, n0, c0, c1, orow, p.epi.bias ? sb : 0u, stage, lane);
+      }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -221,9 +239,9 @@ EpiP make_epi(int N, const float* bias, int bias_bstride, int act, int act_from,
   EpiP e{};
   e.N = N; e.bias = bias; e.bias_bstride = bias_bstride; e.act = act; e.act_from = act_from;
   e.res = res.p; e.resdt = res.dt; e.ldres = res.ld;
-  e.vec_res = res.p && (((uintptr_t)res.p & 15) == 0) && ((res.ld * dsize(res.dt)) % 16 == 0);
   e.out = out.p; e.odt = out.dt; e.ldo = out.ld;
-  e.vec_out = (((uintptr_t)out.p & 15) == 0) && ((out.ld * dsize(out.dt)) % 16 == 0);
+  e.vec = (((uintptr_t)out.p & 15) == 0) && ((out.ld * dsize(out.dt)) % 16 == 0) &&
+          (!res.p || ((((uintptr_t)res.p & 15) == 0) && ((res.ld * dsize(res.dt)) % 16 == 0)));
   return e;
 }
 
@@ -246,8 +264,12 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   TcGemmP p{};
   p.B = a.x.B; p.H = a.x.H; p.W = a.x.W;
   int tw = 1, lg = 0;
-  while (tw < std::min(a.x.W, TC_BM)) { tw <<= 1; ++lg; }
+  if (a.tile_w > 0) { while (tw < std::min(a.tile_w, TC_BM)) { tw <<= 1; ++lg; } }
+  else { while (tw < std::min(a.x.W, TC_BM)) { tw <<= 1; ++lg; } }
   p.tw_log2 = lg;
+  p.out_tiled = a.out_tiled;
+  BRN_CHECK(!a.out_tiled || (a.out.dt == F32 && !a.res.p && !a.rowmap.enabled && w.N <= 256), 5,
+            "tc_gemm: tile-major output is fp32, single N tile, no residual");
   const int TH = TC_BM / tw;
   p.tiles_x = (a.x.W + tw - 1) / tw;
   p.tiles_y = (a.x.H + TH - 1) / TH;

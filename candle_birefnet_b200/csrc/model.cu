@@ -518,10 +518,20 @@ void Model::run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out) {
     View dst = cat.slice(256 * b, 256);
     if (cfg.deform_mode == BRN_DEFORM_DEFORMABLE) {
       const size_t m1 = arena.mark();
-      View om = make_view(arena.alloc(px * 3 * k * k * 4), F32, B, H, W, 3 * k * k);
-      { GemmArgs g; g.x = t; g.w = &w.br[b].om; g.pad = k / 2; g.act = ACT_2SIGMOID_TAIL; g.act_from = 2 * k * k;
-        g.out = om; op_gemm(ctx, g); }
-      { DeformArgs d; d.x = t; d.om = om; d.w = &w.br[b].reg; d.act = ACT_RELU; d.out = dst; op_deform(ctx, d); }
+      // tensor-core path: the offset/modulator conv writes tile-major [16x8-pixel tile][3k^2][128] so that the
+      // gather producers of tc_deform read their per-tap (dy, dx, m) with coalesced loads
+      GemmArgs g; g.x = t; g.w = &w.br[b].om; g.pad = k / 2; g.act = ACT_2SIGMOID_TAIL; g.act_from = 2 * k * k;
+      DeformArgs d; d.x = t; d.w = &w.br[b].reg; d.act = ACT_RELU; d.out = dst;
+      const bool tiled = ctx.precision != BRN_PREC_FP32 && !ctx.force_simt;
+      size_t om_elems = px * 3 * k * k;
+      if (tiled) om_elems = (size_t)B * ((H + 7) / 8) * ((W + 15) / 16) * 128 * 3 * k * k;
+      View om = make_view(arena.alloc(om_elems * 4), F32, B, H, W, 3 * k * k);
+      g.out = om;
+      if (tiled) { g.tile_w = 16; g.out_tiled = 1; d.om_tiled = 1; BRN_CHECK(tc_gemm_supported(g), 5, "om conv: tcgen05 path unavailable"); }
+      d.om = om;
+      op_gemm(ctx, g);
+      if (tiled) BRN_CHECK(tc_deform_supported(d), 5, "deform: tcgen05 path unavailable");
+      op_deform(ctx, d);
       arena.release(m1);
     } else {
       GemmArgs g; g.x = t; g.w = &w.br[b].reg; g.pad = k / 2; g.act = ACT_RELU; g.out = dst; op_gemm(ctx, g);

@@ -1,7 +1,17 @@
-// Shared tcgen05 epilogue: 16 accumulator columns of one output row -> bias / activation / residual -> store.
+// Shared tcgen05 epilogue: accumulator tile (TMEM) -> bias / activation / residual -> coalesced global stores.
+//
+// tcgen05.ld 32x32b gives every thread ONE ROW of the tile, so a direct store makes each warp instruction touch 32
+// different rows (32 half-used sectors, ~1.5 LSU wavefronts per lane).  Instead every epilogue warp owns a 2 KB
+// shared-memory staging block and works in 64-byte output granules (32 x 16-bit or 16 x fp32 columns of its 32 rows):
+//   phase A (thread = row)   : TMEM -> registers, + bias (broadcast LDS), activation, convert, STS.128 into the
+//                              XOR-swizzled staging block (conflict free);
+//   phase B (warp = 8 rows x 64 B per instruction): LDS.128, fp32 residual add (coalesced LDG.128), STG.128 -- every
+//                              store instruction writes 8 full 64-byte row segments.
+// The activation is a template parameter (no per-element branches); erf-GELU is 12 FMA-pipe + 2 MUFU instructions.
 #pragma once
 #include "brn_common.h"
 #include "device_utils.cuh"
+#include "tc_ptx.cuh"
 
 namespace brn {
 
@@ -9,22 +19,37 @@ struct EpiP {
   int N;
   const float* bias; int bias_bstride;
   int act, act_from;
-  const void* res; int resdt; int ldres; int vec_res;
-  void* out; int odt; int ldo; int vec_out;
+  const void* res; int resdt; int ldres;
+  void* out; int odt; int ldo;
+  int vec;       // out (and res) base pointers and row pitches are 16-byte aligned
 };
 
-// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 2 MUFU + ~10 FMA instead of erff's ~40 instructions.  The
-// epilogue evaluates ~0.5 G GELUs per 1024^2 image, so this is what keeps fc1 MMA-paced rather than epilogue-paced.
+constexpr int EPI_STAGE_BYTES = 32 * 64;   // per epilogue warp
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// exact-erf GELU (candle `gelu_erf`, src/swin.rs:105) via Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7):
+//   gelu(x) = relu(x) - |x| * q,   q = 0.5 * erfc(|x| / sqrt2) = 0.5 * poly(t) * t * exp(-x^2 / 2),   t = 1 / (1 + p |x| / sqrt2)
+// The epilogue evaluates ~0.5 G GELUs per 1024^2 image: 12 FMA-pipe + 2 MUFU instructions each.
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  poly *= t;
-  const float erf_abs = 1.f - poly * __expf(-z * z);
-  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.f));
+  const float e = ex2_approx((x * x) * (-0.5f * 1.4426950408889634f));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(t, poly, 0.5f * 1.421413741f);
+  poly = fmaf(t, poly, 0.5f * -0.284496736f);
+  poly = fmaf(t, poly, 0.5f * 0.254829592f);
+  const float q = (poly * t) * e;
+  return fmaf(-ax, q, fmaxf(x, 0.f));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -42,16 +67,7 @@ __device__ __forceinline__ float2 unpack16x2(uint32_t u, int dt) {
   return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
 
-// Epilogue registers of one 16-column chunk: accumulators (raw TMEM bits), bias and residual, all fetched ahead of
-// use so the TMEM load, the L1/L2 bias load and the global residual load of chunk c+1 overlap the math and the
-// stores of chunk c (the epilogue warps have nothing else to hide latency with).
-struct EpiRegs {
-  uint32_t v[16];
-  float bias[16];
-  float res[16];
-};
-
-__device__ __forceinline__ void tmem_ld16_raw(uint32_t taddr, uint32_t (&v)[16]) {
+__device__ __forceinline__ void tmem_ld16_raw(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -69,112 +85,235 @@ __device__ __forceinline__ void tmem_wait_dep(uint32_t (&v)[16]) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tmem_wait_dep(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 
-// Issue the loads of chunk [nb, nb+16) of output row `orow`.  The TMEM load is warp-collective: every lane calls this.
-__device__ __forceinline__ void epi_prefetch(const EpiP& p, EpiRegs& r, uint32_t taddr, int nb, long long orow,
-                                             const float* bias, bool valid) {
-  tmem_ld16_raw(taddr, r.v);
-  const bool full16 = nb + 16 <= p.N;
-  if (bias) {
-    if (full16) {
+template <int ACT>
+__device__ __forceinline__ float epi_act(float f, int col, int act_from) {
+  if (ACT == ACT_RELU) return fmaxf(f, 0.f);
+  if (ACT == ACT_GELU) return gelu_fast(f);
+  if (ACT == ACT_2SIGMOID_TAIL) return col >= act_from ? 2.f * rcp_approx(1.f + ex2_approx(-1.4426950408889634f * f)) : f;
+  return f;
+}
+
+// One epilogue warp's share of an accumulator tile: its 32 rows (TMEM lane quadrant encoded in taddr) x tile columns
+// [c0, c1) (multiples of 16; tile column 0 is output column n0).
+//   orow  : this lane's output row (row index into out / res), < 0 for rows that must not be written
+//   sbias : SHARED address of the tile's bias (index = tile column, zero padded to c1 rounded up to 32), or 0
+//   stage : SHARED address of this warp's EPI_STAGE_BYTES staging block (16-byte aligned)
+// O32: fp32 output (16 columns per 64-byte granule), else 16-bit output by p.odt (32 columns per granule).
+// Residual (out may alias res: the Swin residual stream is updated in place, so residual loads can never be hoisted
+// above earlier stores by the compiler -- they are issued explicitly, two granules ahead, right after the stores):
+//   mode 1: fp32 residual + fp32 output, added in phase B (coalesced LDG.128)
+//   mode 2: 16-bit residual of the output type, added in fp32 in phase A (this thread's 64 contiguous bytes)
+//   mode 3: anything else, scalar loads in phase A
+template <int ACT, bool O32, int RM>
+__device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, int c0, int c1, long long orow,
+                                         uint32_t sbias, uint32_t stage, int lane) {
+  if (c0 >= c1) return;
+  constexpr int GC = O32 ? 16 : 32;       // columns per 64-byte granule
+  constexpr int PER = O32 ? 4 : 8;        // elements per 16-byte chunk
+  constexpr int ESZ = O32 ? 4 : 2;
+  constexpr int rmode = RM;
+  // phase-B geometry: instruction `it` covers rows it*8 + lane/4, 16-byte chunk lane%4
+  const int kb = lane & 3;
+  long long orow_b[4];
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
-        r.bias[j] = bv.x; r.bias[j + 1] = bv.y; r.bias[j + 2] = bv.z; r.bias[j + 3] = bv.w;
-      }
-    } else {
+  for (int it = 0; it < 4; ++it) orow_b[it] = __shfl_sync(0xffffffffu, orow, it * 8 + (lane >> 2));
+  const uint32_t my_row = stage + lane * 64;
+  const int sw_a = (lane >> 1) & 3;
+
+  // residual prefetch: slot (granule & 1) holds the residual of that granule
+  uint4 rq0[4], rq1[4];
+  auto res_issue = [&](int c, uint4 (&q)[4]) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) r.bias[j] = nb + j < p.N ? __ldg(bias + nb + j) : 0.f;
+    for (int i = 0; i < 4; ++i) q[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (c >= c1) return;
+    if (rmode == 1) {
+      const int col = n0 + c + kb * 4;
+      const int nl = min(p.N - col, min(GC, c1 - c) - kb * 4);
+#pragma unroll
+      for (int it = 0; it < 4; ++it)
+        if (orow_b[it] >= 0 && nl >= 4)
+          q[it] = *reinterpret_cast<const uint4*>((const float*)p.res + orow_b[it] * p.ldres + col);
+    } else if (rmode == 2) {
+      const uint16_t* rp = (const uint16_t*)p.res + orow * p.ldres + n0 + c;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (orow >= 0 && 8 * k < c1 - c && n0 + c + 8 * k < p.N) q[k] = *reinterpret_cast<const uint4*>(rp + 8 * k);
     }
-  } else {
+  };
+
+  uint32_t v[GC];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) r.bias[j] = 0.f;
-  }
-  if (p.res && valid) {
-    if (p.vec_res && full16) {
-      if (p.resdt == F32) {
-        const float4* rp = reinterpret_cast<const float4*>((const float*)p.res + orow * p.ldres + nb);
+  for (int j = 0; j < GC; ++j) v[j] = 0u;
+  tmem_ld16_raw(taddr + c0, v);
+  if (!O32 && c0 + 16 < c1) tmem_ld16_raw(taddr + c0 + 16, v + (GC - 16));
+  if (rmode == 1 || rmode == 2) { res_issue(c0, rq0); res_issue(c0 + GC, rq1); }
+
+  auto granule = [&](int c, uint4 (&rq)[4]) {
+    const int ncol = min(GC, c1 - c);
+    tmem_wait_dep(v);
+    // ---- phase A: this thread's row, columns [c, c + ncol) ----
+    float f[GC];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float4 rv = rp[j]; r.res[4 * j] = rv.x; r.res[4 * j + 1] = rv.y; r.res[4 * j + 2] = rv.z; r.res[4 * j + 3] = rv.w; }
-      } else {
-        const uint4* rp = reinterpret_cast<const uint4*>((const uint16_t*)p.res + orow * p.ldres + nb);
+    for (int j = 0; j < GC; ++j) f[j] = __uint_as_float(v[j]);
+    // the next granule's TMEM load overlaps the math and the stores of this one
+    if (c + GC < c1) {
+      tmem_ld16_raw(taddr + c + GC, v);
+      if (!O32 && c + GC + 16 < c1) tmem_ld16_raw(taddr + c + GC + 16, v + (GC - 16));
+    }
+    if (sbias) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const uint4 rv = rp[j];
-          const uint32_t* h = reinterpret_cast<const uint32_t*>(&rv);
+      for (int j = 0; j < GC; j += 4) {
+        const uint4 bv = ptx::lds128(sbias + (c + j) * 4);
+        f[j] += __uint_as_float(bv.x); f[j + 1] += __uint_as_float(bv.y); f[j + 2] += __uint_as_float(bv.z); f[j + 3] += __uint_as_float(bv.w);
+      }
+    }
 #pragma unroll
-          for (int t = 0; t < 4; ++t) { const float2 ff = unpack16x2(h[t], p.resdt); r.res[8 * j + 2 * t] = ff.x; r.res[8 * j + 2 * t + 1] = ff.y; }
+    for (int j = 0; j < GC; ++j) f[j] = epi_act<ACT>(f[j], n0 + c + j, p.act_from);
+    if (!O32 && rmode == 2) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t* h = reinterpret_cast<const uint32_t*>(&rq[k]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 r2 = unpack16x2(h[t], p.odt);
+          f[(8 * k + 2 * t) % GC] += r2.x; f[(8 * k + 2 * t + 1) % GC] += r2.y;
         }
       }
+    } else if (rmode == 3 && orow >= 0) {
+#pragma unroll
+      for (int j = 0; j < GC; ++j)
+        if (j < ncol && n0 + c + j < p.N) f[j] += ld_elem(p.res, p.resdt, orow * p.ldres + n0 + c + j);
+    }
+    if (O32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        ptx::sts128(my_row + ((k ^ sw_a) << 4), make_uint4(__float_as_uint(f[4 * k]), __float_as_uint(f[4 * k + 1]),
+                                                           __float_as_uint(f[4 * k + 2]), __float_as_uint(f[4 * k + 3])));
+    } else if (p.odt == BF16) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        ptx::sts128(my_row + ((k ^ sw_a) << 4),
+            make_uint4(pack_bf16x2(f[(8 * k) % GC], f[(8 * k + 1) % GC]), pack_bf16x2(f[(8 * k + 2) % GC], f[(8 * k + 3) % GC]),
+                       pack_bf16x2(f[(8 * k + 4) % GC], f[(8 * k + 5) % GC]), pack_bf16x2(f[(8 * k + 6) % GC], f[(8 * k + 7) % GC])));
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) r.res[j] = nb + j < p.N ? ld_elem(p.res, p.resdt, orow * p.ldres + nb + j) : 0.f;
+      for (int k = 0; k < 4; ++k)
+        ptx::sts128(my_row + ((k ^ sw_a) << 4),
+            make_uint4(pack_f16x2(f[(8 * k) % GC], f[(8 * k + 1) % GC]), pack_f16x2(f[(8 * k + 2) % GC], f[(8 * k + 3) % GC]),
+                       pack_f16x2(f[(8 * k + 4) % GC], f[(8 * k + 5) % GC]), pack_f16x2(f[(8 * k + 6) % GC], f[(8 * k + 7) % GC])));
     }
-  } else {
+    __syncwarp();
+    // ---- phase B: 8 rows x 64 bytes per instruction ----
+    const int col = n0 + c + kb * PER;                   // first output column of this lane's 16-byte chunk
+    const int nleft = min(p.N - col, ncol - kb * PER);   // valid elements in the chunk (<= 0: none)
+    uint4 val[4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) r.res[j] = 0.f;
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2);
+      val[it] = ptx::lds128(stage + r * 64 + ((kb ^ ((r >> 1) & 3)) << 4));
+    }
+    if (O32 && rmode == 1) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        float4* fv = reinterpret_cast<float4*>(&val[it]);
+        const float4* rv = reinterpret_cast<const float4*>(&rq[it]);
+        fv->x += rv->x; fv->y += rv->y; fv->z += rv->z; fv->w += rv->w;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const long long ro = orow_b[it];
+      if (ro < 0 || nleft <= 0) continue;
+      char* op = (char*)p.out + (ro * p.ldo + col) * ESZ;
+      if (p.vec && nleft >= PER) {
+        *reinterpret_cast<uint4*>(op) = val[it];
+      } else if (O32) {
+        // unaligned / tail columns: element stores; a mode-1 residual of a partial chunk was not prefetched
+        const float* fv = reinterpret_cast<const float*>(&val[it]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (e < nleft) ((float*)op)[e] = fv[e] + (rmode == 1 ? ((const float*)p.res)[ro * p.ldres + col + e] : 0.f);
+      } else {
+        const uint16_t* hv = reinterpret_cast<const uint16_t*>(&val[it]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (e < nleft) ((uint16_t*)op)[e] = hv[e];
+      }
+    }
+    if (rmode == 1 || rmode == 2) res_issue(c + 2 * GC, rq);   // this slot's next granule, after the stores (aliasing)
+    __syncwarp();
+  };
+
+  for (int c = c0; c < c1; c += 2 * GC) {
+    granule(c, rq0);
+    if (c + GC < c1) granule(c + GC, rq1);
   }
 }
 
-// bias / activation / residual / convert / store of a prefetched chunk (call after tcgen05.wait::ld)
-__device__ __forceinline__ void epi_finish(const EpiP& p, const EpiRegs& r, int nb, long long orow) {
-  const int esz = p.odt == F32 ? 4 : 2;
-  const bool full16 = nb + 16 <= p.N;
-  float f[16];
+// Tile-major fp32 output (GemmArgs::out_tiled): element (row r of M tile t, column n) -> out[(t * N + n) * 128 + r].
+// With lane == row the plain thread-per-row store is already perfectly coalesced (32 consecutive floats per
+// instruction); this is the layout the deformable gather reads its offsets / modulators from.
+template <int ACT>
+__device__ __forceinline__ void epi_warp_tiled(const EpiP& p, uint32_t taddr, int n0, int c0, int c1, long long tile,
+                                               int row, uint32_t sbias) {
+  float* const base = (float*)p.out + tile * p.N * 128 + row;
+  for (int c = c0; c < c1; c += 16) {
+    uint32_t v[16];
+    tmem_ld16_raw(taddr + c, v);
+    tmem_wait_dep(v);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r.v[j]) + r.bias[j];
-  if (p.act == ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-  } else if (p.act == ACT_GELU) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = gelu_fast(f[j]);
-  } else if (p.act == ACT_2SIGMOID_TAIL) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) if (nb + j >= p.act_from) f[j] = 2.f / (1.f + __expf(-f[j]));
-  }
-#pragma unroll
-  for (int j = 0; j < 16; ++j) f[j] += r.res[j];
-  char* op = (char*)p.out + (orow * p.ldo + nb) * esz;
-  if (p.vec_out && full16) {
-    if (p.odt == F32) {
-      float4* o4 = reinterpret_cast<float4*>(op);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-    } else {
-      uint4* o4 = reinterpret_cast<uint4*>(op);
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-        o4[j] = make_uint4(pack16x2(f[8 * j], f[8 * j + 1], p.odt), pack16x2(f[8 * j + 2], f[8 * j + 3], p.odt),
-                           pack16x2(f[8 * j + 4], f[8 * j + 5], p.odt), pack16x2(f[8 * j + 6], f[8 * j + 7], p.odt));
+    for (int j = 0; j < 16; ++j) {
+      const int col = n0 + c + j;
+      if (col < p.N) {
+        float f = __uint_as_float(v[j]) + (sbias ? ptx::lds32(sbias + (c + j) * 4) : 0.f);
+        base[(long long)col * 128] = epi_act<ACT>(f, col, p.act_from);
+      }
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (nb + j < p.N) st_elem(op, p.odt, j, f[j]);
+  }
+}
+__device__ __forceinline__ void epi_warp_tiled_dyn(const EpiP& p, uint32_t taddr, int n0, int c0, int c1, long long tile,
+                                                   int row, uint32_t sbias) {
+  switch (p.act) {
+    case ACT_RELU: epi_warp_tiled<ACT_RELU>(p, taddr, n0, c0, c1, tile, row, sbias); break;
+    case ACT_2SIGMOID_TAIL: epi_warp_tiled<ACT_2SIGMOID_TAIL>(p, taddr, n0, c0, c1, tile, row, sbias); break;
+    default: epi_warp_tiled<ACT_NONE>(p, taddr, n0, c0, c1, tile, row, sbias); break;
   }
 }
 
-// One output row of an accumulator tile: chunks first, first+step, ... < nchunks (16 columns each), software
-// pipelined over two register sets.  taddr = TMEM address of column 0 of the tile in this warp's lane quadrant.
-__device__ __forceinline__ void epi_row(const EpiP& p, uint32_t taddr, int n0, int nchunks, int first, int step,
-                                        long long orow, const float* bias, bool valid) {
-  EpiRegs r0, r1;
-  int c = first;
-  if (c >= nchunks) return;
-  epi_prefetch(p, r0, taddr + c * 16, n0 + c * 16, orow, bias, valid);
-  while (true) {
-    tmem_wait_dep(r0.v);
-    const int c1 = c + step;
-    if (c1 < nchunks) epi_prefetch(p, r1, taddr + c1 * 16, n0 + c1 * 16, orow, bias, valid);
-    if (valid) epi_finish(p, r0, n0 + c * 16, orow);
-    if (c1 >= nchunks) break;
-    tmem_wait_dep(r1.v);
-    const int c2 = c1 + step;
-    if (c2 < nchunks) epi_prefetch(p, r0, taddr + c2 * 16, n0 + c2 * 16, orow, bias, valid);
-    if (valid) epi_finish(p, r1, n0 + c1 * 16, orow);
-    if (c2 >= nchunks) break;
-    c = c2;
+// runtime activation / output type / residual mode -> template instance
+template <bool O32, int RM>
+__device__ __forceinline__ void epi_warp_act(const EpiP& p, uint32_t taddr, int n0, int c0, int c1, long long orow,
+                                             uint32_t sbias, uint32_t stage, int lane) {
+  switch (p.act) {
+    case ACT_RELU: epi_warp<ACT_RELU, O32, RM>(p, taddr, n0, c0, c1, orow, sbias, stage, lane); break;
+    case ACT_GELU: epi_warp<ACT_GELU, O32, RM>(p, taddr, n0, c0, c1, orow, sbias, stage, lane); break;
+    case ACT_2SIGMOID_TAIL: epi_warp<ACT_2SIGMOID_TAIL, O32, RM>(p, taddr, n0, c0, c1, orow, sbias, stage, lane); break;
+    default: epi_warp<ACT_NONE, O32, RM>(p, taddr, n0, c0, c1, orow, sbias, stage, lane); break;
+  }
+}
+__device__ __forceinline__ void epi_warp_dyn(const EpiP& p, uint32_t taddr, int n0, int c0, int c1, long long orow,
+                                             uint32_t sbias, uint32_t stage, int lane) {
+  const bool o32 = p.odt == F32;
+  if (!p.res) {
+    if (o32) epi_warp_act<true, 0>(p, taddr, n0, c0, c1, orow, sbias, stage, lane);
+    else epi_warp_act<false, 0>(p, taddr, n0, c0, c1, orow, sbias, stage, lane);
+  } else if (p.act == ACT_NONE && o32 && p.resdt == F32 && p.vec) {
+    epi_warp<ACT_NONE, true, 1>(p, taddr, n0, c0, c1, orow, sbias, stage, lane);
+  } else if (p.act == ACT_NONE && !o32 && p.resdt == p.odt && p.vec && p.N % 8 == 0) {
+    epi_warp<ACT_NONE, false, 2>(p, taddr, n0, c0, c1, orow, sbias, stage, lane);
+  } else {
+    if (o32) epi_warp_act<true, 3>(p, taddr, n0, c0, c1, orow, sbias, stage, lane);
+    else epi_warp_act<false, 3>(p, taddr, n0, c0, c1, orow, sbias, stage, lane);
   }
 }
 
