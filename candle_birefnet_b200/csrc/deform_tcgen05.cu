@@ -34,7 +34,8 @@ constexpr int DF_THREADS = DF_PRODUCERS + 32 + 128;
 constexpr int DF_A_BYTES = 128 * 128;             // 128 pixels x 64 ch bf16
 constexpr int DF_B_BYTES = 256 * 128;
 constexpr int DF_BIAS_LD = 288;
-constexpr int DF_EPI_BYTES = 4 * EPI_STAGE_BYTES + DF_BIAS_LD * 4;
+constexpr int DF_PARAM_BYTES = 2 * 128 * 32;      // double-buffered sampling parameters: 128 pixels x 32 B
+constexpr int DF_EPI_BYTES = 4 * EPI_STAGE_BYTES + DF_BIAS_LD * 4 + DF_PARAM_BYTES;
 constexpr int DF_SMEM = DF_STAGES * (DF_A_BYTES + DF_B_BYTES) + DF_EPI_BYTES + 256 + 1024;
 constexpr int DF_TW = 16, DF_TH = 8;              // an M tile is a 16 x 8 pixel patch of one image (2-D gather locality)
 
@@ -71,7 +72,8 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
   uint8_t* sB = smem + DF_STAGES * DF_A_BYTES;
   uint8_t* sStage = sB + DF_STAGES * DF_B_BYTES;                 // epilogue staging, 2 KB per epilogue warp
   float* sBias = (float*)(sStage + 4 * EPI_STAGE_BYTES);
-  uint64_t* full = (uint64_t*)((uint8_t*)sBias + DF_BIAS_LD * 4);
+  uint8_t* sParams = (uint8_t*)sBias + DF_BIAS_LD * 4;
+  uint64_t* full = (uint64_t*)(sParams + DF_PARAM_BYTES);
   uint64_t* empty = full + DF_STAGES;
   uint64_t* tfull = empty + DF_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -92,71 +94,95 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp < 8) {
-    // ===== gather producers: 2 threads per pixel, 32 channels (4 x 16 B) each =====
-    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    // ===== gather producers =====
+    // Sampling parameters (4 modulated corner weights + 4 clamped corner offsets per pixel) are computed once per
+    // (pixel, tap) by one thread pair and shared through shared memory; the gather itself maps 8 consecutive lanes
+    // to the 8 16-byte chunks of ONE corner row (64 channels = 128 B), so a warp instruction touches 4 full cache
+    // lines instead of 32 partial ones (the L1 tag rate, one line per cycle, is what bounded the old mapping).
+    const int tid = threadIdx.x;
+    const int pr = tid & 127, prow = tid >> 7;        // parameter role: pixel pr, corner row prow (y0 or y0 + 1)
+    const int grp = tid >> 3, l8 = tid & 7;           // gather role: pixels grp + 32 i, channels [8 l8, 8 l8 + 8)
     const int ncols = 3 * p.taps;
+    const uint32_t sPar = ptx::smem_u32(sParams);
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
-      const int y = (t2 / p.tiles_x) * DF_TH + (r >> 4), x = (t2 % p.tiles_x) * DF_TW + (r & 15);
+      const int y = (t2 / p.tiles_x) * DF_TH + (pr >> 4), x = (t2 % p.tiles_x) * DF_TW + (pr & 15);
       const bool row_ok = y < p.H && x < p.W;
-      const uint16_t* xb = p.x + (long long)b * p.H * p.W * p.ldx + half * 32;
-      // offsets / modulator of tap t: o[t*os2], o[t*os2 + os1] and o[(2*taps + t) * os1]  (os1 = stride between columns)
+      const uint16_t* xb = p.x + (long long)b * p.H * p.W * p.ldx + l8 * 8;
+      // offsets / modulator of tap t: o[2t * os1], o[(2t + 1) * os1], o[(2 taps + t) * os1]
       const float* o; long long os1;
-      if (p.om_tiled) { o = p.om + (long long)tile * ncols * 128 + r; os1 = 128; }
+      if (p.om_tiled) { o = p.om + (long long)tile * ncols * 128 + pr; os1 = 128; }
       else { o = p.om + (((long long)b * p.H + min(y, p.H - 1)) * p.W + min(x, p.W - 1)) * p.ldom; os1 = 1; }
       float ndy = ldg_stream(o), ndx = ldg_stream(o + os1), nmk = ldg_stream(o + 2 * p.taps * os1);
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const float dy = ndy, dx = ndx, mk = row_ok ? nmk : 0.f;
-        if (tap + 1 < p.taps) {      // next tap's offsets while this tap's corners are in flight
-          ndy = ldg_stream(o + (2 * tap + 2) * os1); ndx = ldg_stream(o + (2 * tap + 3) * os1);
-          nmk = ldg_stream(o + (2 * p.taps + tap + 1) * os1);
-        }
+
+      auto params = [&](int tap, float dy, float dx, float mk) {
+        // torchvision semantics: zero outside (-1,H)x(-1,W), per-corner validity; folded into the corner weights so
+        // that every corner load is unconditional (clamped address, weight 0)
         const int ky = tap / p.k, kx = tap - ky * p.k;
         const float py = (float)(y - p.pad + ky) + dy, px = (float)(x - p.pad + kx) + dx;
-        // torchvision semantics: zero outside (-1,H)x(-1,W), per-corner validity; folded into the corner weights so
-        // that all 16 loads are issued unconditionally (clamped addresses) and back to back
-        const bool inb = py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W;
+        const bool inb = row_ok && py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W;
         const float fy = floorf(py), fx = floorf(px);
-        const int y0 = (int)fy, x0 = (int)fx;
-        const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
-        const float m0 = inb ? mk : 0.f;
-        const float wy0 = (y0 >= 0) ? hy * m0 : 0.f, wy1 = (y0 + 1 <= p.H - 1) ? ly * m0 : 0.f;
-        const float wx0 = (x0 >= 0) ? hx : 0.f, wx1 = (x0 + 1 <= p.W - 1) ? lx : 0.f;
-        const float wgt[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
-        const int yc0 = min(max(y0, 0), p.H - 1), yc1 = min(max(y0 + 1, 0), p.H - 1);
+        const int yy = (int)fy + prow, x0 = (int)fx;
+        const float ly = py - fy, lx = px - fx;
+        const float wy = (yy >= 0 && yy <= p.H - 1 && inb) ? (prow ? ly : 1.f - ly) * mk : 0.f;
+        const float wx0 = (x0 >= 0) ? 1.f - lx : 0.f, wx1 = (x0 + 1 <= p.W - 1) ? lx : 0.f;
+        const int yc = min(max(yy, 0), p.H - 1);
         const int xc0 = min(max(x0, 0), p.W - 1), xc1 = min(max(x0 + 1, 0), p.W - 1);
-        const uint4* src[4] = {reinterpret_cast<const uint4*>(xb + ((long long)yc0 * p.W + xc0) * p.ldx),
-                               reinterpret_cast<const uint4*>(xb + ((long long)yc0 * p.W + xc1) * p.ldx),
-                               reinterpret_cast<const uint4*>(xb + ((long long)yc1 * p.W + xc0) * p.ldx),
-                               reinterpret_cast<const uint4*>(xb + ((long long)yc1 * p.W + xc1) * p.ldx)};
+        const int o0 = (yc * p.W + xc0) * p.ldx, o1 = (yc * p.W + xc1) * p.ldx;
+        ptx::sts128(sPar + (tap & 1) * 4096 + pr * 32 + prow * 16,
+                    make_uint4(__float_as_uint(wy * wx0), __float_as_uint(wy * wx1), (uint32_t)o0, (uint32_t)o1));
+      };
+      params(0, ndy, ndx, nmk);
+      if (p.taps > 1) { ndy = ldg_stream(o + 2 * os1); ndx = ldg_stream(o + 3 * os1); nmk = ldg_stream(o + (2 * p.taps + 1) * os1); }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      for (int tap = 0; tap < p.taps; ++tap) {
+        // ---- gather: 4 pixels per thread, 4 corners each ----
         uint4 v[4][4];
+        float wgt[4][4];
 #pragma unroll
-        for (int cnr = 0; cnr < 4; ++cnr)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v[cnr][j] = __ldg(src[cnr] + j);
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t pa = sPar + (tap & 1) * 4096 + (grp + 32 * i) * 32;
+          const uint4 q0 = ptx::lds128(pa), q1 = ptx::lds128(pa + 16);
+          wgt[i][0] = __uint_as_float(q0.x); wgt[i][1] = __uint_as_float(q0.y);
+          wgt[i][2] = __uint_as_float(q1.x); wgt[i][3] = __uint_as_float(q1.y);
+          v[i][0] = __ldg(reinterpret_cast<const uint4*>(xb + q0.z));
+          v[i][1] = __ldg(reinterpret_cast<const uint4*>(xb + q0.w));
+          v[i][2] = __ldg(reinterpret_cast<const uint4*>(xb + q1.z));
+          v[i][3] = __ldg(reinterpret_cast<const uint4*>(xb + q1.w));
+        }
+        // ---- next tap's parameters while the corners are in flight ----
+        if (tap + 1 < p.taps) {
+          const float dy = ndy, dx = ndx, mk = nmk;
+          if (tap + 2 < p.taps) {
+            ndy = ldg_stream(o + (2 * tap + 4) * os1); ndx = ldg_stream(o + (2 * tap + 5) * os1);
+            nmk = ldg_stream(o + (2 * p.taps + tap + 2) * os1);
+          }
+          params(tap + 1, dy, dx, mk);
+        }
         float acc[4][8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+          for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
 #pragma unroll
-        for (int cnr = 0; cnr < 4; ++cnr)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) fma_16x8(acc[j], v[cnr][j], wgt[cnr], p.xdt);
+          for (int cnr = 0; cnr < 4; ++cnr) fma_16x8(acc[i], v[i][cnr], wgt[i][cnr], p.xdt);
+        }
         ptx::mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* rowp = sA + stage * DF_A_BYTES + r * 128;
+        const uint32_t sa = ptx::smem_u32(sA) + stage * DF_A_BYTES;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int chunk = (half * 4 + j) ^ (r & 7);
-          *reinterpret_cast<uint4*>(rowp + chunk * 16) =
-              make_uint4(pack16x2(acc[j][0], acc[j][1], p.xdt), pack16x2(acc[j][2], acc[j][3], p.xdt),
-                         pack16x2(acc[j][4], acc[j][5], p.xdt), pack16x2(acc[j][6], acc[j][7], p.xdt));
+        for (int i = 0; i < 4; ++i) {
+          const int r = grp + 32 * i;
+          ptx::sts128(sa + r * 128 + ((l8 ^ (r & 7)) << 4),
+                      make_uint4(pack16x2(acc[i][0], acc[i][1], p.xdt), pack16x2(acc[i][2], acc[i][3], p.xdt),
+                                 pack16x2(acc[i][4], acc[i][5], p.xdt), pack16x2(acc[i][6], acc[i][7], p.xdt)));
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&full[stage]);
         if (++stage == DF_STAGES) { stage = 0; phase ^= 1; }
+        // parameters of tap + 1 visible to everybody; everybody is done reading those of tap
+        asm volatile("bar.sync 2, 256;" ::: "memory");
       }
     }
   } else if (warp == 8) {

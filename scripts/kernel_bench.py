@@ -50,6 +50,12 @@ def main():
                 ms = ops.bench_op("attn", nw, side, side, heads, 0, shift, precision="fp16")
                 fl = 4.0 * 144 * 144 * 32 * nw * heads
                 print(f"attn windows={nw:5d} heads={heads:2d} shift={shift}: {ms*1e3:9.1f} us  {fl/ms/1e9:7.1f} TF/s  {nw*heads/ms/1e3:8.1f} units/us", flush=True)
+    if which == "deform1":   # deform1 <side> <k>
+        side, k = int(sys.argv[2]), int(sys.argv[3])
+        ms = ops.bench_op("deform", 16, side, side, 64, 256, k, act=1, precision="fp16")
+        fl = 2.0 * 16 * side * side * 256 * k * k * 64
+        print(f"deform {side}^2 k={k}: {ms*1e3:9.1f} us  {fl/ms/1e9:7.1f} TF/s", flush=True)
+        return
     if which in ("all", "deform"):
         for (side, k) in ((256, 7), (256, 3), (256, 1), (128, 7), (64, 7)):
             ms = ops.bench_op("deform", 16, side, side, 64, 256, k, act=1, precision="fp16")
