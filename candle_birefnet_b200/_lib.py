@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
     L.brn_model_finalize.argtypes = [vp]
     L.brn_model_set_precision.argtypes = [vp, C.c_int]
     L.brn_model_set_deform_mode.argtypes = [vp, C.c_int]
+    L.brn_model_set_cuda_graph.argtypes = [vp, C.c_int]
     for name in ("brn_forward_logits", "brn_forward"):
         getattr(L, name).argtypes = [vp, vp, i32, i32, i32, C.c_int, vp, C.c_int, vp]
     L.brn_backbone_forward.argtypes = [vp, vp, i32, i32, i32, C.c_int, C.POINTER(vp), C.c_int, vp]

@@ -105,6 +105,15 @@ brn_status brn_model_set_deform_mode(brn_model* m, int mode) {
   });
 }
 
+brn_status brn_model_set_cuda_graph(brn_model* m, int on) {
+  return guard([&] {
+    BRN_CHECK(m, 1, "null model");
+    std::lock_guard<std::mutex> lk(m->impl.mu);
+    m->impl.use_graph = on ? 1 : 0;
+    if (!on) m->impl.drop_graphs();
+  });
+}
+
 brn_status brn_forward_logits(brn_model* m, const float* x, int32_t B, int32_t H, int32_t W, int x_is_device,
                               float* out, int out_is_device, void* stream) {
   return guard([&] {

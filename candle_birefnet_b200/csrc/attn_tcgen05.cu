@@ -88,7 +88,18 @@ __device__ __forceinline__ void tmem_wait8(uint32_t (&v)[8]) {
                : "memory");
 }
 __device__ __forceinline__ void soft_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(AT_SOFT_THREADS) : "memory"); }
+// the two warps that share a set of query rows (key halves 0 / 1) exchange their partial row max through shared memory
+__device__ __forceinline__ void pair_bar_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory"); }
 
+template <int DT>
+__device__ __forceinline__ uint32_t at_pack(float a, float b) { return DT == BF16 ? pack_bf16x2(a, b) : pack_f16x2(a, b); }
+template <int DT>
+__device__ __forceinline__ float2 at_unpack(uint32_t u) {
+  if (DT == BF16) return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+
+template <int DT>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -131,7 +142,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       ptx::prefetch_tmap(&tmQKV);
       ptx::mbar_expect_tx(bias_bar, AT_BIAS_BYTES);
       ptx::bulk_load(sBias, p.bias16 + (size_t)head * 144 * AT_BIAS_LD, AT_BIAS_BYTES, bias_bar);
-      const uint32_t is_bf = p.dt == BF16 ? 1u : 0u;
+      const uint32_t is_bf = DT == BF16 ? 1u : 0u;
       const uint32_t idesc_s = ptx::make_idesc_16(128, 144, 0, 0, is_bf);   // S = Q K^T : both K-major
       const uint32_t idesc_o = ptx::make_idesc_16(128, 32, 0, 1, is_bf);    // O = P V   : V is MN-major
       auto load_unit = [&](int i) {
@@ -200,6 +211,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
     const int tile = warp >= 8 ? 1 : 0;
     const int half = tile ? warp - 8 : warp >> 2;              // keys [72*half, 72*half + 72)
     const int quad = warp & 3;
+    const int pair = tile ? 4 : quad;                          // warps (q, q+4) and (8, 9) share query rows
     const int r = tile ? 128 + lane : quad * 32 + lane;        // query row (>= 144 for the idle lanes of warps 8, 9)
     const bool row_ok = r < 144;
     const int rr = row_ok ? r : 143;
@@ -207,17 +219,19 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
     const uint32_t s_col = (tile ? (half ? AT_COL_S1B : AT_COL_S1A) : AT_COL_S0) + half * 72;
     const int qi = rr / 12, qj = rr % 12;
     const float LOG2E = 1.4426950408889634f;
-    float* smax = sStat;
-    float* ssum = sStat + 2 * 2 * 144;
+    // all shared-memory traffic of this role goes through explicit shared-space instructions
+    const uint32_t smax = ptx::smem_u32(sStat);                // [par][half][144]
+    const uint32_t ssum = smax + 2 * 2 * 144 * 4;
+    const uint32_t sP_a = ptx::smem_u32(sP);
     const int nw = p.nwh * p.nww;
     ptx::mbar_wait(bias_bar, 0);
-    const uint8_t* brow = sBias + (size_t)rr * AT_BIAS_LD * 2 + half * 144;
+    const uint32_t brow = ptx::smem_u32(sBias) + rr * AT_BIAS_LD * 2 + half * 144;
 
     auto epilogue = [&](int j) {   // O(j) / sum(j) -> 16-bit, head-major channel (src/swin.rs:306-307)
       const int par = j & 1, win = w_first + j * w_step;
       ptx::mbar_wait(o_full, par);
       ptx::tc_fence_after();
-      const float inv = 1.f / (ssum[(par * 2 + 0) * 144 + rr] + ssum[(par * 2 + 1) * 144 + rr]);
+      const float inv = 1.f / (ptx::lds32(ssum + ((par * 2 + 0) * 144 + rr) * 4) + ptx::lds32(ssum + ((par * 2 + 1) * 144 + rr) * 4));
       if (!tile) {
         uint32_t v[16];
         ptx::tmem_ld16(lane_base + AT_COL_O0 + half * 16, v);
@@ -225,10 +239,10 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)win * 144 + r) * p.ldo + head * 32 + half * 16);
 #pragma unroll
         for (int g = 0; g < 2; ++g)
-          dst[g] = make_uint4(pack16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv, p.dt),
-                              pack16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv, p.dt),
-                              pack16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv, p.dt),
-                              pack16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv, p.dt));
+          dst[g] = make_uint4(at_pack<DT>(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv),
+                              at_pack<DT>(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv),
+                              at_pack<DT>(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv),
+                              at_pack<DT>(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv));
       } else if (half == 0) {       // rows 128-143 live in lanes 0-15 of quadrant 0: warp 8 writes all 32 dims
         uint32_t v[32];
         ptx::tmem_ld32(lane_base + AT_COL_O1, v);
@@ -237,10 +251,10 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)win * 144 + r) * p.ldo + head * 32);
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            dst[g] = make_uint4(pack16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv, p.dt),
-                                pack16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv, p.dt),
-                                pack16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv, p.dt),
-                                pack16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv, p.dt));
+            dst[g] = make_uint4(at_pack<DT>(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv),
+                                at_pack<DT>(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv),
+                                at_pack<DT>(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv),
+                                at_pack<DT>(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv));
         }
       }
     };
@@ -248,7 +262,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
     for (int i = 0; i < n_units; ++i) {
       const int par = i & 1, win = w_first + i * w_step;
       // analytic shift mask (src/swin.rs:603-655): only the last window row / column mixes regions.  This thread's
-      // keys all have (ki >= 6) == half; kj >= 6 depends on the key column.
+      // keys all have (ki >= 6) == half; kj >= 6 depends on the key column.  Interior windows take the mask-free path.
       const int wl = win % nw, wi = wl / p.nww, wj = wl - wi * p.nww;
       const bool last_r = p.shift > 0 && wi == p.nwh - 1, last_c = p.shift > 0 && wj == p.nww - 1;
       const bool rmask = last_r && ((half != 0) != (qi >= 6));
@@ -267,27 +281,32 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       ptx::tc_fence_before();
       ptx::mbar_arrive(s_empty);
 
-      // ---- pass 1: s + bias + mask (kept in registers), partial row max ----
+      // ---- pass 1: s + bias (+ mask) kept in registers, partial row max ----
       float sc[72];
       float mx = -INFINITY;
 #pragma unroll
       for (int g = 0; g < 9; ++g) {
-        const uint4 bq = *reinterpret_cast<const uint4*>(brow + g * 16);
+        const uint4 bq = ptx::lds128(brow + g * 16);
         const uint32_t* bh = reinterpret_cast<const uint32_t*>(&bq);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const float2 bf = unpack16x2(bh[t], p.dt);
+          const float2 bf = at_unpack<DT>(bh[t]);
           const int c0 = g * 8 + 2 * t, c1 = c0 + 1;       // key column within this half; 72 = 6 * 12 so kj = c % 12
           const float a0 = __uint_as_float(c0 < 32 ? v0[c0 & 31] : c0 < 64 ? v1[c0 & 31] : v2[c0 & 7]);
           const float a1 = __uint_as_float(c1 < 32 ? v0[c1 & 31] : c1 < 64 ? v1[c1 & 31] : v2[c1 & 7]);
-          sc[c0] = a0 + bf.x + mk[(c0 % 12) >= 6 ? 1 : 0];
-          sc[c1] = a1 + bf.y + mk[(c1 % 12) >= 6 ? 1 : 0];
-          mx = fmaxf(mx, fmaxf(sc[c0], sc[c1]));
+          sc[c0] = a0 + bf.x;
+          sc[c1] = a1 + bf.y;
         }
       }
-      if (row_ok) smax[(par * 2 + half) * 144 + r] = mx;
-      soft_bar_sync();
-      const float m = fmaxf(smax[(par * 2 + 0) * 144 + rr], smax[(par * 2 + 1) * 144 + rr]);
+      if (last_r || last_c) {      // warp-uniform: border windows of a shifted block only
+#pragma unroll
+        for (int c = 0; c < 72; ++c) sc[c] += mk[(c % 12) >= 6 ? 1 : 0];
+      }
+#pragma unroll
+      for (int c = 0; c < 72; c += 2) mx = fmaxf(mx, fmaxf(sc[c], sc[c + 1]));
+      if (row_ok) ptx::sts32(smax + ((par * 2 + half) * 144 + r) * 4, mx);
+      pair_bar_sync(pair);
+      const float m = fmaxf(mx, ptx::lds32(smax + ((par * 2 + (half ^ 1)) * 144 + rr) * 4));
       const float moff = m * LOG2E;
 
       // ---- deferred epilogue of the previous unit (its P V finished long ago); also frees the P buffer ----
@@ -302,16 +321,15 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         for (int t = 0; t < 4; ++t) {
           const float p0 = ex2(fmaf(sc[g * 8 + 2 * t], LOG2E, -moff)), p1 = ex2(fmaf(sc[g * 8 + 2 * t + 1], LOG2E, -moff));
           sum += p0 + p1;
-          packed[t] = pack16x2(p0, p1, p.dt);
+          packed[t] = at_pack<DT>(p0, p1);
         }
         if (row_ok) {
           // keys [8*G, 8*G+8), G = 9*half + g: K step G/2, 16-byte chunk (G&1) of the row's 32 B, XOR row bit 2
           const int G = 9 * half + g, j16 = G >> 1, ch = (G & 1) ^ ((r >> 2) & 1);
-          *reinterpret_cast<uint4*>(sP + j16 * AT_P_BLOCK + r * 32 + ch * 16) =
-              make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          ptx::sts128(sP_a + j16 * AT_P_BLOCK + r * 32 + ch * 16, make_uint4(packed[0], packed[1], packed[2], packed[3]));
         }
       }
-      if (row_ok) ssum[(par * 2 + half) * 144 + r] = sum;
+      if (row_ok) ptx::sts32(ssum + ((par * 2 + half) * 144 + r) * 4, sum);
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
@@ -339,14 +357,16 @@ void tc_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   uint64_t str[1] = {(uint64_t)a.qkv.ld * 2};
   uint32_t box[2] = {32, 144};
   CUtensorMap tm = make_tmap_16(a.qkv.p, a.qkv.dt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
-  cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  if (a.qkv.dt == BF16) cudaFuncSetAttribute(tc_attn_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  else cudaFuncSetAttribute(tc_attn_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
   const int sms = device_sm_count();
   int per_head = std::max(1, sms / a.heads);
   per_head = std::min(per_head, a.n_windows);
   char desc[96] = "";
   if (ctx.kt) snprintf(desc, sizeof desc, "windows=%d heads=%d shift=%d grid=%d", a.n_windows, a.heads, a.shift, a.heads * per_head);
   KScope ks(ctx, KC_ATTN_TC, 4.0 * 144 * 144 * 32 * (double)a.n_windows * a.heads, 0, desc);
-  tc_attn_kernel<<<a.heads * per_head, AT_THREADS, AT_SMEM, ctx.stream>>>(tm, p);
+  if (a.qkv.dt == BF16) tc_attn_kernel<BF16><<<a.heads * per_head, AT_THREADS, AT_SMEM, ctx.stream>>>(tm, p);
+  else tc_attn_kernel<F16><<<a.heads * per_head, AT_THREADS, AT_SMEM, ctx.stream>>>(tm, p);
   BRN_CUDA(cudaGetLastError());
 }
 

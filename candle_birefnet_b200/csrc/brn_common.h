@@ -185,8 +185,9 @@ void glue_resize_nhwc(const LaunchCtx&, View in, View out);                     
 void glue_image2patches(const LaunchCtx&, const float* x_nchw, int B, int H, int W, int th, int tw, View out);
 void glue_nchw_to_nhwc(const LaunchCtx&, const float* x, int B, int C, int H, int W, View out);
 void glue_nhwc_to_nchw(const LaunchCtx&, View in, float* out);
-void glue_gap_sum(const LaunchCtx&, View x, float* sums /*[B][C], zeroed here*/);
-void glue_aspp_pool_bias(const LaunchCtx&, const float* sums, int B, int HW, const LayerW* gap_conv,
+int glue_gap_blocks(int HW);                                                  // partial-sum blocks per image
+void glue_gap_sum(const LaunchCtx&, View x, float* part /*[B][glue_gap_blocks(H*W)][C] partial sums*/);
+void glue_aspp_pool_bias(const LaunchCtx&, const float* part, int B, int HW, const LayerW* gap_conv,
                          const float* conv1_tail /*[64][256] fp32, bn1-scaled*/, const float* bn1_shift /*[64]*/,
                          float* out /*[B][64]*/);
 void glue_gate(const LaunchCtx&, View p, View g16, const float* w16, float b0);

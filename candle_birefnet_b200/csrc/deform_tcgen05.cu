@@ -28,7 +28,7 @@ CUtensorMap make_tmap_16(const void* base, int dt, int rank, const uint64_t* dim
 int device_sm_count();
 EpiP make_epi(int N, const float* bias, int bias_bstride, int act, int act_from, const View& res, const View& out);
 
-constexpr int DF_STAGES = 3;                      // 3 x 48 KB: leaves ~70 KB of L1 for the gathered neighbourhood
+constexpr int DF_STAGES = 2;                      // 2 x 48 KB: leaves ~100 KB of L1 for the gathered neighbourhood (84 KB at k=7)
 constexpr int DF_PRODUCERS = 256;                 // 8 warps
 constexpr int DF_THREADS = DF_PRODUCERS + 32 + 128;
 constexpr int DF_A_BYTES = 128 * 128;             // 128 pixels x 64 ch bf16
@@ -54,16 +54,25 @@ __device__ __forceinline__ float ldg_stream(const float* p) {
   return v;
 }
 
-__device__ __forceinline__ void fma_16x8(float (&acc)[8], const uint4& v, float w, int dt) {
+template <int DT>
+__device__ __forceinline__ void fma_16x8(float (&acc)[8], const uint4& v, float w) {
   const uint32_t* h = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    float2 f = unpack16x2(h[t], dt);
+    float2 f;
+    if (DT == BF16) { f.x = __uint_as_float(h[t] << 16); f.y = __uint_as_float(h[t] & 0xffff0000u); }
+    else f = __half22float2(*reinterpret_cast<const __half2*>(&h[t]));
     acc[2 * t] = fmaf(w, f.x, acc[2 * t]);
     acc[2 * t + 1] = fmaf(w, f.y, acc[2 * t + 1]);
   }
 }
+template <int DT>
+__device__ __forceinline__ uint32_t pack2(float a, float b) { return DT == BF16 ? pack_bf16x2(a, b) : pack_f16x2(a, b); }
 
+// CL = CTAs per cluster.  With CL = 2 the two CTAs walk M tiles 2j and 2j+1 through the same tap sequence; each loads
+// half of the tap's weight slab and TMA-multicasts it into both CTAs (the kernel is L2 -> SM bandwidth bound: 32 KB
+// of weights + the L1 misses of the gather per tap-tile).  DT = operand element type (BF16 / F16).
+template <int CL, int DT>
 __global__ void __launch_bounds__(DF_THREADS, 1)
 tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -82,16 +91,21 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     // full: one arrival per producer warp (after its lanes' proxy fences) + the weight TMA's expect_tx arrival
-    for (int s = 0; s < DF_STAGES; ++s) { ptx::mbar_init(&full[s], DF_PRODUCERS / 32 + 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < DF_STAGES; ++s) { ptx::mbar_init(&full[s], DF_PRODUCERS / 32 + 1); ptx::mbar_init(&empty[s], CL); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
     ptx::fence_barrier_init();
   }
   if (warp == 8) ptx::tmem_alloc(tmem_slot, 512);
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();     // peers' barriers are initialised before any multicast can land
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  // work items: this CTA's M tile of item i is i * CL + rank (may be >= m_tiles for the odd tail: all rows masked)
+  const int rank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
+  const int n_items = (p.m_tiles + CL - 1) / CL;
+  const int item0 = blockIdx.x / CL, item_step = gridDim.x / CL;
 
   if (warp < 8) {
     // ===== gather producers =====
@@ -105,10 +119,11 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
     const int ncols = 3 * p.taps;
     const uint32_t sPar = ptx::smem_u32(sParams);
     int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+    for (int item = item0; item < n_items; item += item_step) {
+      const int tile = min(item * CL + rank, p.m_tiles - 1);
       const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
       const int y = (t2 / p.tiles_x) * DF_TH + (pr >> 4), x = (t2 % p.tiles_x) * DF_TW + (pr & 15);
-      const bool row_ok = y < p.H && x < p.W;
+      const bool row_ok = item * CL + rank < p.m_tiles && y < p.H && x < p.W;
       const uint16_t* xb = p.x + (long long)b * p.H * p.W * p.ldx + l8 * 8;
       // offsets / modulator of tap t: o[2t * os1], o[(2t + 1) * os1], o[(2 taps + t) * os1]
       const float* o; long long os1;
@@ -166,16 +181,16 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
 #pragma unroll
-          for (int cnr = 0; cnr < 4; ++cnr) fma_16x8(acc[i], v[i][cnr], wgt[i][cnr], p.xdt);
+          for (int cnr = 0; cnr < 4; ++cnr) fma_16x8<DT>(acc[i], v[i][cnr], wgt[i][cnr]);
         }
-        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        ptx::mbar_wait_backoff(&empty[stage], phase ^ 1);
         const uint32_t sa = ptx::smem_u32(sA) + stage * DF_A_BYTES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = grp + 32 * i;
           ptx::sts128(sa + r * 128 + ((l8 ^ (r & 7)) << 4),
-                      make_uint4(pack16x2(acc[i][0], acc[i][1], p.xdt), pack16x2(acc[i][2], acc[i][3], p.xdt),
-                                 pack16x2(acc[i][4], acc[i][5], p.xdt), pack16x2(acc[i][6], acc[i][7], p.xdt)));
+                      make_uint4(pack2<DT>(acc[i][0], acc[i][1]), pack2<DT>(acc[i][2], acc[i][3]),
+                                 pack2<DT>(acc[i][4], acc[i][5]), pack2<DT>(acc[i][6], acc[i][7])));
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
@@ -189,9 +204,10 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
     if (ptx::elect_one()) {
       // ===== weight TMA + MMA issuer =====
       ptx::prefetch_tmap(&tmB);
-      const uint32_t idesc = ptx::make_idesc_16(128, p.BN, 0, 0, p.xdt == BF16 ? 1u : 0u);
+      const uint32_t idesc = ptx::make_idesc_16(128, p.BN, 0, 0, DT == BF16 ? 1u : 0u);
       const uint32_t b_bytes = p.BN * 128;
-      const int n_my_tiles = blockIdx.x < p.m_tiles ? (p.m_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+      const int b_rows = p.BN / CL;                            // rows of the slab this CTA loads (and multicasts)
+      const int n_my_tiles = item0 < n_items ? (n_items - 1 - item0) / item_step + 1 : 0;
       const long long total = (long long)n_my_tiles * p.taps;
       // the B loads run DF_STAGES ahead of the MMAs (same ring, same stage order)
       long long issued = 0;
@@ -200,7 +216,9 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
         ptx::mbar_wait(&empty[lstage], lphase ^ 1);
         ptx::mbar_expect_tx(&full[lstage], b_bytes);
         const int tap = (int)(issued % p.taps);
-        ptx::tma_load_2d(sB + lstage * DF_B_BYTES, &tmB, &full[lstage], tap * 64, 0);
+        uint8_t* bdst = sB + lstage * DF_B_BYTES + rank * b_rows * 128;
+        if (CL > 1) ptx::tma_load_2d_mc(bdst, &tmB, &full[lstage], tap * 64, rank * b_rows, (uint16_t)((1u << CL) - 1));
+        else ptx::tma_load_2d(bdst, &tmB, &full[lstage], tap * 64, 0);
         ++issued;
         if (++lstage == DF_STAGES) { lstage = 0; lphase ^= 1; }
       };
@@ -218,7 +236,9 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
           const uint64_t b_desc = ptx::make_smem_desc(ptx::smem_u32(sB + stage * DF_B_BYTES), 16, 1024, ptx::SW_128B);
 #pragma unroll
           for (int k = 0; k < 4; ++k) ptx::umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (tap | k) != 0);
-          ptx::umma_commit(&empty[stage]);
+          // the stage is free once the MMAs of EVERY CTA that received the multicast have read it
+          if (CL > 1) ptx::umma_commit_mc(&empty[stage], (uint16_t)((1u << CL) - 1));
+          else ptx::umma_commit(&empty[stage]);
           if (++stage == DF_STAGES) { stage = 0; phase ^= 1; }
           if (issued < total) issue_b();
         }
@@ -239,10 +259,11 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
     }
     const int c1 = ((p.epi.N + 15) >> 4) * 16;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+    for (int item = item0; item < n_items; item += item_step) {
+      const int tile = item * CL + rank;
       const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
       const int y = (t2 / p.tiles_x) * DF_TH + (row >> 4), x = (t2 % p.tiles_x) * DF_TW + (row & 15);
-      const long long orow = (y < p.H && x < p.W) ? ((long long)b * p.H + y) * p.W + x : -1;
+      const long long orow = (tile < p.m_tiles && y < p.H && x < p.W) ? ((long long)b * p.H + y) * p.W + x : -1;
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
@@ -254,6 +275,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();     // no CTA leaves while a peer may still multicast into it / arrive on its barriers
   if (warp == 8) ptx::tmem_dealloc(tmem_base, 512);
 }
 
@@ -278,15 +300,32 @@ void tc_deform(const LaunchCtx& ctx, const DeformArgs& a) {
   const uint64_t ktot = (uint64_t)w.taps() * 64;
   uint64_t bdims[2] = {ktot, (uint64_t)w.N};
   uint64_t bstr[1] = {ktot * 2};
-  uint32_t bbox[2] = {64, (uint32_t)p.BN};
+  const int sms = device_sm_count();
+  const int CL = (p.BN % 16 == 0 && p.m_tiles >= 2 * sms) ? 2 : 1;
+  uint32_t bbox[2] = {64, (uint32_t)(p.BN / CL)};
   CUtensorMap tmB = make_tmap_16(w.w16(a.x.dt), a.x.dt, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B);
-  cudaFuncSetAttribute(tc_deform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM);
-  const int grid = std::min(p.m_tiles, device_sm_count());
   char desc[96] = "";
   const double M = (double)a.x.rows();
-  if (ctx.kt) snprintf(desc, sizeof desc, "M=%lld N=%d k=%d", (long long)a.x.rows(), w.N, p.k);
+  if (ctx.kt) snprintf(desc, sizeof desc, "M=%lld N=%d k=%d cl=%d", (long long)a.x.rows(), w.N, p.k, CL);
   KScope ks(ctx, KC_DEFORM_TC, 2.0 * M * w.N * w.taps() * 64, M * w.taps() * 4 * 128, desc);
-  tc_deform_kernel<<<grid, DF_THREADS, DF_SMEM, ctx.stream>>>(tmB, p);
+  auto launch = [&](auto kern) {
+    BRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM));
+    // keep the shared-memory carve-out at what the kernel needs: the rest of the 228 KB is the gather's L1
+    BRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (DF_SMEM * 100 + 228 * 1024 - 1) / (228 * 1024)));
+    const int items = (p.m_tiles + CL - 1) / CL;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CL * std::min(items, sms / CL));
+    cfg.blockDim = dim3(DF_THREADS);
+    cfg.dynamicSmemBytes = DF_SMEM;
+    cfg.stream = ctx.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmB, p));
+  };
+  if (CL == 2) { if (a.x.dt == BF16) launch(tc_deform_kernel<2, BF16>); else launch(tc_deform_kernel<2, F16>); }
+  else { if (a.x.dt == BF16) launch(tc_deform_kernel<1, BF16>); else launch(tc_deform_kernel<1, F16>); }
   BRN_CUDA(cudaGetLastError());
 }
 

@@ -31,8 +31,49 @@ __global__ void patch_im2col_kernel(const float* x, int B, int H, int W, int P, 
   g_st(out, odt, row * ldo + k, v);
 }
 
+// P = 4, 16-bit dense output rows (48 elements = 96 B): a warp owns 32 consecutive patches of one patch row.  Loads are
+// float4 per (c, ky) with lane = patch (512 contiguous bytes per instruction); the 32 x 96 B block is transposed
+// through shared memory and leaves as six fully coalesced 512-byte stores (32 consecutive rows are contiguous).
+__global__ void __launch_bounds__(256) patch_im2col4_kernel(const float* __restrict__ x, int H, int W, uint16_t* out, int odt,
+                                                            long long n_groups) {
+  __shared__ __align__(16) uint8_t sm[8][32 * 96];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long g = (long long)blockIdx.x * 8 + warp;     // group = 32 consecutive patches of one patch row
+  if (g >= n_groups) return;
+  const int Wp = W >> 2, Hp = H >> 2, gpr = Wp >> 5;         // groups per patch row (Wp % 32 == 0)
+  const int px = (int)(g % gpr) * 32 + lane;
+  const long long t = g / gpr;
+  const int py = (int)(t % Hp); const long long b = t / Hp;
+  uint8_t* mine = sm[warp];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((b * 3 + c) * H + (py * 4 + ky)) * (long long)W + px * 4));
+      uint2 u;
+      if (odt == BF16) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), d = __floats2bfloat162_rn(v.z, v.w);
+        u = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&d));
+      } else {
+        __half2 a = __floats2half2_rn(v.x, v.y), d = __floats2half2_rn(v.z, v.w);
+        u = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&d));
+      }
+      *reinterpret_cast<uint2*>(mine + lane * 96 + (c * 16 + ky * 4) * 2) = u;   // 96-byte pitch: 8-byte stores, 2-way conflicts at most
+    }
+  __syncwarp();
+  uint4* dst = reinterpret_cast<uint4*>(out + (((b * Hp + py) * (long long)Wp + (px - lane)) * 48));
+#pragma unroll
+  for (int i = 0; i < 6; ++i) dst[i * 32 + lane] = *reinterpret_cast<const uint4*>(mine + (i * 32 + lane) * 16);
+}
+
 void glue_patch_im2col(const LaunchCtx& ctx, const float* x, int B, int H, int W, int P, View out) {
   GLUE_LAUNCH_PROLOGUE(ctx);
+  if (P == 4 && out.dt != F32 && out.ld == 48 && (W / 4) % 32 == 0 && ((uintptr_t)out.p & 15) == 0 && ((uintptr_t)x & 15) == 0) {
+    const long long groups = (long long)B * (H / 4) * (W / 4 / 32);
+    patch_im2col4_kernel<<<(unsigned)((groups + 7) / 8), 256, 0, ctx.stream>>>(x, H, W, (uint16_t*)out.p, out.dt, groups);
+    BRN_CUDA(cudaGetLastError());
+    return;
+  }
   long long total = (long long)B * (H / P) * (W / P) * 3 * P * P;
   patch_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(x, B, H, W, P, out.p, out.dt, out.ld,
                                                                               total);
@@ -167,8 +208,59 @@ __global__ void image2patches_kernel(const float* x, int H, int W, int th, int t
   g_st(out, odt, ((b * th + ty) * (long long)tw + tx) * ldo + ch, v);
 }
 
+// Tiled variant (16-bit output, tw % 32 == 0): a block owns 32 consecutive output pixels (b, ty, tx0..tx0+31) and walks
+// the channels in chunks of CH.  For a channel (c, gy, gx) those 32 pixels are 32 CONSECUTIVE floats of one image row
+// (one coalesced 128-byte read per warp); the [32 px][CH] chunk is transposed through shared memory and written as
+// runs of CH contiguous 16-bit channels per pixel.
+template <int CH>
+__global__ void __launch_bounds__(256) image2patches_tiled_kernel(const float* __restrict__ x, int H, int W, int th, int tw,
+                                                                  uint16_t* out, int odt, int ldo) {
+  constexpr int PITCH = CH + 2;                       // 16-bit elements per shared row (odd word count: conflict-free columns)
+  __shared__ __align__(16) uint16_t sm[32 * PITCH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = H / th, gw = W / tw, Cn = 3 * g * gw;
+  const int tx0 = blockIdx.x * 32, ty = blockIdx.y; const long long b = blockIdx.z;
+  for (int ch0 = 0; ch0 < Cn; ch0 += CH) {
+    for (int j = warp; j < CH; j += 8) {
+      const int ch = ch0 + j;
+      const int c = ch / (g * gw), r = ch - c * g * gw, gy = r / gw, gx = r - gy * gw;
+      const float v = __ldg(x + ((b * 3 + c) * H + (gy * th + ty)) * (long long)W + gx * tw + tx0 + lane);
+      uint16_t hv;
+      if (odt == BF16) { __nv_bfloat16 t = __float2bfloat16(v); hv = *reinterpret_cast<uint16_t*>(&t); }
+      else { __half t = __float2half_rn(v); hv = *reinterpret_cast<uint16_t*>(&t); }
+      sm[lane * PITCH + j] = hv;
+    }
+    __syncthreads();
+    for (int px = warp; px < 32; px += 8) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(out + ((b * th + ty) * (long long)tw + tx0 + px) * ldo + ch0);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(sm + px * PITCH);
+      for (int wd = lane; wd < CH / 2; wd += 32) dst[wd] = src[wd];
+    }
+    __syncthreads();
+  }
+}
+
 void glue_image2patches(const LaunchCtx& ctx, const float* x, int B, int H, int W, int th, int tw, View out) {
   GLUE_LAUNCH_PROLOGUE(ctx);
+  const int Cn = 3 * (H / th) * (W / tw);
+  if (out.dt != F32 && tw % 32 == 0 && out.ld % 2 == 0 && ((uintptr_t)out.p & 3) == 0 && th <= 65535 && B <= 65535) {
+    dim3 grid(tw / 32, th, B);
+    if (Cn % 256 == 0) {
+      image2patches_tiled_kernel<256><<<grid, 256, 0, ctx.stream>>>(x, H, W, th, tw, (uint16_t*)out.p, out.dt, out.ld);
+      BRN_CUDA(cudaGetLastError());
+      return;
+    }
+    if (Cn % 192 == 0) {
+      image2patches_tiled_kernel<192><<<grid, 256, 0, ctx.stream>>>(x, H, W, th, tw, (uint16_t*)out.p, out.dt, out.ld);
+      BRN_CUDA(cudaGetLastError());
+      return;
+    }
+    if (Cn == 48) {
+      image2patches_tiled_kernel<48><<<grid, 256, 0, ctx.stream>>>(x, H, W, th, tw, (uint16_t*)out.p, out.dt, out.ld);
+      BRN_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   long long total = (long long)B * 3 * H * W;
   image2patches_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(x, H, W, th, tw, out.p, out.dt,
                                                                                out.ld, total);
@@ -233,42 +325,50 @@ void glue_sigmoid(const LaunchCtx& ctx, float* p, long long n) {
 //   x5 = relu(bn(conv1x1(mean)))  (src/aspp.rs:315-317), broadcast over H,W (:318), then its 256 channels times
 //   conv1.weight[:, 1024:1280] (:327-329) is a constant 64-vector per image.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gap_sum_kernel(const void* x, int xdt, int ldx, int C, int HW, int chunk,
-                                                      float* sums) {
-  __shared__ float part[256];
+// Deterministic two-level reduction (no atomics: a batch must equal its per-image results bit for bit):
+// block (blk, b) writes the partial sums of its pixel chunk to part[b][blk][C]; aspp_pool_bias_kernel adds the
+// partials in block order.
+constexpr int GAP_CHUNK = 1024;
+__global__ void __launch_bounds__(256) gap_sum_kernel(const void* x, int xdt, int ldx, int C, int HW, float* part) {
+  __shared__ float sh[256];
   const int b = blockIdx.y;
   const int lanes = 256 / C;   // pixel lanes (C divides 256: C = 64)
   const int c = threadIdx.x % C, pl = threadIdx.x / C;
-  const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, HW);
+  const int p0 = blockIdx.x * GAP_CHUNK, p1 = min(p0 + GAP_CHUNK, HW);
   float s = 0.f;
   if (pl < lanes)
     for (int px = p0 + pl; px < p1; px += lanes) s += g_ld(x, xdt, ((long long)b * HW + px) * ldx + c);
-  part[threadIdx.x] = s;
+  sh[threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.x < C) {
     float t = 0.f;
-    for (int l = 0; l < lanes; ++l) t += part[l * C + threadIdx.x];
-    atomicAdd(&sums[b * C + threadIdx.x], t);
+    for (int l = 0; l < lanes; ++l) t += sh[l * C + threadIdx.x];
+    part[((long long)b * gridDim.x + blockIdx.x) * C + threadIdx.x] = t;
   }
 }
 
-void glue_gap_sum(const LaunchCtx& ctx, View x, float* sums) {
+int glue_gap_blocks(int HW) { return (HW + GAP_CHUNK - 1) / GAP_CHUNK; }
+
+void glue_gap_sum(const LaunchCtx& ctx, View x, float* part) {
   GLUE_LAUNCH_PROLOGUE(ctx);
   BRN_CHECK(x.C <= 256 && 256 % x.C == 0, 5, "gap_sum: C must divide 256");
-  BRN_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * x.B * x.C, ctx.stream));
-  const int HW = x.H * x.W, chunk = 1024;
-  dim3 grid((HW + chunk - 1) / chunk, x.B);
-  gap_sum_kernel<<<grid, 256, 0, ctx.stream>>>(x.p, x.dt, x.ld, x.C, HW, chunk, sums);
+  const int HW = x.H * x.W;
+  dim3 grid(glue_gap_blocks(HW), x.B);
+  gap_sum_kernel<<<grid, 256, 0, ctx.stream>>>(x.p, x.dt, x.ld, x.C, HW, part);
   BRN_CUDA(cudaGetLastError());
 }
 
-__global__ void __launch_bounds__(256) aspp_pool_bias_kernel(const float* sums, int HW, const float* wg /*[256][64]*/,
+__global__ void __launch_bounds__(256) aspp_pool_bias_kernel(const float* part, int nblk, int HW, const float* wg /*[256][64]*/,
                                                              const float* bg /*[256]*/, const float* tail /*[64][256]*/,
                                                              const float* shift /*[64]*/, float* out) {
   __shared__ float mean[64];
   __shared__ float x5[256];
   const int b = blockIdx.x, t = threadIdx.x;
-  if (t < 64) mean[t] = sums[b * 64 + t] / (float)HW;
+  if (t < 64) {
+    float s = 0.f;
+    for (int k = 0; k < nblk; ++k) s += part[((long long)b * nblk + k) * 64 + t];
+    mean[t] = s / (float)HW;
+  }
   __syncthreads();
   float s = bg[t];
   for (int c = 0; c < 64; ++c) s = fmaf(wg[t * 64 + c], mean[c], s);
@@ -281,10 +381,11 @@ __global__ void __launch_bounds__(256) aspp_pool_bias_kernel(const float* sums, 
   }
 }
 
-void glue_aspp_pool_bias(const LaunchCtx& ctx, const float* sums, int B, int HW, const LayerW* gap_conv,
+void glue_aspp_pool_bias(const LaunchCtx& ctx, const float* part, int B, int HW, const LayerW* gap_conv,
                          const float* conv1_tail, const float* bn1_shift, float* out) {
   GLUE_LAUNCH_PROLOGUE(ctx);
-  aspp_pool_bias_kernel<<<B, 256, 0, ctx.stream>>>(sums, HW, gap_conv->w32, gap_conv->bias, conv1_tail, bn1_shift, out);
+  aspp_pool_bias_kernel<<<B, 256, 0, ctx.stream>>>(part, glue_gap_blocks(HW), HW, gap_conv->w32, gap_conv->bias, conv1_tail,
+                                                   bn1_shift, out);
   BRN_CUDA(cudaGetLastError());
 }
 

@@ -7,8 +7,11 @@
 // Algorithmic bytes per row: 4*n read + esize*n written (n = C or 4C).
 #include "brn_common.h"
 #include "device_utils.cuh"
+#include "tc_ptx.cuh"
 
 namespace brn {
+
+int device_sm_count();
 
 struct LnP {
   const void* x; int xdt; int ldx; int B, h, w, C;
@@ -108,6 +111,121 @@ __global__ void __launch_bounds__(256) ln_vec_kernel(LnP p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bulk-copy pipelined LayerNorm (LN_PLAIN / LN_WINDOW, fp32 source): the register-staged kernel above keeps only
+// ~3 KB per warp in flight and reaches ~55 % of the HBM roofline.  Here a producer warp streams chunks of R
+// destination rows into a 4-stage shared-memory ring with cp.async.bulk (one copy per run of contiguous source rows:
+// a whole chunk for LN_PLAIN, the 12-token window rows for LN_WINDOW, nothing for pad rows), so 72 KB per CTA and
+// ~200 KB per SM are in flight with no register cost; 8 consumer warps normalise one row each from shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int LNB_STAGES = 4;
+constexpr int LNB_CHUNK_FLOATS = 4608;     // R * C <= 4608 floats = 18 KB per stage
+constexpr int LNB_THREADS = 288;           // 8 consumer warps + 1 producer warp
+
+template <int NV>
+__global__ void __launch_bounds__(LNB_THREADS) ln_bulk_kernel(LnP p, int R, long long n_chunks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  float* ring = (float*)smem;                                      // [LNB_STAGES][R * C]
+  float* sg = ring + LNB_STAGES * LNB_CHUNK_FLOATS;                // gamma [C]
+  float* sb = sg + p.C;                                            // beta  [C]
+  uint64_t* full = (uint64_t*)(sb + p.C);
+  uint64_t* empty = full + LNB_STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = p.C, n4 = n >> 2;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LNB_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 8); }
+    ptx::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < n; i += LNB_THREADS) { sg[i] = p.gamma[i]; sb[i] = p.beta[i]; }
+  __syncthreads();
+  const float* xs = (const float*)p.x;
+  const uint32_t row_bytes = (uint32_t)n * 4;
+
+  if (warp == 8) {
+    // ===== producer warp: lane j owns row j of the chunk =====
+    int stage = 0; uint32_t phase = 0;
+    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+      const long long m = ch * R + lane;
+      long long tok = -1;
+      if (lane < R && m < p.rows) tok = p.mode == LN_WINDOW ? window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift) : m;
+      const long long prev = __shfl_up_sync(0xffffffffu, tok, 1);
+      const bool valid = tok >= 0;
+      const bool start = valid && (lane == 0 || prev < 0 || tok != prev + 1 || p.ldx != n);
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid), smask = __ballot_sync(0xffffffffu, start);
+      ptx::mbar_wait_backoff(&empty[stage], phase ^ 1);
+      if (lane == 0) ptx::mbar_expect_tx(&full[stage], (uint32_t)__popc(vmask) * row_bytes);
+      __syncwarp();
+      if (start) {
+        // the run ends before the next run start or the first invalid row after this lane
+        const uint32_t above = ~((2u << lane) - 1u);                 // lanes > this one
+        const uint32_t stop = (smask | ~vmask) & above;
+        const int end = stop ? __ffs(stop) - 1 : 32;
+        ptx::bulk_load(ring + stage * LNB_CHUNK_FLOATS + lane * n, xs + tok * p.ldx, (uint32_t)(end - lane) * row_bytes,
+                       &full[stage]);
+      }
+      if (++stage == LNB_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===== consumers: warp w takes the rows with (row index in the CTA's stream) % 8 == w =====
+    int stage = 0; uint32_t phase = 0;
+    long long seq = 0;
+    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x, ++seq) {
+      ptx::mbar_wait(&full[stage], phase);
+      const float* src = ring + stage * LNB_CHUNK_FLOATS;
+      for (int j = (int)((8 + warp - (seq * R) % 8) % 8); j < R; j += 8) {
+        const long long m = ch * R + j;
+        if (m >= p.rows) break;
+        const bool pad = p.mode == LN_WINDOW && window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift) < 0;
+        float4 v[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int e4 = lane + 32 * i;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e4 < n4 && !pad) {
+            v[i] = *reinterpret_cast<const float4*>(src + j * n + 4 * e4);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+          }
+        }
+        if (pad) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            if (lane + 32 * i < n4) ln_store4(p.out, p.odt, m * p.ldo + 4 * (lane + 32 * i), make_float4(0.f, 0.f, 0.f, 0.f));
+          continue;
+        }
+        const float mean = warp_sum(s) / n;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          if (lane + 32 * i < n4) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+          }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / n + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int e4 = lane + 32 * i;
+          if (e4 < n4) {
+            const float4 g = *reinterpret_cast<const float4*>(sg + 4 * e4);
+            const float4 bb = *reinterpret_cast<const float4*>(sb + 4 * e4);
+            float4 o;
+            o.x = (v[i].x - mean) * rstd * g.x + bb.x;
+            o.y = (v[i].y - mean) * rstd * g.y + bb.y;
+            o.z = (v[i].z - mean) * rstd * g.z + bb.z;
+            o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+            ln_store4(p.out, p.odt, m * p.ldo + 4 * e4, o);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty[stage]);
+      if (++stage == LNB_STAGES) { stage = 0; phase ^= 1; }
+    }
+  }
+}
+
 // generic fallback (any dtype / alignment): three passes over the row
 __global__ void __launch_bounds__(256) ln_generic_kernel(LnP p) {
   const int lane = threadIdx.x & 31;
@@ -169,6 +287,27 @@ void glue_layernorm(const LaunchCtx& ctx, const LnArgs& a) {
                    (a.out.ld * dsize(a.out.dt)) % (4 * dsize(a.out.dt)) == 0 && a.out.ld % 4 == 0 &&
                    (((uintptr_t)a.out.p) & (4 * dsize(a.out.dt) - 1)) == 0 && (((uintptr_t)a.gamma | (uintptr_t)a.beta) & 15) == 0;
   const int nv = (n + 127) / 128;
+  static const bool no_bulk = [] { const char* v = getenv("BRN_LN_BULK"); return v && v[0] == '0'; }();
+  if (vec && !no_bulk && a.mode != LN_MERGE && n <= LNB_CHUNK_FLOATS && nv <= 12 && a.x.p != nullptr &&
+      !(a.x.p == a.out.p && a.mode == LN_WINDOW)) {
+    int R = std::min(32, LNB_CHUNK_FLOATS / n);
+    if (a.mode == LN_WINDOW) { const int cands[6] = {24, 12, 6, 4, 3, 2}; int r = 1; for (int c : cands) if (c <= R) { r = c; break; } R = r; }
+    const long long n_chunks = (p.rows + R - 1) / R;
+    const int smem = LNB_STAGES * LNB_CHUNK_FLOATS * 4 + 2 * n * 4 + 2 * LNB_STAGES * 8 + 128;
+#define LNB_CASE(NV)                                                                                      \
+    do {                                                                                                  \
+      BRN_CUDA(cudaFuncSetAttribute(ln_bulk_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      int occ = 1;                                                                                        \
+      BRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bulk_kernel<NV>, LNB_THREADS, smem)); \
+      const int grid = (int)std::min<long long>(n_chunks, (long long)device_sm_count() * std::max(occ, 1)); \
+      ln_bulk_kernel<NV><<<grid, LNB_THREADS, smem, ctx.stream>>>(p, R, n_chunks);                         \
+    } while (0)
+    if (nv <= 1) LNB_CASE(1); else if (nv <= 2) LNB_CASE(2); else if (nv <= 3) LNB_CASE(3); else if (nv <= 4) LNB_CASE(4);
+    else if (nv <= 6) LNB_CASE(6); else if (nv <= 8) LNB_CASE(8); else LNB_CASE(12);
+#undef LNB_CASE
+    BRN_CUDA(cudaGetLastError());
+    return;
+  }
   if (vec && nv <= 24) {
 #define LN_CASE(NV) ln_vec_kernel<NV><<<grid, 256, 0, ctx.stream>>>(p)
     if (nv <= 1) LN_CASE(1); else if (nv <= 2) LN_CASE(2); else if (nv <= 3) LN_CASE(3); else if (nv <= 4) LN_CASE(4);

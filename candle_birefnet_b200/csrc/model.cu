@@ -56,6 +56,7 @@ Model::Model(const brn_config& c, int dev) : cfg(c), device(dev) {
 
 Model::~Model() {
   cudaSetDevice(device);
+  drop_graphs();
   for (void* p : allocs) cudaFree(p);
   if (arena.base) cudaFree(arena.base);
   for (auto& pe : prof) { if (pe.e0) cudaEventDestroy(pe.e0); if (pe.e1) cudaEventDestroy(pe.e1); }
@@ -411,8 +412,14 @@ void Model::finalize() {
 // ------------------------------------------------------------------------------------------------
 // forward graph
 // ------------------------------------------------------------------------------------------------
+void Model::drop_graphs() {
+  for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  graphs.clear();
+}
+
 void Model::ensure_arena(size_t bytes) {
   if (arena.cap >= bytes) return;
+  drop_graphs();          // captured kernels hold arena addresses
   if (arena.base) { BRN_CUDA(cudaFree(arena.base)); arena.base = nullptr; arena.cap = 0; }
   size_t want = bytes + (bytes >> 4) + (1 << 20);
   BRN_CUDA(cudaMalloc(&arena.base, want));
@@ -537,7 +544,7 @@ void Model::run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out) {
       GemmArgs g; g.x = t; g.w = &w.br[b].reg; g.pad = k / 2; g.act = ACT_RELU; g.out = dst; op_gemm(ctx, g);
     }
   }
-  float* sums = (float*)arena.alloc((size_t)B * 64 * 4);
+  float* sums = (float*)arena.alloc((size_t)B * glue_gap_blocks(H * W) * 64 * 4);
   float* pb = (float*)arena.alloc((size_t)B * 64 * 4);
   glue_gap_sum(ctx, t, sums);
   glue_aspp_pool_bias(ctx, sums, B, H * W, &w.gap, w.conv1_tail, w.bn1_shift, pb);
@@ -680,6 +687,7 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
     for (auto& pe : prof) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
     prof.clear();
   }
+  static const bool graph_env_off = [] { const char* v = getenv("BRN_CUDA_GRAPH"); return v && v[0] == '0'; }();
   for (int b0 = 0; b0 < B; b0 += mb) {
     const int nb = std::min(mb, B - b0);
     arena.off = 0;
@@ -688,7 +696,53 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
     const float* xi = x + (size_t)b0 * 3 * H * W;
     float* oi = out + (size_t)b0 * H * W;
     if (!x_dev) { BRN_CUDA(cudaMemcpyAsync(din, xi, (size_t)nb * 3 * H * W * 4, cudaMemcpyHostToDevice, st)); xi = din; }
-    run_forward(ctx, xi, nb, H, W, out_dev ? oi : dout, apply_sigmoid);
+    float* ko = out_dev ? oi : dout;
+    bool done = false;
+    // the legacy / per-thread default streams cannot be captured
+    const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+    if (use_graph && !graph_env_off && !prof_on && !ctx.force_simt && capturable) {
+      GraphKey key{xi, ko, arena.base, nb, H, W, (int)cfg.precision, (int)cfg.deform_mode, apply_sigmoid ? 1 : 0};
+      GraphEntry* e = nullptr;
+      for (auto& g : graphs) if (g.key == key) { e = &g; break; }
+      if (!e) {
+        if (graphs.size() >= 16) {     // evict the least recently used entry
+          size_t lru = 0;
+          for (size_t i = 1; i < graphs.size(); ++i) if (graphs[i].stamp < graphs[lru].stamp) lru = i;
+          if (graphs[lru].exec) cudaGraphExecDestroy(graphs[lru].exec);
+          graphs.erase(graphs.begin() + lru);
+        }
+        graphs.push_back(GraphEntry{});
+        e = &graphs.back();
+        e->key = key;
+      }
+      e->stamp = ++graph_clock;
+      if (!e->exec && e->seen >= 1) {
+        // second sighting: capture (nothing executes during capture), instantiate, then replay below
+        long long counted = 0;
+        LaunchCtx cctx = ctx; cctx.launches = &counted;
+        cudaGraph_t graph = nullptr;
+        BRN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try {
+          run_forward(cctx, xi, nb, H, W, ko, apply_sigmoid);
+        } catch (...) {
+          cudaStreamEndCapture(st, &graph);
+          if (graph) cudaGraphDestroy(graph);
+          throw;
+        }
+        BRN_CUDA(cudaStreamEndCapture(st, &graph));
+        cudaError_t ie = cudaGraphInstantiate(&e->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        BRN_CHECK(ie == cudaSuccess, 2, std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ie));
+        e->launches = counted;
+      }
+      if (e->exec) {
+        BRN_CUDA(cudaGraphLaunch(e->exec, st));
+        launches += e->launches;
+        done = true;
+      }
+      e->seen++;
+    }
+    if (!done) run_forward(ctx, xi, nb, H, W, ko, apply_sigmoid);
     if (!out_dev) BRN_CUDA(cudaMemcpyAsync(oi, dout, (size_t)nb * H * W * 4, cudaMemcpyDeviceToHost, st));
   }
   if (!x_dev || !out_dev || prof_on) BRN_CUDA(cudaStreamSynchronize(st));

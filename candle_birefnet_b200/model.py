@@ -170,6 +170,10 @@ class BiRefNet:
         check(lib().brn_model_set_deform_mode(self._h, _DEF[mode]))
         self.config.deform_mode = mode
 
+    def set_cuda_graph(self, on: bool) -> None:
+        """Replay the forward as a CUDA graph from the second call with the same buffers/shape (default on)."""
+        check(lib().brn_model_set_cuda_graph(self._h, 1 if on else 0))
+
     def close(self) -> None:
         if self._h:
             lib().brn_model_destroy(self._h)

@@ -105,6 +105,11 @@ BRN_API brn_status brn_model_finalize(brn_model* m);
 
 BRN_API brn_status brn_model_set_precision(brn_model* m, int precision);
 BRN_API brn_status brn_model_set_deform_mode(brn_model* m, int deform_mode);
+/* CUDA-graph replay of the forward (default on): the second call with the same device buffers, shape and modes captures
+ * the ~460-kernel launch sequence of forward_logits into a CUDA graph; later calls replay it (batch-1 latency is
+ * launch-bound otherwise).  Host-pointer calls use the handle's own staging buffers, so they replay as well.  Has no
+ * counterpart in the reference (candle launches op by op). */
+BRN_API brn_status brn_model_set_cuda_graph(brn_model* m, int on);
 
 BRN_API void brn_model_destroy(brn_model* m);
 

@@ -50,6 +50,12 @@ def main():
                 ms = ops.bench_op("attn", nw, side, side, heads, 0, shift, precision="fp16")
                 fl = 4.0 * 144 * 144 * 32 * nw * heads
                 print(f"attn windows={nw:5d} heads={heads:2d} shift={shift}: {ms*1e3:9.1f} us  {fl/ms/1e9:7.1f} TF/s  {nw*heads/ms/1e3:8.1f} units/us", flush=True)
+    if which == "attn1":   # attn1 <windows> <heads> <side> <shift>
+        nw, heads, side, shift = [int(v) for v in sys.argv[2:6]]
+        ms = ops.bench_op("attn", nw, side, side, heads, 0, shift, precision="fp16")
+        fl = 4.0 * 144 * 144 * 32 * nw * heads
+        print(f"attn windows={nw:5d} heads={heads:2d} shift={shift}: {ms*1e3:9.1f} us  {fl/ms/1e9:7.1f} TF/s  {nw*heads/ms/1e3:8.1f} units/us", flush=True)
+        return
     if which == "deform1":   # deform1 <side> <k>
         side, k = int(sys.argv[2]), int(sys.argv[3])
         ms = ops.bench_op("deform", 16, side, side, 64, 256, k, act=1, precision="fp16")

@@ -162,3 +162,56 @@ def test_forward_logits_swin_l_512(precision):
     exp = R.forward_logits(torch.from_numpy(x), as_torch(wnp), cfg, "cpu_fallback").numpy()
     m.close()
     check_logits(got, exp, precision)
+
+
+def test_cuda_graph_replay_is_bit_identical(mini_models):
+    """The forward is captured into a CUDA graph on the second call with the same buffers; eager launches, the capture
+    call and every replay must agree bit for bit, and switching modes / shapes must not replay a stale graph."""
+    m = mini_models["B"]
+    m.set_precision("fp16")
+    m.set_deform_mode("deformable")
+    x = make_input(2, 96, 128, seed=21)
+    m.set_cuda_graph(False)
+    eager = m.forward_logits(x)
+    m.set_cuda_graph(True)
+    runs = [m.forward_logits(x) for _ in range(4)]          # eager, capture + replay, replay, replay
+    for r in runs:
+        assert np.array_equal(r, eager)
+    x2 = make_input(2, 96, 128, seed=22)                     # same staging buffers, new contents
+    m.set_cuda_graph(False)
+    e2 = m.forward_logits(x2)
+    m.set_cuda_graph(True)
+    assert np.array_equal(m.forward_logits(x2), e2)
+    m.set_deform_mode("cpu_fallback")                        # different graph key
+    g3 = m.forward_logits(x2)
+    m.set_cuda_graph(False)
+    assert np.array_equal(m.forward_logits(x2), g3)
+    m.set_cuda_graph(True)
+    m.set_deform_mode("deformable")
+    xd = torch.from_numpy(x).cuda()
+    outs = [m.forward_logits(xd).cpu().numpy() for _ in range(3)]   # device-pointer entry: keyed by the pointers
+    for o in outs:
+        assert np.array_equal(o, eager)
+
+
+def test_full_size_properties_swin_l_1024():
+    """BASELINE.json's full size (Swin-L, 1024x1024): properties that need no oracle run.  (1) Image independence:
+    a batch equals its per-image results bit for bit (the sharding contract).  (2) Weight-set A: the deformable path
+    (zero offset / modulator convs => integer sampling, modulator 1) equals the plain-conv path to rounding.
+    (3) The fp16 tensor-core path stays within the north-star tolerance of the fp32 SIMT path of the same library."""
+    cfg = R.Config.swin_l()
+    wnp = make_weights(cfg, seed=0, weight_set="A")
+    m = cb.BiRefNet.new(py_cfg(cfg, "fp16", "deformable"), wnp)
+    x = make_input(2, 1024, 1024, seed=77)
+    both = m.forward_logits(x)
+    assert both.shape == (2, 1, 1024, 1024) and np.isfinite(both).all()
+    one = m.forward_logits(x[1:2])
+    assert np.array_equal(both[1:2], one)
+    m.set_deform_mode("cpu_fallback")
+    plain = m.forward_logits(x[1:2])
+    ds = np.abs(sigmoid(plain) - sigmoid(one)).max()
+    assert ds <= 1e-2 and iou(sigmoid(plain), sigmoid(one)) >= 0.999, ds
+    m.set_precision("fp32")
+    ref32 = m.forward_logits(x[1:2])
+    m.close()
+    check_logits(plain, ref32, "fp16")
