@@ -364,6 +364,8 @@ brn_status brn_bench_op(int device, int precision, int kind, int32_t B, int32_t 
         View om = make_view(s.alloc(px * 3 * taps * 4), F32, B, H, W, 3 * taps);
         fill(s, om.p, F32, (long long)px * 3 * taps, 3u, 2.0f);
         d.x = x; d.om = om; d.w = &L; d.act = act; d.out = o;
+        // random offsets are layout-agnostic: read them tile-major, as the model does (tc_gemm out_tiled)
+        d.om_tiled = (H % 8 == 0 && W % 16 == 0 && precision != BRN_PREC_FP32) ? 1 : 0;
         launch = [&] { op_deform(ctx, d); };
       }
     } else {

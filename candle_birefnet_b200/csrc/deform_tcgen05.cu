@@ -29,12 +29,14 @@ int device_sm_count();
 EpiP make_epi(int N, const float* bias, int bias_bstride, int act, int act_from, const View& res, const View& out);
 
 constexpr int DF_STAGES = 2;                      // 2 x 48 KB: leaves ~100 KB of L1 for the gathered neighbourhood (84 KB at k=7)
-constexpr int DF_PRODUCERS = 256;                 // 8 warps
+constexpr int DF_PRODUCERS = 512;                 // 16 warps = 2 groups of 8: group q gathers the taps g with g % 2 == q
+constexpr int DF_GROUP = DF_PRODUCERS / 2;
+constexpr int DF_MMA_WARP = DF_PRODUCERS / 32;    // warp 16: weight TMA + MMA issue; warps 17-20: epilogue
 constexpr int DF_THREADS = DF_PRODUCERS + 32 + 128;
 constexpr int DF_A_BYTES = 128 * 128;             // 128 pixels x 64 ch bf16
 constexpr int DF_B_BYTES = 256 * 128;
 constexpr int DF_BIAS_LD = 288;
-constexpr int DF_PARAM_BYTES = 2 * 128 * 32;      // double-buffered sampling parameters: 128 pixels x 32 B
+constexpr int DF_PARAM_BYTES = 2 * 2 * 128 * 32;  // per group: double-buffered sampling parameters, 128 pixels x 32 B
 constexpr int DF_EPI_BYTES = 4 * EPI_STAGE_BYTES + DF_BIAS_LD * 4 + DF_PARAM_BYTES;
 constexpr int DF_SMEM = DF_STAGES * (DF_A_BYTES + DF_B_BYTES) + DF_EPI_BYTES + 256 + 1024;
 constexpr int DF_TW = 16, DF_TH = 8;              // an M tile is a 16 x 8 pixel patch of one image (2-D gather locality)
@@ -91,11 +93,11 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     // full: one arrival per producer warp (after its lanes' proxy fences) + the weight TMA's expect_tx arrival
-    for (int s = 0; s < DF_STAGES; ++s) { ptx::mbar_init(&full[s], DF_PRODUCERS / 32 + 1); ptx::mbar_init(&empty[s], CL); }
+    for (int s = 0; s < DF_STAGES; ++s) { ptx::mbar_init(&full[s], DF_GROUP / 32 + 1); ptx::mbar_init(&empty[s], CL); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
     ptx::fence_barrier_init();
   }
-  if (warp == 8) ptx::tmem_alloc(tmem_slot, 512);
+  if (warp == DF_MMA_WARP) ptx::tmem_alloc(tmem_slot, 512);
   ptx::tc_fence_before();
   __syncthreads();
   if (CL > 1) ptx::cluster_sync_all();     // peers' barriers are initialised before any multicast can land
@@ -107,57 +109,84 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
   const int n_items = (p.m_tiles + CL - 1) / CL;
   const int item0 = blockIdx.x / CL, item_step = gridDim.x / CL;
 
-  if (warp < 8) {
+  if (warp < DF_MMA_WARP) {
     // ===== gather producers =====
+    // Two groups of 8 warps; the taps of this CTA's tile sequence are numbered g = 0, 1, 2, ... (tile-major) and group
+    // q owns the taps with g % 2 == q, i.e. ring stage q.  While one group waits for its corner loads the other one
+    // blends -- the gather is latency bound (L2 hits of a 2-D neighbourhood), not bandwidth bound.
     // Sampling parameters (4 modulated corner weights + 4 clamped corner offsets per pixel) are computed once per
-    // (pixel, tap) by one thread pair and shared through shared memory; the gather itself maps 8 consecutive lanes
-    // to the 8 16-byte chunks of ONE corner row (64 channels = 128 B), so a warp instruction touches 4 full cache
-    // lines instead of 32 partial ones (the L1 tag rate, one line per cycle, is what bounded the old mapping).
-    const int tid = threadIdx.x;
-    const int pr = tid & 127, prow = tid >> 7;        // parameter role: pixel pr, corner row prow (y0 or y0 + 1)
-    const int grp = tid >> 3, l8 = tid & 7;           // gather role: pixels grp + 32 i, channels [8 l8, 8 l8 + 8)
+    // (pixel, tap) by one thread pair of the group and shared through shared memory; the gather maps 8 consecutive
+    // lanes to the 8 16-byte chunks of ONE corner row (64 channels = 128 B), so a warp instruction touches 4 full
+    // cache lines instead of 32 partial ones (the L1 tag rate is one line per cycle).
+    static_assert(DF_STAGES == 2, "group q <-> ring stage q");
+    const int q = warp >> 3, gtid = threadIdx.x & (DF_GROUP - 1);
+    const int pr = gtid & 127, prow = gtid >> 7;      // parameter role: pixel pr, corner row prow (y0 or y0 + 1)
+    const int grp = gtid >> 3, l8 = gtid & 7;         // gather role: pixels grp + 32 i, channels [8 l8, 8 l8 + 8)
     const int ncols = 3 * p.taps;
-    const uint32_t sPar = ptx::smem_u32(sParams);
-    int stage = 0; uint32_t phase = 0;
-    for (int item = item0; item < n_items; item += item_step) {
-      const int tile = min(item * CL + rank, p.m_tiles - 1);
+    const uint32_t sPar = ptx::smem_u32(sParams) + q * 8192;
+    const uint32_t sa = ptx::smem_u32(sA) + q * DF_A_BYTES;
+    const int n_my_items = item0 < n_items ? (n_items - 1 - item0) / item_step + 1 : 0;
+    const long long img_elems = (long long)p.H * p.W * p.ldx;
+
+    // position in the tap sequence: local item `it`, tap (ky, kx); per-pixel data of the parameter role
+    int it = 0, tap = q, ky = 0, kx = 0, y = 0, x = 0, tile = 0;
+    bool row_ok = false;
+    const float* o = p.om; long long os1 = 1;
+    auto enter_tile = [&]() {
+      while (tap >= p.taps) { tap -= p.taps; ++it; }
+      if (it >= n_my_items) return;
+      const int t = (item0 + it * item_step) * CL + rank;
+      tile = min(t, p.m_tiles - 1);
       const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
-      const int y = (t2 / p.tiles_x) * DF_TH + (pr >> 4), x = (t2 % p.tiles_x) * DF_TW + (pr & 15);
-      const bool row_ok = item * CL + rank < p.m_tiles && y < p.H && x < p.W;
-      const uint16_t* xb = p.x + (long long)b * p.H * p.W * p.ldx + l8 * 8;
+      y = (t2 / p.tiles_x) * DF_TH + (pr >> 4); x = (t2 % p.tiles_x) * DF_TW + (pr & 15);
+      row_ok = t < p.m_tiles && y < p.H && x < p.W;
+      ky = tap / p.k; kx = tap - ky * p.k;
       // offsets / modulator of tap t: o[2t * os1], o[(2t + 1) * os1], o[(2 taps + t) * os1]
-      const float* o; long long os1;
       if (p.om_tiled) { o = p.om + (long long)tile * ncols * 128 + pr; os1 = 128; }
       else { o = p.om + (((long long)b * p.H + min(y, p.H - 1)) * p.W + min(x, p.W - 1)) * p.ldom; os1 = 1; }
-      float ndy = ldg_stream(o), ndx = ldg_stream(o + os1), nmk = ldg_stream(o + 2 * p.taps * os1);
+    };
+    auto advance2 = [&]() {
+      tap += 2; kx += 2;
+      if (tap >= p.taps) { enter_tile(); return; }
+      if (kx >= p.k) { kx -= p.k; ++ky; }
+      if (kx >= p.k) { kx -= p.k; ++ky; }
+    };
+    auto params = [&](int buf, float dy, float dx, float mk) {
+      // torchvision semantics: zero outside (-1,H)x(-1,W), per-corner validity; folded into the corner weights so
+      // that every corner load is unconditional (clamped address, weight 0)
+      const float py = (float)(y - p.pad + ky) + dy, px = (float)(x - p.pad + kx) + dx;
+      const bool inb = row_ok && py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W;
+      const float fy = floorf(py), fx = floorf(px);
+      const int yy = (int)fy + prow, x0 = (int)fx;
+      const float ly = py - fy, lx = px - fx;
+      const float wy = (yy >= 0 && yy <= p.H - 1 && inb) ? (prow ? ly : 1.f - ly) * mk : 0.f;
+      const float wx0 = (x0 >= 0) ? 1.f - lx : 0.f, wx1 = (x0 + 1 <= p.W - 1) ? lx : 0.f;
+      const int yc = min(max(yy, 0), p.H - 1);
+      const int xc0 = min(max(x0, 0), p.W - 1), xc1 = min(max(x0 + 1, 0), p.W - 1);
+      const int o0 = (yc * p.W + xc0) * p.ldx, o1 = (yc * p.W + xc1) * p.ldx;
+      ptx::sts128(sPar + buf * 4096 + pr * 32 + prow * 16,
+                  make_uint4(__float_as_uint(wy * wx0), __float_as_uint(wy * wx1), (uint32_t)o0, (uint32_t)o1));
+    };
 
-      auto params = [&](int tap, float dy, float dx, float mk) {
-        // torchvision semantics: zero outside (-1,H)x(-1,W), per-corner validity; folded into the corner weights so
-        // that every corner load is unconditional (clamped address, weight 0)
-        const int ky = tap / p.k, kx = tap - ky * p.k;
-        const float py = (float)(y - p.pad + ky) + dy, px = (float)(x - p.pad + kx) + dx;
-        const bool inb = row_ok && py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W;
-        const float fy = floorf(py), fx = floorf(px);
-        const int yy = (int)fy + prow, x0 = (int)fx;
-        const float ly = py - fy, lx = px - fx;
-        const float wy = (yy >= 0 && yy <= p.H - 1 && inb) ? (prow ? ly : 1.f - ly) * mk : 0.f;
-        const float wx0 = (x0 >= 0) ? 1.f - lx : 0.f, wx1 = (x0 + 1 <= p.W - 1) ? lx : 0.f;
-        const int yc = min(max(yy, 0), p.H - 1);
-        const int xc0 = min(max(x0, 0), p.W - 1), xc1 = min(max(x0 + 1, 0), p.W - 1);
-        const int o0 = (yc * p.W + xc0) * p.ldx, o1 = (yc * p.W + xc1) * p.ldx;
-        ptx::sts128(sPar + (tap & 1) * 4096 + pr * 32 + prow * 16,
-                    make_uint4(__float_as_uint(wy * wx0), __float_as_uint(wy * wx1), (uint32_t)o0, (uint32_t)o1));
-      };
-      params(0, ndy, ndx, nmk);
-      if (p.taps > 1) { ndy = ldg_stream(o + 2 * os1); ndx = ldg_stream(o + 3 * os1); nmk = ldg_stream(o + (2 * p.taps + 1) * os1); }
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      for (int tap = 0; tap < p.taps; ++tap) {
-        // ---- gather: 4 pixels per thread, 4 corners each ----
-        uint4 v[4][4];
-        float wgt[4][4];
+    enter_tile();
+    if (it < n_my_items) params(0, ldg_stream(o + 2 * tap * os1), ldg_stream(o + (2 * tap + 1) * os1), ldg_stream(o + (2 * p.taps + tap) * os1));
+    asm volatile("bar.sync %0, 256;" ::"r"(2 + q) : "memory");
+    for (int k = 0; it < n_my_items; ++k) {
+      const uint16_t* xb = p.x + (long long)(tile / tiles_per_img) * img_elems + l8 * 8;   // image of the CURRENT tap's tile
+      // step to the group's next tap and fetch its offsets now; its parameters are computed below, while the second
+      // half of this tap's corners is in flight
+      advance2();
+      const bool more = it < n_my_items;
+      float ndy = 0.f, ndx = 0.f, nmk = 0.f;
+      if (more) { ndy = ldg_stream(o + 2 * tap * os1); ndx = ldg_stream(o + (2 * tap + 1) * os1); nmk = ldg_stream(o + (2 * p.taps + tap) * os1); }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t pa = sPar + (tap & 1) * 4096 + (grp + 32 * i) * 32;
+      for (int h = 0; h < 2; ++h) {
+        // ---- gather: 2 pixels per half, 4 corners each ----
+        uint4 v[2][4];
+        float wgt[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t pa = sPar + (k & 1) * 4096 + (grp + 32 * (2 * h + i)) * 32;
           const uint4 q0 = ptx::lds128(pa), q1 = ptx::lds128(pa + 16);
           wgt[i][0] = __uint_as_float(q0.x); wgt[i][1] = __uint_as_float(q0.y);
           wgt[i][2] = __uint_as_float(q1.x); wgt[i][3] = __uint_as_float(q1.y);
@@ -166,41 +195,31 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
           v[i][2] = __ldg(reinterpret_cast<const uint4*>(xb + q1.z));
           v[i][3] = __ldg(reinterpret_cast<const uint4*>(xb + q1.w));
         }
-        // ---- next tap's parameters while the corners are in flight ----
-        if (tap + 1 < p.taps) {
-          const float dy = ndy, dx = ndx, mk = nmk;
-          if (tap + 2 < p.taps) {
-            ndy = ldg_stream(o + (2 * tap + 4) * os1); ndx = ldg_stream(o + (2 * tap + 5) * os1);
-            nmk = ldg_stream(o + (2 * p.taps + tap + 2) * os1);
-          }
-          params(tap + 1, dy, dx, mk);
-        }
-        float acc[4][8];
+        if (h == 1 && more) params((k + 1) & 1, ndy, ndx, nmk);
+        float acc[2][8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
 #pragma unroll
           for (int cnr = 0; cnr < 4; ++cnr) fma_16x8<DT>(acc[i], v[i][cnr], wgt[i][cnr]);
         }
-        ptx::mbar_wait_backoff(&empty[stage], phase ^ 1);
-        const uint32_t sa = ptx::smem_u32(sA) + stage * DF_A_BYTES;
+        if (h == 0) ptx::mbar_wait_backoff(&empty[q], (uint32_t)((k & 1) ^ 1));
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = grp + 32 * i;
+        for (int i = 0; i < 2; ++i) {
+          const int r = grp + 32 * (2 * h + i);
           ptx::sts128(sa + r * 128 + ((l8 ^ (r & 7)) << 4),
                       make_uint4(pack2<DT>(acc[i][0], acc[i][1]), pack2<DT>(acc[i][2], acc[i][3]),
                                  pack2<DT>(acc[i][4], acc[i][5]), pack2<DT>(acc[i][6], acc[i][7])));
         }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&full[stage]);
-        if (++stage == DF_STAGES) { stage = 0; phase ^= 1; }
-        // parameters of tap + 1 visible to everybody; everybody is done reading those of tap
-        asm volatile("bar.sync 2, 256;" ::: "memory");
       }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&full[q]);
+      // the next tap's parameters are visible to the whole group; everybody is done reading this tap's
+      asm volatile("bar.sync %0, 256;" ::"r"(2 + q) : "memory");
     }
-  } else if (warp == 8) {
+  } else if (warp == DF_MMA_WARP) {
     if (ptx::elect_one()) {
       // ===== weight TMA + MMA issuer =====
       ptx::prefetch_tmap(&tmB);
@@ -251,7 +270,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int eth = threadIdx.x - (DF_PRODUCERS + 32);
-    const uint32_t stage = ptx::smem_u32(sStage) + (warp - 9) * EPI_STAGE_BYTES;
+    const uint32_t stage = ptx::smem_u32(sStage) + (warp - DF_MMA_WARP - 1) * EPI_STAGE_BYTES;
     const uint32_t sb = ptx::smem_u32(sBias);
     if (p.epi.bias) {
       for (int t = eth; t < DF_BIAS_LD; t += 128) ptx::sts32(sb + t * 4, t < p.epi.N ? __ldg(p.epi.bias + t) : 0.f);
@@ -267,7 +286,15 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      epi_warp_dyn(p.epi, taddr, 0, 0, c1, orow, p.epi.bias ? sb : 0u, stage, lane);
+      // only the epilogues a deformable conv can have (no residual; none / ReLU): keeps the 80-register kernel small
+      const uint32_t sbb = p.epi.bias ? sb : 0u;
+      if (p.epi.odt == F32) {
+        if (p.epi.act == ACT_RELU) epi_warp<ACT_RELU, true, 0>(p.epi, taddr, 0, 0, c1, orow, sbb, stage, lane);
+        else epi_warp<ACT_NONE, true, 0>(p.epi, taddr, 0, 0, c1, orow, sbb, stage, lane);
+      } else {
+        if (p.epi.act == ACT_RELU) epi_warp<ACT_RELU, false, 0>(p.epi, taddr, 0, 0, c1, orow, sbb, stage, lane);
+        else epi_warp<ACT_NONE, false, 0>(p.epi, taddr, 0, 0, c1, orow, sbb, stage, lane);
+      }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -276,11 +303,11 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
   ptx::tc_fence_before();
   __syncthreads();
   if (CL > 1) ptx::cluster_sync_all();     // no CTA leaves while a peer may still multicast into it / arrive on its barriers
-  if (warp == 8) ptx::tmem_dealloc(tmem_base, 512);
+  if (warp == DF_MMA_WARP) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 bool tc_deform_supported(const DeformArgs& a) {
-  return a.w && (a.x.dt == BF16 || a.x.dt == F16) && a.w->w16(a.x.dt) && a.x.C == 64 && a.w->cin_pad == 64 && a.x.ld % 8 == 0 &&
+  return a.w && (a.act == ACT_NONE || a.act == ACT_RELU) && (a.x.dt == BF16 || a.x.dt == F16) && a.w->w16(a.x.dt) && a.x.C == 64 && a.w->cin_pad == 64 && a.x.ld % 8 == 0 &&
          (((uintptr_t)a.x.p) & 15) == 0 && a.w->N <= 256 && a.om.dt == F32;
 }
 

@@ -25,8 +25,8 @@
 namespace brn {
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;
-constexpr int TC_EPI_WARPS = 8;                               // two per TMEM lane quadrant, interleaved column chunks
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;            // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_EPI_WARPS = 8;                               // two per TMEM lane quadrant (contiguous column parts; 12 warps measured slower)
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;            // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 constexpr int TC_B_BYTES = 256 * TC_BK * 2;     // 32 KB (BN <= 256)
 constexpr int TC_BIAS_LD = 288;                                // floats per accumulator stage (BN <= 256, padded to 32)
@@ -138,9 +138,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===== epilogue: 8 warps; warp % 4 selects the TMEM lane quadrant, (warp - 2) / 4 the column half =====
+    // ===== epilogue: warp % 4 selects the TMEM lane quadrant, (warp - 2) / 4 the column part =====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;
+    constexpr int PER_Q = TC_EPI_WARPS / 4;
     const int row = q * 32 + lane;
     const int eth = threadIdx.x - 64;
     const uint32_t stage = ptx::smem_u32(sStage) + (warp - 2) * EPI_STAGE_BYTES;
@@ -155,9 +156,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (valid && p.rm.enabled) orow = window_row_to_token(orow, p.rm.h, p.rm.w, p.rm.hp, p.rm.wp, p.rm.shift);
       const int n0 = n_tile * p.BN;
       const int nch = min(p.BN, p.epi.N - n0 + 15) >> 4;     // 16-column chunks of this tile that hold real columns
-      int h0 = (nch + 1) >> 1;
-      if (!o32) h0 = min((h0 + 1) & ~1, nch);                // 16-bit output: keep the split on a 32-column granule
-      const int c0 = half ? h0 * 16 : 0, c1 = half ? nch * 16 : h0 * 16;
+      const int gsz = o32 ? 1 : 2;                           // 16-bit output: keep the split on 32-column granules
+      const int per = ((nch + gsz - 1) / gsz + PER_Q - 1) / PER_Q * gsz;
+      const int c0 = min(part * per, nch) * 16, c1 = min((part + 1) * per, nch) * 16;
       const uint32_t sb = ptx::smem_u32(sBias) + acc * TC_BIAS_LD * 4;
       if (p.epi.bias) {
         // this tile's bias -> shared (double buffered with the accumulator stage; an M tile lies inside one image)

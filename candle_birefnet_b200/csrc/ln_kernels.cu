@@ -122,8 +122,10 @@ constexpr int LNB_STAGES = 4;
 constexpr int LNB_CHUNK_FLOATS = 4608;     // R * C <= 4608 floats = 18 KB per stage
 constexpr int LNB_THREADS = 288;           // 8 consumer warps + 1 producer warp
 
-template <int NV>
+// NV float4 per lane, LPR lanes per row (32, or 16 for short rows: two rows per warp, no idle lanes at C = 192)
+template <int NV, int LPR>
 __global__ void __launch_bounds__(LNB_THREADS) ln_bulk_kernel(LnP p, int R, long long n_chunks) {
+  constexpr int RPW = 32 / LPR;                                     // rows per warp pass
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   float* ring = (float*)smem;                                      // [LNB_STAGES][R * C]
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bulk_kernel(LnP p, int R, long
   float* sb = sg + p.C;                                            // beta  [C]
   uint64_t* full = (uint64_t*)(sb + p.C);
   uint64_t* empty = full + LNB_STAGES;
+  int* sflag = (int*)(empty + LNB_STAGES);                         // [LNB_STAGES][32]: 1 = real row, 0 = pad / past the end
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = p.C, n4 = n >> 2;
   if (threadIdx.x == 0) {
@@ -154,6 +157,8 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bulk_kernel(LnP p, int R, long
       const bool start = valid && (lane == 0 || prev < 0 || tok != prev + 1 || p.ldx != n);
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid), smask = __ballot_sync(0xffffffffu, start);
       ptx::mbar_wait_backoff(&empty[stage], phase ^ 1);
+      sflag[stage * 32 + lane] = valid ? 1 : 0;
+      __syncwarp();
       if (lane == 0) ptx::mbar_expect_tx(&full[stage], (uint32_t)__popc(vmask) * row_bytes);
       __syncwarp();
       if (start) {
@@ -167,54 +172,58 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bulk_kernel(LnP p, int R, long
       if (++stage == LNB_STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
-    // ===== consumers: warp w takes the rows with (row index in the CTA's stream) % 8 == w =====
+    // ===== consumers: row groups (RPW adjacent rows) go round-robin over the 8 warps across chunks =====
+    const int sub = lane / LPR, l = lane % LPR;
+    const int gpc = (R + RPW - 1) / RPW;                            // row groups per chunk
     int stage = 0; uint32_t phase = 0;
     long long seq = 0;
     for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x, ++seq) {
       ptx::mbar_wait(&full[stage], phase);
       const float* src = ring + stage * LNB_CHUNK_FLOATS;
-      for (int j = (int)((8 + warp - (seq * R) % 8) % 8); j < R; j += 8) {
+      for (int gj = (int)((8 + warp - (seq * gpc) % 8) % 8); gj < gpc; gj += 8) {
+        const int j = gj * RPW + sub;
         const long long m = ch * R + j;
-        if (m >= p.rows) break;
-        const bool pad = p.mode == LN_WINDOW && window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift) < 0;
+        const bool in_range = j < R && m < p.rows;
+        const bool real = in_range && sflag[stage * 32 + j] != 0;
         float4 v[NV];
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          const int e4 = lane + 32 * i;
+          const int e4 = l + LPR * i;
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e4 < n4 && !pad) {
+          if (e4 < n4 && real) {
             v[i] = *reinterpret_cast<const float4*>(src + j * n + 4 * e4);
             s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
           }
         }
-        if (pad) {
 #pragma unroll
-          for (int i = 0; i < NV; ++i)
-            if (lane + 32 * i < n4) ln_store4(p.out, p.odt, m * p.ldo + 4 * (lane + 32 * i), make_float4(0.f, 0.f, 0.f, 0.f));
-          continue;
-        }
-        const float mean = warp_sum(s) / n;
+        for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / n;
         float q = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          if (lane + 32 * i < n4) {
+          if (l + LPR * i < n4) {
             const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
             q += (a * a + b * b) + (c * c + d * d);
           }
         }
-        const float rstd = rsqrtf(warp_sum(q) / n + 1e-5f);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q / n + 1e-5f);
+        if (!in_range) continue;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          const int e4 = lane + 32 * i;
+          const int e4 = l + LPR * i;
           if (e4 < n4) {
-            const float4 g = *reinterpret_cast<const float4*>(sg + 4 * e4);
-            const float4 bb = *reinterpret_cast<const float4*>(sb + 4 * e4);
-            float4 o;
-            o.x = (v[i].x - mean) * rstd * g.x + bb.x;
-            o.y = (v[i].y - mean) * rstd * g.y + bb.y;
-            o.z = (v[i].z - mean) * rstd * g.z + bb.z;
-            o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);            // pad rows of LN_WINDOW are zeros AFTER the norm
+            if (real) {
+              const float4 g = *reinterpret_cast<const float4*>(sg + 4 * e4);
+              const float4 bb = *reinterpret_cast<const float4*>(sb + 4 * e4);
+              o.x = (v[i].x - mean) * rstd * g.x + bb.x;
+              o.y = (v[i].y - mean) * rstd * g.y + bb.y;
+              o.z = (v[i].z - mean) * rstd * g.z + bb.z;
+              o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+            }
             ln_store4(p.out, p.odt, m * p.ldo + 4 * e4, o);
           }
         }
@@ -293,17 +302,19 @@ void glue_layernorm(const LaunchCtx& ctx, const LnArgs& a) {
     int R = std::min(32, LNB_CHUNK_FLOATS / n);
     if (a.mode == LN_WINDOW) { const int cands[6] = {24, 12, 6, 4, 3, 2}; int r = 1; for (int c : cands) if (c <= R) { r = c; break; } R = r; }
     const long long n_chunks = (p.rows + R - 1) / R;
-    const int smem = LNB_STAGES * LNB_CHUNK_FLOATS * 4 + 2 * n * 4 + 2 * LNB_STAGES * 8 + 128;
-#define LNB_CASE(NV)                                                                                      \
+    const int smem = LNB_STAGES * LNB_CHUNK_FLOATS * 4 + 2 * n * 4 + 2 * LNB_STAGES * 8 + LNB_STAGES * 32 * 4 + 128;
+#define LNB_CASE(NV, LPR)                                                                                 \
     do {                                                                                                  \
-      BRN_CUDA(cudaFuncSetAttribute(ln_bulk_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      BRN_CUDA(cudaFuncSetAttribute(ln_bulk_kernel<NV, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
       int occ = 1;                                                                                        \
-      BRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bulk_kernel<NV>, LNB_THREADS, smem)); \
+      BRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bulk_kernel<NV, LPR>, LNB_THREADS, smem)); \
       const int grid = (int)std::min<long long>(n_chunks, (long long)device_sm_count() * std::max(occ, 1)); \
-      ln_bulk_kernel<NV><<<grid, LNB_THREADS, smem, ctx.stream>>>(p, R, n_chunks);                         \
+      ln_bulk_kernel<NV, LPR><<<grid, LNB_THREADS, smem, ctx.stream>>>(p, R, n_chunks);                    \
     } while (0)
-    if (nv <= 1) LNB_CASE(1); else if (nv <= 2) LNB_CASE(2); else if (nv <= 3) LNB_CASE(3); else if (nv <= 4) LNB_CASE(4);
-    else if (nv <= 6) LNB_CASE(6); else if (nv <= 8) LNB_CASE(8); else LNB_CASE(12);
+    const int n4 = n / 4;
+    if (n4 <= 16) LNB_CASE(1, 16); else if (n4 <= 32) LNB_CASE(2, 16); else if (n4 <= 48) LNB_CASE(3, 16);
+    else if (nv <= 2) LNB_CASE(2, 32); else if (nv <= 3) LNB_CASE(3, 32); else if (nv <= 4) LNB_CASE(4, 32);
+    else if (nv <= 6) LNB_CASE(6, 32); else if (nv <= 8) LNB_CASE(8, 32); else LNB_CASE(12, 32);
 #undef LNB_CASE
     BRN_CUDA(cudaGetLastError());
     return;
