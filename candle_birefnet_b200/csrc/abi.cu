@@ -295,14 +295,12 @@ brn_status brn_window_attention(int device, int precision, const float* qkv, con
     View qx = q32;
     if (AD != F32) { qx = make_view(s.alloc(rows * 3 * C * 2), AD, 1, 1, (int)rows, 3 * C); glue_copy_cast(ctx, q32, qx); }
     float* b32 = s.put(bias, (size_t)heads * 144 * 144);
-    // bf16 padded copy [heads][144][152]
-    std::vector<float> padded((size_t)heads * 144 * 152, 0.f);
-    for (size_t r = 0; r < (size_t)heads * 144; ++r) memcpy(&padded[r * 152], &bias[r * 144], 144 * 4);
-    View p32 = make_view(s.put(padded.data(), padded.size()), F32, 1, 1, heads * 144, 152);
-    View p16 = make_view(s.alloc(padded.size() * 2), AD == F16 ? F16 : BF16, 1, 1, heads * 144, 152);
-    glue_copy_cast(ctx, p32, p16);
+    // padded fp32 copy [heads][144][148] for the tcgen05 kernel
+    std::vector<float> padded((size_t)heads * 144 * 148, 0.f);
+    for (size_t r = 0; r < (size_t)heads * 144; ++r) memcpy(&padded[r * 148], &bias[r * 144], 144 * 4);
+    float* b32p = s.put(padded.data(), padded.size());
     View o = make_view(s.alloc(rows * C * dsize(AD)), AD, 1, 1, (int)rows, C);
-    AttnArgs a; a.qkv = qx; a.bias32 = b32; a.bias16 = p16.p; a.n_windows = n_windows;
+    AttnArgs a; a.qkv = qx; a.bias32 = b32; a.bias32p = b32p; a.n_windows = n_windows;
     a.heads = heads; a.nwh = hp / 12; a.nww = wp / 12; a.shift = shift; a.out = o;
     op_attention(ctx, a);
     View o32 = o;
@@ -373,12 +371,12 @@ brn_status brn_bench_op(int device, int precision, int kind, int32_t B, int32_t 
       const size_t rows = (size_t)nwin * 144;
       View q = make_view(s.alloc(rows * 3 * Cc * dsize(AD)), AD, 1, 1, (int)rows, 3 * Cc);
       fill(s, q.p, AD, (long long)rows * 3 * Cc, 5u, 1.0f);
-      void* b16 = s.alloc((size_t)heads * 144 * 152 * 2);
-      fill(s, b16, AD == F32 ? BF16 : AD, (long long)heads * 144 * 152, 6u, 0.5f);
+      float* b32p = (float*)s.alloc((size_t)heads * 144 * 148 * 4);
+      fill(s, b32p, F32, (long long)heads * 144 * 148, 6u, 0.5f);
       float* b32 = (float*)s.alloc((size_t)heads * 144 * 144 * 4);
       fill(s, b32, F32, (long long)heads * 144 * 144, 7u, 0.5f);
       View o = make_view(s.alloc(rows * Cc * dsize(AD)), AD, 1, 1, (int)rows, Cc);
-      at.qkv = q; at.bias32 = b32; at.bias16 = b16; at.n_windows = nwin; at.heads = heads;
+      at.qkv = q; at.bias32 = b32; at.bias32p = b32p; at.n_windows = nwin; at.heads = heads;
       at.nwh = H; at.nww = W; at.shift = k; at.out = o;
       launch = [&] { op_attention(ctx, at); };
     }

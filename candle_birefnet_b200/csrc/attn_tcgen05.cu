@@ -39,9 +39,9 @@ int device_sm_count();
 constexpr int AT_SOFT_WARPS = 10;
 constexpr int AT_SOFT_THREADS = 32 * AT_SOFT_WARPS;      // 320
 constexpr int AT_THREADS = AT_SOFT_THREADS + 32;         // + control warp
-constexpr int AT_BIAS_LD = 152;                          // 16-bit elements per bias row (304 B)
-constexpr int AT_BIAS_BYTES = 144 * AT_BIAS_LD * 2;      // 43,776
-constexpr int AT_BIAS_REGION = 44 * 1024;
+constexpr int AT_BIAS_LD = 148;                          // fp32 elements per bias row (592 B: conflict-free 16-byte row reads)
+constexpr int AT_BIAS_BYTES = 144 * AT_BIAS_LD * 4;      // 85,248
+constexpr int AT_BIAS_REGION = 84 * 1024;
 constexpr int AT_TILE_BYTES = 144 * 64;                  // one of Q/K/V: 9,216
 constexpr int AT_STAGE_BYTES = 3 * AT_TILE_BYTES;        // 27,648
 constexpr int AT_STAGES = 3;
@@ -52,7 +52,7 @@ constexpr int AT_SMEM = AT_BIAS_REGION + AT_STAGES * AT_STAGE_BYTES + AT_P_REGIO
 constexpr uint32_t AT_COL_S0 = 0, AT_COL_S1A = 144, AT_COL_S1B = 288, AT_COL_O0 = 432, AT_COL_O1 = 464;
 
 struct AttnP {
-  const uint16_t* bias16;        // [heads][144][152], bf16 or fp16 (dt)
+  const float* bias32p;          // [heads][144][148] fp32
   int dt;                        // operand / output element type: BF16 or F16
   int n_windows, heads, C;
   int nwh, nww, shift;
@@ -141,7 +141,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       // ===== TMA + MMA issuer =====
       ptx::prefetch_tmap(&tmQKV);
       ptx::mbar_expect_tx(bias_bar, AT_BIAS_BYTES);
-      ptx::bulk_load(sBias, p.bias16 + (size_t)head * 144 * AT_BIAS_LD, AT_BIAS_BYTES, bias_bar);
+      ptx::bulk_load(sBias, p.bias32p + (size_t)head * 144 * AT_BIAS_LD, AT_BIAS_BYTES, bias_bar);
       const uint32_t is_bf = DT == BF16 ? 1u : 0u;
       const uint32_t idesc_s = ptx::make_idesc_16(128, 144, 0, 0, is_bf);   // S = Q K^T : both K-major
       const uint32_t idesc_o = ptx::make_idesc_16(128, 32, 0, 1, is_bf);    // O = P V   : V is MN-major
@@ -192,16 +192,16 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       issue_s(0);
       for (int i = 0; i < n_units; ++i) {
         if (i + 1 < n_units) {      // S of the next unit as soon as this unit's scores sit in registers
-          ptx::mbar_wait(&qkv_full[(i + 1) % AT_STAGES], ((i + 1) / AT_STAGES) & 1);
-          ptx::mbar_wait(s_empty, i & 1);
+          ptx::mbar_wait_backoff(&qkv_full[(i + 1) % AT_STAGES], ((i + 1) / AT_STAGES) & 1);
+          ptx::mbar_wait_backoff(s_empty, i & 1);
           ptx::tc_fence_after();
           issue_s(i + 1);
         }
         if (i + 2 < n_units) {      // prefetch two units ahead; that stage held unit i-1
-          if (i >= 1) ptx::mbar_wait(&qkv_empty[(i + 2) % AT_STAGES], ((i - 1) / AT_STAGES) & 1);
+          if (i >= 1) ptx::mbar_wait_backoff(&qkv_empty[(i + 2) % AT_STAGES], ((i - 1) / AT_STAGES) & 1);
           load_unit(i + 2);
         }
-        ptx::mbar_wait(p_full, i & 1);
+        ptx::mbar_wait_backoff(p_full, i & 1);
         ptx::tc_fence_after();
         issue_pv(i);
       }
@@ -225,7 +225,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
     const uint32_t sP_a = ptx::smem_u32(sP);
     const int nw = p.nwh * p.nww;
     ptx::mbar_wait(bias_bar, 0);
-    const uint32_t brow = ptx::smem_u32(sBias) + rr * AT_BIAS_LD * 2 + half * 144;
+    const uint32_t brow = ptx::smem_u32(sBias) + rr * AT_BIAS_LD * 4 + half * 288;
 
     auto epilogue = [&](int j) {   // O(j) / sum(j) -> 16-bit, head-major channel (src/swin.rs:306-307)
       const int par = j & 1, win = w_first + j * w_step;
@@ -285,17 +285,14 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       float sc[72];
       float mx = -INFINITY;
 #pragma unroll
-      for (int g = 0; g < 9; ++g) {
-        const uint4 bq = ptx::lds128(brow + g * 16);
-        const uint32_t* bh = reinterpret_cast<const uint32_t*>(&bq);
+      for (int g = 0; g < 18; ++g) {
+        const uint4 bq = ptx::lds128(brow + g * 16);       // 4 fp32 bias values
+        const uint32_t* bf = reinterpret_cast<const uint32_t*>(&bq);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const float2 bf = at_unpack<DT>(bh[t]);
-          const int c0 = g * 8 + 2 * t, c1 = c0 + 1;       // key column within this half; 72 = 6 * 12 so kj = c % 12
-          const float a0 = __uint_as_float(c0 < 32 ? v0[c0 & 31] : c0 < 64 ? v1[c0 & 31] : v2[c0 & 7]);
-          const float a1 = __uint_as_float(c1 < 32 ? v0[c1 & 31] : c1 < 64 ? v1[c1 & 31] : v2[c1 & 7]);
-          sc[c0] = a0 + bf.x;
-          sc[c1] = a1 + bf.y;
+          const int c = g * 4 + t;                         // key column within this half; 72 = 6 * 12 so kj = c % 12
+          const float a = __uint_as_float(c < 32 ? v0[c & 31] : c < 64 ? v1[c & 31] : v2[c & 7]);
+          sc[c] = a + __uint_as_float(bf[t]);
         }
       }
       if (last_r || last_c) {      // warp-uniform: border windows of a shifted block only
@@ -349,7 +346,8 @@ void tc_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   BRN_CHECK(a.qkv.ld % 8 == 0 && a.out.ld % 8 == 0 && (((uintptr_t)a.qkv.p | (uintptr_t)a.out.p) & 15) == 0, 5,
             "tc_attention: alignment");
   AttnP p{};
-  p.bias16 = (const uint16_t*)a.bias16; p.dt = a.qkv.dt; p.n_windows = a.n_windows; p.heads = a.heads; p.C = a.heads * 32;
+  BRN_CHECK(a.bias32p != nullptr, 1, "tc_attention: padded fp32 bias missing");
+  p.bias32p = a.bias32p; p.dt = a.qkv.dt; p.n_windows = a.n_windows; p.heads = a.heads; p.C = a.heads * 32;
   p.nwh = a.nwh; p.nww = a.nww; p.shift = a.shift;
   p.out = (uint16_t*)a.out.p; p.ldo = a.out.ld;
   const uint64_t rows = (uint64_t)a.n_windows * 144;

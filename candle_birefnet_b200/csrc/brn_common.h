@@ -111,7 +111,8 @@ struct DeformArgs {
 struct AttnArgs {
   View qkv;               // [rows = nWin*144, 3C], window order, q pre-scaled
   const float* bias32 = nullptr;          // [heads][144][144] fp32
-  const void* bias16 = nullptr;           // [heads][144][152] bf16 or fp16 matching qkv.dt (rows padded to 304 B)
+  const float* bias32p = nullptr;         // [heads][144][148] fp32: rows padded to 592 B (conflict-free row-per-thread
+                                          // 16-byte shared-memory reads in tc_attn_kernel)
   int n_windows = 0;      // total windows (B * nW)
   int heads = 0;
   int nwh = 0, nww = 0;   // windows per image along h / w

@@ -71,6 +71,29 @@ __device__ __forceinline__ void fma_16x8(float (&acc)[8], const uint4& v, float 
 template <int DT>
 __device__ __forceinline__ uint32_t pack2(float a, float b) { return DT == BF16 ? pack_bf16x2(a, b) : pack_f16x2(a, b); }
 
+// base + 32-bit byte offset as one IMAD.WIDE.U32 (the plain C++ form compiles to an IMAD + two IADD3 per load: the
+// 16 corner addresses per thread-tap were 20 % of the kernel's instructions)
+__device__ __forceinline__ const uint4* addr_off(const void* base, uint32_t off_bytes) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(off_bytes), "l"((unsigned long long)base));
+  return reinterpret_cast<const uint4*>(r);
+}
+// fp16 operands: blend the 4 corners in packed half2 arithmetic (one HMUL2 + three HFMA2 per channel pair instead of
+// 4 x (unpack + FFMA) + pack).  The weights arrive as duplicated half2; the result is the A-operand bit pattern.
+__device__ __forceinline__ uint4 blend_h2(const uint4 (&v)[4], const uint32_t (&w)[4]) {
+  uint4 r;
+  uint32_t* ro = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    __half2 a = __hmul2(*reinterpret_cast<const __half2*>(&reinterpret_cast<const uint32_t*>(&v[0])[t]), *reinterpret_cast<const __half2*>(&w[0]));
+#pragma unroll
+    for (int c = 1; c < 4; ++c)
+      a = __hfma2(*reinterpret_cast<const __half2*>(&reinterpret_cast<const uint32_t*>(&v[c])[t]), *reinterpret_cast<const __half2*>(&w[c]), a);
+    ro[t] = *reinterpret_cast<uint32_t*>(&a);
+  }
+  return r;
+}
+
 // CL = CTAs per cluster.  With CL = 2 the two CTAs walk M tiles 2j and 2j+1 through the same tap sequence; each loads
 // half of the tap's weight slab and TMA-multicasts it into both CTAs (the kernel is L2 -> SM bandwidth bound: 32 KB
 // of weights + the L1 misses of the gather per tap-tile).  DT = operand element type (BF16 / F16).
@@ -163,9 +186,13 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
       const float wx0 = (x0 >= 0) ? 1.f - lx : 0.f, wx1 = (x0 + 1 <= p.W - 1) ? lx : 0.f;
       const int yc = min(max(yy, 0), p.H - 1);
       const int xc0 = min(max(x0, 0), p.W - 1), xc1 = min(max(x0 + 1, 0), p.W - 1);
-      const int o0 = (yc * p.W + xc0) * p.ldx, o1 = (yc * p.W + xc1) * p.ldx;
-      ptx::sts128(sPar + buf * 4096 + pr * 32 + prow * 16,
-                  make_uint4(__float_as_uint(wy * wx0), __float_as_uint(wy * wx1), (uint32_t)o0, (uint32_t)o1));
+      const uint32_t o0 = (uint32_t)((yc * p.W + xc0) * p.ldx) * 2u, o1 = (uint32_t)((yc * p.W + xc1) * p.ldx) * 2u;   // bytes
+      uint32_t w0, w1;
+      if (DT == F16) {
+        const __half2 h0 = __float2half2_rn(wy * wx0), h1 = __float2half2_rn(wy * wx1);
+        w0 = *reinterpret_cast<const uint32_t*>(&h0); w1 = *reinterpret_cast<const uint32_t*>(&h1);
+      } else { w0 = __float_as_uint(wy * wx0); w1 = __float_as_uint(wy * wx1); }
+      ptx::sts128(sPar + buf * 4096 + pr * 32 + prow * 16, make_uint4(w0, w1, o0, o1));
     };
 
     enter_tile();
@@ -183,34 +210,38 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
       for (int h = 0; h < 2; ++h) {
         // ---- gather: 2 pixels per half, 4 corners each ----
         uint4 v[2][4];
-        float wgt[2][4];
+        uint32_t wgt[2][4];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const uint32_t pa = sPar + (k & 1) * 4096 + (grp + 32 * (2 * h + i)) * 32;
           const uint4 q0 = ptx::lds128(pa), q1 = ptx::lds128(pa + 16);
-          wgt[i][0] = __uint_as_float(q0.x); wgt[i][1] = __uint_as_float(q0.y);
-          wgt[i][2] = __uint_as_float(q1.x); wgt[i][3] = __uint_as_float(q1.y);
-          v[i][0] = __ldg(reinterpret_cast<const uint4*>(xb + q0.z));
-          v[i][1] = __ldg(reinterpret_cast<const uint4*>(xb + q0.w));
-          v[i][2] = __ldg(reinterpret_cast<const uint4*>(xb + q1.z));
-          v[i][3] = __ldg(reinterpret_cast<const uint4*>(xb + q1.w));
+          wgt[i][0] = q0.x; wgt[i][1] = q0.y; wgt[i][2] = q1.x; wgt[i][3] = q1.y;
+          v[i][0] = __ldg(addr_off(xb, q0.z));
+          v[i][1] = __ldg(addr_off(xb, q0.w));
+          v[i][2] = __ldg(addr_off(xb, q1.z));
+          v[i][3] = __ldg(addr_off(xb, q1.w));
         }
         if (h == 1 && more) params((k + 1) & 1, ndy, ndx, nmk);
-        float acc[2][8];
+        uint4 res[2];
+        if (DT == F16) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+          for (int i = 0; i < 2; ++i) res[i] = blend_h2(v[i], wgt[i]);
+        } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+          for (int i = 0; i < 2; ++i) {
+            float acc[8];
 #pragma unroll
-          for (int cnr = 0; cnr < 4; ++cnr) fma_16x8<DT>(acc[i], v[i][cnr], wgt[i][cnr]);
+            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+            for (int cnr = 0; cnr < 4; ++cnr) fma_16x8<DT>(acc, v[i][cnr], __uint_as_float(wgt[i][cnr]));
+            res[i] = make_uint4(pack2<DT>(acc[0], acc[1]), pack2<DT>(acc[2], acc[3]), pack2<DT>(acc[4], acc[5]), pack2<DT>(acc[6], acc[7]));
+          }
         }
         if (h == 0) ptx::mbar_wait_backoff(&empty[q], (uint32_t)((k & 1) ^ 1));
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int r = grp + 32 * (2 * h + i);
-          ptx::sts128(sa + r * 128 + ((l8 ^ (r & 7)) << 4),
-                      make_uint4(pack2<DT>(acc[i][0], acc[i][1]), pack2<DT>(acc[i][2], acc[i][3]),
-                                 pack2<DT>(acc[i][4], acc[i][5]), pack2<DT>(acc[i][6], acc[i][7])));
+          ptx::sts128(sa + r * 128 + ((l8 ^ (r & 7)) << 4), res[i]);
         }
       }
       ptx::fence_proxy_async_smem();
@@ -249,7 +280,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int tap = 0; tap < p.taps; ++tap) {
-          ptx::mbar_wait(&full[stage], phase);
+          ptx::mbar_wait_backoff(&full[stage], phase);      // the gather is the pace setter: do not burn issue slots spinning
           ptx::tc_fence_after();
           const uint64_t a_desc = ptx::make_smem_desc(ptx::smem_u32(sA + stage * DF_A_BYTES), 16, 1024, ptx::SW_128B);
           const uint64_t b_desc = ptx::make_smem_desc(ptx::smem_u32(sB + stage * DF_B_BYTES), 16, 1024, ptx::SW_128B);

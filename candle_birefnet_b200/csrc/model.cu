@@ -304,22 +304,17 @@ void Model::finalize() {
         // WindowAttention::new (src/swin.rs:143-152): bias[h,q,k] = table[index[q,k], h],
         // index[(i,j),(k,l)] = (i-k+11)*23 + (j-l+11)  (src/swin.rs:182-184)
         const HostTensor& tb = T(p + ".attn.relative_position_bias_table");
-        std::vector<float> b32((size_t)heads * 144 * 144);
-        std::vector<uint16_t> b16((size_t)heads * 144 * 152, 0), h16((size_t)heads * 144 * 152, 0);
+        std::vector<float> b32((size_t)heads * 144 * 144), b32p((size_t)heads * 144 * 148, 0.f);
         for (int h = 0; h < heads; ++h)
           for (int q = 0; q < 144; ++q)
             for (int k = 0; k < 144; ++k) {
               int idx = (q / 12 - k / 12 + 11) * 23 + (q % 12 - k % 12 + 11);
               float v = tb.data[(size_t)idx * heads + h];
               b32[((size_t)h * 144 + q) * 144 + k] = v;
-              b16[((size_t)h * 144 + q) * 152 + k] = f2bf(v);
-              h16[((size_t)h * 144 + q) * 152 + k] = f2h(v);
+              b32p[((size_t)h * 144 + q) * 148 + k] = v;
             }
         B.bias32 = upload(b32);
-        BRN_CUDA(cudaMalloc(&B.bias_bf16, b16.size() * 2)); allocs.push_back(B.bias_bf16);
-        BRN_CUDA(cudaMemcpy(B.bias_bf16, b16.data(), b16.size() * 2, cudaMemcpyHostToDevice));
-        BRN_CUDA(cudaMalloc(&B.bias_fp16, h16.size() * 2)); allocs.push_back(B.bias_fp16);
-        BRN_CUDA(cudaMemcpy(B.bias_fp16, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice));
+        B.bias32p = upload(b32p);
       }
       S.blocks.push_back(B);
     }
@@ -477,7 +472,7 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
       View qkv = make_view(arena.alloc((size_t)Tp * 3 * Ci * dsize(AD)), AD, 1, 1, (int)Tp, 3 * Ci);
       { GemmArgs g; g.x = xw; g.w = &bw.qkv; g.out = qkv; op_gemm(ctx, g); }
       View ao = make_view(xw.p, AD, 1, 1, (int)Tp, Ci);   // reuse the xw buffer (qkv GEMM has consumed it)
-      { AttnArgs a; a.qkv = qkv; a.bias32 = bw.bias32; a.bias16 = AD == F16 ? bw.bias_fp16 : bw.bias_bf16; a.n_windows = (int)(Tp / 144);
+      { AttnArgs a; a.qkv = qkv; a.bias32 = bw.bias32; a.bias32p = bw.bias32p; a.n_windows = (int)(Tp / 144);
         a.heads = heads; a.nwh = hp / 12; a.nww = wp / 12; a.shift = shift; a.out = ao; op_attention(ctx, a); }
       // proj + window_reverse + roll back + crop + residual (src/swin.rs:310,387-406)
       { GemmArgs g; g.x = ao; g.w = &bw.proj; g.out = xt; g.res = xt;

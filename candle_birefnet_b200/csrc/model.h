@@ -39,8 +39,7 @@ struct BlockW {
   float *n1g, *n1b, *n2g, *n2b;
   LayerW qkv, proj, fc1, fc2;
   float* bias32;           // [heads][144][144]
-  uint16_t* bias_bf16;     // [heads][144][152] bf16
-  uint16_t* bias_fp16;     // same, fp16
+  float* bias32p;          // [heads][144][148] (padded rows, tcgen05 attention kernel)
 };
 struct StageW {
   std::vector<BlockW> blocks;
