@@ -10,7 +10,8 @@ import re
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libbirefnet_b200.so"
+import os
+LIB_PATH = Path(os.environ["BRN_LIB_PATH"]) if os.environ.get("BRN_LIB_PATH") else HERE / "libbirefnet_b200.so"   # A/B builds
 HEADER = HERE.parent / "include" / "birefnet_b200.h"
 
 OK = 0

@@ -33,6 +33,23 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, defines: list[str]) -> Path:
+    """A/B experiment build: libbirefnet_b200_<name>.so with extra -D flags (select it with BRN_LIB_PATH)."""
+    out = HERE / f"libbirefnet_b200_{name}.so"
+    bdir = HERE / "build" / name
+    bdir.mkdir(parents=True, exist_ok=True)
+    procs, objs = [], []
+    for s in SOURCES:
+        o = bdir / (s + ".o")
+        procs.append(subprocess.Popen([_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(CSRC / s), "-o", str(o)]))
+        objs.append(str(o))
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("nvcc compilation failed")
+    subprocess.run([_nvcc(), "-shared", "-o", str(out), *objs, "-lcudart"], check=True)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     stamp_file = HERE / "build" / "stamp"
     stamp = _stamp()

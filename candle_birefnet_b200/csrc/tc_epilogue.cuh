@@ -129,6 +129,10 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
   for (int it = 0; it < 4; ++it) orow_b[it] = __shfl_sync(0xffffffffu, orow, it * 8 + (lane >> 2));
   const uint32_t my_row = stage + lane * 64;
   const int sw_a = (lane >> 1) & 3;
+  // phase-B row base pointers (byte address of column n0 of each of this lane's 4 rows), once per tile
+  char* orow_p[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) orow_p[it] = (char*)p.out + (orow_b[it] * p.ldo + n0) * ESZ;
 
   // residual prefetch: slot (granule & 1) holds the residual of that granule
   uint4 rq0[4], rq1[4];
@@ -234,7 +238,7 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
     for (int it = 0; it < 4; ++it) {
       const long long ro = orow_b[it];
       if (ro < 0 || nleft <= 0) continue;
-      char* op = (char*)p.out + (ro * p.ldo + col) * ESZ;
+      char* op = orow_p[it] + (c + kb * PER) * ESZ;
       if (p.vec && nleft >= PER) {
         *reinterpret_cast<uint4*>(op) = val[it];
       } else if (O32) {

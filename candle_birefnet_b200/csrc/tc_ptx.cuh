@@ -49,14 +49,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint parks the thread in hardware until the phase completes or the hint expires,
+// instead of re-issuing SYNCS + BRA every ~12 cycles: the polling of the TMA / MMA warps took 20 % of the issue slots
+// of the epilogue-bound GEMMs (ncu, r01), and polling epilogue warps burn power the tensor pipe could use.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef BRN_POLL_WAIT
   while (!mbar_try_wait(bar, parity)) {
   }
+  return;
+#endif
+  uint32_t ok = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+  } while (!ok);
 }
-
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {   // long waits: do not burn issue slots
-  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
-}
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 
 // explicit shared-space accesses (32-bit shared addresses): generic LD/ST through a pointer whose provenance the
 // compiler lost costs an address-space check and the long-scoreboard path
