@@ -137,9 +137,10 @@ def run_reference(args):
         "impl": "reference", "metric": "images/s BiRefNet Swin-L @1024^2", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": nsteps, "warmup": warm, "ms_per_step": med * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BiRefNet Swin-L forward_logits {H}x{W}, reference CPU path (PyTorch-CPU restatement of "
-                               "candle's CPU forward; candle itself cannot be built here: no Rust toolchain)",
-                   "sample": "1 image per step", "deform_mode": "cpu_fallback"},
+        "config": {"workload": f"BiRefNet swin_l forward_logits {H}x{W}, batch 16 per GPU (BASELINE.json configs[2])",
+                   "implementation": "reference CPU path: PyTorch-CPU restatement of candle's CPU forward (candle itself "
+                                     "cannot be built here: no Rust toolchain)",
+                   "sample": "1 image per step (1/16 of a batch)", "deform_mode": "cpu_fallback"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"1 image {H}x{W} per step, {nsteps} timed step(s)"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -217,45 +218,45 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """(device ms, host wall ms) of `steps` calls, both max over ranks; barrier + synchronize on both sides, the
+        host clock runs strictly inside the barriers."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
         e0.record(stream)
         for i in range(steps):
             fn(i)
         e1.record(stream)
         torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - w0) * 1e3
         ms = e0.elapsed_time(e1)
         if dist:
-            t = torch.tensor([ms], device="cuda")
+            t = torch.tensor([ms, wall_ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            ms, wall_ms = float(t[0].item()), float(t[1].item())
         barrier()
-        return ms
+        return ms, wall_ms
 
-    for i in range(warmup):
+    # every rotating input buffer is seen twice before timing: the second sighting of a (buffers, shape) key is where
+    # the library captures its CUDA graph; capture must not land inside the timed region
+    for i in range(max(warmup, 2 * nrot)):
         step_dev(i)
     torch.cuda.synchronize()
     model.reset_launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total = timed(step_dev, args.steps)
+    ms_total, _ = timed(step_dev, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = model.launch_count()
     value = world * B * args.steps / (ms_total / 1e3)
 
     # ---- e2e through the C ABI with host buffers ----
     step_e2e(0)
-    wall0 = time.time()
-    ms_e2e = timed(step_e2e, args.steps)
-    wall_e2e = time.time() - wall0
-    ms_e2e = max(ms_e2e, 0.0)
-    # host-pointer calls synchronise inside the call; wall clock is the honest end-to-end figure
-    e2e_s = wall_e2e
-    if dist:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    step_e2e(1)                            # second sighting of the staging buffers: CUDA-graph capture happens here
+    # host-pointer calls synchronise inside the call; the host wall clock (max over ranks) is the honest figure
+    ms_e2e_dev, ms_e2e_wall = timed(step_e2e, args.steps)
+    e2e_s = max(ms_e2e_dev, ms_e2e_wall) / 1e3
     e2e_value = world * B * args.steps / e2e_s
 
     # ---- roofline of the dominant kernel class, live CUDA events around every launch (untimed step) ----

@@ -56,6 +56,7 @@ struct AttnP {
   int dt;                        // operand / output element type: BF16 or F16
   int n_windows, heads, C;
   int nwh, nww, shift;
+  int split_win, nwh2, nww2;     // windows >= split_win (if > 0) belong to a second grid (merged half-resolution pass)
   uint16_t* out; int ldo;
 };
 
@@ -263,8 +264,10 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       const int par = i & 1, win = w_first + i * w_step;
       // analytic shift mask (src/swin.rs:603-655): only the last window row / column mixes regions.  This thread's
       // keys all have (ki >= 6) == half; kj >= 6 depends on the key column.  Interior windows take the mask-free path.
-      const int wl = win % nw, wi = wl / p.nww, wj = wl - wi * p.nww;
-      const bool last_r = p.shift > 0 && wi == p.nwh - 1, last_c = p.shift > 0 && wj == p.nww - 1;
+      int g_nwh = p.nwh, g_nww = p.nww, g_nw = nw, g_win = win;
+      if (p.split_win > 0 && win >= p.split_win) { g_nwh = p.nwh2; g_nww = p.nww2; g_nw = p.nwh2 * p.nww2; g_win = win - p.split_win; }
+      const int wl = g_win % g_nw, wi = wl / g_nww, wj = wl - wi * g_nww;
+      const bool last_r = p.shift > 0 && wi == g_nwh - 1, last_c = p.shift > 0 && wj == g_nww - 1;
       const bool rmask = last_r && ((half != 0) != (qi >= 6));
       float mk[2];   // index = (kj >= 6)
       mk[0] = (rmask || (last_c && (qj >= 6))) ? -100.0f : 0.0f;
@@ -349,6 +352,7 @@ void tc_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   BRN_CHECK(a.bias32p != nullptr, 1, "tc_attention: padded fp32 bias missing");
   p.bias32p = a.bias32p; p.dt = a.qkv.dt; p.n_windows = a.n_windows; p.heads = a.heads; p.C = a.heads * 32;
   p.nwh = a.nwh; p.nww = a.nww; p.shift = a.shift;
+  p.split_win = a.split_win; p.nwh2 = a.nwh2; p.nww2 = a.nww2;
   p.out = (uint16_t*)a.out.p; p.ldo = a.out.ld;
   const uint64_t rows = (uint64_t)a.n_windows * 144;
   uint64_t dims[2] = {(uint64_t)3 * p.C, rows};

@@ -74,9 +74,15 @@ struct LayerW {
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_2SIGMOID_TAIL = 3 };
 
 // window-reverse row map of the proj GEMM epilogue (src/swin.rs:387-401): window-ordered padded row -> token row
+// Two segments: rows [0, split) use geometry (h, w, hp, wp) and map to token rows [0, ...); rows [split, ...) belong
+// to a second token grid (the half-resolution backbone pass runs merged with the full-resolution one: same weights,
+// token matrices concatenated along M) with geometry (h2, w2, hp2, wp2), its tokens starting at row tok2.
 struct RowMap {
   int enabled = 0;
   int h = 0, w = 0, hp = 0, wp = 0, shift = 0;
+  long long split = 0;           // 0: single segment
+  int h2 = 0, w2 = 0, hp2 = 0, wp2 = 0;
+  long long tok2 = 0;
 };
 
 // One implicit-GEMM problem: out[m, n] = act(sum_k A[m,k] W[n,k] + bias) (+ res[m,n]).
@@ -117,6 +123,8 @@ struct AttnArgs {
   int heads = 0;
   int nwh = 0, nww = 0;   // windows per image along h / w
   int shift = 0;          // 0: no mask at all (src/swin.rs:383)
+  int split_win = 0;      // > 0: windows [split_win, n_windows) belong to a second grid with nwh2 x nww2 windows per image
+  int nwh2 = 0, nww2 = 0;
   View out;               // [rows, C]
 };
 

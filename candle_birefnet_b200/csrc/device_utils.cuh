@@ -25,6 +25,14 @@ __host__ __device__ __forceinline__ long long window_row_to_token(long long m, i
   return (b * h + r) * (long long)w + c;
 }
 
+__host__ __device__ __forceinline__ long long rowmap_token(const RowMap& rm, long long m) {
+  if (rm.split > 0 && m >= rm.split) {
+    const long long t = window_row_to_token(m - rm.split, rm.h2, rm.w2, rm.hp2, rm.wp2, rm.shift);
+    return t < 0 ? t : t + rm.tok2;
+  }
+  return window_row_to_token(m, rm.h, rm.w, rm.hp, rm.wp, rm.shift);
+}
+
 // element load / store by runtime dtype tag (F32 / BF16 / F16)
 __device__ __forceinline__ float ld_elem(const void* p, int dt, long long i) {
   if (dt == F32) return ((const float*)p)[i];

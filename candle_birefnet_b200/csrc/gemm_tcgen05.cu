@@ -153,7 +153,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int y = (r / p.tiles_x) * TH + (row >> p.tw_log2), x = (r % p.tiles_x) * TW + (row & (TW - 1));
       const bool valid = m_tile < p.m_tiles && y < p.H && x < p.W;
       long long orow = valid ? ((long long)b * p.H + y) * p.W + x : -1;
-      if (valid && p.rm.enabled) orow = window_row_to_token(orow, p.rm.h, p.rm.w, p.rm.hp, p.rm.wp, p.rm.shift);
+      if (valid && p.rm.enabled) orow = rowmap_token(p.rm, orow);
       const int n0 = n_tile * p.BN;
       const int nch = min(p.BN, p.epi.N - n0 + 15) >> 4;     // 16-column chunks of this tile that hold real columns
       const int gsz = o32 ? 1 : 2;                           // 16-bit output: keep the split on 32-column granules

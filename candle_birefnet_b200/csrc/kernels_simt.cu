@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtGemmP p) {
     if (m >= p.M) continue;
     long long orow = m;
     if (p.rm.enabled) {
-      orow = window_row_to_token(m, p.rm.h, p.rm.w, p.rm.hp, p.rm.wp, p.rm.shift);
+      orow = rowmap_token(p.rm, m);
       if (orow < 0) continue;
     }
     int b = p.bias_bstride ? (int)(m / ((long long)p.H * p.W)) : 0;
@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(160) simt_attn_kernel(SimtAttnP p) {
 void simt_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   if (ctx.launches) ++*ctx.launches;
   if (ctx.dry) return;
+  BRN_CHECK(a.split_win == 0, 7, "simt_attention: merged two-grid passes are a tensor-core-path feature");
   SimtAttnP p{};
   p.qkv = a.qkv.p; p.dt = a.qkv.dt; p.ldq = a.qkv.ld; p.C = a.heads * 32;
   p.bias = a.bias32; p.heads = a.heads; p.nwh = a.nwh; p.nww = a.nww; p.shift = a.shift;

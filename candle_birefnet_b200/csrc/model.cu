@@ -442,65 +442,101 @@ void Model::prof_end(LaunchCtx& ctx) {
 }
 
 // SwinTransformer::forward (src/swin.rs:768-797).  feats[i]: destination NHWC views (dtype = activation dtype).
-void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, View feats[4]) {
+// Optional second input (img2 at H2 x W2, features to feats2): BiRefNet runs the SAME backbone on the image and on its
+// half-resolution copy (src/birefnet.rs:416-426).  On the tensor-core path both token grids are concatenated along M,
+// so every row-wise op (qkv / proj / fc1 / fc2 GEMMs, norm2, window attention) is ONE launch over 1.25x the rows
+// instead of two launches of which the small one fills 2.6 waves of the GPU; only the ops that see the 2-D geometry
+// (window gather, patch merging, stage norms into the concat buffers) run once per grid.  Row results do not depend on
+// the M tiling, so the outputs are bit-identical to two separate passes.
+void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, View feats[4], const float* img2, int H2,
+                         int W2, View* feats2) {
   const int AD = act_dtype();
   const size_t m0 = arena.mark();
-  int h = H / 4, w = W / 4;
+  const int nseg = img2 ? 2 : 1;
+  const float* imgs[2] = {img, img2};
+  int h[2] = {H / 4, img2 ? H2 / 4 : 0}, w[2] = {W / 4, img2 ? W2 / 4 : 0};
+  auto rows_of = [&](const int* hh, const int* ww, long long* r) { r[0] = (long long)B * hh[0] * ww[0]; r[1] = nseg > 1 ? (long long)B * hh[1] * ww[1] : 0; };
+  long long T[2]; rows_of(h, w, T);
   // PatchEmbed (src/swin.rs:692-714): conv 4x4/4 as a [T,48]x[48,E] GEMM, then LN over C
-  View a0 = make_view(arena.alloc((size_t)B * h * w * 48 * dsize(AD)), AD, 1, 1, B * h * w, 48);
-  glue_patch_im2col(ctx, img, B, H, W, 4, a0);
-  View x = make_view(arena.alloc((size_t)B * h * w * C(0) * 4), F32, B, h, w, C(0));
+  const long long Tt0 = T[0] + T[1];
+  View a0 = make_view(arena.alloc((size_t)Tt0 * 48 * dsize(AD)), AD, 1, 1, (int)Tt0, 48);
+  for (int s = 0; s < nseg; ++s) {
+    View seg = make_view((char*)a0.p + (size_t)(s ? T[0] : 0) * 48 * dsize(AD), AD, 1, 1, (int)T[s], 48);
+    glue_patch_im2col(ctx, imgs[s], B, s ? H2 : H, s ? W2 : W, 4, seg);
+  }
+  float* xbuf = (float*)arena.alloc((size_t)Tt0 * C(0) * 4);
   {
-    GemmArgs g; g.x = a0; g.w = &patch_embed; g.out = make_view(x.p, F32, 1, 1, B * h * w, C(0));
+    GemmArgs g; g.x = a0; g.w = &patch_embed; g.out = make_view(xbuf, F32, 1, 1, (int)Tt0, C(0));
     op_gemm(ctx, g);
     LnArgs l; l.x = g.out; l.gamma = pe_g; l.beta = pe_b; l.out = g.out; l.mode = LN_PLAIN;
     glue_layernorm(ctx, l);
   }
   for (int i = 0; i < 4; ++i) {
     const int Ci = C(i), heads = cfg.num_heads[i];
-    const int hp = (h + 11) / 12 * 12, wp = (w + 11) / 12 * 12;
-    const long long T = (long long)B * h * w, Tp = (long long)B * hp * wp;
-    View xt = make_view(x.p, F32, 1, 1, (int)T, Ci);   // token-matrix view of the residual stream
+    int hp[2], wp[2]; long long Tp[2] = {0, 0};
+    for (int s = 0; s < nseg; ++s) { hp[s] = (h[s] + 11) / 12 * 12; wp[s] = (w[s] + 11) / 12 * 12; Tp[s] = (long long)B * hp[s] * wp[s]; }
+    rows_of(h, w, T);
+    const long long Tt = T[0] + T[1], Tpt = Tp[0] + Tp[1];
+    BRN_CHECK(Tpt < (1ll << 31), 5, "too many tokens for one pass: lower micro_batch");
+    View xt = make_view(xbuf, F32, 1, 1, (int)Tt, Ci);          // token-matrix view of the residual stream (both grids)
+    auto grid_view = [&](int s) { return make_view(xbuf + (size_t)(s ? T[0] : 0) * Ci, F32, B, h[s], w[s], Ci); };
     for (size_t j = 0; j < stages[i].blocks.size(); ++j) {
       const BlockW& bw = stages[i].blocks[j];
       const int shift = (j % 2 == 0) ? 0 : 6;          // src/swin.rs:552
       const size_t mb = arena.mark();
-      // norm1 -> pad -> roll -> partition (src/swin.rs:355-380) in one gather kernel
-      View xw = make_view(arena.alloc((size_t)Tp * Ci * dsize(AD)), AD, 1, 1, (int)Tp, Ci);
-      { LnArgs l; l.x = x; l.gamma = bw.n1g; l.beta = bw.n1b; l.out = xw; l.mode = LN_WINDOW; l.hp = hp; l.wp = wp;
-        l.shift = shift; glue_layernorm(ctx, l); }
-      View qkv = make_view(arena.alloc((size_t)Tp * 3 * Ci * dsize(AD)), AD, 1, 1, (int)Tp, 3 * Ci);
+      // norm1 -> pad -> roll -> partition (src/swin.rs:355-380) in one gather kernel per grid
+      View xw = make_view(arena.alloc((size_t)Tpt * Ci * dsize(AD)), AD, 1, 1, (int)Tpt, Ci);
+      for (int s = 0; s < nseg; ++s) {
+        LnArgs l; l.x = grid_view(s); l.gamma = bw.n1g; l.beta = bw.n1b;
+        l.out = make_view((char*)xw.p + (size_t)(s ? Tp[0] : 0) * Ci * dsize(AD), AD, 1, 1, (int)Tp[s], Ci);
+        l.mode = LN_WINDOW; l.hp = hp[s]; l.wp = wp[s]; l.shift = shift;
+        glue_layernorm(ctx, l);
+      }
+      View qkv = make_view(arena.alloc((size_t)Tpt * 3 * Ci * dsize(AD)), AD, 1, 1, (int)Tpt, 3 * Ci);
       { GemmArgs g; g.x = xw; g.w = &bw.qkv; g.out = qkv; op_gemm(ctx, g); }
-      View ao = make_view(xw.p, AD, 1, 1, (int)Tp, Ci);   // reuse the xw buffer (qkv GEMM has consumed it)
-      { AttnArgs a; a.qkv = qkv; a.bias32 = bw.bias32; a.bias32p = bw.bias32p; a.n_windows = (int)(Tp / 144);
-        a.heads = heads; a.nwh = hp / 12; a.nww = wp / 12; a.shift = shift; a.out = ao; op_attention(ctx, a); }
+      View ao = make_view(xw.p, AD, 1, 1, (int)Tpt, Ci);   // reuse the xw buffer (qkv GEMM has consumed it)
+      { AttnArgs a; a.qkv = qkv; a.bias32 = bw.bias32; a.bias32p = bw.bias32p; a.n_windows = (int)(Tpt / 144);
+        a.heads = heads; a.nwh = hp[0] / 12; a.nww = wp[0] / 12; a.shift = shift; a.out = ao;
+        if (nseg > 1) { a.split_win = (int)(Tp[0] / 144); a.nwh2 = hp[1] / 12; a.nww2 = wp[1] / 12; }
+        op_attention(ctx, a); }
       // proj + window_reverse + roll back + crop + residual (src/swin.rs:310,387-406)
       { GemmArgs g; g.x = ao; g.w = &bw.proj; g.out = xt; g.res = xt;
-        g.rowmap.enabled = 1; g.rowmap.h = h; g.rowmap.w = w; g.rowmap.hp = hp; g.rowmap.wp = wp; g.rowmap.shift = shift;
+        g.rowmap.enabled = 1; g.rowmap.h = h[0]; g.rowmap.w = w[0]; g.rowmap.hp = hp[0]; g.rowmap.wp = wp[0]; g.rowmap.shift = shift;
+        if (nseg > 1) { g.rowmap.split = Tp[0]; g.rowmap.h2 = h[1]; g.rowmap.w2 = w[1]; g.rowmap.hp2 = hp[1]; g.rowmap.wp2 = wp[1];
+                        g.rowmap.tok2 = T[0]; }
         op_gemm(ctx, g); }
       // x + fc2(gelu(fc1(norm2(x))))  (src/swin.rs:407)
-      View xn = make_view(arena.alloc((size_t)T * Ci * dsize(AD)), AD, 1, 1, (int)T, Ci);
+      View xn = make_view(arena.alloc((size_t)Tt * Ci * dsize(AD)), AD, 1, 1, (int)Tt, Ci);
       { LnArgs l; l.x = xt; l.gamma = bw.n2g; l.beta = bw.n2b; l.out = xn; l.mode = LN_PLAIN; glue_layernorm(ctx, l); }
-      View hd = make_view(arena.alloc((size_t)T * cfg.mlp_ratio * Ci * dsize(AD)), AD, 1, 1, (int)T, cfg.mlp_ratio * Ci);
+      View hd = make_view(arena.alloc((size_t)Tt * cfg.mlp_ratio * Ci * dsize(AD)), AD, 1, 1, (int)Tt, cfg.mlp_ratio * Ci);
       { GemmArgs g; g.x = xn; g.w = &bw.fc1; g.act = ACT_GELU; g.out = hd; op_gemm(ctx, g); }
       { GemmArgs g; g.x = hd; g.w = &bw.fc2; g.out = xt; g.res = xt; op_gemm(ctx, g); }
       arena.release(mb);
     }
-    // norm{i} -> NCHW view (src/swin.rs:784-788): written straight into the caller's NHWC slice
-    { LnArgs l; l.x = xt; l.gamma = stages[i].ng; l.beta = stages[i].nb;
-      l.out = make_view(feats[i].p, feats[i].dt, 1, 1, (int)T, Ci, feats[i].ld); l.mode = LN_PLAIN;
-      glue_layernorm(ctx, l); }
+    // norm{i} -> NCHW view (src/swin.rs:784-788): written straight into the caller's NHWC slices
+    for (int s = 0; s < nseg; ++s) {
+      View* f = s ? feats2 : feats;
+      LnArgs l; l.x = make_view(xbuf + (size_t)(s ? T[0] : 0) * Ci, F32, 1, 1, (int)T[s], Ci); l.gamma = stages[i].ng; l.beta = stages[i].nb;
+      l.out = make_view(f[i].p, f[i].dt, 1, 1, (int)T[s], Ci, f[i].ld); l.mode = LN_PLAIN;
+      glue_layernorm(ctx, l);
+    }
     if (stages[i].has_down) {
-      // PatchMerging (src/swin.rs:491-527)
-      const int h2 = (h + 1) / 2, w2 = (w + 1) / 2;
-      const long long T2 = (long long)B * h2 * w2;
-      View xm = make_view(arena.alloc((size_t)T2 * 4 * Ci * dsize(AD)), AD, 1, 1, (int)T2, 4 * Ci);
-      { LnArgs l; l.x = x; l.gamma = stages[i].dng; l.beta = stages[i].dnb; l.out = xm; l.mode = LN_MERGE;
-        glue_layernorm(ctx, l); }
-      View xnew = make_view(arena.alloc((size_t)T2 * 2 * Ci * 4), F32, B, h2, w2, 2 * Ci);
-      { GemmArgs g; g.x = xm; g.w = &stages[i].red; g.out = make_view(xnew.p, F32, 1, 1, (int)T2, 2 * Ci);
+      // PatchMerging (src/swin.rs:491-527): 2x2 gather + LN per grid, one reduction GEMM
+      int h2[2], w2[2]; long long T2[2] = {0, 0};
+      for (int s = 0; s < nseg; ++s) { h2[s] = (h[s] + 1) / 2; w2[s] = (w[s] + 1) / 2; T2[s] = (long long)B * h2[s] * w2[s]; }
+      const long long T2t = T2[0] + T2[1];
+      View xm = make_view(arena.alloc((size_t)T2t * 4 * Ci * dsize(AD)), AD, 1, 1, (int)T2t, 4 * Ci);
+      for (int s = 0; s < nseg; ++s) {
+        LnArgs l; l.x = grid_view(s); l.gamma = stages[i].dng; l.beta = stages[i].dnb;
+        l.out = make_view((char*)xm.p + (size_t)(s ? T2[0] : 0) * 4 * Ci * dsize(AD), AD, 1, 1, (int)T2[s], 4 * Ci);
+        l.mode = LN_MERGE;
+        glue_layernorm(ctx, l);
+      }
+      float* xnew = (float*)arena.alloc((size_t)T2t * 2 * Ci * 4);
+      { GemmArgs g; g.x = xm; g.w = &stages[i].red; g.out = make_view(xnew, F32, 1, 1, (int)T2t, 2 * Ci);
         op_gemm(ctx, g); }
-      x = xnew; h = h2; w = w2;
+      xbuf = xnew;
+      for (int s = 0; s < nseg; ++s) { h[s] = h2[s]; w[s] = w2[s]; }
     }
   }
   arena.release(m0);
@@ -615,6 +651,8 @@ void Model::run_squeeze_decoder(LaunchCtx& ctx, const float* img, int B, int H, 
   prof_end(ctx);
 }
 
+static bool env_flag(const char* n) { const char* v = getenv(n); return v && v[0] && v[0] != '0'; }
+
 // BiRefNet::forward_logits (src/birefnet.rs:412-461)
 void Model::run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, float* out, bool apply_sigmoid) {
   const int AD = dec_dtype();
@@ -628,19 +666,28 @@ void Model::run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, f
   View X4cat = make_view(arena.alloc((size_t)B * hs[3] * ws[3] * c4 * dsize(AD)), AD, B, hs[3], ws[3], c4);
   const int off4 = lat(0) + lat(1) + lat(2);
   View feats[4] = {X[0].slice(0, C(0)), X[1].slice(0, C(1)), X[2].slice(0, C(2)), X4cat.slice(off4, C(3))};
-  prof_begin(ctx, "backbone_full");
-  run_backbone(ctx, img, B, H, W, feats);                                    // :416-420
-  prof_end(ctx);
+  const bool merged = cfg.precision != BRN_PREC_FP32 && !ctx.force_simt && !env_flag("BRN_SPLIT_BACKBONE");
   {
-    prof_begin(ctx, "backbone_half");
     const size_t m1 = arena.mark();
     float* half = (float*)arena.alloc((size_t)B * 3 * (H / 2) * (W / 2) * 4);
-    glue_resize_nchw(ctx, img, B, 3, H, W, half, H / 2, W / 2);              // :425
     View fh[4];
     for (int i = 0; i < 4; ++i)
       fh[i] = make_view(arena.alloc((size_t)B * (hs[i] / 2) * (ws[i] / 2) * C(i) * dsize(AD)), AD, B, hs[i] / 2,
                         ws[i] / 2, C(i));
-    run_backbone(ctx, half, B, H / 2, W / 2, fh);                            // :426
+    if (merged) {
+      prof_begin(ctx, "backbone_full+half");
+      glue_resize_nchw(ctx, img, B, 3, H, W, half, H / 2, W / 2);              // :425
+      run_backbone(ctx, img, B, H, W, feats, half, H / 2, W / 2, fh);          // :416-420 and :426 in one pass
+      prof_end(ctx);
+      prof_begin(ctx, "half_upsample");
+    } else {
+      prof_begin(ctx, "backbone_full");
+      run_backbone(ctx, img, B, H, W, feats);                                  // :416-420
+      prof_end(ctx);
+      prof_begin(ctx, "backbone_half");
+      glue_resize_nchw(ctx, img, B, 3, H, W, half, H / 2, W / 2);              // :425
+      run_backbone(ctx, half, B, H / 2, W / 2, fh);                            // :426
+    }
     View dst[4] = {X[0].slice(C(0), C(0)), X[1].slice(C(1), C(1)), X[2].slice(C(2), C(2)), X4cat.slice(off4 + C(3), C(3))};
     for (int i = 0; i < 4; ++i) glue_resize_nhwc(ctx, fh[i], dst[i]);        // :435-443
     arena.release(m1);
@@ -654,8 +701,6 @@ void Model::run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, f
   run_squeeze_decoder(ctx, img, B, H, W, X[0], X[1], X[2], X4cat, out, apply_sigmoid);
   arena.release(m0);
 }
-
-static bool env_flag(const char* n) { const char* v = getenv(n); return v && v[0] && v[0] != '0'; }
 
 void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out, bool out_dev, cudaStream_t s,
                     bool apply_sigmoid) {

@@ -146,7 +146,8 @@ struct Model {
 
  private:
   void run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, float* out, bool apply_sigmoid);
-  void run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, View feats[4]);
+  void run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, View feats[4], const float* img2 = nullptr,
+                    int H2 = 0, int W2 = 0, View* feats2 = nullptr);
   void run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out);
   void run_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, View X1, View X2, View X3, View D4in,
                    float* out, bool apply_sigmoid);
