@@ -95,6 +95,14 @@ __device__ __forceinline__ void tmem_wait_dep(uint32_t (&v)[32]) {
                : "memory");
 }
 
+// 16-byte global load that asks L2 to fetch the whole 256-byte neighbourhood on a miss: the fp32 residual is read in
+// 64-byte row segments (8 rows per instruction), and the next three granules of the same rows follow shortly after
+__device__ __forceinline__ uint4 ldg_l2_256(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 template <int ACT>
 __device__ __forceinline__ float epi_act(float f, int col, int act_from) {
   if (ACT == ACT_RELU) return fmaxf(f, 0.f);
@@ -146,12 +154,12 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
 #pragma unroll
       for (int it = 0; it < 4; ++it)
         if (orow_b[it] >= 0 && nl >= 4)
-          q[it] = *reinterpret_cast<const uint4*>((const float*)p.res + orow_b[it] * p.ldres + col);
+          q[it] = ldg_l2_256((const float*)p.res + orow_b[it] * p.ldres + col);
     } else if (rmode == 2) {
       const uint16_t* rp = (const uint16_t*)p.res + orow * p.ldres + n0 + c;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (orow >= 0 && 8 * k < c1 - c && n0 + c + 8 * k < p.N) q[k] = *reinterpret_cast<const uint4*>(rp + 8 * k);
+        if (orow >= 0 && 8 * k < c1 - c && n0 + c + 8 * k < p.N) q[k] = ldg_l2_256(rp + 8 * k);
     }
   };
 
