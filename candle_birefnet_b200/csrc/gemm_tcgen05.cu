@@ -25,7 +25,10 @@
 namespace brn {
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;
-constexpr int TC_EPI_WARPS = 8;                               // two per TMEM lane quadrant (contiguous column parts; 12 warps measured slower)
+#ifndef BRN_EPI_WARPS
+#define BRN_EPI_WARPS 8
+#endif
+constexpr int TC_EPI_WARPS = BRN_EPI_WARPS;                               // two per TMEM lane quadrant (contiguous column parts; 12 warps measured slower)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;            // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 constexpr int TC_B_BYTES = 256 * TC_BK * 2;     // 32 KB (BN <= 256)
