@@ -317,11 +317,13 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
 #pragma unroll
       for (int g = 0; g < 9; ++g) {
         uint32_t packed[4];
+        {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float p0 = ex2(fmaf(sc[g * 8 + 2 * t], LOG2E, -moff)), p1 = ex2(fmaf(sc[g * 8 + 2 * t + 1], LOG2E, -moff));
-          sum += p0 + p1;
-          packed[t] = at_pack<DT>(p0, p1);
+          for (int t = 0; t < 4; ++t) {
+            const float p0 = ex2(fmaf(sc[g * 8 + 2 * t], LOG2E, -moff)), p1 = ex2(fmaf(sc[g * 8 + 2 * t + 1], LOG2E, -moff));
+            sum += p0 + p1;
+            packed[t] = at_pack<DT>(p0, p1);
+          }
         }
         if (row_ok) {
           // keys [8*G, 8*G+8), G = 9*half + g: K step G/2, 16-byte chunk (G&1) of the row's 32 B, XOR row bit 2

@@ -477,6 +477,85 @@ void glue_gate(const LaunchCtx& ctx, View p, View g16, const float* w16, float b
   BRN_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------
+// 1x1 modulated deformable conv = per-pixel bilinear resample with a learned offset, times the modulator, followed by
+// an ordinary 1x1 conv (src/deform_conv.rs:101-215 with k = 1).  With a single tap the gather -> MMA pipeline of
+// tc_deform_kernel has nothing to overlap with (its 4 epilogue warps become the pace setter), so the sampling runs
+// here (8 lanes x 16 bytes per pixel, same arithmetic as the fused kernel) and the contraction goes to tc_gemm.
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(256) deform_sample_k1_kernel(const uint16_t* __restrict__ x, int ldx, int B, int H, int W,
+                                                               const float* __restrict__ om, int ldom, int om_tiled,
+                                                               uint16_t* out, int ldo, long long total) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int l8 = (int)(i & 7); const long long px = i >> 3;
+  const int xx = (int)(px % W); const long long t = px / W; const int y = (int)(t % H); const long long b = t / H;
+  float dy, dx, mk;
+  if (om_tiled) {
+    const int tiles_x = (W + 15) / 16, tiles_y = (H + 7) / 8;
+    const long long tile = (b * tiles_y + (y >> 3)) * tiles_x + (xx >> 4);
+    const float* o = om + tile * 3 * 128 + ((y & 7) * 16 + (xx & 15));
+    dy = __ldg(o); dx = __ldg(o + 128); mk = __ldg(o + 256);
+  } else {
+    const float* o = om + px * ldom;
+    dy = __ldg(o); dx = __ldg(o + 1); mk = __ldg(o + 2);
+  }
+  const float py = (float)y + dy, pxf = (float)xx + dx;
+  const bool inb = py > -1.f && py < (float)H && pxf > -1.f && pxf < (float)W;
+  const float fy = floorf(py), fx = floorf(pxf);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const float ly = py - fy, lx = pxf - fx;
+  const float m0 = inb ? mk : 0.f;
+  const float wy0 = (y0 >= 0 && y0 <= H - 1) ? (1.f - ly) * m0 : 0.f, wy1 = (y0 + 1 >= 0 && y0 + 1 <= H - 1) ? ly * m0 : 0.f;
+  const float wx0 = (x0 >= 0) ? 1.f - lx : 0.f, wx1 = (x0 + 1 <= W - 1) ? lx : 0.f;
+  const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+  const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+  const uint16_t* xb = x + b * H * W * ldx + l8 * 8;
+  const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)yc0 * W + xc0) * ldx));
+  const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)yc0 * W + xc1) * ldx));
+  const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)yc1 * W + xc0) * ldx));
+  const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)yc1 * W + xc1) * ldx));
+  const float w[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
+  const uint4* v[4] = {&v00, &v01, &v10, &v11};
+  uint4 r;
+  uint32_t* ro = reinterpret_cast<uint32_t*>(&r);
+  if (DT == F16) {      // same packed half2 blend as tc_deform_kernel (HMUL2 + 3 HFMA2 per channel pair)
+    __half2 wh[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) wh[c] = __float2half2_rn(w[c]);
+#pragma unroll
+    for (int tt = 0; tt < 4; ++tt) {
+      __half2 a = __hmul2(*reinterpret_cast<const __half2*>(&reinterpret_cast<const uint32_t*>(v[0])[tt]), wh[0]);
+#pragma unroll
+      for (int c = 1; c < 4; ++c) a = __hfma2(*reinterpret_cast<const __half2*>(&reinterpret_cast<const uint32_t*>(v[c])[tt]), wh[c], a);
+      ro[tt] = *reinterpret_cast<uint32_t*>(&a);
+    }
+  } else {
+#pragma unroll
+    for (int tt = 0; tt < 4; ++tt) {
+      float ax = 0.f, ay = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { const float2 f = up16(reinterpret_cast<const uint32_t*>(v[c])[tt], DT); ax = fmaf(w[c], f.x, ax); ay = fmaf(w[c], f.y, ay); }
+      ro[tt] = pk16(ax, ay, DT);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + px * ldo + l8 * 8) = r;
+}
+
+void glue_deform_sample_k1(const LaunchCtx& ctx, View x, View om, int om_tiled, View out) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  BRN_CHECK(x.C == 64 && x.dt != F32 && out.dt == x.dt && x.ld % 8 == 0 && out.ld % 8 == 0, 5, "deform_sample_k1: layout");
+  const long long total = x.rows() * 8;
+  if (x.dt == BF16)
+    deform_sample_k1_kernel<BF16><<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>((const uint16_t*)x.p, x.ld, x.B, x.H, x.W,
+        (const float*)om.p, om.ld, om_tiled, (uint16_t*)out.p, out.ld, total);
+  else
+    deform_sample_k1_kernel<F16><<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>((const uint16_t*)x.p, x.ld, x.B, x.H, x.W,
+        (const float*)om.p, om.ld, om_tiled, (uint16_t*)out.p, out.ld, total);
+  BRN_CUDA(cudaGetLastError());
+}
+
 // out[row] = sum_c w[c] * p[row, c]   (the p1 half of conv_out1)
 __global__ void __launch_bounds__(256) dot1_kernel(const void* p, int pdt, int ldp, int C, const float* w, float* out,
                                                    long long rows) {

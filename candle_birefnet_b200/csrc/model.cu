@@ -22,7 +22,17 @@ void op_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   else simt_gemm(ctx, a);
 }
 void op_deform(const LaunchCtx& ctx, const DeformArgs& a) {
-  if (ctx.precision != BRN_PREC_FP32 && !ctx.force_simt && tc_deform_supported(a)) tc_deform(ctx, a);
+  const bool tc = ctx.precision != BRN_PREC_FP32 && !ctx.force_simt && tc_deform_supported(a);
+  if (tc && a.scratch && a.w->taps() == 1) {
+    // 1x1: sampling kernel + ordinary 1x1 implicit GEMM (same rounding points as the fused kernel)
+    View smp = make_view(a.scratch, a.x.dt, a.x.B, a.x.H, a.x.W, 64);
+    glue_deform_sample_k1(ctx, a.x, a.om, a.om_tiled, smp);
+    GemmArgs g; g.x = smp; g.w = a.w; g.bias = a.bias; g.act = a.act; g.out = a.out;
+    BRN_CHECK(tc_gemm_supported(g), 5, "deform k=1: tcgen05 GEMM unavailable");
+    tc_gemm(ctx, g);
+    return;
+  }
+  if (tc) tc_deform(ctx, a);
   else simt_deform(ctx, a);
 }
 void op_attention(const LaunchCtx& ctx, const AttnArgs& a) {
@@ -567,6 +577,7 @@ void Model::run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out) {
       g.out = om;
       if (tiled) { g.tile_w = 16; g.out_tiled = 1; d.om_tiled = 1; BRN_CHECK(tc_gemm_supported(g), 5, "om conv: tcgen05 path unavailable"); }
       d.om = om;
+      if (tiled && k == 1) d.scratch = arena.alloc(px * 64 * dsize(AD));
       op_gemm(ctx, g);
       if (tiled) BRN_CHECK(tc_deform_supported(d), 5, "deform: tcgen05 path unavailable");
       op_deform(ctx, d);
