@@ -59,6 +59,7 @@ def lib() -> C.CDLL:
     L.brn_model_set_tensor.argtypes = [vp, C.c_char_p, vp, C.c_int, C.POINTER(i64), C.c_int]
     L.brn_model_num_tensors.argtypes = [vp]
     L.brn_model_tensor_info.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(i64), C.POINTER(i32)]
+    L.brn_model_load_safetensors.argtypes = [vp, C.c_char_p, C.POINTER(i32)]
     L.brn_model_finalize.argtypes = [vp]
     L.brn_model_set_precision.argtypes = [vp, C.c_int]
     L.brn_model_set_deform_mode.argtypes = [vp, C.c_int]

@@ -79,6 +79,15 @@ brn_status brn_model_tensor_info(const brn_model* m, int32_t i, const char** key
   });
 }
 
+brn_status brn_model_load_safetensors(brn_model* m, const char* path, int32_t* n_loaded) {
+  return guard([&] {
+    BRN_CHECK(m && path, 1, "null argument");
+    std::lock_guard<std::mutex> lk(m->impl.mu);
+    const int n = load_safetensors(m->impl, path);
+    if (n_loaded) *n_loaded = n;
+  });
+}
+
 brn_status brn_model_finalize(brn_model* m) {
   return guard([&] {
     BRN_CHECK(m, 1, "null model");

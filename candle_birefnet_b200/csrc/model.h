@@ -166,6 +166,9 @@ struct Model {
   LayerW make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w_oihw, const std::vector<float>* bias);
 };
 
+// safetensors_loader.cpp: sets every tensor of `path` that the schema knows; returns how many were set
+int load_safetensors(Model& m, const char* path);
+
 // generic dispatchers (precision + support -> tcgen05 or SIMT)
 void op_gemm(const LaunchCtx&, const GemmArgs&);
 void op_deform(const LaunchCtx&, const DeformArgs&);

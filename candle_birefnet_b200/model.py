@@ -89,8 +89,16 @@ class BiRefNet:
         check(L.brn_model_create(C.byref(c), device, C.byref(h)))
         m = BiRefNet(h, config, device)
         if isinstance(vb, str):
-            from safetensors.numpy import load_file
-            vb = load_file(vb)
+            # the library's own safetensors reader (brn_model_load_safetensors): no Python-side parsing
+            try:
+                n = C.c_int32(0)
+                check(L.brn_model_load_safetensors(h, vb.encode(), C.byref(n)))
+                check(L.brn_model_finalize(h))
+            except Exception:
+                L.brn_model_destroy(h)
+                m._h = None
+                raise
+            return m
         try:
             for key in m.tensor_keys():
                 if key not in vb:

@@ -94,6 +94,12 @@ BRN_API brn_status brn_model_create(const brn_config* cfg, int device, brn_model
 BRN_API brn_status brn_model_set_tensor(brn_model* m, const char* key, const void* data, int dtype,
                                 const int64_t* shape, int rank);
 
+/* Replaces `candle_core::safetensors::load(path)` + `VarBuilder::from_tensors` (examples/infer_image.rs:35-40): reads a
+ * .safetensors file (F32 / F16 / BF16 tensors) and sets every tensor the schema knows; like VarBuilder, tensors the
+ * model never asks for (e.g. `num_batches_tracked`, cached index buffers of the HF checkpoint) are ignored, and a
+ * tensor that is missing shows up at brn_model_finalize as BRN_ERR_MISSING_TENSOR.  *n_loaded = tensors set. */
+BRN_API brn_status brn_model_load_safetensors(brn_model* m, const char* path, int32_t* n_loaded);
+
 /* Number of tensors in the schema and the i-th key/shape (for loaders and tests). */
 BRN_API int32_t brn_model_num_tensors(const brn_model* m);
 BRN_API brn_status brn_model_tensor_info(const brn_model* m, int32_t index, const char** key, int64_t shape[4], int32_t* rank);

@@ -215,3 +215,48 @@ def test_full_size_properties_swin_l_1024():
     ref32 = m.forward_logits(x[1:2])
     m.close()
     check_logits(plain, ref32, "fp16")
+
+
+def test_safetensors_loader(mini_cfg, mini_weights_B, tmp_path):
+    """brn_model_load_safetensors == candle_core::safetensors::load + VarBuilder (examples/infer_image.rs:35-40): same
+    forward as the tensor-by-tensor path, extra tensors ignored, 16-bit tensors accepted, a missing one fails at finalize."""
+    from safetensors.numpy import save_file
+    cfgp = py_cfg(mini_cfg, "fp16", "deformable")
+    ref = cb.BiRefNet.new(cfgp, mini_weights_B)
+    x = make_input(1, 64, 96, seed=7)
+    want = ref.forward_logits(x)
+    ref.close()
+    w = {k: np.ascontiguousarray(v) for k, v in mini_weights_B.items()}
+    w["bb.layers.0.blocks.0.attn.relative_position_index"] = np.zeros((144, 144), np.int64)   # HF buffers: not in the schema
+    w["decoder.some_module.num_batches_tracked"] = np.zeros((), np.int64)
+    f1 = str(tmp_path / "mini.safetensors")
+    save_file(w, f1, metadata={"format": "pt"})
+    m = cb.BiRefNet.new(cfgp, f1)
+    assert np.array_equal(m.forward_logits(x), want)
+    m.close()
+    # fp16 storage of one tensor whose values are exactly representable: still bit-identical
+    w2 = dict(w)
+    k = "bb.patch_embed.norm.bias"
+    w2[k] = w[k].astype(np.float16)
+    w_ref = dict(mini_weights_B); w_ref[k] = w2[k].astype(np.float32)
+    r2 = cb.BiRefNet.new(cfgp, w_ref); want2 = r2.forward_logits(x); r2.close()
+    f2 = str(tmp_path / "mini_f16.safetensors")
+    save_file(w2, f2)
+    m2 = cb.BiRefNet.new(cfgp, f2)
+    assert np.array_equal(m2.forward_logits(x), want2)
+    m2.close()
+    # missing tensor -> BRN_ERR_MISSING_TENSOR at finalize; not a safetensors file -> BRN_ERR_SHAPE; no file -> BRN_ERR_INVALID
+    w3 = dict(w); w3.pop("bb.norm2.weight")
+    f3 = str(tmp_path / "missing.safetensors")
+    save_file(w3, f3)
+    with pytest.raises(cb.BrnError) as e:
+        cb.BiRefNet.new(cfgp, f3)
+    assert e.value.status == 3
+    f4 = tmp_path / "garbage.safetensors"
+    f4.write_bytes(b"\x00" * 64)
+    with pytest.raises(cb.BrnError) as e:
+        cb.BiRefNet.new(cfgp, str(f4))
+    assert e.value.status == 5
+    with pytest.raises(cb.BrnError) as e:
+        cb.BiRefNet.new(cfgp, str(tmp_path / "nope.safetensors"))
+    assert e.value.status == 1
