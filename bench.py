@@ -331,10 +331,10 @@ def main():
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "swin_l":
-        ips, cores, n, med = oracle_images_per_s(H, W, 1, 0, budget_s=60.0)
+        ips, cores, n, med = oracle_images_per_s(H, W, 5, 1, budget_s=45.0)
         cpu_base = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                    "sample": f"1 image {H}x{W} (1/{B} of a step), PyTorch-CPU restatement of the reference's CPU forward "
-                              f"(deform_mode=cpu_fallback), {n} run, {med:.1f} s"}
+                    "sample": f"{n} x 1 image {H}x{W} (each 1/{B} of a step) after 1 warm-up, median {med:.1f} s per image; "
+                              f"PyTorch-CPU restatement of the reference's CPU forward (deform_mode=cpu_fallback)"}
 
     if rank == 0:
         gflop = GFLOP_PER_IMAGE_1024 * (H * W) / (1024.0 * 1024.0)

@@ -123,9 +123,11 @@ constexpr int LNB_CHUNK_FLOATS = 4608;     // R * C <= 4608 floats = 18 KB per s
 constexpr int LNB_THREADS = 288;           // 8 consumer warps + 1 producer warp
 
 // NV float4 per lane, LPR lanes per row (32, or 16 for short rows: two rows per warp, no idle lanes at C = 192)
-template <int NV, int LPR>
+// ODT = output element type; EXACT: n / 4 == NV * LPR (no column predicates).
+template <int NV, int LPR, int ODT, bool EXACT>
 __global__ void __launch_bounds__(LNB_THREADS) ln_bulk_kernel(LnP p, int R, long long n_chunks) {
   constexpr int RPW = 32 / LPR;                                     // rows per warp pass
+  constexpr bool GREG = NV <= 6;                                    // gamma / beta of this lane's columns live in registers
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   float* ring = (float*)smem;                                      // [LNB_STAGES][R * C]
@@ -173,58 +175,92 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bulk_kernel(LnP p, int R, long
     }
   } else {
     // ===== consumers: row groups (RPW adjacent rows) go round-robin over the 8 warps across chunks =====
+    // The first version of this loop issued ~22 instructions per element (64-bit index math per store, run-time
+    // output-type switch, gamma / beta re-read per row, column predicates) and ran at 63 % issue-active / 52-64 % of
+    // DRAM peak (ncu, profiles/r01_kernel_notes.md): everything row- or lane-invariant is hoisted now.
     const int sub = lane / LPR, l = lane % LPR;
     const int gpc = (R + RPW - 1) / RPW;                            // row groups per chunk
+    const uint32_t ring_a = ptx::smem_u32(ring), sg_a = ptx::smem_u32(sg), sb_a = ptx::smem_u32(sb);
+    const float inv_n = 1.f / (float)n;
+    constexpr int OSZ = ODT == F32 ? 4 : 2;
+    float4 gr[GREG ? NV : 1], br[GREG ? NV : 1];
+    if (GREG) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int e4 = l + LPR * i;
+        gr[i] = br[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EXACT || e4 < n4) {
+          const uint4 g4 = ptx::lds128(sg_a + e4 * 16), b4 = ptx::lds128(sb_a + e4 * 16);
+          gr[i] = make_float4(__uint_as_float(g4.x), __uint_as_float(g4.y), __uint_as_float(g4.z), __uint_as_float(g4.w));
+          br[i] = make_float4(__uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z), __uint_as_float(b4.w));
+        }
+      }
+    }
     int stage = 0; uint32_t phase = 0;
     long long seq = 0;
     for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x, ++seq) {
       ptx::mbar_wait(&full[stage], phase);
-      const float* src = ring + stage * LNB_CHUNK_FLOATS;
+      const uint32_t src = ring_a + stage * (LNB_CHUNK_FLOATS * 4);
       for (int gj = (int)((8 + warp - (seq * gpc) % 8) % 8); gj < gpc; gj += 8) {
         const int j = gj * RPW + sub;
         const long long m = ch * R + j;
         const bool in_range = j < R && m < p.rows;
         const bool real = in_range && sflag[stage * 32 + j] != 0;
+        const uint32_t srow = src + (uint32_t)(j * n + 4 * l) * 4;
+        char* const orow = (char*)p.out + (m * p.ldo + 4 * l) * OSZ;
         float4 v[NV];
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          const int e4 = l + LPR * i;
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e4 < n4 && real) {
-            v[i] = *reinterpret_cast<const float4*>(src + j * n + 4 * e4);
+          if ((EXACT || l + LPR * i < n4) && real) {
+            const uint4 t = ptx::lds128(srow + i * (LPR * 16));
+            v[i] = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w));
             s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
           }
         }
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mean = s / n;
+        const float mean = s * inv_n;
         float q = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          if (l + LPR * i < n4) {
-            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-            q += (a * a + b * b) + (c * c + d * d);
+          if (EXACT || l + LPR * i < n4) {
+            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+            q = fmaf(v[i].x, v[i].x, q); q = fmaf(v[i].y, v[i].y, q); q = fmaf(v[i].z, v[i].z, q); q = fmaf(v[i].w, v[i].w, q);
           }
         }
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-        const float rstd = rsqrtf(q / n + 1e-5f);
+        const float rstd = rsqrtf(q * inv_n + 1e-5f);
         if (!in_range) continue;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          const int e4 = l + LPR * i;
-          if (e4 < n4) {
+          if (EXACT || l + LPR * i < n4) {
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);            // pad rows of LN_WINDOW are zeros AFTER the norm
             if (real) {
-              const float4 g = *reinterpret_cast<const float4*>(sg + 4 * e4);
-              const float4 bb = *reinterpret_cast<const float4*>(sb + 4 * e4);
-              o.x = (v[i].x - mean) * rstd * g.x + bb.x;
-              o.y = (v[i].y - mean) * rstd * g.y + bb.y;
-              o.z = (v[i].z - mean) * rstd * g.z + bb.z;
-              o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+              float4 g, bb;
+              if (GREG) { g = gr[i]; bb = br[i]; }
+              else {
+                const uint4 g4 = ptx::lds128(sg_a + (l + LPR * i) * 16), b4 = ptx::lds128(sb_a + (l + LPR * i) * 16);
+                g = make_float4(__uint_as_float(g4.x), __uint_as_float(g4.y), __uint_as_float(g4.z), __uint_as_float(g4.w));
+                bb = make_float4(__uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z), __uint_as_float(b4.w));
+              }
+              o.x = fmaf(v[i].x * rstd, g.x, bb.x);
+              o.y = fmaf(v[i].y * rstd, g.y, bb.y);
+              o.z = fmaf(v[i].z * rstd, g.z, bb.z);
+              o.w = fmaf(v[i].w * rstd, g.w, bb.w);
             }
-            ln_store4(p.out, p.odt, m * p.ldo + 4 * e4, o);
+            char* op = orow + i * (LPR * 4 * OSZ);
+            if (ODT == F32) {
+              *reinterpret_cast<float4*>(op) = o;
+            } else if (ODT == BF16) {
+              __nv_bfloat162 a = __floats2bfloat162_rn(o.x, o.y), b2 = __floats2bfloat162_rn(o.z, o.w);
+              *reinterpret_cast<uint2*>(op) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b2));
+            } else {
+              __half2 a = __floats2half2_rn(o.x, o.y), b2 = __floats2half2_rn(o.z, o.w);
+              *reinterpret_cast<uint2*>(op) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b2));
+            }
           }
         }
       }
@@ -303,18 +339,27 @@ void glue_layernorm(const LaunchCtx& ctx, const LnArgs& a) {
     if (a.mode == LN_WINDOW) { const int cands[6] = {24, 12, 6, 4, 3, 2}; int r = 1; for (int c : cands) if (c <= R) { r = c; break; } R = r; }
     const long long n_chunks = (p.rows + R - 1) / R;
     const int smem = LNB_STAGES * LNB_CHUNK_FLOATS * 4 + 2 * n * 4 + 2 * LNB_STAGES * 8 + LNB_STAGES * 32 * 4 + 128;
+#define LNB_LAUNCH(NV, LPR, ODT, EX)                                                                      \
+    do {                                                                                                  \
+      auto kern = ln_bulk_kernel<NV, LPR, ODT, EX>;                                                       \
+      BRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));            \
+      int occ = 1;                                                                                        \
+      BRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LNB_THREADS, smem));             \
+      const int grid = (int)std::min<long long>(n_chunks, (long long)device_sm_count() * std::max(occ, 1)); \
+      kern<<<grid, LNB_THREADS, smem, ctx.stream>>>(p, R, n_chunks);                                      \
+    } while (0)
 #define LNB_CASE(NV, LPR)                                                                                 \
     do {                                                                                                  \
-      BRN_CUDA(cudaFuncSetAttribute(ln_bulk_kernel<NV, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      int occ = 1;                                                                                        \
-      BRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bulk_kernel<NV, LPR>, LNB_THREADS, smem)); \
-      const int grid = (int)std::min<long long>(n_chunks, (long long)device_sm_count() * std::max(occ, 1)); \
-      ln_bulk_kernel<NV, LPR><<<grid, LNB_THREADS, smem, ctx.stream>>>(p, R, n_chunks);                    \
+      const bool ex = (n / 4) == NV * LPR;                                                                \
+      if (a.out.dt == F32) { if (ex) LNB_LAUNCH(NV, LPR, F32, true); else LNB_LAUNCH(NV, LPR, F32, false); } \
+      else if (a.out.dt == BF16) { if (ex) LNB_LAUNCH(NV, LPR, BF16, true); else LNB_LAUNCH(NV, LPR, BF16, false); } \
+      else { if (ex) LNB_LAUNCH(NV, LPR, F16, true); else LNB_LAUNCH(NV, LPR, F16, false); }                \
     } while (0)
     const int n4 = n / 4;
     if (n4 <= 16) LNB_CASE(1, 16); else if (n4 <= 32) LNB_CASE(2, 16); else if (n4 <= 48) LNB_CASE(3, 16);
     else if (nv <= 2) LNB_CASE(2, 32); else if (nv <= 3) LNB_CASE(3, 32); else if (nv <= 4) LNB_CASE(4, 32);
     else if (nv <= 6) LNB_CASE(6, 32); else if (nv <= 8) LNB_CASE(8, 32); else LNB_CASE(12, 32);
+#undef LNB_LAUNCH
 #undef LNB_CASE
     BRN_CUDA(cudaGetLastError());
     return;
