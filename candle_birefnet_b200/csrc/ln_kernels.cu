@@ -130,14 +130,14 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bulk_kernel(LnP p, int R, long
   constexpr bool GREG = NV <= 6;                                    // gamma / beta of this lane's columns live in registers
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-  float* ring = (float*)smem;                                      // [LNB_STAGES][R * C]
-  float* sg = ring + LNB_STAGES * LNB_CHUNK_FLOATS;                // gamma [C]
-  float* sb = sg + p.C;                                            // beta  [C]
-  uint64_t* full = (uint64_t*)(sb + p.C);
+  const int n = p.mode == LN_MERGE ? 4 * p.C : p.C, n4 = n >> 2;   // normalised row length
+  float* ring = (float*)smem;                                      // [LNB_STAGES][R * n]
+  float* sg = ring + LNB_STAGES * LNB_CHUNK_FLOATS;                // gamma [n]
+  float* sb = sg + n;                                              // beta  [n]
+  uint64_t* full = (uint64_t*)(sb + n);
   uint64_t* empty = full + LNB_STAGES;
   int* sflag = (int*)(empty + LNB_STAGES);                         // [LNB_STAGES][32]: 1 = real row, 0 = pad / past the end
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = p.C, n4 = n >> 2;
   if (threadIdx.x == 0) {
     for (int s = 0; s < LNB_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 8); }
     ptx::fence_barrier_init();
@@ -152,6 +152,30 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bulk_kernel(LnP p, int R, long
     int stage = 0; uint32_t phase = 0;
     for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
       const long long m = ch * R + lane;
+      if (p.mode == LN_MERGE) {
+        // row (b, i, j) of the merged grid <- [x(2i,2j) | x(2i+1,2j) | x(2i,2j+1) | x(2i+1,2j+1)] (src/swin.rs:505-515):
+        // four bulk copies of C floats per row (h and w are even here, so no part is padding)
+        const bool valid = lane < R && m < p.rows;
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        ptx::mbar_wait_backoff(&empty[stage], phase ^ 1);
+        sflag[stage * 32 + lane] = valid ? 1 : 0;
+        __syncwarp();
+        if (lane == 0) ptx::mbar_expect_tx(&full[stage], (uint32_t)__popc(vmask) * row_bytes);
+        __syncwarp();
+        if (valid) {
+          const int h2 = p.h >> 1, w2 = p.w >> 1, C = p.C;
+          const long long b = m / ((long long)h2 * w2);
+          const int r = (int)(m - b * (long long)h2 * w2);
+          const int i = r / w2, j = r - i * w2;
+#pragma unroll
+          for (int part = 0; part < 4; ++part) {
+            const long long srow = (b * p.h + 2 * i + (part & 1)) * (long long)p.w + 2 * j + (part >> 1);
+            ptx::bulk_load(ring + stage * LNB_CHUNK_FLOATS + lane * n + part * C, xs + srow * p.ldx, (uint32_t)C * 4, &full[stage]);
+          }
+        }
+        if (++stage == LNB_STAGES) { stage = 0; phase ^= 1; }
+        continue;
+      }
       long long tok = -1;
       if (lane < R && m < p.rows) tok = p.mode == LN_WINDOW ? window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift) : m;
       const long long prev = __shfl_up_sync(0xffffffffu, tok, 1);
@@ -333,7 +357,8 @@ void glue_layernorm(const LaunchCtx& ctx, const LnArgs& a) {
                    (((uintptr_t)a.out.p) & (4 * dsize(a.out.dt) - 1)) == 0 && (((uintptr_t)a.gamma | (uintptr_t)a.beta) & 15) == 0;
   const int nv = (n + 127) / 128;
   static const bool no_bulk = [] { const char* v = getenv("BRN_LN_BULK"); return v && v[0] == '0'; }();
-  if (vec && !no_bulk && a.mode != LN_MERGE && n <= LNB_CHUNK_FLOATS && nv <= 12 && a.x.p != nullptr &&
+  const bool merge_ok = a.mode != LN_MERGE || (a.x.H % 2 == 0 && a.x.W % 2 == 0 && a.x.p != a.out.p);
+  if (vec && !no_bulk && merge_ok && n <= LNB_CHUNK_FLOATS && nv <= 24 && a.x.p != nullptr &&
       !(a.x.p == a.out.p && a.mode == LN_WINDOW)) {
     int R = std::min(32, LNB_CHUNK_FLOATS / n);
     if (a.mode == LN_WINDOW) { const int cands[6] = {24, 12, 6, 4, 3, 2}; int r = 1; for (int c : cands) if (c <= R) { r = c; break; } R = r; }
@@ -358,7 +383,8 @@ void glue_layernorm(const LaunchCtx& ctx, const LnArgs& a) {
     const int n4 = n / 4;
     if (n4 <= 16) LNB_CASE(1, 16); else if (n4 <= 32) LNB_CASE(2, 16); else if (n4 <= 48) LNB_CASE(3, 16);
     else if (nv <= 2) LNB_CASE(2, 32); else if (nv <= 3) LNB_CASE(3, 32); else if (nv <= 4) LNB_CASE(4, 32);
-    else if (nv <= 6) LNB_CASE(6, 32); else if (nv <= 8) LNB_CASE(8, 32); else LNB_CASE(12, 32);
+    else if (nv <= 6) LNB_CASE(6, 32); else if (nv <= 8) LNB_CASE(8, 32); else if (nv <= 12) LNB_CASE(12, 32);
+    else if (nv <= 16) LNB_CASE(16, 32); else LNB_CASE(24, 32);
 #undef LNB_LAUNCH
 #undef LNB_CASE
     BRN_CUDA(cudaGetLastError());
