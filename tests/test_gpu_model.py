@@ -260,3 +260,52 @@ def test_safetensors_loader(mini_cfg, mini_weights_B, tmp_path):
     with pytest.raises(cb.BrnError) as e:
         cb.BiRefNet.new(cfgp, str(tmp_path / "nope.safetensors"))
     assert e.value.status == 1
+
+
+def test_hr_2048_swin_l():
+    """BASELINE.json configs[4] resolution (2048x2048, Swin-L): runs, finite, image-independent, and on weight-set A the
+    deformable path equals the plain-conv path within the north-star tolerance."""
+    cfg = R.Config.swin_l()
+    wnp = make_weights(cfg, seed=0, weight_set="A")
+    m = cb.BiRefNet.new(py_cfg(cfg, "fp16", "deformable"), wnp)
+    x = make_input(2, 2048, 2048, seed=31)
+    both = m.forward_logits(x)
+    assert both.shape == (2, 1, 2048, 2048) and np.isfinite(both).all()
+    one = m.forward_logits(x[:1])
+    assert np.array_equal(both[:1], one)
+    m.set_deform_mode("cpu_fallback")
+    plain = m.forward_logits(x[:1])
+    m.close()
+    ds = np.abs(sigmoid(plain) - sigmoid(one)).max()
+    assert ds <= 1e-2 and iou(sigmoid(plain), sigmoid(one)) >= 0.999, ds
+
+
+def test_call_order_and_concurrent_calls(mini_cfg, mini_weights_A):
+    """Error behaviour of the handle (candle's Result): forward before finalize is BRN_ERR_STATE; a handle is
+    thread-compatible -- concurrent calls are serialised by its mutex and give the single-threaded result."""
+    import ctypes as C
+    import threading
+    L = cb.lib()
+    c = cb._lib.BrnConfig()
+    L.brn_config_swin_l(C.byref(c))
+    h = C.c_void_p()
+    cb._lib.check(L.brn_model_create(C.byref(c), 0, C.byref(h)))
+    x = np.zeros((1, 3, 64, 64), np.float32)
+    o = np.zeros((1, 1, 64, 64), np.float32)
+    st = L.brn_forward_logits(h, x.ctypes.data_as(C.c_void_p), 1, 64, 64, 0, o.ctypes.data_as(C.c_void_p), 0, None)
+    assert st == 6 and b"finalize" in L.brn_last_error()
+    assert L.brn_model_finalize(h) == 3          # nothing was set: missing tensor
+    L.brn_model_destroy(h)
+
+    m = cb.BiRefNet.new(py_cfg(mini_cfg, "fp16", "deformable"), mini_weights_A)
+    xs = [make_input(1, 64, 96, seed=40 + i) for i in range(4)]
+    want = [m.forward_logits(v) for v in xs]
+    got = [None] * 4
+    def run(i):
+        for _ in range(3):
+            got[i] = m.forward_logits(xs[i])
+    ts = [threading.Thread(target=run, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    m.close()
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
