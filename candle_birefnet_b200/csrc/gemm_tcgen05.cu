@@ -51,7 +51,11 @@ struct TcGemmP {
 // half of the shared B (weight) tile and TMA-multicasts it into both CTAs' shared memory, so the L2 -> SMEM bytes per
 // 128x256x64 MMA block drop from 48 KB to 32 KB (the kernel is L2-bandwidth bound at 48 KB: ~42 B/clk/SM of L2 vs
 // 94 B/clk/SM needed to keep the tensor pipe busy).
-template <int CL>
+// EPI = epilogue variant compiled into this instance (one kernel per hot epilogue instead of a run-time switch over all
+// 18 variants inside one 27k-instruction kernel: per-variant register allocation, hot loop within the instruction cache).
+enum EpiKind { EK_GENERIC = 0, EK_NONE16, EK_RELU16, EK_GELU16, EK_NONE32, EK_SIG32_TILED, EK_RES32, EK_RES16 };
+
+template <int CL, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -173,10 +177,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      if (p.out_tiled) {
-        if (m_tile < p.m_tiles) epi_warp_tiled_dyn(p.epi, taddr, n0, c0, c1, m_tile, row, p.epi.bias ? sb : 0u);
+      const uint32_t sbb = p.epi.bias ? sb : 0u;
+      if (EPI == EK_NONE16) epi_warp<ACT_NONE, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
+      else if (EPI == EK_RELU16) epi_warp<ACT_RELU, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
+      else if (EPI == EK_GELU16) epi_warp<ACT_GELU, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
+      else if (EPI == EK_NONE32) epi_warp<ACT_NONE, true, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
+      else if (EPI == EK_RES32) epi_warp<ACT_NONE, true, 1>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
+      else if (EPI == EK_RES16) epi_warp<ACT_NONE, false, 2>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
+      else if (EPI == EK_SIG32_TILED) {
+        if (m_tile < p.m_tiles) epi_warp_tiled<ACT_2SIGMOID_TAIL>(p.epi, taddr, n0, c0, c1, m_tile, row, sbb);
+      } else if (p.out_tiled) {
+        if (m_tile < p.m_tiles) epi_warp_tiled_dyn(p.epi, taddr, n0, c0, c1, m_tile, row, sbb);
       } else {
-        epi_warp_dyn(p.epi, taddr, n0, c0, c1, orow, p.epi.bias ? sb : 0u, stage, lane);
+        epi_warp_dyn(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[acc]);
@@ -307,24 +320,37 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
                        w.N, w.taps(), w.Cin, p.BN, p.m_tiles * p.n_tiles, a.act, a.res.p ? 1 : 0, a.out.dt, CL);
   KScope ks(ctx, KC_GEMM_TC, 2.0 * rows * w.N * w.taps() * w.Cin,
             rows * a.x.C * 2 + rows * w.N * dsize(a.out.dt) + (double)w.N * w.taps() * w.cin_pad * 2, desc);
-  if (CL == 2) {
-    BRN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    const int items = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  // epilogue variant (the conditions mirror epi_warp_dyn's dispatch)
+  const bool o32 = a.out.dt == F32;
+  int ek = EK_GENERIC;
+  if (a.out_tiled) ek = (a.act == ACT_2SIGMOID_TAIL) ? EK_SIG32_TILED : EK_GENERIC;
+  else if (!a.res.p) {
+    if (!o32) ek = a.act == ACT_NONE ? EK_NONE16 : a.act == ACT_RELU ? EK_RELU16 : a.act == ACT_GELU ? EK_GELU16 : EK_GENERIC;
+    else ek = a.act == ACT_NONE ? EK_NONE32 : EK_GENERIC;
+  } else if (a.act == ACT_NONE && o32 && a.res.dt == F32 && p.epi.vec) ek = EK_RES32;
+  else if (a.act == ACT_NONE && !o32 && a.res.dt == a.out.dt && p.epi.vec && w.N % 8 == 0) ek = EK_RES16;
+
+  auto launch = [&](auto kern) {
+    BRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    const int items = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * std::min(items, sms / 2));
+    cfg.gridDim = dim3(CL * std::min(items, sms / CL));
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = TC_SMEM;
     cfg.stream = ctx.stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    BRN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<2>, tmA, tmB, p));
-  } else {
-    BRN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    const int grid = std::min(p.m_tiles * p.n_tiles, sms);
-    tc_gemm_kernel<1><<<grid, TC_THREADS, TC_SMEM, ctx.stream>>>(tmA, tmB, p);
+    BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  };
+#define TC_EK_CASE(E) case E: if (CL == 2) launch(tc_gemm_kernel<2, E>); else launch(tc_gemm_kernel<1, E>); break
+  switch (ek) {
+    TC_EK_CASE(EK_NONE16); TC_EK_CASE(EK_RELU16); TC_EK_CASE(EK_GELU16); TC_EK_CASE(EK_NONE32);
+    TC_EK_CASE(EK_SIG32_TILED); TC_EK_CASE(EK_RES32); TC_EK_CASE(EK_RES16);
+    default: if (CL == 2) launch(tc_gemm_kernel<2, EK_GENERIC>); else launch(tc_gemm_kernel<1, EK_GENERIC>); break;
   }
+#undef TC_EK_CASE
   BRN_CUDA(cudaGetLastError());
 }
 
