@@ -5,8 +5,8 @@
 // relative-position bias of WindowAttention::new (src/swin.rs:143-152) and the analytic -100 region mask of
 // BasicLayer::create_attention_mask (src/swin.rs:603-655).  The [nW,heads,144,144] score tensor never leaves the SM.
 //
-// Work unit = (window, head).  A persistent CTA owns ONE head (its 144x144 bias stays resident in shared memory,
-// rows padded to 304 B so row-per-thread 16-byte reads are bank-conflict free) and walks the windows.
+// Work unit = (window, head).  A persistent CTA owns ONE head (its 144x144 fp32 bias stays resident in shared memory,
+// rows padded to 592 B so row-per-thread 16-byte reads are bank-conflict free) and walks the windows.
 //   warp 10  : one elected thread issues TMA (Q,K,V tiles of the window-ordered qkv matrix, 64B-swizzled, 3 stages)
 //              and all tcgen05.mma:  S = Q K^T (M=128 tiles over the 144 queries, N=144, K=32) into TMEM, then
 //              O = P V (M=128 x2, N=32, K=144; V is the MN-major B operand straight from the TMA tile).
@@ -14,7 +14,8 @@
 //              scores in registers: S is read from TMEM once and released immediately, which lets the MMA warp
 //              compute S of the NEXT window while this one is in its exp phase.  warps 0-3 / 4-7: rows 0-127
 //              (TMEM lane quadrant = warp % 4), warps 8 / 9: rows 128-143.  Row max and row sum are combined
-//              through shared memory; P (bf16/fp16) goes to shared memory in the 32B-swizzled K-major layout the
+//              through shared memory (a named barrier per warp pair); the -100 shift mask is applied only in the
+//              border windows; P (bf16/fp16) goes to shared memory in the 32B-swizzled K-major layout the
 //              P V MMA reads; 1/sum is applied to O in the epilogue, which is deferred into the next unit's softmax
 //              so the P V latency is hidden.
 //   TMEM   : S0 [0,144) rows 0-127 | S1a [144,288) rows 128-143 in lanes 0-15 (for warp 8) | S1b [288,432) the same
@@ -94,12 +95,6 @@ __device__ __forceinline__ void pair_bar_sync(int pair) { asm volatile("bar.sync
 
 template <int DT>
 __device__ __forceinline__ uint32_t at_pack(float a, float b) { return DT == BF16 ? pack_bf16x2(a, b) : pack_f16x2(a, b); }
-template <int DT>
-__device__ __forceinline__ float2 at_unpack(uint32_t u) {
-  if (DT == BF16) return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-  return __half22float2(*reinterpret_cast<const __half2*>(&u));
-}
-
 template <int DT>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {

@@ -2,16 +2,18 @@
 //
 //   out[m, n] = act( sum_{tap, c} X[pixel(m) + tap, c] * W[n, tap, c] + bias ) (+ residual)
 //
-// * A operand: NHWC bf16 activations through a 4-D TMA tensor map {C, W, H, B}; one M tile is a TH x TW pixel
+// * A operand: NHWC 16-bit (bf16 / fp16) activations through a 4-D TMA tensor map {C, W, H, B}; one M tile is a TH x TW pixel
 //   patch (TH*TW = 128) of one image, so a conv tap is just a shifted box and TMA's out-of-bounds zero fill is the
 //   conv's zero padding (and the channel tail when C % 64 != 0).  Linear layers are the 1-tap case on {K, rows,1,1}.
-// * B operand: weights [N][taps][cin_pad] bf16 (K-major) through a 2-D map, box {64, BN}.
+// * B operand: weights [N][taps][cin_pad] 16-bit (K-major) through a 2-D map, box {64, BN}; in 2-CTA clusters each
+//   CTA loads half of the tile and multicasts it.
 // * 128B-swizzled K-major smem tiles, 4-stage mbarrier ring, warp-specialised: warp 0 = TMA producer,
 //   warp 1 = MMA issuer (one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128, N=BN<=256, K=16),
-//   warps 2-5 = epilogue (tcgen05.ld 32x32b, bias / ReLU / erf-GELU / 2*sigmoid / residual / window-reverse row
-//   scatter, bf16 or fp32 stores).  Two TMEM accumulator stages (2 x 256 columns) overlap the epilogue of tile i
-//   with the MMAs of tile i+1; the kernel is persistent (grid = min(tiles, #SM)).
-// Roofline: tensor pipe (2*M*N*K flop per launch) for K >= 384, HBM (A read + out write) below that.
+//   warps 2-9 = epilogue (tc_epilogue.cuh: tcgen05.ld 32x32b, bias / ReLU / erf-GELU / 2*sigmoid / residual /
+//   window-reverse row scatter, smem-staged coalesced 16-bit or fp32 stores).  Two TMEM accumulator stages (2 x 256
+//   columns) overlap the epilogue of tile i with the MMAs of tile i+1; the kernel is persistent (grid = min(tiles, #SM))
+//   and instantiated once per hot epilogue variant (EpiKind).
+// Roofline: tensor pipe (2*M*N*K flop per launch) for K >= 384 without GELU; HBM / epilogue issue below that.
 #include <cuda.h>
 
 #include <cstdio>
