@@ -53,6 +53,8 @@ def lib() -> C.CDLL:
     L.brn_version.restype = C.c_char_p
     L.brn_config_swin_l.argtypes = [C.POINTER(BrnConfig)]
     L.brn_config_swin_l.restype = None
+    L.brn_config_swin_b.argtypes = [C.POINTER(BrnConfig)]
+    L.brn_config_swin_b.restype = None
     L.brn_model_create.argtypes = [C.POINTER(BrnConfig), C.c_int, C.POINTER(vp)]
     L.brn_model_destroy.argtypes = [vp]
     L.brn_model_destroy.restype = None

@@ -48,6 +48,14 @@ void brn_config_swin_l(brn_config* cfg) {
   cfg->precision = BRN_PREC_FP16; cfg->deform_mode = BRN_DEFORM_DEFORMABLE; cfg->micro_batch = 0;
 }
 
+void brn_config_swin_b(brn_config* cfg) {
+  if (!cfg) return;
+  brn_config_swin_l(cfg);
+  cfg->embed_dim = 128;
+  const int h[4] = {4, 8, 16, 32};
+  for (int i = 0; i < 4; ++i) cfg->num_heads[i] = h[i];
+}
+
 brn_status brn_model_create(const brn_config* cfg, int device, brn_model** out) {
   return guard([&] {
     BRN_CHECK(cfg && out, 1, "brn_model_create: null argument");
@@ -117,7 +125,8 @@ brn_status brn_model_set_deform_mode(brn_model* m, int mode) {
 brn_status brn_model_set_cuda_graph(brn_model* m, int on) {
   return guard([&] {
     BRN_CHECK(m, 1, "null model");
-    std::lock_guard<std::mutex> lk(m->impl.mu);
+    std::unique_lock<std::mutex> lk(m->impl.mu);
+    m->impl.quiesce(lk);
     m->impl.use_graph = on ? 1 : 0;
     if (!on) m->impl.drop_graphs();
   });

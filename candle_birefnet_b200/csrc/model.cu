@@ -61,6 +61,10 @@ Model::Model(const brn_config& c, int dev) : cfg(c), device(dev) {
   BRN_CHECK(prop.major == 10, 2, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
                                      ", this library is built for sm_100a only");
   BRN_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+  for (auto& l : lanes) {
+    BRN_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    BRN_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+  }
   build_schema();
 }
 
@@ -69,6 +73,11 @@ Model::~Model() {
   drop_graphs();
   for (void* p : allocs) cudaFree(p);
   if (arena.base) cudaFree(arena.base);
+  for (auto& l : lanes) {
+    if (l.arena.base) cudaFree(l.arena.base);
+    if (l.done) cudaEventDestroy(l.done);
+    if (l.stream) cudaStreamDestroy(l.stream);
+  }
   for (auto& pe : prof) { if (pe.e0) cudaEventDestroy(pe.e0); if (pe.e1) cudaEventDestroy(pe.e1); }
   for (auto e : ktimer.pool) cudaEventDestroy(e);
   if (own_stream) cudaStreamDestroy(own_stream);
@@ -417,14 +426,49 @@ void Model::finalize() {
 // ------------------------------------------------------------------------------------------------
 // forward graph
 // ------------------------------------------------------------------------------------------------
-void Model::drop_graphs() {
-  for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-  graphs.clear();
+void Model::drop_graphs(const void* arena_base) {
+  for (size_t i = graphs.size(); i-- > 0;) {
+    if (arena_base && graphs[i].key.arena_base != arena_base) continue;
+    if (graphs[i].exec) cudaGraphExecDestroy(graphs[i].exec);
+    graphs.erase(graphs.begin() + i);
+  }
+}
+
+int Model::acquire_lane(std::unique_lock<std::mutex>& lk, cudaStream_t s) {
+  // Preference: the lane this caller stream used last (stream order makes reuse free and its CUDA graphs match), then
+  // a lane whose previous call has finished on the device, then any lane nobody is launching into (the new call is
+  // ordered behind the old one with the lane's event).
+  for (;;) {
+    int pick = -1;
+    if (s)
+      for (int i = 0; i < kLanes && pick < 0; ++i) if (!lanes[i].busy && lanes[i].last == s) pick = i;
+    for (int i = 0; i < kLanes && pick < 0; ++i)
+      if (!lanes[i].busy) {
+        if (cudaEventQuery(lanes[i].done) == cudaSuccess) pick = i;
+        else cudaGetLastError();
+      }
+    for (int i = 0; i < kLanes && pick < 0; ++i) if (!lanes[i].busy) pick = i;
+    if (pick >= 0) {
+      lanes[pick].busy = true;
+      std::swap(arena, lanes[pick].arena);
+      return pick;
+    }
+    lane_cv.wait(lk);
+  }
+}
+
+void Model::release_lane(int i) {
+  lanes[i].busy = false;
+  lane_cv.notify_one();
+}
+
+void Model::quiesce(std::unique_lock<std::mutex>& lk) {
+  lane_cv.wait(lk, [&] { for (auto& l : lanes) if (l.busy) return false; return true; });
 }
 
 void Model::ensure_arena(size_t bytes) {
   if (arena.cap >= bytes) return;
-  drop_graphs();          // captured kernels hold arena addresses
+  if (arena.base) drop_graphs(arena.base);          // captured kernels hold arena addresses
   if (arena.base) { BRN_CUDA(cudaFree(arena.base)); arena.base = nullptr; arena.cap = 0; }
   size_t want = bytes + (bytes >> 4) + (1 << 20);
   BRN_CUDA(cudaMalloc(&arena.base, want));
@@ -718,9 +762,15 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
   BRN_CHECK(finalized, 6, "forward before finalize");
   BRN_CHECK(x && out && B > 0, 1, "forward: bad argument");
   BRN_CHECK(H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, 5, "H and W must be positive multiples of 32");
-  std::lock_guard<std::mutex> lk(mu);
+  std::unique_lock<std::mutex> lk(mu);
   BRN_CUDA(cudaSetDevice(device));
-  cudaStream_t st = s ? s : own_stream;
+  const int li = acquire_lane(lk, s);
+  cudaStream_t st = s ? s : lanes[li].stream;
+  lanes[li].last = st;
+  const float* last_src = nullptr; float* last_dst = nullptr; size_t last_bytes = 0;
+  try {
+  // an earlier call may have used this lane's workspace on another stream
+  BRN_CUDA(cudaStreamWaitEvent(st, lanes[li].done, 0));
   const int mb = micro_batch(B, H, W);
   // plan pass
   LaunchCtx ctx; ctx.stream = st; ctx.precision = cfg.precision; ctx.force_simt = env_flag("BRN_FORCE_SIMT");
@@ -794,9 +844,13 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
       e->seen++;
     }
     if (!done) run_forward(ctx, xi, nb, H, W, ko, apply_sigmoid);
-    if (!out_dev) BRN_CUDA(cudaMemcpyAsync(oi, dout, (size_t)nb * H * W * 4, cudaMemcpyDeviceToHost, st));
+    if (!out_dev) {
+      // the last read-back is issued after `mu` is dropped (a pageable destination makes the copy block the host)
+      if (b0 + mb >= B && !prof_on) { last_src = dout; last_dst = oi; last_bytes = (size_t)nb * H * W * 4; }
+      else BRN_CUDA(cudaMemcpyAsync(oi, dout, (size_t)nb * H * W * 4, cudaMemcpyDeviceToHost, st));
+    }
   }
-  if (!x_dev || !out_dev || prof_on) BRN_CUDA(cudaStreamSynchronize(st));
+  if (prof_on) BRN_CUDA(cudaStreamSynchronize(st));
   if (prof_on >= 2) {
     for (int c = 0; c < KC_COUNT; ++c) { kc_ms[c] = 0; kc_flops[c] = 0; kc_bytes[c] = 0; kc_count[c] = 0; }
     for (auto& r : ktimer.recs) {
@@ -821,6 +875,25 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
       prof_names.push_back(pe.name.c_str()); prof_ms.push_back(ms); prof_flops.push_back(pe.flops);
     }
   }
+  } catch (...) {
+    cudaStreamSynchronize(st);
+    std::swap(arena, lanes[li].arena);
+    release_lane(li);
+    throw;
+  }
+  // host-side state is done with: hand the workspace back to the lane and wait for the device without the lock
+  std::swap(arena, lanes[li].arena);
+  cudaError_t werr = cudaSuccess;
+  if (last_bytes || ((!x_dev || !out_dev) && !prof_on)) {
+    lk.unlock();
+    if (last_bytes) werr = cudaMemcpyAsync(last_dst, last_src, last_bytes, cudaMemcpyDeviceToHost, st);
+    if (werr == cudaSuccess) werr = cudaStreamSynchronize(st);
+    lk.lock();
+  } else {
+    werr = cudaEventRecord(lanes[li].done, st);
+  }
+  release_lane(li);
+  BRN_CHECK(werr == cudaSuccess, 2, std::string("forward: ") + cudaGetErrorString(werr));
 }
 
 void Model::backbone_api(const float* x, int B, int H, int W, bool x_dev, float* const outs[4], bool out_dev,

@@ -1,5 +1,6 @@
 // Model handle: weight schema, finalize (folding + upload) and the forward graph.  Private to the library.
 #pragma once
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -95,7 +96,18 @@ struct Model {
   float *pe_g = nullptr, *pe_b = nullptr;
   DecoderW dw;
 
+  // `arena` is the workspace the host-side code is currently planning / launching into (always accessed under `mu`).
+  // forward() borrows one of two lanes (workspace + stream + completion event) for the duration of a call and
+  // swaps the lane's arena in while it holds `mu`; it drops `mu` while it waits for the device, so two host threads
+  // can keep two calls in flight: the host<->device copies of one overlap the kernels of the other.
   Arena arena;
+  struct Lane { Arena arena; cudaStream_t stream = nullptr, last = nullptr; cudaEvent_t done = nullptr; bool busy = false; };
+  static constexpr int kLanes = 2;
+  Lane lanes[kLanes];
+  std::condition_variable lane_cv;
+  int acquire_lane(std::unique_lock<std::mutex>& lk, cudaStream_t s);
+  void release_lane(int i);
+  void quiesce(std::unique_lock<std::mutex>& lk);     // wait until no forward() is in flight
   long long launches = 0;
 
   // CUDA-graph replay of the forward: the launch sequence of run_forward for one (buffers, shape, mode) key is
@@ -112,7 +124,7 @@ struct Model {
   std::vector<GraphEntry> graphs;
   long long graph_clock = 0;
   int use_graph = 1;
-  void drop_graphs();
+  void drop_graphs(const void* arena_base = nullptr);   // nullptr: all
 
   int prof_on = 0;          // 1: per-stage events, 2: + per-kernel-class events (KTimer)
   KTimer ktimer;

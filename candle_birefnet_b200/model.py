@@ -40,6 +40,11 @@ class SwinConfig:
     def swin_l() -> "SwinConfig":
         return SwinConfig()
 
+    @staticmethod
+    def swin_b() -> "SwinConfig":
+        """SwinConfig::swin_b (src/swin.rs:54-66)."""
+        return SwinConfig(embed_dim=128, num_heads=(4, 8, 16, 32))
+
 
 @dataclass
 class BiRefNetConfig:

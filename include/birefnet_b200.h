@@ -16,10 +16,14 @@
  * thread-local message (mirrors candle_core::Result / bail!, src/aspp.rs:101,117).
  * Nothing throws or aborts across the ABI.
  *
- * Threading: a handle is thread-compatible, not thread-safe: calls on one
- * handle are serialised by an internal mutex (the reference's `&self` forward
- * is immutable; here the workspace arena is per handle).  Use one handle per
- * GPU for image sharding.
+ * Threading: every entry point may be called from several host threads on one
+ * handle (the reference's `&self` forward is immutable and callable
+ * concurrently).  Host-side planning and launching is serialised by an
+ * internal mutex; brn_forward_logits / brn_forward then wait for the device
+ * WITHOUT the mutex, on one of two internal lanes (workspace + stream), so two
+ * threads keep two calls in flight and the host<->device copies of one
+ * overlap the kernels of the other.  Use one handle per GPU for image
+ * sharding.
  */
 #ifndef BIREFNET_B200_H
 #define BIREFNET_B200_H
@@ -81,6 +85,12 @@ typedef struct {
 
 /* BiRefNetConfig::swin_l() (src/birefnet.rs:64-66) + SwinConfig::swin_l() (src/swin.rs:69-80). */
 BRN_API void brn_config_swin_l(brn_config* cfg);
+
+/* SwinConfig::swin_b() (src/swin.rs:54-66): the other window-12 / head_dim-32 member of the family (embed 128,
+ * heads 4/8/16/32).  The reference's BiRefNet::new always builds swin_l (src/birefnet.rs:390-391); the decoder
+ * widths follow the backbone's channel counts, so the same path runs at this width.  swin_t/swin_s
+ * (window 7) are not supported: brn_model_create rejects window_size != 12. */
+BRN_API void brn_config_swin_b(brn_config* cfg);
 
 /* ---- model lifetime: replaces BiRefNet::new(config, vb) (src/birefnet.rs:389-409) ------------------------- */
 

@@ -62,6 +62,11 @@ class Config:
     def swin_l() -> "Config":
         return Config()
 
+    # src/swin.rs:54-66
+    @staticmethod
+    def swin_b() -> "Config":
+        return Config(embed_dim=128, num_heads=(4, 8, 16, 32), name="swin_b")
+
     @staticmethod
     def mini() -> "Config":
         return Config(embed_dim=64, depths=(2, 2, 2, 2), num_heads=(2, 4, 8, 16), name="mini")

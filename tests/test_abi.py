@@ -7,6 +7,7 @@ import pytest
 
 import candle_birefnet_b200 as cb
 from candle_birefnet_b200 import _lib
+from oracle import birefnet_ref as R
 from tests.conftest import has_gpu
 
 
@@ -27,6 +28,17 @@ def test_config_swin_l_matches_reference():
     assert c.window_size == 12 and c.mlp_ratio == 4 and c.patch_size == 4
     py = cb.BiRefNetConfig.swin_l()
     assert py.swin.embed_dim == 192 and py.size == (1024, 1024) and py.mul_scl_ipt
+
+
+def test_config_swin_b_matches_reference():
+    c = _lib.BrnConfig()
+    cb.lib().brn_config_swin_b(C.byref(c))
+    # SwinConfig::swin_b (src/swin.rs:54-66)
+    assert c.embed_dim == 128 and list(c.depths) == [2, 2, 18, 2] and list(c.num_heads) == [4, 8, 16, 32]
+    assert c.window_size == 12 and c.mlp_ratio == 4 and c.patch_size == 4
+    py = cb.SwinConfig.swin_b()
+    assert py.embed_dim == 128 and py.num_heads == (4, 8, 16, 32) and py.window_size == 12
+    assert R.Config.swin_b().stage_channels() == [128, 256, 512, 1024]
 
 
 def test_product_path_has_no_oracle_or_cpu_fallback():

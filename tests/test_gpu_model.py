@@ -164,6 +164,21 @@ def test_forward_logits_swin_l_512(precision):
     check_logits(got, exp, precision)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_forward_logits_swin_b_384(precision):
+    """SURVEY 8f N4: SwinConfig::swin_b (src/swin.rs:54-66), the other window-12 member, through the same path."""
+    cfg = R.Config.swin_b()
+    wnp = make_weights(cfg, seed=3, weight_set="B")
+    m = cb.BiRefNet.new(cb.BiRefNetConfig(swin=cb.SwinConfig.swin_b(), precision=precision, deform_mode="deformable"), wnp)
+    x = make_input(2, 384, 384, seed=77)
+    got = m.forward_logits(x)
+    feats = m.backbone_forward(x[:1])
+    exp = R.forward_logits(torch.from_numpy(x), as_torch(wnp), cfg, "deformable").numpy()
+    m.close()
+    assert [f.shape[1] for f in feats] == [128, 256, 512, 1024]
+    check_logits(got, exp, precision)
+
+
 def test_cuda_graph_replay_is_bit_identical(mini_models):
     """The forward is captured into a CUDA graph on the second call with the same buffers; eager launches, the capture
     call and every replay must agree bit for bit, and switching modes / shapes must not replay a stale graph."""
