@@ -373,8 +373,12 @@ brn_status brn_bench_op(int device, int precision, int kind, int32_t B, int32_t 
       View o = make_view(s.alloc(px * N * dsize(OD)), OD, B, H, W, N);
       if (kind == 0) {
         g.x = x; g.w = &L; g.pad = k / 2; g.act = act; g.out = o;
-        if (with_res) { g.res = make_view(s.alloc(px * N * 4), F32, B, H, W, N); fill(s, g.res.p, F32, (long long)px * N, 2u, 1.0f);
-                        g.out = make_view(g.res.p, F32, B, H, W, N); }
+        if (with_res == 2) {          // 16-bit residual, separate 16-bit output (decoder laterals)
+          g.res = make_view(s.alloc(px * N * dsize(AD)), AD, B, H, W, N); fill(s, g.res.p, AD, (long long)px * N, 2u, 1.0f);
+        } else if (with_res) {        // fp32 residual stream updated in place (backbone proj / fc2)
+          g.res = make_view(s.alloc(px * N * 4), F32, B, H, W, N); fill(s, g.res.p, F32, (long long)px * N, 2u, 1.0f);
+          g.out = make_view(g.res.p, F32, B, H, W, N);
+        }
         launch = [&] { op_gemm(ctx, g); };
       } else {
         View om = make_view(s.alloc(px * 3 * taps * 4), F32, B, H, W, 3 * taps);

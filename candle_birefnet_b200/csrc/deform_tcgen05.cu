@@ -303,8 +303,9 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
     const int eth = threadIdx.x - (DF_PRODUCERS + 32);
     const uint32_t stage = ptx::smem_u32(sStage) + (warp - DF_MMA_WARP - 1) * EPI_STAGE_BYTES;
     const uint32_t sb = ptx::smem_u32(sBias);
-    if (p.epi.bias) {
-      for (int t = eth; t < DF_BIAS_LD; t += 128) ptx::sts32(sb + t * 4, t < p.epi.N ? __ldg(p.epi.bias + t) : 0.f);
+    {
+      for (int t = eth; t < DF_BIAS_LD; t += 128)
+        ptx::sts32(sb + t * 4, (p.epi.bias && t < p.epi.N) ? __ldg(p.epi.bias + t) : 0.f);
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     const int c1 = ((p.epi.N + 15) >> 4) * 16;
@@ -318,13 +319,13 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
       // only the epilogues a deformable conv can have (no residual; none / ReLU): keeps the 80-register kernel small
-      const uint32_t sbb = p.epi.bias ? sb : 0u;
+      const uint32_t sbb = sb;
       if (p.epi.odt == F32) {
-        if (p.epi.act == ACT_RELU) epi_warp<ACT_RELU, true, 0>(p.epi, taddr, 0, 0, c1, orow, sbb, stage, lane);
-        else epi_warp<ACT_NONE, true, 0>(p.epi, taddr, 0, 0, c1, orow, sbb, stage, lane);
+        if (p.epi.act == ACT_RELU) epi_warp<ACT_RELU, true, 0, false>(p.epi, taddr, 0, 0, c1, orow, sbb, stage, lane);
+        else epi_warp<ACT_NONE, true, 0, false>(p.epi, taddr, 0, 0, c1, orow, sbb, stage, lane);
       } else {
-        if (p.epi.act == ACT_RELU) epi_warp<ACT_RELU, false, 0>(p.epi, taddr, 0, 0, c1, orow, sbb, stage, lane);
-        else epi_warp<ACT_NONE, false, 0>(p.epi, taddr, 0, 0, c1, orow, sbb, stage, lane);
+        if (p.epi.act == ACT_RELU) epi_warp<ACT_RELU, false, 0, false>(p.epi, taddr, 0, 0, c1, orow, sbb, stage, lane);
+        else epi_warp<ACT_NONE, false, 0, false>(p.epi, taddr, 0, 0, c1, orow, sbb, stage, lane);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[acc]);

@@ -38,6 +38,23 @@ constexpr int TC_BIAS_LD = 288;                                // floats per acc
 constexpr int TC_EPI_BYTES = TC_EPI_WARPS * EPI_STAGE_BYTES + 2 * TC_BIAS_LD * 4;
 constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_EPI_BYTES + 256 + 1024;
 
+// Division by a run-time constant as multiply-high + shift (valid for numerators < 2^31): the epilogue warps derive
+// the tile coordinates and the window row map per tile, and a hardware-less integer division is ~20 instructions.
+struct FastDiv {
+  uint32_t d = 1, mul = 0, shr = 0;
+  FastDiv() = default;
+  explicit FastDiv(uint32_t div) : d(div) {
+    if (div > 1) {
+      uint32_t lg = 0;
+      while ((1ull << lg) < div) ++lg;
+      const uint32_t pw = 31 + lg;
+      mul = (uint32_t)(((1ull << pw) + div - 1) / div);
+      shr = pw - 32;
+    }
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d != 1 ? __umulhi(n, mul) >> shr : n; }
+};
+
 struct TcGemmP {
   int B, H, W;
   int tw_log2, tiles_x, tiles_y;
@@ -47,7 +64,34 @@ struct TcGemmP {
   int out_tiled; // fp32 out is [m_tile][N][128]
   EpiP epi;
   RowMap rm;
+  FastDiv fd_nt, fd_tpi, fd_tx;        // n_tiles, tiles_x * tiles_y, tiles_x
+  FastDiv fd_rows1, fd_nww1;           // row map, first grid: rows per image (windows * 144), windows per row
+  FastDiv fd_rows2, fd_nww2;           // second grid (merged two-resolution pass)
 };
+
+// rowmap_token (device_utils.cuh) with the run-time divisions replaced; rows < 2^31
+__device__ __forceinline__ long long window_row_to_token_fd(uint32_t m, int h, int w, int hp, int wp, int shift,
+                                                           const FastDiv& rows, const FastDiv& nww) {
+  const uint32_t b = rows.div(m);
+  const uint32_t rem = m - b * rows.d;
+  const uint32_t wid = rem / 144u, t = rem - wid * 144u;
+  const uint32_t wi = nww.div(wid), wj = wid - wi * nww.d;
+  const uint32_t ti = t / 12u, tj = t - ti * 12u;
+  int r = (int)(wi * 12u + ti) + shift, c = (int)(wj * 12u + tj) + shift;
+  if (r >= hp) r -= hp;
+  if (c >= wp) c -= wp;
+  if (r >= h || c >= w) return -1;
+  return ((long long)b * h + r) * (long long)w + c;
+}
+__device__ __forceinline__ long long rowmap_token_fd(const TcGemmP& p, long long m) {
+  const RowMap& rm = p.rm;
+  if (rm.split > 0 && m >= rm.split) {
+    const long long t = window_row_to_token_fd((uint32_t)(m - rm.split), rm.h2, rm.w2, rm.hp2, rm.wp2, rm.shift,
+                                               p.fd_rows2, p.fd_nww2);
+    return t < 0 ? t : t + rm.tok2;
+  }
+  return window_row_to_token_fd((uint32_t)m, rm.h, rm.w, rm.hp, rm.wp, rm.shift, p.fd_rows1, p.fd_nww1);
+}
 
 // CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs own M tiles 2j and 2j+1 of the same N tile: each loads
 // half of the shared B (weight) tile and TMA-multicasts it into both CTAs' shared memory, so the L2 -> SMEM bytes per
@@ -157,29 +201,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool o32 = p.epi.odt == F32;
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = item0; item < num_items; item += item_step) {
-      const int m_tile = (item / p.n_tiles) * CL + rank, n_tile = item % p.n_tiles;
-      const int b = m_tile / tiles_per_img, r = m_tile - b * tiles_per_img;
-      const int y = (r / p.tiles_x) * TH + (row >> p.tw_log2), x = (r % p.tiles_x) * TW + (row & (TW - 1));
+      const int mg = (int)p.fd_nt.div((uint32_t)item);
+      const int m_tile = mg * CL + rank, n_tile = item - mg * p.n_tiles;
+      const int b = (int)p.fd_tpi.div((uint32_t)m_tile), r = m_tile - b * tiles_per_img;
+      const int ty = (int)p.fd_tx.div((uint32_t)r), tx = r - ty * p.tiles_x;
+      const int y = ty * TH + (row >> p.tw_log2), x = tx * TW + (row & (TW - 1));
       const bool valid = m_tile < p.m_tiles && y < p.H && x < p.W;
       long long orow = valid ? ((long long)b * p.H + y) * p.W + x : -1;
-      if (valid && p.rm.enabled) orow = rowmap_token(p.rm, orow);
+      if (valid && p.rm.enabled) orow = rowmap_token_fd(p, orow);
       const int n0 = n_tile * p.BN;
       const int nch = min(p.BN, p.epi.N - n0 + 15) >> 4;     // 16-column chunks of this tile that hold real columns
       const int gsz = o32 ? 1 : 2;                           // 16-bit output: keep the split on 32-column granules
       const int per = ((nch + gsz - 1) / gsz + PER_Q - 1) / PER_Q * gsz;
       const int c0 = min(part * per, nch) * 16, c1 = min((part + 1) * per, nch) * 16;
       const uint32_t sb = ptx::smem_u32(sBias) + acc * TC_BIAS_LD * 4;
-      if (p.epi.bias) {
-        // this tile's bias -> shared (double buffered with the accumulator stage; an M tile lies inside one image)
-        const float* bias = p.epi.bias + (long long)(m_tile < p.m_tiles ? b : 0) * p.epi.bias_bstride;
+      {
+        // this tile's bias -> shared (double buffered with the accumulator stage; an M tile lies inside one image).
+        // Staged unconditionally (zeros without a bias): an optional add costs a register move per element.
+        const float* bias = p.epi.bias ? p.epi.bias + (long long)(m_tile < p.m_tiles ? b : 0) * p.epi.bias_bstride : nullptr;
         for (int t = eth; t < TC_BIAS_LD; t += 32 * TC_EPI_WARPS)
-          ptx::sts32(sb + t * 4, (t < p.BN && n0 + t < p.epi.N) ? __ldg(bias + n0 + t) : 0.f);
+          ptx::sts32(sb + t * 4, (bias && t < p.BN && n0 + t < p.epi.N) ? __ldg(bias + n0 + t) : 0.f);
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
       }
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      const uint32_t sbb = p.epi.bias ? sb : 0u;
+      const uint32_t sbb = sb;
       if (EPI == EK_NONE16) epi_warp<ACT_NONE, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
       else if (EPI == EK_RELU16) epi_warp<ACT_RELU, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
       else if (EPI == EK_GELU16) epi_warp<ACT_GELU, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
@@ -298,6 +345,18 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   p.taps = w.taps(); p.kw = w.kw; p.pad = a.pad; p.cin_pad = w.cin_pad; p.cblocks = w.cin_pad / TC_BK;
   p.epi = make_epi(w.N, a.bias ? a.bias : w.bias, a.bias_bstride, a.act, a.act_from, a.res, a.out);
   p.rm = a.rowmap;
+  p.fd_nt = FastDiv((uint32_t)p.n_tiles);
+  p.fd_tpi = FastDiv((uint32_t)(p.tiles_x * p.tiles_y));
+  p.fd_tx = FastDiv((uint32_t)p.tiles_x);
+  if (p.rm.enabled) {
+    BRN_CHECK((long long)a.x.rows() < (1ll << 31), 5, "tc_gemm: row map needs fewer than 2^31 rows");
+    p.fd_rows1 = FastDiv((uint32_t)((p.rm.hp / 12) * (p.rm.wp / 12) * 144));
+    p.fd_nww1 = FastDiv((uint32_t)(p.rm.wp / 12));
+    if (p.rm.split > 0) {
+      p.fd_rows2 = FastDiv((uint32_t)((p.rm.hp2 / 12) * (p.rm.wp2 / 12) * 144));
+      p.fd_nww2 = FastDiv((uint32_t)(p.rm.wp2 / 12));
+    }
+  }
   p.in_bf16 = a.x.dt == BF16 ? 1 : 0;
 
   const uint64_t ld2 = (uint64_t)a.x.ld * 2;

@@ -106,6 +106,14 @@ __device__ __forceinline__ uint4 ldg_l2_256(const void* p) {
   return v;
 }
 
+// packed add of two 16-bit pairs (bf16x2 or f16x2 by run-time type)
+__device__ __forceinline__ uint32_t add16x2(uint32_t a, uint32_t b, int dt) {
+  uint32_t r;
+  if (dt == BF16) asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  else asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
 template <int ACT>
 __device__ __forceinline__ float epi_act(float f, int col, int act_from) {
   if (ACT == ACT_RELU) return fmaxf(f, 0.f);
@@ -117,7 +125,7 @@ __device__ __forceinline__ float epi_act(float f, int col, int act_from) {
 // One epilogue warp's share of an accumulator tile: its 32 rows (TMEM lane quadrant encoded in taddr) x tile columns
 // [c0, c1) (multiples of 16; tile column 0 is output column n0).
 //   orow  : this lane's output row (row index into out / res), < 0 for rows that must not be written
-//   sbias : SHARED address of the tile's bias (index = tile column, zero padded to c1 rounded up to 32), or 0
+//   sbias : SHARED address of the tile's bias (index = tile column, zero padded to c1 rounded up to 32; zeros if none)
 //   stage : SHARED address of this warp's EPI_STAGE_BYTES staging block (16-byte aligned)
 // O32: fp32 output (16 columns per 64-byte granule), else 16-bit output by p.odt (32 columns per granule).
 // Residual (out may alias res: the Swin residual stream is updated in place, so residual loads can never be hoisted
@@ -125,7 +133,7 @@ __device__ __forceinline__ float epi_act(float f, int col, int act_from) {
 //   mode 1: fp32 residual + fp32 output, added in phase B (coalesced LDG.128)
 //   mode 2: 16-bit residual of the output type, added in fp32 in phase A (this thread's 64 contiguous bytes)
 //   mode 3: anything else, scalar loads in phase A
-template <int ACT, bool O32, int RM>
+template <int ACT, bool O32, int RM, bool PP = (RM == 0)>
 __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, int c0, int c1, long long orow,
                                          uint32_t sbias, uint32_t stage, int lane) {
   if (c0 >= c1) return;
@@ -159,52 +167,53 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
         if (orow_b[it] >= 0 && nl >= 4)
           q[it] = ldg_l2_256((const float*)p.res + orow_b[it] * p.ldres + col);
     } else if (rmode == 2) {
-      const uint16_t* rp = (const uint16_t*)p.res + orow * p.ldres + n0 + c;
+      // 16-bit residual of a 16-bit output: fetched in the phase-B geometry (8 rows x 64 bytes per instruction)
+      const int col = n0 + c + kb * 8;
+      const int nl = min(p.N - col, min(GC, c1 - c) - kb * 8);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (orow >= 0 && 8 * k < c1 - c && n0 + c + 8 * k < p.N) q[k] = ldg_l2_256(rp + 8 * k);
+      for (int it = 0; it < 4; ++it)
+        if (orow_b[it] >= 0 && nl >= 8)
+          q[it] = ldg_l2_256((const uint16_t*)p.res + orow_b[it] * p.ldres + col);
     }
   };
 
-  uint32_t v[GC];
+  // PP: two TMEM destination register sets in ping-pong -- the load of granule g+1 is in flight while granule g is
+  // worked on.  !PP (register-starved callers: the 80-register deformable kernel, the residual variants): one set,
+  // which costs one register move per element to free it for the next load.
+  uint32_t va[GC], vb[PP ? GC : 1];
 #pragma unroll
-  for (int j = 0; j < GC; ++j) v[j] = 0u;
-  tmem_ld16_raw(taddr + c0, v);
-  if (!O32 && c0 + 16 < c1) tmem_ld16_raw(taddr + c0 + 16, v + (GC - 16));
+  for (int j = 0; j < GC; ++j) { va[j] = 0u; if (PP) vb[j] = 0u; }
+  tmem_ld16_raw(taddr + c0, va);
+  if (!O32 && c0 + 16 < c1) tmem_ld16_raw(taddr + c0 + 16, va + (GC - 16));
   if (rmode == 1 || rmode == 2) { res_issue(c0, rq0); res_issue(c0 + GC, rq1); }
+  // every row of this warp is a real output row: the interior store path needs no per-row predicate
+  const bool rows_ok = __all_sync(0xffffffffu, orow >= 0);
 
-  auto granule = [&](int c, uint4 (&rq)[4]) {
+  auto granule = [&](int c, uint4 (&rq)[4], uint32_t (&v)[GC], uint32_t* vn) {
     const int ncol = min(GC, c1 - c);
     tmem_wait_dep(v);
+    // the next granule's TMEM load overlaps the math and the stores of this one
+    auto load_next = [&] {
+      if (c + GC < c1) {
+        tmem_ld16_raw(taddr + c + GC, vn);
+        if (!O32 && c + GC + 16 < c1) tmem_ld16_raw(taddr + c + GC + 16, vn + (GC - 16));
+      }
+    };
+    if (PP) load_next();
     // ---- phase A: this thread's row, columns [c, c + ncol) ----
     float f[GC];
 #pragma unroll
     for (int j = 0; j < GC; ++j) f[j] = __uint_as_float(v[j]);
-    // the next granule's TMEM load overlaps the math and the stores of this one
-    if (c + GC < c1) {
-      tmem_ld16_raw(taddr + c + GC, v);
-      if (!O32 && c + GC + 16 < c1) tmem_ld16_raw(taddr + c + GC + 16, v + (GC - 16));
-    }
-    if (sbias) {
+    if (!PP) load_next();
+    // the bias is always staged (zeros when the layer has none)
 #pragma unroll
-      for (int j = 0; j < GC; j += 4) {
-        const uint4 bv = ptx::lds128(sbias + (c + j) * 4);
-        f[j] += __uint_as_float(bv.x); f[j + 1] += __uint_as_float(bv.y); f[j + 2] += __uint_as_float(bv.z); f[j + 3] += __uint_as_float(bv.w);
-      }
+    for (int j = 0; j < GC; j += 4) {
+      const uint4 bv = ptx::lds128(sbias + (c + j) * 4);
+      f[j] += __uint_as_float(bv.x); f[j + 1] += __uint_as_float(bv.y); f[j + 2] += __uint_as_float(bv.z); f[j + 3] += __uint_as_float(bv.w);
     }
 #pragma unroll
     for (int j = 0; j < GC; ++j) f[j] = epi_act<ACT>(f[j], n0 + c + j, p.act_from);
-    if (!O32 && rmode == 2) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t* h = reinterpret_cast<const uint32_t*>(&rq[k]);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 r2 = unpack16x2(h[t], p.odt);
-          f[(8 * k + 2 * t) % GC] += r2.x; f[(8 * k + 2 * t + 1) % GC] += r2.y;
-        }
-      }
-    } else if (rmode == 3 && orow >= 0) {
+    if (rmode == 3 && orow >= 0) {
 #pragma unroll
       for (int j = 0; j < GC; ++j)
         if (j < ncol && n0 + c + j < p.N) f[j] += ld_elem(p.res, p.resdt, orow * p.ldres + n0 + c + j);
@@ -245,6 +254,19 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
         fv->x += rv->x; fv->y += rv->y; fv->z += rv->z; fv->w += rv->w;
       }
     }
+    if (!O32 && rmode == 2) {
+      // packed 16-bit add of the already rounded value (one extra rounding of <= 0.5 ulp of the 16-bit type)
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        val[it].x = add16x2(val[it].x, rq[it].x, p.odt); val[it].y = add16x2(val[it].y, rq[it].y, p.odt);
+        val[it].z = add16x2(val[it].z, rq[it].z, p.odt); val[it].w = add16x2(val[it].w, rq[it].w, p.odt);
+      }
+    }
+    if (rows_ok && p.vec && ncol == GC && n0 + c + GC <= p.N) {
+      // interior granule: four unpredicated 16-byte stores
+#pragma unroll
+      for (int it = 0; it < 4; ++it) *reinterpret_cast<uint4*>(orow_p[it] + (c + kb * PER) * ESZ) = val[it];
+    } else
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const long long ro = orow_b[it];
@@ -262,7 +284,12 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
         const uint16_t* hv = reinterpret_cast<const uint16_t*>(&val[it]);
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-          if (e < nleft) ((uint16_t*)op)[e] = hv[e];
+          if (e < nleft) {
+            uint16_t h = hv[e];
+            // a mode-2 residual of a partial chunk was not prefetched
+            if (rmode == 2) h = (uint16_t)add16x2(h, ((const uint16_t*)p.res)[ro * p.ldres + col + e], p.odt);
+            ((uint16_t*)op)[e] = h;
+          }
       }
     }
     if (rmode == 1 || rmode == 2) res_issue(c + 2 * GC, rq);   // this slot's next granule, after the stores (aliasing)
@@ -270,8 +297,13 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
   };
 
   for (int c = c0; c < c1; c += 2 * GC) {
-    granule(c, rq0);
-    if (c + GC < c1) granule(c + GC, rq1);
+    if constexpr (PP) {
+      granule(c, rq0, va, vb);
+      if (c + GC < c1) granule(c + GC, rq1, vb, va);
+    } else {
+      granule(c, rq0, va, va);
+      if (c + GC < c1) granule(c + GC, rq1, va, va);
+    }
   }
 }
 

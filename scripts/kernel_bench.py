@@ -9,7 +9,7 @@ PEAK = 1388.4
 def gemm(tag, M, N, K, k=1, act=0, res=False, f32=False, H=None, W=None, B=1, prec="fp16"):
     if H is None:
         B, H, W = 1, 1, M
-    ms = ops.bench_op("gemm", B, H, W, K, N, k, act, res, f32, precision=prec)
+    ms = ops.bench_op("gemm", B, H, W, K, N, k, act, int(res), f32, precision=prec)
     fl = 2.0 * B * H * W * N * K * k * k
     print(f"gemm {tag:28s} M={B*H*W:8d} N={N:5d} K={k*k}x{K:5d} act={act} res={int(res)}: {ms*1e3:9.1f} us  {fl/ms/1e9:7.1f} TF/s ({fl/ms/1e9/PEAK*100:4.1f}%)", flush=True)
 
@@ -38,6 +38,15 @@ def main():
         gemm("dec1 conv1 1024->64", 0, 64, 1024, k=1, act=1, B=16, H=256, W=256)
         gemm("dec1 conv_out 64->192", 0, 192, 64, k=3, f32=True, B=16, H=256, W=256)
         gemm("lat2 384->384 res", 0, 384, 384, k=1, res=True, B=16, H=256, W=256)
+    if which == "lat":
+        gemm("lat2 res16", 0, 384, 384, k=1, res=2, B=16, H=256, W=256)
+        gemm("lat2 nores", 0, 384, 384, k=1, B=16, H=256, W=256)
+        gemm("lat2 res32 out32", 0, 384, 384, k=1, res=True, f32=True, B=16, H=256, W=256)
+        gemm("lat2 linear res16", 1048576, 384, 384, res=2)
+        gemm("lat2 linear nores", 1048576, 384, 384)
+        gemm("lat2 N=192 nores", 0, 192, 384, k=1, B=16, H=256, W=256)
+        gemm("lat3 768 res16", 0, 768, 768, k=1, res=2, B=16, H=128, W=128)
+        gemm("lat3 768 nores", 0, 768, 768, k=1, B=16, H=128, W=128)
     if which == "small":
         for N in (3, 16, 32, 64):
             for act in (0, 3):
