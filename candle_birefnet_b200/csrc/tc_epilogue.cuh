@@ -38,21 +38,55 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 // exact-erf GELU (candle `gelu_erf`, src/swin.rs:105):  gelu(x) = relu(x) - |x| * q(|x|),  q(a) = 0.5 * erfc(a / sqrt2).
-// log2 q is smooth and nearly quadratic, so a degree-6 polynomial (weighted minimax fit on [0, 6.2], coefficients from
-// scripts/fit_gelu.py) followed by ONE ex2.approx gives q directly: max |error| 2.8e-7 over fp32 inputs in [-8, 8]
-// (beyond 6.2 the argument is clamped: |x| q < 2e-9 |x|).  10 instructions per element, 1 MUFU -- the fc1 epilogue
-// evaluates ~0.5 G GELUs per 1024^2 image and its math phase was co-limited by the XU pipe with the previous
-// Abramowitz-Stegun form (rcp + ex2: 14 instructions, 2 MUFU).
+// log2 q is smooth and nearly quadratic, so a degree-5 polynomial (weighted minimax fit on [0, 6.2], coefficients from
+// scripts/fit_gelu.py) followed by ONE ex2.approx gives q directly: max |error| 6.4e-7 over fp32 inputs in [-60, 60].
+// The leading coefficient is negative, so the polynomial keeps falling beyond the fit interval (q -> 0) and the
+// argument needs no clamp.  8 instructions per element, 1 MUFU -- the fc1 epilogue evaluates ~0.5 G GELUs per 1024^2
+// image and is issue-bound on this math (was: degree 6 + clamp, 10 instructions; before that Abramowitz-Stegun with
+// rcp + ex2, 14 instructions and 2 MUFU).
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float ax = fabsf(x);
-  const float a = fminf(ax, 6.2f);
-  float l = fmaf(a, 3.309384919703007e-05f, -0.0007692287908867002f);
-  l = fmaf(a, l, 0.008080746047198772f);
-  l = fmaf(a, l, -0.05341215059161186f);
-  l = fmaf(a, l, -0.4587709307670593f);
-  l = fmaf(a, l, -1.1512017250061035f);
-  l = fmaf(a, l, -0.999993085861206f);
-  return fmaf(-ax, ex2_approx(l), fmaxf(x, 0.f));
+  const float a = fabsf(x);
+  float l = fmaf(a, -0.0004732935631182045f, 0.007084455341100693f);
+  l = fmaf(a, l, -0.05182714760303497f);
+  l = fmaf(a, l, -0.4599926769733429f);
+  l = fmaf(a, l, -1.1507877111434937f);
+  l = fmaf(a, l, -1.000037670135498f);
+  return fmaf(-a, ex2_approx(l), fmaxf(x, 0.f));
+}
+
+// sm_100 packed fp32 pairs (FFMA2 / FADD2: two lanes of math per issue slot; the epilogue is issue-bound)
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a0, a1)), "l"(pk2(b0, b1)));
+  upk2(r, a0, a1);
+}
+// gelu_fast on a pair: the polynomial runs in -|x| (odd coefficients negated; the sign trick folds into the FFMA2
+// operand modifier), 6 FFMA2 + 2 FMNMX + 2 MUFU per two elements
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  const unsigned long long na = pk2(-fabsf(x0), -fabsf(x1));
+  unsigned long long l = fma2(na, pk2(0.0004732935631182045f, 0.0004732935631182045f),
+                              pk2(0.007084455341100693f, 0.007084455341100693f));
+  l = fma2(na, l, pk2(0.05182714760303497f, 0.05182714760303497f));
+  l = fma2(na, l, pk2(-0.4599926769733429f, -0.4599926769733429f));
+  l = fma2(na, l, pk2(1.1507877111434937f, 1.1507877111434937f));
+  l = fma2(na, l, pk2(-1.000037670135498f, -1.000037670135498f));
+  float l0, l1;
+  upk2(l, l0, l1);
+  const unsigned long long r = fma2(na, pk2(ex2_approx(l0), ex2_approx(l1)), pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+  upk2(r, x0, x1);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -131,7 +165,7 @@ __device__ __forceinline__ float epi_act(float f, int col, int act_from) {
 // Residual (out may alias res: the Swin residual stream is updated in place, so residual loads can never be hoisted
 // above earlier stores by the compiler -- they are issued explicitly, two granules ahead, right after the stores):
 //   mode 1: fp32 residual + fp32 output, added in phase B (coalesced LDG.128)
-//   mode 2: 16-bit residual of the output type, added in fp32 in phase A (this thread's 64 contiguous bytes)
+//   mode 2: 16-bit residual of a 16-bit output, added packed in phase B (coalesced LDG.128; one extra 16-bit rounding)
 //   mode 3: anything else, scalar loads in phase A
 template <int ACT, bool O32, int RM, bool PP = (RM == 0)>
 __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, int c0, int c1, long long orow,
@@ -209,10 +243,16 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
 #pragma unroll
     for (int j = 0; j < GC; j += 4) {
       const uint4 bv = ptx::lds128(sbias + (c + j) * 4);
-      f[j] += __uint_as_float(bv.x); f[j + 1] += __uint_as_float(bv.y); f[j + 2] += __uint_as_float(bv.z); f[j + 3] += __uint_as_float(bv.w);
+      add2(f[j], f[j + 1], __uint_as_float(bv.x), __uint_as_float(bv.y));
+      add2(f[j + 2], f[j + 3], __uint_as_float(bv.z), __uint_as_float(bv.w));
     }
+    if (ACT == ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < GC; ++j) f[j] = epi_act<ACT>(f[j], n0 + c + j, p.act_from);
+      for (int j = 0; j < GC; j += 2) gelu_fast2(f[j], f[j + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < GC; ++j) f[j] = epi_act<ACT>(f[j], n0 + c + j, p.act_from);
+    }
     if (rmode == 3 && orow >= 0) {
 #pragma unroll
       for (int j = 0; j < GC; ++j)
@@ -251,7 +291,7 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
       for (int it = 0; it < 4; ++it) {
         float4* fv = reinterpret_cast<float4*>(&val[it]);
         const float4* rv = reinterpret_cast<const float4*>(&rq[it]);
-        fv->x += rv->x; fv->y += rv->y; fv->z += rv->z; fv->w += rv->w;
+        add2(fv->x, fv->y, rv->x, rv->y); add2(fv->z, fv->w, rv->z, rv->w);
       }
     }
     if (!O32 && rmode == 2) {
