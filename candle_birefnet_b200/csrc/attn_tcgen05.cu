@@ -228,6 +228,12 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       ptx::mbar_wait(o_full, par);
       ptx::tc_fence_after();
       const float inv = 1.f / (ptx::lds32(ssum + ((par * 2 + 0) * 144 + rr) * 4) + ptx::lds32(ssum + ((par * 2 + 1) * 144 + rr) * 4));
+      const unsigned long long inv2 = pk2(inv, inv);
+      auto pack_scaled = [&](uint32_t a, uint32_t b) {
+        float x, y;
+        upk2(fmul2(pk2(__uint_as_float(a), __uint_as_float(b)), inv2), x, y);
+        return at_pack<DT>(x, y);
+      };
       if (!tile) {
         uint32_t v[16];
         ptx::tmem_ld16(lane_base + AT_COL_O0 + half * 16, v);
@@ -235,10 +241,10 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)win * 144 + r) * p.ldo + head * 32 + half * 16);
 #pragma unroll
         for (int g = 0; g < 2; ++g)
-          dst[g] = make_uint4(at_pack<DT>(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv),
-                              at_pack<DT>(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv),
-                              at_pack<DT>(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv),
-                              at_pack<DT>(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv));
+          dst[g] = make_uint4(pack_scaled(v[8 * g], v[8 * g + 1]),
+                              pack_scaled(v[8 * g + 2], v[8 * g + 3]),
+                              pack_scaled(v[8 * g + 4], v[8 * g + 5]),
+                              pack_scaled(v[8 * g + 6], v[8 * g + 7]));
       } else if (half == 0) {       // rows 128-143 live in lanes 0-15 of quadrant 0: warp 8 writes all 32 dims
         uint32_t v[32];
         ptx::tmem_ld32(lane_base + AT_COL_O1, v);
@@ -247,10 +253,10 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)win * 144 + r) * p.ldo + head * 32);
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            dst[g] = make_uint4(at_pack<DT>(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv),
-                                at_pack<DT>(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv),
-                                at_pack<DT>(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv),
-                                at_pack<DT>(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv));
+            dst[g] = make_uint4(pack_scaled(v[8 * g], v[8 * g + 1]),
+                                pack_scaled(v[8 * g + 2], v[8 * g + 3]),
+                                pack_scaled(v[8 * g + 4], v[8 * g + 5]),
+                                pack_scaled(v[8 * g + 6], v[8 * g + 7]));
         }
       }
     };
@@ -279,26 +285,28 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       ptx::tc_fence_before();
       ptx::mbar_arrive(s_empty);
 
-      // ---- pass 1: s + bias (+ mask) kept in registers, partial row max ----
-      float sc[72];
+      // ---- pass 1: s + bias (+ mask) kept in registers as packed fp32 pairs (FADD2), partial row max ----
+      unsigned long long sc[36];
       float mx = -INFINITY;
 #pragma unroll
       for (int g = 0; g < 18; ++g) {
         const uint4 bq = ptx::lds128(brow + g * 16);       // 4 fp32 bias values
-        const uint32_t* bf = reinterpret_cast<const uint32_t*>(&bq);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int c = g * 4 + t;                         // key column within this half; 72 = 6 * 12 so kj = c % 12
-          const float a = __uint_as_float(c < 32 ? v0[c & 31] : c < 64 ? v1[c & 31] : v2[c & 7]);
-          sc[c] = a + __uint_as_float(bf[t]);
-        }
+        const int c = g * 4;                               // key column within this half; 72 = 6 * 12 so kj = c % 12
+        auto sv = [&](int cc) { return __uint_as_float(cc < 32 ? v0[cc & 31] : cc < 64 ? v1[cc & 31] : v2[cc & 7]); };
+        sc[2 * g] = fadd2(pk2(sv(c), sv(c + 1)), pk2(__uint_as_float(bq.x), __uint_as_float(bq.y)));
+        sc[2 * g + 1] = fadd2(pk2(sv(c + 2), sv(c + 3)), pk2(__uint_as_float(bq.z), __uint_as_float(bq.w)));
       }
       if (last_r || last_c) {      // warp-uniform: border windows of a shifted block only
+        const unsigned long long mk2[2] = {pk2(mk[0], mk[0]), pk2(mk[1], mk[1])};
 #pragma unroll
-        for (int c = 0; c < 72; ++c) sc[c] += mk[(c % 12) >= 6 ? 1 : 0];
+        for (int c2 = 0; c2 < 36; ++c2) sc[c2] = fadd2(sc[c2], mk2[((2 * c2) % 12) >= 6 ? 1 : 0]);
       }
 #pragma unroll
-      for (int c = 0; c < 72; c += 2) mx = fmaxf(mx, fmaxf(sc[c], sc[c + 1]));
+      for (int c2 = 0; c2 < 36; ++c2) {
+        float lo, hi;
+        upk2(sc[c2], lo, hi);
+        mx = fmaxf(mx, fmaxf(lo, hi));
+      }
       if (row_ok) ptx::sts32(smax + ((par * 2 + half) * 144 + r) * 4, mx);
       pair_bar_sync(pair);
       const float m = fmaxf(mx, ptx::lds32(smax + ((par * 2 + (half ^ 1)) * 144 + rr) * 4));
@@ -308,23 +316,30 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       if (i > 0) epilogue(i - 1);
 
       // ---- pass 2: p = exp2((s - max) * log2e), partial row sum, 16-bit P -> shared (K-major, 32B swizzle) ----
-      float sum = 0.f;
+      unsigned long long sum2 = pk2(0.f, 0.f);
+      const unsigned long long l2e2 = pk2(LOG2E, LOG2E), noff2 = pk2(-moff, -moff);
 #pragma unroll
       for (int g = 0; g < 9; ++g) {
         uint32_t packed[4];
-        {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float p0 = ex2(fmaf(sc[g * 8 + 2 * t], LOG2E, -moff)), p1 = ex2(fmaf(sc[g * 8 + 2 * t + 1], LOG2E, -moff));
-            sum += p0 + p1;
-            packed[t] = at_pack<DT>(p0, p1);
-          }
+        for (int t = 0; t < 4; ++t) {
+          float a0, a1;
+          upk2(fma2(sc[g * 4 + t], l2e2, noff2), a0, a1);
+          const float p0 = ex2(a0), p1 = ex2(a1);
+          sum2 = fadd2(sum2, pk2(p0, p1));
+          packed[t] = at_pack<DT>(p0, p1);
         }
         if (row_ok) {
           // keys [8*G, 8*G+8), G = 9*half + g: K step G/2, 16-byte chunk (G&1) of the row's 32 B, XOR row bit 2
           const int G = 9 * half + g, j16 = G >> 1, ch = (G & 1) ^ ((r >> 2) & 1);
           ptx::sts128(sP_a + j16 * AT_P_BLOCK + r * 32 + ch * 16, make_uint4(packed[0], packed[1], packed[2], packed[3]));
         }
+      }
+      float sum;
+      {
+        float s0, s1;
+        upk2(sum2, s0, s1);
+        sum = s0 + s1;
       }
       if (row_ok) ptx::sts32(ssum + ((par * 2 + half) * 144 + r) * 4, sum);
       ptx::fence_proxy_async_smem();

@@ -32,7 +32,7 @@ constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;
 #endif
 constexpr int TC_EPI_WARPS = BRN_EPI_WARPS;                               // two per TMEM lane quadrant (contiguous column parts; 12 warps measured slower)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;            // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+constexpr int TC_A_BYTES = (TC_BM + 16) * TC_BK * 2;   // 18 KB: a 16x8-pixel tile plus one halo row above and below (tap groups)
 constexpr int TC_B_BYTES = 256 * TC_BK * 2;     // 32 KB (BN <= 256)
 constexpr int TC_BIAS_LD = 288;                                // floats per accumulator stage (BN <= 256, padded to 32)
 constexpr int TC_EPI_BYTES = TC_EPI_WARPS * EPI_STAGE_BYTES + 2 * TC_BIAS_LD * 4;
@@ -61,6 +61,7 @@ struct TcGemmP {
   int m_tiles, n_tiles, BN;
   int taps, kw, pad, cblocks, cin_pad;
   int in_bf16;   // operand format: 1 = bf16, 0 = fp16
+  int tg;        // 3x3 tap groups: one A load of (16+2) x 8 pixels serves the three vertical taps of a kernel column
   int out_tiled; // fp32 out is [m_tile][N][128]
   EpiP epi;
   RowMap rm;
@@ -135,7 +136,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m_groups = (p.m_tiles + CL - 1) / CL;
   const int num_items = m_groups * p.n_tiles;
   const int item0 = blockIdx.x / CL, item_step = gridDim.x / CL;
-  const int kblocks = p.taps * p.cblocks;
+  const int kblocks = (p.tg ? 3 : p.taps) * p.cblocks;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int TW = 1 << p.tw_log2, TH = TC_BM >> p.tw_log2;
 
@@ -143,7 +144,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (ptx::elect_one()) {
       // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx_bytes = TC_A_BYTES + p.BN * TC_BK * 2;
+      const uint32_t tx_bytes = p.tg ? TC_A_BYTES + 3 * p.BN * TC_BK * 2 : TC_BM * TC_BK * 2 + p.BN * TC_BK * 2;
       const int b_rows = p.BN / CL;                           // rows of B this CTA loads (and multicasts)
       for (int item = item0; item < num_items; item += item_step) {
         const int m_tile = (item / p.n_tiles) * CL + rank, n_tile = item % p.n_tiles;
@@ -153,6 +154,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_wait_backoff(&empty[stage], phase ^ 1);
           ptx::mbar_expect_tx(&full[stage], tx_bytes);
           const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+          if (p.tg) {
+            // `tap` is the kernel column kx: the (TH+2) x TW box holds the input rows of all three vertical taps
+            ptx::tma_load_4d(sA + stage * TC_A_BYTES, &tmA, &full[stage], cb * TC_BK, x0 + tap - 1, y0 - 1, b);
+            const int bn = n_tile * p.BN + rank * b_rows;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              uint8_t* bdst = sB + stage * TC_B_BYTES + ky * p.BN * (TC_BK * 2) + rank * b_rows * (TC_BK * 2);
+              const int bk = (ky * 3 + tap) * p.cin_pad + cb * TC_BK;
+              if (CL > 1) ptx::tma_load_2d_mc(bdst, &tmB, &full[stage], bk, bn, (uint16_t)((1u << CL) - 1));
+              else ptx::tma_load_2d(bdst, &tmB, &full[stage], bk, bn);
+            }
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
           ptx::tma_load_4d(sA + stage * TC_A_BYTES, &tmA, &full[stage], cb * TC_BK, x0 + kx - p.pad, y0 + ky - p.pad, b);
           uint8_t* bdst = sB + stage * TC_B_BYTES + rank * b_rows * (TC_BK * 2);
@@ -178,9 +193,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tc_fence_after();
           const uint64_t a_desc = ptx::make_smem_desc(ptx::smem_u32(sA + stage * TC_A_BYTES), 16, 1024, ptx::SW_128B);
           const uint64_t b_desc = ptx::make_smem_desc(ptx::smem_u32(sB + stage * TC_B_BYTES), 16, 1024, ptx::SW_128B);
+          if (p.tg) {
+            // vertical tap ky = the same box read one pixel row (8 pixels = one 1024-byte swizzle atom) further down
+            const uint32_t b_step = (uint32_t)(p.BN * TC_BK * 2) >> 4;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)   // +32 B (= 2 in the >>4 address field) per K=16 step inside the 128B atom
-            ptx::umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                ptx::umma_f16_ss(d_tmem, a_desc + ky * (1024 >> 4) + 2 * k, b_desc + ky * b_step + 2 * k, idesc, (kb | ky | k) != 0);
+          } else {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)   // +32 B (= 2 in the >>4 address field) per K=16 step inside the 128B atom
+              ptx::umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
           // the stage is free once the MMAs of EVERY CTA that received the multicast have read it
           if (CL > 1) ptx::umma_commit_mc(&empty[stage], (uint16_t)((1u << CL) - 1));
           else ptx::umma_commit(&empty[stage]);
@@ -329,9 +354,17 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   BRN_CHECK(w.Cin == a.x.C, 5, "tc_gemm: weight/input channel mismatch");
   TcGemmP p{};
   p.B = a.x.B; p.H = a.x.H; p.W = a.x.W;
+  // 3x3 convs with few output channels are L2->SMEM bound when every tap re-loads its 128-pixel box (9 loads per
+  // channel block for <= 80 MMA columns): with 16x8-pixel tiles one (16+2) x 8 box serves the three vertical taps.
+  static const bool no_tg = [] { const char* v = getenv("BRN_GEMM_TG"); return v && v[0] == '0'; }();
+  const int bn0 = pick_bn(w.N);
+  const bool tg = !no_tg && w.kh == 3 && w.kw == 3 && a.pad == 1 && a.tile_w <= 0 && w.N <= bn0 &&
+                  3 * bn0 * TC_BK * 2 <= TC_B_BYTES && bn0 % 8 == 0 && a.x.W >= 8 && a.x.H >= 16;
   int tw = 1, lg = 0;
-  if (a.tile_w > 0) { while (tw < std::min(a.tile_w, TC_BM)) { tw <<= 1; ++lg; } }
+  if (tg) { tw = 8; lg = 3; }
+  else if (a.tile_w > 0) { while (tw < std::min(a.tile_w, TC_BM)) { tw <<= 1; ++lg; } }
   else { while (tw < std::min(a.x.W, TC_BM)) { tw <<= 1; ++lg; } }
+  p.tg = tg ? 1 : 0;
   p.tw_log2 = lg;
   p.out_tiled = a.out_tiled;
   BRN_CHECK(!a.out_tiled || (a.out.dt == F32 && !a.res.p && !a.rowmap.enabled && w.N <= 256), 5,
@@ -362,7 +395,7 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   const uint64_t ld2 = (uint64_t)a.x.ld * 2;
   uint64_t adims[4] = {(uint64_t)a.x.C, (uint64_t)a.x.W, (uint64_t)a.x.H, (uint64_t)a.x.B};
   uint64_t astr[3] = {ld2, ld2 * a.x.W, ld2 * a.x.W * a.x.H};
-  uint32_t abox[4] = {(uint32_t)TC_BK, (uint32_t)tw, (uint32_t)TH, 1};
+  uint32_t abox[4] = {(uint32_t)TC_BK, (uint32_t)tw, (uint32_t)(tg ? TH + 2 : TH), 1};
   CUtensorMap tmA = make_tmap_16(a.x.p, a.x.dt, 4, adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_128B);
   const uint64_t ktot = (uint64_t)w.taps() * w.cin_pad;
   uint64_t bdims[2] = {ktot, (uint64_t)w.N};
@@ -377,8 +410,8 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
 
   const double rows = (double)a.x.rows();
   char desc[128] = "";
-  if (ctx.kt) snprintf(desc, sizeof desc, "M=%lld N=%d K=%dx%d BN=%d tiles=%d act=%d res=%d odt=%d cl=%d", (long long)a.x.rows(),
-                       w.N, w.taps(), w.Cin, p.BN, p.m_tiles * p.n_tiles, a.act, a.res.p ? 1 : 0, a.out.dt, CL);
+  if (ctx.kt) snprintf(desc, sizeof desc, "M=%lld N=%d K=%dx%d BN=%d tiles=%d act=%d res=%d odt=%d cl=%d tg=%d", (long long)a.x.rows(),
+                       w.N, w.taps(), w.Cin, p.BN, p.m_tiles * p.n_tiles, a.act, a.res.p ? 1 : 0, a.out.dt, CL, p.tg);
   KScope ks(ctx, KC_GEMM_TC, 2.0 * rows * w.N * w.taps() * w.Cin,
             rows * a.x.C * 2 + rows * w.N * dsize(a.out.dt) + (double)w.N * w.taps() * w.cin_pad * 2, desc);
   // epilogue variant (the conditions mirror epi_warp_dyn's dispatch)

@@ -38,6 +38,15 @@ def main():
         gemm("dec1 conv1 1024->64", 0, 64, 1024, k=1, act=1, B=16, H=256, W=256)
         gemm("dec1 conv_out 64->192", 0, 192, 64, k=3, f32=True, B=16, H=256, W=256)
         gemm("lat2 384->384 res", 0, 384, 384, k=1, res=True, B=16, H=256, W=256)
+    if which == "tg":
+        gemm("dec1 conv_in 480->64", 0, 64, 480, k=3, act=1, B=16, H=256, W=256)
+        gemm("dec2 conv_in 960->64", 0, 64, 960, k=3, act=1, B=16, H=128, W=128)
+        gemm("dec3 conv_in 1920->64", 0, 64, 1920, k=3, act=1, B=16, H=64, W=64)
+        gemm("sq conv_in 5760->64", 0, 64, 5760, k=3, act=1, B=16, H=32, W=32)
+        gemm("ipt 48->64", 0, 64, 48, k=3, B=16, H=256, W=256)
+        gemm("gdt 384->16", 0, 16, 384, k=3, act=1, B=16, H=128, W=128)
+        gemm("k3 offmod N=27", 0, 27, 64, k=3, act=3, f32=True, B=16, H=256, W=256)
+        gemm("conv_out 64->192", 0, 192, 64, k=3, f32=True, B=16, H=256, W=256)
     if which == "lat":
         gemm("lat2 res16", 0, 384, 384, k=1, res=2, B=16, H=256, W=256)
         gemm("lat2 nores", 0, 384, 384, k=1, B=16, H=256, W=256)
