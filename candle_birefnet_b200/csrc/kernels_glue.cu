@@ -148,17 +148,22 @@ __device__ __forceinline__ uint32_t pk16(float a, float b, int dt) {
 // vector variant: 16-bit in == 16-bit out, 8 channels (16 bytes) per thread.  blockIdx.y = output row, blockIdx.z =
 // image: the row interpolation is block-uniform and the only per-thread division is t / C8 (the flat index math of
 // the scalar kernel was ~40 % of this kernel's instructions).
+constexpr int RS_ROWS = 4;
 template <int DT>
 __global__ void __launch_bounds__(256) resize_nhwc_vec8_kernel(ResizeP p) {
   const int C8 = p.C >> 3;
   const int t = blockIdx.x * 256 + threadIdx.x;
   if (t >= p.Wo * C8) return;
   const int ox = t / C8, c8 = t - ox * C8;
-  const int oy = blockIdx.y; const long long b = blockIdx.z;
-  int y0, y1, x0, x1; float ly, lx;
-  bilin_coord(oy, p.H, p.Ho, y0, y1, ly);
+  const long long b = blockIdx.z;
+  int x0, x1; float lx;
   bilin_coord(ox, p.W, p.Wo, x0, x1, lx);
   const uint16_t* xs = (const uint16_t*)p.x + b * p.H * p.W * p.ldx + c8 * 8;
+  // RS_ROWS consecutive output rows per thread: neighbouring output rows read the same two input rows (up-sampling), so
+  // the second to fourth row are served by L1 instead of L2 (the kernel was L2->SM bound at 4x the output bytes)
+  for (int oy = blockIdx.y * RS_ROWS; oy < min((int)(blockIdx.y + 1) * RS_ROWS, p.Ho); ++oy) {
+  int y0, y1; float ly;
+  bilin_coord(oy, p.H, p.Ho, y0, y1, ly);
   const uint4 a00 = __ldg(reinterpret_cast<const uint4*>(xs + ((long long)y0 * p.W + x0) * p.ldx));
   const uint4 a01 = __ldg(reinterpret_cast<const uint4*>(xs + ((long long)y0 * p.W + x1) * p.ldx));
   const uint4 a10 = __ldg(reinterpret_cast<const uint4*>(xs + ((long long)y1 * p.W + x0) * p.ldx));
@@ -166,17 +171,22 @@ __global__ void __launch_bounds__(256) resize_nhwc_vec8_kernel(ResizeP p) {
   const uint32_t *p00 = reinterpret_cast<const uint32_t*>(&a00), *p01 = reinterpret_cast<const uint32_t*>(&a01),
                  *p10 = reinterpret_cast<const uint32_t*>(&a10), *p11 = reinterpret_cast<const uint32_t*>(&a11);
   const float hx = 1.f - lx, hy = 1.f - ly;
+  const unsigned long long hx2 = pk2(hx, hx), lx2 = pk2(lx, lx), hy2 = pk2(hy, hy), ly2 = pk2(ly, ly);
   uint32_t o[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 f00 = up16(p00[j], DT), f01 = up16(p01[j], DT), f10 = up16(p10[j], DT), f11 = up16(p11[j], DT);
-    // same association as the scalar kernel / F.interpolate: (1-ly)*((1-lx)*v00 + lx*v01) + ly*(...)
-    const float ax = hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x);
-    const float ay = hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y);
+    // same association as the scalar kernel / F.interpolate: (1-ly)*((1-lx)*v00 + lx*v01) + ly*(...), two channels per
+    // instruction (FMUL2 / FFMA2): the kernel is issue-bound, not bandwidth-bound, with scalar fp32 math
+    const unsigned long long top = fma2(lx2, pk2(f01.x, f01.y), fmul2(hx2, pk2(f00.x, f00.y)));
+    const unsigned long long bot = fma2(lx2, pk2(f11.x, f11.y), fmul2(hx2, pk2(f10.x, f10.y)));
+    float ax, ay;
+    upk2(fma2(ly2, bot, fmul2(hy2, top)), ax, ay);
     o[j] = pk16(ax, ay, DT);
   }
   *reinterpret_cast<uint4*>((uint16_t*)p.out + ((b * p.Ho + oy) * (long long)p.Wo + ox) * p.ldo + c8 * 8) =
       make_uint4(o[0], o[1], o[2], o[3]);
+  }
 }
 
 void glue_resize_nhwc(const LaunchCtx& ctx, View in, View out) {
@@ -185,7 +195,7 @@ void glue_resize_nhwc(const LaunchCtx& ctx, View in, View out) {
   const bool vec = in.dt != F32 && in.dt == out.dt && in.C % 8 == 0 && in.ld % 8 == 0 && out.ld % 8 == 0 &&
                    (((uintptr_t)in.p | (uintptr_t)out.p) & 15) == 0;
   if (vec && out.H <= 65535 && in.B <= 65535) {
-    dim3 grid((out.W * (in.C / 8) + 255) / 256, out.H, in.B);
+    dim3 grid((out.W * (in.C / 8) + 255) / 256, (out.H + RS_ROWS - 1) / RS_ROWS, in.B);
     if (in.dt == BF16) resize_nhwc_vec8_kernel<BF16><<<grid, 256, 0, ctx.stream>>>(p);
     else resize_nhwc_vec8_kernel<F16><<<grid, 256, 0, ctx.stream>>>(p);
     BRN_CUDA(cudaGetLastError());

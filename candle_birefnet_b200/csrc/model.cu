@@ -400,8 +400,26 @@ void Model::finalize() {
     // final layer rewrite; done in double
     const HostTensor& wo = T("decoder.conv_out1.0.weight");   // [1, P + 48, 1, 1]
     const int P = lat(0) / 2;
-    std::vector<float> wp(wo.data.begin(), wo.data.begin() + P);
-    dw.out_wp = upload(wp);
+    {
+      // conv_out1 is linear in p1 and decoder_block1 ends in conv_out + BN with no activation (src/decoder.rs:137-140):
+      // w_p . (BN(conv3x3(a))) is ONE 3x3 conv 64 -> 1 with weights sum_n w_p[n] * sc[n] * W[n], so the 192-channel
+      // p1 is never materialised.
+      const std::string bp = "decoder.decoder_block1";
+      const HostTensor& cw = T(bp + ".conv_out.weight");          // [P, 64, 3, 3]
+      const HostTensor& cb = T(bp + ".conv_out.bias");
+      std::vector<double> sc, sh;
+      bn_affine(T(bp + ".bn_out.running_mean"), T(bp + ".bn_out.running_var"), T(bp + ".bn_out.weight"), T(bp + ".bn_out.bias"), sc, sh);
+      std::vector<float> wq((size_t)64 * 9), bq(1);
+      for (size_t i = 0; i < wq.size(); ++i) {
+        double acc = 0;
+        for (int n = 0; n < P; ++n) acc += (double)wo.data[n] * sc[n] * (double)cw.data[(size_t)n * 64 * 9 + i];
+        wq[i] = (float)acc;
+      }
+      double accb = 0;
+      for (int n = 0; n < P; ++n) accb += (double)wo.data[n] * ((double)cb.data[n] * sc[n] + sh[n]);
+      bq[0] = (float)accb;
+      dw.out_q = make_layer(1, 64, 3, 3, wq, &bq);
+    }
     const HostTensor& c1 = T("decoder.ipt_blk1.conv1.weight");     // [64,3,3,3]
     const HostTensor& co = T("decoder.ipt_blk1.conv_out.weight");  // [48,64,3,3]
     const HostTensor& cob = T("decoder.ipt_blk1.conv_out.bias");
@@ -597,7 +615,7 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
 }
 
 // BasicDecBlk::forward (src/decoder.rs:126-141) with ASPPDeformable (src/aspp.rs:303-333)
-void Model::run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out) {
+void Model::run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out, const LayerW* conv_out) {
   const int AD = dec_dtype();
   const size_t m0 = arena.mark();
   const int B = in.B, H = in.H, W = in.W;
@@ -636,7 +654,7 @@ void Model::run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out) {
   glue_aspp_pool_bias(ctx, sums, B, H * W, &w.gap, w.conv1_tail, w.bn1_shift, pb);
   View a = make_view(t.p, AD, B, H, W, 64);  // reuse t (all branches have consumed it)
   { GemmArgs g; g.x = cat; g.w = &w.conv1; g.bias = pb; g.bias_bstride = 64; g.act = ACT_RELU; g.out = a; op_gemm(ctx, g); }
-  { GemmArgs g; g.x = a; g.w = &w.conv_out; g.pad = 1; g.out = out; op_gemm(ctx, g); }
+  { GemmArgs g; g.x = a; g.w = conv_out ? conv_out : &w.conv_out; g.pad = 1; g.out = out; op_gemm(ctx, g); }
   arena.release(m0);
 }
 
@@ -664,11 +682,14 @@ void Model::run_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, V
         op_gemm(ctx, g); }
       arena.release(m1);
     }
-    // p1 (the last block's output) only feeds the 1x1 output conv: keep it in fp32 (no 16-bit rounding before the dot)
-    const int PD = d == 3 ? F32 : AD;
-    p = make_view(arena.alloc(px * dec_out[d] * dsize(PD)), PD, B, hh, ww, dec_out[d]);
+    if (d == 3) {
+      // p1 only feeds the 1x1 output conv, which is folded into the block's last conv: q = w_p . p1 directly (fp32)
+      p = make_view(arena.alloc(px * 4), F32, B, hh, ww, 1);
+      run_decblk(ctx, dw.dec[d], din, p, &dw.out_q);
+      break;
+    }
+    p = make_view(arena.alloc(px * dec_out[d] * dsize(AD)), AD, B, hh, ww, dec_out[d]);
     run_decblk(ctx, dw.dec[d], din, p);
-    if (d == 3) break;
     // GDT gate (src/birefnet.rs:327-329)
     {
       const size_t m1 = arena.mark();
@@ -687,9 +708,7 @@ void Model::run_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, V
     din = dn;
   }
   // final: conv_out1(cat(up(p1), ipt_blk1(x))) (src/birefnet.rs:372-375), rewritten (Appendix F.9)
-  float* q = (float*)arena.alloc((size_t)B * p.H * p.W * 4);
-  glue_dot1(ctx, p, dw.out_wp, q);
-  glue_final(ctx, img, B, H, W, dw.fin_tab, q, p.H, p.W, out, apply_sigmoid ? 1 : 0);
+  glue_final(ctx, img, B, H, W, dw.fin_tab, (const float*)p.p, p.H, p.W, out, apply_sigmoid ? 1 : 0);
 }
 
 void Model::run_squeeze_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, View X1, View X2, View X3,

@@ -70,7 +70,7 @@ struct DecoderW {
   LayerW gdt[3];                     // gdt_convs_{4,3,2}.0 + .1 folded
   float* gdt_attn_w[3] = {nullptr, nullptr, nullptr};
   float gdt_attn_b[3] = {0, 0, 0};
-  float* out_wp = nullptr;           // conv_out1 weights on p1 channels
+  LayerW out_q;                      // conv_out1 (p1 channels) folded into decoder_block1.conv_out + bn_out: 3x3, 64 -> 1
   float* fin_tab = nullptr;          // folded final-layer table (final_kernel.cu)
 };
 
@@ -160,7 +160,7 @@ struct Model {
   void run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, float* out, bool apply_sigmoid);
   void run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, View feats[4], const float* img2 = nullptr,
                     int H2 = 0, int W2 = 0, View* feats2 = nullptr);
-  void run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out);
+  void run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out, const LayerW* conv_out = nullptr);
   void run_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, View X1, View X2, View X3, View D4in,
                    float* out, bool apply_sigmoid);
   void run_squeeze_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, View X1, View X2, View X3,

@@ -54,30 +54,6 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(-a, ex2_approx(l), fmaxf(x, 0.f));
 }
 
-// sm_100 packed fp32 pairs (FFMA2 / FADD2: two lanes of math per issue slot; the epilogue is issue-bound)
-__device__ __forceinline__ unsigned long long pk2(float a, float b) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk2(unsigned long long v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
 __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
   unsigned long long r;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a0, a1)), "l"(pk2(b0, b1)));
