@@ -205,7 +205,8 @@ void glue_gate(const LaunchCtx&, View p, View g16, const float* w16, float b0);
 void glue_deform_sample_k1(const LaunchCtx&, View x, View om, int om_tiled, View out);
 void glue_dot1(const LaunchCtx&, View p, const float* w, float* out /*[rows]*/);
 void glue_final(const LaunchCtx&, const float* x_nchw, int B, int H, int W, const float* tab /*final_kernel.cu*/,
-                const float* q, int qh, int qw, float* out, int apply_sigmoid);
+                const float* tab_host /*same table, host copy*/, const float* q, int qh, int qw, float* out,
+                int apply_sigmoid);
 void build_final_table(const float* w1 /*[64][27]*/, const float* b1 /*[64]*/, const double* wc /*[64][9]*/, double bc,
                        float* tab /*[336]*/);
 void glue_copy_cast(const LaunchCtx&, View in, View out);

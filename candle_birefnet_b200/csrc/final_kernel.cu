@@ -18,7 +18,13 @@ namespace brn {
 
 // table layout (floats): [0,75) K5[ci][u][v] | [75,318) M[ij][ci*9+ky*3+kx] | [318,327) Bt[ij] | 327 b | 328 b + sum Bt
 constexpr int FIN_TAB = 336;
-constexpr int FT_W = 32, FT_H = 8;
+constexpr int FT_W = 128, FT_H = 8, FT_PX = 4;          // block = 128 x 8 outputs, FT_PX horizontally adjacent outputs per thread
+constexpr int FT_THREADS = (FT_W / FT_PX) * FT_H;
+constexpr int FT_LD = FT_W + 4;                          // 132 floats: 16-byte aligned rows
+
+// the 5x5 kernel and its bias travel in the kernel parameter (constant bank): the unrolled FFMAs read them as
+// immediate-offset constant operands instead of one shared-memory load per MAC
+struct FinK5 { float k[76]; };
 
 __device__ __forceinline__ void fin_bilin(int dst, int in, int out, int& i0, int& i1, float& l) {
   float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
@@ -28,66 +34,94 @@ __device__ __forceinline__ void fin_bilin(int dst, int in, int out, int& i0, int
   l = s - (float)i0;
 }
 
-__global__ void __launch_bounds__(FT_W * FT_H) final_kernel(const float* __restrict__ x, int H, int W,
-                                                            const float* __restrict__ tab, const float* __restrict__ q,
-                                                            int qh, int qw, float* __restrict__ out, int apply_sigmoid) {
-  __shared__ float xin[3][FT_H + 4][FT_W + 4];
+__global__ void __launch_bounds__(FT_THREADS) final_kernel(const float* __restrict__ x, int H, int W, const FinK5 k5,
+                                                           const float* __restrict__ tab, const float* __restrict__ q,
+                                                           int qh, int qw, float* __restrict__ out, int apply_sigmoid) {
+  __shared__ __align__(16) float xin[3][FT_H + 4][FT_LD];
   __shared__ float st[FIN_TAB];
   const int b = blockIdx.z, ty0 = blockIdx.y * FT_H, tx0 = blockIdx.x * FT_W, tid = threadIdx.x;
-  for (int i = tid; i < FIN_TAB; i += FT_W * FT_H) st[i] = tab[i];
-  for (int i = tid; i < 3 * (FT_H + 4) * (FT_W + 4); i += FT_W * FT_H) {
-    const int c = i / ((FT_H + 4) * (FT_W + 4)), r = i % ((FT_H + 4) * (FT_W + 4)), yy = r / (FT_W + 4), xx = r % (FT_W + 4);
+  for (int i = tid; i < FIN_TAB; i += FT_THREADS) st[i] = tab[i];
+  for (int i = tid; i < 3 * (FT_H + 4) * FT_LD; i += FT_THREADS) {
+    const int c = i / ((FT_H + 4) * FT_LD), r = i % ((FT_H + 4) * FT_LD), yy = r / FT_LD, xx = r % FT_LD;
     const int gy = ty0 + yy - 2, gx = tx0 + xx - 2;
     xin[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(x + ((long long)(b * 3 + c) * H + gy) * W + gx) : 0.f;
   }
   __syncthreads();
-  const int ly = tid / FT_W, lx = tid % FT_W;
-  const int gy = ty0 + ly, gx = tx0 + lx;
-  if (gy >= H || gx >= W) return;
-  float acc;
-  if (gy >= 1 && gy <= H - 2 && gx >= 1 && gx <= W - 2) {
-    acc = st[328];
+  const int ly = tid / (FT_W / FT_PX), lx = (tid % (FT_W / FT_PX)) * FT_PX;
+  const int gy = ty0 + ly, gx0 = tx0 + lx;
+  if (gy >= H || gx0 >= W) return;
+  int y0, y1; float fy;
+  fin_bilin(gy, qh, H, y0, y1, fy);
+  const float* qb = q + (long long)b * qh * qw;
+  auto finish = [&](int gx, float a) {       // + up(q), optional sigmoid
+    int x0, x1; float fx;
+    fin_bilin(gx, qw, W, x0, x1, fx);
+    const float up = (1.f - fy) * ((1.f - fx) * __ldg(qb + y0 * qw + x0) + fx * __ldg(qb + y0 * qw + x1)) +
+                     fy * ((1.f - fx) * __ldg(qb + y1 * qw + x0) + fx * __ldg(qb + y1 * qw + x1));
+    float v = a + up;
+    if (apply_sigmoid) v = 1.f / (1.f + expf(-v));
+    return v;
+  };
+  float* op = out + ((long long)b * H + gy) * W + gx0;
+  if (gy >= 1 && gy <= H - 2 && gx0 >= 1 && gx0 + FT_PX - 1 <= W - 2 && (W & 3) == 0) {
+    // interior: one 5x5x3 convolution per output; a thread's FT_PX outputs share each 8-float input row segment
+    float acc[FT_PX];
+#pragma unroll
+    for (int e = 0; e < FT_PX; ++e) acc[e] = k5.k[75];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-      for (int u = 0; u < 5; ++u)
+      for (int u = 0; u < 5; ++u) {
+        const float4 r0 = *reinterpret_cast<const float4*>(&xin[ci][ly + u][lx]);
+        const float4 r1 = *reinterpret_cast<const float4*>(&xin[ci][ly + u][lx + 4]);
+        const float row[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-        for (int v = 0; v < 5; ++v) acc = fmaf(st[ci * 25 + u * 5 + v], xin[ci][ly + u][lx + v], acc);
-  } else {
-    acc = st[327];
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) {
-        const int py = gy + i - 1, px = gx + j - 1;
-        if (py < 0 || py >= H || px < 0 || px >= W) continue;
-        const float* m = &st[75 + (i * 3 + j) * 27];
-        float s = st[318 + i * 3 + j];
+        for (int v = 0; v < 5; ++v)
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) s = fmaf(m[ci * 9 + ky * 3 + kx], xin[ci][ly + i + ky][lx + j + kx], s);
-        acc += s;
+          for (int e = 0; e < FT_PX; ++e) acc[e] = fmaf(k5.k[ci * 25 + u * 5 + v], row[e + v], acc[e]);
       }
+    *reinterpret_cast<float4*>(op) = make_float4(finish(gx0, acc[0]), finish(gx0 + 1, acc[1]), finish(gx0 + 2, acc[2]),
+                                                 finish(gx0 + 3, acc[3]));
+    return;
   }
-  int y0, y1, x0, x1; float fy, fx;
-  fin_bilin(gy, qh, H, y0, y1, fy);
-  fin_bilin(gx, qw, W, x0, x1, fx);
-  const float* qb = q + (long long)b * qh * qw;
-  const float up = (1.f - fy) * ((1.f - fx) * __ldg(qb + y0 * qw + x0) + fx * __ldg(qb + y0 * qw + x1)) +
-                   fy * ((1.f - fx) * __ldg(qb + y1 * qw + x0) + fx * __ldg(qb + y1 * qw + x1));
-  float v = acc + up;
-  if (apply_sigmoid) v = 1.f / (1.f + expf(-v));
-  out[((long long)b * H + gy) * W + gx] = v;
+  // image border (and the odd-width fallback): per-output path with the valid intermediate taps only
+  for (int e = 0; e < FT_PX; ++e) {
+    const int gx = gx0 + e;
+    if (gx >= W) break;
+    float a;
+    if (gy >= 1 && gy <= H - 2 && gx >= 1 && gx <= W - 2) {
+      a = st[328];
+      for (int ci = 0; ci < 3; ++ci)
+        for (int u = 0; u < 5; ++u)
+          for (int v = 0; v < 5; ++v) a = fmaf(st[ci * 25 + u * 5 + v], xin[ci][ly + u][lx + e + v], a);
+    } else {
+      a = st[327];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          const int py = gy + i - 1, px = gx + j - 1;
+          if (py < 0 || py >= H || px < 0 || px >= W) continue;
+          const float* m = &st[75 + (i * 3 + j) * 27];
+          float s = st[318 + i * 3 + j];
+          for (int ci = 0; ci < 3; ++ci)
+            for (int ky = 0; ky < 3; ++ky)
+              for (int kx = 0; kx < 3; ++kx) s = fmaf(m[ci * 9 + ky * 3 + kx], xin[ci][ly + i + ky][lx + e + j + kx], s);
+          a += s;
+        }
+    }
+    op[e] = finish(gx, a);
+  }
 }
 
-void glue_final(const LaunchCtx& ctx, const float* x, int B, int H, int W, const float* tab, const float* q, int qh,
-                int qw, float* out, int apply_sigmoid) {
+void glue_final(const LaunchCtx& ctx, const float* x, int B, int H, int W, const float* tab, const float* tab_host,
+                const float* q, int qh, int qw, float* out, int apply_sigmoid) {
   if (ctx.launches) ++*ctx.launches;
   if (ctx.dry) return;
   KScope ks(ctx, KC_GLUE, 2.0 * 75 * (double)B * H * W, 16.0 * B * H * W, "final");
+  FinK5 k5;
+  for (int i = 0; i < 75; ++i) k5.k[i] = tab_host[i];
+  k5.k[75] = tab_host[328];
   dim3 grid((W + FT_W - 1) / FT_W, (H + FT_H - 1) / FT_H, B);
-  final_kernel<<<grid, FT_W * FT_H, 0, ctx.stream>>>(x, H, W, tab, q, qh, qw, out, apply_sigmoid);
+  final_kernel<<<grid, FT_THREADS, 0, ctx.stream>>>(x, H, W, k5, tab, q, qh, qw, out, apply_sigmoid);
   BRN_CUDA(cudaGetLastError());
 }
 

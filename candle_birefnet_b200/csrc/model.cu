@@ -435,6 +435,7 @@ void Model::finalize() {
     std::vector<float> tab(336);
     build_final_table(c1.data.data(), T("decoder.ipt_blk1.conv1.bias").data.data(), wc.data(), bc, tab.data());
     dw.fin_tab = upload(tab);
+    dw.fin_tab_host = tab;
   }
   // host copies are no longer needed
   for (auto& t : tensors) { std::vector<float>().swap(t.data); }
@@ -708,7 +709,7 @@ void Model::run_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, V
     din = dn;
   }
   // final: conv_out1(cat(up(p1), ipt_blk1(x))) (src/birefnet.rs:372-375), rewritten (Appendix F.9)
-  glue_final(ctx, img, B, H, W, dw.fin_tab, (const float*)p.p, p.H, p.W, out, apply_sigmoid ? 1 : 0);
+  glue_final(ctx, img, B, H, W, dw.fin_tab, dw.fin_tab_host.data(), (const float*)p.p, p.H, p.W, out, apply_sigmoid ? 1 : 0);
 }
 
 void Model::run_squeeze_decoder(LaunchCtx& ctx, const float* img, int B, int H, int W, View X1, View X2, View X3,

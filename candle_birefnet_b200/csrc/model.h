@@ -72,6 +72,7 @@ struct DecoderW {
   float gdt_attn_b[3] = {0, 0, 0};
   LayerW out_q;                      // conv_out1 (p1 channels) folded into decoder_block1.conv_out + bn_out: 3x3, 64 -> 1
   float* fin_tab = nullptr;          // folded final-layer table (final_kernel.cu)
+  std::vector<float> fin_tab_host;   // host copy: the 5x5 kernel is passed to final_kernel as a launch parameter
 };
 
 struct ProfEntry {
