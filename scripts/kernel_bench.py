@@ -47,6 +47,13 @@ def main():
         gemm("gdt 384->16", 0, 16, 384, k=3, act=1, B=16, H=128, W=128)
         gemm("k3 offmod N=27", 0, 27, 64, k=3, act=3, f32=True, B=16, H=256, W=256)
         gemm("conv_out 64->192", 0, 192, 64, k=3, f32=True, B=16, H=256, W=256)
+    if which == "res":
+        gemm("s0 proj res", 1115136, 192, 192, res=True, f32=True)
+        gemm("s0 fc2 res", 1048576, 192, 768, res=True, f32=True)
+        gemm("s1 proj res", 278784, 384, 384, res=True, f32=True)
+        gemm("s1 fc2 res", 262144, 384, 1536, res=True, f32=True)
+        gemm("s2 proj res", 82944, 768, 768, res=True, f32=True)
+        gemm("s2 fc2 res", 65536, 768, 3072, res=True, f32=True)
     if which == "lat":
         gemm("lat2 res16", 0, 384, 384, k=1, res=2, B=16, H=256, W=256)
         gemm("lat2 nores", 0, 384, 384, k=1, B=16, H=256, W=256)

@@ -38,7 +38,7 @@ if bl.exists():
     js = [l for l in bl.read_text().splitlines() if l.startswith("{")]
     if js: bench = json.loads(js[-1])
 md = [f"# {tag}: ncu launch list of one bench step (batch 16, 1024^2, fp16 tensor-core path, direct launches)\n",
-      "Command: `BRN_CUDA_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -s 1932 -c 322 --csv python bench.py "
+      "Command: `BRN_CUDA_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -s 1926 -c 321 --csv python bench.py "
       "--steps 1 --warmup 3 --no-cpu-baseline --no-latency` (after the same command exited 0 without ncu).  Per-launch times under "
       "ncu are cold-cache and serialised: compare the SHARES with the live CUDA-event shares of `bench.py` (right column), not the absolutes.\n",
       f"{len(rows)} launches, {tot/1e3:.2f} ms summed.\n", "| class | launches | ms (ncu) | share (ncu) | share (bench.py CUDA events) |", "|---|---|---|---|---|"]
@@ -75,7 +75,7 @@ if rep.exists():
     dram = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
     M, N, K = 81920, 3072, 768
     alg = M * K * 2 + M * N * 2 + N * K * 2
-    json.dump({"kernel": "tc_gemm_kernel<2>, stage-2 fc1 + erf-GELU of the merged backbone pass (M=81920 N=3072 K=768, fp16 in/out)",
+    json.dump({"kernel": "tc_gemm_kernel<2, 3> (2-CTA cluster, GELU16 epilogue), stage-2 fc1 + erf-GELU of the merged backbone pass (M=81920 N=3072 K=768, fp16 in/out)",
                "dram_bytes_per_launch": dram, "algorithmic_bytes_per_launch": alg,
                "note": f"ncu --set full capture {tag}: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant GEMM "
                        f"(stage-2 fc1, 18 launches per step); algorithmic bytes of that launch = {alg/1e6:.0f} MB (A + out + W); part of the "
