@@ -232,11 +232,17 @@ __global__ void __launch_bounds__(256) image2patches_tiled_kernel(const float* _
   __shared__ __align__(16) uint16_t sm[32 * PITCH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = H / th, gw = W / tw, Cn = 3 * g * gw;
+  const int lg = (g == gw && (g & (g - 1)) == 0) ? 31 - __clz(g) : -1;
   const int tx0 = blockIdx.x * 32, ty = blockIdx.y; const long long b = blockIdx.z;
   for (int ch0 = 0; ch0 < Cn; ch0 += CH) {
     for (int j = warp; j < CH; j += 8) {
       const int ch = ch0 + j;
-      const int c = ch / (g * gw), r = ch - c * g * gw, gy = r / gw, gx = r - gy * gw;
+      int c, gy, gx;
+      if (lg >= 0) {            // the grid is 2^lg x 2^lg (always, for H, W multiples of 32): shifts instead of divisions
+        c = ch >> (2 * lg); gy = (ch >> lg) & (gw - 1); gx = ch & (gw - 1);
+      } else {
+        c = ch / (g * gw); const int r = ch - c * g * gw; gy = r / gw; gx = r - gy * gw;
+      }
       const float v = __ldg(x + ((b * 3 + c) * H + (gy * th + ty)) * (long long)W + gx * tw + tx0 + lane);
       uint16_t hv;
       if (odt == BF16) { __nv_bfloat16 t = __float2bfloat16(v); hv = *reinterpret_cast<uint16_t*>(&t); }
