@@ -109,6 +109,7 @@ struct DeformArgs {
   View om;                // [B,H,W,3*taps] fp32: 2*taps offsets (dy,dx interleaved) then taps modulators
   int om_tiled = 0;       // 1: om.p is [m_tile][3*taps][128] over 16x8-pixel tiles (tc_gemm out_tiled, tile_w 16)
   void* scratch = nullptr; // k = 1 only: [B*H*W, 64] elements of x.dt; when set the conv runs as sample kernel + tc_gemm
+  const LayerW* om_layer = nullptr;  // k = 1 with scratch: the sample kernel computes the offset conv itself (om unused)
   const LayerW* w = nullptr;
   const float* bias = nullptr;
   int act = ACT_NONE;
@@ -202,7 +203,8 @@ void glue_aspp_pool_bias(const LaunchCtx&, const float* part, int B, int HW, con
                          float* out /*[B][64]*/);
 void glue_gate(const LaunchCtx&, View p, View g16, const float* w16, float b0);
 // 1x1 deformable conv, sampling half: out[px, 0:64] = m(px) * bilinear(x, px + (dy, dx)) (torchvision semantics)
-void glue_deform_sample_k1(const LaunchCtx&, View x, View om, int om_tiled, View out);
+void glue_deform_sample_k1(const LaunchCtx&, View x, View om, int om_tiled, const LayerW* om_layer /*fused 1x1 offset conv or null*/,
+                           View out);
 void glue_dot1(const LaunchCtx&, View p, const float* w, float* out /*[rows]*/);
 void glue_final(const LaunchCtx&, const float* x_nchw, int B, int H, int W, const float* tab /*final_kernel.cu*/,
                 const float* tab_host /*same table, host copy*/, const float* q, int qh, int qw, float* out,

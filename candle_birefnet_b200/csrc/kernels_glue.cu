@@ -499,16 +499,41 @@ void glue_gate(const LaunchCtx& ctx, View p, View g16, const float* w16, float b
 // tc_deform_kernel has nothing to overlap with (its 4 epilogue warps become the pace setter), so the sampling runs
 // here (8 lanes x 16 bytes per pixel, same arithmetic as the fused kernel) and the contraction goes to tc_gemm.
 // ------------------------------------------------------------------------------------------------
-template <int DT>
+// FUSED: the 1x1 offset / modulator conv (3 outputs: dy, dx, 2*sigmoid(m); src/aspp.rs:58-99) is computed here from the
+// pixel's own 64 channels (8 lanes x 8 channels, 16-bit weights, fp32 accumulation, 3-step shuffle reduction) instead of
+// a 3-column GEMM launch plus a round trip of its output through HBM.
+template <int DT, bool FUSED>
 __global__ void __launch_bounds__(256) deform_sample_k1_kernel(const uint16_t* __restrict__ x, int ldx, int B, int H, int W,
                                                                const float* __restrict__ om, int ldom, int om_tiled,
+                                                               const uint16_t* __restrict__ omw, int omw_ld,
+                                                               const float* __restrict__ omb,
                                                                uint16_t* out, int ldo, long long total) {
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i >= total) return;
+  const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long i = FUSED ? min(i0, total - 1) : i0;      // FUSED: every lane takes part in the shuffles
+  if (!FUSED && i >= total) return;
   const int l8 = (int)(i & 7); const long long px = i >> 3;
   const int xx = (int)(px % W); const long long t = px / W; const int y = (int)(t % H); const long long b = t / H;
   float dy, dx, mk;
-  if (om_tiled) {
+  if (FUSED) {
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + px * ldx + l8 * 8));
+    const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xv);
+    float acc[3];
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      const uint4 wv = __ldg(reinterpret_cast<const uint4*>(omw + n * omw_ld + l8 * 8));
+      const uint32_t* ww = reinterpret_cast<const uint32_t*>(&wv);
+      float a = 0.f;
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt) {
+        const float2 xf = up16(xw[tt], DT), wf = up16(ww[tt], DT);
+        a = fmaf(xf.x, wf.x, a); a = fmaf(xf.y, wf.y, a);
+      }
+      a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2); a += __shfl_xor_sync(0xffffffffu, a, 4);
+      acc[n] = a + __ldg(omb + n);
+    }
+    dy = acc[0]; dx = acc[1]; mk = 2.f / (1.f + __expf(-acc[2]));
+    if (i0 >= total) return;
+  } else if (om_tiled) {
     const int tiles_x = (W + 15) / 16, tiles_y = (H + 7) / 8;
     const long long tile = (b * tiles_y + (y >> 3)) * tiles_x + (xx >> 4);
     const float* o = om + tile * 3 * 128 + ((y & 7) * 16 + (xx & 15));
@@ -559,16 +584,28 @@ __global__ void __launch_bounds__(256) deform_sample_k1_kernel(const uint16_t* _
   *reinterpret_cast<uint4*>(out + px * ldo + l8 * 8) = r;
 }
 
-void glue_deform_sample_k1(const LaunchCtx& ctx, View x, View om, int om_tiled, View out) {
+void glue_deform_sample_k1(const LaunchCtx& ctx, View x, View om, int om_tiled, const LayerW* om_layer, View out) {
   GLUE_LAUNCH_PROLOGUE(ctx);
   BRN_CHECK(x.C == 64 && x.dt != F32 && out.dt == x.dt && x.ld % 8 == 0 && out.ld % 8 == 0, 5, "deform_sample_k1: layout");
   const long long total = x.rows() * 8;
-  if (x.dt == BF16)
-    deform_sample_k1_kernel<BF16><<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>((const uint16_t*)x.p, x.ld, x.B, x.H, x.W,
-        (const float*)om.p, om.ld, om_tiled, (uint16_t*)out.p, out.ld, total);
-  else
-    deform_sample_k1_kernel<F16><<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>((const uint16_t*)x.p, x.ld, x.B, x.H, x.W,
-        (const float*)om.p, om.ld, om_tiled, (uint16_t*)out.p, out.ld, total);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (om_layer) {
+    BRN_CHECK(om_layer->N == 3 && om_layer->Cin == 64 && om_layer->taps() == 1 && om_layer->bias && om_layer->w16(x.dt), 5,
+              "deform_sample_k1: fused offset conv is 64 -> 3, 1x1, with bias");
+    const uint16_t* w = (const uint16_t*)om_layer->w16(x.dt);
+    if (x.dt == BF16)
+      deform_sample_k1_kernel<BF16, true><<<grid, 256, 0, ctx.stream>>>((const uint16_t*)x.p, x.ld, x.B, x.H, x.W, nullptr, 0, 0,
+          w, om_layer->cin_pad, om_layer->bias, (uint16_t*)out.p, out.ld, total);
+    else
+      deform_sample_k1_kernel<F16, true><<<grid, 256, 0, ctx.stream>>>((const uint16_t*)x.p, x.ld, x.B, x.H, x.W, nullptr, 0, 0,
+          w, om_layer->cin_pad, om_layer->bias, (uint16_t*)out.p, out.ld, total);
+  } else if (x.dt == BF16) {
+    deform_sample_k1_kernel<BF16, false><<<grid, 256, 0, ctx.stream>>>((const uint16_t*)x.p, x.ld, x.B, x.H, x.W,
+        (const float*)om.p, om.ld, om_tiled, nullptr, 0, nullptr, (uint16_t*)out.p, out.ld, total);
+  } else {
+    deform_sample_k1_kernel<F16, false><<<grid, 256, 0, ctx.stream>>>((const uint16_t*)x.p, x.ld, x.B, x.H, x.W,
+        (const float*)om.p, om.ld, om_tiled, nullptr, 0, nullptr, (uint16_t*)out.p, out.ld, total);
+  }
   BRN_CUDA(cudaGetLastError());
 }
 

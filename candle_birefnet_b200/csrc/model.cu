@@ -26,7 +26,7 @@ void op_deform(const LaunchCtx& ctx, const DeformArgs& a) {
   if (tc && a.scratch && a.w->taps() == 1) {
     // 1x1: sampling kernel + ordinary 1x1 implicit GEMM (same rounding points as the fused kernel)
     View smp = make_view(a.scratch, a.x.dt, a.x.B, a.x.H, a.x.W, 64);
-    glue_deform_sample_k1(ctx, a.x, a.om, a.om_tiled, smp);
+    glue_deform_sample_k1(ctx, a.x, a.om, a.om_tiled, a.om_layer, smp);
     GemmArgs g; g.x = smp; g.w = a.w; g.bias = a.bias; g.act = a.act; g.out = a.out;
     BRN_CHECK(tc_gemm_supported(g), 5, "deform k=1: tcgen05 GEMM unavailable");
     tc_gemm(ctx, g);
@@ -640,8 +640,13 @@ void Model::run_decblk(LaunchCtx& ctx, const DecBlkW& w, View in, View out, cons
       g.out = om;
       if (tiled) { g.tile_w = 16; g.out_tiled = 1; d.om_tiled = 1; BRN_CHECK(tc_gemm_supported(g), 5, "om conv: tcgen05 path unavailable"); }
       d.om = om;
-      if (tiled && k == 1) d.scratch = arena.alloc(px * 64 * dsize(AD));
-      op_gemm(ctx, g);
+      if (tiled && k == 1) {
+        // 1x1 branch: the sampler computes its own three offset / modulator values (no om conv launch)
+        d.scratch = arena.alloc(px * 64 * dsize(AD));
+        d.om_layer = &w.br[b].om;
+      } else {
+        op_gemm(ctx, g);
+      }
       if (tiled) BRN_CHECK(tc_deform_supported(d), 5, "deform: tcgen05 path unavailable");
       op_deform(ctx, d);
       arena.release(m1);

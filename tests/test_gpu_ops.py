@@ -64,7 +64,9 @@ def test_linear_epilogues(act, precision):
 
 
 @pytest.mark.parametrize("C,O,k,H,W", [(64, 64, 3, 32, 32), (64, 256, 1, 16, 24), (64, 147, 7, 16, 16), (224, 64, 3, 64, 64),
-                                        (48, 64, 3, 20, 12), (128, 16, 3, 8, 8)])
+                                        (48, 64, 3, 20, 12), (128, 16, 3, 8, 8),
+                                        # 3x3 tap-group mode (N <= 80, 16x8-pixel tiles): ragged tiles, N = 80 / 16 / 1
+                                        (96, 80, 3, 24, 40), (64, 16, 3, 40, 24), (64, 1, 3, 32, 16), (480, 64, 3, 17, 9)])
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_conv2d(C, O, k, H, W, precision):
     rng = np.random.default_rng(C + O + k)
