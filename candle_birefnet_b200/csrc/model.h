@@ -113,7 +113,7 @@ struct Model {
 
   // CUDA-graph replay of the forward: the launch sequence of run_forward for one (buffers, shape, mode) key is
   // captured the second time the key is seen (the first call runs eagerly: lazy module loading, attribute setup) and
-  // replayed afterwards, which removes ~460 launch gaps per pass (batch-1 latency is launch-bound otherwise).
+  // replayed afterwards, which removes ~310 launch gaps per pass (batch-1 latency is launch-bound otherwise).
   struct GraphKey {
     const void* x; const void* out; void* arena_base; int B, H, W, precision, deform, sigmoid;
     bool operator==(const GraphKey& o) const {
