@@ -188,6 +188,10 @@ struct LnArgs {
   View out;                // destination rows
   int mode = LN_PLAIN;
   int hp = 0, wp = 0, shift = 0;  // LN_WINDOW
+  // LN_WINDOW over two grids in one launch: output rows >= split gather from a second [B,h2,w2,C] grid whose tokens
+  // start at row tok2 of x (the merged full + half resolution backbone pass)
+  long long split = 0, tok2 = 0;
+  int h2 = 0, w2 = 0, hp2 = 0, wp2 = 0;
 };
 void glue_layernorm(const LaunchCtx&, const LnArgs&);
 void glue_patch_im2col(const LaunchCtx&, const float* x_nchw, int B, int H, int W, int patch, View out);

@@ -19,7 +19,18 @@ struct LnP {
   void* out; int odt; int ldo;
   int mode, hp, wp, shift;
   long long rows;
+  // LN_WINDOW over two token grids in one launch (merged two-resolution pass): window rows >= split belong to grid 2
+  long long split, tok2;
+  int h2, w2, hp2, wp2;
 };
+
+__device__ __forceinline__ long long ln_window_token(const LnP& p, long long m) {
+  if (p.split > 0 && m >= p.split) {
+    const long long t = window_row_to_token(m - p.split, p.h2, p.w2, p.hp2, p.wp2, p.shift);
+    return t < 0 ? t : t + p.tok2;
+  }
+  return window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift);
+}
 
 __device__ __forceinline__ void ln_store4(void* out, int odt, long long idx, float4 v) {
   if (odt == F32) {
@@ -48,7 +59,7 @@ __global__ void __launch_bounds__(256) ln_vec_kernel(LnP p) {
   if (p.mode == LN_PLAIN) {
     src[0] = m * p.ldx;
   } else if (p.mode == LN_WINDOW) {
-    const long long tok = window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift);
+    const long long tok = ln_window_token(p, m);
     if (tok < 0) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
@@ -177,7 +188,7 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_bulk_kernel(LnP p, int R, long
         continue;
       }
       long long tok = -1;
-      if (lane < R && m < p.rows) tok = p.mode == LN_WINDOW ? window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift) : m;
+      if (lane < R && m < p.rows) tok = p.mode == LN_WINDOW ? ln_window_token(p, m) : m;
       const long long prev = __shfl_up_sync(0xffffffffu, tok, 1);
       const bool valid = tok >= 0;
       const bool start = valid && (lane == 0 || prev < 0 || tok != prev + 1 || p.ldx != n);
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(256) ln_generic_kernel(LnP p) {
   if (p.mode == LN_PLAIN) {
     src[0] = m * p.ldx;
   } else if (p.mode == LN_WINDOW) {
-    long long tok = window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift);
+    long long tok = ln_window_token(p, m);
     if (tok < 0) {
       for (int e = lane; e < n; e += 32) st_elem(p.out, p.odt, m * p.ldo + e, 0.f);
       return;
@@ -348,6 +359,7 @@ void glue_layernorm(const LaunchCtx& ctx, const LnArgs& a) {
   p.out = a.out.p; p.odt = a.out.dt; p.ldo = a.out.ld;
   p.mode = a.mode; p.hp = a.hp; p.wp = a.wp; p.shift = a.shift;
   p.rows = a.out.rows();
+  p.split = a.split; p.tok2 = a.tok2; p.h2 = a.h2; p.w2 = a.w2; p.hp2 = a.hp2; p.wp2 = a.wp2;
   const int n = a.mode == LN_MERGE ? 4 * a.x.C : a.x.C;
   KScope ks(ctx, KC_LN, 0.0, (double)p.rows * n * (4 + dsize(a.out.dt)),
             a.mode == LN_WINDOW ? "ln_window" : a.mode == LN_MERGE ? "ln_merge" : "ln_plain");

@@ -559,10 +559,10 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
       const size_t mb = arena.mark();
       // norm1 -> pad -> roll -> partition (src/swin.rs:355-380) in one gather kernel per grid
       View xw = make_view(arena.alloc((size_t)Tpt * Ci * dsize(AD)), AD, 1, 1, (int)Tpt, Ci);
-      for (int s = 0; s < nseg; ++s) {
-        LnArgs l; l.x = grid_view(s); l.gamma = bw.n1g; l.beta = bw.n1b;
-        l.out = make_view((char*)xw.p + (size_t)(s ? Tp[0] : 0) * Ci * dsize(AD), AD, 1, 1, (int)Tp[s], Ci);
-        l.mode = LN_WINDOW; l.hp = hp[s]; l.wp = wp[s]; l.shift = shift;
+      {
+        LnArgs l; l.x = grid_view(0); l.gamma = bw.n1g; l.beta = bw.n1b; l.out = xw;
+        l.mode = LN_WINDOW; l.hp = hp[0]; l.wp = wp[0]; l.shift = shift;
+        if (nseg > 1) { l.split = Tp[0]; l.tok2 = T[0]; l.h2 = h[1]; l.w2 = w[1]; l.hp2 = hp[1]; l.wp2 = wp[1]; }
         glue_layernorm(ctx, l);
       }
       View qkv = make_view(arena.alloc((size_t)Tpt * 3 * Ci * dsize(AD)), AD, 1, 1, (int)Tpt, 3 * Ci);
