@@ -10,17 +10,19 @@
 //   warp 10  : one elected thread issues TMA (Q,K,V tiles of the window-ordered qkv matrix, 64B-swizzled, 3 stages)
 //              and all tcgen05.mma:  S = Q K^T (M=128 tiles over the 144 queries, N=144, K=32) into TMEM, then
 //              O = P V (M=128 x2, N=32, K=144; V is the MN-major B operand straight from the TMA tile).
-//   warps 0-9: softmax.  Every query row is split between TWO threads (keys 0-71 / 72-143), so a thread keeps its 72
-//              scores in registers: S is read from TMEM once and released immediately, which lets the MMA warp
-//              compute S of the NEXT window while this one is in its exp phase.  warps 0-3 / 4-7: rows 0-127
-//              (TMEM lane quadrant = warp % 4), warps 8 / 9: rows 128-143.  Row max and row sum are combined
-//              through shared memory (a named barrier per warp pair); the -100 shift mask is applied only in the
-//              border windows; P (bf16/fp16) goes to shared memory in the 32B-swizzled K-major layout the
-//              P V MMA reads; 1/sum is applied to O in the epilogue, which is deferred into the next unit's softmax
-//              so the P V latency is hidden.
-//   TMEM   : S0 [0,144) rows 0-127 | S1a [144,288) rows 128-143 in lanes 0-15 (for warp 8) | S1b [288,432) the same
-//            rows in lanes 32-47 (A tile started 32 rows earlier; for warp 9, whose quadrant is lanes 32-63) |
-//            O0 [432,464) | O1 [464,496).
+//   warps 0-14: softmax.  Every query row is split between THREE threads (keys 0-47 / 48-95 / 96-143), so a thread
+//              keeps its 48 scores in registers: S is read from TMEM once and released immediately, which lets the MMA
+//              warp compute S of the NEXT window while this one is in its exp phase.  warps 0-3 / 4-7 / 8-11: rows
+//              0-127 (TMEM lane quadrant = warp % 4), warps 12 / 13 / 14: rows 128-143.  The kernel is bound by the
+//              dependent chain of a softmax thread (TMEM load -> bias -> max -> exchange -> exp -> pack -> store), not
+//              by issue slots or the MUFU pipe: 15 warps of 48 scores instead of 10 of 72 shorten the chain by a third
+//              and put four warps on every SMSP.  Row max and row sum are combined through shared memory (a named
+//              barrier per warp trio); the -100 shift mask is applied only in the border windows; P (bf16/fp16) goes
+//              to shared memory in the 32B-swizzled K-major layout the P V MMA reads; 1/sum is applied to O in the
+//              epilogue, which is deferred into the next unit's softmax so the P V latency is hidden.
+//   TMEM   : S0 [0,144) rows 0-127 | S1 [144,288): rows 128-143 against key third t in columns [144+48t, 192+48t),
+//            lanes 0-15 of lane quadrant t (A tile started at query row 128-32t; for warp 12+t) | O0 [288,320) |
+//            O1 [320,352).
 // Bound: MUFU (144*144 exp per unit = 1296 clk at 16/clk/SM) vs ~650 clk of tensor work per unit.
 #include <cuda.h>
 
@@ -37,8 +39,8 @@ CUtensorMap make_tmap_16(const void* base, int dt, int rank, const uint64_t* dim
                          const uint32_t* box, CUtensorMapSwizzle swz);
 int device_sm_count();
 
-constexpr int AT_SOFT_WARPS = 10;
-constexpr int AT_SOFT_THREADS = 32 * AT_SOFT_WARPS;      // 320
+constexpr int AT_SOFT_WARPS = 15;                        // 12 for query rows 0-127 (3 per TMEM lane quadrant) + 3 for rows 128-143
+constexpr int AT_SOFT_THREADS = 32 * AT_SOFT_WARPS;      // 480
 constexpr int AT_THREADS = AT_SOFT_THREADS + 32;         // + control warp
 constexpr int AT_BIAS_LD = 148;                          // fp32 elements per bias row (592 B: conflict-free 16-byte row reads)
 constexpr int AT_BIAS_BYTES = 144 * AT_BIAS_LD * 4;      // 85,248
@@ -48,9 +50,9 @@ constexpr int AT_STAGE_BYTES = 3 * AT_TILE_BYTES;        // 27,648
 constexpr int AT_STAGES = 3;
 constexpr int AT_P_BLOCK = 144 * 32;                     // one K=16 step of P: 4,608
 constexpr int AT_P_REGION = 44 * 1024;                   // 9 blocks (41,472) + over-read slack of the 16-row tile
-constexpr int AT_STAT_BYTES = 2 * 2 * 2 * 144 * 4;       // {max,sum} x parity x half x row
+constexpr int AT_STAT_BYTES = 2 * 2 * 3 * 144 * 4;       // {max,sum} x parity x third x row
 constexpr int AT_SMEM = AT_BIAS_REGION + AT_STAGES * AT_STAGE_BYTES + AT_P_REGION + AT_STAT_BYTES + 256 + 1024;
-constexpr uint32_t AT_COL_S0 = 0, AT_COL_S1A = 144, AT_COL_S1B = 288, AT_COL_O0 = 432, AT_COL_O1 = 464;
+constexpr uint32_t AT_COL_S0 = 0, AT_COL_S1 = 144, AT_COL_O0 = 288, AT_COL_O1 = 320;
 
 struct AttnP {
   const float* bias32p;          // [heads][144][148] fp32
@@ -91,7 +93,7 @@ __device__ __forceinline__ void tmem_wait8(uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ void soft_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(AT_SOFT_THREADS) : "memory"); }
 // the two warps that share a set of query rows (key halves 0 / 1) exchange their partial row max through shared memory
-__device__ __forceinline__ void pair_bar_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory"); }
+__device__ __forceinline__ void pair_bar_sync(int pair) { asm volatile("bar.sync %0, 96;" ::"r"(2 + pair) : "memory"); }
 
 template <int DT>
 __device__ __forceinline__ uint32_t at_pack(float a, float b) { return DT == BF16 ? pack_bf16x2(a, b) : pack_f16x2(a, b); }
@@ -103,7 +105,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
   uint8_t* sBias = smem;
   uint8_t* sQKV = smem + AT_BIAS_REGION;
   uint8_t* sP = sQKV + AT_STAGES * AT_STAGE_BYTES;
-  float* sStat = (float*)(sP + AT_P_REGION);                 // smax[par][half][row], then ssum[par][half][row]
+  float* sStat = (float*)(sP + AT_P_REGION);                 // smax[par][third][row], then ssum[par][third][row]
   uint64_t* bars = (uint64_t*)((uint8_t*)sStat + AT_STAT_BYTES);
   uint64_t* qkv_full = bars;        // [3]
   uint64_t* qkv_empty = bars + 3;   // [3]
@@ -140,6 +142,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       ptx::bulk_load(sBias, p.bias32p + (size_t)head * 144 * AT_BIAS_LD, AT_BIAS_BYTES, bias_bar);
       const uint32_t is_bf = DT == BF16 ? 1u : 0u;
       const uint32_t idesc_s = ptx::make_idesc_16(128, 144, 0, 0, is_bf);   // S = Q K^T : both K-major
+      const uint32_t idesc_s1 = ptx::make_idesc_16(128, 48, 0, 0, is_bf);   // rows 128-143 against one key third
       const uint32_t idesc_o = ptx::make_idesc_16(128, 32, 0, 1, is_bf);    // O = P V   : V is MN-major
       auto load_unit = [&](int i) {
         const int s = i % AT_STAGES, win = w_first + i * w_step;
@@ -151,15 +154,22 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       };
       auto issue_s = [&](int i) {
         const uint32_t q_addr = ptx::smem_u32(sQKV + (i % AT_STAGES) * AT_STAGE_BYTES), k_addr = q_addr + AT_TILE_BYTES;
-        // K-major, 64B swizzle: 8-row groups 512 B apart; +32 B per K=16 step.  A tiles start at query rows 0 / 128 / 96.
-        const uint32_t a_row[3] = {0, 128, 96};
-        const uint32_t d_col[3] = {AT_COL_S0, AT_COL_S1A, AT_COL_S1B};
+        // K-major, 64B swizzle: 8-row groups 512 B apart; +32 B per K=16 step.
+        // S0: query rows 0-127 x all 144 keys.  S1 (rows 128-143), once per key third t: the A tile starts at query
+        // row 128 - 32 t, so the 16 rows land in lanes 0-15 of TMEM lane quadrant t (the quadrant of softmax warp
+        // 12 + t), against keys [48 t, 48 t + 48) only (N = 48).
         const uint64_t b = ptx::make_smem_desc(k_addr, 16, 512, ptx::SW_64B);
+        {
+          const uint64_t a = ptx::make_smem_desc(q_addr, 16, 512, ptx::SW_64B);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) ptx::umma_f16_ss(tmem_base + AT_COL_S0, a + 2 * k, b + 2 * k, idesc_s, k);
+        }
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          const uint64_t a = ptx::make_smem_desc(q_addr + a_row[t] * 64, 16, 512, ptx::SW_64B);
+          const uint64_t a = ptx::make_smem_desc(q_addr + (128 - 32 * t) * 64, 16, 512, ptx::SW_64B);
+          const uint64_t bt = ptx::make_smem_desc(k_addr + t * 48 * 64, 16, 512, ptx::SW_64B);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) ptx::umma_f16_ss(tmem_base + d_col[t], a + 2 * k, b + 2 * k, idesc_s, k);
+          for (int k = 0; k < 2; ++k) ptx::umma_f16_ss(tmem_base + AT_COL_S1 + 48 * t, a + 2 * k, bt + 2 * k, idesc_s1, k);
         }
         ptx::umma_commit(s_full);
       };
@@ -204,30 +214,31 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
     }
   } else if (n_units > 0) {
     // ===== softmax + epilogue =====
-    const int tile = warp >= 8 ? 1 : 0;
-    const int half = tile ? warp - 8 : warp >> 2;              // keys [72*half, 72*half + 72)
+    const int tile = warp >= 12 ? 1 : 0;
+    const int third = tile ? warp - 12 : warp >> 2;            // keys [48*third, 48*third + 48)
     const int quad = warp & 3;
-    const int pair = tile ? 4 : quad;                          // warps (q, q+4) and (8, 9) share query rows
+    const int pair = tile ? 4 : quad;                          // warps (q, q+4, q+8) and (12, 13, 14) share query rows
     const int r = tile ? 128 + lane : quad * 32 + lane;        // query row (>= 144 for the idle lanes of warps 8, 9)
     const bool row_ok = r < 144;
     const int rr = row_ok ? r : 143;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t s_col = (tile ? (half ? AT_COL_S1B : AT_COL_S1A) : AT_COL_S0) + half * 72;
+    const uint32_t s_col = (tile ? AT_COL_S1 : AT_COL_S0) + third * 48;
     const int qi = rr / 12, qj = rr % 12;
     const float LOG2E = 1.4426950408889634f;
     // all shared-memory traffic of this role goes through explicit shared-space instructions
-    const uint32_t smax = ptx::smem_u32(sStat);                // [par][half][144]
-    const uint32_t ssum = smax + 2 * 2 * 144 * 4;
+    const uint32_t smax = ptx::smem_u32(sStat);                // [par][third][144]
+    const uint32_t ssum = smax + 2 * 3 * 144 * 4;
     const uint32_t sP_a = ptx::smem_u32(sP);
     const int nw = p.nwh * p.nww;
     ptx::mbar_wait(bias_bar, 0);
-    const uint32_t brow = ptx::smem_u32(sBias) + rr * AT_BIAS_LD * 4 + half * 288;
+    const uint32_t brow = ptx::smem_u32(sBias) + rr * AT_BIAS_LD * 4 + third * 192;
 
     auto epilogue = [&](int j) {   // O(j) / sum(j) -> 16-bit, head-major channel (src/swin.rs:306-307)
       const int par = j & 1, win = w_first + j * w_step;
       ptx::mbar_wait(o_full, par);
       ptx::tc_fence_after();
-      const float inv = 1.f / (ptx::lds32(ssum + ((par * 2 + 0) * 144 + rr) * 4) + ptx::lds32(ssum + ((par * 2 + 1) * 144 + rr) * 4));
+      const float inv = 1.f / (ptx::lds32(ssum + ((par * 3 + 0) * 144 + rr) * 4) + ptx::lds32(ssum + ((par * 3 + 1) * 144 + rr) * 4) +
+                               ptx::lds32(ssum + ((par * 3 + 2) * 144 + rr) * 4));
       const unsigned long long inv2 = pk2(inv, inv);
       auto pack_scaled = [&](uint32_t a, uint32_t b) {
         float x, y;
@@ -235,17 +246,18 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         return at_pack<DT>(x, y);
       };
       if (!tile) {
+        if (third == 2) return;       // the 32 output dims of a row are written by its first two warps, 16 each
         uint32_t v[16];
-        ptx::tmem_ld16(lane_base + AT_COL_O0 + half * 16, v);
+        ptx::tmem_ld16(lane_base + AT_COL_O0 + third * 16, v);
         tmem_wait_dep(v);
-        uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)win * 144 + r) * p.ldo + head * 32 + half * 16);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)win * 144 + r) * p.ldo + head * 32 + third * 16);
 #pragma unroll
         for (int g = 0; g < 2; ++g)
           dst[g] = make_uint4(pack_scaled(v[8 * g], v[8 * g + 1]),
                               pack_scaled(v[8 * g + 2], v[8 * g + 3]),
                               pack_scaled(v[8 * g + 4], v[8 * g + 5]),
                               pack_scaled(v[8 * g + 6], v[8 * g + 7]));
-      } else if (half == 0) {       // rows 128-143 live in lanes 0-15 of quadrant 0: warp 8 writes all 32 dims
+      } else if (third == 0) {      // rows 128-143 live in lanes 0-15 of quadrant 0: warp 12 writes all 32 dims
         uint32_t v[32];
         ptx::tmem_ld32(lane_base + AT_COL_O1, v);
         tmem_wait32(v);
@@ -263,53 +275,55 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
 
     for (int i = 0; i < n_units; ++i) {
       const int par = i & 1, win = w_first + i * w_step;
-      // analytic shift mask (src/swin.rs:603-655): only the last window row / column mixes regions.  This thread's
-      // keys all have (ki >= 6) == half; kj >= 6 depends on the key column.  Interior windows take the mask-free path.
+      // analytic shift mask (src/swin.rs:603-655): only the last window row / column mixes regions.  Key c of this
+      // third sits at ki = 4*third + c/12, kj = c%12; interior windows take the mask-free path.
       int g_nwh = p.nwh, g_nww = p.nww, g_nw = nw, g_win = win;
       if (p.split_win > 0 && win >= p.split_win) { g_nwh = p.nwh2; g_nww = p.nww2; g_nw = p.nwh2 * p.nww2; g_win = win - p.split_win; }
       const int wl = g_win % g_nw, wi = wl / g_nww, wj = wl - wi * g_nww;
       const bool last_r = p.shift > 0 && wi == g_nwh - 1, last_c = p.shift > 0 && wj == g_nww - 1;
-      const bool rmask = last_r && ((half != 0) != (qi >= 6));
-      float mk[2];   // index = (kj >= 6)
-      mk[0] = (rmask || (last_c && (qj >= 6))) ? -100.0f : 0.0f;
-      mk[1] = (rmask || (last_c && (qj < 6))) ? -100.0f : 0.0f;
 
       // ---- scores: TMEM -> registers once, then hand the S region back to the MMA warp ----
-      uint32_t v0[32], v1[32], v2[8];
+      uint32_t v0[32], v1[16];
       ptx::mbar_wait(s_full, par);
       ptx::tc_fence_after();
       ptx::tmem_ld32(lane_base + s_col, v0);
-      ptx::tmem_ld32(lane_base + s_col + 32, v1);
-      tmem_ld8(lane_base + s_col + 64, v2);
-      tmem_wait32(v0); tmem_wait32(v1); tmem_wait8(v2);
+      ptx::tmem_ld16(lane_base + s_col + 32, v1);
+      tmem_wait32(v0); tmem_wait_dep(v1);
       ptx::tc_fence_before();
       ptx::mbar_arrive(s_empty);
 
       // ---- pass 1: s + bias (+ mask) kept in registers as packed fp32 pairs (FADD2), partial row max ----
-      unsigned long long sc[36];
+      unsigned long long sc[24];
       float mx = -INFINITY;
 #pragma unroll
-      for (int g = 0; g < 18; ++g) {
+      for (int g = 0; g < 12; ++g) {
         const uint4 bq = ptx::lds128(brow + g * 16);       // 4 fp32 bias values
-        const int c = g * 4;                               // key column within this half; 72 = 6 * 12 so kj = c % 12
-        auto sv = [&](int cc) { return __uint_as_float(cc < 32 ? v0[cc & 31] : cc < 64 ? v1[cc & 31] : v2[cc & 7]); };
+        const int c = g * 4;                               // key column within this third; 48 = 4 * 12 so kj = c % 12
+        auto sv = [&](int cc) { return __uint_as_float(cc < 32 ? v0[cc & 31] : v1[cc & 15]); };
         sc[2 * g] = fadd2(pk2(sv(c), sv(c + 1)), pk2(__uint_as_float(bq.x), __uint_as_float(bq.y)));
         sc[2 * g + 1] = fadd2(pk2(sv(c + 2), sv(c + 3)), pk2(__uint_as_float(bq.z), __uint_as_float(bq.w)));
       }
       if (last_r || last_c) {      // warp-uniform: border windows of a shifted block only
-        const unsigned long long mk2[2] = {pk2(mk[0], mk[0]), pk2(mk[1], mk[1])};
 #pragma unroll
-        for (int c2 = 0; c2 < 36; ++c2) sc[c2] = fadd2(sc[c2], mk2[((2 * c2) % 12) >= 6 ? 1 : 0]);
+        for (int kr = 0; kr < 4; ++kr) {                   // the four key rows of this third
+          const bool rmask = last_r && ((4 * third + kr >= 6) != (qi >= 6));
+          const float m0 = (rmask || (last_c && (qj >= 6))) ? -100.0f : 0.0f;    // kj < 6
+          const float m1 = (rmask || (last_c && (qj < 6))) ? -100.0f : 0.0f;     // kj >= 6
+          const unsigned long long mk0 = pk2(m0, m0), mk1 = pk2(m1, m1);
+#pragma unroll
+          for (int c2 = 0; c2 < 6; ++c2) sc[kr * 6 + c2] = fadd2(sc[kr * 6 + c2], c2 >= 3 ? mk1 : mk0);
+        }
       }
 #pragma unroll
-      for (int c2 = 0; c2 < 36; ++c2) {
+      for (int c2 = 0; c2 < 24; ++c2) {
         float lo, hi;
         upk2(sc[c2], lo, hi);
         mx = fmaxf(mx, fmaxf(lo, hi));
       }
-      if (row_ok) ptx::sts32(smax + ((par * 2 + half) * 144 + r) * 4, mx);
+      if (row_ok) ptx::sts32(smax + ((par * 3 + third) * 144 + r) * 4, mx);
       pair_bar_sync(pair);
-      const float m = fmaxf(mx, ptx::lds32(smax + ((par * 2 + (half ^ 1)) * 144 + rr) * 4));
+      const float m = fmaxf(fmaxf(ptx::lds32(smax + ((par * 3 + 0) * 144 + rr) * 4), ptx::lds32(smax + ((par * 3 + 1) * 144 + rr) * 4)),
+                            ptx::lds32(smax + ((par * 3 + 2) * 144 + rr) * 4));
       const float moff = m * LOG2E;
 
       // ---- deferred epilogue of the previous unit (its P V finished long ago); also frees the P buffer ----
@@ -319,7 +333,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       unsigned long long sum2 = pk2(0.f, 0.f);
       const unsigned long long l2e2 = pk2(LOG2E, LOG2E), noff2 = pk2(-moff, -moff);
 #pragma unroll
-      for (int g = 0; g < 9; ++g) {
+      for (int g = 0; g < 6; ++g) {
         uint32_t packed[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -330,8 +344,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
           packed[t] = at_pack<DT>(p0, p1);
         }
         if (row_ok) {
-          // keys [8*G, 8*G+8), G = 9*half + g: K step G/2, 16-byte chunk (G&1) of the row's 32 B, XOR row bit 2
-          const int G = 9 * half + g, j16 = G >> 1, ch = (G & 1) ^ ((r >> 2) & 1);
+          // keys [8*G, 8*G+8), G = 6*third + g: K step G/2, 16-byte chunk (G&1) of the row's 32 B, XOR row bit 2
+          const int G = 6 * third + g, j16 = G >> 1, ch = (G & 1) ^ ((r >> 2) & 1);
           ptx::sts128(sP_a + j16 * AT_P_BLOCK + r * 32 + ch * 16, make_uint4(packed[0], packed[1], packed[2], packed[3]));
         }
       }
@@ -341,7 +355,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         upk2(sum2, s0, s1);
         sum = s0 + s1;
       }
-      if (row_ok) ptx::sts32(ssum + ((par * 2 + half) * 144 + r) * 4, sum);
+      if (row_ok) ptx::sts32(ssum + ((par * 3 + third) * 144 + r) * 4, sum);
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
