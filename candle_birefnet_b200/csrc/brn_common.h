@@ -152,6 +152,8 @@ struct LaunchCtx {
   long long* launches = nullptr;
   bool force_simt = false;
   KTimer* kt = nullptr;
+  float* splitk = nullptr;     // scratch for split-K partial sums (tc_gemm decides per launch); null: never split
+  size_t splitk_bytes = 0;
 };
 
 struct KScope {
@@ -175,6 +177,7 @@ void simt_attention(const LaunchCtx&, const AttnArgs&);
 // ---- tcgen05 kernels ----
 bool tc_gemm_supported(const GemmArgs&);
 void tc_gemm(const LaunchCtx&, const GemmArgs&);
+size_t tc_gemm_splitk_scratch_bytes(int batch);   // LaunchCtx::splitk size that every split-K launch of a batch fits in
 void tc_attention(const LaunchCtx&, const AttnArgs&);
 bool tc_deform_supported(const DeformArgs&);
 void tc_deform(const LaunchCtx&, const DeformArgs&);

@@ -61,11 +61,14 @@ struct TcGemmP {
   int m_tiles, n_tiles, BN;
   int taps, kw, pad, cblocks, cin_pad;
   int in_bf16;   // operand format: 1 = bf16, 0 = fp16
+  int ksplit, kb_per;   // split-K (tiny M, long K): K blocks [ks*kb_per, (ks+1)*kb_per) per work item; fp32 partials
+  long long rows_total; //   of split ks go to out rows [ks*rows_total, ...); a reduce kernel adds bias / activation
   int tg;        // 3x3 tap groups: one A load of (16+2) x 8 pixels serves the three vertical taps of a kernel column
   int out_tiled; // fp32 out is [m_tile][N][128]
   EpiP epi;
   RowMap rm;
   FastDiv fd_nt, fd_tpi, fd_tx;        // n_tiles, tiles_x * tiles_y, tiles_x
+  FastDiv fd_ks;                       // ksplit
   FastDiv fd_rows1, fd_nww1;           // row map, first grid: rows per image (windows * 144), windows per row
   FastDiv fd_rows2, fd_nww2;           // second grid (merged two-resolution pass)
 };
@@ -134,7 +137,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   // work items: (m_group, n_tile); this CTA's M tile is m_group * CL + rank
   const int m_groups = (p.m_tiles + CL - 1) / CL;
-  const int num_items = m_groups * p.n_tiles;
+  const int num_items = m_groups * p.n_tiles * p.ksplit;
   const int item0 = blockIdx.x / CL, item_step = gridDim.x / CL;
   const int kblocks = (p.tg ? 3 : p.taps) * p.cblocks;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -147,10 +150,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tx_bytes = p.tg ? TC_A_BYTES + 3 * p.BN * TC_BK * 2 : TC_BM * TC_BK * 2 + p.BN * TC_BK * 2;
       const int b_rows = p.BN / CL;                           // rows of B this CTA loads (and multicasts)
       for (int item = item0; item < num_items; item += item_step) {
-        const int m_tile = (item / p.n_tiles) * CL + rank, n_tile = item % p.n_tiles;
+        const int it2 = item / p.ksplit, ks = item - it2 * p.ksplit;
+        const int kb0 = ks * p.kb_per, kb1 = min(kblocks, kb0 + p.kb_per);
+        const int m_tile = (it2 / p.n_tiles) * CL + rank, n_tile = it2 % p.n_tiles;
         const int b = m_tile / tiles_per_img, r = m_tile - b * tiles_per_img;   // b >= B for the odd tail: TMA zero-fills
         const int y0 = (r / p.tiles_x) * TH, x0 = (r % p.tiles_x) * TW;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait_backoff(&empty[stage], phase ^ 1);
           ptx::mbar_expect_tx(&full[stage], tx_bytes);
           const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
@@ -188,7 +193,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::mbar_wait_backoff(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int ks = item % p.ksplit;
+        const int kbn = min(kblocks, (ks + 1) * p.kb_per) - ks * p.kb_per;     // K blocks of this work item
+        for (int kb = 0; kb < kbn; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
           const uint64_t a_desc = ptx::make_smem_desc(ptx::smem_u32(sA + stage * TC_A_BYTES), 16, 1024, ptx::SW_128B);
@@ -226,14 +233,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool o32 = p.epi.odt == F32;
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = item0; item < num_items; item += item_step) {
-      const int mg = (int)p.fd_nt.div((uint32_t)item);
-      const int m_tile = mg * CL + rank, n_tile = item - mg * p.n_tiles;
+      const int it2 = (int)p.fd_ks.div((uint32_t)item), ks = item - it2 * p.ksplit;
+      const int mg = (int)p.fd_nt.div((uint32_t)it2);
+      const int m_tile = mg * CL + rank, n_tile = it2 - mg * p.n_tiles;
       const int b = (int)p.fd_tpi.div((uint32_t)m_tile), r = m_tile - b * tiles_per_img;
       const int ty = (int)p.fd_tx.div((uint32_t)r), tx = r - ty * p.tiles_x;
       const int y = ty * TH + (row >> p.tw_log2), x = tx * TW + (row & (TW - 1));
       const bool valid = m_tile < p.m_tiles && y < p.H && x < p.W;
       long long orow = valid ? ((long long)b * p.H + y) * p.W + x : -1;
       if (valid && p.rm.enabled) orow = rowmap_token_fd(p, orow);
+      if (valid) orow += ks * p.rows_total;
       const int n0 = n_tile * p.BN;
       const int nch = min(p.BN, p.epi.N - n0 + 15) >> 4;     // 16-column chunks of this tile that hold real columns
       const int gsz = o32 ? 1 : 2;                           // 16-bit output: keep the split on 32-column granules
@@ -347,10 +356,59 @@ static int pick_bn(int N) {
   return best;
 }
 
-void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
-  if (ctx.launches) ++*ctx.launches;
-  if (ctx.dry) return;
+// split-K tail: out[m, n] = act(sum_s part[s][m][n] + bias[n]) in a fixed order (deterministic), 4 columns per thread
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int S, long long rows, int N,
+                                                            const float* __restrict__ bias, int act, void* out, int odt,
+                                                            int ldo) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int n4 = N >> 2;
+  if (i >= rows * n4) return;
+  const long long m = i / n4; const int n = (int)(i - m * n4) * 4;
+  float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < S; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(part + ((long long)s * rows + m) * N + n));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (act == ACT_RELU) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+  if (odt == F32) {
+    float* o = (float*)out + m * ldo + n;
+    o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
+  } else {
+    uint16_t* o = (uint16_t*)out + m * ldo + n;
+    const uint32_t lo = odt == BF16 ? pack_bf16x2(acc.x, acc.y) : pack_f16x2(acc.x, acc.y);
+    const uint32_t hi = odt == BF16 ? pack_bf16x2(acc.z, acc.w) : pack_f16x2(acc.z, acc.w);
+    o[0] = (uint16_t)lo; o[1] = (uint16_t)(lo >> 16); o[2] = (uint16_t)hi; o[3] = (uint16_t)(hi >> 16);
+  }
+}
+
+// Split-K plan: with very few output tiles per image (decoder convs at 32x32: 8 tiles, 270 K stages each) a handful of
+// SMs walks a long K loop while the rest idle at small batch.  The decision and the split depend on the PER-IMAGE
+// geometry only, never on the batch size, so an image's result does not depend on what it is batched with.
+// Returns the number of K splits (1 = none) and the K blocks per split.
+constexpr int SPLITK_MAX = 16, SPLITK_MAX_TILES = 16, SPLITK_MAX_N = 64;
+size_t tc_gemm_splitk_scratch_bytes(int batch) {
+  return (size_t)batch * SPLITK_MAX * SPLITK_MAX_TILES * TC_BM * SPLITK_MAX_N * 4;
+}
+static int plan_splitk(const LaunchCtx& ctx, const GemmArgs& a, int tiles_per_img, int n_tiles, int kblocks, int* kb_per) {
+  static const bool off = [] { const char* v = getenv("BRN_GEMM_SPLITK"); return v && v[0] == '0'; }();
+  *kb_per = kblocks;
   const LayerW& w = *a.w;
+  if (off || !ctx.splitk || a.out_tiled || a.rowmap.enabled || a.res.p || a.bias_bstride != 0 || w.N % 4 != 0 ||
+      w.N > SPLITK_MAX_N || (a.act != ACT_NONE && a.act != ACT_RELU) || tiles_per_img * n_tiles > SPLITK_MAX_TILES ||
+      kblocks < 16)
+    return 1;
+  int S = std::min(SPLITK_MAX, kblocks / 4);
+  const int per = (kblocks + S - 1) / S;
+  S = (kblocks + per - 1) / per;
+  if (S < 2) return 1;
+  BRN_CHECK((size_t)S * (size_t)a.x.rows() * w.N * 4 <= ctx.splitk_bytes, 2, "tc_gemm: split-K scratch too small");
+  *kb_per = per;
+  return S;
+}
+
+void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
+  const LayerW& w = *a.w;
+  if (ctx.launches) ++*ctx.launches;
   BRN_CHECK(w.Cin == a.x.C, 5, "tc_gemm: weight/input channel mismatch");
   TcGemmP p{};
   p.B = a.x.B; p.H = a.x.H; p.W = a.x.W;
@@ -376,7 +434,16 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   p.BN = pick_bn(w.N);
   p.n_tiles = (w.N + p.BN - 1) / p.BN;
   p.taps = w.taps(); p.kw = w.kw; p.pad = a.pad; p.cin_pad = w.cin_pad; p.cblocks = w.cin_pad / TC_BK;
-  p.epi = make_epi(w.N, a.bias ? a.bias : w.bias, a.bias_bstride, a.act, a.act_from, a.res, a.out);
+  // split-K: decided from shapes only, so the plan pass (which stops here) counts the reduce launch as well
+  const int kblocks = (tg ? 3 : w.taps()) * p.cblocks;
+  int kb_per = kblocks;
+  const int S = plan_splitk(ctx, a, p.tiles_x * p.tiles_y, p.n_tiles, kblocks, &kb_per);
+  if (S > 1 && ctx.launches) ++*ctx.launches;
+  if (ctx.dry) return;
+  p.ksplit = S; p.kb_per = kb_per; p.rows_total = a.x.rows(); p.fd_ks = FastDiv((uint32_t)S);
+  const View part = S > 1 ? make_view(ctx.splitk, F32, 1, 1, (int)(S * a.x.rows()), w.N) : View{};
+  if (S > 1) p.epi = make_epi(w.N, nullptr, 0, ACT_NONE, 0, View{}, part);
+  else p.epi = make_epi(w.N, a.bias ? a.bias : w.bias, a.bias_bstride, a.act, a.act_from, a.res, a.out);
   p.rm = a.rowmap;
   p.fd_nt = FastDiv((uint32_t)p.n_tiles);
   p.fd_tpi = FastDiv((uint32_t)(p.tiles_x * p.tiles_y));
@@ -415,9 +482,10 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   KScope ks(ctx, KC_GEMM_TC, 2.0 * rows * w.N * w.taps() * w.Cin,
             rows * a.x.C * 2 + rows * w.N * dsize(a.out.dt) + (double)w.N * w.taps() * w.cin_pad * 2, desc);
   // epilogue variant (the conditions mirror epi_warp_dyn's dispatch)
-  const bool o32 = a.out.dt == F32;
+  const bool o32 = S > 1 || a.out.dt == F32;
   int ek = EK_GENERIC;
-  if (a.out_tiled) ek = (a.act == ACT_2SIGMOID_TAIL) ? EK_SIG32_TILED : EK_GENERIC;
+  if (S > 1) ek = EK_NONE32;
+  else if (a.out_tiled) ek = (a.act == ACT_2SIGMOID_TAIL) ? EK_SIG32_TILED : EK_GENERIC;
   else if (!a.res.p) {
     if (!o32) ek = a.act == ACT_NONE ? EK_NONE16 : a.act == ACT_RELU ? EK_RELU16 : a.act == ACT_GELU ? EK_GELU16 : EK_GENERIC;
     else ek = a.act == ACT_NONE ? EK_NONE32 : EK_GENERIC;
@@ -426,7 +494,7 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
 
   auto launch = [&](auto kern) {
     BRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    const int items = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;
+    const int items = ((p.m_tiles + CL - 1) / CL) * p.n_tiles * p.ksplit;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CL * std::min(items, sms / CL));
     cfg.blockDim = dim3(TC_THREADS);
@@ -446,6 +514,12 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   }
 #undef TC_EK_CASE
   BRN_CUDA(cudaGetLastError());
+  if (S > 1) {
+    const long long rows = a.x.rows(), work = rows * (w.N / 4);
+    splitk_reduce_kernel<<<(unsigned)((work + 255) / 256), 256, 0, ctx.stream>>>(
+        (const float*)ctx.splitk, S, rows, w.N, a.bias ? a.bias : w.bias, a.act, a.out.p, a.out.dt, a.out.ld);
+    BRN_CUDA(cudaGetLastError());
+  }
 }
 
 }  // namespace brn

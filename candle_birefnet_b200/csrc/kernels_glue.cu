@@ -233,8 +233,12 @@ __global__ void __launch_bounds__(256) image2patches_tiled_kernel(const float* _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = H / th, gw = W / tw, Cn = 3 * g * gw;
   const int lg = (g == gw && (g & (g - 1)) == 0) ? 31 - __clz(g) : -1;
-  const int tx0 = blockIdx.x * 32, ty = blockIdx.y; const long long b = blockIdx.z;
-  for (int ch0 = 0; ch0 < Cn; ch0 += CH) {
+  // one CH-channel chunk per block (blockIdx.z = image * chunks + chunk): at batch 1 the 32x32 level has only 32
+  // pixel strips, far too few blocks when each of them walks all 3072 channels
+  const int nchunks = Cn / CH;
+  const int tx0 = blockIdx.x * 32, ty = blockIdx.y; const long long b = blockIdx.z / nchunks;
+  {
+    const int ch0 = (int)(blockIdx.z % nchunks) * CH;
     for (int j = warp; j < CH; j += 8) {
       const int ch = ch0 + j;
       int c, gy, gx;
@@ -262,20 +266,20 @@ __global__ void __launch_bounds__(256) image2patches_tiled_kernel(const float* _
 void glue_image2patches(const LaunchCtx& ctx, const float* x, int B, int H, int W, int th, int tw, View out) {
   GLUE_LAUNCH_PROLOGUE(ctx);
   const int Cn = 3 * (H / th) * (W / tw);
-  if (out.dt != F32 && tw % 32 == 0 && out.ld % 2 == 0 && ((uintptr_t)out.p & 3) == 0 && th <= 65535 && B <= 65535) {
-    dim3 grid(tw / 32, th, B);
+  if (out.dt != F32 && tw % 32 == 0 && out.ld % 2 == 0 && ((uintptr_t)out.p & 3) == 0 && th <= 65535 && (long long)B * (Cn / 48) <= 65535) {
+    auto grid_for = [&](int ch) { return dim3(tw / 32, th, B * (Cn / ch)); };
     if (Cn % 256 == 0) {
-      image2patches_tiled_kernel<256><<<grid, 256, 0, ctx.stream>>>(x, H, W, th, tw, (uint16_t*)out.p, out.dt, out.ld);
+      image2patches_tiled_kernel<256><<<grid_for(256), 256, 0, ctx.stream>>>(x, H, W, th, tw, (uint16_t*)out.p, out.dt, out.ld);
       BRN_CUDA(cudaGetLastError());
       return;
     }
     if (Cn % 192 == 0) {
-      image2patches_tiled_kernel<192><<<grid, 256, 0, ctx.stream>>>(x, H, W, th, tw, (uint16_t*)out.p, out.dt, out.ld);
+      image2patches_tiled_kernel<192><<<grid_for(192), 256, 0, ctx.stream>>>(x, H, W, th, tw, (uint16_t*)out.p, out.dt, out.ld);
       BRN_CUDA(cudaGetLastError());
       return;
     }
     if (Cn == 48) {
-      image2patches_tiled_kernel<48><<<grid, 256, 0, ctx.stream>>>(x, H, W, th, tw, (uint16_t*)out.p, out.dt, out.ld);
+      image2patches_tiled_kernel<48><<<grid_for(48), 256, 0, ctx.stream>>>(x, H, W, th, tw, (uint16_t*)out.p, out.dt, out.ld);
       BRN_CUDA(cudaGetLastError());
       return;
     }

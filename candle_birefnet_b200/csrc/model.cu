@@ -737,6 +737,9 @@ static bool env_flag(const char* n) { const char* v = getenv(n); return v && v[0
 void Model::run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, float* out, bool apply_sigmoid) {
   const int AD = dec_dtype();
   const size_t m0 = arena.mark();
+  // scratch for split-K partial sums (small batches: the 32x32-level decoder convs have 8 output tiles per image)
+  ctx.splitk_bytes = tc_gemm_splitk_scratch_bytes(B);
+  ctx.splitk = (float*)arena.alloc(ctx.splitk_bytes);
   int hs[4], ws[4];
   for (int i = 0; i < 4; ++i) { hs[i] = H / (4 << i); ws[i] = W / (4 << i); }
   View X[4];

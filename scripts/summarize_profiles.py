@@ -38,7 +38,7 @@ if bl.exists():
     js = [l for l in bl.read_text().splitlines() if l.startswith("{")]
     if js: bench = json.loads(js[-1])
 md = [f"# {tag}: ncu launch list of one bench step (batch 16, 1024^2, fp16 tensor-core path, direct launches)\n",
-      "Command: `BRN_CUDA_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -s 1722 -c 287 --csv python bench.py "
+      "Command: `BRN_CUDA_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -s 1746 -c 291 --csv python bench.py "
       "--steps 1 --warmup 3 --no-cpu-baseline --no-latency` (after the same command exited 0 without ncu).  Per-launch times under "
       "ncu are cold-cache and serialised: compare the SHARES with the live CUDA-event shares of `bench.py` (right column), not the absolutes.\n",
       f"{len(rows)} launches, {tot/1e3:.2f} ms summed.\n", "| class | launches | ms (ncu) | share (ncu) | share (bench.py CUDA events) |", "|---|---|---|---|---|"]
