@@ -218,7 +218,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
     const int third = tile ? warp - 12 : warp >> 2;            // keys [48*third, 48*third + 48)
     const int quad = warp & 3;
     const int pair = tile ? 4 : quad;                          // warps (q, q+4, q+8) and (12, 13, 14) share query rows
-    const int r = tile ? 128 + lane : quad * 32 + lane;        // query row (>= 144 for the idle lanes of warps 8, 9)
+    const int r = tile ? 128 + lane : quad * 32 + lane;        // query row (>= 144 for the idle lanes of warps 12-14)
     const bool row_ok = r < 144;
     const int rr = row_ok ? r : 143;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
