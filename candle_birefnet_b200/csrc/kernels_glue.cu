@@ -425,14 +425,27 @@ __global__ void __launch_bounds__(256) aspp_pool_bias_kernel(const float* part, 
     mean[t] = s / (float)HW;
   }
   __syncthreads();
-  float s = bg[t];
-  for (int c = 0; c < 64; ++c) s = fmaf(wg[t * 64 + c], mean[c], s);
-  x5[t] = fmaxf(s, 0.f);
+  // both mat-vecs with coalesced weight rows and a fixed shuffle tree per output (one block per image: at batch 1 this
+  // kernel is pure latency, and a thread-per-output loop walks 64 / 256 strided loads in sequence)
+  const int warp = t >> 5, lane = t & 31;
+  const float m0 = mean[lane], m1 = mean[lane + 32];
+#pragma unroll 8
+  for (int o = warp * 32; o < warp * 32 + 32; ++o) {
+    float s = fmaf(wg[o * 64 + lane], m0, wg[o * 64 + lane + 32] * m1);
+    s = warp_sum(s);
+    if (lane == 0) x5[o] = fmaxf(s + bg[o], 0.f);
+  }
   __syncthreads();
-  if (t < 64) {
-    float o = shift[t];
-    for (int j = 0; j < 256; ++j) o = fmaf(tail[t * 256 + j], x5[j], o);
-    out[b * 64 + t] = o;
+  float xv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) xv[k] = x5[lane + 32 * k];
+#pragma unroll
+  for (int o = warp * 8; o < warp * 8 + 8; ++o) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = fmaf(tail[o * 256 + lane + 32 * k], xv[k], s);
+    s = warp_sum(s);
+    if (lane == 0) out[b * 64 + o] = s + shift[o];
   }
 }
 
