@@ -69,6 +69,7 @@ def lib() -> C.CDLL:
     for name in ("brn_forward_logits", "brn_forward"):
         getattr(L, name).argtypes = [vp, vp, i32, i32, i32, C.c_int, vp, C.c_int, vp]
     L.brn_backbone_forward.argtypes = [vp, vp, i32, i32, i32, C.c_int, C.POINTER(vp), C.c_int, vp]
+    L.brn_features_forward.argtypes = [vp, vp, i32, i32, i32, C.c_int, C.POINTER(vp), C.c_int, vp]
     L.brn_decoder_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_int, vp, vp]
     L.brn_window_attention.argtypes = [C.c_int, C.c_int, vp, vp, i32, i32, i32, i32, i32, vp]
     L.brn_deform_conv2d.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]

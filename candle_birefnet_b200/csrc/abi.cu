@@ -156,6 +156,14 @@ brn_status brn_backbone_forward(brn_model* m, const float* x, int32_t B, int32_t
   });
 }
 
+brn_status brn_features_forward(brn_model* m, const float* x, int32_t B, int32_t H, int32_t W, int x_is_device,
+                                float* const outs[4], int out_is_device, void* stream) {
+  return guard([&] {
+    BRN_CHECK(m && x && outs, 1, "null argument");
+    m->impl.features_api(x, B, H, W, x_is_device != 0, outs, out_is_device != 0, (cudaStream_t)stream);
+  });
+}
+
 brn_status brn_decoder_forward(brn_model* m, const float* x, const float* x1, const float* x2, const float* x3,
                                const float* x4, int32_t B, int32_t H, int32_t W, int is_device, float* out,
                                void* stream) {
@@ -193,16 +201,20 @@ int32_t brn_profile_get(const brn_model* m, const char*** names, const float** m
 struct Scratch {
   std::vector<void*> ptrs;
   cudaStream_t stream = nullptr;
+  int prev_dev = -1;
   explicit Scratch(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     BRN_CHECK(e == cudaSuccess && n > 0, 2, "no CUDA device available (this library has no CPU fallback)");
+    BRN_CHECK(device >= 0 && device < n, 1, "device index out of range");
+    if (cudaGetDevice(&prev_dev) != cudaSuccess || prev_dev == device) prev_dev = -1;
     BRN_CUDA(cudaSetDevice(device));
     BRN_CUDA(cudaStreamCreate(&stream));
   }
   ~Scratch() {
     for (void* p : ptrs) cudaFree(p);
     if (stream) cudaStreamDestroy(stream);
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);   // the caller's current device is left as it was
   }
   void* alloc(size_t bytes) {
     void* p = nullptr;

@@ -28,6 +28,17 @@ struct Error : std::runtime_error {
     if (!(cond)) throw ::brn::Error((status), (msg));       \
   } while (0)
 
+// cudaSetDevice for the duration of an entry point; the caller's current device is restored on exit
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) BRN_CUDA(cudaSetDevice(dev));
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // Activation / operand element types.  The 16-bit tensor-core path uses bf16 in the backbone (fp32 residual stream,
 // wide dynamic range) and fp16 in the squeeze module + decoder (BN-normalised, O(1) activations; 3 more mantissa
 // bits are what the IoU >= 0.999 tolerance on near-zero logits needs, see DESIGN.md "precision").

@@ -55,7 +55,7 @@ Model::Model(const brn_config& c, int dev) : cfg(c), device(dev) {
   BRN_CHECK(e == cudaSuccess && ndev > 0, 2,
             std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
   BRN_CHECK(dev >= 0 && dev < ndev, 1, "device index out of range");
-  BRN_CUDA(cudaSetDevice(dev));
+  DeviceGuard dg(dev);
   cudaDeviceProp prop;
   BRN_CUDA(cudaGetDeviceProperties(&prop, dev));
   BRN_CHECK(prop.major == 10, 2, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
@@ -69,6 +69,8 @@ Model::Model(const brn_config& c, int dev) : cfg(c), device(dev) {
 }
 
 Model::~Model() {
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
   cudaSetDevice(device);
   drop_graphs();
   for (void* p : allocs) cudaFree(p);
@@ -81,6 +83,7 @@ Model::~Model() {
   for (auto& pe : prof) { if (pe.e0) cudaEventDestroy(pe.e0); if (pe.e1) cudaEventDestroy(pe.e1); }
   for (auto e : ktimer.pool) cudaEventDestroy(e);
   if (own_stream) cudaStreamDestroy(own_stream);
+  if (prev_dev >= 0 && prev_dev != device) cudaSetDevice(prev_dev);
 }
 
 void Model::build_schema() {
@@ -264,7 +267,7 @@ void Model::finalize() {
   BRN_CHECK(!finalized, 6, "finalize called twice");
   for (size_t i = 0; i < keys.size(); ++i)
     BRN_CHECK(tensors[i].set, 3, "missing tensor: " + keys[i]);
-  BRN_CUDA(cudaSetDevice(device));
+  DeviceGuard dg(device);
 
   // conv (+ optional BN fold) -> LayerW
   auto conv_bn = [&](const std::string& cp, bool has_bias, const std::string& bnp) -> LayerW {
@@ -478,7 +481,7 @@ int Model::acquire_lane(std::unique_lock<std::mutex>& lk, cudaStream_t s) {
 
 void Model::release_lane(int i) {
   lanes[i].busy = false;
-  lane_cv.notify_one();
+  lane_cv.notify_all();   // two kinds of waiter share the condition variable (acquire_lane, quiesce)
 }
 
 void Model::quiesce(std::unique_lock<std::mutex>& lk) {
@@ -731,36 +734,40 @@ void Model::run_squeeze_decoder(LaunchCtx& ctx, const float* img, int B, int H, 
   prof_end(ctx);
 }
 
+static bool env_flag(const char* n);
+int Model::dec_dtype() const {
+  if (cfg.precision == BRN_PREC_BF16) {
+    const char* v = getenv("BRN_BF16_DECODER");            // experiments: "bf16" | "fp16" overrides the handle's setting
+    if (v && v[0]) return v[0] == 'f' ? F16 : BF16;
+    return bf16_decoder_fp16 ? F16 : BF16;
+  }
+  return act_dtype();
+}
 static bool env_flag(const char* n) { const char* v = getenv(n); return v && v[0] && v[0] != '0'; }
 
-// BiRefNet::forward_logits (src/birefnet.rs:412-461)
-void Model::run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, float* out, bool apply_sigmoid) {
+// First half of BiRefNet::forward_logits (src/birefnet.rs:412-454): both backbone passes, the multi-scale concat
+// (x_k = [bb(x)_k | up(bb(x_half)_k)]) and the cxt concat into X4cat.  X[0..2] and X4cat are caller-allocated.
+void Model::run_features(LaunchCtx& ctx, const float* img, int B, int H, int W, View X[3], View X4cat) {
   const int AD = dec_dtype();
-  const size_t m0 = arena.mark();
-  // scratch for split-K partial sums (small batches: the 32x32-level decoder convs have 8 output tiles per image)
-  ctx.splitk_bytes = tc_gemm_splitk_scratch_bytes(B);
-  ctx.splitk = (float*)arena.alloc(ctx.splitk_bytes);
-  int hs[4], ws[4];
-  for (int i = 0; i < 4; ++i) { hs[i] = H / (4 << i); ws[i] = W / (4 << i); }
-  View X[4];
-  for (int i = 0; i < 3; ++i)
-    X[i] = make_view(arena.alloc((size_t)B * hs[i] * ws[i] * lat(i) * dsize(AD)), AD, B, hs[i], ws[i], lat(i));
-  const int c4 = x4_channels();
-  View X4cat = make_view(arena.alloc((size_t)B * hs[3] * ws[3] * c4 * dsize(AD)), AD, B, hs[3], ws[3], c4);
   const int off4 = lat(0) + lat(1) + lat(2);
   View feats[4] = {X[0].slice(0, C(0)), X[1].slice(0, C(1)), X[2].slice(0, C(2)), X4cat.slice(off4, C(3))};
   const bool merged = cfg.precision != BRN_PREC_FP32 && !ctx.force_simt && !env_flag("BRN_SPLIT_BACKBONE");
   {
     const size_t m1 = arena.mark();
-    float* half = (float*)arena.alloc((size_t)B * 3 * (H / 2) * (W / 2) * 4);
+    const int H2 = H / 2, W2 = W / 2;
+    float* half = (float*)arena.alloc((size_t)B * 3 * H2 * W2 * 4);
+    // token grids of the half-resolution pass: the backbone's own chain (PatchEmbed /4, then PatchMerging rounds
+    // odd grids UP: src/swin.rs:496-503,586) -- not (H/4 >> i) / 2, which rounds down when H/32 is odd
     View fh[4];
-    for (int i = 0; i < 4; ++i)
-      fh[i] = make_view(arena.alloc((size_t)B * (hs[i] / 2) * (ws[i] / 2) * C(i) * dsize(AD)), AD, B, hs[i] / 2,
-                        ws[i] / 2, C(i));
+    int hh = H2 / 4, wh = W2 / 4;
+    for (int i = 0; i < 4; ++i) {
+      fh[i] = make_view(arena.alloc((size_t)B * hh * wh * C(i) * dsize(AD)), AD, B, hh, wh, C(i));
+      hh = (hh + 1) / 2; wh = (wh + 1) / 2;
+    }
     if (merged) {
       prof_begin(ctx, "backbone_full+half");
-      glue_resize_nchw(ctx, img, B, 3, H, W, half, H / 2, W / 2);              // :425
-      run_backbone(ctx, img, B, H, W, feats, half, H / 2, W / 2, fh);          // :416-420 and :426 in one pass
+      glue_resize_nchw(ctx, img, B, 3, H, W, half, H2, W2);                    // :425
+      run_backbone(ctx, img, B, H, W, feats, half, H2, W2, fh);                // :416-420 and :426 in one pass
       prof_end(ctx);
       prof_begin(ctx, "half_upsample");
     } else {
@@ -768,8 +775,8 @@ void Model::run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, f
       run_backbone(ctx, img, B, H, W, feats);                                  // :416-420
       prof_end(ctx);
       prof_begin(ctx, "backbone_half");
-      glue_resize_nchw(ctx, img, B, 3, H, W, half, H / 2, W / 2);              // :425
-      run_backbone(ctx, half, B, H / 2, W / 2, fh);                            // :426
+      glue_resize_nchw(ctx, img, B, 3, H, W, half, H2, W2);                    // :425
+      run_backbone(ctx, half, B, H2, W2, fh);                                  // :426
     }
     View dst[4] = {X[0].slice(C(0), C(0)), X[1].slice(C(1), C(1)), X[2].slice(C(2), C(2)), X4cat.slice(off4 + C(3), C(3))};
     for (int i = 0; i < 4; ++i) glue_resize_nhwc(ctx, fh[i], dst[i]);        // :435-443
@@ -781,6 +788,23 @@ void Model::run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, f
   glue_resize_nhwc(ctx, X[1], X4cat.slice(lat(0), lat(1)));
   glue_resize_nhwc(ctx, X[2], X4cat.slice(lat(0) + lat(1), lat(2)));
   prof_end(ctx);
+}
+
+// BiRefNet::forward_logits (src/birefnet.rs:412-461)
+void Model::run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, float* out, bool apply_sigmoid) {
+  const int AD = dec_dtype();
+  const size_t m0 = arena.mark();
+  // scratch for split-K partial sums (small batches: the 32x32-level decoder convs have 8 output tiles per image)
+  ctx.splitk_bytes = tc_gemm_splitk_scratch_bytes(B);
+  ctx.splitk = (float*)arena.alloc(ctx.splitk_bytes);
+  int hs[4], ws[4];
+  for (int i = 0; i < 4; ++i) { hs[i] = H / (4 << i); ws[i] = W / (4 << i); }
+  View X[3];
+  for (int i = 0; i < 3; ++i)
+    X[i] = make_view(arena.alloc((size_t)B * hs[i] * ws[i] * lat(i) * dsize(AD)), AD, B, hs[i], ws[i], lat(i));
+  const int c4 = x4_channels();
+  View X4cat = make_view(arena.alloc((size_t)B * hs[3] * ws[3] * c4 * dsize(AD)), AD, B, hs[3], ws[3], c4);
+  run_features(ctx, img, B, H, W, X, X4cat);
   run_squeeze_decoder(ctx, img, B, H, W, X[0], X[1], X[2], X4cat, out, apply_sigmoid);
   arena.release(m0);
 }
@@ -790,8 +814,8 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
   BRN_CHECK(finalized, 6, "forward before finalize");
   BRN_CHECK(x && out && B > 0, 1, "forward: bad argument");
   BRN_CHECK(H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, 5, "H and W must be positive multiples of 32");
+  DeviceGuard dg(device);
   std::unique_lock<std::mutex> lk(mu);
-  BRN_CUDA(cudaSetDevice(device));
   const int li = acquire_lane(lk, s);
   cudaStream_t st = s ? s : lanes[li].stream;
   lanes[li].last = st;
@@ -830,7 +854,7 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
     // the legacy / per-thread default streams cannot be captured
     const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
     if (use_graph && !graph_env_off && !prof_on && !ctx.force_simt && capturable) {
-      GraphKey key{xi, ko, arena.base, nb, H, W, (int)cfg.precision, (int)cfg.deform_mode, apply_sigmoid ? 1 : 0};
+      GraphKey key{xi, ko, arena.base, nb, H, W, (int)cfg.precision | (dec_dtype() << 8), (int)cfg.deform_mode, apply_sigmoid ? 1 : 0};
       GraphEntry* e = nullptr;
       for (auto& g : graphs) if (g.key == key) { e = &g; break; }
       if (!e) {
@@ -928,8 +952,8 @@ void Model::backbone_api(const float* x, int B, int H, int W, bool x_dev, float*
                          cudaStream_t s) {
   BRN_CHECK(finalized, 6, "backbone_forward before finalize");
   BRN_CHECK(H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, 5, "H and W must be positive multiples of 32");
+  DeviceGuard dg(device);
   std::lock_guard<std::mutex> lk(mu);
-  BRN_CUDA(cudaSetDevice(device));
   cudaStream_t st = s ? s : own_stream;
   const int AD = act_dtype();
   LaunchCtx ctx; ctx.stream = st; ctx.precision = cfg.precision; ctx.force_simt = env_flag("BRN_FORCE_SIMT");
@@ -960,12 +984,48 @@ void Model::backbone_api(const float* x, int B, int H, int W, bool x_dev, float*
   BRN_CUDA(cudaStreamSynchronize(st));
 }
 
+// x1..x3 and the cxt-concatenated x4 (src/birefnet.rs:412-454) as NCHW fp32: the inputs brn_decoder_forward takes
+void Model::features_api(const float* x, int B, int H, int W, bool x_dev, float* const outs[4], bool out_dev,
+                         cudaStream_t s) {
+  BRN_CHECK(finalized, 6, "features_forward before finalize");
+  BRN_CHECK(x && outs && B > 0, 1, "features_forward: bad argument");
+  BRN_CHECK(H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, 5, "H and W must be positive multiples of 32");
+  DeviceGuard dg(device);
+  std::lock_guard<std::mutex> lk(mu);
+  cudaStream_t st = s ? s : own_stream;
+  const int AD = dec_dtype();
+  LaunchCtx ctx; ctx.stream = st; ctx.precision = cfg.precision; ctx.force_simt = env_flag("BRN_FORCE_SIMT");
+  long long dummy = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    arena.dry = pass == 0; ctx.dry = pass == 0; ctx.launches = pass == 0 ? &dummy : &launches;
+    arena.off = 0; if (pass == 0) arena.peak = 0;
+    float* din = (float*)arena.alloc((size_t)B * 3 * H * W * 4);
+    View X[4]; float* dn[4];
+    for (int i = 0; i < 4; ++i) {
+      const int hh = H / (4 << i), ww = W / (4 << i), c = i < 3 ? lat(i) : x4_channels();
+      X[i] = make_view(arena.alloc((size_t)B * hh * ww * c * dsize(AD)), AD, B, hh, ww, c);
+      dn[i] = (float*)arena.alloc((size_t)B * hh * ww * c * 4);
+    }
+    if (pass == 1)
+      BRN_CUDA(cudaMemcpyAsync(din, x, (size_t)B * 3 * H * W * 4, x_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    run_features(ctx, din, B, H, W, X, X[3]);
+    for (int i = 0; i < 4; ++i) {
+      glue_nhwc_to_nchw(ctx, X[i], dn[i]);
+      if (pass == 1)
+        BRN_CUDA(cudaMemcpyAsync(outs[i], dn[i], (size_t)X[i].rows() * X[i].C * 4,
+                                 out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    }
+    if (pass == 0) ensure_arena(arena.peak);
+  }
+  BRN_CUDA(cudaStreamSynchronize(st));
+}
+
 void Model::decoder_api(const float* x, const float* x1, const float* x2, const float* x3, const float* x4, int B,
                         int H, int W, bool is_dev, float* out, cudaStream_t s) {
   BRN_CHECK(finalized, 6, "decoder_forward before finalize");
   BRN_CHECK(H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, 5, "H and W must be positive multiples of 32");
+  DeviceGuard dg(device);
   std::lock_guard<std::mutex> lk(mu);
-  BRN_CUDA(cudaSetDevice(device));
   cudaStream_t st = s ? s : own_stream;
   const int AD = dec_dtype();
   LaunchCtx ctx; ctx.stream = st; ctx.precision = cfg.precision; ctx.force_simt = env_flag("BRN_FORCE_SIMT");

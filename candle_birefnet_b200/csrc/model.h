@@ -154,10 +154,13 @@ struct Model {
                bool apply_sigmoid);
   void backbone_api(const float* x, int B, int H, int W, bool x_dev, float* const outs[4], bool out_dev,
                     cudaStream_t s);
+  void features_api(const float* x, int B, int H, int W, bool x_dev, float* const outs[4], bool out_dev,
+                    cudaStream_t s);
   void decoder_api(const float* x, const float* x1, const float* x2, const float* x3, const float* x4, int B, int H,
                    int W, bool is_dev, float* out, cudaStream_t s);
 
  private:
+  void run_features(LaunchCtx& ctx, const float* img, int B, int H, int W, View X[3], View X4cat);
   void run_forward(LaunchCtx& ctx, const float* img, int B, int H, int W, float* out, bool apply_sigmoid);
   void run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, View feats[4], const float* img2 = nullptr,
                     int H2 = 0, int W2 = 0, View* feats2 = nullptr);
@@ -170,7 +173,11 @@ struct Model {
   int micro_batch(int B, int H, int W) const;
   // element type of stored activations / GEMM operands for the current precision (fp32 | bf16 | fp16)
   int act_dtype() const { return cfg.precision == BRN_PREC_BF16 ? BF16 : cfg.precision == BRN_PREC_FP16 ? F16 : F32; }
-  int dec_dtype() const { return act_dtype(); }
+  // squeeze module + decoder operands.  precision = bf16 keeps bf16 in the backbone (fp32 residual stream, wide dynamic
+  // range) and, with bf16_decoder_fp16 set, runs the BN-normalised O(1) decoder activations in fp16 (same tensor-core
+  // rate, 3 more mantissa bits -- what IoU >= 0.999 on near-threshold logits needs)
+  int bf16_decoder_fp16 = 1;
+  int dec_dtype() const;
   void prof_begin(LaunchCtx& ctx, const char* name);
   void prof_end(LaunchCtx& ctx);
 

@@ -204,8 +204,13 @@ class BiRefNet:
             import torch
             assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4 and x.shape[1] == 3
             B, _, H, W = x.shape
+            if x.device.index != self.device:
+                raise BrnError(1, f"input lives on cuda:{x.device.index}, the handle on cuda:{self.device}")
             if out is None:
                 out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+            elif not (_is_torch_cuda(out) and out.device == x.device and out.dtype == torch.float32 and
+                      out.is_contiguous() and tuple(out.shape) == (B, 1, H, W)):
+                raise BrnError(5, f"`out` must be a contiguous float32 CUDA tensor [{B},1,{H},{W}] on {x.device}")
             s = stream if stream is not None else torch.cuda.current_stream(x.device).cuda_stream
             if not s:
                 s = 1   # cudaStreamLegacy: torch's default stream, explicitly (NULL would mean the handle's own stream)
@@ -217,6 +222,9 @@ class BiRefNet:
         B, _, H, W = x.shape
         if out is None:
             out = np.empty((B, 1, H, W), dtype=np.float32)
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags.c_contiguous and
+                  out.shape == (B, 1, H, W)):
+            raise BrnError(5, f"`out` must be a C-contiguous float32 array [{B},1,{H},{W}]")
         check(fn(self._h, x.ctypes.data_as(C.c_void_p), B, H, W, 0, out.ctypes.data_as(C.c_void_p), 0, None))
         return out
 
@@ -238,6 +246,18 @@ class BiRefNet:
         outs = [np.empty((B, E << i, H // (4 << i), W // (4 << i)), dtype=np.float32) for i in range(4)]
         ptrs = (C.c_void_p * 4)(*[o.ctypes.data_as(C.c_void_p) for o in outs])
         check(lib().brn_backbone_forward(self._h, x.ctypes.data_as(C.c_void_p), B, H, W, 0, ptrs, 0, None))
+        return outs
+
+    def features_forward(self, x: np.ndarray) -> List[np.ndarray]:
+        """First half of forward_logits (src/birefnet.rs:412-454) -> [x1,x2,x3,x4_cxt] NCHW float32: the multi-scale
+        features the squeeze module and decoder consume (what examples/bench_inference.rs times as `backbone`)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        B, _, H, W = x.shape
+        E = self.config.swin.embed_dim
+        ch = [2 * (E << i) for i in range(3)] + [2 * E * 15]
+        outs = [np.empty((B, ch[i], H // (4 << i), W // (4 << i)), dtype=np.float32) for i in range(4)]
+        ptrs = (C.c_void_p * 4)(*[o.ctypes.data_as(C.c_void_p) for o in outs])
+        check(lib().brn_features_forward(self._h, x.ctypes.data_as(C.c_void_p), B, H, W, 0, ptrs, 0, None))
         return outs
 
     def decoder_forward(self, x, x1, x2, x3, x4) -> np.ndarray:

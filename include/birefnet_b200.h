@@ -122,7 +122,7 @@ BRN_API brn_status brn_model_finalize(brn_model* m);
 BRN_API brn_status brn_model_set_precision(brn_model* m, int precision);
 BRN_API brn_status brn_model_set_deform_mode(brn_model* m, int deform_mode);
 /* CUDA-graph replay of the forward (default on): the second call with the same device buffers, shape and modes captures
- * the ~460-kernel launch sequence of forward_logits into a CUDA graph; later calls replay it (batch-1 latency is
+ * the launch sequence (a few hundred kernels) of forward_logits into a CUDA graph; later calls replay it (batch-1 latency is
  * launch-bound otherwise).  Host-pointer calls use the handle's own staging buffers, so they replay as well.  Has no
  * counterpart in the reference (candle launches op by op). */
 BRN_API brn_status brn_model_set_cuda_graph(brn_model* m, int on);
@@ -144,6 +144,13 @@ BRN_API brn_status brn_forward(brn_model* m, const float* x, int32_t B, int32_t 
 
 /* SwinTransformer::forward (src/swin.rs:768-797): 4 NCHW fp32 maps [B,C_i,H/4>>i,W/4>>i] (BASELINE config 2). */
 BRN_API brn_status brn_backbone_forward(brn_model* m, const float* x, int32_t B, int32_t H, int32_t W, int x_is_device,
+                                float* const outs[4], int out_is_device, void* stream);
+
+/* First half of BiRefNet::forward_logits (src/birefnet.rs:412-454): both backbone passes (full and half resolution),
+ * the multi-scale concat and the cxt concat.  outs[0..2] = x1..x3 [B,2C_i,H/4>>i,W/4>>i], outs[3] = the
+ * cxt-concatenated x4 [B,x4_channels,H/32,W/32] -- exactly the inputs brn_decoder_forward takes (the reference's
+ * examples/bench_inference.rs:37-92 times these pieces separately).  NCHW fp32. */
+BRN_API brn_status brn_features_forward(brn_model* m, const float* x, int32_t B, int32_t H, int32_t W, int x_is_device,
                                 float* const outs[4], int out_is_device, void* stream);
 
 /* SqueezeModule::forward + BiRefNetDecoder::forward (src/birefnet.rs:86-94, 278-376) on caller-provided

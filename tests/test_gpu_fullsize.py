@@ -1,0 +1,128 @@
+"""GPU parity of the BENCHMARKED configuration against the oracle (VERDICT r01 task 1).
+
+Swin-L at 1024x1024, one image, through the C ABI:
+  * weight-set A / cpu_fallback  == the reference's candle-CPU forward (src/aspp.rs:183-185), fp32 + both 16-bit paths
+  * weight-set B / deformable    == what bench.py runs (random deformable offsets), fp32 + both 16-bit paths
+  * inputs: randn (examples/bench_inference.rs:30) and examples/assets/cat.png -> resize 1024^2 (Triangle) ->
+    ImageNet normalise (examples/infer_image.rs:44-67; decoded pixels committed as tests/golden/cat_768_u8.npz)
+Tolerances are the north_star's: fp32 path max |dlogit| <= 1e-3; 16-bit paths max |dsigmoid| <= 1e-2, IoU@0.5 >= 0.999.
+Plus the real-geometry check the 64x96 golden fixture could not see: the multi-scale features x1..x4 for inputs whose
+H/32 or W/32 is odd (the half-resolution pass then has odd token grids that PatchMerging pads, src/swin.rs:496-503).
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import candle_birefnet_b200 as cb
+from oracle import birefnet_ref as R
+from oracle import imageops_ref as IM
+from oracle.make_weights import as_torch, make_input, make_weights
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def iou(a, b):
+    a, b = a > 0.5, b > 0.5
+    u = np.logical_or(a, b).sum()
+    return 1.0 if u == 0 else float(np.logical_and(a, b).sum() / u)
+
+
+def check_logits(got, exp, precision, tag=""):
+    if precision == "fp32":
+        err = np.abs(got - exp).max()
+        assert err <= 1e-3, f"{tag} fp32 path max |dlogit| = {err}"
+    else:
+        ds = np.abs(sigmoid(got) - sigmoid(exp)).max()
+        i = iou(sigmoid(got), sigmoid(exp))
+        assert ds <= 1e-2 and i >= 0.999, f"{tag} {precision} path max |dsigmoid| = {ds}, IoU = {i}"
+
+
+def py_cfg(cfg, precision, mode):
+    return cb.BiRefNetConfig(swin=cb.SwinConfig(embed_dim=cfg.embed_dim, depths=tuple(cfg.depths),
+                                               num_heads=tuple(cfg.num_heads)), precision=precision, deform_mode=mode)
+
+
+_INPUTS = {}
+
+
+def full_input(kind):
+    if kind not in _INPUTS:
+        if kind == "randn":
+            _INPUTS[kind] = make_input(1, 1024, 1024, seed=1234)
+        else:
+            rgb = np.load(GOLD / "cat_768_u8.npz")["rgb"]
+            _INPUTS[kind] = IM.preprocess(rgb, 1024)
+    return _INPUTS[kind]
+
+
+@pytest.fixture(scope="module")
+def swin_l_case():
+    """One Swin-L handle + oracle logits per (weight-set, mode, input); the oracle runs once per key (3-30 s each)."""
+    cfg = R.Config.swin_l()
+    state = {"cfg": cfg, "w": {}, "m": {}, "exp": {}}
+
+    def get(wset, mode, kind):
+        if wset not in state["m"]:
+            for k in list(state["m"]):              # one 220 M-parameter handle at a time
+                state["m"].pop(k).close()
+                state["w"].pop(k)
+            state["w"][wset] = make_weights(cfg, seed=0, weight_set=wset, offset_sigma=2.0)
+            state["m"][wset] = cb.BiRefNet.new(py_cfg(cfg, "fp16", mode), state["w"][wset])
+        key = (wset, mode, kind)
+        if key not in state["exp"]:
+            with torch.no_grad():
+                state["exp"][key] = R.forward_logits(torch.from_numpy(full_input(kind)), as_torch(state["w"][wset]), cfg,
+                                                     mode).numpy()
+        return state["m"][wset], state["exp"][key]
+    yield get
+    for m in state["m"].values():
+        m.close()
+
+
+@pytest.mark.parametrize("wset,mode", [("A", "cpu_fallback"), ("B", "deformable")])
+@pytest.mark.parametrize("kind", ["randn", "cat"])
+def test_swin_l_1024_vs_oracle(swin_l_case, wset, mode, kind):
+    m, exp = swin_l_case(wset, mode, kind)
+    m.set_deform_mode(mode)
+    x = full_input(kind)
+    for precision in ("fp32", "fp16", "bf16"):
+        m.set_precision(precision)
+        got = m.forward_logits(x)
+        check_logits(got, exp, precision, tag=f"{wset}/{mode}/{kind}")
+    if wset == "A":
+        # zero offset / modulator convs: the deformable kernels must reproduce the plain-conv result
+        m.set_precision("fp16")
+        m.set_deform_mode("deformable")
+        check_logits(m.forward_logits(x), exp, "fp16", tag="A/deformable-as-plain")
+
+
+@pytest.mark.parametrize("hw", [(32, 32), (96, 160), (64, 96), (224, 96)])
+def test_features_odd_half_grids(mini_cfg, mini_weights_B, hw):
+    """x1..x3 and the cxt-concatenated x4 (src/birefnet.rs:412-454) for B = 2 against the oracle.  With H/32 or W/32
+    odd the half-resolution pass ends on token grids like 1x2 / 2x3 / 4x2 that only exist through PatchMerging's
+    padding; a wrong grid shifts rows between the two images of the batch."""
+    m = cb.BiRefNet.new(py_cfg(mini_cfg, "fp32", "deformable"), mini_weights_B)
+    x = make_input(2, hw[0], hw[1], seed=17)
+    with torch.no_grad():
+        exp = R.features(torch.from_numpy(x), as_torch(mini_weights_B), mini_cfg)
+    try:
+        for precision, tol in (("fp32", 2e-4), ("fp16", 2e-2), ("bf16", 8e-2)):
+            m.set_precision(precision)
+            got = m.features_forward(x)
+            for i in range(4):
+                e = exp[i].numpy()
+                assert got[i].shape == e.shape, (i, got[i].shape, e.shape)
+                rel = np.abs(got[i] - e).max() / max(1.0, np.abs(e).max())
+                assert rel <= tol, (precision, hw, i, rel)
+            full = m.forward_logits(x)
+            for b in range(2):      # image independence survives the odd grids
+                assert np.array_equal(full[b:b + 1], m.forward_logits(x[b:b + 1]))
+    finally:
+        m.close()
