@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
     L.brn_window_attention.argtypes = [C.c_int, C.c_int, vp, vp, i32, i32, i32, i32, i32, vp]
     L.brn_deform_conv2d.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.brn_linear.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.brn_ln_linear.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.brn_conv2d.argtypes = [C.c_int, C.c_int, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     L.brn_bench_op.argtypes = [C.c_int, C.c_int, C.c_int] + [i32] * 10 + [fp]
     L.brn_launch_count.argtypes = [vp]

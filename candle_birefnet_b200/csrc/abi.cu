@@ -256,6 +256,41 @@ brn_status brn_linear(int device, int precision, const float* a, const float* w,
   });
 }
 
+brn_status brn_ln_linear(int device, int precision, const float* x, const float* gamma, const float* beta,
+                         const float* w, const float* bias, int32_t M, int32_t N, int32_t K, int32_t act, float* out) {
+  return guard([&] {
+    BRN_CHECK(x && gamma && beta && w && out && M > 0 && N > 0 && K > 0, 1, "brn_ln_linear: bad argument");
+    BRN_CHECK(precision != BRN_PREC_FP32, 7, "brn_ln_linear: the LayerNorm fold is a tensor-core-path feature");
+    Scratch s(device);
+    LaunchCtx ctx = make_ctx(s, precision);
+    const int AD = precision == BRN_PREC_FP16 ? F16 : BF16;
+    // fold exactly as Model::make_folded does
+    std::vector<float> wf((size_t)N * K), bf(N);
+    for (int n = 0; n < N; ++n) {
+      double acc = bias ? bias[n] : 0.0;
+      for (int c = 0; c < K; ++c) {
+        wf[(size_t)n * K + c] = (float)((double)w[(size_t)n * K + c] * gamma[c]);
+        acc += (double)w[(size_t)n * K + c] * beta[c];
+      }
+      bf[n] = (float)acc;
+    }
+    LayerW L = make_layer_standalone(N, K, 1, 1, wf.data(), bf.data(), s.ptrs, true);
+    View x32 = make_view(s.put(x, (size_t)M * K), F32, 1, 1, M, K);
+    View x16 = make_view(s.alloc((size_t)M * K * 2), AD, 1, 1, M, K);
+    float2* stats = (float2*)s.alloc((size_t)M * sizeof(float2));
+    glue_ln_stats_cast(ctx, x32, x16, stats);
+    View o16 = make_view(s.alloc((size_t)M * N * 2), AD, 1, 1, M, N);
+    GemmArgs g; g.x = x16; g.w = &L; g.act = act; g.out = o16;
+    g.lnf.stats = stats; g.lnf.parts = 1; g.lnf.stride = M; g.lnf.C = K;
+    BRN_CHECK(tc_gemm_supported(g), 5, "brn_ln_linear: K must be a multiple of 8");
+    tc_gemm(ctx, g);
+    View o32 = make_view(s.alloc((size_t)M * N * 4), F32, 1, 1, M, N);
+    glue_copy_cast(ctx, o16, o32);
+    BRN_CUDA(cudaMemcpyAsync(out, o32.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost, s.stream));
+    BRN_CUDA(cudaStreamSynchronize(s.stream));
+  });
+}
+
 brn_status brn_conv2d(int device, int precision, const float* x, const float* weight, const float* bias, int32_t B,
                       int32_t C, int32_t H, int32_t W, int32_t O, int32_t k, int32_t act, float* out) {
   return guard([&] {

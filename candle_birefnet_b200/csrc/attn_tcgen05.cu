@@ -61,7 +61,18 @@ struct AttnP {
   int nwh, nww, shift;
   int split_win, nwh2, nww2;     // windows >= split_win (if > 0) belong to a second grid (merged half-resolution pass)
   uint16_t* out; int ldo;
+  // token geometry: h > 0 enables the pad-row fix-up (q = k = v = bias for window rows in the pad region) and, with
+  // token_out, the store straight to token order (window_reverse + roll back + crop, src/swin.rs:387-401)
+  int h, w, h2, w2;
+  int token_out; long long tok2;
+  const uint16_t* bias16;        // [3C] qkv bias in the operand type
 };
+
+// padded-grid coordinate of window-local index t (0..11) of window index wi: (12 wi + t + shift) mod hp
+__device__ __forceinline__ int at_src_coord(int wi, int t, int shift, int hp) {
+  int r = wi * 12 + t + shift;
+  return r >= hp ? r - hp : r;
+}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -135,15 +146,25 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == AT_SOFT_WARPS) {
-    if (ptx::elect_one() && n_units > 0) {
-      // ===== TMA + MMA issuer =====
-      ptx::prefetch_tmap(&tmQKV);
-      ptx::mbar_expect_tx(bias_bar, AT_BIAS_BYTES);
-      ptx::bulk_load(sBias, p.bias32p + (size_t)head * 144 * AT_BIAS_LD, AT_BIAS_BYTES, bias_bar);
+    if (n_units > 0) {
+      // ===== control warp: lane 0 issues TMA and every tcgen05.mma; all 32 lanes patch pad rows of staged tiles =====
+      const bool leader = lane == 0;
       const uint32_t is_bf = DT == BF16 ? 1u : 0u;
       const uint32_t idesc_s = ptx::make_idesc_16(128, 144, 0, 0, is_bf);   // S = Q K^T : both K-major
       const uint32_t idesc_s1 = ptx::make_idesc_16(128, 48, 0, 0, is_bf);   // rows 128-143 against one key third
       const uint32_t idesc_o = ptx::make_idesc_16(128, 32, 0, 1, is_bf);    // O = P V   : V is MN-major
+      if (leader) {
+        ptx::prefetch_tmap(&tmQKV);
+        ptx::mbar_expect_tx(bias_bar, AT_BIAS_BYTES);
+        ptx::bulk_load(sBias, p.bias32p + (size_t)head * 144 * AT_BIAS_LD, AT_BIAS_BYTES, bias_bar);
+      }
+      // this lane's 16-byte chunk (lane & 3) of the head's q / k / v bias rows: the qkv of a pad token
+      uint4 bq[3];
+      if (p.h > 0) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          bq[t] = __ldg(reinterpret_cast<const uint4*>(p.bias16 + (size_t)t * p.C + head * 32) + (lane & 3));
+      }
       auto load_unit = [&](int i) {
         const int s = i % AT_STAGES, win = w_first + i * w_step;
         uint8_t* st = sQKV + s * AT_STAGE_BYTES;
@@ -151,6 +172,37 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         ptx::tma_load_2d(st, &tmQKV, &qkv_full[s], head * 32, win * 144);
         ptx::tma_load_2d(st + AT_TILE_BYTES, &tmQKV, &qkv_full[s], p.C + head * 32, win * 144);
         ptx::tma_load_2d(st + 2 * AT_TILE_BYTES, &tmQKV, &qkv_full[s], 2 * p.C + head * 32, win * 144);
+      };
+      // Pad tokens are zeros AFTER norm1 (src/swin.rs:355-366), so their q, k, v equal the qkv bias and they take part
+      // as keys.  The token-order qkv GEMM never computes those rows: write them into the staged tiles here (64B
+      // swizzle: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)).  Warp-uniform early out for the
+      // windows that hold no pad position (all but the last window row / column of a grid).
+      auto fix_pads = [&](int i) {
+        if (p.h <= 0) return;
+        int win = w_first + i * w_step;
+        int g_h = p.h, g_w = p.w, g_nwh = p.nwh, g_nww = p.nww;
+        if (p.split_win > 0 && win >= p.split_win) { win -= p.split_win; g_h = p.h2; g_w = p.w2; g_nwh = p.nwh2; g_nww = p.nww2; }
+        const int hp = g_nwh * 12, wp = g_nww * 12;
+        if (hp == g_h && wp == g_w) return;
+        const int wl = win % (g_nwh * g_nww), wi = wl / g_nww, wj = wl - wi * g_nww;
+        uint32_t rmask = 0, cmask = 0;
+#pragma unroll
+        for (int t = 0; t < 12; ++t) {
+          rmask |= (at_src_coord(wi, t, p.shift, hp) >= g_h ? 1u : 0u) << t;
+          cmask |= (at_src_coord(wj, t, p.shift, wp) >= g_w ? 1u : 0u) << t;
+        }
+        if ((rmask | cmask) == 0) return;
+        const uint32_t base = ptx::smem_u32(sQKV + (i % AT_STAGES) * AT_STAGE_BYTES);
+        const int ch = lane & 3;
+        for (int r = lane >> 2; r < 144; r += 8) {
+          const int ti = r / 12, tj = r - ti * 12;
+          if (((rmask >> ti) | (cmask >> tj)) & 1u) {
+            const uint32_t a = base + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
+#pragma unroll
+            for (int t = 0; t < 3; ++t) ptx::sts128(a + t * AT_TILE_BYTES, bq[t]);
+          }
+        }
+        ptx::fence_proxy_async_smem();
       };
       auto issue_s = [&](int i) {
         const uint32_t q_addr = ptx::smem_u32(sQKV + (i % AT_STAGES) * AT_STAGE_BYTES), k_addr = q_addr + AT_TILE_BYTES;
@@ -191,25 +243,38 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         ptx::umma_commit(o_full);
         ptx::umma_commit(&qkv_empty[s]);
       };
-      load_unit(0);
-      if (n_units > 1) load_unit(1);
+      if (leader) {
+        load_unit(0);
+        if (n_units > 1) load_unit(1);
+      }
       ptx::mbar_wait(&qkv_full[0], 0);
-      ptx::tc_fence_after();
-      issue_s(0);
+      fix_pads(0);
+      __syncwarp();
+      if (leader) {
+        ptx::tc_fence_after();
+        issue_s(0);
+      }
       for (int i = 0; i < n_units; ++i) {
         if (i + 1 < n_units) {      // S of the next unit as soon as this unit's scores sit in registers
           ptx::mbar_wait_backoff(&qkv_full[(i + 1) % AT_STAGES], ((i + 1) / AT_STAGES) & 1);
-          ptx::mbar_wait_backoff(s_empty, i & 1);
+          fix_pads(i + 1);
+          __syncwarp();
+          if (leader) {
+            ptx::mbar_wait_backoff(s_empty, i & 1);
+            ptx::tc_fence_after();
+            issue_s(i + 1);
+          }
+        }
+        if (leader) {
+          if (i + 2 < n_units) {      // prefetch two units ahead; that stage held unit i-1
+            if (i >= 1) ptx::mbar_wait_backoff(&qkv_empty[(i + 2) % AT_STAGES], ((i - 1) / AT_STAGES) & 1);
+            load_unit(i + 2);
+          }
+          ptx::mbar_wait_backoff(p_full, i & 1);
           ptx::tc_fence_after();
-          issue_s(i + 1);
+          issue_pv(i);
         }
-        if (i + 2 < n_units) {      // prefetch two units ahead; that stage held unit i-1
-          if (i >= 1) ptx::mbar_wait_backoff(&qkv_empty[(i + 2) % AT_STAGES], ((i - 1) / AT_STAGES) & 1);
-          load_unit(i + 2);
-        }
-        ptx::mbar_wait_backoff(p_full, i & 1);
-        ptx::tc_fence_after();
-        issue_pv(i);
+        __syncwarp();
       }
     }
   } else if (n_units > 0) {
@@ -233,8 +298,22 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
     ptx::mbar_wait(bias_bar, 0);
     const uint32_t brow = ptx::smem_u32(sBias) + rr * AT_BIAS_LD * 4 + third * 192;
 
+    // output row of this thread's query row for a unit: the window-ordered row, or with token_out the token row
+    // (-1: pad position, nothing is stored)
+    auto out_row = [&](int win) -> long long {
+      if (!p.token_out) return (long long)win * 144 + r;
+      int g_h = p.h, g_w = p.w, g_nwh = p.nwh, g_nww = p.nww; long long t0 = 0;
+      if (p.split_win > 0 && win >= p.split_win) { win -= p.split_win; g_h = p.h2; g_w = p.w2; g_nwh = p.nwh2; g_nww = p.nww2; t0 = p.tok2; }
+      const int g_nw = g_nwh * g_nww;
+      const int b = win / g_nw, wl = win - b * g_nw, wi = wl / g_nww, wj = wl - wi * g_nww;
+      const int pr = at_src_coord(wi, qi, p.shift, g_nwh * 12), pc = at_src_coord(wj, qj, p.shift, g_nww * 12);
+      if (pr >= g_h || pc >= g_w) return -1;
+      return t0 + ((long long)b * g_h + pr) * g_w + pc;
+    };
+    long long orow_prev = -1;       // output row of the unit whose epilogue is still pending
+
     auto epilogue = [&](int j) {   // O(j) / sum(j) -> 16-bit, head-major channel (src/swin.rs:306-307)
-      const int par = j & 1, win = w_first + j * w_step;
+      const int par = j & 1;
       ptx::mbar_wait(o_full, par);
       ptx::tc_fence_after();
       const float inv = 1.f / (ptx::lds32(ssum + ((par * 3 + 0) * 144 + rr) * 4) + ptx::lds32(ssum + ((par * 3 + 1) * 144 + rr) * 4) +
@@ -250,7 +329,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         uint32_t v[16];
         ptx::tmem_ld16(lane_base + AT_COL_O0 + third * 16, v);
         tmem_wait_dep(v);
-        uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)win * 144 + r) * p.ldo + head * 32 + third * 16);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)orow_prev * p.ldo + head * 32 + third * 16);
+        if (orow_prev >= 0)
 #pragma unroll
         for (int g = 0; g < 2; ++g)
           dst[g] = make_uint4(pack_scaled(v[8 * g], v[8 * g + 1]),
@@ -261,8 +341,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         uint32_t v[32];
         ptx::tmem_ld32(lane_base + AT_COL_O1, v);
         tmem_wait32(v);
-        if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)win * 144 + r) * p.ldo + head * 32);
+        if (row_ok && orow_prev >= 0) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)orow_prev * p.ldo + head * 32);
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             dst[g] = make_uint4(pack_scaled(v[8 * g], v[8 * g + 1]),
@@ -328,6 +408,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
 
       // ---- deferred epilogue of the previous unit (its P V finished long ago); also frees the P buffer ----
       if (i > 0) epilogue(i - 1);
+      orow_prev = row_ok ? out_row(win) : -1;
 
       // ---- pass 2: p = exp2((s - max) * log2e), partial row sum, 16-bit P -> shared (K-major, 32B swizzle) ----
       unsigned long long sum2 = pk2(0.f, 0.f);
@@ -380,6 +461,11 @@ void tc_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   p.nwh = a.nwh; p.nww = a.nww; p.shift = a.shift;
   p.split_win = a.split_win; p.nwh2 = a.nwh2; p.nww2 = a.nww2;
   p.out = (uint16_t*)a.out.p; p.ldo = a.out.ld;
+  p.h = a.h; p.w = a.w; p.h2 = a.h2; p.w2 = a.w2; p.token_out = a.token_out; p.tok2 = a.tok2;
+  p.bias16 = (const uint16_t*)a.qkv_bias16;
+  BRN_CHECK(a.h <= 0 || (a.qkv_bias16 && (((uintptr_t)a.qkv_bias16) & 15) == 0 && a.w > 0), 1,
+            "tc_attention: token geometry needs the 16-bit qkv bias");
+  BRN_CHECK(!a.token_out || a.h > 0, 1, "tc_attention: token-order output needs the token geometry");
   const uint64_t rows = (uint64_t)a.n_windows * 144;
   uint64_t dims[2] = {(uint64_t)3 * p.C, rows};
   uint64_t str[1] = {(uint64_t)a.qkv.ld * 2};

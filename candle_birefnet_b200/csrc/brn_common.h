@@ -79,6 +79,11 @@ struct LayerW {
   void* w_fp16 = nullptr;        // same, fp16 (precision fp16)
   const void* w16(int dt) const { return dt == F16 ? w_fp16 : w_bf16; }
   float* bias = nullptr;         // [N] fp32 or null
+  // LayerNorm folded into this linear layer (LnFold): sum_c of the ROUNDED 16-bit weights per output row, one array per
+  // operand type (the epilogue subtracts mean * colsum, which must cancel against what the MMA really multiplied)
+  float* colsum_bf16 = nullptr;
+  float* colsum_fp16 = nullptr;
+  const float* colsum(int dt) const { return dt == F16 ? colsum_fp16 : colsum_bf16; }
   int taps() const { return kh * kw; }
 };
 
@@ -89,12 +94,34 @@ enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_2SIGMOID_TAIL = 3 };
 // to a second token grid (the half-resolution backbone pass runs merged with the full-resolution one: same weights,
 // token matrices concatenated along M) with geometry (h2, w2, hp2, wp2), its tokens starting at row tok2.
 struct RowMap {
-  int enabled = 0;
+  int enabled = 0;               // 1: window-ordered padded row -> token row (proj; pad rows are skipped)
+                                 // 2: token row -> window-ordered padded row (qkv computed in token order and scattered
+                                 //    into the layout the attention kernel loads; pad rows are never written)
   int h = 0, w = 0, hp = 0, wp = 0, shift = 0;
   long long split = 0;           // 0: single segment
   int h2 = 0, w2 = 0, hp2 = 0, wp2 = 0;
   long long tok2 = 0;
 };
+
+// LayerNorm folded into the GEMM that consumes it (src/swin.rs:355,407 norm1 -> qkv,
+// norm2 -> fc1):  LN(x) W^T + b  =  rstd * (x (gamma .* W)^T  -  mean * colsum(gamma .* W))  +  (W beta + b).
+// The GEMM runs on the RAW 16-bit copy of the residual stream with gamma folded into the weights; the per-row
+// statistics come from the epilogue that produced the stream (LnEmit) as `parts` partial (sum, sum of squares)
+// pairs per row, summed here in a fixed order (deterministic: results do not depend on the batch an image is in).
+struct LnFold {
+  const float2* stats = nullptr;   // [parts][stride] (sum, sumsq) over disjoint column ranges of the row; null: off
+  int parts = 0;
+  long long stride = 0;            // rows per part
+  int C = 0;                       // row length the statistics cover
+};
+// Producer side: the epilogue that writes the fp32 residual stream also writes its raw 16-bit copy and the row
+// statistics of the values it stores (one partial per (N tile, column part)).
+struct LnEmit {
+  float2* stats = nullptr;         // [parts][stride]; null: off
+  long long stride = 0;
+  void* x16 = nullptr; int x16dt = BF16; int ldx16 = 0;
+};
+int tc_gemm_ln_parts(int N);       // partials per row an LnEmit epilogue writes for an N-column output
 
 // One implicit-GEMM problem: out[m, n] = act(sum_k A[m,k] W[n,k] + bias) (+ res[m,n]).
 // A is the conv patch matrix of `x` (NHWC, stride 1, zero padding `pad`), K order (tap, channel).
@@ -112,6 +139,8 @@ struct GemmArgs {
   int tile_w = 0;                // conv M tile = tile_w x (128 / tile_w) pixels (power of two); 0 = widest that fits W
   int out_tiled = 0;             // 1: fp32 out is [m_tile][N][128] (tile-major, row-in-tile fastest): the layout the
                                  //    deformable gather reads its offsets from with coalesced loads
+  LnFold lnf;                    // consumer of a folded LayerNorm (tcgen05 path only)
+  LnEmit lne;                    // producer of the statistics + raw 16-bit copy (tcgen05 path only)
   double flops = 0;
 };
 
@@ -138,6 +167,15 @@ struct AttnArgs {
   int shift = 0;          // 0: no mask at all (src/swin.rs:383)
   int split_win = 0;      // > 0: windows [split_win, n_windows) belong to a second grid with nwh2 x nww2 windows per image
   int nwh2 = 0, nww2 = 0;
+  // Token geometry (tcgen05 kernel).  h > 0: rows of a window that fall into the pad region of the [h, w] token grid
+  // get q = k = v = qkv_bias (pad tokens are zeros AFTER norm1, src/swin.rs:355-366, so their qkv is the bias) written
+  // into the staged tiles by the kernel itself -- the qkv matrix need not hold valid pad rows.
+  int h = 0, w = 0, h2 = 0, w2 = 0;
+  const void* qkv_bias16 = nullptr;   // [3C] in the operand type (q part pre-scaled); required when h > 0
+  // token_out: out is the TOKEN-ordered [tokens, C] matrix (window_reverse + roll back + crop, src/swin.rs:387-401, done
+  // by the store); second-grid tokens start at row tok2.  Otherwise out is window-ordered like qkv.
+  int token_out = 0;
+  long long tok2 = 0;
   View out;               // [rows, C]
 };
 
@@ -230,6 +268,7 @@ void glue_final(const LaunchCtx&, const float* x_nchw, int B, int H, int W, cons
 void build_final_table(const float* w1 /*[64][27]*/, const float* b1 /*[64]*/, const double* wc /*[64][9]*/, double bc,
                        float* tab /*[336]*/);
 void glue_copy_cast(const LaunchCtx&, View in, View out);
+void glue_ln_stats_cast(const LaunchCtx&, View x, View x16, float2* stats /*[rows] (sum, sumsq)*/);
 void glue_sigmoid(const LaunchCtx&, float* p, long long n);
 
 }  // namespace brn

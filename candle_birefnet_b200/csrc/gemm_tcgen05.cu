@@ -35,7 +35,7 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;            // warp 0 TMA, war
 constexpr int TC_A_BYTES = (TC_BM + 16) * TC_BK * 2;   // 18 KB: a 16x8-pixel tile plus one halo row above and below (tap groups)
 constexpr int TC_B_BYTES = 256 * TC_BK * 2;     // 32 KB (BN <= 256)
 constexpr int TC_BIAS_LD = 288;                                // floats per accumulator stage (BN <= 256, padded to 32)
-constexpr int TC_EPI_BYTES = TC_EPI_WARPS * EPI_STAGE_BYTES + 2 * TC_BIAS_LD * 4;
+constexpr int TC_EPI_BYTES = TC_EPI_WARPS * EPI_STAGE_BYTES + 4 * TC_BIAS_LD * 4;   // bias + LnFold column sums, x2 accumulator stages
 constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_EPI_BYTES + 256 + 1024;
 
 // Division by a run-time constant as multiply-high + shift (valid for numerators < 2^31): the epilogue warps derive
@@ -71,6 +71,7 @@ struct TcGemmP {
   FastDiv fd_ks;                       // ksplit
   FastDiv fd_rows1, fd_nww1;           // row map, first grid: rows per image (windows * 144), windows per row
   FastDiv fd_rows2, fd_nww2;           // second grid (merged two-resolution pass)
+  FastDiv fd_hw1, fd_w1, fd_hw2, fd_w2;   // row map mode 2 (token -> window row): tokens per image, tokens per row
 };
 
 // rowmap_token (device_utils.cuh) with the run-time divisions replaced; rows < 2^31
@@ -87,8 +88,28 @@ __device__ __forceinline__ long long window_row_to_token_fd(uint32_t m, int h, i
   if (r >= h || c >= w) return -1;
   return ((long long)b * h + r) * (long long)w + c;
 }
+// inverse map (RowMap mode 2): token row of the [B,h,w] grid -> its window-ordered padded row (pad -> roll(-shift) ->
+// window_partition, src/swin.rs:359-380)
+__device__ __forceinline__ long long token_to_window_row_fd(uint32_t m, int h, int w, int hp, int wp, int shift,
+                                                           const FastDiv& hw, const FastDiv& fw) {
+  const uint32_t b = hw.div(m);
+  const uint32_t rem = m - b * hw.d;
+  const uint32_t r = fw.div(rem), c = rem - r * fw.d;
+  int pr = (int)r - shift, pc = (int)c - shift;
+  if (pr < 0) pr += hp;
+  if (pc < 0) pc += wp;
+  const uint32_t wi = (uint32_t)pr / 12u, ti = (uint32_t)pr - wi * 12u;
+  const uint32_t wj = (uint32_t)pc / 12u, tj = (uint32_t)pc - wj * 12u;
+  const uint32_t nww = (uint32_t)wp / 12u, nw = ((uint32_t)hp / 12u) * nww;
+  return (long long)(b * nw + wi * nww + wj) * 144 + ti * 12u + tj;
+}
 __device__ __forceinline__ long long rowmap_token_fd(const TcGemmP& p, long long m) {
   const RowMap& rm = p.rm;
+  if (rm.enabled == 2) {
+    if (rm.split > 0 && m >= rm.tok2)
+      return rm.split + token_to_window_row_fd((uint32_t)(m - rm.tok2), rm.h2, rm.w2, rm.hp2, rm.wp2, rm.shift, p.fd_hw2, p.fd_w2);
+    return token_to_window_row_fd((uint32_t)m, rm.h, rm.w, rm.hp, rm.wp, rm.shift, p.fd_hw1, p.fd_w1);
+  }
   if (rm.split > 0 && m >= rm.split) {
     const long long t = window_row_to_token_fd((uint32_t)(m - rm.split), rm.h2, rm.w2, rm.hp2, rm.wp2, rm.shift,
                                                p.fd_rows2, p.fd_nww2);
@@ -103,7 +124,9 @@ __device__ __forceinline__ long long rowmap_token_fd(const TcGemmP& p, long long
 // 94 B/clk/SM needed to keep the tensor pipe busy).
 // EPI = epilogue variant compiled into this instance (one kernel per hot epilogue instead of a run-time switch over all
 // 18 variants inside one 27k-instruction kernel: per-variant register allocation, hot loop within the instruction cache).
-enum EpiKind { EK_GENERIC = 0, EK_NONE16, EK_RELU16, EK_GELU16, EK_NONE32, EK_SIG32_TILED, EK_RES32, EK_RES16 };
+enum EpiKind { EK_GENERIC = 0, EK_NONE16, EK_RELU16, EK_GELU16, EK_NONE32, EK_SIG32_TILED, EK_RES32, EK_RES16,
+               EK_LNF_NONE16, EK_LNF_GELU16,      // folded LayerNorm consumers (qkv, fc1)
+               EK_RES32_EMIT, EK_NONE32_EMIT };   // fp32 stream producers that also emit statistics + the raw 16-bit copy
 
 template <int CL, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -114,7 +137,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sB = smem + TC_STAGES * TC_A_BYTES;
   uint8_t* sStage = sB + TC_STAGES * TC_B_BYTES;                 // epilogue staging, 2 KB per epilogue warp
   float* sBias = (float*)(sStage + TC_EPI_WARPS * EPI_STAGE_BYTES);
-  uint64_t* full = (uint64_t*)((uint8_t*)sBias + 2 * TC_BIAS_LD * 4);
+  float* sCs = sBias + 2 * TC_BIAS_LD;                           // LnFold column sums, staged like the bias
+  uint64_t* full = (uint64_t*)((uint8_t*)sBias + 4 * TC_BIAS_LD * 4);
   uint64_t* empty = full + TC_STAGES;
   uint64_t* tfull = empty + TC_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -241,6 +265,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int y = ty * TH + (row >> p.tw_log2), x = tx * TW + (row & (TW - 1));
       const bool valid = m_tile < p.m_tiles && y < p.H && x < p.W;
       long long orow = valid ? ((long long)b * p.H + y) * p.W + x : -1;
+      constexpr bool kLnf = EPI == EK_LNF_NONE16 || EPI == EK_LNF_GELU16;
+      float nmu = 0.f, rstd = 1.f;
+      if (kLnf && valid) lnf_row_stats(p.epi, orow, nmu, rstd);     // issued before the accumulator wait
       if (valid && p.rm.enabled) orow = rowmap_token_fd(p, orow);
       if (valid) orow += ks * p.rows_total;
       const int n0 = n_tile * p.BN;
@@ -253,8 +280,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // this tile's bias -> shared (double buffered with the accumulator stage; an M tile lies inside one image).
         // Staged unconditionally (zeros without a bias): an optional add costs a register move per element.
         const float* bias = p.epi.bias ? p.epi.bias + (long long)(m_tile < p.m_tiles ? b : 0) * p.epi.bias_bstride : nullptr;
-        for (int t = eth; t < TC_BIAS_LD; t += 32 * TC_EPI_WARPS)
+        for (int t = eth; t < TC_BIAS_LD; t += 32 * TC_EPI_WARPS) {
           ptx::sts32(sb + t * 4, (bias && t < p.BN && n0 + t < p.epi.N) ? __ldg(bias + n0 + t) : 0.f);
+          if (kLnf)
+            ptx::sts32(ptx::smem_u32(sCs) + (acc * TC_BIAS_LD + t) * 4,
+                       (t < p.BN && n0 + t < p.epi.N) ? __ldg(p.epi.lnf_colsum + n0 + t) : 0.f);
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
       }
       ptx::mbar_wait(&tfull[acc], acc_phase);
@@ -267,6 +298,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       else if (EPI == EK_NONE32) epi_warp<ACT_NONE, true, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
       else if (EPI == EK_RES32) epi_warp<ACT_NONE, true, 1>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
       else if (EPI == EK_RES16) epi_warp<ACT_NONE, false, 2>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
+      else if (EPI == EK_LNF_NONE16)
+        epi_warp<ACT_NONE, false, 0, true, true, false>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane, nmu, rstd,
+                                                        ptx::smem_u32(sCs) + acc * TC_BIAS_LD * 4);
+      else if (EPI == EK_LNF_GELU16)
+        epi_warp<ACT_GELU, false, 0, true, true, false>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane, nmu, rstd,
+                                                        ptx::smem_u32(sCs) + acc * TC_BIAS_LD * 4);
+      else if (EPI == EK_RES32_EMIT)
+        epi_warp<ACT_NONE, true, 1, false, false, true>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane, 0.f, 1.f, 0,
+                                                        n_tile * PER_Q + part);
+      else if (EPI == EK_NONE32_EMIT)
+        epi_warp<ACT_NONE, true, 0, true, false, true>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane, 0.f, 1.f, 0,
+                                                       n_tile * PER_Q + part);
       else if (EPI == EK_SIG32_TILED) {
         if (m_tile < p.m_tiles) epi_warp_tiled<ACT_2SIGMOID_TAIL>(p.epi, taddr, n0, c0, c1, m_tile, row, sbb);
       } else if (p.out_tiled) {
@@ -343,6 +386,12 @@ EpiP make_epi(int N, const float* bias, int bias_bstride, int act, int act_from,
   e.vec = (((uintptr_t)out.p & 15) == 0) && ((out.ld * dsize(out.dt)) % 16 == 0) &&
           (!res.p || ((((uintptr_t)res.p & 15) == 0) && ((res.ld * dsize(res.dt)) % 16 == 0)));
   return e;
+}
+
+static int pick_bn(int N);
+int tc_gemm_ln_parts(int N) {
+  const int bn = pick_bn(N);
+  return ((N + bn - 1) / bn) * (TC_EPI_WARPS / 4);
 }
 
 static int pick_bn(int N) {
@@ -448,6 +497,24 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   p.fd_nt = FastDiv((uint32_t)p.n_tiles);
   p.fd_tpi = FastDiv((uint32_t)(p.tiles_x * p.tiles_y));
   p.fd_tx = FastDiv((uint32_t)p.tiles_x);
+  if (p.rm.enabled == 2) {
+    p.fd_hw1 = FastDiv((uint32_t)(p.rm.h * p.rm.w)); p.fd_w1 = FastDiv((uint32_t)p.rm.w);
+    if (p.rm.split > 0) { p.fd_hw2 = FastDiv((uint32_t)(p.rm.h2 * p.rm.w2)); p.fd_w2 = FastDiv((uint32_t)p.rm.w2); }
+  }
+  if (a.lnf.stats) {
+    BRN_CHECK(S == 1 && !a.out_tiled && !a.res.p && a.out.dt != F32 && w.taps() == 1 && w.colsum(a.x.dt) &&
+              (a.act == ACT_NONE || a.act == ACT_GELU) && a.lnf.C == w.Cin && a.lnf.parts > 0, 5,
+              "tc_gemm: LnFold needs a 1x1 layer with column sums, a 16-bit output and act none|gelu");
+    p.epi.lnf_stats = a.lnf.stats; p.epi.lnf_parts = a.lnf.parts; p.epi.lnf_stride = a.lnf.stride;
+    p.epi.lnf_invC = 1.0f / (float)a.lnf.C; p.epi.lnf_colsum = w.colsum(a.x.dt);
+  }
+  if (a.lne.stats) {
+    BRN_CHECK(S == 1 && !a.out_tiled && a.out.dt == F32 && a.act == ACT_NONE && w.N % 16 == 0 && p.epi.vec &&
+              (!a.res.p || a.res.dt == F32) && a.lne.x16 && a.lne.ldx16 % 4 == 0 && (((uintptr_t)a.lne.x16) & 7) == 0, 5,
+              "tc_gemm: LnEmit needs an fp32 output with N % 16 == 0 and aligned rows");
+    p.epi.lne_stats = a.lne.stats; p.epi.lne_stride = a.lne.stride;
+    p.epi.x16 = a.lne.x16; p.epi.x16dt = a.lne.x16dt; p.epi.ldx16 = a.lne.ldx16;
+  }
   if (p.rm.enabled) {
     BRN_CHECK((long long)a.x.rows() < (1ll << 31), 5, "tc_gemm: row map needs fewer than 2^31 rows");
     p.fd_rows1 = FastDiv((uint32_t)((p.rm.hp / 12) * (p.rm.wp / 12) * 144));
@@ -491,6 +558,11 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
     else ek = a.act == ACT_NONE ? EK_NONE32 : EK_GENERIC;
   } else if (a.act == ACT_NONE && o32 && a.res.dt == F32 && p.epi.vec) ek = EK_RES32;
   else if (a.act == ACT_NONE && !o32 && a.res.dt == a.out.dt && p.epi.vec && w.N % 8 == 0) ek = EK_RES16;
+  if (a.lnf.stats) ek = a.act == ACT_GELU ? EK_LNF_GELU16 : EK_LNF_NONE16;
+  if (a.lne.stats) {
+    BRN_CHECK(ek == EK_RES32 || ek == EK_NONE32, 5, "tc_gemm: LnEmit on an unsupported epilogue variant");
+    ek = ek == EK_RES32 ? EK_RES32_EMIT : EK_NONE32_EMIT;
+  }
 
   auto launch = [&](auto kern) {
     BRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
@@ -510,6 +582,7 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   switch (ek) {
     TC_EK_CASE(EK_NONE16); TC_EK_CASE(EK_RELU16); TC_EK_CASE(EK_GELU16); TC_EK_CASE(EK_NONE32);
     TC_EK_CASE(EK_SIG32_TILED); TC_EK_CASE(EK_RES32); TC_EK_CASE(EK_RES16);
+    TC_EK_CASE(EK_LNF_NONE16); TC_EK_CASE(EK_LNF_GELU16); TC_EK_CASE(EK_RES32_EMIT); TC_EK_CASE(EK_NONE32_EMIT);
     default: if (CL == 2) launch(tc_gemm_kernel<2, EK_GENERIC>); else launch(tc_gemm_kernel<1, EK_GENERIC>); break;
   }
 #undef TC_EK_CASE

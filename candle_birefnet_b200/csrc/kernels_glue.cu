@@ -333,6 +333,31 @@ void glue_copy_cast(const LaunchCtx& ctx, View in, View out) {
   BRN_CUDA(cudaGetLastError());
 }
 
+// Row statistics + raw 16-bit copy of an fp32 matrix: what an LnEmit epilogue produces (one partial per row), for
+// streams that no GEMM epilogue wrote (operator-level entry brn_ln_linear).  One warp per row.
+__global__ void __launch_bounds__(256) ln_stats_cast_kernel(const float* __restrict__ x, int ldx, long long rows, int C,
+                                                            void* x16, int dt, int ld16, float2* stats) {
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= rows) return;
+  float s = 0.f, q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float v = x[m * ldx + c];
+    s += v; q = fmaf(v, v, q);
+    g_st(x16, dt, m * ld16 + c, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if (lane == 0) stats[m] = make_float2(s, q);
+}
+void glue_ln_stats_cast(const LaunchCtx& ctx, View x, View x16, float2* stats) {
+  GLUE_LAUNCH_PROLOGUE(ctx);
+  BRN_CHECK(x.dt == F32 && x16.dt != F32, 5, "ln_stats_cast: fp32 in, 16-bit out");
+  ln_stats_cast_kernel<<<(unsigned)((x.rows() + 7) / 8), 256, 0, ctx.stream>>>((const float*)x.p, x.ld, x.rows(), x.C, x16.p,
+                                                                             x16.dt, x16.ld, stats);
+  BRN_CUDA(cudaGetLastError());
+}
+
 __global__ void sigmoid_kernel(float* p, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 1.f / (1.f + expf(-p[i]));

@@ -11,6 +11,8 @@
 
 namespace brn {
 
+static bool env_flag(const char* n);
+
 static const int kIptIn[5] = {3, 48, 192, 768, 3072};     // image2patches channel counts 3*g*g
 static const int kIptOut[5] = {48, 96, 192, 384, 384};    // src/birefnet.rs:180
 
@@ -219,7 +221,7 @@ static uint16_t f2h(float f) {
 }
 
 LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w, const float* bias,
-                             std::vector<void*>& allocs) {
+                             std::vector<void*>& allocs, bool folded_ln) {
   LayerW L;
   L.N = N; L.Cin = Cin; L.kh = kh; L.kw = kw;
   L.cin_pad = (Cin + 63) / 64 * 64;
@@ -234,8 +236,27 @@ LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w, con
         wbf[((size_t)n * taps + t) * L.cin_pad + c] = f2bf(v);
         wfp[((size_t)n * taps + t) * L.cin_pad + c] = f2h(v);
       }
-  BRN_CUDA(cudaMalloc(&L.w32, w32.size() * 4)); allocs.push_back(L.w32);
-  BRN_CUDA(cudaMemcpy(L.w32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice));
+  if (!folded_ln) {      // a gamma-folded copy is only ever read by the tensor-core path
+    BRN_CUDA(cudaMalloc(&L.w32, w32.size() * 4)); allocs.push_back(L.w32);
+    BRN_CUDA(cudaMemcpy(L.w32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice));
+  } else {
+    // column sums of the weights AS ROUNDED: the LnFold epilogue computes acc - mean * colsum, and acc was
+    // accumulated from the rounded values
+    std::vector<float> cb(N), cf(N);
+    for (int n = 0; n < N; ++n) {
+      double sb = 0, sf = 0;
+      for (size_t i = 0; i < (size_t)taps * L.cin_pad; ++i) {
+        uint32_t ub = (uint32_t)wbf[(size_t)n * taps * L.cin_pad + i] << 16; float fb; memcpy(&fb, &ub, 4);
+        __half hh; memcpy(&hh, &wfp[(size_t)n * taps * L.cin_pad + i], 2);
+        sb += fb; sf += __half2float(hh);
+      }
+      cb[n] = (float)sb; cf[n] = (float)sf;
+    }
+    BRN_CUDA(cudaMalloc(&L.colsum_bf16, (size_t)N * 4)); allocs.push_back(L.colsum_bf16);
+    BRN_CUDA(cudaMemcpy(L.colsum_bf16, cb.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+    BRN_CUDA(cudaMalloc(&L.colsum_fp16, (size_t)N * 4)); allocs.push_back(L.colsum_fp16);
+    BRN_CUDA(cudaMemcpy(L.colsum_fp16, cf.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+  }
   BRN_CUDA(cudaMalloc(&L.w_bf16, wbf.size() * 2)); allocs.push_back(L.w_bf16);
   BRN_CUDA(cudaMemcpy(L.w_bf16, wbf.data(), wbf.size() * 2, cudaMemcpyHostToDevice));
   BRN_CUDA(cudaMalloc(&L.w_fp16, wfp.size() * 2)); allocs.push_back(L.w_fp16);
@@ -247,9 +268,26 @@ LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w, con
   return L;
 }
 
-LayerW Model::make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w, const std::vector<float>* bias) {
+LayerW Model::make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w, const std::vector<float>* bias,
+                         bool folded_ln) {
   BRN_CHECK(w.size() == (size_t)N * Cin * kh * kw, 5, "internal: make_layer size");
-  return make_layer_standalone(N, Cin, kh, kw, w.data(), bias ? bias->data() : nullptr, allocs);
+  return make_layer_standalone(N, Cin, kh, kw, w.data(), bias ? bias->data() : nullptr, allocs, folded_ln);
+}
+
+// LayerNorm folded into the linear layer that consumes it:
+//   LN(x) W^T + b = rstd * (x (gamma .* W)^T - mean * colsum(gamma .* W)) + (W beta + b)
+LayerW Model::make_folded(const std::vector<float>& w, const std::vector<float>& b, const std::vector<float>& gamma,
+                          const std::vector<float>& beta, int N, int C) {
+  std::vector<float> wf((size_t)N * C), bf(N);
+  for (int n = 0; n < N; ++n) {
+    double acc = b[n];
+    for (int c = 0; c < C; ++c) {
+      wf[(size_t)n * C + c] = (float)((double)w[(size_t)n * C + c] * gamma[c]);
+      acc += (double)w[(size_t)n * C + c] * beta[c];
+    }
+    bf[n] = (float)acc;
+  }
+  return make_layer(N, C, 1, 1, wf, &bf, true);
 }
 
 // eval BatchNorm as (scale, shift): y = x*scale + shift  (candle batch_norm(C,1e-5).forward_t(x,false))
@@ -318,9 +356,17 @@ void Model::finalize() {
           b[r] = (float)((double)b[r] * scale);
         }
         B.qkv = make_layer(3 * Ci, Ci, 1, 1, w, &b);
+        B.qkv_f = make_folded(w, b, T(p + ".norm1.weight").data, T(p + ".norm1.bias").data, 3 * Ci, Ci);
+        // qkv of a pad token = the (q-scaled) bias, in both operand types: [3C] bf16 then [3C] fp16
+        std::vector<uint16_t> b16((size_t)6 * Ci);
+        for (int n = 0; n < 3 * Ci; ++n) { b16[n] = f2bf(b[n]); b16[3 * Ci + n] = f2h(b[n]); }
+        BRN_CUDA(cudaMalloc(&B.qkv_bias16, b16.size() * 2)); allocs.push_back(B.qkv_bias16);
+        BRN_CUDA(cudaMemcpy(B.qkv_bias16, b16.data(), b16.size() * 2, cudaMemcpyHostToDevice));
       }
       B.proj = linear(p + ".attn.proj", true);
       B.fc1 = linear(p + ".mlp.fc1", true);
+      B.fc1_f = make_folded(T(p + ".mlp.fc1.weight").data, T(p + ".mlp.fc1.bias").data, T(p + ".norm2.weight").data,
+                            T(p + ".norm2.bias").data, cfg.mlp_ratio * Ci, Ci);
       B.fc2 = linear(p + ".mlp.fc2", true);
       {
         // WindowAttention::new (src/swin.rs:143-152): bias[h,q,k] = table[index[q,k], h],
@@ -547,6 +593,10 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
     LnArgs l; l.x = g.out; l.gamma = pe_g; l.beta = pe_b; l.out = g.out; l.mode = LN_PLAIN;
     glue_layernorm(ctx, l);
   }
+  // LayerNorm folding needs the tcgen05 epilogues (16-column granules: C % 16 == 0 holds for head_dim 32)
+  const bool fold = ctx.precision != BRN_PREC_FP32 && !ctx.force_simt && !env_flag("BRN_LN_UNFUSED");
+  bool have_stats = false;          // x16 / stats describe the current residual stream
+  View next_x16{}; float2* next_stats = nullptr;
   for (int i = 0; i < 4; ++i) {
     const int Ci = C(i), heads = cfg.num_heads[i];
     int hp[2], wp[2]; long long Tp[2] = {0, 0};
@@ -556,37 +606,81 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
     BRN_CHECK(Tpt < (1ll << 31), 5, "too many tokens for one pass: lower micro_batch");
     View xt = make_view(xbuf, F32, 1, 1, (int)Tt, Ci);          // token-matrix view of the residual stream (both grids)
     auto grid_view = [&](int s) { return make_view(xbuf + (size_t)(s ? T[0] : 0) * Ci, F32, B, h[s], w[s], Ci); };
+    // Tensor-core path: LayerNorm is folded into the GEMM that consumes it (LnFold / LnEmit, brn_common.h).  The
+    // epilogue that writes the fp32 residual stream (proj, fc2, the PatchMerging reduction) also writes its raw 16-bit
+    // copy `x16` and per-row (sum, sumsq) partials `stats`; qkv and fc1 run on x16 with gamma folded into their weights
+    // and apply mean / rstd in their own epilogues.  All four GEMMs of a block run in TOKEN order: the qkv epilogue
+    // scatters rows into the window-ordered padded layout the attention kernel loads (pad rows are synthesised inside
+    // that kernel), and attention stores straight back to token order -- norm1 -> pad -> roll -> partition and
+    // window_reverse -> roll -> crop (src/swin.rs:355-401) never exist as passes.
+    View x16{}; float2* stats = nullptr; int parts = 0;
+    if (fold) {
+      parts = tc_gemm_ln_parts(Ci);
+      if (have_stats) {     // the previous stage's reduction GEMM emitted into these buffers
+        x16 = next_x16; stats = next_stats;
+      } else {
+        x16 = make_view(arena.alloc((size_t)Tt * Ci * dsize(AD)), AD, 1, 1, (int)Tt, Ci);
+        stats = (float2*)arena.alloc((size_t)parts * Tt * sizeof(float2));
+      }
+    }
+    auto emit = [&](GemmArgs& g) {
+      if (!fold) return;
+      g.lne.stats = stats; g.lne.stride = Tt; g.lne.x16 = x16.p; g.lne.x16dt = AD; g.lne.ldx16 = Ci;
+    };
+    auto folded = [&](GemmArgs& g) { g.lnf.stats = stats; g.lnf.parts = parts; g.lnf.stride = Tt; g.lnf.C = Ci; };
     for (size_t j = 0; j < stages[i].blocks.size(); ++j) {
       const BlockW& bw = stages[i].blocks[j];
       const int shift = (j % 2 == 0) ? 0 : 6;          // src/swin.rs:552
       const size_t mb = arena.mark();
-      // norm1 -> pad -> roll -> partition (src/swin.rs:355-380) in one gather kernel per grid
-      View xw = make_view(arena.alloc((size_t)Tpt * Ci * dsize(AD)), AD, 1, 1, (int)Tpt, Ci);
-      {
+      View qkv = make_view(arena.alloc((size_t)Tpt * 3 * Ci * dsize(AD)), AD, 1, 1, (int)Tpt, 3 * Ci);
+      View xw{};
+      RowMap wmap;      // window-ordered padded rows <-> token rows of the (merged) grids
+      wmap.h = h[0]; wmap.w = w[0]; wmap.hp = hp[0]; wmap.wp = wp[0]; wmap.shift = shift;
+      if (nseg > 1) { wmap.split = Tp[0]; wmap.h2 = h[1]; wmap.w2 = w[1]; wmap.hp2 = hp[1]; wmap.wp2 = wp[1]; wmap.tok2 = T[0]; }
+      if (fold && have_stats) {
+        // norm1 folded: qkv = LN(x) Wqkv^T + b on the raw 16-bit stream, rows scattered to the window layout
+        GemmArgs g; g.x = x16; g.w = &bw.qkv_f; g.out = qkv; folded(g);
+        g.rowmap = wmap; g.rowmap.enabled = 2;
+        BRN_CHECK(tc_gemm_supported(g), 5, "folded qkv: tcgen05 path unavailable");
+        tc_gemm(ctx, g);
+      } else {
+        // norm1 -> pad -> roll -> partition (src/swin.rs:355-380) in one gather kernel per grid
+        xw = make_view(arena.alloc((size_t)Tpt * Ci * dsize(AD)), AD, 1, 1, (int)Tpt, Ci);
         LnArgs l; l.x = grid_view(0); l.gamma = bw.n1g; l.beta = bw.n1b; l.out = xw;
         l.mode = LN_WINDOW; l.hp = hp[0]; l.wp = wp[0]; l.shift = shift;
         if (nseg > 1) { l.split = Tp[0]; l.tok2 = T[0]; l.h2 = h[1]; l.w2 = w[1]; l.hp2 = hp[1]; l.wp2 = wp[1]; }
         glue_layernorm(ctx, l);
+        GemmArgs g; g.x = xw; g.w = &bw.qkv; g.out = qkv; op_gemm(ctx, g);
       }
-      View qkv = make_view(arena.alloc((size_t)Tpt * 3 * Ci * dsize(AD)), AD, 1, 1, (int)Tpt, 3 * Ci);
-      { GemmArgs g; g.x = xw; g.w = &bw.qkv; g.out = qkv; op_gemm(ctx, g); }
-      View ao = make_view(xw.p, AD, 1, 1, (int)Tpt, Ci);   // reuse the xw buffer (qkv GEMM has consumed it)
+      // attention output: token order on the tensor-core path, window order on the SIMT path
+      View ao = fold ? make_view(arena.alloc((size_t)Tt * Ci * dsize(AD)), AD, 1, 1, (int)Tt, Ci)
+                     : make_view(xw.p, AD, 1, 1, (int)Tpt, Ci);   // SIMT: reuse the xw buffer (qkv GEMM has consumed it)
       { AttnArgs a; a.qkv = qkv; a.bias32 = bw.bias32; a.bias32p = bw.bias32p; a.n_windows = (int)(Tpt / 144);
         a.heads = heads; a.nwh = hp[0] / 12; a.nww = wp[0] / 12; a.shift = shift; a.out = ao;
         if (nseg > 1) { a.split_win = (int)(Tp[0] / 144); a.nwh2 = hp[1] / 12; a.nww2 = wp[1] / 12; }
+        if (fold) {
+          a.h = h[0]; a.w = w[0]; a.h2 = h[1]; a.w2 = w[1]; a.tok2 = T[0]; a.token_out = 1;
+          a.qkv_bias16 = bw.qkv_bias16 + (AD == F16 ? 3 * Ci : 0);
+        }
         op_attention(ctx, a); }
-      // proj + window_reverse + roll back + crop + residual (src/swin.rs:310,387-406)
+      // proj (+ window_reverse + roll back + crop on the SIMT path) + residual (src/swin.rs:310,387-406)
       { GemmArgs g; g.x = ao; g.w = &bw.proj; g.out = xt; g.res = xt;
-        g.rowmap.enabled = 1; g.rowmap.h = h[0]; g.rowmap.w = w[0]; g.rowmap.hp = hp[0]; g.rowmap.wp = wp[0]; g.rowmap.shift = shift;
-        if (nseg > 1) { g.rowmap.split = Tp[0]; g.rowmap.h2 = h[1]; g.rowmap.w2 = w[1]; g.rowmap.hp2 = hp[1]; g.rowmap.wp2 = wp[1];
-                        g.rowmap.tok2 = T[0]; }
+        if (!fold) { g.rowmap = wmap; g.rowmap.enabled = 1; }
+        emit(g);
         op_gemm(ctx, g); }
       // x + fc2(gelu(fc1(norm2(x))))  (src/swin.rs:407)
-      View xn = make_view(arena.alloc((size_t)Tt * Ci * dsize(AD)), AD, 1, 1, (int)Tt, Ci);
-      { LnArgs l; l.x = xt; l.gamma = bw.n2g; l.beta = bw.n2b; l.out = xn; l.mode = LN_PLAIN; glue_layernorm(ctx, l); }
       View hd = make_view(arena.alloc((size_t)Tt * cfg.mlp_ratio * Ci * dsize(AD)), AD, 1, 1, (int)Tt, cfg.mlp_ratio * Ci);
-      { GemmArgs g; g.x = xn; g.w = &bw.fc1; g.act = ACT_GELU; g.out = hd; op_gemm(ctx, g); }
-      { GemmArgs g; g.x = hd; g.w = &bw.fc2; g.out = xt; g.res = xt; op_gemm(ctx, g); }
+      if (fold) {
+        GemmArgs g; g.x = x16; g.w = &bw.fc1_f; g.act = ACT_GELU; g.out = hd; folded(g);
+        BRN_CHECK(tc_gemm_supported(g), 5, "folded fc1: tcgen05 path unavailable");
+        tc_gemm(ctx, g);
+      } else {
+        View xn = make_view(arena.alloc((size_t)Tt * Ci * dsize(AD)), AD, 1, 1, (int)Tt, Ci);
+        { LnArgs l; l.x = xt; l.gamma = bw.n2g; l.beta = bw.n2b; l.out = xn; l.mode = LN_PLAIN; glue_layernorm(ctx, l); }
+        GemmArgs g; g.x = xn; g.w = &bw.fc1; g.act = ACT_GELU; g.out = hd; op_gemm(ctx, g);
+      }
+      { GemmArgs g; g.x = hd; g.w = &bw.fc2; g.out = xt; g.res = xt; emit(g); op_gemm(ctx, g); }
+      have_stats = fold;
       arena.release(mb);
     }
     // norm{i} -> NCHW view (src/swin.rs:784-788): written straight into the caller's NHWC slices
@@ -610,6 +704,12 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
       }
       float* xnew = (float*)arena.alloc((size_t)T2t * 2 * Ci * 4);
       { GemmArgs g; g.x = xm; g.w = &stages[i].red; g.out = make_view(xnew, F32, 1, 1, (int)T2t, 2 * Ci);
+        if (fold) {     // the next stage's first norm1 is folded too: this epilogue produces its statistics
+          next_x16 = make_view(arena.alloc((size_t)T2t * 2 * Ci * dsize(AD)), AD, 1, 1, (int)T2t, 2 * Ci);
+          next_stats = (float2*)arena.alloc((size_t)tc_gemm_ln_parts(2 * Ci) * T2t * sizeof(float2));
+          g.lne.stats = next_stats; g.lne.stride = T2t; g.lne.x16 = next_x16.p; g.lne.x16dt = AD; g.lne.ldx16 = 2 * Ci;
+          have_stats = true;
+        }
         op_gemm(ctx, g); }
       xbuf = xnew;
       for (int s = 0; s < nseg; ++s) { h[s] = h2[s]; w[s] = w2[s]; }

@@ -39,6 +39,8 @@ struct Arena {
 struct BlockW {
   float *n1g, *n1b, *n2g, *n2b;
   LayerW qkv, proj, fc1, fc2;
+  LayerW qkv_f, fc1_f;     // norm1 / norm2 folded in (gamma into the weights, W beta into the bias): tensor-core path
+  uint16_t* qkv_bias16 = nullptr;   // [2][3C]: the q-scaled qkv bias as bf16, then as fp16 (qkv of a pad token)
   float* bias32;           // [heads][144][144]
   float* bias32p;          // [heads][144][148] (padded rows, tcgen05 attention kernel)
 };
@@ -183,7 +185,10 @@ struct Model {
 
   const HostTensor& T(const std::string& k) const;
   float* upload(const std::vector<float>& v);
-  LayerW make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w_oihw, const std::vector<float>* bias);
+  LayerW make_layer(int N, int Cin, int kh, int kw, const std::vector<float>& w_oihw, const std::vector<float>* bias,
+                    bool folded_ln = false);
+  LayerW make_folded(const std::vector<float>& w, const std::vector<float>& b, const std::vector<float>& gamma,
+                     const std::vector<float>& beta, int N, int C);
 };
 
 // safetensors_loader.cpp: sets every tensor of `path` that the schema knows; returns how many were set
@@ -196,6 +201,6 @@ void op_attention(const LaunchCtx&, const AttnArgs&);
 
 // standalone layer upload for the operator-level ABI
 LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w_oihw, const float* bias,
-                             std::vector<void*>& allocs);
+                             std::vector<void*>& allocs, bool folded_ln = false);
 
 }  // namespace brn

@@ -22,7 +22,25 @@ struct EpiP {
   const void* res; int resdt; int ldres;
   void* out; int odt; int ldo;
   int vec;       // out (and res) base pointers and row pitches are 16-byte aligned
+  // LayerNorm fold, consumer side (LnFold): per-row (sum, sumsq) partials of the fp32 stream the A operand was rounded from
+  const float2* lnf_stats; int lnf_parts; long long lnf_stride; float lnf_invC;
+  const float* lnf_colsum;   // [N] column sums of the rounded gamma-folded weights
+  // producer side (LnEmit): statistics + raw 16-bit copy of the rows this epilogue stores
+  float2* lne_stats; long long lne_stride; void* x16; int x16dt; int ldx16;
 };
+
+// row statistics of a folded LayerNorm: the partials are summed in index order (deterministic)
+__device__ __forceinline__ void lnf_row_stats(const EpiP& p, long long arow, float& nmu, float& rstd) {
+  float s = 0.f, q = 0.f;
+  for (int i = 0; i < p.lnf_parts; ++i) {
+    const float2 t = __ldg(p.lnf_stats + (long long)i * p.lnf_stride + arow);
+    s += t.x; q += t.y;
+  }
+  const float mu = s * p.lnf_invC;
+  const float var = fmaxf(fmaf(-mu, mu, q * p.lnf_invC), 0.f);
+  nmu = -mu;
+  rstd = rsqrtf(var + 1e-5f);
+}
 
 constexpr int EPI_STAGE_BYTES = 32 * 64;   // per epilogue warp
 
@@ -153,10 +171,21 @@ __device__ __forceinline__ float epi_act(float f, int col, int act_from) {
 //   mode 1: fp32 residual + fp32 output, added in phase B (coalesced LDG.128)
 //   mode 2: 16-bit residual of a 16-bit output, added packed in phase B (coalesced LDG.128; one extra 16-bit rounding)
 //   mode 3: anything else, scalar loads in phase A
-template <int ACT, bool O32, int RM, bool PP = (RM == 0)>
+// LNF : folded LayerNorm -- value = rstd * (acc - mean * colsum[col]) + bias[col]; `nmu` = -mean and `rstd` of THIS
+//       lane's row (phase A geometry), `scs` = SHARED address of the staged column sums (indexed like sbias).
+// EMIT: (fp32 output only) the stored rows' raw 16-bit copy goes to p.x16 and their (sum, sumsq) over this warp's
+//       columns to p.lne_stats[part_idx * stride + row] (phase-B geometry: the values after the residual add).
+template <int ACT, bool O32, int RM, bool PP = (RM == 0), bool LNF = false, bool EMIT = false>
 __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, int c0, int c1, long long orow,
-                                         uint32_t sbias, uint32_t stage, int lane) {
-  if (c0 >= c1) return;
+                                         uint32_t sbias, uint32_t stage, int lane, float nmu = 0.f, float rstd = 1.f,
+                                         uint32_t scs = 0, int part_idx = 0) {
+  static_assert(!EMIT || O32, "LnEmit needs the fp32 output path");
+  if (c0 >= c1) {
+    if (EMIT) {   // an empty column part still owns a statistics slot: zeros
+      if (orow >= 0) p.lne_stats[(long long)part_idx * p.lne_stride + orow] = make_float2(0.f, 0.f);
+    }
+    return;
+  }
   constexpr int GC = O32 ? 16 : 32;       // columns per 64-byte granule
   constexpr int PER = O32 ? 4 : 8;        // elements per 16-byte chunk
   constexpr int ESZ = O32 ? 4 : 2;
@@ -208,6 +237,12 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
   if (rmode == 1 || rmode == 2) { res_issue(c0, rq0); res_issue(c0 + GC, rq1); }
   // every row of this warp is a real output row: the interior store path needs no per-row predicate
   const bool rows_ok = __all_sync(0xffffffffu, orow >= 0);
+  float es[EMIT ? 4 : 1], eq[EMIT ? 4 : 1];
+  if (EMIT) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) { es[it] = 0.f; eq[it] = 0.f; }
+  }
+  const unsigned long long nmu2 = pk2(nmu, nmu), rstd2 = pk2(rstd, rstd);
 
   auto granule = [&](int c, uint4 (&rq)[4], uint32_t (&v)[GC], uint32_t* vn) {
     const int ncol = min(GC, c1 - c);
@@ -226,11 +261,24 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
     for (int j = 0; j < GC; ++j) f[j] = __uint_as_float(v[j]);
     if (!PP) load_next();
     // the bias is always staged (zeros when the layer has none)
+    if (LNF) {
 #pragma unroll
-    for (int j = 0; j < GC; j += 4) {
-      const uint4 bv = ptx::lds128(sbias + (c + j) * 4);
-      add2(f[j], f[j + 1], __uint_as_float(bv.x), __uint_as_float(bv.y));
-      add2(f[j + 2], f[j + 3], __uint_as_float(bv.z), __uint_as_float(bv.w));
+      for (int j = 0; j < GC; j += 4) {
+        const uint4 bv = ptx::lds128(sbias + (c + j) * 4), cv = ptx::lds128(scs + (c + j) * 4);
+        unsigned long long t0 = fma2(nmu2, pk2(__uint_as_float(cv.x), __uint_as_float(cv.y)), pk2(f[j], f[j + 1]));
+        unsigned long long t1 = fma2(nmu2, pk2(__uint_as_float(cv.z), __uint_as_float(cv.w)), pk2(f[j + 2], f[j + 3]));
+        t0 = fma2(rstd2, t0, pk2(__uint_as_float(bv.x), __uint_as_float(bv.y)));
+        t1 = fma2(rstd2, t1, pk2(__uint_as_float(bv.z), __uint_as_float(bv.w)));
+        upk2(t0, f[j], f[j + 1]);
+        upk2(t1, f[j + 2], f[j + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < GC; j += 4) {
+        const uint4 bv = ptx::lds128(sbias + (c + j) * 4);
+        add2(f[j], f[j + 1], __uint_as_float(bv.x), __uint_as_float(bv.y));
+        add2(f[j + 2], f[j + 3], __uint_as_float(bv.z), __uint_as_float(bv.w));
+      }
     }
     if (ACT == ACT_GELU) {
 #pragma unroll
@@ -288,6 +336,21 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
         val[it].z = add16x2(val[it].z, rq[it].z, p.odt); val[it].w = add16x2(val[it].w, rq[it].w, p.odt);
       }
     }
+    if (EMIT) {
+      // LnEmit (N % 16 == 0 and vec are launch preconditions, so every granule is whole): statistics of the stored fp32
+      // values and their raw 16-bit copy, 8 bytes per lane (32 contiguous bytes = one sector per row)
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const float4 fv = *reinterpret_cast<const float4*>(&val[it]);
+        es[it] += (fv.x + fv.y) + (fv.z + fv.w);
+        eq[it] = fmaf(fv.x, fv.x, fmaf(fv.y, fv.y, fmaf(fv.z, fv.z, fmaf(fv.w, fv.w, eq[it]))));
+        if (orow_b[it] >= 0) {
+          const uint2 h = p.x16dt == BF16 ? make_uint2(pack_bf16x2(fv.x, fv.y), pack_bf16x2(fv.z, fv.w))
+                                          : make_uint2(pack_f16x2(fv.x, fv.y), pack_f16x2(fv.z, fv.w));
+          *reinterpret_cast<uint2*>((uint16_t*)p.x16 + orow_b[it] * p.ldx16 + n0 + c + kb * 4) = h;
+        }
+      }
+    }
     if (rows_ok && p.vec && ncol == GC && n0 + c + GC <= p.N) {
       // interior granule: four unpredicated 16-byte stores
 #pragma unroll
@@ -329,6 +392,16 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
     } else {
       granule(c, rq0, va, va);
       if (c + GC < c1) granule(c + GC, rq1, va, va);
+    }
+  }
+  if (EMIT) {
+    // the four lanes of a row (16-byte chunks kb = 0..3) hold its partial sums: fixed-order butterfly, lane kb = 0 writes
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      es[it] += __shfl_xor_sync(0xffffffffu, es[it], 1); eq[it] += __shfl_xor_sync(0xffffffffu, eq[it], 1);
+      es[it] += __shfl_xor_sync(0xffffffffu, es[it], 2); eq[it] += __shfl_xor_sync(0xffffffffu, eq[it], 2);
+      if (kb == 0 && orow_b[it] >= 0)
+        p.lne_stats[(long long)part_idx * p.lne_stride + orow_b[it]] = make_float2(es[it], eq[it]);
     }
   }
 }

@@ -31,6 +31,17 @@ def linear(a, w, bias=None, residual=None, act: int = 0, precision: str = "bf16"
     return out
 
 
+def ln_linear(x, gamma, beta, w, bias=None, act: int = 0, precision: str = "fp16", device: int = 0) -> np.ndarray:
+    """LayerNorm folded into the consuming linear layer (norm1 -> qkv, norm2 -> fc1; src/swin.rs:355,217,407,104)."""
+    x, gamma, beta, w, bias = _f32(x), _f32(gamma), _f32(beta), _f32(w), _f32(bias)
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape == (N, K) and gamma.shape == (K,) and beta.shape == (K,)
+    out = np.empty((M, N), dtype=np.float32)
+    check(lib().brn_ln_linear(device, _PREC[precision], _p(x), _p(gamma), _p(beta), _p(w), _p(bias), M, N, K, act, _p(out)))
+    return out
+
+
 def conv2d(x, weight, bias=None, act: int = 0, precision: str = "bf16", device: int = 0) -> np.ndarray:
     """candle_nn::conv2d, stride 1, padding k//2, NCHW."""
     x, weight, bias = _f32(x), _f32(weight), _f32(bias)

@@ -184,6 +184,14 @@ BRN_API brn_status brn_deform_conv2d(int device, int precision, const float* x, 
 BRN_API brn_status brn_linear(int device, int precision, const float* a, const float* w, const float* bias,
                       const float* residual, int32_t M, int32_t N, int32_t K, int32_t act, float* out);
 
+/* act(LayerNorm(x; gamma, beta, eps 1e-5) W^T + bias) with the LayerNorm FOLDED into the GEMM the way the Swin blocks
+ * run it on the tensor-core path (norm1 -> qkv, norm2 -> fc1: src/swin.rs:355,217 and :407,104): the GEMM reads the raw
+ * 16-bit copy of x with gamma folded into W, the epilogue applies rstd * (acc - mean * colsum) + (W beta + bias).
+ * x: HOST fp32 [M,K]; out: HOST fp32 [M,N] (values rounded to the 16-bit operand type on the way).  precision must be
+ * BRN_PREC_BF16 or BRN_PREC_FP16.  act: 0 none, 2 exact-erf gelu. */
+BRN_API brn_status brn_ln_linear(int device, int precision, const float* x, const float* gamma, const float* beta,
+                         const float* w, const float* bias, int32_t M, int32_t N, int32_t K, int32_t act, float* out);
+
 /* conv2d, stride 1, zero padding k/2, NCHW fp32 HOST tensors (candle_nn::conv2d; src/decoder.rs:44-45,104,113). */
 BRN_API brn_status brn_conv2d(int device, int precision, const float* x, const float* weight, const float* bias, int32_t B,
                       int32_t C, int32_t H, int32_t W, int32_t O, int32_t k, int32_t act, float* out);

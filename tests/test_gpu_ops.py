@@ -120,3 +120,36 @@ def test_window_attention(nimg, hp, wp, heads, shift, precision):
     err = np.abs(got - exp).max()
     # 16-bit paths: q (scaled), bias, P and the output are rounded to bf16 / fp16; |out| <= ~1
     assert err < {"bf16": 3e-2, "fp16": 4e-3, "fp32": 2e-5}[precision], err
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 576, 192), (1000, 1152, 384), (777, 3072, 768), (200, 4608, 1536)])
+@pytest.mark.parametrize("mean_over_std", [0.0, 3.0, 30.0])
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("act", [0, 2])
+def test_ln_linear_fold(M, N, K, mean_over_std, precision, act):
+    """LayerNorm folded into the consuming GEMM (norm1 -> qkv, norm2 -> fc1) against
+    F.layer_norm -> linear in fp64.  The epilogue forms rstd * (acc - mean * colsum) + bias': with |row mean| >> row std
+    acc and mean * colsum are both large and must cancel (fp32 accumulate, column sums of the ROUNDED weights), and the
+    raw 16-bit copy of x carries a rounding error relative to |x|, not |x - mean| -- the tolerance scales with that."""
+    if act == 2 and (K != 768 or mean_over_std == 30.0):
+        pytest.skip("GELU variant: one shape")
+    rng = np.random.default_rng(M + N + K + int(mean_over_std))
+    x = rng.standard_normal((M, K))
+    x = x * rng.uniform(0.5, 4.0, size=(M, 1)) + mean_over_std * rng.uniform(0.5, 1.5, size=(M, 1)) * np.sign(rng.standard_normal((M, 1)))
+    x = x.astype(np.float32)
+    gamma = (1.0 + 0.1 * rng.standard_normal(K)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(K)).astype(np.float32)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    got = cb.ops.ln_linear(x, gamma, beta, w, b, act=act, precision=precision)
+    xd = torch.from_numpy(x).double()
+    ln = F.layer_norm(xd, (K,), torch.from_numpy(gamma).double(), torch.from_numpy(beta).double(), 1e-5)
+    exp = ln @ torch.from_numpy(w).double().T + torch.from_numpy(b).double()
+    if act == 2:
+        exp = F.gelu(exp)
+    exp = exp.numpy()
+    eps = 2.0 ** -11 if precision == "fp16" else 2.0 ** -8
+    # operand rounding (x relative to |x|/std, W) + output rounding, on O(1) outputs of K-term sums
+    tol = eps * (4.0 + 2.0 * (1.0 + mean_over_std))
+    err = np.abs(got - exp).max() / max(1.0, np.abs(exp).max())
+    assert err < tol, (err, tol)
