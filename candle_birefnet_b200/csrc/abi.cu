@@ -279,9 +279,11 @@ brn_status brn_ln_linear(int device, int precision, const float* x, const float*
     View x16 = make_view(s.alloc((size_t)M * K * 2), AD, 1, 1, M, K);
     float2* stats = (float2*)s.alloc((size_t)M * sizeof(float2));
     glue_ln_stats_cast(ctx, x32, x16, stats);
+    float2* mr = (float2*)s.alloc((size_t)M * sizeof(float2));
+    glue_ln_finalize(ctx, stats, 1, M, M, K, mr);
     View o16 = make_view(s.alloc((size_t)M * N * 2), AD, 1, 1, M, N);
     GemmArgs g; g.x = x16; g.w = &L; g.act = act; g.out = o16;
-    g.lnf.stats = stats; g.lnf.parts = 1; g.lnf.stride = M; g.lnf.C = K;
+    g.lnf.mr = mr; g.lnf.C = K;
     BRN_CHECK(tc_gemm_supported(g), 5, "brn_ln_linear: K must be a multiple of 8");
     tc_gemm(ctx, g);
     View o32 = make_view(s.alloc((size_t)M * N * 4), F32, 1, 1, M, N);
@@ -371,6 +373,63 @@ brn_status brn_window_attention(int device, int precision, const float* qkv, con
     View o32 = o;
     if (AD != F32) { o32 = make_view(s.alloc(rows * C * 4), F32, 1, 1, (int)rows, C); glue_copy_cast(ctx, o, o32); }
     BRN_CUDA(cudaMemcpyAsync(out, o32.p, rows * C * 4, cudaMemcpyDeviceToHost, s.stream));
+    BRN_CUDA(cudaStreamSynchronize(s.stream));
+  });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pre / post-processing: the steps either side of forward_logits in examples/infer_image.rs
+// ---------------------------------------------------------------------------------------------------------------
+brn_status brn_preprocess_rgb8(int device, const uint8_t* rgb, int32_t B, int32_t h, int32_t w, int32_t H, int32_t W,
+                               float* out) {
+  return guard([&] {
+    BRN_CHECK(rgb && out && B > 0 && h > 0 && w > 0 && H > 0 && W > 0, 1, "brn_preprocess_rgb8: bad argument");
+    Scratch s(device);
+    const size_t nin = (size_t)B * h * w * 3, nout = (size_t)B * 3 * H * W;
+    uint8_t* din = (uint8_t*)s.alloc(nin);
+    BRN_CUDA(cudaMemcpyAsync(din, rgb, nin, cudaMemcpyHostToDevice, s.stream));
+    float* tmp = (float*)s.alloc((size_t)B * H * w * 3 * 4);
+    float* dout = (float*)s.alloc(nout * 4);
+    prepost_preprocess(s.stream, din, B, h, w, H, W, tmp, dout);
+    BRN_CUDA(cudaMemcpyAsync(out, dout, nout * 4, cudaMemcpyDeviceToHost, s.stream));
+    BRN_CUDA(cudaStreamSynchronize(s.stream));
+  });
+}
+
+brn_status brn_postprocess_mask(int device, const float* logits, int32_t B, int32_t H, int32_t W, int32_t orig_h,
+                                int32_t orig_w, uint8_t* out) {
+  return guard([&] {
+    BRN_CHECK(logits && out && B > 0 && H > 0 && W > 0 && orig_h > 0 && orig_w > 0, 1, "brn_postprocess_mask: bad argument");
+    Scratch s(device);
+    float* dl = s.put(logits, (size_t)B * H * W);
+    uint8_t* m8 = (uint8_t*)s.alloc((size_t)B * H * W);
+    float* tmp = (float*)s.alloc((size_t)B * orig_h * W * 4);
+    uint8_t* dout = (uint8_t*)s.alloc((size_t)B * orig_h * orig_w);
+    prepost_postprocess(s.stream, dl, 0, B, H, W, orig_h, orig_w, m8, tmp, dout);
+    BRN_CUDA(cudaMemcpyAsync(out, dout, (size_t)B * orig_h * orig_w, cudaMemcpyDeviceToHost, s.stream));
+    BRN_CUDA(cudaStreamSynchronize(s.stream));
+  });
+}
+
+brn_status brn_infer_rgb8(brn_model* m, const uint8_t* rgb, int32_t B, int32_t h, int32_t w, int32_t H, int32_t W,
+                          uint8_t* masks) {
+  return guard([&] {
+    BRN_CHECK(m && rgb && masks && B > 0 && h > 0 && w > 0, 1, "brn_infer_rgb8: bad argument");
+    BRN_CHECK(H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, 5, "H and W must be positive multiples of 32");
+    Scratch s(m->impl.device);
+    const size_t nin = (size_t)B * h * w * 3;
+    uint8_t* din = (uint8_t*)s.alloc(nin);
+    BRN_CUDA(cudaMemcpyAsync(din, rgb, nin, cudaMemcpyHostToDevice, s.stream));
+    const size_t tmp_floats = std::max((size_t)B * H * w * 3, (size_t)B * h * W);
+    float* tmp = (float*)s.alloc(tmp_floats * 4);
+    float* dx = (float*)s.alloc((size_t)B * 3 * H * W * 4);
+    float* dl = (float*)s.alloc((size_t)B * H * W * 4);
+    uint8_t* m8 = (uint8_t*)s.alloc((size_t)B * H * W);
+    uint8_t* dout = (uint8_t*)s.alloc((size_t)B * h * w);
+    prepost_preprocess(s.stream, din, B, h, w, H, W, tmp, dx);
+    m->impl.forward(dx, B, H, W, true, dl, true, s.stream, false);     // enqueued on the same stream
+    prepost_postprocess(s.stream, dl, 0, B, H, W, h, w, m8, tmp, dout);
+    BRN_CUDA(cudaMemcpyAsync(masks, dout, (size_t)B * h * w, cudaMemcpyDeviceToHost, s.stream));
     BRN_CUDA(cudaStreamSynchronize(s.stream));
   });
 }

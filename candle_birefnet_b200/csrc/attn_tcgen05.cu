@@ -66,6 +66,7 @@ struct AttnP {
   int h, w, h2, w2;
   int token_out; long long tok2;
   const uint16_t* bias16;        // [3C] qkv bias in the operand type
+  FastDiv fd_nw1, fd_nww1, fd_nw2, fd_nww2;   // windows per image / per window row, both grids
 };
 
 // padded-grid coordinate of window-local index t (0..11) of window index wi: (12 wi + t + shift) mod hp
@@ -73,6 +74,39 @@ __device__ __forceinline__ int at_src_coord(int wi, int t, int shift, int hp) {
   int r = wi * 12 + t + shift;
   return r >= hp ? r - hp : r;
 }
+
+// (grid, image, window row, window column) of a window index; the divisions are multiply-high (FastDiv)
+struct AtGeo {
+  int g2, b, wi, wj;
+};
+__device__ __forceinline__ AtGeo at_geo(const AttnP& p, int win) {
+  AtGeo g;
+  g.g2 = (p.split_win > 0 && win >= p.split_win) ? 1 : 0;
+  if (g.g2) win -= p.split_win;
+  const FastDiv& fnw = g.g2 ? p.fd_nw2 : p.fd_nw1;
+  const FastDiv& fnww = g.g2 ? p.fd_nww2 : p.fd_nww1;
+  g.b = (int)fnw.div((uint32_t)win);
+  const int wl = win - g.b * (int)fnw.d;
+  g.wi = (int)fnww.div((uint32_t)wl);
+  g.wj = wl - g.wi * (int)fnww.d;
+  return g;
+}
+// does the window hold any pad position of its [h, w] token grid?  Its rows cover padded coordinates
+// [12 wi + shift, 12 wi + shift + 12) mod hp; the pad region is [h, hp).
+__device__ __forceinline__ bool at_has_pad(const AttnP& p, const AtGeo& g) {
+  const int nwh = g.g2 ? p.nwh2 : p.nwh, nww = g.g2 ? p.nww2 : p.nww, h = g.g2 ? p.h2 : p.h, w = g.g2 ? p.w2 : p.w;
+  const int hp = nwh * 12, wp = nww * 12;
+  const int a = g.wi * 12 + p.shift, c = g.wj * 12 + p.shift;
+  const bool rp = hp > h && (a + 12 > hp || a + 11 >= h);
+  const bool cp = wp > w && (c + 12 > wp || c + 11 >= w);
+  return rp || cp;
+}
+__device__ __forceinline__ bool at_row_is_pad(const AttnP& p, const AtGeo& g, int ti, int tj) {
+  const int nwh = g.g2 ? p.nwh2 : p.nwh, nww = g.g2 ? p.nww2 : p.nww, h = g.g2 ? p.h2 : p.h, w = g.g2 ? p.w2 : p.w;
+  return at_src_coord(g.wi, ti, p.shift, nwh * 12) >= h || at_src_coord(g.wj, tj, p.shift, nww * 12) >= w;
+}
+
+
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -174,29 +208,19 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         ptx::tma_load_2d(st + 2 * AT_TILE_BYTES, &tmQKV, &qkv_full[s], 2 * p.C + head * 32, win * 144);
       };
       // Pad tokens are zeros AFTER norm1 (src/swin.rs:355-366), so their q, k, v equal the qkv bias and they take part
-      // as keys.  The token-order qkv GEMM never computes those rows: write them into the staged tiles here (64B
-      // swizzle: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)).  Warp-uniform early out for the
-      // windows that hold no pad position (all but the last window row / column of a grid).
-      auto fix_pads = [&](int i) {
+      // as keys.  The token-order qkv GEMM never computes those rows: they are written into the staged tiles (64B
+      // swizzle: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)) -- for unit 0 by this warp, for every later
+      // unit by the softmax warps just before they release S (480 threads: a few stores each; this warp alone would
+      // need a whole unit time for the loop and stall the MMA issue).
+      auto fix_pads0 = [&]() {
         if (p.h <= 0) return;
-        int win = w_first + i * w_step;
-        int g_h = p.h, g_w = p.w, g_nwh = p.nwh, g_nww = p.nww;
-        if (p.split_win > 0 && win >= p.split_win) { win -= p.split_win; g_h = p.h2; g_w = p.w2; g_nwh = p.nwh2; g_nww = p.nww2; }
-        const int hp = g_nwh * 12, wp = g_nww * 12;
-        if (hp == g_h && wp == g_w) return;
-        const int wl = win % (g_nwh * g_nww), wi = wl / g_nww, wj = wl - wi * g_nww;
-        uint32_t rmask = 0, cmask = 0;
-#pragma unroll
-        for (int t = 0; t < 12; ++t) {
-          rmask |= (at_src_coord(wi, t, p.shift, hp) >= g_h ? 1u : 0u) << t;
-          cmask |= (at_src_coord(wj, t, p.shift, wp) >= g_w ? 1u : 0u) << t;
-        }
-        if ((rmask | cmask) == 0) return;
-        const uint32_t base = ptx::smem_u32(sQKV + (i % AT_STAGES) * AT_STAGE_BYTES);
+        const AtGeo g = at_geo(p, w_first);
+        if (!at_has_pad(p, g)) return;
+        const uint32_t base = ptx::smem_u32(sQKV);
         const int ch = lane & 3;
         for (int r = lane >> 2; r < 144; r += 8) {
           const int ti = r / 12, tj = r - ti * 12;
-          if (((rmask >> ti) | (cmask >> tj)) & 1u) {
+          if (at_row_is_pad(p, g, ti, tj)) {
             const uint32_t a = base + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
 #pragma unroll
             for (int t = 0; t < 3; ++t) ptx::sts128(a + t * AT_TILE_BYTES, bq[t]);
@@ -248,24 +272,18 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         if (n_units > 1) load_unit(1);
       }
       ptx::mbar_wait(&qkv_full[0], 0);
-      fix_pads(0);
+      fix_pads0();
       __syncwarp();
       if (leader) {
         ptx::tc_fence_after();
         issue_s(0);
-      }
-      for (int i = 0; i < n_units; ++i) {
-        if (i + 1 < n_units) {      // S of the next unit as soon as this unit's scores sit in registers
-          ptx::mbar_wait_backoff(&qkv_full[(i + 1) % AT_STAGES], ((i + 1) / AT_STAGES) & 1);
-          fix_pads(i + 1);
-          __syncwarp();
-          if (leader) {
+        for (int i = 0; i < n_units; ++i) {
+          if (i + 1 < n_units) {      // S of the next unit as soon as this unit's scores sit in registers (and its pad rows are patched)
+            ptx::mbar_wait_backoff(&qkv_full[(i + 1) % AT_STAGES], ((i + 1) / AT_STAGES) & 1);
             ptx::mbar_wait_backoff(s_empty, i & 1);
             ptx::tc_fence_after();
             issue_s(i + 1);
           }
-        }
-        if (leader) {
           if (i + 2 < n_units) {      // prefetch two units ahead; that stage held unit i-1
             if (i >= 1) ptx::mbar_wait_backoff(&qkv_empty[(i + 2) % AT_STAGES], ((i - 1) / AT_STAGES) & 1);
             load_unit(i + 2);
@@ -274,8 +292,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
           ptx::tc_fence_after();
           issue_pv(i);
         }
-        __syncwarp();
       }
+      __syncwarp();
     }
   } else if (n_units > 0) {
     // ===== softmax + epilogue =====
@@ -294,22 +312,35 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
     const uint32_t smax = ptx::smem_u32(sStat);                // [par][third][144]
     const uint32_t ssum = smax + 2 * 3 * 144 * 4;
     const uint32_t sP_a = ptx::smem_u32(sP);
-    const int nw = p.nwh * p.nww;
     ptx::mbar_wait(bias_bar, 0);
     const uint32_t brow = ptx::smem_u32(sBias) + rr * AT_BIAS_LD * 4 + third * 192;
 
     // output row of this thread's query row for a unit: the window-ordered row, or with token_out the token row
     // (-1: pad position, nothing is stored)
-    auto out_row = [&](int win) -> long long {
+    auto out_row = [&](int win, const AtGeo& g) -> long long {
       if (!p.token_out) return (long long)win * 144 + r;
-      int g_h = p.h, g_w = p.w, g_nwh = p.nwh, g_nww = p.nww; long long t0 = 0;
-      if (p.split_win > 0 && win >= p.split_win) { win -= p.split_win; g_h = p.h2; g_w = p.w2; g_nwh = p.nwh2; g_nww = p.nww2; t0 = p.tok2; }
-      const int g_nw = g_nwh * g_nww;
-      const int b = win / g_nw, wl = win - b * g_nw, wi = wl / g_nww, wj = wl - wi * g_nww;
-      const int pr = at_src_coord(wi, qi, p.shift, g_nwh * 12), pc = at_src_coord(wj, qj, p.shift, g_nww * 12);
+      const int g_h = g.g2 ? p.h2 : p.h, g_w = g.g2 ? p.w2 : p.w, g_nwh = g.g2 ? p.nwh2 : p.nwh, g_nww = g.g2 ? p.nww2 : p.nww;
+      const int pr = at_src_coord(g.wi, qi, p.shift, g_nwh * 12), pc = at_src_coord(g.wj, qj, p.shift, g_nww * 12);
       if (pr >= g_h || pc >= g_w) return -1;
-      return t0 + ((long long)b * g_h + pr) * g_w + pc;
+      return (g.g2 ? p.tok2 : 0) + ((long long)g.b * g_h + pr) * g_w + pc;
     };
+    // pad rows of the NEXT unit's staged q / k / v tiles (see fix_pads0): thread t < 432 owns row t % 144 of tile t / 144
+    auto fix_pads_next = [&](int i1, const AtGeo& g) {
+      ptx::mbar_wait(&qkv_full[i1 % AT_STAGES], (i1 / AT_STAGES) & 1);
+      const int t = threadIdx.x;
+      if (t < 432) {
+        const int tq = t / 144, row = t - tq * 144;
+        const int ti = row / 12, tj = row - ti * 12;
+        if (at_row_is_pad(p, g, ti, tj)) {
+          const uint4* bsrc = reinterpret_cast<const uint4*>(p.bias16 + (size_t)tq * p.C + head * 32);
+          const uint32_t a = ptx::smem_u32(sQKV + (i1 % AT_STAGES) * AT_STAGE_BYTES) + tq * AT_TILE_BYTES + row * 64;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) ptx::sts128(a + ((ch ^ ((row >> 1) & 3)) << 4), __ldg(bsrc + ch));
+        }
+      }
+      ptx::fence_proxy_async_smem();
+    };
+    AtGeo geo = at_geo(p, w_first);
     long long orow_prev = -1;       // output row of the unit whose epilogue is still pending
 
     auto epilogue = [&](int j) {   // O(j) / sum(j) -> 16-bit, head-major channel (src/swin.rs:306-307)
@@ -357,10 +388,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       const int par = i & 1, win = w_first + i * w_step;
       // analytic shift mask (src/swin.rs:603-655): only the last window row / column mixes regions.  Key c of this
       // third sits at ki = 4*third + c/12, kj = c%12; interior windows take the mask-free path.
-      int g_nwh = p.nwh, g_nww = p.nww, g_nw = nw, g_win = win;
-      if (p.split_win > 0 && win >= p.split_win) { g_nwh = p.nwh2; g_nww = p.nww2; g_nw = p.nwh2 * p.nww2; g_win = win - p.split_win; }
-      const int wl = g_win % g_nw, wi = wl / g_nww, wj = wl - wi * g_nww;
-      const bool last_r = p.shift > 0 && wi == g_nwh - 1, last_c = p.shift > 0 && wj == g_nww - 1;
+      const int g_nwh = geo.g2 ? p.nwh2 : p.nwh, g_nww = geo.g2 ? p.nww2 : p.nww;
+      const bool last_r = p.shift > 0 && geo.wi == g_nwh - 1, last_c = p.shift > 0 && geo.wj == g_nww - 1;
 
       // ---- scores: TMEM -> registers once, then hand the S region back to the MMA warp ----
       uint32_t v0[32], v1[16];
@@ -369,6 +398,12 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       ptx::tmem_ld32(lane_base + s_col, v0);
       ptx::tmem_ld16(lane_base + s_col + 32, v1);
       tmem_wait32(v0); tmem_wait_dep(v1);
+      // geometry of the next unit; its pad rows are patched before S is released (the MMA warp issues S(i+1) then)
+      const AtGeo geo_cur = geo;
+      if (i + 1 < n_units) {
+        geo = at_geo(p, win + w_step);
+        if (p.h > 0 && at_has_pad(p, geo)) fix_pads_next(i + 1, geo);
+      }
       ptx::tc_fence_before();
       ptx::mbar_arrive(s_empty);
 
@@ -408,7 +443,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
 
       // ---- deferred epilogue of the previous unit (its P V finished long ago); also frees the P buffer ----
       if (i > 0) epilogue(i - 1);
-      orow_prev = row_ok ? out_row(win) : -1;
+      orow_prev = row_ok ? out_row(win, geo_cur) : -1;
 
       // ---- pass 2: p = exp2((s - max) * log2e), partial row sum, 16-bit P -> shared (K-major, 32B swizzle) ----
       unsigned long long sum2 = pk2(0.f, 0.f);
@@ -463,6 +498,8 @@ void tc_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   p.out = (uint16_t*)a.out.p; p.ldo = a.out.ld;
   p.h = a.h; p.w = a.w; p.h2 = a.h2; p.w2 = a.w2; p.token_out = a.token_out; p.tok2 = a.tok2;
   p.bias16 = (const uint16_t*)a.qkv_bias16;
+  p.fd_nw1 = FastDiv((uint32_t)(a.nwh * a.nww)); p.fd_nww1 = FastDiv((uint32_t)a.nww);
+  if (a.split_win > 0) { p.fd_nw2 = FastDiv((uint32_t)(a.nwh2 * a.nww2)); p.fd_nww2 = FastDiv((uint32_t)a.nww2); }
   BRN_CHECK(a.h <= 0 || (a.qkv_bias16 && (((uintptr_t)a.qkv_bias16) & 15) == 0 && a.w > 0), 1,
             "tc_attention: token geometry needs the 16-bit qkv bias");
   BRN_CHECK(!a.token_out || a.h > 0, 1, "tc_attention: token-order output needs the token geometry");

@@ -109,10 +109,8 @@ struct RowMap {
 // statistics come from the epilogue that produced the stream (LnEmit) as `parts` partial (sum, sum of squares)
 // pairs per row, summed here in a fixed order (deterministic: results do not depend on the batch an image is in).
 struct LnFold {
-  const float2* stats = nullptr;   // [parts][stride] (sum, sumsq) over disjoint column ranges of the row; null: off
-  int parts = 0;
-  long long stride = 0;            // rows per part
-  int C = 0;                       // row length the statistics cover
+  const float2* mr = nullptr;      // [rows] (-mean, rstd) of the fp32 stream (glue_ln_finalize); null: off
+  int C = 0;                       // row length the statistics cover (checked against the layer's K)
 };
 // Producer side: the epilogue that writes the fp32 residual stream also writes its raw 16-bit copy and the row
 // statistics of the values it stores (one partial per (N tile, column part)).
@@ -269,6 +267,14 @@ void build_final_table(const float* w1 /*[64][27]*/, const float* b1 /*[64]*/, c
                        float* tab /*[336]*/);
 void glue_copy_cast(const LaunchCtx&, View in, View out);
 void glue_ln_stats_cast(const LaunchCtx&, View x, View x16, float2* stats /*[rows] (sum, sumsq)*/);
+// (sum, sumsq) partials [parts][stride] -> (-mean, rstd) [rows], partials added in index order (deterministic); eps 1e-5
+void glue_ln_finalize(const LaunchCtx&, const float2* stats, int parts, long long stride, long long rows, int C, float2* mr);
 void glue_sigmoid(const LaunchCtx&, float* p, long long n);
+
+// ---- pre / post-processing around the hot path: prepost.cu (examples/infer_image.rs:44-67, 85-105) ----
+void prepost_preprocess(cudaStream_t st, const uint8_t* src_dev, int B, int h, int w, int H, int W, float* scratch_dev,
+                        float* out_dev);
+void prepost_postprocess(cudaStream_t st, const float* logits_dev, int already_prob, int B, int H, int W, int oh, int ow,
+                         uint8_t* m8_dev, float* scratch_dev, uint8_t* out_dev);
 
 }  // namespace brn

@@ -6,6 +6,24 @@
 
 namespace brn {
 
+// Division by a run-time constant as multiply-high + shift (valid for numerators < 2^31): the epilogue warps derive
+// the tile coordinates and the window row map per tile, and a hardware-less integer division is ~20 instructions.
+struct FastDiv {
+  uint32_t d = 1, mul = 0, shr = 0;
+  FastDiv() = default;
+  explicit FastDiv(uint32_t div) : d(div) {
+    if (div > 1) {
+      uint32_t lg = 0;
+      while ((1ull << lg) < div) ++lg;
+      const uint32_t pw = 31 + lg;
+      mul = (uint32_t)(((1ull << pw) + div - 1) / div);
+      shr = pw - 32;
+    }
+  }
+  __host__ __device__ __forceinline__ uint32_t div_any(uint32_t n) const { return n / d; }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d != 1 ? __umulhi(n, mul) >> shr : n; }
+};
+
 // Window-ordered padded row m (batch-major, window id, token ti*12+tj; src/swin.rs:446-459) -> token row of the
 // un-shifted, un-padded [B,h,w] grid, or -1 for a pad position.  Inverse of pad -> roll(-shift) -> partition
 // (src/swin.rs:359-380) == window_reverse -> roll(+shift) -> crop (src/swin.rs:387-401).

@@ -38,23 +38,6 @@ constexpr int TC_BIAS_LD = 288;                                // floats per acc
 constexpr int TC_EPI_BYTES = TC_EPI_WARPS * EPI_STAGE_BYTES + 4 * TC_BIAS_LD * 4;   // bias + LnFold column sums, x2 accumulator stages
 constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_EPI_BYTES + 256 + 1024;
 
-// Division by a run-time constant as multiply-high + shift (valid for numerators < 2^31): the epilogue warps derive
-// the tile coordinates and the window row map per tile, and a hardware-less integer division is ~20 instructions.
-struct FastDiv {
-  uint32_t d = 1, mul = 0, shr = 0;
-  FastDiv() = default;
-  explicit FastDiv(uint32_t div) : d(div) {
-    if (div > 1) {
-      uint32_t lg = 0;
-      while ((1ull << lg) < div) ++lg;
-      const uint32_t pw = 31 + lg;
-      mul = (uint32_t)(((1ull << pw) + div - 1) / div);
-      shr = pw - 32;
-    }
-  }
-  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d != 1 ? __umulhi(n, mul) >> shr : n; }
-};
-
 struct TcGemmP {
   int B, H, W;
   int tw_log2, tiles_x, tiles_y;
@@ -256,6 +239,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t stage = ptx::smem_u32(sStage) + (warp - 2) * EPI_STAGE_BYTES;
     const bool o32 = p.epi.odt == F32;
     int acc = 0; uint32_t acc_phase = 0;
+    // A-matrix row of this thread's tile row for a work item (-1: past the end / outside the image)
+    auto a_row_of = [&](int item) -> long long {
+      if (item >= num_items) return -1;
+      const int it2 = (int)p.fd_ks.div((uint32_t)item);
+      const int mg = (int)p.fd_nt.div((uint32_t)it2);
+      const int m_tile = mg * CL + rank;
+      const int b = (int)p.fd_tpi.div((uint32_t)m_tile), r = m_tile - b * tiles_per_img;
+      const int ty = (int)p.fd_tx.div((uint32_t)r), tx = r - ty * p.tiles_x;
+      const int y = ty * TH + (row >> p.tw_log2), x = tx * TW + (row & (TW - 1));
+      if (!(m_tile < p.m_tiles && y < p.H && x < p.W)) return -1;
+      return ((long long)b * p.H + y) * p.W + x;
+    };
+    float2 mr_next = make_float2(0.f, 1.f);
+    if (EPI == EK_LNF_NONE16 || EPI == EK_LNF_GELU16) {
+      const long long a0 = a_row_of(item0);
+      if (a0 >= 0) mr_next = __ldg(p.epi.lnf_mr + a0);
+    }
     for (int item = item0; item < num_items; item += item_step) {
       const int it2 = (int)p.fd_ks.div((uint32_t)item), ks = item - it2 * p.ksplit;
       const int mg = (int)p.fd_nt.div((uint32_t)it2);
@@ -266,8 +266,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = m_tile < p.m_tiles && y < p.H && x < p.W;
       long long orow = valid ? ((long long)b * p.H + y) * p.W + x : -1;
       constexpr bool kLnf = EPI == EK_LNF_NONE16 || EPI == EK_LNF_GELU16;
+      // LnFold: this row's (-mean, rstd) was fetched during the previous tile's epilogue; fetch the next tile's now
       float nmu = 0.f, rstd = 1.f;
-      if (kLnf && valid) lnf_row_stats(p.epi, orow, nmu, rstd);     // issued before the accumulator wait
+      if (kLnf) {
+        nmu = mr_next.x; rstd = mr_next.y;
+        const long long an = a_row_of(item + item_step);
+        if (an >= 0) mr_next = __ldg(p.epi.lnf_mr + an);
+      }
       if (valid && p.rm.enabled) orow = rowmap_token_fd(p, orow);
       if (valid) orow += ks * p.rows_total;
       const int n0 = n_tile * p.BN;
@@ -501,12 +506,11 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
     p.fd_hw1 = FastDiv((uint32_t)(p.rm.h * p.rm.w)); p.fd_w1 = FastDiv((uint32_t)p.rm.w);
     if (p.rm.split > 0) { p.fd_hw2 = FastDiv((uint32_t)(p.rm.h2 * p.rm.w2)); p.fd_w2 = FastDiv((uint32_t)p.rm.w2); }
   }
-  if (a.lnf.stats) {
+  if (a.lnf.mr) {
     BRN_CHECK(S == 1 && !a.out_tiled && !a.res.p && a.out.dt != F32 && w.taps() == 1 && w.colsum(a.x.dt) &&
-              (a.act == ACT_NONE || a.act == ACT_GELU) && a.lnf.C == w.Cin && a.lnf.parts > 0, 5,
+              (a.act == ACT_NONE || a.act == ACT_GELU) && a.lnf.C == w.Cin, 5,
               "tc_gemm: LnFold needs a 1x1 layer with column sums, a 16-bit output and act none|gelu");
-    p.epi.lnf_stats = a.lnf.stats; p.epi.lnf_parts = a.lnf.parts; p.epi.lnf_stride = a.lnf.stride;
-    p.epi.lnf_invC = 1.0f / (float)a.lnf.C; p.epi.lnf_colsum = w.colsum(a.x.dt);
+    p.epi.lnf_mr = a.lnf.mr; p.epi.lnf_colsum = w.colsum(a.x.dt);
   }
   if (a.lne.stats) {
     BRN_CHECK(S == 1 && !a.out_tiled && a.out.dt == F32 && a.act == ACT_NONE && w.N % 16 == 0 && p.epi.vec &&
@@ -558,7 +562,7 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
     else ek = a.act == ACT_NONE ? EK_NONE32 : EK_GENERIC;
   } else if (a.act == ACT_NONE && o32 && a.res.dt == F32 && p.epi.vec) ek = EK_RES32;
   else if (a.act == ACT_NONE && !o32 && a.res.dt == a.out.dt && p.epi.vec && w.N % 8 == 0) ek = EK_RES16;
-  if (a.lnf.stats) ek = a.act == ACT_GELU ? EK_LNF_GELU16 : EK_LNF_NONE16;
+  if (a.lnf.mr) ek = a.act == ACT_GELU ? EK_LNF_GELU16 : EK_LNF_NONE16;
   if (a.lne.stats) {
     BRN_CHECK(ek == EK_RES32 || ek == EK_NONE32, 5, "tc_gemm: LnEmit on an unsupported epilogue variant");
     ek = ek == EK_RES32 ? EK_RES32_EMIT : EK_NONE32_EMIT;

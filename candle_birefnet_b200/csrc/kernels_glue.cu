@@ -358,6 +358,31 @@ void glue_ln_stats_cast(const LaunchCtx& ctx, View x, View x16, float2* stats) {
   BRN_CUDA(cudaGetLastError());
 }
 
+// The consumer GEMM's epilogue needs one (-mean, rstd) pair per row, one tile ahead of its math: a compact array it can
+// prefetch with a single 8-byte load (summing the partials inside the epilogue put an L2 round trip on the critical
+// path of every tile: +30 % on the epilogue-bound stage-0 qkv GEMM, r02 run B).
+__global__ void __launch_bounds__(256) ln_finalize_kernel(const float2* __restrict__ stats, int parts, long long stride,
+                                                          long long rows, float invC, float2* __restrict__ mr) {
+  const long long m = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (m >= rows) return;
+  float s = 0.f, q = 0.f;
+  for (int i = 0; i < parts; ++i) {
+    const float2 t = __ldg(stats + (long long)i * stride + m);
+    s += t.x; q += t.y;
+  }
+  const float mu = s * invC;
+  const float var = fmaxf(fmaf(-mu, mu, q * invC), 0.f);
+  mr[m] = make_float2(-mu, rsqrtf(var + 1e-5f));
+}
+void glue_ln_finalize(const LaunchCtx& ctx, const float2* stats, int parts, long long stride, long long rows, int C,
+                      float2* mr) {
+  if (ctx.launches) ++*ctx.launches;
+  if (ctx.dry) return;
+  KScope ks(ctx, KC_LN, 0.0, (double)rows * (parts + 1) * 8, "ln_finalize");
+  ln_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx.stream>>>(stats, parts, stride, rows, 1.0f / (float)C, mr);
+  BRN_CUDA(cudaGetLastError());
+}
+
 __global__ void sigmoid_kernel(float* p, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 1.f / (1.f + expf(-p[i]));

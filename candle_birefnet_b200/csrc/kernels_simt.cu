@@ -142,7 +142,7 @@ void simt_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   SimtGemmP p{};
   p.x = a.x.p; p.xdt = a.x.dt; p.B = a.x.B; p.H = a.x.H; p.W = a.x.W; p.Cin = a.x.C; p.ldx = a.x.ld;
   BRN_CHECK(a.w && a.w->Cin == a.x.C, 5, "simt_gemm: weight/input channel mismatch");
-  BRN_CHECK(a.rowmap.enabled != 2 && !a.lnf.stats && !a.lne.stats, 7,
+  BRN_CHECK(a.rowmap.enabled != 2 && !a.lnf.mr && !a.lne.stats, 7,
             "simt_gemm: the folded-LayerNorm epilogues and the token->window row map are tensor-core-path features");
   BRN_CHECK(a.w->w32 != nullptr, 7, "simt_gemm: layer has no fp32 weights (a folded tensor-core-only copy)");
   p.kh = a.w->kh; p.kw = a.w->kw; p.pad = a.pad;

@@ -613,21 +613,25 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
     // scatters rows into the window-ordered padded layout the attention kernel loads (pad rows are synthesised inside
     // that kernel), and attention stores straight back to token order -- norm1 -> pad -> roll -> partition and
     // window_reverse -> roll -> crop (src/swin.rs:355-401) never exist as passes.
-    View x16{}; float2* stats = nullptr; int parts = 0;
+    View x16{}; float2 *stats = nullptr, *mr = nullptr; int parts = 0;
     if (fold) {
       parts = tc_gemm_ln_parts(Ci);
+      mr = (float2*)arena.alloc((size_t)Tt * sizeof(float2));
       if (have_stats) {     // the previous stage's reduction GEMM emitted into these buffers
         x16 = next_x16; stats = next_stats;
+        glue_ln_finalize(ctx, stats, parts, Tt, Tt, Ci, mr);
       } else {
         x16 = make_view(arena.alloc((size_t)Tt * Ci * dsize(AD)), AD, 1, 1, (int)Tt, Ci);
         stats = (float2*)arena.alloc((size_t)parts * Tt * sizeof(float2));
       }
     }
-    auto emit = [&](GemmArgs& g) {
-      if (!fold) return;
-      g.lne.stats = stats; g.lne.stride = Tt; g.lne.x16 = x16.p; g.lne.x16dt = AD; g.lne.ldx16 = Ci;
+    // producer: op_gemm with the emit fields set, then the partials -> (-mean, rstd) pass the consumers prefetch from
+    auto emit_gemm = [&](GemmArgs& g) {
+      if (fold) { g.lne.stats = stats; g.lne.stride = Tt; g.lne.x16 = x16.p; g.lne.x16dt = AD; g.lne.ldx16 = Ci; }
+      op_gemm(ctx, g);
+      if (fold) glue_ln_finalize(ctx, stats, parts, Tt, Tt, Ci, mr);
     };
-    auto folded = [&](GemmArgs& g) { g.lnf.stats = stats; g.lnf.parts = parts; g.lnf.stride = Tt; g.lnf.C = Ci; };
+    auto folded = [&](GemmArgs& g) { g.lnf.mr = mr; g.lnf.C = Ci; };
     for (size_t j = 0; j < stages[i].blocks.size(); ++j) {
       const BlockW& bw = stages[i].blocks[j];
       const int shift = (j % 2 == 0) ? 0 : 6;          // src/swin.rs:552
@@ -666,8 +670,7 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
       // proj (+ window_reverse + roll back + crop on the SIMT path) + residual (src/swin.rs:310,387-406)
       { GemmArgs g; g.x = ao; g.w = &bw.proj; g.out = xt; g.res = xt;
         if (!fold) { g.rowmap = wmap; g.rowmap.enabled = 1; }
-        emit(g);
-        op_gemm(ctx, g); }
+        emit_gemm(g); }
       // x + fc2(gelu(fc1(norm2(x))))  (src/swin.rs:407)
       View hd = make_view(arena.alloc((size_t)Tt * cfg.mlp_ratio * Ci * dsize(AD)), AD, 1, 1, (int)Tt, cfg.mlp_ratio * Ci);
       if (fold) {
@@ -679,7 +682,7 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
         { LnArgs l; l.x = xt; l.gamma = bw.n2g; l.beta = bw.n2b; l.out = xn; l.mode = LN_PLAIN; glue_layernorm(ctx, l); }
         GemmArgs g; g.x = xn; g.w = &bw.fc1; g.act = ACT_GELU; g.out = hd; op_gemm(ctx, g);
       }
-      { GemmArgs g; g.x = hd; g.w = &bw.fc2; g.out = xt; g.res = xt; emit(g); op_gemm(ctx, g); }
+      { GemmArgs g; g.x = hd; g.w = &bw.fc2; g.out = xt; g.res = xt; emit_gemm(g); }
       have_stats = fold;
       arena.release(mb);
     }

@@ -22,25 +22,12 @@ struct EpiP {
   const void* res; int resdt; int ldres;
   void* out; int odt; int ldo;
   int vec;       // out (and res) base pointers and row pitches are 16-byte aligned
-  // LayerNorm fold, consumer side (LnFold): per-row (sum, sumsq) partials of the fp32 stream the A operand was rounded from
-  const float2* lnf_stats; int lnf_parts; long long lnf_stride; float lnf_invC;
+  // LayerNorm fold, consumer side (LnFold): (-mean, rstd) per A row of the fp32 stream the operand was rounded from
+  const float2* lnf_mr;
   const float* lnf_colsum;   // [N] column sums of the rounded gamma-folded weights
   // producer side (LnEmit): statistics + raw 16-bit copy of the rows this epilogue stores
   float2* lne_stats; long long lne_stride; void* x16; int x16dt; int ldx16;
 };
-
-// row statistics of a folded LayerNorm: the partials are summed in index order (deterministic)
-__device__ __forceinline__ void lnf_row_stats(const EpiP& p, long long arow, float& nmu, float& rstd) {
-  float s = 0.f, q = 0.f;
-  for (int i = 0; i < p.lnf_parts; ++i) {
-    const float2 t = __ldg(p.lnf_stats + (long long)i * p.lnf_stride + arow);
-    s += t.x; q += t.y;
-  }
-  const float mu = s * p.lnf_invC;
-  const float var = fmaxf(fmaf(-mu, mu, q * p.lnf_invC), 0.f);
-  nmu = -mu;
-  rstd = rsqrtf(var + 1e-5f);
-}
 
 constexpr int EPI_STAGE_BYTES = 32 * 64;   // per epilogue warp
 

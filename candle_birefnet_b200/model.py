@@ -269,6 +269,20 @@ class BiRefNet:
                                         out.ctypes.data_as(C.c_void_p), None))
         return out
 
+    def infer_rgb8(self, rgb: np.ndarray, size: Tuple[int, int] = (1024, 1024)) -> np.ndarray:
+        """examples/infer_image.rs:44-105 on the device: uint8 RGB [B,h,w,3] -> uint8 masks [B,h,w] (resize to `size`
+        with Triangle, ImageNet normalise, forward_logits, sigmoid, u8, Lanczos3 resize back)."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        if rgb.ndim == 3:
+            rgb = rgb[None]
+        B, h, w, c = rgb.shape
+        if c != 3:
+            raise BrnError(5, f"expected [B,h,w,3] uint8, got {rgb.shape}")
+        out = np.empty((B, h, w), dtype=np.uint8)
+        check(lib().brn_infer_rgb8(self._h, rgb.ctypes.data_as(C.c_void_p), B, h, w, size[0], size[1],
+                                   out.ctypes.data_as(C.c_void_p)))
+        return out
+
     # ---- introspection -------------------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(lib().brn_launch_count(self._h))

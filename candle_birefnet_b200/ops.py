@@ -75,6 +75,29 @@ def window_attention(qkv, bias, hp: int, wp: int, shift: int, precision: str = "
     return out
 
 
+def preprocess_rgb8(rgb: np.ndarray, H: int = 1024, W: int = 1024, device: int = 0) -> np.ndarray:
+    """examples/infer_image.rs:44-67: Triangle resize_exact + ImageNet normalise.  rgb uint8 [h,w,3] or [B,h,w,3]."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    if rgb.ndim == 3:
+        rgb = rgb[None]
+    B, h, w, c = rgb.shape
+    assert c == 3
+    out = np.empty((B, 3, H, W), dtype=np.float32)
+    check(lib().brn_preprocess_rgb8(device, _p(rgb), B, h, w, H, W, _p(out)))
+    return out
+
+
+def postprocess_mask(logits: np.ndarray, orig_h: int, orig_w: int, device: int = 0) -> np.ndarray:
+    """examples/infer_image.rs:85-105: sigmoid -> u8 -> Lanczos3 resize.  logits float32 [B,1,H,W] or [B,H,W]."""
+    logits = np.ascontiguousarray(logits, dtype=np.float32)
+    if logits.ndim == 4:
+        logits = logits[:, 0]
+    B, H, W = logits.shape
+    out = np.empty((B, orig_h, orig_w), dtype=np.uint8)
+    check(lib().brn_postprocess_mask(device, _p(np.ascontiguousarray(logits)), B, H, W, orig_h, orig_w, _p(out)))
+    return out
+
+
 def bench_op(kind: str, B: int, H: int, W: int, Cin: int, N: int = 0, k: int = 1, act: int = 0, with_res: bool = False,
              out_f32: bool = False, iters: int = 20, precision: str = "fp16", device: int = 0) -> float:
     """Mean device ms per launch of one kernel on synthetic device-resident data (kind: gemm | attn | deform)."""

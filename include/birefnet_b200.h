@@ -160,6 +160,25 @@ BRN_API brn_status brn_decoder_forward(brn_model* m, const float* x, const float
                                const float* x4, int32_t B, int32_t H, int32_t W, int is_device, float* out,
                                void* stream);
 
+/* ---- the steps either side of the path (examples/infer_image.rs) ---------------------------- */
+
+/* examples/infer_image.rs:44-67: `img.resize_exact(W, H, FilterType::Triangle)` + ImageNet normalisation.
+ * rgb: HOST u8 [B,h,w,3]; out: HOST fp32 NCHW [B,3,H,W].  The resampling restates the `image` crate 0.25.9
+ * (`imageops::sample`: vertical pass in f32, horizontal pass, clamp, round half away from zero). */
+BRN_API brn_status brn_preprocess_rgb8(int device, const uint8_t* rgb, int32_t B, int32_t h, int32_t w, int32_t H, int32_t W,
+                               float* out);
+
+/* examples/infer_image.rs:85-105: sigmoid -> `(v * 255.0).clamp(0, 255) as u8` -> `imageops::resize(orig_w, orig_h,
+ * Lanczos3)`.  logits: HOST fp32 [B,H,W]; out: HOST u8 [B,orig_h,orig_w]. */
+BRN_API brn_status brn_postprocess_mask(int device, const float* logits, int32_t B, int32_t H, int32_t W, int32_t orig_h,
+                                int32_t orig_w, uint8_t* out);
+
+/* examples/infer_image.rs:44-105 end to end on the device: RGB8 images in, u8 masks of the same size out; only the
+ * 8-bit pixels cross PCIe (3 bytes in, 1 byte out per source pixel).  rgb: HOST u8 [B,h,w,3]; inference runs at
+ * H x W (the CLI uses 1024 x 1024); masks: HOST u8 [B,h,w]. */
+BRN_API brn_status brn_infer_rgb8(brn_model* m, const uint8_t* rgb, int32_t B, int32_t h, int32_t w, int32_t H, int32_t W,
+                          uint8_t* masks);
+
 /* ---- operator level (kernel parity tests; the reference's native boundaries) ---------------------------------- */
 
 /* Plain-chain window attention: out = softmax(scale*q k^T + bias[h] (+ mask[w % nW])) v, the computation of

@@ -93,7 +93,8 @@ def resize(img_u8: np.ndarray, new_h: int, new_w: int, filt: str) -> np.ndarray:
     tmp = _apply(img_u8, 0, new_h, filt)
     out = _apply(tmp, 1, new_w, filt)
     out = np.clip(out, F(0.0), F(255.0))
-    return np.floor(out + F(0.5)).astype(np.uint8)       # f32::round on non-negative values
+    fl = np.floor(out)
+    return (fl + ((out - fl) >= F(0.5))).astype(np.uint8)   # f32::round (half away from zero) on non-negative values
 
 
 def normalize_imagenet(rgb_u8: np.ndarray) -> np.ndarray:

@@ -153,3 +153,57 @@ def test_ln_linear_fold(M, N, K, mean_over_std, precision, act):
     tol = eps * (4.0 + 2.0 * (1.0 + mean_over_std))
     err = np.abs(got - exp).max() / max(1.0, np.abs(exp).max())
     assert err < tol, (err, tol)
+
+
+def test_preprocess_matches_image_crate_restatement():
+    """examples/infer_image.rs:44-67 on the device: Triangle resize_exact + ImageNet normalise of the reference's own
+    test photo, against oracle/imageops_ref.py (restatement of the `image` 0.25.9 sampling code).  Triangle weights are
+    plain IEEE f32 arithmetic on both sides and the kernels do not contract multiply-adds: bit-exact."""
+    from pathlib import Path
+    from oracle import imageops_ref as IM
+    rgb = np.load(Path(__file__).parent / "golden" / "cat_768_u8.npz")["rgb"]
+    got = cb.ops.preprocess_rgb8(rgb, 1024, 1024)
+    exp = IM.preprocess(rgb, 1024)
+    assert got.shape == (1, 3, 1024, 1024)
+    assert np.array_equal(got, exp), float(np.abs(got - exp).max())
+    # down-scaling (support grows with the ratio), non-square, batch of 2, and the same-size copy path
+    two = np.stack([rgb[:600, :700], rgb[100:700, 50:750]])
+    got = cb.ops.preprocess_rgb8(two, 256, 320)
+    for b in range(2):
+        assert np.array_equal(got[b], IM.normalize_imagenet(IM.resize(two[b], 256, 320, "triangle"))[0])
+    same = cb.ops.preprocess_rgb8(rgb, 768, 768)
+    assert np.array_equal(same, IM.normalize_imagenet(rgb))
+
+
+def test_postprocess_matches_image_crate_restatement():
+    """examples/infer_image.rs:85-105: sigmoid -> u8 (truncation) -> Lanczos3 resize.  expf / sinf differ from numpy's in
+    the last ulp, which can move a value across a truncation or rounding boundary: <= 1 level, on < 0.1 % of the pixels."""
+    from oracle import imageops_ref as IM
+    rng = np.random.default_rng(3)
+    logits = (rng.standard_normal((2, 256, 320)) * 3).astype(np.float32)
+    logits[0, :40] = 30.0       # saturated regions: Lanczos overshoot must clamp
+    logits[0, 40:80] = -30.0
+    for (oh, ow) in ((256, 320), (768, 768), (100, 517)):
+        got = cb.ops.postprocess_mask(logits, oh, ow)
+        for b in range(2):
+            exp = IM.postprocess(logits[b], oh, ow)
+            d = np.abs(got[b].astype(int) - exp.astype(int))
+            assert d.max() <= 1 and (d > 0).mean() < 1e-3, (oh, ow, int(d.max()), float((d > 0).mean()))
+
+
+def test_infer_rgb8_end_to_end(mini_cfg, mini_weights_B):
+    """brn_infer_rgb8 == preprocess -> forward_logits -> postprocess chained through the separate entry points."""
+    from pathlib import Path
+    rgb = np.load(Path(__file__).parent / "golden" / "cat_768_u8.npz")["rgb"][::3, ::3].copy()      # 256 x 256
+    two = np.stack([rgb, rgb[::-1].copy()])
+    cfg = cb.BiRefNetConfig(swin=cb.SwinConfig(embed_dim=mini_cfg.embed_dim, depths=tuple(mini_cfg.depths),
+                                               num_heads=tuple(mini_cfg.num_heads)), precision="fp16")
+    m = cb.BiRefNet.new(cfg, mini_weights_B)
+    try:
+        got = m.infer_rgb8(two, size=(128, 160))
+        x = cb.ops.preprocess_rgb8(two, 128, 160)
+        exp = cb.ops.postprocess_mask(m.forward_logits(x), 256, 256)
+        assert got.shape == (2, 256, 256) and got.dtype == np.uint8
+        assert np.array_equal(got, exp)
+    finally:
+        m.close()
