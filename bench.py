@@ -15,6 +15,14 @@ Weights are the seeded random-init Swin-L set (weight-set B: random deformable o
   cpu_baseline  the oracle (PyTorch CPU restatement of the reference, kind "port": candle cannot be built here) timed
             on this box's host cores on a bounded sample (1 image of the same 1024^2 workload), rank 0, N=1 only.
 
+  parity    image 0 of the first batch against the oracle (same weights, deformable mode), outside the timed region:
+            max |dsigmoid| and IoU@0.5 of the benchmarked dtype (fp16 operands) and of the bf16 policy.
+  bf16      the same step with bf16 backbone operands (what BASELINE.json configs[2] names): images/s + its parity.
+
+`--config` selects the workload: c3 (default) = BASELINE.json configs[2] as above; c2 = configs[1], Swin-L backbone
+only, batch 1 (images/s + p50 latency, the oracle's backbone beside it); c4 = configs[3], squeeze module + decoder
+isolated on multi-scale feature maps, batch 16, with the deformable offset sweep sigma in {0, 0.5, 2, 8} px; c5 =
+configs[4], 2048x2048, GLOBAL batch 64 sharded over the N ranks ("scaling": "strong").
 `--impl reference` times only that CPU restatement (all host threads) and prints the same JSON line.
 Multi-GPU: one process per GPU (torchrun), images sharded, no data-path collective ("scaling": "weak").
 """
@@ -95,9 +103,21 @@ class ClockSampler:
                     power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
 
 
-def oracle_images_per_s(H: int, W: int, steps: int, warmup: int, budget_s: float = 240.0):
+WORKLOADS = {
+    "c2": "Swin-L backbone only (SwinTransformer::forward), {H}x{W}, batch {B} per GPU (BASELINE.json configs[1])",
+    "c3": "BiRefNet {model} forward_logits {H}x{W}, batch {B} per GPU (BASELINE.json configs[2] shape; operands {prec}: "
+          "bf16 operands run at the same tcgen05 kind::f16 rate but miss the IoU 0.999 gate on randn inputs, see `parity` / `bf16`)",
+    "c4": "squeeze module + BiRefNetDecoder on multi-scale Swin-L feature maps, {H}x{W}, batch {B} per GPU, deformable "
+          "offset sweep (BASELINE.json configs[3])",
+    "c5": "BiRefNet {model} forward_logits {H}x{W} (HR), GLOBAL batch {GB} image-sharded over {N} GPU(s) "
+          "(BASELINE.json configs[4])",
+}
+
+
+def oracle_images_per_s(H: int, W: int, steps: int, warmup: int, budget_s: float = 240.0, what: str = "forward"):
     """Times the CPU restatement of the reference (deform_mode=cpu_fallback: what candle computes on Device::Cpu,
-    src/aspp.rs:183-185) on one image per step.  Bounded: stops early when the budget is spent."""
+    src/aspp.rs:183-185) on one image per step.  Bounded: stops early when the budget is spent.
+    what = "forward" (forward_logits) | "backbone" (SwinTransformer::forward, config c2)."""
     import torch
     from oracle import birefnet_ref as R
     from oracle.make_weights import as_torch, make_input, make_weights
@@ -111,15 +131,16 @@ def oracle_images_per_s(H: int, W: int, steps: int, warmup: int, budget_s: float
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.time()
-            R.forward_logits(x, w, cfg, "cpu_fallback")
+            if what == "backbone":
+                R.swin_forward(x, w, cfg)
+            else:
+                R.forward_logits(x, w, cfg, "cpu_fallback")
             dt = time.time() - t0
             if i >= warmup:
                 times.append(dt)
             elapsed = time.time() - t_start
             if times and elapsed + dt > budget_s:
                 break
-            if not times and i + 1 >= warmup:
-                continue
     if not times:   # budget exhausted inside warm-up: the last warm-up run is the sample
         times = [dt]
     med = statistics.median(times)
@@ -132,15 +153,17 @@ def run_reference(args):
         return 0
     H = W = args.size
     warm = min(args.warmup, 1)
-    ips, cores, nsteps, med = oracle_images_per_s(H, W, args.steps, warm)
+    what = "backbone" if args.config == "c2" else "forward"
+    ips, cores, nsteps, med = oracle_images_per_s(H, W, args.steps, warm, what=what)
+    wl = WORKLOADS[args.config].format(H=H, W=W, B=args.batch, model="swin_l", prec="fp32", GB=64, N=args.gpus)
     line = {
         "impl": "reference", "metric": "images/s BiRefNet Swin-L @1024^2", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": nsteps, "warmup": warm, "ms_per_step": med * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BiRefNet swin_l forward_logits {H}x{W}, batch 16 per GPU (BASELINE.json configs[2])",
+        "scaling": "strong" if args.config == "c5" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl,
                    "implementation": "reference CPU path: PyTorch-CPU restatement of candle's CPU forward (candle itself "
                                      "cannot be built here: no Rust toolchain)",
-                   "sample": "1 image per step (1/16 of a batch)", "deform_mode": "cpu_fallback"},
+                   "sample": "1 image per step", "deform_mode": "cpu_fallback"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"1 image {H}x{W} per step, {nsteps} timed step(s)"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -150,33 +173,65 @@ def run_reference(args):
     return 0
 
 
+def parity_vs_oracle(model, x1, weights, precisions, deform_mode):
+    """Image 0 of the benchmarked batch against the oracle on the SAME weights (outside every timed region).
+    Returns {precision: {max_dsigmoid, iou, max_dlogit}} + the oracle's wall time."""
+    import numpy as np
+    import torch
+    from oracle import birefnet_ref as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    wt = {k: torch.from_numpy(v) for k, v in weights.items()}
+    t0 = time.time()
+    with torch.no_grad():
+        exp = R.forward_logits(torch.from_numpy(x1), wt, R.Config.swin_l(), deform_mode).numpy()
+    t_or = time.time() - t0
+    sig = lambda z: 1.0 / (1.0 + np.exp(-z))
+    out = {"oracle": f"oracle/birefnet_ref.py forward_logits, mode {deform_mode}, fp32, {t_or:.1f} s", "input": "image 0 of batch 0 (randn)"}
+    keep = model.config.precision
+    for p in precisions:
+        model.set_precision(p)
+        got = model.forward_logits(x1)
+        a, b = sig(got) > 0.5, sig(exp) > 0.5
+        out[p] = {"max_dsigmoid": float(np.abs(sig(got) - sig(exp)).max()), "max_dlogit": float(np.abs(got - exp).max()),
+                  "iou": float(np.logical_and(a, b).sum() / max(1, np.logical_or(a, b).sum()))}
+    model.set_precision(keep)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
-    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4", "c5"], help="BASELINE.json configs[1..4]")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: 16; c2: 1; c5: 64 / N)")
+    ap.add_argument("--size", type=int, default=0, help="input side (default 1024; c5: 2048)")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--deform-mode", default="deformable", choices=["deformable", "cpu_fallback"])
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads issuing e2e calls on the one handle")
     ap.add_argument("--dev-streams", type=int, default=1, help="streams the device-resident steps alternate over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-bf16", action="store_true")
     ap.add_argument("--kernel-log", default="", help="write a per-launch CSV (class, ms, gflop, desc) of one step")
     ap.add_argument("--model", default="swin_l", choices=["swin_l", "mini"], help="mini is for smoke runs only")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not args.size:
+        args.size = 2048 if args.config == "c5" else 1024
+    if not args.batch:
+        args.batch = 1 if args.config == "c2" else max(1, 64 // world) if args.config == "c5" else 16
     if args.impl == "reference":
         return run_reference(args)
 
     import numpy as np
     import torch
     import candle_birefnet_b200 as cb
-    from candle_birefnet_b200.synth import synthetic_input as make_input
+    from candle_birefnet_b200.synth import synthetic_input as make_input, synthetic_weights
 
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
@@ -189,40 +244,94 @@ def main():
     warmup = max(args.warmup, 3)
     H = W = args.size
     B = args.batch
+    cfgname = args.config
 
     swin = cb.SwinConfig.swin_l() if args.model == "swin_l" else cb.SwinConfig(embed_dim=64, depths=(2, 2, 2, 2),
                                                                                num_heads=(2, 4, 8, 16))
     pcfg = cb.BiRefNetConfig(swin=swin, precision=args.precision, deform_mode=args.deform_mode)
-    model = cb.BiRefNet.new_synthetic(pcfg, seed=0, weight_set="B", offset_sigma=2.0, device=local)
+
+    def make_model(offset_sigma=2.0):
+        probe = cb.BiRefNet._create(pcfg, local)
+        try:
+            sc = probe.tensor_schema()
+        finally:
+            probe.close()
+        w = synthetic_weights(sc, 0, "B", offset_sigma)
+        return cb.BiRefNet.new(pcfg, w, local), w
+
+    model, weights = make_model()
+    E = swin.embed_dim
 
     # ---- inputs: 3 rotating batches, device-resident for `value`, pinned host copies for `e2e` ----
     nrot = 3
     host_in = [torch.from_numpy(make_input(B, H, W, seed=1234 + 7 * rank + i)).pin_memory() for i in range(nrot)]
     dev_in = [h.cuda(non_blocking=True) for h in host_in]
-    dev_out = torch.empty((B, 1, H, W), dtype=torch.float32, device="cuda")
-    host_out = torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory()
     stream = torch.cuda.Stream()          # a real (non-default) stream: kernels and the timing events share it
     torch.cuda.set_stream(stream)
-
     nds = max(1, args.dev_streams)
     dstreams = [stream] + [torch.cuda.Stream() for _ in range(nds - 1)]
-    dev_outs = [dev_out] + [torch.empty_like(dev_out) for _ in range(nds - 1)]
-
-    def step_dev(i):
-        model.forward_logits(dev_in[i % nrot], out=dev_outs[i % nds], stream=dstreams[i % nds].cuda_stream)
-
-    # e2e: `e2e_threads` host threads share the handle; each call is synchronous (returns with the masks in its
-    # pinned host buffer), the handle keeps two calls in flight so the copies of one overlap the kernels of the other
     nthr = max(1, args.e2e_threads)
-    host_outs = [host_out] + [torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(nthr - 1)]
+    import ctypes as C
+    L = cb.lib()
 
-    def step_e2e(i, t=0):
-        import ctypes as C
-        h = host_in[i % nrot]
-        cb._lib.check(cb.lib().brn_forward_logits(model._h, C.c_void_p(h.data_ptr()), B, H, W, 0,
-                                                  C.c_void_p(host_outs[t].data_ptr()), 0, None))
+    if cfgname == "c2":
+        # SwinTransformer::forward: 4 NCHW maps out
+        chans = [E << i for i in range(4)]
+        dev_feats = [[torch.empty((B, chans[i], H // (4 << i), W // (4 << i)), dtype=torch.float32, device="cuda")
+                      for i in range(4)] for _ in range(nds)]
+        host_feats = [[torch.empty((B, chans[i], H // (4 << i), W // (4 << i)), dtype=torch.float32).pin_memory()
+                       for i in range(4)] for _ in range(nthr)]
+        out_bytes = sum(t.numel() * 4 for t in host_feats[0])
 
-    def run_e2e(steps):
+        def step_dev(i):
+            outs = dev_feats[i % nds]
+            ptrs = (C.c_void_p * 4)(*[C.c_void_p(o.data_ptr()) for o in outs])
+            cb._lib.check(L.brn_backbone_forward(model._h, C.c_void_p(dev_in[i % nrot].data_ptr()), B, H, W, 1, ptrs, 1,
+                                                 C.c_void_p(dstreams[i % nds].cuda_stream)))
+
+        def step_e2e(i, t=0):
+            ptrs = (C.c_void_p * 4)(*[C.c_void_p(o.data_ptr()) for o in host_feats[t]])
+            cb._lib.check(L.brn_backbone_forward(model._h, C.c_void_p(host_in[i % nrot].data_ptr()), B, H, W, 0, ptrs, 0, None))
+    elif cfgname == "c4":
+        # synthetic multi-scale features with the statistics of LayerNorm outputs (N(0,1)); the image feeds the ipt blocks
+        g = torch.Generator(device="cuda").manual_seed(99 + rank)
+        fch = [2 * (E << i) for i in range(3)] + [30 * E]
+        dev_f = [[torch.randn((B, fch[i], H // (4 << i), W // (4 << i)), generator=g, device="cuda") for i in range(4)]
+                 for _ in range(2)]
+        host_f = [t.cpu().pin_memory() for t in dev_f[0]]
+        dev_out = torch.empty((B, 1, H, W), dtype=torch.float32, device="cuda")
+        host_outs = [torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(nthr)]
+        out_bytes = B * H * W * 4
+
+        def dec_call(m, i):
+            f = dev_f[i % 2]
+            cb._lib.check(L.brn_decoder_forward(m._h, C.c_void_p(dev_in[i % nrot].data_ptr()), *[C.c_void_p(t.data_ptr()) for t in f],
+                                                B, H, W, 1, C.c_void_p(dev_out.data_ptr()), C.c_void_p(stream.cuda_stream)))
+
+        def step_dev(i):
+            dec_call(model, i)
+
+        def step_e2e(i, t=0):
+            cb._lib.check(L.brn_decoder_forward(model._h, C.c_void_p(host_in[i % nrot].data_ptr()),
+                                                *[C.c_void_p(x.data_ptr()) for x in host_f], B, H, W, 0,
+                                                C.c_void_p(host_outs[t].data_ptr()), None))
+    else:
+        dev_outs = [torch.empty((B, 1, H, W), dtype=torch.float32, device="cuda") for _ in range(nds)]
+        host_outs = [torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(nthr)]
+        out_bytes = B * H * W * 4
+
+        def step_dev(i):
+            model.forward_logits(dev_in[i % nrot], out=dev_outs[i % nds], stream=dstreams[i % nds].cuda_stream)
+
+        # e2e: `e2e_threads` host threads share the handle; each call is synchronous (returns with the masks in its
+        # pinned host buffer), the handle keeps two calls in flight so the copies of one overlap the kernels of the other
+        def step_e2e(i, t=0):
+            h = host_in[i % nrot]
+            cb._lib.check(L.brn_forward_logits(model._h, C.c_void_p(h.data_ptr()), B, H, W, 0,
+                                               C.c_void_p(host_outs[t].data_ptr()), 0, None))
+    in_bytes = B * 3 * H * W * 4 + (sum(t.numel() * 4 for t in host_f) if cfgname == "c4" else 0)
+
+    def run_e2e(steps, threads=nthr):
         """`steps` calls spread over the host threads (shared counter)."""
         nxt = iter(range(steps))
         lock, errs = threading.Lock(), []
@@ -237,7 +346,7 @@ def main():
                     step_e2e(i, t)
             except Exception as e:     # noqa: BLE001 - re-raised below
                 errs.append(e)
-        ts = [threading.Thread(target=work, args=(t,)) for t in range(nthr)]
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
         [t.start() for t in ts]
         [t.join() for t in ts]
         if errs:
@@ -306,34 +415,43 @@ def main():
 
     # ---- roofline of the dominant kernel class, live CUDA events around every launch (untimed step) ----
     peaks = load_peaks()
-    roof, classes = None, None
-    if rank == 0:
-        model.profile(2)
-        step_dev(0)                        # first pass creates the event pool
+
+    def profile_classes(m, call, log=""):
+        """Three profiled passes, keep the one with the smallest kernel-time total (a pass now and then contains one
+        multi-ms outlier on an arbitrary launch: a host-side hiccup between two event records, not kernel time)."""
+        m.profile(2)
+        call(0)                            # first pass creates the event pool
         torch.cuda.synchronize()
-        # three profiled passes, keep the one with the smallest kernel-time total (a pass now and then contains one
-        # multi-ms outlier on an arbitrary launch: a host-side hiccup between two event records, not kernel time)
         best = None
         for rep in range(3):
-            if args.kernel_log:
-                os.environ["BRN_KERNEL_LOG"] = args.kernel_log + (".tmp%d" % rep)
-            step_dev(0)
+            if log:
+                os.environ["BRN_KERNEL_LOG"] = log + (".tmp%d" % rep)
+            call(0)
             torch.cuda.synchronize()
             os.environ.pop("BRN_KERNEL_LOG", None)
-            c = model.kernel_class_times()
+            c = m.kernel_class_times()
             t = sum(v["ms"] for v in c.values())
             if best is None or t < best[0]:
-                best = (t, c, model.profile_get(), rep)
-        if args.kernel_log:
+                best = (t, c, m.profile_get(), rep)
+        if log:
             for rep in range(3):
-                tmp = args.kernel_log + (".tmp%d" % rep)
+                tmp = log + (".tmp%d" % rep)
                 if os.path.exists(tmp):
                     if rep == best[3]:
-                        os.replace(tmp, args.kernel_log)
+                        os.replace(tmp, log)
                     else:
                         os.remove(tmp)
-        classes, stages = best[1], best[2]
-        model.profile(0)
+        m.profile(0)
+        return best[1], best[2]
+
+    roof, classes = None, None
+    if rank == 0 and cfgname != "c2":
+        prof_call = step_dev if cfgname != "c4" else (lambda i: dec_call(model, i))
+        classes, stages = profile_classes(model, prof_call, args.kernel_log)
+    elif rank == 0:
+        # brn_backbone_forward has no per-stage events; the kernel classes still record
+        classes, stages = profile_classes(model, step_dev, args.kernel_log)
+    if rank == 0:
         g = classes["gemm_tcgen05"] if classes["gemm_tcgen05"]["launches"] else classes["gemm_simt"]
         tot_ms = sum(c["ms"] for c in classes.values())
         achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
@@ -343,6 +461,10 @@ def main():
         if tf.exists():
             tj = json.loads(tf.read_text())
             traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note")
+        hbm = peaks["hbm_gbs"]
+
+        def gbs(v):
+            return round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 0) if v["ms"] > 0 and v.get("bytes") else None
         roof = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05 implicit GEMM)", "achieved": achieved,
                 "peak": peaks["tflops_sustained"], "peak_source": peaks["source"] + " bf16_tflops_sustained",
                 "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
@@ -350,58 +472,140 @@ def main():
                 "launches_per_step": g["launches"], "avg_launch_ms": g["ms"] / max(g["launches"], 1),
                 "share_of_kernel_time": g["ms"] / tot_ms if tot_ms else None,
                 "classes_ms": {k: round(v["ms"], 3) for k, v in classes.items()},
+                "classes_launches": {k: v["launches"] for k, v in classes.items()},
                 "classes_tflops": {k: (round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["ms"] > 0 and v["flops"] else None)
                                    for k, v in classes.items()},
-                "classes_gbs": {k: (round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 0) if v["ms"] > 0 and v.get("bytes") else None)
-                                for k, v in classes.items()},
-                "hbm_peak_gbs": peaks["hbm_gbs"],
+                # compulsory HBM bytes (every operand once) / measured time, and the same as a fraction of the measured
+                # copy bandwidth: the roofline of the HBM-bound classes (layernorm, glue), context for the tensor-bound ones
+                "classes_compulsory_gbs": {k: gbs(v) for k, v in classes.items()},
+                "classes_hbm_frac": {k: (round(gbs(v) / hbm, 3) if gbs(v) else None) for k, v in classes.items()},
+                "hbm_peak_gbs": hbm,
                 "stages_ms": {n: round(ms, 3) for n, ms in stages}}
 
-    # ---- p50 batch-1 latency (device-resident input) ----
-    lat = None
-    if rank == 0 and not args.no_latency:
+    # ---- c4: deformable offset sweep (gather-bandwidth sweep of BASELINE.json configs[3]) ----
+    sweep = None
+    if rank == 0 and cfgname == "c4":
+        sweep = []
+        for sigma in (0.0, 0.5, 2.0, 8.0):
+            m2, _ = (model, None) if sigma == 2.0 else make_model(sigma)
+            for i in range(3):
+                dec_call(m2, i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(5):
+                dec_call(m2, i)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            cl, _ = profile_classes(m2, lambda i: dec_call(m2, i))
+            d = cl["deform_tcgen05"]
+            # sampled bytes: 4 corners x 64 channels x 2 B per output pixel and tap, k = 3 and 7 over the 5 decoder blocks
+            px = B * sum((H // s) * (W // s) for s in (32, 32, 16, 8, 4))
+            sampled = px * (9 + 49) * 4 * 128
+            sweep.append({"offset_sigma_px": sigma, "ms_per_step": round(ms, 3), "images_per_s": round(B / ms * 1e3, 1),
+                          "deform_ms": round(d["ms"], 3),
+                          "deform_tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1) if d["ms"] else None,
+                          "deform_tensor_frac": round(d["flops"] / (d["ms"] * 1e-3) / 1e12 / peaks["tflops_sustained"], 3) if d["ms"] else None,
+                          "gather_sampled_gbs": round(sampled / (d["ms"] * 1e-3) / 1e9, 0) if d["ms"] else None,
+                          "deform_compulsory_hbm_gbs": round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 0) if d["ms"] else None})
+            if m2 is not model:
+                m2.close()
+
+    # ---- p50 batch-1 latency: device-resident input, and end to end with host buffers ----
+    lat, lat_e2e = None, None
+    if rank == 0 and not args.no_latency and cfgname in ("c2", "c3", "c5"):
         x1 = dev_in[0][:1].contiguous()
-        o1 = torch.empty((1, 1, H, W), dtype=torch.float32, device="cuda")
+        hx1 = host_in[0][:1].contiguous().pin_memory()
+        if cfgname == "c2":
+            chans = [E << i for i in range(4)]
+            o1 = [torch.empty((1, chans[i], H // (4 << i), W // (4 << i)), dtype=torch.float32, device="cuda") for i in range(4)]
+            ho1 = [t.cpu().pin_memory() for t in o1]
+            p1 = (C.c_void_p * 4)(*[C.c_void_p(o.data_ptr()) for o in o1])
+            hp1 = (C.c_void_p * 4)(*[C.c_void_p(o.data_ptr()) for o in ho1])
+            call_dev = lambda: cb._lib.check(L.brn_backbone_forward(model._h, C.c_void_p(x1.data_ptr()), 1, H, W, 1, p1, 1,
+                                                                    C.c_void_p(stream.cuda_stream)))
+            call_host = lambda: cb._lib.check(L.brn_backbone_forward(model._h, C.c_void_p(hx1.data_ptr()), 1, H, W, 0, hp1, 0, None))
+        else:
+            o1 = torch.empty((1, 1, H, W), dtype=torch.float32, device="cuda")
+            ho1 = torch.empty((1, 1, H, W), dtype=torch.float32).pin_memory()
+            call_dev = lambda: model.forward_logits(x1, out=o1, stream=stream.cuda_stream)
+            call_host = lambda: cb._lib.check(L.brn_forward_logits(model._h, C.c_void_p(hx1.data_ptr()), 1, H, W, 0,
+                                                                   C.c_void_p(ho1.data_ptr()), 0, None))
         for _ in range(3):
-            model.forward_logits(x1, out=o1, stream=stream.cuda_stream)
+            call_dev()
         ts = []
         for _ in range(15):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            model.forward_logits(x1, out=o1, stream=stream.cuda_stream)
+            call_dev()
             e1.record(stream)
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         lat = statistics.median(ts)
+        for _ in range(4):
+            call_host()
+        ts = []
+        for _ in range(15):
+            t0 = time.perf_counter()
+            call_host()                      # synchronous: returns with the result in the pinned host buffer
+            ts.append((time.perf_counter() - t0) * 1e3)
+        lat_e2e = statistics.median(ts)
+
+    # ---- parity of the benchmarked configuration against the oracle + the bf16 policy beside it ----
+    parity, bf16 = None, None
+    if rank == 0 and world == 1 and cfgname == "c3" and args.model == "swin_l" and not args.no_parity:
+        precs = [args.precision] + (["bf16"] if args.precision != "bf16" and not args.no_bf16 else [])
+        parity = parity_vs_oracle(model, host_in[0][:1].numpy(), weights, precs, args.deform_mode)
+    if rank == 0 and cfgname == "c3" and args.precision != "bf16" and not args.no_bf16:
+        model.set_precision("bf16")
+        for i in range(2 * nrot):
+            step_dev(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nb = max(3, args.steps // 2)
+        e0.record(stream)
+        for i in range(nb):
+            step_dev(i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        bf16 = {"value": B * nb / (e0.elapsed_time(e1) / 1e3), "unit": "images/s per GPU", "steps": nb,
+                "policy": "bf16 operands in the backbone, fp16 in the squeeze module + decoder"}
+        model.set_precision(args.precision)
 
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "swin_l":
-        ips, cores, n, med = oracle_images_per_s(H, W, 5, 1, budget_s=45.0)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "swin_l" and cfgname in ("c2", "c3"):
+        what = "backbone" if cfgname == "c2" else "forward"
+        ips, cores, n, med = oracle_images_per_s(H, W, 5, 1, budget_s=45.0, what=what)
         cpu_base = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                    "sample": f"{n} x 1 image {H}x{W} (each 1/{B} of a step) after 1 warm-up, median {med:.1f} s per image; "
-                              f"PyTorch-CPU restatement of the reference's CPU forward (deform_mode=cpu_fallback)"}
+                    "sample": f"{n} x 1 image {H}x{W} after 1 warm-up, median {med:.1f} s per image; PyTorch-CPU "
+                              f"restatement of the reference's CPU {what} (deform_mode=cpu_fallback)"}
 
     if rank == 0:
         gflop = GFLOP_PER_IMAGE_1024 * (H * W) / (1024.0 * 1024.0)
+        wl = WORKLOADS[cfgname].format(H=H, W=W, B=B, model=args.model, prec=args.precision, GB=B * world, N=world)
         line = {
             "metric": "images/s BiRefNet Swin-L @1024^2", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "strong" if cfgname == "c5" else "weak", "vs_baseline": None,
             "dtype": {"fp16": "fp16", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
-            "config": {"workload": f"BiRefNet {args.model} forward_logits {H}x{W}, batch {B} per GPU "
-                                   f"(BASELINE.json configs[2])",
+            "config": {"workload": wl,
                        "global_batch": B * world, "parallelism": f"image-sharded x{world}, no collective",
                        "precision": args.precision, "deform_mode": args.deform_mode,
-                       "weights": "seeded random-init, weight-set B", "l2": "inputs rotate over 3 batches of "
-                       f"{B * 3 * H * W * 4 / 1e6:.0f} MB (> 126 MB L2)"},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
-                    "d2h_bytes_per_step": B * H * W * 4, "ms_per_step": e2e_s * 1e3 / args.steps,
+                       "weights": "seeded random-init, weight-set B (offset sigma 2 px)", "l2": "inputs rotate over 3 batches of "
+                       f"{B * 3 * H * W * 4 / 1e6:.0f} MB; activations are GBs per step (> 126 MB L2)"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_s * 1e3 / args.steps,
                     "host_threads": nthr},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
-            "model_tensor_frac": (value / world) * gflop / 1e3 / peaks["tflops_sustained"],
+            "model_tensor_frac": (value / world) * gflop / 1e3 / peaks["tflops_sustained"] if cfgname in ("c3", "c5") else None,
             "latency_ms_p50_b1": lat,
+            "latency_ms_p50_b1_e2e": lat_e2e,
+            "parity": parity,
+            "bf16": (dict(bf16, parity=parity.get("bf16") if parity else None) if bf16 else None),
+            "sweep": sweep,
             "cpu_baseline": cpu_base,
         }
         print(json.dumps(line))

@@ -506,6 +506,13 @@ brn_status brn_bench_op(int device, int precision, int kind, int32_t B, int32_t 
       View o = make_view(s.alloc(rows * Cc * dsize(AD)), AD, 1, 1, (int)rows, Cc);
       at.qkv = q; at.bias32 = b32; at.bias32p = b32p; at.n_windows = nwin; at.heads = heads;
       at.nwh = H; at.nww = W; at.shift = k; at.out = o;
+      if (with_res) {       // the model's configuration: token-order output + pad-row fix-up, N pad tokens per grid side
+        at.h = H * 12 - N; at.w = W * 12 - N; at.token_out = 1;
+        void* b16 = s.alloc((size_t)3 * Cc * 2);
+        fill(s, b16, AD, (long long)3 * Cc, 8u, 0.5f);
+        at.qkv_bias16 = b16;
+        at.out = make_view(o.p, AD, 1, 1, (nwin / (H * W)) * at.h * at.w, Cc);
+      }
       launch = [&] { op_attention(ctx, at); };
     }
     for (int i = 0; i < 3; ++i) launch();

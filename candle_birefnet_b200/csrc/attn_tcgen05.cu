@@ -51,7 +51,8 @@ constexpr int AT_STAGES = 3;
 constexpr int AT_P_BLOCK = 144 * 32;                     // one K=16 step of P: 4,608
 constexpr int AT_P_REGION = 44 * 1024;                   // 9 blocks (41,472) + over-read slack of the 16-row tile
 constexpr int AT_STAT_BYTES = 2 * 2 * 3 * 144 * 4;       // {max,sum} x parity x third x row
-constexpr int AT_SMEM = AT_BIAS_REGION + AT_STAGES * AT_STAGE_BYTES + AT_P_REGION + AT_STAT_BYTES + 256 + 1024;
+constexpr int AT_B16_BYTES = 3 * 64;                     // this head's q / k / v bias rows (the qkv of a pad token)
+constexpr int AT_SMEM = AT_BIAS_REGION + AT_STAGES * AT_STAGE_BYTES + AT_P_REGION + AT_STAT_BYTES + AT_B16_BYTES + 256 + 1024;
 constexpr uint32_t AT_COL_S0 = 0, AT_COL_S1 = 144, AT_COL_O0 = 288, AT_COL_O1 = 320;
 
 struct AttnP {
@@ -114,6 +115,13 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// three-input maximum (one FMNMX3 on sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -140,6 +148,34 @@ __device__ __forceinline__ void soft_bar_sync() { asm volatile("bar.sync 1, %0;"
 // the two warps that share a set of query rows (key halves 0 / 1) exchange their partial row max through shared memory
 __device__ __forceinline__ void pair_bar_sync(int pair) { asm volatile("bar.sync %0, 96;" ::"r"(2 + pair) : "memory"); }
 
+// exp2 on the FMA pipe for a pair of non-positive arguments (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], max
+// relative error 7.5e-5 -- the 16-bit rounding of P is 4.9e-4 / 3.9e-3): the kernel's binding pipe is XU (48 MUFU.EX2 +
+// 24 F2FP per thread and unit at 4 lanes/clk/SMSP), so AT_POLY_PAIRS of every 4 score pairs take this path instead.
+//   t = a + 1.5*2^23 (round to nearest integer n in the low mantissa bits), f = a - n, p = poly(f), bits += n << 23
+#ifndef BRN_ATTN_POLY_PAIRS
+#define BRN_ATTN_POLY_PAIRS 0
+#endif
+constexpr int AT_POLY_PAIRS = BRN_ATTN_POLY_PAIRS;
+__device__ __forceinline__ void ex2_poly2(unsigned long long a2, float& p0, float& p1) {
+  float a0, a1;
+  upk2(a2, a0, a1);
+  a0 = fmaxf(a0, -125.f); a1 = fmaxf(a1, -125.f);          // masked scores (-100 -> -144 in base 2): clamp, result ~ 2^-125
+  const unsigned long long ac = pk2(a0, a1);
+  const unsigned long long magic = pk2(12582912.f, 12582912.f), nmagic = pk2(-12582912.f, -12582912.f);
+  const unsigned long long t2 = fadd2(ac, magic);
+  const unsigned long long n2 = fadd2(t2, nmagic);
+  const unsigned long long f2 = fma2(n2, pk2(-1.f, -1.f), ac);
+  unsigned long long q = fma2(f2, pk2(0.05517164617776871f, 0.05517164617776871f), pk2(0.2426111251115799f, 0.2426111251115799f));
+  q = fma2(f2, q, pk2(0.6932609677314758f, 0.6932609677314758f));
+  q = fma2(f2, q, pk2(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, t0, t1;
+  upk2(q, q0, q1);
+  upk2(t2, t0, t1);
+  // (t_bits << 23) == n * 2^23 mod 2^32 (the magic constant's low 9 bits are zero): one IMAD per element
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
 template <int DT>
 __device__ __forceinline__ uint32_t at_pack(float a, float b) { return DT == BF16 ? pack_bf16x2(a, b) : pack_f16x2(a, b); }
 template <int DT>
@@ -151,7 +187,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
   uint8_t* sQKV = smem + AT_BIAS_REGION;
   uint8_t* sP = sQKV + AT_STAGES * AT_STAGE_BYTES;
   float* sStat = (float*)(sP + AT_P_REGION);                 // smax[par][third][row], then ssum[par][third][row]
-  uint64_t* bars = (uint64_t*)((uint8_t*)sStat + AT_STAT_BYTES);
+  uint8_t* sB16 = (uint8_t*)sStat + AT_STAT_BYTES;           // [3][64 B]
+  uint64_t* bars = (uint64_t*)(sB16 + AT_B16_BYTES);
   uint64_t* qkv_full = bars;        // [3]
   uint64_t* qkv_empty = bars + 3;   // [3]
   uint64_t* s_full = bars + 6;
@@ -174,6 +211,9 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
     ptx::fence_barrier_init();
   }
   if (warp == AT_SOFT_WARPS) ptx::tmem_alloc(tmem_slot, 512);
+  if (warp == 0 && lane < 12 && p.h > 0)
+    reinterpret_cast<uint4*>(sB16)[lane] =
+        __ldg(reinterpret_cast<const uint4*>(p.bias16 + (size_t)(lane >> 2) * p.C + head * 32) + (lane & 3));
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -196,8 +236,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       uint4 bq[3];
       if (p.h > 0) {
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
-          bq[t] = __ldg(reinterpret_cast<const uint4*>(p.bias16 + (size_t)t * p.C + head * 32) + (lane & 3));
+        for (int t = 0; t < 3; ++t) bq[t] = ptx::lds128(ptx::smem_u32(sB16) + t * 64 + (lane & 3) * 16);
       }
       auto load_unit = [&](int i) {
         const int s = i % AT_STAGES, win = w_first + i * w_step;
@@ -332,10 +371,10 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         const int tq = t / 144, row = t - tq * 144;
         const int ti = row / 12, tj = row - ti * 12;
         if (at_row_is_pad(p, g, ti, tj)) {
-          const uint4* bsrc = reinterpret_cast<const uint4*>(p.bias16 + (size_t)tq * p.C + head * 32);
+          const uint32_t bsrc = ptx::smem_u32(sB16) + tq * 64;
           const uint32_t a = ptx::smem_u32(sQKV + (i1 % AT_STAGES) * AT_STAGE_BYTES) + tq * AT_TILE_BYTES + row * 64;
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) ptx::sts128(a + ((ch ^ ((row >> 1) & 3)) << 4), __ldg(bsrc + ch));
+          for (int ch = 0; ch < 4; ++ch) ptx::sts128(a + ((ch ^ ((row >> 1) & 3)) << 4), ptx::lds128(bsrc + ch * 16));
         }
       }
       ptx::fence_proxy_async_smem();
@@ -433,11 +472,11 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       for (int c2 = 0; c2 < 24; ++c2) {
         float lo, hi;
         upk2(sc[c2], lo, hi);
-        mx = fmaxf(mx, fmaxf(lo, hi));
+        mx = fmax3(mx, lo, hi);
       }
       if (row_ok) ptx::sts32(smax + ((par * 3 + third) * 144 + r) * 4, mx);
       pair_bar_sync(pair);
-      const float m = fmaxf(fmaxf(ptx::lds32(smax + ((par * 3 + 0) * 144 + rr) * 4), ptx::lds32(smax + ((par * 3 + 1) * 144 + rr) * 4)),
+      const float m = fmax3(ptx::lds32(smax + ((par * 3 + 0) * 144 + rr) * 4), ptx::lds32(smax + ((par * 3 + 1) * 144 + rr) * 4),
                             ptx::lds32(smax + ((par * 3 + 2) * 144 + rr) * 4));
       const float moff = m * LOG2E;
 
@@ -453,9 +492,15 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
         uint32_t packed[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          float a0, a1;
-          upk2(fma2(sc[g * 4 + t], l2e2, noff2), a0, a1);
-          const float p0 = ex2(a0), p1 = ex2(a1);
+          const unsigned long long a2 = fma2(sc[g * 4 + t], l2e2, noff2);
+          float p0, p1;
+          if (t < AT_POLY_PAIRS) {
+            ex2_poly2(a2, p0, p1);
+          } else {
+            float a0, a1;
+            upk2(a2, a0, a1);
+            p0 = ex2(a0); p1 = ex2(a1);
+          }
           sum2 = fadd2(sum2, pk2(p0, p1));
           packed[t] = at_pack<DT>(p0, p1);
         }
@@ -515,7 +560,8 @@ void tc_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   per_head = std::min(per_head, a.n_windows);
   char desc[96] = "";
   if (ctx.kt) snprintf(desc, sizeof desc, "windows=%d heads=%d shift=%d grid=%d", a.n_windows, a.heads, a.shift, a.heads * per_head);
-  KScope ks(ctx, KC_ATTN_TC, 4.0 * 144 * 144 * 32 * (double)a.n_windows * a.heads, 0, desc);
+  KScope ks(ctx, KC_ATTN_TC, 4.0 * 144 * 144 * 32 * (double)a.n_windows * a.heads,
+            (double)a.n_windows * a.heads * 144 * 32 * 4 * dsize(a.qkv.dt), desc);   // q, k, v in + o out
   if (a.qkv.dt == BF16) tc_attn_kernel<BF16><<<a.heads * per_head, AT_THREADS, AT_SMEM, ctx.stream>>>(tm, p);
   else tc_attn_kernel<F16><<<a.heads * per_head, AT_THREADS, AT_SMEM, ctx.stream>>>(tm, p);
   BRN_CUDA(cudaGetLastError());

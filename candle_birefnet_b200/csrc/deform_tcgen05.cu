@@ -365,8 +365,12 @@ void tc_deform(const LaunchCtx& ctx, const DeformArgs& a) {
   CUtensorMap tmB = make_tmap_16(w.w16(a.x.dt), a.x.dt, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B);
   char desc[96] = "";
   const double M = (double)a.x.rows();
-  if (ctx.kt) snprintf(desc, sizeof desc, "M=%lld N=%d k=%d cl=%d", (long long)a.x.rows(), w.N, p.k, CL);
-  KScope ks(ctx, KC_DEFORM_TC, 2.0 * M * w.N * w.taps() * 64, M * w.taps() * 4 * 128, desc);
+  // bytes = COMPULSORY HBM traffic (input + offsets/modulators + output + weights once); the gather's sampled bytes
+  // (4 corners x 128 B per pixel and tap, served by L1 / L2) go into the description
+  if (ctx.kt) snprintf(desc, sizeof desc, "M=%lld N=%d k=%d cl=%d sampled_mb=%.1f", (long long)a.x.rows(), w.N, p.k, CL,
+                       M * w.taps() * 4 * 128 / 1e6);
+  KScope ks(ctx, KC_DEFORM_TC, 2.0 * M * w.N * w.taps() * 64,
+            M * (64.0 * dsize(a.x.dt) + 3.0 * w.taps() * 4 + (double)w.N * dsize(a.out.dt)) + (double)w.N * w.taps() * 64 * 2, desc);
   auto launch = [&](auto kern) {
     BRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM));
     // keep the shared-memory carve-out at what the kernel needs: the rest of the 228 KB is the gather's L1

@@ -9,10 +9,12 @@ namespace brn {
 __device__ __forceinline__ float g_ld(const void* p, int dt, long long i) { return ld_elem(p, dt, i); }
 __device__ __forceinline__ void g_st(void* p, int dt, long long i, float v) { st_elem(p, dt, i, v); }
 
-#define GLUE_LAUNCH_PROLOGUE(ctx)        \
+// `bytes` = compulsory HBM traffic of the launch (every input element read once + every output element written once):
+// the figure bench.py divides by the measured time for the glue class's achieved GB/s
+#define GLUE_LAUNCH_PROLOGUE(ctx, bytes)  \
   if ((ctx).launches) ++*(ctx).launches; \
   if ((ctx).dry) return;                 \
-  KScope ks__((ctx), KC_GLUE, 0.0, 0.0, __func__);
+  KScope ks__((ctx), KC_GLUE, 0.0, (double)(bytes), __func__);
 
 // ------------------------------------------------------------------------------------------------
 // PatchEmbed im2col (src/swin.rs:692-704): row (b,py,px), k = c*P*P + ky*P + kx  <-  x[b,c,py*P+ky,px*P+kx]
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(256) patch_im2col4_kernel(const float* __restr
 }
 
 void glue_patch_im2col(const LaunchCtx& ctx, const float* x, int B, int H, int W, int P, View out) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)B * 3 * H * W * (4 + dsize(out.dt)));
   if (P == 4 && out.dt != F32 && out.ld == 48 && (W / 4) % 32 == 0 && ((uintptr_t)out.p & 15) == 0 && ((uintptr_t)x & 15) == 0) {
     const long long groups = (long long)B * (H / 4) * (W / 4 / 32);
     patch_im2col4_kernel<<<(unsigned)((groups + 7) / 8), 256, 0, ctx.stream>>>(x, H, W, (uint16_t*)out.p, out.dt, groups);
@@ -106,7 +108,7 @@ __global__ void resize_nchw_kernel(const float* x, int C, int H, int W, float* o
 }
 
 void glue_resize_nchw(const LaunchCtx& ctx, const float* x, int B, int C, int H, int W, float* out, int Ho, int Wo) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)B * C * 4 * ((double)H * W + (double)Ho * Wo));
   long long total = (long long)B * C * Ho * Wo;
   resize_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(x, C, H, W, out, Ho, Wo, total);
   BRN_CUDA(cudaGetLastError());
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(256) resize_nhwc_vec8_kernel(ResizeP p) {
 }
 
 void glue_resize_nhwc(const LaunchCtx& ctx, View in, View out) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)in.rows() * in.C * dsize(in.dt) + (double)out.rows() * out.C * dsize(out.dt));
   ResizeP p{in.p, in.dt, in.ld, in.H, in.W, in.C, out.p, out.dt, out.ld, out.H, out.W, 0};
   const bool vec = in.dt != F32 && in.dt == out.dt && in.C % 8 == 0 && in.ld % 8 == 0 && out.ld % 8 == 0 &&
                    (((uintptr_t)in.p | (uintptr_t)out.p) & 15) == 0;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(256) image2patches_tiled_kernel(const float* _
 }
 
 void glue_image2patches(const LaunchCtx& ctx, const float* x, int B, int H, int W, int th, int tw, View out) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)B * 3 * H * W * (4 + dsize(out.dt)));
   const int Cn = 3 * (H / th) * (W / tw);
   if (out.dt != F32 && tw % 32 == 0 && out.ld % 2 == 0 && ((uintptr_t)out.p & 3) == 0 && th <= 65535 && (long long)B * (Cn / 48) <= 65535) {
     auto grid_for = [&](int ch) { return dim3(tw / 32, th, B * (Cn / ch)); };
@@ -298,7 +300,7 @@ __global__ void nchw_to_nhwc_kernel(const float* x, int C, int H, int W, void* o
   g_st(out, odt, ((b * H + y) * (long long)W + xx) * ldo + c, x[((b * C + c) * H + y) * (long long)W + xx]);
 }
 void glue_nchw_to_nhwc(const LaunchCtx& ctx, const float* x, int B, int C, int H, int W, View out) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)B * C * H * W * (4 + dsize(out.dt)));
   long long total = (long long)B * C * H * W;
   nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(x, C, H, W, out.p, out.dt, out.ld, total);
   BRN_CUDA(cudaGetLastError());
@@ -312,7 +314,7 @@ __global__ void nhwc_to_nchw_kernel(const void* x, int xdt, int ldx, int C, int 
   out[i] = g_ld(x, xdt, ((b * H + y) * (long long)W + xx) * ldx + c);
 }
 void glue_nhwc_to_nchw(const LaunchCtx& ctx, View in, float* out) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)in.rows() * in.C * (4 + dsize(in.dt)));
   long long total = (long long)in.B * in.C * in.H * in.W;
   nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(in.p, in.dt, in.ld, in.C, in.H, in.W,
                                                                               out, total);
@@ -326,7 +328,7 @@ __global__ void copy_cast_kernel(const void* x, int xdt, int ldx, void* out, int
   g_st(out, odt, row * ldo + c, g_ld(x, xdt, row * ldx + c));
 }
 void glue_copy_cast(const LaunchCtx& ctx, View in, View out) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)in.rows() * in.C * (dsize(in.dt) + dsize(out.dt)));
   long long total = in.rows() * in.C;
   copy_cast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx.stream>>>(in.p, in.dt, in.ld, out.p, out.dt, out.ld,
                                                                            in.C, total);
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(256) ln_stats_cast_kernel(const float* __restr
   if (lane == 0) stats[m] = make_float2(s, q);
 }
 void glue_ln_stats_cast(const LaunchCtx& ctx, View x, View x16, float2* stats) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)x.rows() * (x.C * 6.0 + 8.0));
   BRN_CHECK(x.dt == F32 && x16.dt != F32, 5, "ln_stats_cast: fp32 in, 16-bit out");
   ln_stats_cast_kernel<<<(unsigned)((x.rows() + 7) / 8), 256, 0, ctx.stream>>>((const float*)x.p, x.ld, x.rows(), x.C, x16.p,
                                                                              x16.dt, x16.ld, stats);
@@ -388,7 +390,7 @@ __global__ void sigmoid_kernel(float* p, long long n) {
   if (i < n) p[i] = 1.f / (1.f + expf(-p[i]));
 }
 void glue_sigmoid(const LaunchCtx& ctx, float* p, long long n) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, 8.0 * (double)n);
   sigmoid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx.stream>>>(p, n);
   BRN_CUDA(cudaGetLastError());
 }
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(256) gap_sum64_kernel(const uint16_t* __restri
 int glue_gap_blocks(int HW) { return (HW + GAP_CHUNK - 1) / GAP_CHUNK; }
 
 void glue_gap_sum(const LaunchCtx& ctx, View x, float* part) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)x.rows() * x.C * dsize(x.dt));
   BRN_CHECK(x.C <= 256 && 256 % x.C == 0, 5, "gap_sum: C must divide 256");
   const int HW = x.H * x.W;
   dim3 grid(glue_gap_blocks(HW), x.B);
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(256) aspp_pool_bias_kernel(const float* part, 
 
 void glue_aspp_pool_bias(const LaunchCtx& ctx, const float* part, int B, int HW, const LayerW* gap_conv,
                          const float* conv1_tail, const float* bn1_shift, float* out) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)B * (glue_gap_blocks(HW) * 64 + 64) * 4.0 + (256.0 * 64 + 64 * 256) * 4.0);
   aspp_pool_bias_kernel<<<B, 256, 0, ctx.stream>>>(part, glue_gap_blocks(HW), HW, gap_conv->w32, gap_conv->bias, conv1_tail,
                                                    bn1_shift, out);
   BRN_CUDA(cudaGetLastError());
@@ -545,7 +547,7 @@ __global__ void __launch_bounds__(256) gate_vec8_kernel(uint16_t* p, int dt, int
 }
 
 void glue_gate(const LaunchCtx& ctx, View p, View g16, const float* w16, float b0) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)p.rows() * (2.0 * p.C * dsize(p.dt) + 16.0 * dsize(g16.dt)));
   if (p.dt != F32 && g16.dt == p.dt && p.C % 8 == 0 && p.ld % 8 == 0 && g16.ld % 8 == 0 && g16.C == 16 &&
       (((uintptr_t)p.p | (uintptr_t)g16.p) & 15) == 0) {
     const long long tot = p.rows() * (p.C / 8);
@@ -652,7 +654,7 @@ __global__ void __launch_bounds__(256) deform_sample_k1_kernel(const uint16_t* _
 }
 
 void glue_deform_sample_k1(const LaunchCtx& ctx, View x, View om, int om_tiled, const LayerW* om_layer, View out) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)x.rows() * 64 * (dsize(x.dt) + dsize(out.dt)) + (om_layer ? 0.0 : (double)x.rows() * 12));
   BRN_CHECK(x.C == 64 && x.dt != F32 && out.dt == x.dt && x.ld % 8 == 0 && out.ld % 8 == 0, 5, "deform_sample_k1: layout");
   const long long total = x.rows() * 8;
   const unsigned grid = (unsigned)((total + 255) / 256);
@@ -688,7 +690,7 @@ __global__ void __launch_bounds__(256) dot1_kernel(const void* p, int pdt, int l
   if (lane == 0) out[m] = s;
 }
 void glue_dot1(const LaunchCtx& ctx, View p, const float* w, float* out) {
-  GLUE_LAUNCH_PROLOGUE(ctx);
+  GLUE_LAUNCH_PROLOGUE(ctx, (double)p.rows() * (p.C * dsize(p.dt) + 4.0));
   long long rows = p.rows();
   dot1_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ctx.stream>>>(p.p, p.dt, p.ld, p.C, w, out, rows);
   BRN_CUDA(cudaGetLastError());

@@ -190,7 +190,11 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
   for (int it = 0; it < 4; ++it) orow_p[it] = (char*)p.out + (orow_b[it] * p.ldo + n0) * ESZ;
 
   // residual prefetch: slot (granule & 1) holds the residual of that granule
-  uint4 rq0[4], rq1[4];
+  // residual prefetch ring: slot (granule % RSLOTS) holds the residual of that granule.  Four granules (4 x 16-byte
+  // loads x 32 lanes = 8 KB per warp, 64 KB per SM) in flight: with two the residual GEMMs sat at 3.7-3.9 TB/s whatever
+  // their shape (r02 run C) -- Little's law on ~1 us of loaded DRAM latency.
+  constexpr int RSLOTS = RM == 1 ? 4 : 2;                 // (the 16-bit residual variant spills at four)
+  uint4 rq0[4], rq1[4], rq2[RSLOTS == 4 ? 4 : 1], rq3[RSLOTS == 4 ? 4 : 1];
   auto res_issue = [&](int c, uint4 (&q)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) q[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -221,7 +225,10 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
   for (int j = 0; j < GC; ++j) { va[j] = 0u; if (PP) vb[j] = 0u; }
   tmem_ld16_raw(taddr + c0, va);
   if (!O32 && c0 + 16 < c1) tmem_ld16_raw(taddr + c0 + 16, va + (GC - 16));
-  if (rmode == 1 || rmode == 2) { res_issue(c0, rq0); res_issue(c0 + GC, rq1); }
+  if (rmode == 1 || rmode == 2) {
+    res_issue(c0, rq0); res_issue(c0 + GC, rq1);
+    if constexpr (RSLOTS == 4) { res_issue(c0 + 2 * GC, rq2); res_issue(c0 + 3 * GC, rq3); }
+  }
   // every row of this warp is a real output row: the interior store path needs no per-row predicate
   const bool rows_ok = __all_sync(0xffffffffu, orow >= 0);
   float es[EMIT ? 4 : 1], eq[EMIT ? 4 : 1];
@@ -368,17 +375,27 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
           }
       }
     }
-    if (rmode == 1 || rmode == 2) res_issue(c + 2 * GC, rq);   // this slot's next granule, after the stores (aliasing)
+    if (rmode == 1 || rmode == 2) res_issue(c + RSLOTS * GC, rq);   // this slot's next granule, after the stores (aliasing)
     __syncwarp();
   };
 
-  for (int c = c0; c < c1; c += 2 * GC) {
-    if constexpr (PP) {
-      granule(c, rq0, va, vb);
-      if (c + GC < c1) granule(c + GC, rq1, vb, va);
-    } else {
+  if constexpr (RSLOTS == 4) {
+    static_assert(!PP, "the residual variants use one TMEM register set");
+    for (int c = c0; c < c1; c += 4 * GC) {
       granule(c, rq0, va, va);
       if (c + GC < c1) granule(c + GC, rq1, va, va);
+      if (c + 2 * GC < c1) granule(c + 2 * GC, rq2, va, va);
+      if (c + 3 * GC < c1) granule(c + 3 * GC, rq3, va, va);
+    }
+  } else {
+    for (int c = c0; c < c1; c += 2 * GC) {
+      if constexpr (PP) {
+        granule(c, rq0, va, vb);
+        if (c + GC < c1) granule(c + GC, rq1, vb, va);
+      } else {
+        granule(c, rq0, va, va);
+        if (c + GC < c1) granule(c + GC, rq1, va, va);
+      }
     }
   }
   if (EMIT) {

@@ -238,30 +238,51 @@ class BiRefNet:
 
     __call__ = forward
 
-    def backbone_forward(self, x: np.ndarray) -> List[np.ndarray]:
-        """SwinTransformer::forward (src/swin.rs:768-797) -> [x1,x2,x3,x4] NCHW float32."""
+    def _feature_call(self, fn, x, chans, stream=None):
+        """Shared marshalling of brn_backbone_forward / brn_features_forward: host numpy or torch CUDA tensors."""
+        if _is_torch_cuda(x):
+            import torch
+            assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4 and x.shape[1] == 3
+            if x.device.index != self.device:
+                raise BrnError(1, f"input lives on cuda:{x.device.index}, the handle on cuda:{self.device}")
+            B, _, H, W = x.shape
+            outs = [torch.empty((B, chans[i], H // (4 << i), W // (4 << i)), dtype=torch.float32, device=x.device)
+                    for i in range(4)]
+            ptrs = (C.c_void_p * 4)(*[C.c_void_p(o.data_ptr()) for o in outs])
+            s = stream if stream is not None else torch.cuda.current_stream(x.device).cuda_stream
+            check(fn(self._h, C.c_void_p(x.data_ptr()), B, H, W, 1, ptrs, 1, C.c_void_p(s or 1)))
+            return outs
         x = np.ascontiguousarray(x, dtype=np.float32)
         B, _, H, W = x.shape
-        E = self.config.swin.embed_dim
-        outs = [np.empty((B, E << i, H // (4 << i), W // (4 << i)), dtype=np.float32) for i in range(4)]
+        outs = [np.empty((B, chans[i], H // (4 << i), W // (4 << i)), dtype=np.float32) for i in range(4)]
         ptrs = (C.c_void_p * 4)(*[o.ctypes.data_as(C.c_void_p) for o in outs])
-        check(lib().brn_backbone_forward(self._h, x.ctypes.data_as(C.c_void_p), B, H, W, 0, ptrs, 0, None))
+        check(fn(self._h, x.ctypes.data_as(C.c_void_p), B, H, W, 0, ptrs, 0, None))
         return outs
 
-    def features_forward(self, x: np.ndarray) -> List[np.ndarray]:
+    def backbone_forward(self, x, stream=None):
+        """SwinTransformer::forward (src/swin.rs:768-797) -> [x1,x2,x3,x4] NCHW float32."""
+        E = self.config.swin.embed_dim
+        return self._feature_call(lib().brn_backbone_forward, x, [E << i for i in range(4)], stream)
+
+    def features_forward(self, x, stream=None):
         """First half of forward_logits (src/birefnet.rs:412-454) -> [x1,x2,x3,x4_cxt] NCHW float32: the multi-scale
         features the squeeze module and decoder consume (what examples/bench_inference.rs times as `backbone`)."""
-        x = np.ascontiguousarray(x, dtype=np.float32)
-        B, _, H, W = x.shape
         E = self.config.swin.embed_dim
-        ch = [2 * (E << i) for i in range(3)] + [2 * E * 15]
-        outs = [np.empty((B, ch[i], H // (4 << i), W // (4 << i)), dtype=np.float32) for i in range(4)]
-        ptrs = (C.c_void_p * 4)(*[o.ctypes.data_as(C.c_void_p) for o in outs])
-        check(lib().brn_features_forward(self._h, x.ctypes.data_as(C.c_void_p), B, H, W, 0, ptrs, 0, None))
-        return outs
+        return self._feature_call(lib().brn_features_forward, x, [2 * (E << i) for i in range(3)] + [30 * E], stream)
 
-    def decoder_forward(self, x, x1, x2, x3, x4) -> np.ndarray:
+    def decoder_forward(self, x, x1, x2, x3, x4, out=None, stream=None):
         """SqueezeModule + BiRefNetDecoder::forward (src/birefnet.rs:86-94, 278-376) on given features."""
+        if _is_torch_cuda(x):
+            import torch
+            ts = (x, x1, x2, x3, x4)
+            assert all(_is_torch_cuda(t) and t.dtype == torch.float32 and t.is_contiguous() for t in ts)
+            B, _, H, W = x.shape
+            if out is None:
+                out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+            s = stream if stream is not None else torch.cuda.current_stream(x.device).cuda_stream
+            check(lib().brn_decoder_forward(self._h, *[C.c_void_p(t.data_ptr()) for t in ts], B, H, W, 1,
+                                            C.c_void_p(out.data_ptr()), C.c_void_p(s or 1)))
+            return out
         arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (x, x1, x2, x3, x4)]
         B, _, H, W = arrs[0].shape
         out = np.empty((B, 1, H, W), dtype=np.float32)

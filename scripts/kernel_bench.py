@@ -75,6 +75,14 @@ def main():
                 ms = ops.bench_op("attn", nw, side, side, heads, 0, shift, precision="fp16")
                 fl = 4.0 * 144 * 144 * 32 * nw * heads
                 print(f"attn windows={nw:5d} heads={heads:2d} shift={shift}: {ms*1e3:9.1f} us  {fl/ms/1e9:7.1f} TF/s  {nw*heads/ms/1e3:8.1f} units/us", flush=True)
+    if which == "attnm":   # the model's attention launches (token-order output, pad fix-up): full-resolution grids at batch 16
+        for (nw, heads, side, pad) in ((7744, 6, 22, 8), (1936, 12, 11, 4), (576, 24, 6, 8), (144, 48, 3, 4), (64, 48, 2, 8)):
+            for shift in (0, 6):
+                ms0 = ops.bench_op("attn", nw, side, side, heads, 0, shift, precision="fp16")
+                ms1 = ops.bench_op("attn", nw, side, side, heads, pad, shift, with_res=True, precision="fp16")
+                print(f"attn windows={nw:5d} heads={heads:2d} shift={shift} pad={pad}: window-order {ms0*1e3:8.1f} us {nw*heads/ms0/1e3:6.1f} units/us | "
+                      f"token-order+pads {ms1*1e3:8.1f} us {nw*heads/ms1/1e3:6.1f} units/us", flush=True)
+        return
     if which == "attn1":   # attn1 <windows> <heads> <side> <shift>
         nw, heads, side, shift = [int(v) for v in sys.argv[2:6]]
         ms = ops.bench_op("attn", nw, side, side, heads, 0, shift, precision="fp16")
