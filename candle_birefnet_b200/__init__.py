@@ -6,5 +6,6 @@ mirror of `BiRefNet::new(BiRefNetConfig::swin_l(), vb)` / `forward_logits` plus 
 from .model import BiRefNet, BiRefNetConfig, SwinConfig  # noqa: F401
 from ._lib import BrnError, lib  # noqa: F401
 from . import ops  # noqa: F401
+from .ops import DeformableConv2d  # noqa: F401  (src/lib.rs:13 re-export)
 
-__all__ = ["BiRefNet", "BiRefNetConfig", "SwinConfig", "BrnError", "ops", "lib"]
+__all__ = ["BiRefNet", "BiRefNetConfig", "SwinConfig", "BrnError", "DeformableConv2d", "ops", "lib"]

@@ -72,7 +72,9 @@ def lib() -> C.CDLL:
     L.brn_features_forward.argtypes = [vp, vp, i32, i32, i32, C.c_int, C.POINTER(vp), C.c_int, vp]
     L.brn_decoder_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_int, vp, vp]
     L.brn_window_attention.argtypes = [C.c_int, C.c_int, vp, vp, i32, i32, i32, i32, i32, vp]
-    L.brn_deform_conv2d.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.brn_deform_conv2d.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.brn_deformable_conv2d.argtypes = [C.c_int, C.c_int, C.c_int, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32,
+                                        i32, vp]
     L.brn_linear.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.brn_preprocess_rgb8.argtypes = [C.c_int, vp, i32, i32, i32, i32, i32, vp]
     L.brn_postprocess_mask.argtypes = [C.c_int, vp, i32, i32, i32, i32, i32, vp]
@@ -80,6 +82,20 @@ def lib() -> C.CDLL:
     L.brn_ln_linear.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.brn_conv2d.argtypes = [C.c_int, C.c_int, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     L.brn_bench_op.argtypes = [C.c_int, C.c_int, C.c_int] + [i32] * 10 + [fp]
+    L.brn_sharded_create.argtypes = [C.POINTER(BrnConfig), C.POINTER(i32), i32, C.POINTER(vp)]
+    L.brn_sharded_destroy.argtypes = [vp]
+    L.brn_sharded_destroy.restype = None
+    L.brn_sharded_num_devices.argtypes = [vp]
+    L.brn_sharded_num_devices.restype = i32
+    L.brn_sharded_set_tensor.argtypes = [vp, C.c_char_p, vp, C.c_int, C.POINTER(i64), C.c_int]
+    L.brn_sharded_load_safetensors.argtypes = [vp, C.c_char_p, C.POINTER(i32)]
+    L.brn_sharded_finalize.argtypes = [vp]
+    for name in ("brn_sharded_forward_logits", "brn_sharded_forward"):
+        getattr(L, name).argtypes = [vp, vp, i32, i32, i32, vp]
+    L.brn_host_alloc.argtypes = [C.c_size_t]
+    L.brn_host_alloc.restype = vp
+    L.brn_host_free.argtypes = [vp]
+    L.brn_host_free.restype = None
     L.brn_launch_count.argtypes = [vp]
     L.brn_launch_count.restype = i64
     L.brn_launch_count_reset.argtypes = [vp]

@@ -32,6 +32,11 @@ struct brn_model {
   Model impl;
   brn_model(const brn_config& c, int dev) : impl(c, dev) {}
 };
+struct brn_sharded {          // defined in sharded.cpp; the ABI only needs the handle list
+  std::vector<Model*> models;
+  std::vector<int> devices;
+  ~brn_sharded();
+};
 
 extern "C" {
 
@@ -172,6 +177,46 @@ brn_status brn_decoder_forward(brn_model* m, const float* x, const float* x1, co
     m->impl.decoder_api(x, x1, x2, x3, x4, B, H, W, is_device != 0, out, (cudaStream_t)stream);
   });
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// single-process image sharding: one handle + one host thread per GPU
+// ---------------------------------------------------------------------------------------------------------------
+brn_status brn_sharded_create(const brn_config* cfg, const int32_t* devices, int32_t n_devices, brn_sharded** out) {
+  return guard([&] {
+    BRN_CHECK(cfg && devices && out, 1, "brn_sharded_create: null argument");
+    std::vector<int> d(devices, devices + (n_devices > 0 ? n_devices : 0));
+    *out = sharded_create(*cfg, d.data(), (int)d.size());
+  });
+}
+void brn_sharded_destroy(brn_sharded* s) { delete s; }
+int32_t brn_sharded_num_devices(const brn_sharded* s) { return s ? (int32_t)s->models.size() : 0; }
+brn_status brn_sharded_set_tensor(brn_sharded* s, const char* key, const void* data, int dtype, const int64_t* shape,
+                                  int rank) {
+  return guard([&] { BRN_CHECK(s, 1, "null handle"); sharded_set_tensor(s, key, data, dtype, shape, rank); });
+}
+brn_status brn_sharded_load_safetensors(brn_sharded* s, const char* path, int32_t* n_loaded) {
+  return guard([&] {
+    BRN_CHECK(s && path, 1, "null argument");
+    const int n = sharded_load_safetensors(s, path);
+    if (n_loaded) *n_loaded = n;
+  });
+}
+brn_status brn_sharded_finalize(brn_sharded* s) {
+  return guard([&] { BRN_CHECK(s, 1, "null handle"); sharded_finalize(s); });
+}
+brn_status brn_sharded_forward_logits(brn_sharded* s, const float* x, int32_t B, int32_t H, int32_t W, float* out) {
+  return guard([&] { BRN_CHECK(s, 1, "null handle"); sharded_forward(s, x, B, H, W, out, false); });
+}
+brn_status brn_sharded_forward(brn_sharded* s, const float* x, int32_t B, int32_t H, int32_t W, float* out) {
+  return guard([&] { BRN_CHECK(s, 1, "null handle"); sharded_forward(s, x, B, H, W, out, true); });
+}
+// pinned, portable host memory: buffers every GPU of a sharded handle can copy from / to at full PCIe rate
+void* brn_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void brn_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int64_t brn_launch_count(const brn_model* m) { return m ? m->impl.launches : 0; }
 void brn_launch_count_reset(brn_model* m) { if (m) m->impl.launches = 0; }
@@ -316,9 +361,11 @@ brn_status brn_conv2d(int device, int precision, const float* x, const float* we
 
 brn_status brn_deform_conv2d(int device, int precision, const float* x, const float* offset, const float* mask,
                              const float* weight, const float* bias, int32_t B, int32_t C, int32_t H, int32_t W,
-                             int32_t O, int32_t k, float* out) {
+                             int32_t O, int32_t k, int32_t stride, int32_t padding, float* out) {
   return guard([&] {
-    BRN_CHECK(x && offset && mask && weight && out && (k & 1), 1, "brn_deform_conv2d: bad argument");
+    BRN_CHECK(x && offset && mask && weight && out && k > 0 && stride > 0 && padding >= 0, 1, "brn_deform_conv2d: bad argument");
+    const int Ho = (H + 2 * padding - k) / stride + 1, Wo = (W + 2 * padding - k) / stride + 1;
+    BRN_CHECK(Ho > 0 && Wo > 0, 5, "brn_deform_conv2d: empty output");
     Scratch s(device);
     LaunchCtx ctx = make_ctx(s, precision);
     const int AD = precision == BRN_PREC_FP16 ? F16 : precision == BRN_PREC_BF16 ? BF16 : F32;
@@ -327,16 +374,64 @@ brn_status brn_deform_conv2d(int device, int precision, const float* x, const fl
     float* dx = s.put(x, (size_t)B * C * H * W);
     View xv = make_view(s.alloc((size_t)B * C * H * W * dsize(AD)), AD, B, H, W, C);
     glue_nchw_to_nhwc(ctx, dx, B, C, H, W, xv);
-    // offsets (2*taps channels) and modulators (taps channels) -> one NHWC fp32 tensor [.., 3*taps]
-    View om = make_view(s.alloc((size_t)B * H * W * 3 * taps * 4), F32, B, H, W, 3 * taps);
-    glue_nchw_to_nhwc(ctx, s.put(offset, (size_t)B * 2 * taps * H * W), B, 2 * taps, H, W, om.slice(0, 2 * taps));
-    glue_nchw_to_nhwc(ctx, s.put(mask, (size_t)B * taps * H * W), B, taps, H, W, om.slice(2 * taps, taps));
-    View o = make_view(s.alloc((size_t)B * O * H * W * 4), F32, B, H, W, O);
-    DeformArgs d; d.x = xv; d.om = om; d.w = &L; d.out = o;
+    // offsets (2*taps channels) and modulators (taps channels), at the OUTPUT resolution -> one NHWC fp32 tensor [.., 3*taps]
+    View om = make_view(s.alloc((size_t)B * Ho * Wo * 3 * taps * 4), F32, B, Ho, Wo, 3 * taps);
+    glue_nchw_to_nhwc(ctx, s.put(offset, (size_t)B * 2 * taps * Ho * Wo), B, 2 * taps, Ho, Wo, om.slice(0, 2 * taps));
+    glue_nchw_to_nhwc(ctx, s.put(mask, (size_t)B * taps * Ho * Wo), B, taps, Ho, Wo, om.slice(2 * taps, taps));
+    View o = make_view(s.alloc((size_t)B * O * Ho * Wo * 4), F32, B, Ho, Wo, O);
+    DeformArgs d; d.x = xv; d.om = om; d.w = &L; d.out = o; d.stride = stride; d.pad = padding;
     op_deform(ctx, d);
-    float* on = (float*)s.alloc((size_t)B * O * H * W * 4);
+    float* on = (float*)s.alloc((size_t)B * O * Ho * Wo * 4);
     glue_nhwc_to_nchw(ctx, o, on);
-    BRN_CUDA(cudaMemcpyAsync(out, on, (size_t)B * O * H * W * 4, cudaMemcpyDeviceToHost, s.stream));
+    BRN_CUDA(cudaMemcpyAsync(out, on, (size_t)B * O * Ho * Wo * 4, cudaMemcpyDeviceToHost, s.stream));
+    BRN_CUDA(cudaStreamSynchronize(s.stream));
+  });
+}
+
+// DeformableConv2d::new + forward (src/deform_conv.rs:29-99): the module owns offset_conv, modulator_conv and
+// regular_conv (all k x k, same stride / padding, with bias); offset = offset_conv(x), modulator = 2 sigmoid(
+// modulator_conv(x)) (:83-86); then the modulated deformable conv (Metal path, :102-215) or -- deform_mode
+// CPU_FALLBACK, what candle computes on Device::Cpu (:95-98) -- plain regular_conv(x).
+brn_status brn_deformable_conv2d(int device, int precision, int deform_mode, const float* x, int32_t B, int32_t C, int32_t H,
+                                 int32_t W, const float* offset_w, const float* offset_b, const float* modulator_w,
+                                 const float* modulator_b, const float* regular_w, const float* regular_b, int32_t O,
+                                 int32_t k, int32_t stride, int32_t padding, float* out) {
+  return guard([&] {
+    BRN_CHECK(x && offset_w && offset_b && modulator_w && modulator_b && regular_w && out, 1, "brn_deformable_conv2d: null argument");
+    BRN_CHECK(B > 0 && C > 0 && O > 0 && k > 0 && stride > 0 && padding >= 0, 1, "brn_deformable_conv2d: bad argument");
+    BRN_CHECK(deform_mode == BRN_DEFORM_CPU_FALLBACK || deform_mode == BRN_DEFORM_DEFORMABLE, 1, "bad deform mode");
+    const int Ho = (H + 2 * padding - k) / stride + 1, Wo = (W + 2 * padding - k) / stride + 1;
+    BRN_CHECK(Ho > 0 && Wo > 0, 5, "brn_deformable_conv2d: empty output");
+    Scratch s(device);
+    LaunchCtx ctx = make_ctx(s, precision);
+    const int AD = precision == BRN_PREC_FP16 ? F16 : precision == BRN_PREC_BF16 ? BF16 : F32;
+    const int taps = k * k;
+    float* dx = s.put(x, (size_t)B * C * H * W);
+    View xv = make_view(s.alloc((size_t)B * C * H * W * dsize(AD)), AD, B, H, W, C);
+    glue_nchw_to_nhwc(ctx, dx, B, C, H, W, xv);
+    LayerW Lr = make_layer_standalone(O, C, k, k, regular_w, regular_b, s.ptrs);
+    View o = make_view(s.alloc((size_t)B * O * Ho * Wo * 4), F32, B, Ho, Wo, O);
+    if (deform_mode == BRN_DEFORM_CPU_FALLBACK) {
+      GemmArgs g; g.x = xv; g.w = &Lr; g.pad = padding; g.stride = stride; g.out = o;
+      op_gemm(ctx, g);
+    } else {
+      // offset_conv ++ modulator_conv share input and geometry: one conv with 3 k^2 outputs, 2 sigmoid on the tail
+      std::vector<float> wom((size_t)3 * taps * C * taps), bom((size_t)3 * taps);
+      memcpy(wom.data(), offset_w, (size_t)2 * taps * C * taps * 4);
+      memcpy(wom.data() + (size_t)2 * taps * C * taps, modulator_w, (size_t)taps * C * taps * 4);
+      memcpy(bom.data(), offset_b, (size_t)2 * taps * 4);
+      memcpy(bom.data() + 2 * taps, modulator_b, (size_t)taps * 4);
+      LayerW Lom = make_layer_standalone(3 * taps, C, k, k, wom.data(), bom.data(), s.ptrs);
+      View om = make_view(s.alloc((size_t)B * Ho * Wo * 3 * taps * 4), F32, B, Ho, Wo, 3 * taps);
+      GemmArgs g; g.x = xv; g.w = &Lom; g.pad = padding; g.stride = stride; g.act = ACT_2SIGMOID_TAIL; g.act_from = 2 * taps;
+      g.out = om;
+      op_gemm(ctx, g);
+      DeformArgs d; d.x = xv; d.om = om; d.w = &Lr; d.out = o; d.stride = stride; d.pad = padding;
+      op_deform(ctx, d);
+    }
+    float* on = (float*)s.alloc((size_t)B * O * Ho * Wo * 4);
+    glue_nhwc_to_nchw(ctx, o, on);
+    BRN_CUDA(cudaMemcpyAsync(out, on, (size_t)B * O * Ho * Wo * 4, cudaMemcpyDeviceToHost, s.stream));
     BRN_CUDA(cudaStreamSynchronize(s.stream));
   });
 }

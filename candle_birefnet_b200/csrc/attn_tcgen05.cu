@@ -153,7 +153,7 @@ __device__ __forceinline__ void pair_bar_sync(int pair) { asm volatile("bar.sync
 // 24 F2FP per thread and unit at 4 lanes/clk/SMSP), so AT_POLY_PAIRS of every 4 score pairs take this path instead.
 //   t = a + 1.5*2^23 (round to nearest integer n in the low mantissa bits), f = a - n, p = poly(f), bits += n << 23
 #ifndef BRN_ATTN_POLY_PAIRS
-#define BRN_ATTN_POLY_PAIRS 0
+#define BRN_ATTN_POLY_PAIRS 1      // A/B on B200 (r02 run D): 0 -> 62.0, 1 -> 65.8, 2 -> 63.2, 3 -> 58.2 units/us (7744 windows x 6 heads)
 #endif
 constexpr int AT_POLY_PAIRS = BRN_ATTN_POLY_PAIRS;
 __device__ __forceinline__ void ex2_poly2(unsigned long long a2, float& p0, float& p1) {

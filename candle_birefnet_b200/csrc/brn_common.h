@@ -127,6 +127,7 @@ struct GemmArgs {
   View x;                 // input activation
   const LayerW* w = nullptr;
   int pad = 0;
+  int stride = 1;                // > 1 (or pad != k/2): SIMT kernels only; the model's convs are all stride 1, "same"
   const float* bias = nullptr;   // overrides w->bias when non-null
   int bias_bstride = 0;          // >0: bias is [B][N] (per-image bias; ASPP global-pool branch)
   int act = ACT_NONE;
@@ -151,6 +152,7 @@ struct DeformArgs {
   const LayerW* w = nullptr;
   const float* bias = nullptr;
   int act = ACT_NONE;
+  int stride = 1, pad = -1;       // pad < 0: k/2; stride > 1 or pad != k/2: SIMT kernel only (DeformableConv2d, src/deform_conv.rs:29-99)
   View out;
 };
 

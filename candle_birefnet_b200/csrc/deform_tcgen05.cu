@@ -339,7 +339,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
 }
 
 bool tc_deform_supported(const DeformArgs& a) {
-  return a.w && (a.act == ACT_NONE || a.act == ACT_RELU) && (a.x.dt == BF16 || a.x.dt == F16) && a.w->w16(a.x.dt) && a.x.C == 64 && a.w->cin_pad == 64 && a.x.ld % 8 == 0 &&
+  return a.w && a.stride == 1 && (a.pad < 0 || a.pad == a.w->kh / 2) && (a.act == ACT_NONE || a.act == ACT_RELU) && (a.x.dt == BF16 || a.x.dt == F16) && a.w->w16(a.x.dt) && a.x.C == 64 && a.w->cin_pad == 64 && a.x.ld % 8 == 0 &&
          (((uintptr_t)a.x.p) & 15) == 0 && a.w->N <= 256 && a.om.dt == F32;
 }
 

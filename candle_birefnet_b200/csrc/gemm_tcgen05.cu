@@ -378,6 +378,7 @@ bool tc_gemm_supported(const GemmArgs& a) {
   if (!a.w) return false;
   if ((a.x.dt != BF16 && a.x.dt != F16) || !a.w->w16(a.x.dt)) return false;
   if (a.x.C % 8 != 0 || a.x.ld % 8 != 0 || ((uintptr_t)a.x.p & 15)) return false;
+  if (a.stride != 1 || a.pad != (a.w->kh - 1) / 2 || a.w->kh != a.w->kw) return false;   // stride 1, "same" padding only
   if (a.rowmap.enabled && !(a.x.B == 1 && a.x.H == 1)) return false;
   if (a.bias_bstride && a.x.H * a.x.W < 1) return false;
   return true;

@@ -11,6 +11,7 @@ namespace brn {
 struct SimtGemmP {
   const void* x; int xdt; int B, H, W, Cin, ldx;
   int kh, kw, pad;
+  int stride, Ho, Wo;    // output grid (Ho = (H + 2 pad - kh) / stride + 1); the model itself only uses stride 1, "same"
   const float* w;        // [N][taps][Cin]
   const float* bias; int bias_bstride;
   int N; int act; int act_from;
@@ -56,10 +57,10 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtGemmP p) {
   const bool arow_ok = am < p.M;
   int ab = 0, ay = 0, ax = 0;
   if (arow_ok) {
-    long long hw = (long long)p.H * p.W;
+    long long hw = (long long)p.Ho * p.Wo;
     ab = (int)(am / hw);
     int r = (int)(am % hw);
-    ay = r / p.W; ax = r % p.W;
+    ay = (r / p.Wo) * p.stride; ax = (r % p.Wo) * p.stride;      // top-left input coordinate before padding
   }
   const long long abase = (long long)ab * p.H * p.W * p.ldx;
   const int wn = n0 + lrow;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtGemmP p) {
       orow = rowmap_token(p.rm, m);
       if (orow < 0) continue;
     }
-    int b = p.bias_bstride ? (int)(m / ((long long)p.H * p.W)) : 0;
+    int b = p.bias_bstride ? (int)(m / ((long long)p.Ho * p.Wo)) : 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
@@ -146,6 +147,9 @@ void simt_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
             "simt_gemm: the folded-LayerNorm epilogues and the token->window row map are tensor-core-path features");
   BRN_CHECK(a.w->w32 != nullptr, 7, "simt_gemm: layer has no fp32 weights (a folded tensor-core-only copy)");
   p.kh = a.w->kh; p.kw = a.w->kw; p.pad = a.pad;
+  p.stride = a.stride > 0 ? a.stride : 1;
+  p.Ho = (a.x.H + 2 * a.pad - a.w->kh) / p.stride + 1; p.Wo = (a.x.W + 2 * a.pad - a.w->kw) / p.stride + 1;
+  BRN_CHECK(p.Ho > 0 && p.Wo > 0 && (long long)a.x.B * p.Ho * p.Wo == a.out.rows(), 5, "simt_gemm: output grid mismatch");
   p.w = a.w->w32;
   p.bias = a.bias ? a.bias : a.w->bias; p.bias_bstride = a.bias_bstride;
   p.N = a.w->N; p.act = a.act; p.act_from = a.act_from;
@@ -153,22 +157,26 @@ void simt_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   p.out = a.out.p; p.odt = a.out.dt; p.ldo = a.out.ld;
   p.rm = a.rowmap;
   p.om = nullptr; p.ldom = 0; p.deform = 0;
-  p.M = a.x.rows();
+  p.M = a.out.rows();
   launch_simt_gemm(ctx, p);
 }
 
 void simt_deform(const LaunchCtx& ctx, const DeformArgs& a) {
   SimtGemmP p{};
   p.x = a.x.p; p.xdt = a.x.dt; p.B = a.x.B; p.H = a.x.H; p.W = a.x.W; p.Cin = a.x.C; p.ldx = a.x.ld;
-  p.kh = a.w->kh; p.kw = a.w->kw; p.pad = a.w->kh / 2;
+  p.kh = a.w->kh; p.kw = a.w->kw; p.pad = a.pad >= 0 ? a.pad : a.w->kh / 2;
+  p.stride = a.stride > 0 ? a.stride : 1;
+  p.Ho = (a.x.H + 2 * p.pad - a.w->kh) / p.stride + 1; p.Wo = (a.x.W + 2 * p.pad - a.w->kw) / p.stride + 1;
+  BRN_CHECK(p.Ho > 0 && p.Wo > 0 && (long long)a.x.B * p.Ho * p.Wo == a.out.rows(), 5, "simt_deform: output grid mismatch");
+  BRN_CHECK(a.w->w32 != nullptr, 7, "simt_deform: layer has no fp32 weights");
   p.w = a.w->w32;
   p.bias = a.bias ? a.bias : a.w->bias; p.bias_bstride = 0;
   p.N = a.w->N; p.act = a.act; p.act_from = 0;
   p.res = nullptr; p.resdt = 0; p.ldres = 0;
   p.out = a.out.p; p.odt = a.out.dt; p.ldo = a.out.ld;
   p.om = (const float*)a.om.p; p.ldom = a.om.ld; p.deform = 1;
-  BRN_CHECK(a.om.dt == F32, 5, "simt_deform: offsets must be fp32");
-  p.M = a.x.rows();
+  BRN_CHECK(a.om.dt == F32 && !a.om_tiled, 5, "simt_deform: offsets must be fp32, pixel-major");
+  p.M = a.out.rows();
   launch_simt_gemm(ctx, p);
 }
 

@@ -191,6 +191,17 @@ struct Model {
                      const std::vector<float>& beta, int N, int C);
 };
 
+}  // namespace brn
+
+// sharded.cpp: one handle + one host thread per GPU behind a single C-ABI object
+struct brn_sharded;
+namespace brn {
+brn_sharded* sharded_create(const brn_config& cfg, const int* devices, int n);
+void sharded_set_tensor(brn_sharded*, const char* key, const void* data, int dtype, const int64_t* shape, int rank);
+int sharded_load_safetensors(brn_sharded*, const char* path);
+void sharded_finalize(brn_sharded*);
+void sharded_forward(brn_sharded*, const float* x, int B, int H, int W, float* out, bool apply_sigmoid);
+
 // safetensors_loader.cpp: sets every tensor of `path` that the schema knows; returns how many were set
 int load_safetensors(Model& m, const char* path);
 

@@ -9,7 +9,7 @@
     model.forward_logits(&x)          birefnet.rs:412     model.forward_logits(x)    x: float32 [B,3,H,W]
     model.forward(&x) / Module        birefnet.rs:466     model.forward(x) / model(x)
     model.backbone.forward(&x)        swin.rs:768         model.backbone_forward(x) -> 4 NCHW maps
-    DeformableConv2d::forward         deform_conv.rs:82   ops.deform_conv2d(...)
+    DeformableConv2d::new / forward   deform_conv.rs:29   ops.DeformableConv2d(in, out, k, stride, padding, vb)(x)
 
 Inputs/outputs are host numpy arrays (copied inside the C call) or torch CUDA tensors (zero-copy device pointers).
 All arithmetic happens in libbirefnet_b200.so; this file only marshals pointers.

@@ -52,16 +52,62 @@ def conv2d(x, weight, bias=None, act: int = 0, precision: str = "bf16", device: 
     return out
 
 
-def deform_conv2d(x, offset, mask, weight, bias=None, precision: str = "bf16", device: int = 0) -> np.ndarray:
-    """DeformableConv2d / DeformConvASPP Metal math (src/deform_conv.rs:102-215, src/aspp.rs:58-165); stride 1."""
+def deform_conv2d(x, offset, mask, weight, bias=None, stride: int = 1, padding: int = None, precision: str = "bf16",
+                  device: int = 0) -> np.ndarray:
+    """DeformableConv2d / DeformConvASPP Metal math (src/deform_conv.rs:102-215, src/aspp.rs:58-165) ==
+    torchvision.ops.deform_conv2d(x, offset, weight, bias, stride, padding, mask=mask)."""
     x, offset, mask, weight, bias = _f32(x), _f32(offset), _f32(mask), _f32(weight), _f32(bias)
     B, Cin, H, W = x.shape
     O, _, k, _ = weight.shape
-    assert offset.shape == (B, 2 * k * k, H, W) and mask.shape == (B, k * k, H, W)
-    out = np.empty((B, O, H, W), dtype=np.float32)
+    if padding is None:
+        padding = k // 2
+    Ho, Wo = (H + 2 * padding - k) // stride + 1, (W + 2 * padding - k) // stride + 1
+    assert offset.shape == (B, 2 * k * k, Ho, Wo) and mask.shape == (B, k * k, Ho, Wo)
+    out = np.empty((B, O, Ho, Wo), dtype=np.float32)
     check(lib().brn_deform_conv2d(device, _PREC[precision], _p(x), _p(offset), _p(mask), _p(weight), _p(bias), B, Cin,
-                                  H, W, O, k, _p(out)))
+                                  H, W, O, k, stride, padding, _p(out)))
     return out
+
+
+class DeformableConv2d:
+    """DeformableConv2d (src/deform_conv.rs:16-99; crate root export src/lib.rs:13): `new(in, out, k, stride, padding, vb)`
+    with vb keys offset_conv.{weight,bias}, modulator_conv.{weight,bias}, regular_conv.{weight,bias}; `forward(x)`."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int, stride: int, padding: int, vb,
+                 precision: str = "fp16", deform_mode: str = "deformable", device: int = 0):
+        k = kernel_size
+        shapes = {"offset_conv.weight": (2 * k * k, in_channels, k, k), "offset_conv.bias": (2 * k * k,),
+                  "modulator_conv.weight": (k * k, in_channels, k, k), "modulator_conv.bias": (k * k,),
+                  "regular_conv.weight": (out_channels, in_channels, k, k), "regular_conv.bias": (out_channels,)}
+        self.w = {}
+        for key, shp in shapes.items():
+            if key not in vb:
+                raise _lib.BrnError(3, f"cannot find tensor {key}")          # candle: vb.get fails inside new()
+            a = _f32(vb[key])
+            if a.shape != shp:
+                raise _lib.BrnError(5, f"shape mismatch for {key}: {a.shape} != {shp}")
+            self.w[key] = a
+        self.cin, self.cout, self.k, self.stride, self.padding = in_channels, out_channels, k, stride, padding
+        self.precision, self.deform_mode, self.device = precision, deform_mode, device
+
+    def forward(self, x) -> np.ndarray:
+        x = _f32(x)
+        B, Cin, H, W = x.shape
+        if Cin != self.cin:
+            raise _lib.BrnError(5, f"expected {self.cin} input channels, got {Cin}")
+        k, s, p = self.k, self.stride, self.padding
+        Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        out = np.empty((B, self.cout, Ho, Wo), dtype=np.float32)
+        w = self.w
+        mode = {"cpu_fallback": _lib.DEFORM_CPU_FALLBACK, "deformable": _lib.DEFORM_DEFORMABLE}[self.deform_mode]
+        check(lib().brn_deformable_conv2d(self.device, _PREC[self.precision], mode, _p(x), B, Cin, H, W,
+                                          _p(w["offset_conv.weight"]), _p(w["offset_conv.bias"]),
+                                          _p(w["modulator_conv.weight"]), _p(w["modulator_conv.bias"]),
+                                          _p(w["regular_conv.weight"]), _p(w["regular_conv.bias"]), self.cout, k, s, p,
+                                          _p(out)))
+        return out
+
+    __call__ = forward
 
 
 def window_attention(qkv, bias, hp: int, wp: int, shift: int, precision: str = "bf16", device: int = 0) -> np.ndarray:

@@ -47,3 +47,80 @@ def forward_sharded(forward: Callable[[np.ndarray], np.ndarray], x: np.ndarray, 
     if rank != 0:
         return None
     return np.concatenate(parts, axis=0)
+
+
+class ShardedBiRefNet:
+    """One process, several GPUs: `brn_sharded_*` of the C ABI (one model handle + one host thread per GPU, contiguous
+    image split, weights replicated, no collective).  Mirrors BiRefNet.new / forward_logits / forward on host arrays."""
+
+    def __init__(self, config, vb, devices):
+        import ctypes as C
+        from . import _lib
+        from .model import BiRefNet, _DEF, _PREC
+        L = _lib.lib()
+        c = _lib.BrnConfig()
+        c.embed_dim = config.swin.embed_dim
+        for i in range(4):
+            c.depths[i] = config.swin.depths[i]
+            c.num_heads[i] = config.swin.num_heads[i]
+        c.window_size, c.mlp_ratio, c.patch_size = config.swin.window_size, config.swin.mlp_ratio, config.swin.patch_size
+        c.precision, c.deform_mode, c.micro_batch = _PREC[config.precision], _DEF[config.deform_mode], config.micro_batch
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        _lib.check(L.brn_sharded_create(C.byref(c), devs, len(devices), C.byref(h)))
+        self._h, self.config, self.devices = h, config, list(devices)
+        try:
+            if isinstance(vb, str):
+                n = C.c_int32(0)
+                _lib.check(L.brn_sharded_load_safetensors(h, vb.encode(), C.byref(n)))
+            else:
+                probe = BiRefNet._create(config, devices[0])
+                try:
+                    keys = probe.tensor_keys()
+                finally:
+                    probe.close()
+                for key in keys:
+                    if key not in vb:
+                        raise _lib.BrnError(3, f"cannot find tensor {key}")
+                    a = np.ascontiguousarray(vb[key], dtype=np.float32)
+                    shape = (C.c_int64 * a.ndim)(*a.shape)
+                    _lib.check(L.brn_sharded_set_tensor(h, key.encode(), a.ctypes.data_as(C.c_void_p), _lib.F32, shape, a.ndim))
+            _lib.check(L.brn_sharded_finalize(h))
+        except Exception:
+            L.brn_sharded_destroy(h)
+            self._h = None
+            raise
+
+    def _run(self, fn, x, out=None):
+        import ctypes as C
+        from . import _lib
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 4 or x.shape[1] != 3:
+            raise _lib.BrnError(5, f"expected [B,3,H,W], got {x.shape}")
+        B, _, H, W = x.shape
+        if out is None:
+            out = np.empty((B, 1, H, W), dtype=np.float32)
+        _lib.check(fn(self._h, x.ctypes.data_as(C.c_void_p), B, H, W, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def forward_logits(self, x, out=None):
+        from . import _lib
+        return self._run(_lib.lib().brn_sharded_forward_logits, x, out)
+
+    def forward(self, x, out=None):
+        from . import _lib
+        return self._run(_lib.lib().brn_sharded_forward, x, out)
+
+    __call__ = forward
+
+    def close(self):
+        from . import _lib
+        if self._h:
+            _lib.lib().brn_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

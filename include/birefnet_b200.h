@@ -28,6 +28,7 @@
 #ifndef BIREFNET_B200_H
 #define BIREFNET_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__GNUC__)
@@ -160,6 +161,28 @@ BRN_API brn_status brn_decoder_forward(brn_model* m, const float* x, const float
                                const float* x4, int32_t B, int32_t H, int32_t W, int is_device, float* out,
                                void* stream);
 
+/* ---- image sharding inside one process ----------------------------------------------------
+ * The reference is single-device; its forward is independent per image (eval-mode BatchNorm: src/decoder.rs:129,139,
+ * src/aspp.rs:220,316,330), so a batch shards by images with no exchange step.  A brn_sharded owns one model handle
+ * and one host thread per listed GPU (a device may be listed more than once), replicates the weights, splits a batch
+ * into contiguous image ranges (the first B % n shards get one extra image) and runs the shards concurrently; the
+ * caller's HOST buffers are read and written directly by every GPU (use brn_host_alloc for pinned memory).  Results are
+ * bit-identical to a single-handle brn_forward_logits. */
+typedef struct brn_sharded brn_sharded;
+BRN_API brn_status brn_sharded_create(const brn_config* cfg, const int32_t* devices, int32_t n_devices, brn_sharded** out);
+BRN_API brn_status brn_sharded_set_tensor(brn_sharded* s, const char* key, const void* data, int dtype, const int64_t* shape,
+                                  int rank);
+BRN_API brn_status brn_sharded_load_safetensors(brn_sharded* s, const char* path, int32_t* n_loaded);
+BRN_API brn_status brn_sharded_finalize(brn_sharded* s);
+BRN_API int32_t brn_sharded_num_devices(const brn_sharded* s);
+/* x: HOST fp32 [B,3,H,W]; out: HOST fp32 [B,1,H,W] (forward_logits / forward = sigmoid, src/birefnet.rs:412-469). */
+BRN_API brn_status brn_sharded_forward_logits(brn_sharded* s, const float* x, int32_t B, int32_t H, int32_t W, float* out);
+BRN_API brn_status brn_sharded_forward(brn_sharded* s, const float* x, int32_t B, int32_t H, int32_t W, float* out);
+BRN_API void brn_sharded_destroy(brn_sharded* s);
+/* Pinned (page-locked, portable) host memory for input / output buffers; NULL on failure. */
+BRN_API void* brn_host_alloc(size_t bytes);
+BRN_API void brn_host_free(void* p);
+
 /* ---- the steps either side of the path (examples/infer_image.rs) ---------------------------- */
 
 /* examples/infer_image.rs:44-67: `img.resize_exact(W, H, FilterType::Triangle)` + ImageNet normalisation.
@@ -191,12 +214,26 @@ BRN_API brn_status brn_window_attention(int device, int precision, const float* 
                                 int32_t heads, int32_t hp, int32_t wp, int32_t shift, float* out);
 
 /* Modulated deformable conv == call_deformable_im2col + weight matmul (src/aspp.rs:138-164,
- * src/deform_conv.rs:177-214).  x: HOST fp32 NCHW [B,C,H,W]; offset [B,2k^2,H,W] (dy,dx interleaved per tap),
- * mask [B,k^2,H,W], weight [O,C,k,k], bias [O] or NULL; stride 1, padding k/2, dilation 1, one offset group.
- * out: HOST fp32 NCHW [B,O,H,W]. */
+ * src/deform_conv.rs:177-214), torchvision `deform_conv2d(x, offset, weight, bias, stride, padding, dilation=1, mask)`
+ * semantics.  x: HOST fp32 NCHW [B,C,H,W]; with Ho = (H + 2 padding - k) / stride + 1: offset [B,2k^2,Ho,Wo] (dy,dx
+ * interleaved per tap), mask [B,k^2,Ho,Wo], weight [O,C,k,k], bias [O] or NULL; dilation 1, one offset group.
+ * out: HOST fp32 NCHW [B,O,Ho,Wo].  The tcgen05 kernel serves stride 1, padding k/2, C = 64 (the ASPP shapes); any other
+ * geometry runs on the SIMT fp32 kernel. */
 BRN_API brn_status brn_deform_conv2d(int device, int precision, const float* x, const float* offset, const float* mask,
                              const float* weight, const float* bias, int32_t B, int32_t C, int32_t H, int32_t W,
-                             int32_t O, int32_t k, float* out);
+                             int32_t O, int32_t k, int32_t stride, int32_t padding, float* out);
+
+/* DeformableConv2d::new(in, out, k, stride, padding, vb) + forward (src/deform_conv.rs:29-99), exported by the crate
+ * root (src/lib.rs:13): the module owns offset_conv [2k^2,C,k,k], modulator_conv [k^2,C,k,k] and regular_conv
+ * [O,C,k,k], all with bias and the same stride / padding.  forward: offset = offset_conv(x); modulator =
+ * 2 sigmoid(modulator_conv(x)) (:83-86); deform_mode DEFORMABLE = the Metal path (:102-215), CPU_FALLBACK =
+ * regular_conv(x), what candle computes on Device::Cpu (:95-98).  All HOST fp32; out [B,O,Ho,Wo]; regular_b may be
+ * NULL. */
+BRN_API brn_status brn_deformable_conv2d(int device, int precision, int deform_mode, const float* x, int32_t B, int32_t C,
+                                 int32_t H, int32_t W, const float* offset_w, const float* offset_b,
+                                 const float* modulator_w, const float* modulator_b, const float* regular_w,
+                                 const float* regular_b, int32_t O, int32_t k, int32_t stride, int32_t padding,
+                                 float* out);
 
 /* D[M,N] = act(A[M,K] W[N,K]^T + bias[N]) (+ residual[M,N]); candle_nn::linear (src/swin.rs:98-107,130-131).
  * act: 0 none, 1 relu, 2 exact-erf gelu.  All HOST fp32 row-major. */

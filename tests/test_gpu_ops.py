@@ -207,3 +207,57 @@ def test_infer_rgb8_end_to_end(mini_cfg, mini_weights_B):
         assert np.array_equal(got, exp)
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("k,stride,padding", [(3, 1, 1), (3, 2, 1), (3, 2, 0), (5, 1, 2), (1, 1, 0), (7, 3, 2)])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_deform_conv2d_stride_padding_bias(k, stride, padding, precision):
+    """The operator at the geometry the reference's module allows (src/deform_conv.rs:29-46: any kernel / stride /
+    padding, bias), against torchvision.  C = 32 and non-"same" geometries take the SIMT kernel in every precision."""
+    import torchvision
+    rng = np.random.default_rng(k * 100 + stride * 10 + padding)
+    B, C, H, W, O = 2, 32, 19, 23, 40
+    Ho, Wo = (H + 2 * padding - k) // stride + 1, (W + 2 * padding - k) // stride + 1
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = (rng.standard_normal((O, C, k, k)) / np.sqrt(C * k * k)).astype(np.float32)
+    b = rng.standard_normal(O).astype(np.float32)
+    off = (rng.standard_normal((B, 2 * k * k, Ho, Wo)) * 1.5).astype(np.float32)
+    msk = rng.uniform(0, 2, (B, k * k, Ho, Wo)).astype(np.float32)
+    got = cb.ops.deform_conv2d(x, off, msk, w, b, stride=stride, padding=padding, precision=precision)
+    xx = r16(x, precision)
+    exp = torchvision.ops.deform_conv2d(torch.from_numpy(xx).double(), torch.from_numpy(off).double(),
+                                        torch.from_numpy(w).double(), torch.from_numpy(b).double(), stride=stride,
+                                        padding=padding, mask=torch.from_numpy(msk).double()).numpy()
+    assert got.shape == exp.shape
+    assert relerr(got, exp) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,padding", [(64, 256, 3, 1, 1), (64, 256, 7, 1, 3), (16, 24, 3, 2, 1), (8, 8, 5, 1, 0)])
+@pytest.mark.parametrize("mode", ["deformable", "cpu_fallback"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_deformable_conv2d_module(cin, cout, k, stride, padding, mode, precision):
+    """DeformableConv2d::new + forward (src/deform_conv.rs:29-99) against the oracle's restatement, both device
+    behaviours (Metal path / candle-CPU fallback).  The (64 -> 256, same padding) cases run the tcgen05 kernels."""
+    rng = np.random.default_rng(cin + cout + k + stride)
+    B, H, W = 2, 24, 32
+    vb = {"offset_conv.weight": (rng.standard_normal((2 * k * k, cin, k, k)) * 0.5 / np.sqrt(cin * k * k)),
+          "offset_conv.bias": rng.standard_normal(2 * k * k) * 0.5,
+          "modulator_conv.weight": rng.standard_normal((k * k, cin, k, k)) / np.sqrt(cin * k * k),
+          "modulator_conv.bias": rng.standard_normal(k * k) * 0.1,
+          "regular_conv.weight": rng.standard_normal((cout, cin, k, k)) / np.sqrt(cin * k * k),
+          "regular_conv.bias": rng.standard_normal(cout)}
+    vb = {n: v.astype(np.float32) for n, v in vb.items()}
+    x = rng.standard_normal((B, cin, H, W)).astype(np.float32)
+    m = cb.DeformableConv2d(cin, cout, k, stride, padding, vb, precision=precision, deform_mode=mode)
+    got = m(x)
+    wt = {"m." + n: torch.from_numpy(v).double() for n, v in vb.items()}
+    exp = R.deformable_conv2d(torch.from_numpy(x).double(), wt, "m", k, stride, padding, mode).numpy()
+    assert got.shape == exp.shape
+    tc = precision == "fp16" and cin == 64 and stride == 1 and padding == k // 2
+    # fp16 tensor-core path: offsets come from an fp16-operand conv (sampling positions move by ~1e-3 px) and the
+    # sampled values are rounded to fp16; the SIMT path is fp32 arithmetic (on fp16-rounded x when precision = fp16)
+    tol = 1e-2 if tc else (2e-3 if precision == "fp16" else 1e-4)
+    assert relerr(got, exp) < tol, relerr(got, exp)
+    with pytest.raises(cb.BrnError) as e:
+        cb.DeformableConv2d(cin, cout, k, stride, padding, {n: v for n, v in vb.items() if n != "regular_conv.bias"})
+    assert e.value.status == 3
