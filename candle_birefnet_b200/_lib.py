@@ -55,6 +55,9 @@ def lib() -> C.CDLL:
     L.brn_config_swin_l.restype = None
     L.brn_config_swin_b.argtypes = [C.POINTER(BrnConfig)]
     L.brn_config_swin_b.restype = None
+    for name in ("brn_config_swin_t", "brn_config_swin_s"):
+        getattr(L, name).argtypes = [C.POINTER(BrnConfig)]
+        getattr(L, name).restype = None
     L.brn_model_create.argtypes = [C.POINTER(BrnConfig), C.c_int, C.POINTER(vp)]
     L.brn_model_destroy.argtypes = [vp]
     L.brn_model_destroy.restype = None
@@ -71,7 +74,7 @@ def lib() -> C.CDLL:
     L.brn_backbone_forward.argtypes = [vp, vp, i32, i32, i32, C.c_int, C.POINTER(vp), C.c_int, vp]
     L.brn_features_forward.argtypes = [vp, vp, i32, i32, i32, C.c_int, C.POINTER(vp), C.c_int, vp]
     L.brn_decoder_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_int, vp, vp]
-    L.brn_window_attention.argtypes = [C.c_int, C.c_int, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.brn_window_attention.argtypes = [C.c_int, C.c_int, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.brn_deform_conv2d.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     L.brn_deformable_conv2d.argtypes = [C.c_int, C.c_int, C.c_int, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32,
                                         i32, vp]

@@ -61,6 +61,21 @@ void brn_config_swin_b(brn_config* cfg) {
   for (int i = 0; i < 4; ++i) cfg->num_heads[i] = h[i];
 }
 
+// SwinConfig::swin_t / swin_s (src/swin.rs:27-52): embed 96, heads 3/6/12/24, window 7 (49-token windows)
+void brn_config_swin_t(brn_config* cfg) {
+  if (!cfg) return;
+  brn_config_swin_l(cfg);
+  cfg->embed_dim = 96;
+  const int d[4] = {2, 2, 6, 2}, h[4] = {3, 6, 12, 24};
+  for (int i = 0; i < 4; ++i) { cfg->depths[i] = d[i]; cfg->num_heads[i] = h[i]; }
+  cfg->window_size = 7;
+}
+void brn_config_swin_s(brn_config* cfg) {
+  if (!cfg) return;
+  brn_config_swin_t(cfg);
+  cfg->depths[2] = 18;
+}
+
 brn_status brn_model_create(const brn_config* cfg, int device, brn_model** out) {
   return guard([&] {
     BRN_CHECK(cfg && out, 1, "brn_model_create: null argument");
@@ -437,17 +452,20 @@ brn_status brn_deformable_conv2d(int device, int precision, int deform_mode, con
 }
 
 brn_status brn_window_attention(int device, int precision, const float* qkv, const float* bias, int32_t n_windows,
-                                int32_t heads, int32_t hp, int32_t wp, int32_t shift, float* out) {
+                                int32_t heads, int32_t window_size, int32_t hp, int32_t wp, int32_t shift, float* out) {
   return guard([&] {
     BRN_CHECK(qkv && bias && out && n_windows > 0 && heads > 0, 1, "brn_window_attention: bad argument");
-    BRN_CHECK(hp % 12 == 0 && wp % 12 == 0 && (shift == 0 || shift == 6), 5, "hp, wp must be multiples of 12; shift 0|6");
-    const int nw = (hp / 12) * (wp / 12);
-    BRN_CHECK(n_windows % nw == 0, 5, "n_windows must be a multiple of (hp/12)*(wp/12)");
+    const int ws = window_size, wn = ws * ws;
+    BRN_CHECK(ws == 12 || ws == 7, 7, "window_size must be 12 or 7");
+    BRN_CHECK(hp % ws == 0 && wp % ws == 0 && (shift == 0 || shift == ws / 2), 5,
+              "hp, wp must be multiples of window_size; shift 0 | window_size / 2");
+    const int nw = (hp / ws) * (wp / ws);
+    BRN_CHECK(n_windows % nw == 0, 5, "n_windows must be a multiple of (hp/ws)*(wp/ws)");
     Scratch s(device);
     LaunchCtx ctx = make_ctx(s, precision);
     const int AD = precision == BRN_PREC_FP16 ? F16 : precision == BRN_PREC_BF16 ? BF16 : F32;
     const int C = heads * 32;
-    const size_t rows = (size_t)n_windows * 144;
+    const size_t rows = (size_t)n_windows * wn;
     // fold the q scale the way finalize does (src/swin.rs:278)
     std::vector<float> hq(qkv, qkv + rows * 3 * C);
     const float sc = 0.17677669529663687f;
@@ -456,14 +474,14 @@ brn_status brn_window_attention(int device, int precision, const float* qkv, con
     View q32 = make_view(s.put(hq.data(), hq.size()), F32, 1, 1, (int)rows, 3 * C);
     View qx = q32;
     if (AD != F32) { qx = make_view(s.alloc(rows * 3 * C * 2), AD, 1, 1, (int)rows, 3 * C); glue_copy_cast(ctx, q32, qx); }
-    float* b32 = s.put(bias, (size_t)heads * 144 * 144);
+    float* b32 = s.put(bias, (size_t)heads * wn * wn);
     // padded fp32 copy [heads][144][148] for the tcgen05 kernel
-    std::vector<float> padded((size_t)heads * 144 * 148, 0.f);
-    for (size_t r = 0; r < (size_t)heads * 144; ++r) memcpy(&padded[r * 148], &bias[r * 144], 144 * 4);
+    std::vector<float> padded((size_t)heads * wn * (wn + 4), 0.f);
+    for (size_t r = 0; r < (size_t)heads * wn; ++r) memcpy(&padded[r * (wn + 4)], &bias[r * wn], (size_t)wn * 4);
     float* b32p = s.put(padded.data(), padded.size());
     View o = make_view(s.alloc(rows * C * dsize(AD)), AD, 1, 1, (int)rows, C);
     AttnArgs a; a.qkv = qx; a.bias32 = b32; a.bias32p = b32p; a.n_windows = n_windows;
-    a.heads = heads; a.nwh = hp / 12; a.nww = wp / 12; a.shift = shift; a.out = o;
+    a.heads = heads; a.nwh = hp / ws; a.nww = wp / ws; a.shift = shift; a.ws = ws; a.out = o;
     op_attention(ctx, a);
     View o32 = o;
     if (AD != F32) { o32 = make_view(s.alloc(rows * C * 4), F32, 1, 1, (int)rows, C); glue_copy_cast(ctx, o, o32); }

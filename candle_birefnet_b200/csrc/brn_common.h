@@ -98,6 +98,7 @@ struct RowMap {
                                  // 2: token row -> window-ordered padded row (qkv computed in token order and scattered
                                  //    into the layout the attention kernel loads; pad rows are never written)
   int h = 0, w = 0, hp = 0, wp = 0, shift = 0;
+  int ws = 12;                   // window side (12: swin_b / swin_l, 7: swin_t / swin_s)
   long long split = 0;           // 0: single segment
   int h2 = 0, w2 = 0, hp2 = 0, wp2 = 0;
   long long tok2 = 0;
@@ -165,6 +166,7 @@ struct AttnArgs {
   int heads = 0;
   int nwh = 0, nww = 0;   // windows per image along h / w
   int shift = 0;          // 0: no mask at all (src/swin.rs:383)
+  int ws = 12;            // window side; the tcgen05 kernel is built for 12 (144-token windows), 7 runs on the SIMT kernel
   int split_win = 0;      // > 0: windows [split_win, n_windows) belong to a second grid with nwh2 x nww2 windows per image
   int nwh2 = 0, nww2 = 0;
   // Token geometry (tcgen05 kernel).  h > 0: rows of a window that fall into the pad region of the [h, w] token grid
@@ -240,6 +242,7 @@ struct LnArgs {
   View out;                // destination rows
   int mode = LN_PLAIN;
   int hp = 0, wp = 0, shift = 0;  // LN_WINDOW
+  int ws = 12;                    // LN_WINDOW: window side
   // LN_WINDOW over two grids in one launch: output rows >= split gather from a second [B,h2,w2,C] grid whose tokens
   // start at row tok2 of x (the merged full + half resolution backbone pass)
   long long split = 0, tok2 = 0;

@@ -28,15 +28,16 @@ struct FastDiv {
 // un-shifted, un-padded [B,h,w] grid, or -1 for a pad position.  Inverse of pad -> roll(-shift) -> partition
 // (src/swin.rs:359-380) == window_reverse -> roll(+shift) -> crop (src/swin.rs:387-401).
 __host__ __device__ __forceinline__ long long window_row_to_token(long long m, int h, int w, int hp, int wp,
-                                                                  int shift) {
-  const int nww = wp / 12;
-  const int nw = (hp / 12) * nww;
-  const long long b = m / ((long long)nw * 144);
-  const int rem = (int)(m - b * (long long)nw * 144);
-  const int wid = rem / 144, t = rem - wid * 144;
+                                                                  int shift, int ws = 12) {
+  const int n = ws * ws;
+  const int nww = wp / ws;
+  const int nw = (hp / ws) * nww;
+  const long long b = m / ((long long)nw * n);
+  const int rem = (int)(m - b * (long long)nw * n);
+  const int wid = rem / n, t = rem - wid * n;
   const int wi = wid / nww, wj = wid - wi * nww;
-  const int ti = t / 12, tj = t - ti * 12;
-  int r = wi * 12 + ti + shift, c = wj * 12 + tj + shift;
+  const int ti = t / ws, tj = t - ti * ws;
+  int r = wi * ws + ti + shift, c = wj * ws + tj + shift;
   if (r >= hp) r -= hp;
   if (c >= wp) c -= wp;
   if (r >= h || c >= w) return -1;
@@ -45,10 +46,10 @@ __host__ __device__ __forceinline__ long long window_row_to_token(long long m, i
 
 __host__ __device__ __forceinline__ long long rowmap_token(const RowMap& rm, long long m) {
   if (rm.split > 0 && m >= rm.split) {
-    const long long t = window_row_to_token(m - rm.split, rm.h2, rm.w2, rm.hp2, rm.wp2, rm.shift);
+    const long long t = window_row_to_token(m - rm.split, rm.h2, rm.w2, rm.hp2, rm.wp2, rm.shift, rm.ws);
     return t < 0 ? t : t + rm.tok2;
   }
-  return window_row_to_token(m, rm.h, rm.w, rm.hp, rm.wp, rm.shift);
+  return window_row_to_token(m, rm.h, rm.w, rm.hp, rm.wp, rm.shift, rm.ws);
 }
 
 // element load / store by runtime dtype tag (F32 / BF16 / F16)

@@ -48,6 +48,7 @@ struct TcGemmP {
   long long rows_total; //   of split ks go to out rows [ks*rows_total, ...); a reduce kernel adds bias / activation
   int tg;        // 3x3 tap groups: one A load of (16+2) x 8 pixels serves the three vertical taps of a kernel column
   int out_tiled; // fp32 out is [m_tile][N][128]
+  int tma_store; // 16-bit row-major token-matrix output without residual / row map: the epilogue stores through tmO
   EpiP epi;
   RowMap rm;
   FastDiv fd_nt, fd_tpi, fd_tx;        // n_tiles, tiles_x * tiles_y, tiles_x
@@ -59,13 +60,14 @@ struct TcGemmP {
 
 // rowmap_token (device_utils.cuh) with the run-time divisions replaced; rows < 2^31
 __device__ __forceinline__ long long window_row_to_token_fd(uint32_t m, int h, int w, int hp, int wp, int shift,
-                                                           const FastDiv& rows, const FastDiv& nww) {
+                                                           const FastDiv& rows, const FastDiv& nww, uint32_t ws) {
   const uint32_t b = rows.div(m);
   const uint32_t rem = m - b * rows.d;
-  const uint32_t wid = rem / 144u, t = rem - wid * 144u;
+  uint32_t wid, t, ti, tj;
+  if (ws == 12u) { wid = rem / 144u; t = rem - wid * 144u; ti = t / 12u; tj = t - ti * 12u; }     // constant divisors
+  else { wid = rem / (ws * ws); t = rem - wid * ws * ws; ti = t / ws; tj = t - ti * ws; }
   const uint32_t wi = nww.div(wid), wj = wid - wi * nww.d;
-  const uint32_t ti = t / 12u, tj = t - ti * 12u;
-  int r = (int)(wi * 12u + ti) + shift, c = (int)(wj * 12u + tj) + shift;
+  int r = (int)(wi * ws + ti) + shift, c = (int)(wj * ws + tj) + shift;
   if (r >= hp) r -= hp;
   if (c >= wp) c -= wp;
   if (r >= h || c >= w) return -1;
@@ -95,10 +97,10 @@ __device__ __forceinline__ long long rowmap_token_fd(const TcGemmP& p, long long
   }
   if (rm.split > 0 && m >= rm.split) {
     const long long t = window_row_to_token_fd((uint32_t)(m - rm.split), rm.h2, rm.w2, rm.hp2, rm.wp2, rm.shift,
-                                               p.fd_rows2, p.fd_nww2);
+                                               p.fd_rows2, p.fd_nww2, (uint32_t)rm.ws);
     return t < 0 ? t : t + rm.tok2;
   }
-  return window_row_to_token_fd((uint32_t)m, rm.h, rm.w, rm.hp, rm.wp, rm.shift, p.fd_rows1, p.fd_nww1);
+  return window_row_to_token_fd((uint32_t)m, rm.h, rm.w, rm.hp, rm.wp, rm.shift, p.fd_rows1, p.fd_nww1, (uint32_t)rm.ws);
 }
 
 // CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs own M tiles 2j and 2j+1 of the same N tile: each loads
@@ -113,7 +115,8 @@ enum EpiKind { EK_GENERIC = 0, EK_NONE16, EK_RELU16, EK_GELU16, EK_NONE32, EK_SI
 
 template <int CL, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmP p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const TcGemmP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -134,7 +137,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 32 * TC_EPI_WARPS); }
     ptx::fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); }
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); if (p.tma_store) ptx::prefetch_tmap(&tmO); }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
   ptx::tc_fence_before();
   __syncthreads();
@@ -297,7 +300,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
       const uint32_t sbb = sb;
-      if (EPI == EK_NONE16) epi_warp<ACT_NONE, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
+      const int trow0 = m_tile * TC_BM + q * 32;       // TMA-store path: token matrices only (tiles = 128 consecutive rows)
+      if (EPI == EK_NONE16 && p.tma_store)
+        epi_warp<ACT_NONE, false, 0, true, false, false, true>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane, 0.f, 1.f, 0, 0, &tmO, trow0);
+      else if (EPI == EK_GELU16 && p.tma_store)
+        epi_warp<ACT_GELU, false, 0, true, false, false, true>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane, 0.f, 1.f, 0, 0, &tmO, trow0);
+      else if (EPI == EK_LNF_GELU16 && p.tma_store)
+        epi_warp<ACT_GELU, false, 0, true, true, false, true>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane, nmu, rstd,
+                                                              ptx::smem_u32(sCs) + acc * TC_BIAS_LD * 4, 0, &tmO, trow0);
+      else if (EPI == EK_NONE16) epi_warp<ACT_NONE, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
       else if (EPI == EK_RELU16) epi_warp<ACT_RELU, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
       else if (EPI == EK_GELU16) epi_warp<ACT_GELU, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
       else if (EPI == EK_NONE32) epi_warp<ACT_NONE, true, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
@@ -326,6 +337,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_arrive(&tempty[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
+    if ((EPI == EK_NONE16 || EPI == EK_GELU16 || EPI == EK_LNF_GELU16) && p.tma_store && lane == 0)
+      ptx::tma_store_wait_all();           // this warp's bulk stores are performed before the CTA retires
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -522,11 +535,13 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   }
   if (p.rm.enabled) {
     BRN_CHECK((long long)a.x.rows() < (1ll << 31), 5, "tc_gemm: row map needs fewer than 2^31 rows");
-    p.fd_rows1 = FastDiv((uint32_t)((p.rm.hp / 12) * (p.rm.wp / 12) * 144));
-    p.fd_nww1 = FastDiv((uint32_t)(p.rm.wp / 12));
+    const int ws = p.rm.ws;
+    BRN_CHECK(p.rm.enabled != 2 || ws == 12, 7, "tc_gemm: the token -> window scatter is built for 12x12 windows");
+    p.fd_rows1 = FastDiv((uint32_t)((p.rm.hp / ws) * (p.rm.wp / ws) * ws * ws));
+    p.fd_nww1 = FastDiv((uint32_t)(p.rm.wp / ws));
     if (p.rm.split > 0) {
-      p.fd_rows2 = FastDiv((uint32_t)((p.rm.hp2 / 12) * (p.rm.wp2 / 12) * 144));
-      p.fd_nww2 = FastDiv((uint32_t)(p.rm.wp2 / 12));
+      p.fd_rows2 = FastDiv((uint32_t)((p.rm.hp2 / ws) * (p.rm.wp2 / ws) * ws * ws));
+      p.fd_nww2 = FastDiv((uint32_t)(p.rm.wp2 / ws));
     }
   }
   p.in_bf16 = a.x.dt == BF16 ? 1 : 0;
@@ -569,6 +584,19 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
     ek = ek == EK_RES32 ? EK_RES32_EMIT : EK_NONE32_EMIT;
   }
 
+  // TMA store of the staged 16-bit tile: plain row-major token matrices (a tile = 128 consecutive output rows), no
+  // residual, no row map.  BRN_GEMM_TMA_STORE=0 keeps the LDS + STG phase B (A/B testing).
+  static const bool no_ts = [] { const char* v = getenv("BRN_GEMM_TMA_STORE"); return v && v[0] == '0'; }();
+  CUtensorMap tmO = tmA;                 // placeholder when unused (never dereferenced)
+  p.tma_store = 0;
+  if (!no_ts && (ek == EK_NONE16 || ek == EK_GELU16 || ek == EK_LNF_GELU16) && a.x.B == 1 && a.x.H == 1 && !a.rowmap.enabled &&
+      p.epi.vec && a.out.B == 1 && a.out.H == 1 && tw == TC_BM) {
+    uint64_t odims[2] = {(uint64_t)w.N, (uint64_t)a.out.rows()};
+    uint64_t ostr[1] = {(uint64_t)a.out.ld * 2};
+    uint32_t obox[2] = {32, 32};
+    tmO = make_tmap_16(a.out.p, a.out.dt, 2, odims, ostr, obox, CU_TENSOR_MAP_SWIZZLE_64B);
+    p.tma_store = 1;
+  }
   auto launch = [&](auto kern) {
     BRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     const int items = ((p.m_tiles + CL - 1) / CL) * p.n_tiles * p.ksplit;
@@ -581,7 +609,7 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+    BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, p));
   };
 #define TC_EK_CASE(E) case E: if (CL == 2) launch(tc_gemm_kernel<2, E>); else launch(tc_gemm_kernel<1, E>); break
   switch (ek) {

@@ -149,7 +149,8 @@ void simt_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   p.kh = a.w->kh; p.kw = a.w->kw; p.pad = a.pad;
   p.stride = a.stride > 0 ? a.stride : 1;
   p.Ho = (a.x.H + 2 * a.pad - a.w->kh) / p.stride + 1; p.Wo = (a.x.W + 2 * a.pad - a.w->kw) / p.stride + 1;
-  BRN_CHECK(p.Ho > 0 && p.Wo > 0 && (long long)a.x.B * p.Ho * p.Wo == a.out.rows(), 5, "simt_gemm: output grid mismatch");
+  BRN_CHECK(p.Ho > 0 && p.Wo > 0 && (a.rowmap.enabled || (long long)a.x.B * p.Ho * p.Wo == a.out.rows()), 5,
+            "simt_gemm: output grid mismatch");
   p.w = a.w->w32;
   p.bias = a.bias ? a.bias : a.w->bias; p.bias_bstride = a.bias_bstride;
   p.N = a.w->N; p.act = a.act; p.act_from = a.act_from;
@@ -157,7 +158,7 @@ void simt_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   p.out = a.out.p; p.odt = a.out.dt; p.ldo = a.out.ld;
   p.rm = a.rowmap;
   p.om = nullptr; p.ldom = 0; p.deform = 0;
-  p.M = a.out.rows();
+  p.M = (long long)a.x.B * p.Ho * p.Wo;
   launch_simt_gemm(ctx, p);
 }
 
@@ -191,37 +192,40 @@ struct SimtAttnP {
   void* out; int odt; int ldo;
 };
 
+template <int WS>
 __global__ void __launch_bounds__(160) simt_attn_kernel(SimtAttnP p) {
-  __shared__ float Ks[144][33];
-  __shared__ float Vs[144][33];
+  constexpr int N = WS * WS;                  // tokens per window: 144 (swin_b / swin_l) or 49 (swin_t / swin_s)
+  constexpr int HALF = WS - WS / 2;           // first local row / column of the shifted-in region (src/swin.rs:608-629)
+  __shared__ float Ks[N][33];
+  __shared__ float Vs[N][33];
   const int win = blockIdx.x, head = blockIdx.y;
   const int tid = threadIdx.x;
-  const long long row0 = (long long)win * 144;
-  for (int i = tid; i < 144 * 32; i += blockDim.x) {
+  const long long row0 = (long long)win * N;
+  for (int i = tid; i < N * 32; i += blockDim.x) {
     int r = i / 32, d = i % 32;
     Ks[r][d] = ld_act(p.qkv, p.dt, (row0 + r) * p.ldq + p.C + head * 32 + d);
     Vs[r][d] = ld_act(p.qkv, p.dt, (row0 + r) * p.ldq + 2 * p.C + head * 32 + d);
   }
   __syncthreads();
-  if (tid >= 144) return;
+  if (tid >= N) return;
   float q[32];
 #pragma unroll
   for (int d = 0; d < 32; ++d) q[d] = ld_act(p.qkv, p.dt, (row0 + tid) * p.ldq + head * 32 + d);
   const int nw = p.nwh * p.nww;
   const int wi = (win % nw) / p.nww, wj = (win % nw) % p.nww;
   const bool last_r = p.shift > 0 && wi == p.nwh - 1, last_c = p.shift > 0 && wj == p.nww - 1;
-  const int qi = tid / 12, qj = tid % 12;
-  const float* brow = p.bias + ((long long)head * 144 + tid) * 144;
+  const int qi = tid / WS, qj = tid % WS;
+  const float* brow = p.bias + ((long long)head * N + tid) * N;
   float mx = -INFINITY, sum = 0.f, o[32];
 #pragma unroll
   for (int d = 0; d < 32; ++d) o[d] = 0.f;
-  for (int k = 0; k < 144; ++k) {
+  for (int k = 0; k < N; ++k) {
     float s = 0.f;
 #pragma unroll
     for (int d = 0; d < 32; ++d) s = fmaf(q[d], Ks[k][d], s);
     s += brow[k];
-    int ki = k / 12, kj = k % 12;
-    if ((last_r && ((ki >= 6) != (qi >= 6))) || (last_c && ((kj >= 6) != (qj >= 6)))) s += -100.0f;
+    int ki = k / WS, kj = k % WS;
+    if ((last_r && ((ki >= HALF) != (qi >= HALF))) || (last_c && ((kj >= HALF) != (qj >= HALF)))) s += -100.0f;
     float nm = fmaxf(mx, s);
     float corr = __expf(mx - nm), e = __expf(s - nm);
     sum = sum * corr + e;
@@ -243,8 +247,12 @@ void simt_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   p.bias = a.bias32; p.heads = a.heads; p.nwh = a.nwh; p.nww = a.nww; p.shift = a.shift;
   p.out = a.out.p; p.odt = a.out.dt; p.ldo = a.out.ld;
   dim3 grid(a.n_windows, a.heads);
-  KScope ks(ctx, KC_ATTN_SIMT, 4.0 * 144 * 144 * 32 * (double)a.n_windows * a.heads);
-  simt_attn_kernel<<<grid, 160, 0, ctx.stream>>>(p);
+  BRN_CHECK(a.ws == 12 || a.ws == 7, 7, "simt_attention: window side must be 7 or 12");
+  BRN_CHECK(!a.token_out, 7, "simt_attention: token-order output is a tensor-core-path feature");
+  const double n = (double)a.ws * a.ws;
+  KScope ks(ctx, KC_ATTN_SIMT, 4.0 * n * n * 32 * (double)a.n_windows * a.heads);
+  if (a.ws == 12) simt_attn_kernel<12><<<grid, 160, 0, ctx.stream>>>(p);
+  else simt_attn_kernel<7><<<grid, 160, 0, ctx.stream>>>(p);
   BRN_CUDA(cudaGetLastError());
 }
 

@@ -17,7 +17,7 @@ struct LnP {
   const void* x; int xdt; int ldx; int B, h, w, C;
   const float* gamma; const float* beta;
   void* out; int odt; int ldo;
-  int mode, hp, wp, shift;
+  int mode, hp, wp, shift, ws;
   long long rows;
   // LN_WINDOW over two token grids in one launch (merged two-resolution pass): window rows >= split belong to grid 2
   long long split, tok2;
@@ -26,10 +26,10 @@ struct LnP {
 
 __device__ __forceinline__ long long ln_window_token(const LnP& p, long long m) {
   if (p.split > 0 && m >= p.split) {
-    const long long t = window_row_to_token(m - p.split, p.h2, p.w2, p.hp2, p.wp2, p.shift);
+    const long long t = window_row_to_token(m - p.split, p.h2, p.w2, p.hp2, p.wp2, p.shift, p.ws);
     return t < 0 ? t : t + p.tok2;
   }
-  return window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift);
+  return window_row_to_token(m, p.h, p.w, p.hp, p.wp, p.shift, p.ws);
 }
 
 __device__ __forceinline__ void ln_store4(void* out, int odt, long long idx, float4 v) {
@@ -357,7 +357,7 @@ void glue_layernorm(const LaunchCtx& ctx, const LnArgs& a) {
   p.x = a.x.p; p.xdt = a.x.dt; p.ldx = a.x.ld; p.B = a.x.B; p.h = a.x.H; p.w = a.x.W; p.C = a.x.C;
   p.gamma = a.gamma; p.beta = a.beta;
   p.out = a.out.p; p.odt = a.out.dt; p.ldo = a.out.ld;
-  p.mode = a.mode; p.hp = a.hp; p.wp = a.wp; p.shift = a.shift;
+  p.mode = a.mode; p.hp = a.hp; p.wp = a.wp; p.shift = a.shift; p.ws = a.ws;
   p.rows = a.out.rows();
   p.split = a.split; p.tok2 = a.tok2; p.h2 = a.h2; p.w2 = a.w2; p.hp2 = a.hp2; p.wp2 = a.wp2;
   const int n = a.mode == LN_MERGE ? 4 * a.x.C : a.x.C;
@@ -373,7 +373,13 @@ void glue_layernorm(const LaunchCtx& ctx, const LnArgs& a) {
   if (vec && !no_bulk && merge_ok && n <= LNB_CHUNK_FLOATS && nv <= 24 && a.x.p != nullptr &&
       !(a.x.p == a.out.p && a.mode == LN_WINDOW)) {
     int R = std::min(32, LNB_CHUNK_FLOATS / n);
-    if (a.mode == LN_WINDOW) { const int cands[6] = {24, 12, 6, 4, 3, 2}; int r = 1; for (int c : cands) if (c <= R) { r = c; break; } R = r; }
+    if (a.mode == LN_WINDOW) {      // chunks of whole window rows (runs of ws contiguous tokens), or divisors of one
+      const int cands12[6] = {24, 12, 6, 4, 3, 2}, cands7[3] = {28, 14, 7};
+      int r = 1;
+      if (a.ws == 12) { for (int c : cands12) if (c <= R) { r = c; break; } }
+      else if (a.ws == 7) { for (int c : cands7) if (c <= R) { r = c; break; } }
+      R = r;
+    }
     const long long n_chunks = (p.rows + R - 1) / R;
     const int smem = LNB_STAGES * LNB_CHUNK_FLOATS * 4 + 2 * n * 4 + 2 * LNB_STAGES * 8 + LNB_STAGES * 32 * 4 + 128;
 #define LNB_LAUNCH(NV, LPR, ODT, EX)                                                                      \

@@ -38,7 +38,8 @@ void op_deform(const LaunchCtx& ctx, const DeformArgs& a) {
   else simt_deform(ctx, a);
 }
 void op_attention(const LaunchCtx& ctx, const AttnArgs& a) {
-  if (ctx.precision != BRN_PREC_FP32 && !ctx.force_simt && (a.qkv.dt == BF16 || a.qkv.dt == F16) && a.out.dt == a.qkv.dt)
+  if (ctx.precision != BRN_PREC_FP32 && !ctx.force_simt && a.ws == 12 && (a.qkv.dt == BF16 || a.qkv.dt == F16) &&
+      a.out.dt == a.qkv.dt)
     tc_attention(ctx, a);
   else simt_attention(ctx, a);
 }
@@ -47,7 +48,7 @@ void op_attention(const LaunchCtx& ctx, const AttnArgs& a) {
 // construction / schema
 // ------------------------------------------------------------------------------------------------
 Model::Model(const brn_config& c, int dev) : cfg(c), device(dev) {
-  BRN_CHECK(c.window_size == 12, 7, "only window_size 12 is supported");
+  BRN_CHECK(c.window_size == 12 || c.window_size == 7, 7, "window_size must be 12 (swin_b / swin_l) or 7 (swin_t / swin_s)");
   BRN_CHECK(c.embed_dim > 0 && c.embed_dim % 32 == 0, 7, "embed_dim must be a multiple of 32");
   for (int i = 0; i < 4; ++i)
     BRN_CHECK(c.num_heads[i] * 32 == (c.embed_dim << i), 7, "head_dim must be 32 at every stage");
@@ -117,7 +118,7 @@ void Model::build_schema() {
       ln(p + ".norm1", Ci);
       lin(p + ".attn.qkv", 3 * Ci, Ci);
       lin(p + ".attn.proj", Ci, Ci);
-      add(p + ".attn.relative_position_bias_table", {23 * 23, cfg.num_heads[i]});
+      add(p + ".attn.relative_position_bias_table", {(2 * cfg.window_size - 1) * (2 * cfg.window_size - 1), cfg.num_heads[i]});
       ln(p + ".norm2", Ci);
       lin(p + ".mlp.fc1", cfg.mlp_ratio * Ci, Ci);
       lin(p + ".mlp.fc2", Ci, cfg.mlp_ratio * Ci);
@@ -372,14 +373,16 @@ void Model::finalize() {
         // WindowAttention::new (src/swin.rs:143-152): bias[h,q,k] = table[index[q,k], h],
         // index[(i,j),(k,l)] = (i-k+11)*23 + (j-l+11)  (src/swin.rs:182-184)
         const HostTensor& tb = T(p + ".attn.relative_position_bias_table");
-        std::vector<float> b32((size_t)heads * 144 * 144), b32p((size_t)heads * 144 * 148, 0.f);
+        // generic window side ws: index = (qi - ki + ws - 1) * (2 ws - 1) + (qj - kj + ws - 1)
+        const int ws = cfg.window_size, n = ws * ws, ldp = n + 4;
+        std::vector<float> b32((size_t)heads * n * n), b32p((size_t)heads * n * ldp, 0.f);
         for (int h = 0; h < heads; ++h)
-          for (int q = 0; q < 144; ++q)
-            for (int k = 0; k < 144; ++k) {
-              int idx = (q / 12 - k / 12 + 11) * 23 + (q % 12 - k % 12 + 11);
+          for (int q = 0; q < n; ++q)
+            for (int k = 0; k < n; ++k) {
+              int idx = (q / ws - k / ws + ws - 1) * (2 * ws - 1) + (q % ws - k % ws + ws - 1);
               float v = tb.data[(size_t)idx * heads + h];
-              b32[((size_t)h * 144 + q) * 144 + k] = v;
-              b32p[((size_t)h * 144 + q) * 148 + k] = v;
+              b32[((size_t)h * n + q) * n + k] = v;
+              b32p[((size_t)h * n + q) * ldp + k] = v;
             }
         B.bias32 = upload(b32);
         B.bias32p = upload(b32p);
@@ -594,13 +597,15 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
     glue_layernorm(ctx, l);
   }
   // LayerNorm folding needs the tcgen05 epilogues (16-column granules: C % 16 == 0 holds for head_dim 32)
-  const bool fold = ctx.precision != BRN_PREC_FP32 && !ctx.force_simt && !env_flag("BRN_LN_UNFUSED");
+  // ... and the tcgen05 attention kernel's pad fix-up / token-order store, which is built for 12x12 windows
+  const int ws = cfg.window_size, wn = ws * ws;
+  const bool fold = ctx.precision != BRN_PREC_FP32 && !ctx.force_simt && ws == 12 && !env_flag("BRN_LN_UNFUSED");
   bool have_stats = false;          // x16 / stats describe the current residual stream
   View next_x16{}; float2* next_stats = nullptr;
   for (int i = 0; i < 4; ++i) {
     const int Ci = C(i), heads = cfg.num_heads[i];
     int hp[2], wp[2]; long long Tp[2] = {0, 0};
-    for (int s = 0; s < nseg; ++s) { hp[s] = (h[s] + 11) / 12 * 12; wp[s] = (w[s] + 11) / 12 * 12; Tp[s] = (long long)B * hp[s] * wp[s]; }
+    for (int s = 0; s < nseg; ++s) { hp[s] = (h[s] + ws - 1) / ws * ws; wp[s] = (w[s] + ws - 1) / ws * ws; Tp[s] = (long long)B * hp[s] * wp[s]; }
     rows_of(h, w, T);
     const long long Tt = T[0] + T[1], Tpt = Tp[0] + Tp[1];
     BRN_CHECK(Tpt < (1ll << 31), 5, "too many tokens for one pass: lower micro_batch");
@@ -634,12 +639,12 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
     auto folded = [&](GemmArgs& g) { g.lnf.mr = mr; g.lnf.C = Ci; };
     for (size_t j = 0; j < stages[i].blocks.size(); ++j) {
       const BlockW& bw = stages[i].blocks[j];
-      const int shift = (j % 2 == 0) ? 0 : 6;          // src/swin.rs:552
+      const int shift = (j % 2 == 0) ? 0 : ws / 2;     // src/swin.rs:548,552
       const size_t mb = arena.mark();
       View qkv = make_view(arena.alloc((size_t)Tpt * 3 * Ci * dsize(AD)), AD, 1, 1, (int)Tpt, 3 * Ci);
       View xw{};
       RowMap wmap;      // window-ordered padded rows <-> token rows of the (merged) grids
-      wmap.h = h[0]; wmap.w = w[0]; wmap.hp = hp[0]; wmap.wp = wp[0]; wmap.shift = shift;
+      wmap.h = h[0]; wmap.w = w[0]; wmap.hp = hp[0]; wmap.wp = wp[0]; wmap.shift = shift; wmap.ws = ws;
       if (nseg > 1) { wmap.split = Tp[0]; wmap.h2 = h[1]; wmap.w2 = w[1]; wmap.hp2 = hp[1]; wmap.wp2 = wp[1]; wmap.tok2 = T[0]; }
       if (fold && have_stats) {
         // norm1 folded: qkv = LN(x) Wqkv^T + b on the raw 16-bit stream, rows scattered to the window layout
@@ -651,7 +656,7 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
         // norm1 -> pad -> roll -> partition (src/swin.rs:355-380) in one gather kernel per grid
         xw = make_view(arena.alloc((size_t)Tpt * Ci * dsize(AD)), AD, 1, 1, (int)Tpt, Ci);
         LnArgs l; l.x = grid_view(0); l.gamma = bw.n1g; l.beta = bw.n1b; l.out = xw;
-        l.mode = LN_WINDOW; l.hp = hp[0]; l.wp = wp[0]; l.shift = shift;
+        l.mode = LN_WINDOW; l.hp = hp[0]; l.wp = wp[0]; l.shift = shift; l.ws = ws;
         if (nseg > 1) { l.split = Tp[0]; l.tok2 = T[0]; l.h2 = h[1]; l.w2 = w[1]; l.hp2 = hp[1]; l.wp2 = wp[1]; }
         glue_layernorm(ctx, l);
         GemmArgs g; g.x = xw; g.w = &bw.qkv; g.out = qkv; op_gemm(ctx, g);
@@ -659,9 +664,9 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
       // attention output: token order on the tensor-core path, window order on the SIMT path
       View ao = fold ? make_view(arena.alloc((size_t)Tt * Ci * dsize(AD)), AD, 1, 1, (int)Tt, Ci)
                      : make_view(xw.p, AD, 1, 1, (int)Tpt, Ci);   // SIMT: reuse the xw buffer (qkv GEMM has consumed it)
-      { AttnArgs a; a.qkv = qkv; a.bias32 = bw.bias32; a.bias32p = bw.bias32p; a.n_windows = (int)(Tpt / 144);
-        a.heads = heads; a.nwh = hp[0] / 12; a.nww = wp[0] / 12; a.shift = shift; a.out = ao;
-        if (nseg > 1) { a.split_win = (int)(Tp[0] / 144); a.nwh2 = hp[1] / 12; a.nww2 = wp[1] / 12; }
+      { AttnArgs a; a.qkv = qkv; a.bias32 = bw.bias32; a.bias32p = bw.bias32p; a.n_windows = (int)(Tpt / wn); a.ws = ws;
+        a.heads = heads; a.nwh = hp[0] / ws; a.nww = wp[0] / ws; a.shift = shift; a.out = ao;
+        if (nseg > 1) { a.split_win = (int)(Tp[0] / wn); a.nwh2 = hp[1] / ws; a.nww2 = wp[1] / ws; }
         if (fold) {
           a.h = h[0]; a.w = w[0]; a.h2 = h[1]; a.w2 = w[1]; a.tok2 = T[0]; a.token_out = 1;
           a.qkv_bias16 = bw.qkv_bias16 + (AD == F16 ? 3 * Ci : 0);
@@ -854,7 +859,8 @@ void Model::run_features(LaunchCtx& ctx, const float* img, int B, int H, int W, 
   const int AD = dec_dtype();
   const int off4 = lat(0) + lat(1) + lat(2);
   View feats[4] = {X[0].slice(0, C(0)), X[1].slice(0, C(1)), X[2].slice(0, C(2)), X4cat.slice(off4, C(3))};
-  const bool merged = cfg.precision != BRN_PREC_FP32 && !ctx.force_simt && !env_flag("BRN_SPLIT_BACKBONE");
+  // (the SIMT attention kernel handles one token grid per launch, so window-7 models run the two passes separately)
+  const bool merged = cfg.precision != BRN_PREC_FP32 && !ctx.force_simt && cfg.window_size == 12 && !env_flag("BRN_SPLIT_BACKBONE");
   {
     const size_t m1 = arena.mark();
     const int H2 = H / 2, W2 = W / 2;

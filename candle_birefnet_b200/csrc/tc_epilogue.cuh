@@ -162,11 +162,17 @@ __device__ __forceinline__ float epi_act(float f, int col, int act_from) {
 //       lane's row (phase A geometry), `scs` = SHARED address of the staged column sums (indexed like sbias).
 // EMIT: (fp32 output only) the stored rows' raw 16-bit copy goes to p.x16 and their (sum, sumsq) over this warp's
 //       columns to p.lne_stats[part_idx * stride + row] (phase-B geometry: the values after the residual add).
-template <int ACT, bool O32, int RM, bool PP = (RM == 0), bool LNF = false, bool EMIT = false>
+// TS  : (16-bit output, no residual, plain row-major token matrix) phase B is ONE TMA store per granule: lane 0 hands
+//       the staged 32 rows x 64 B block (its XOR swizzle is exactly CU_TENSOR_MAP_SWIZZLE_64B) to cp.async.bulk.tensor;
+//       rows / columns past the matrix are clipped by the tensor map, so the granule needs no predicates, no LDS and no
+//       STG.  `tmO` = output tensor map (box 32 elements x 32 rows), `trow0` = output row of this warp's lane 0.
+template <int ACT, bool O32, int RM, bool PP = (RM == 0), bool LNF = false, bool EMIT = false, bool TS = false>
 __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, int c0, int c1, long long orow,
                                          uint32_t sbias, uint32_t stage, int lane, float nmu = 0.f, float rstd = 1.f,
-                                         uint32_t scs = 0, int part_idx = 0) {
+                                         uint32_t scs = 0, int part_idx = 0, const CUtensorMap* tmO = nullptr,
+                                         int trow0 = 0) {
   static_assert(!EMIT || O32, "LnEmit needs the fp32 output path");
+  static_assert(!TS || (!O32 && RM == 0), "TMA store: 16-bit output without residual");
   if (c0 >= c1) {
     if (EMIT) {   // an empty column part still owns a statistics slot: zeros
       if (orow >= 0) p.lne_stats[(long long)part_idx * p.lne_stride + orow] = make_float2(0.f, 0.f);
@@ -286,6 +292,10 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
       for (int j = 0; j < GC; ++j)
         if (j < ncol && n0 + c + j < p.N) f[j] += ld_elem(p.res, p.resdt, orow * p.ldres + n0 + c + j);
     }
+    if (TS) {       // the previous granule's TMA store must have read the staging block before it is overwritten
+      if (lane == 0) ptx::tma_store_wait_read();
+      __syncwarp();
+    }
     if (O32) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -303,6 +313,12 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
         ptx::sts128(my_row + ((k ^ sw_a) << 4),
             make_uint4(pack_f16x2(f[(8 * k) % GC], f[(8 * k + 1) % GC]), pack_f16x2(f[(8 * k + 2) % GC], f[(8 * k + 3) % GC]),
                        pack_f16x2(f[(8 * k + 4) % GC], f[(8 * k + 5) % GC]), pack_f16x2(f[(8 * k + 6) % GC], f[(8 * k + 7) % GC])));
+    }
+    if (TS) {
+      ptx::fence_proxy_async_smem();        // generic-proxy STS -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) { ptx::tma_store_2d(tmO, stage, n0 + c, trow0); ptx::tma_store_commit(); }
+      return;
     }
     __syncwarp();
     // ---- phase B: 8 rows x 64 bytes per instruction ----
@@ -397,6 +413,10 @@ __device__ __forceinline__ void epi_warp(const EpiP& p, uint32_t taddr, int n0, 
         if (c + GC < c1) granule(c + GC, rq1, va, va);
       }
     }
+  }
+  if (TS) {
+    if (lane == 0) ptx::tma_store_wait_read();          // the next tile's first granule reuses the block
+    __syncwarp();
   }
   if (EMIT) {
     // the four lanes of a row (16-byte chunks kb = 0..3) hold its partial sums: fixed-order butterfly, lane kb = 0 writes

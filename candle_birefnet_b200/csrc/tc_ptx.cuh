@@ -125,6 +125,18 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem, const CUtensorMap* m,
       : "memory");
 }
 
+// TMA store: shared (swizzled like the tensor map says) -> global tile; bulk async-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_addr, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(smem_addr),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed groups have finished READING shared memory (the staging block may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed (writes performed)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- clusters ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

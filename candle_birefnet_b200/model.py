@@ -28,7 +28,7 @@ from ._lib import BrnConfig, BrnError, check, lib
 
 @dataclass
 class SwinConfig:
-    """SwinConfig (src/swin.rs:13-23); only window 12 / head_dim 32 variants are supported."""
+    """SwinConfig (src/swin.rs:13-23); head_dim 32, window 12 (swin_b / swin_l) or 7 (swin_t / swin_s)."""
     embed_dim: int = 192
     depths: Tuple[int, int, int, int] = (2, 2, 18, 2)
     num_heads: Tuple[int, int, int, int] = (6, 12, 24, 48)
@@ -44,6 +44,16 @@ class SwinConfig:
     def swin_b() -> "SwinConfig":
         """SwinConfig::swin_b (src/swin.rs:54-66)."""
         return SwinConfig(embed_dim=128, num_heads=(4, 8, 16, 32))
+
+    @staticmethod
+    def swin_t() -> "SwinConfig":
+        """SwinConfig::swin_t (src/swin.rs:27-38): window 7."""
+        return SwinConfig(embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24), window_size=7)
+
+    @staticmethod
+    def swin_s() -> "SwinConfig":
+        """SwinConfig::swin_s (src/swin.rs:41-52): window 7."""
+        return SwinConfig(embed_dim=96, depths=(2, 2, 18, 2), num_heads=(3, 6, 12, 24), window_size=7)
 
 
 @dataclass

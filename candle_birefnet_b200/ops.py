@@ -115,9 +115,10 @@ def window_attention(qkv, bias, hp: int, wp: int, shift: int, precision: str = "
     qkv, bias = _f32(qkv), _f32(bias)
     nwin, n, c3 = qkv.shape
     heads = bias.shape[0]
-    assert n == 144 and c3 == 3 * heads * 32 and bias.shape == (heads, 144, 144)
-    out = np.empty((nwin, 144, heads * 32), dtype=np.float32)
-    check(lib().brn_window_attention(device, _PREC[precision], _p(qkv), _p(bias), nwin, heads, hp, wp, shift, _p(out)))
+    ws = {144: 12, 49: 7}[n]
+    assert c3 == 3 * heads * 32 and bias.shape == (heads, n, n)
+    out = np.empty((nwin, n, heads * 32), dtype=np.float32)
+    check(lib().brn_window_attention(device, _PREC[precision], _p(qkv), _p(bias), nwin, heads, ws, hp, wp, shift, _p(out)))
     return out
 
 

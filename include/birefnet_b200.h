@@ -71,12 +71,12 @@ typedef enum { BRN_PREC_FP32 = 0, BRN_PREC_BF16 = 1, BRN_PREC_FP16 = 2 } brn_pre
 typedef enum { BRN_DEFORM_CPU_FALLBACK = 0, BRN_DEFORM_DEFORMABLE = 1 } brn_deform_mode;
 
 /* Mirror of SwinConfig (src/swin.rs:13-23) + the BiRefNetConfig fields that are read (src/birefnet.rs:13-30).
- * window_size must be 12 and embed_dim/num_heads[0] must be 32. */
+ * window_size must be 12 or 7 and embed_dim/num_heads[0] must be 32. */
 typedef struct {
   int32_t embed_dim;      /* 192 for swin_l                      */
   int32_t depths[4];      /* {2,2,18,2}                          */
   int32_t num_heads[4];   /* {6,12,24,48}                        */
-  int32_t window_size;    /* 12                                  */
+  int32_t window_size;    /* 12 (swin_b / swin_l) or 7 (swin_t/s) */
   int32_t mlp_ratio;      /* 4                                   */
   int32_t patch_size;     /* 4                                   */
   int32_t precision;      /* brn_precision (initial; changeable) */
@@ -89,9 +89,14 @@ BRN_API void brn_config_swin_l(brn_config* cfg);
 
 /* SwinConfig::swin_b() (src/swin.rs:54-66): the other window-12 / head_dim-32 member of the family (embed 128,
  * heads 4/8/16/32).  The reference's BiRefNet::new always builds swin_l (src/birefnet.rs:390-391); the decoder
- * widths follow the backbone's channel counts, so the same path runs at this width.  swin_t/swin_s
- * (window 7) are not supported: brn_model_create rejects window_size != 12. */
+ * widths follow the backbone's channel counts, so the same path runs at this width. */
 BRN_API void brn_config_swin_b(brn_config* cfg);
+
+/* SwinConfig::swin_t() / swin_s() (src/swin.rs:27-52): embed 96, heads 3/6/12/24, depths 2/2/6/2 and 2/2/18/2, window 7
+ * (49-token windows, shift 3).  Window-7 models run LayerNorm, the GEMMs, the decoder and the deformable convs on the
+ * same kernels as swin_l; their attention runs on the SIMT kernel (the tcgen05 attention tile is 144 tokens). */
+BRN_API void brn_config_swin_t(brn_config* cfg);
+BRN_API void brn_config_swin_s(brn_config* cfg);
 
 /* ---- model lifetime: replaces BiRefNet::new(config, vb) (src/birefnet.rs:389-409) ------------------------- */
 
@@ -208,10 +213,12 @@ BRN_API brn_status brn_infer_rgb8(brn_model* m, const uint8_t* rgb, int32_t B, i
  * WindowAttention::forward_standard (src/swin.rs:266-311) == what flash_attention_with_[repeating_]bias replaces
  * (src/swin.rs:243,252; examples/test_flash_bias.rs:30-36).  qkv: HOST fp32 [n_windows,144,3*heads*32] (channel =
  * s*C + head*32 + d, src/swin.rs:218-223), bias: HOST fp32 [heads,144,144]; shift geometry (hp,wp in tokens, shift
- * 0 or 6) selects the analytic -100 mask of create_attention_mask (src/swin.rs:603-655).
- * out: HOST fp32 [n_windows,144,heads*32]. */
+ * 0 or window_size / 2) selects the analytic -100 mask of create_attention_mask (src/swin.rs:603-655).
+ * window_size 12 (144-token windows: the tcgen05 kernel in the 16-bit precisions) or 7 (49 tokens, swin_t / swin_s:
+ * SIMT kernel); with N = window_size^2 the shapes are qkv [n_windows,N,3*heads*32], bias [heads,N,N],
+ * out: HOST fp32 [n_windows,N,heads*32]. */
 BRN_API brn_status brn_window_attention(int device, int precision, const float* qkv, const float* bias, int32_t n_windows,
-                                int32_t heads, int32_t hp, int32_t wp, int32_t shift, float* out);
+                                int32_t heads, int32_t window_size, int32_t hp, int32_t wp, int32_t shift, float* out);
 
 /* Modulated deformable conv == call_deformable_im2col + weight matmul (src/aspp.rs:138-164,
  * src/deform_conv.rs:177-214), torchvision `deform_conv2d(x, offset, weight, bias, stride, padding, dilation=1, mask)`

@@ -46,7 +46,7 @@ MASK_VALUE = -100.0  # src/swin.rs:651
 class Config:
     """Mirror of SwinConfig (src/swin.rs:13-23) + BiRefNetConfig (src/birefnet.rs:13-30).
 
-    Only window 12 / head_dim 32 variants are in scope.  `swin_l()` is the one
+    head_dim 32 variants: window 12 (swin_b, swin_l) and window 7 (swin_t, swin_s).  `swin_l()` is the one
     the reference ever builds (src/birefnet.rs:390-391); `mini()` is a reduced
     width/depth variant of the same architecture used to keep CPU tests fast.
     """
@@ -66,6 +66,19 @@ class Config:
     @staticmethod
     def swin_b() -> "Config":
         return Config(embed_dim=128, num_heads=(4, 8, 16, 32), name="swin_b")
+
+    # src/swin.rs:27-38 and :41-52 (window 7: 49-token windows, shift 3)
+    @staticmethod
+    def swin_t() -> "Config":
+        return Config(embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24), window_size=7, name="swin_t")
+
+    @staticmethod
+    def swin_s() -> "Config":
+        return Config(embed_dim=96, depths=(2, 2, 18, 2), num_heads=(3, 6, 12, 24), window_size=7, name="swin_s")
+
+    @staticmethod
+    def mini7() -> "Config":
+        return Config(embed_dim=64, depths=(2, 2, 2, 2), num_heads=(2, 4, 8, 16), window_size=7, name="mini7")
 
     @staticmethod
     def mini() -> "Config":

@@ -55,6 +55,8 @@ pub struct brn_config {
 extern "C" {
     pub fn brn_config_swin_l(cfg: *mut brn_config);
     pub fn brn_config_swin_b(cfg: *mut brn_config);
+    pub fn brn_config_swin_t(cfg: *mut brn_config);
+    pub fn brn_config_swin_s(cfg: *mut brn_config);
 
     // ---- model lifetime: BiRefNet::new(config, vb) (src/birefnet.rs:389-409)
     pub fn brn_model_create(cfg: *const brn_config, device: c_int, out: *mut *mut brn_model) -> brn_status;
@@ -108,7 +110,7 @@ extern "C" {
 
     // ---- operator level
     pub fn brn_window_attention(device: c_int, precision: c_int, qkv: *const f32, bias: *const f32, n_windows: i32,
-                                heads: i32, hp: i32, wp: i32, shift: i32, out: *mut f32) -> brn_status;
+                                heads: i32, window_size: i32, hp: i32, wp: i32, shift: i32, out: *mut f32) -> brn_status;
     pub fn brn_deform_conv2d(device: c_int, precision: c_int, x: *const f32, offset: *const f32, mask: *const f32,
                              weight: *const f32, bias: *const f32, b: i32, c: i32, h: i32, w: i32, o: i32, k: i32,
                              stride: i32, padding: i32, out: *mut f32) -> brn_status;

@@ -41,6 +41,18 @@ def test_config_swin_b_matches_reference():
     assert R.Config.swin_b().stage_channels() == [128, 256, 512, 1024]
 
 
+def test_config_swin_t_s_match_reference():
+    c = _lib.BrnConfig()
+    cb.lib().brn_config_swin_t(C.byref(c))
+    # SwinConfig::swin_t (src/swin.rs:27-38)
+    assert c.embed_dim == 96 and list(c.depths) == [2, 2, 6, 2] and list(c.num_heads) == [3, 6, 12, 24] and c.window_size == 7
+    cb.lib().brn_config_swin_s(C.byref(c))
+    # SwinConfig::swin_s (src/swin.rs:41-52)
+    assert c.embed_dim == 96 and list(c.depths) == [2, 2, 18, 2] and list(c.num_heads) == [3, 6, 12, 24] and c.window_size == 7
+    assert cb.SwinConfig.swin_t().window_size == 7 and cb.SwinConfig.swin_s().depths == (2, 2, 18, 2)
+    assert R.Config.swin_t().stage_channels() == [96, 192, 384, 768]
+
+
 def test_product_path_has_no_oracle_or_cpu_fallback():
     import inspect
     import candle_birefnet_b200.model as m

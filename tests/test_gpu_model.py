@@ -327,3 +327,41 @@ def test_call_order_and_concurrent_calls(mini_cfg, mini_weights_A):
     m.close()
     for g, w in zip(got, want):
         assert np.array_equal(g, w)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_window7_family(precision):
+    """SURVEY 8f N4: the window-7 members of the family (SwinConfig::swin_t / swin_s, src/swin.rs:27-52): 49-token
+    windows, shift 3.  (1) A reduced-width window-7 model at sizes with and without window padding (224 -> 56 tokens =
+    8 windows, 160 x 192 -> 40 x 48 tokens padded to 42 x 49), features and logits against the oracle; (2) swin_t itself
+    at 224 x 224.  LayerNorm, GEMMs, decoder and deformable convs are the swin_l kernels; attention is the SIMT kernel."""
+    cfg = R.Config.mini7()
+    w = make_weights(cfg, seed=2, weight_set="B", offset_sigma=2.0)
+    pc = cb.BiRefNetConfig(swin=cb.SwinConfig(embed_dim=cfg.embed_dim, depths=tuple(cfg.depths), num_heads=tuple(cfg.num_heads),
+                                              window_size=7), precision=precision, deform_mode="deformable")
+    m = cb.BiRefNet.new(pc, w)
+    try:
+        for hw in ((224, 224), (160, 192)):
+            x = make_input(2, hw[0], hw[1], seed=13)
+            feats = m.backbone_forward(x)
+            exp_f = R.swin_forward(torch.from_numpy(x), as_torch(w), cfg)
+            for i in range(4):
+                e = exp_f[i].numpy()
+                rel = np.abs(feats[i] - e).max() / np.abs(e).max()
+                assert feats[i].shape == e.shape and rel < (1e-4 if precision == "fp32" else 6e-3), (hw, i, rel)
+            got = m.forward_logits(x)
+            exp = R.forward_logits(torch.from_numpy(x), as_torch(w), cfg, "deformable").numpy()
+            check_logits(got, exp, precision)
+    finally:
+        m.close()
+    cfg = R.Config.swin_t()
+    w = make_weights(cfg, seed=4, weight_set="A")
+    m = cb.BiRefNet.new(cb.BiRefNetConfig(swin=cb.SwinConfig.swin_t(), precision=precision, deform_mode="deformable"), w)
+    try:
+        x = make_input(1, 224, 224, seed=6)
+        got = m.forward_logits(x)
+        exp = R.forward_logits(torch.from_numpy(x), as_torch(w), cfg, "cpu_fallback").numpy()
+        check_logits(got, exp, precision)
+        assert [f.shape[1] for f in m.backbone_forward(x)] == [96, 192, 384, 768]
+    finally:
+        m.close()

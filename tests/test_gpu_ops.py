@@ -261,3 +261,26 @@ def test_deformable_conv2d_module(cin, cout, k, stride, padding, mode, precision
     with pytest.raises(cb.BrnError) as e:
         cb.DeformableConv2d(cin, cout, k, stride, padding, {n: v for n, v in vb.items() if n != "regular_conv.bias"})
     assert e.value.status == 3
+
+
+@pytest.mark.parametrize("nimg,hp,wp,heads,shift", [(1, 14, 21, 3, 0), (2, 14, 21, 3, 3), (1, 7, 7, 6, 3), (1, 70, 70, 3, 3)])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_window_attention_window7(nimg, hp, wp, heads, shift, precision):
+    """The same plain chain for swin_t / swin_s windows (src/swin.rs:27-52: window 7, shift 3; 49 tokens per window),
+    mask from the oracle's create_attention_mask (regions split at hp - 7 and hp - 3, src/swin.rs:608-629)."""
+    rng = np.random.default_rng(hp + heads + shift)
+    n, nw = 49, (hp // 7) * (wp // 7)
+    C = heads * 32
+    qkv = rng.standard_normal((nimg * nw, n, 3 * C)).astype(np.float32)
+    bias = (rng.standard_normal((heads, n, n)) * 0.5).astype(np.float32)
+    got = cb.ops.window_attention(qkv, bias, hp, wp, shift, precision=precision)
+    t = torch.from_numpy(r16(qkv, precision)).double()
+    q, k, v = [t[..., i * C:(i + 1) * C].reshape(nimg * nw, n, heads, 32).permute(0, 2, 1, 3) for i in range(3)]
+    s = (q * 32 ** -0.5) @ k.transpose(-1, -2) + torch.from_numpy(bias).double()
+    if shift:
+        m = R.create_attention_mask(hp, wp, 7, 3, torch.float64)
+        s = (s.reshape(nimg, nw, heads, n, n) + m[None, :, None]).reshape(nimg * nw, heads, n, n)
+    exp = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(nimg * nw, n, C).numpy()
+    err = np.abs(got - exp).max()
+    # window 7 runs the SIMT kernel in every precision: fp32 arithmetic on (for fp16) fp16-rounded q, k, v and output
+    assert err < {"fp16": 4e-3, "fp32": 2e-5}[precision], err
