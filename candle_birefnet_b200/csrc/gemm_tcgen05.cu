@@ -49,6 +49,10 @@ struct TcGemmP {
   int tg;        // 3x3 tap groups: one A load of (16+2) x 8 pixels serves the three vertical taps of a kernel column
   int out_tiled; // fp32 out is [m_tile][N][128]
   int tma_store; // 16-bit row-major token-matrix output without residual / row map: the epilogue stores through tmO
+  int u2;        // CL = 2 only: the pair runs ONE tcgen05.mma.cta_group::2 (M = 256) per K step instead of two M = 128
+                 // MMAs on multicast copies of B: each CTA keeps its 128 rows of A and HALF of the B tile, which cuts the
+                 // shared-memory traffic per K block from 48 KB written + 48 KB read to 32 + 32 (the limiter of the
+                 // K >= 768 GEMMs: 64 % tensor-pipe active with the multicast scheme, ncu r02)
   EpiP epi;
   RowMap rm;
   FastDiv fd_nt, fd_tpi, fd_tx;        // n_tiles, tiles_x * tiles_y, tiles_x
@@ -113,7 +117,10 @@ enum EpiKind { EK_GENERIC = 0, EK_NONE16, EK_RELU16, EK_GELU16, EK_NONE32, EK_SI
                EK_LNF_NONE16, EK_LNF_GELU16,      // folded LayerNorm consumers (qkv, fc1)
                EK_RES32_EMIT, EK_NONE32_EMIT };   // fp32 stream producers that also emit statistics + the raw 16-bit copy
 
-template <int CL, int EPI>
+// U2: CTA-pair instance -- every tcgen05 alloc / mma / commit / dealloc of the kernel carries cta_group::2 (a kernel
+// must not mix the two CTA-group forms: the run-time switch of the first version worked in isolation and hung as soon
+// as two forwards were in flight on two streams, r02 run H).
+template <int CL, int EPI, bool U2 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcGemmP p) {
@@ -133,12 +140,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], CL); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 32 * TC_EPI_WARPS); }
+    constexpr bool u2i = U2;
+    for (int s = 0; s < TC_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], u2i ? 1 : CL); }
+    // pair mode: one elected lane per epilogue warp of BOTH CTAs arrives on the leader's accumulator-empty barrier
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], u2i ? 2 * TC_EPI_WARPS : 32 * TC_EPI_WARPS); }
     ptx::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); if (p.tma_store) ptx::prefetch_tmap(&tmO); }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  constexpr bool u2 = U2;
+  static_assert(!U2 || CL == 2, "CTA pairs are 2-CTA clusters");
+  if (warp == 1) { if (u2) ptx::tmem_alloc_2sm(tmem_slot, 512); else ptx::tmem_alloc(tmem_slot, 512); }
   ptx::tc_fence_before();
   __syncthreads();
   if (CL > 1) ptx::cluster_sync_all();     // peers' barriers are initialised before any multicast can land
@@ -167,7 +178,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int y0 = (r / p.tiles_x) * TH, x0 = (r % p.tiles_x) * TW;
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait_backoff(&empty[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full[stage], tx_bytes);
+          if (!u2) ptx::mbar_expect_tx(&full[stage], tx_bytes);
+          else if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * (TC_BM * TC_BK * 2 + b_rows * TC_BK * 2));
           const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
           if (p.tg) {
             // `tap` is the kernel column kx: the (TH+2) x TW box holds the input rows of all three vertical taps
@@ -184,6 +196,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             continue;
           }
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
+          if (u2) {
+            // CTA pair: both CTAs' boxes are counted on the LEADER's barrier (it expects the bytes of both); B is not
+            // multicast -- this CTA keeps rows [rank * BN/2, (rank + 1) * BN/2) of the tile at offset 0 of its B stage
+            // (the expect_tx above went to this CTA's own barrier: only the leader's is ever waited on, so the leader
+            // expects twice the per-CTA bytes and the follower's own barrier is simply not used in this mode)
+            const uint32_t lbar = ptx::mapa_shared(ptx::smem_u32(&full[stage]), 0);
+            ptx::tma_load_4d_2sm(sA + stage * TC_A_BYTES, &tmA, lbar, cb * TC_BK, x0 + kx - p.pad, y0 + ky - p.pad, b);
+            ptx::tma_load_2d_2sm(sB + stage * TC_B_BYTES, &tmB, lbar, tap * p.cin_pad + cb * TC_BK, n_tile * p.BN + rank * b_rows);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           ptx::tma_load_4d(sA + stage * TC_A_BYTES, &tmA, &full[stage], cb * TC_BK, x0 + kx - p.pad, y0 + ky - p.pad, b);
           uint8_t* bdst = sB + stage * TC_B_BYTES + rank * b_rows * (TC_BK * 2);
           const int bk = tap * p.cin_pad + cb * TC_BK, bn = n_tile * p.BN + rank * b_rows;
@@ -194,9 +217,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (ptx::elect_one()) {
+    if (ptx::elect_one() && !(u2 && rank != 0)) {      // pair mode: the leader CTA issues for both
       // ===== MMA issuer =====
-      const uint32_t idesc = ptx::make_idesc_16(TC_BM, p.BN, 0, 0, p.in_bf16);
+      const uint32_t idesc = ptx::make_idesc_16(u2 ? 2 * TC_BM : TC_BM, p.BN, 0, 0, p.in_bf16);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int item = item0; item < num_items; item += item_step) {
@@ -218,17 +241,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k)
                 ptx::umma_f16_ss(d_tmem, a_desc + ky * (1024 >> 4) + 2 * k, b_desc + ky * b_step + 2 * k, idesc, (kb | ky | k) != 0);
+          } else if (u2) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)
+              ptx::umma_f16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           } else {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)   // +32 B (= 2 in the >>4 address field) per K=16 step inside the 128B atom
               ptx::umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
           // the stage is free once the MMAs of EVERY CTA that received the multicast have read it
-          if (CL > 1) ptx::umma_commit_mc(&empty[stage], (uint16_t)((1u << CL) - 1));
+          if (u2) ptx::umma_commit_2sm(&empty[stage], (uint16_t)3);
+          else if (CL > 1) ptx::umma_commit_mc(&empty[stage], (uint16_t)((1u << CL) - 1));
           else ptx::umma_commit(&empty[stage]);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tfull[acc]);
+        if (u2) ptx::umma_commit_2sm(&tfull[acc], (uint16_t)3);     // both CTAs' epilogues
+        else ptx::umma_commit(&tfull[acc]);
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
     }
@@ -334,7 +363,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         epi_warp_dyn(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty[acc]);
+      if (u2) {
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&tempty[acc]), 0));
+      } else {
+        ptx::mbar_arrive(&tempty[acc]);
+      }
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
     if ((EPI == EK_NONE16 || EPI == EK_GELU16 || EPI == EK_LNF_GELU16) && p.tma_store && lane == 0)
@@ -343,7 +377,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   ptx::tc_fence_before();
   __syncthreads();
   if (CL > 1) ptx::cluster_sync_all();     // no CTA leaves while a peer may still multicast into it / arrive on its barriers
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+  if (warp == 1) { if (u2) ptx::tmem_dealloc_2sm(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -587,6 +621,12 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   // TMA store of the staged 16-bit tile: plain row-major token matrices (a tile = 128 consecutive output rows), no
   // residual, no row map.  BRN_GEMM_TMA_STORE=0 keeps the LDS + STG phase B (A/B testing).
   static const bool no_ts = [] { const char* v = getenv("BRN_GEMM_TMA_STORE"); return v && v[0] == '0'; }();
+  // CTA-pair UMMA (cta_group::2) for every 2-CTA launch that is not a tap-group conv; BRN_GEMM_UMMA2=0: multicast scheme
+  static const bool no_u2 = [] { const char* v = getenv("BRN_GEMM_UMMA2"); return v && v[0] == '0'; }();
+  // (K >= 1536 only: the pair couples the two CTAs' epilogues, which costs 20-40 % on the epilogue-bound short-K shapes
+  //  and gains 1-2 % on the long-K ones -- kernel_bench A/B, r02 run G)
+  p.u2 = (!no_u2 && CL == 2 && !tg && S == 1 && p.BN == 256 && kblocks >= 24 &&
+          (ek == EK_RES32_EMIT || ek == EK_NONE32_EMIT || ek == EK_LNF_GELU16 || ek == EK_LNF_NONE16)) ? 1 : 0;
   CUtensorMap tmO = tmA;                 // placeholder when unused (never dereferenced)
   p.tma_store = 0;
   if (!no_ts && (ek == EK_NONE16 || ek == EK_GELU16 || ek == EK_LNF_GELU16) && a.x.B == 1 && a.x.H == 1 && !a.rowmap.enabled &&
@@ -612,6 +652,15 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
     BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, p));
   };
 #define TC_EK_CASE(E) case E: if (CL == 2) launch(tc_gemm_kernel<2, E>); else launch(tc_gemm_kernel<1, E>); break
+  if (p.u2) {      // CTA-pair instances exist for the epilogues of the long-K backbone GEMMs only
+    switch (ek) {
+      case EK_RES32_EMIT: launch(tc_gemm_kernel<2, EK_RES32_EMIT, true>); break;
+      case EK_NONE32_EMIT: launch(tc_gemm_kernel<2, EK_NONE32_EMIT, true>); break;
+      case EK_LNF_GELU16: launch(tc_gemm_kernel<2, EK_LNF_GELU16, true>); break;
+      case EK_LNF_NONE16: launch(tc_gemm_kernel<2, EK_LNF_NONE16, true>); break;
+      default: BRN_CHECK(false, 2, "internal: no CTA-pair instance for this epilogue");
+    }
+  } else
   switch (ek) {
     TC_EK_CASE(EK_NONE16); TC_EK_CASE(EK_RELU16); TC_EK_CASE(EK_GELU16); TC_EK_CASE(EK_NONE32);
     TC_EK_CASE(EK_SIG32_TILED); TC_EK_CASE(EK_RES32); TC_EK_CASE(EK_RES16);
