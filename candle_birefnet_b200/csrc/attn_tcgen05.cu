@@ -102,6 +102,40 @@ __device__ __forceinline__ bool at_has_pad(const AttnP& p, const AtGeo& g) {
   const bool cp = wp > w && (c + 12 > wp || c + 11 >= w);
   return rp || cp;
 }
+// Everything a softmax thread needs to know about one unit, computed once per unit with the grid's constants taken
+// straight from the parameter bank (one warp-uniform branch on the grid instead of a select per constant):
+//   orow  : output row of this thread's query row (token row with token_out, else window row; -1: pad position)
+//   flags : 1 = last window row of a shifted block, 2 = last window column (the analytic mask applies), 4 = the window
+//           holds pad positions (its staged tiles need the bias rows)
+struct AtUnit {
+  int orow;
+  uint32_t flags;
+};
+__device__ __forceinline__ AtUnit at_unit_grid(const AttnP& p, int win_abs, int win, int r, int qi, int qj, int h, int w,
+                                               int nwh, int nww, long long t0, const FastDiv& fnw, const FastDiv& fnww) {
+  const int b = (int)fnw.div((uint32_t)win);
+  const int wl = win - b * (int)fnw.d;
+  const int wi = (int)fnww.div((uint32_t)wl), wj = wl - wi * (int)fnww.d;
+  const int hp = nwh * 12, wp = nww * 12;
+  const int a = wi * 12 + p.shift, c = wj * 12 + p.shift;
+  AtUnit u;
+  u.flags = (p.shift > 0 && wi == nwh - 1 ? 1u : 0u) | (p.shift > 0 && wj == nww - 1 ? 2u : 0u) |
+            (((hp > h && (a + 12 > hp || a + 11 >= h)) || (wp > w && (c + 12 > wp || c + 11 >= w))) ? 4u : 0u);
+  if (!p.token_out) {
+    u.orow = win_abs * 144 + r;
+  } else {
+    int pr = a + qi, pc = c + qj;
+    if (pr >= hp) pr -= hp;
+    if (pc >= wp) pc -= wp;
+    u.orow = (pr < h && pc < w) ? (int)t0 + (b * h + pr) * w + pc : -1;
+  }
+  return u;
+}
+__device__ __forceinline__ AtUnit at_unit(const AttnP& p, int win, int r, int qi, int qj) {
+  if (p.split_win > 0 && win >= p.split_win)
+    return at_unit_grid(p, win, win - p.split_win, r, qi, qj, p.h2, p.w2, p.nwh2, p.nww2, p.tok2, p.fd_nw2, p.fd_nww2);
+  return at_unit_grid(p, win, win, r, qi, qj, p.h, p.w, p.nwh, p.nww, 0, p.fd_nw1, p.fd_nww1);
+}
 __device__ __forceinline__ bool at_row_is_pad(const AttnP& p, const AtGeo& g, int ti, int tj) {
   const int nwh = g.g2 ? p.nwh2 : p.nwh, nww = g.g2 ? p.nww2 : p.nww, h = g.g2 ? p.h2 : p.h, w = g.g2 ? p.w2 : p.w;
   return at_src_coord(g.wi, ti, p.shift, nwh * 12) >= h || at_src_coord(g.wj, tj, p.shift, nww * 12) >= w;
@@ -113,6 +147,18 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// predicated 16-byte shared store (no branch around it)
+__device__ __forceinline__ void sts128_pred(uint32_t addr, const uint4& v, bool pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "@p st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n"
+      "}\n" ::"r"(addr),
+      "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((uint32_t)pred)
+      : "memory");
 }
 
 // three-input maximum (one FMNMX3 on sm_100)
@@ -356,31 +402,29 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
 
     // output row of this thread's query row for a unit: the window-ordered row, or with token_out the token row
     // (-1: pad position, nothing is stored)
-    auto out_row = [&](int win, const AtGeo& g) -> long long {
-      if (!p.token_out) return (long long)win * 144 + r;
-      const int g_h = g.g2 ? p.h2 : p.h, g_w = g.g2 ? p.w2 : p.w, g_nwh = g.g2 ? p.nwh2 : p.nwh, g_nww = g.g2 ? p.nww2 : p.nww;
-      const int pr = at_src_coord(g.wi, qi, p.shift, g_nwh * 12), pc = at_src_coord(g.wj, qj, p.shift, g_nww * 12);
-      if (pr >= g_h || pc >= g_w) return -1;
-      return (g.g2 ? p.tok2 : 0) + ((long long)g.b * g_h + pr) * g_w + pc;
-    };
     // pad rows of the NEXT unit's staged q / k / v tiles (see fix_pads0): thread t < 432 owns row t % 144 of tile t / 144
+    // Only the K and V tiles are patched (a pad QUERY row only produces an output row that is never stored), by
+    // threads 0-287 (row t % 144 of tile 1 + t / 144); only the threads that actually write wait for the TMA and fence.
     auto fix_pads_next = [&](int i1, const AtGeo& g) {
-      ptx::mbar_wait(&qkv_full[i1 % AT_STAGES], (i1 / AT_STAGES) & 1);
       const int t = threadIdx.x;
-      if (t < 432) {
-        const int tq = t / 144, row = t - tq * 144;
+      if (t < 288) {
+        const int tq = 1 + t / 144, row = t - (tq - 1) * 144;
         const int ti = row / 12, tj = row - ti * 12;
         if (at_row_is_pad(p, g, ti, tj)) {
+          ptx::mbar_wait(&qkv_full[i1 % AT_STAGES], (i1 / AT_STAGES) & 1);
           const uint32_t bsrc = ptx::smem_u32(sB16) + tq * 64;
           const uint32_t a = ptx::smem_u32(sQKV + (i1 % AT_STAGES) * AT_STAGE_BYTES) + tq * AT_TILE_BYTES + row * 64;
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) ptx::sts128(a + ((ch ^ ((row >> 1) & 3)) << 4), ptx::lds128(bsrc + ch * 16));
+          ptx::fence_proxy_async_smem();
         }
       }
-      ptx::fence_proxy_async_smem();
     };
-    AtGeo geo = at_geo(p, w_first);
-    long long orow_prev = -1;       // output row of the unit whose epilogue is still pending
+    AtUnit cur = at_unit(p, w_first, rr, qi, qj);
+    uint32_t pbase[2];
+    pbase[0] = sP_a + 3 * third * AT_P_BLOCK + rr * 32 + ((rr >> 2) & 1) * 16;
+    pbase[1] = sP_a + 3 * third * AT_P_BLOCK + rr * 32 + (((rr >> 2) & 1) ^ 1) * 16;
+    int orow_prev = -1;             // output row of the unit whose epilogue is still pending
 
     auto epilogue = [&](int j) {   // O(j) / sum(j) -> 16-bit, head-major channel (src/swin.rs:306-307)
       const int par = j & 1;
@@ -427,8 +471,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       const int par = i & 1, win = w_first + i * w_step;
       // analytic shift mask (src/swin.rs:603-655): only the last window row / column mixes regions.  Key c of this
       // third sits at ki = 4*third + c/12, kj = c%12; interior windows take the mask-free path.
-      const int g_nwh = geo.g2 ? p.nwh2 : p.nwh, g_nww = geo.g2 ? p.nww2 : p.nww;
-      const bool last_r = p.shift > 0 && geo.wi == g_nwh - 1, last_c = p.shift > 0 && geo.wj == g_nww - 1;
+      const bool last_r = (cur.flags & 1u) != 0, last_c = (cur.flags & 2u) != 0;
 
       // ---- scores: TMEM -> registers once, then hand the S region back to the MMA warp ----
       uint32_t v0[32], v1[16];
@@ -438,34 +481,44 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
       ptx::tmem_ld16(lane_base + s_col + 32, v1);
       tmem_wait32(v0); tmem_wait_dep(v1);
       // geometry of the next unit; its pad rows are patched before S is released (the MMA warp issues S(i+1) then)
-      const AtGeo geo_cur = geo;
+      AtUnit nxt = cur;
       if (i + 1 < n_units) {
-        geo = at_geo(p, win + w_step);
-        if (p.h > 0 && at_has_pad(p, geo)) fix_pads_next(i + 1, geo);
+        nxt = at_unit(p, win + w_step, rr, qi, qj);
+        if (p.h > 0 && (nxt.flags & 4u)) fix_pads_next(i + 1, at_geo(p, win + w_step));     // rare: border windows of padded grids
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(s_empty);
 
       // ---- pass 1: s + bias (+ mask) kept in registers as packed fp32 pairs (FADD2), partial row max ----
+      // The masked and the plain version are two COMPLETE loops that both define sc[] (a mask applied in place after
+      // the bias add made the compiler copy all 48 score registers in front of the branch: ~40 moves per warp and unit).
       unsigned long long sc[24];
       float mx = -INFINITY;
-#pragma unroll
-      for (int g = 0; g < 12; ++g) {
-        const uint4 bq = ptx::lds128(brow + g * 16);       // 4 fp32 bias values
-        const int c = g * 4;                               // key column within this third; 48 = 4 * 12 so kj = c % 12
-        auto sv = [&](int cc) { return __uint_as_float(cc < 32 ? v0[cc & 31] : v1[cc & 15]); };
-        sc[2 * g] = fadd2(pk2(sv(c), sv(c + 1)), pk2(__uint_as_float(bq.x), __uint_as_float(bq.y)));
-        sc[2 * g + 1] = fadd2(pk2(sv(c + 2), sv(c + 3)), pk2(__uint_as_float(bq.z), __uint_as_float(bq.w)));
-      }
+      auto sv = [&](int cc) { return __uint_as_float(cc < 32 ? v0[cc & 31] : v1[cc & 15]); };
       if (last_r || last_c) {      // warp-uniform: border windows of a shifted block only
 #pragma unroll
-        for (int kr = 0; kr < 4; ++kr) {                   // the four key rows of this third
+        for (int kr = 0; kr < 4; ++kr) {                   // the four key rows of this third (3 bias chunks = 12 keys each)
           const bool rmask = last_r && ((4 * third + kr >= 6) != (qi >= 6));
           const float m0 = (rmask || (last_c && (qj >= 6))) ? -100.0f : 0.0f;    // kj < 6
           const float m1 = (rmask || (last_c && (qj < 6))) ? -100.0f : 0.0f;     // kj >= 6
           const unsigned long long mk0 = pk2(m0, m0), mk1 = pk2(m1, m1);
 #pragma unroll
-          for (int c2 = 0; c2 < 6; ++c2) sc[kr * 6 + c2] = fadd2(sc[kr * 6 + c2], c2 >= 3 ? mk1 : mk0);
+          for (int gg = 0; gg < 3; ++gg) {
+            const int g = kr * 3 + gg, c = g * 4;
+            const uint4 bq = ptx::lds128(brow + g * 16);
+            const unsigned long long b0 = fadd2(pk2(__uint_as_float(bq.x), __uint_as_float(bq.y)), (2 * gg) >= 3 ? mk1 : mk0);
+            const unsigned long long b1 = fadd2(pk2(__uint_as_float(bq.z), __uint_as_float(bq.w)), (2 * gg + 1) >= 3 ? mk1 : mk0);
+            sc[2 * g] = fadd2(pk2(sv(c), sv(c + 1)), b0);
+            sc[2 * g + 1] = fadd2(pk2(sv(c + 2), sv(c + 3)), b1);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < 12; ++g) {
+          const uint4 bq = ptx::lds128(brow + g * 16);       // 4 fp32 bias values
+          const int c = g * 4;                               // key column within this third; 48 = 4 * 12 so kj = c % 12
+          sc[2 * g] = fadd2(pk2(sv(c), sv(c + 1)), pk2(__uint_as_float(bq.x), __uint_as_float(bq.y)));
+          sc[2 * g + 1] = fadd2(pk2(sv(c + 2), sv(c + 3)), pk2(__uint_as_float(bq.z), __uint_as_float(bq.w)));
         }
       }
 #pragma unroll
@@ -482,7 +535,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
 
       // ---- deferred epilogue of the previous unit (its P V finished long ago); also frees the P buffer ----
       if (i > 0) epilogue(i - 1);
-      orow_prev = row_ok ? out_row(win, geo_cur) : -1;
+      orow_prev = row_ok ? cur.orow : -1;
+      cur = nxt;
 
       // ---- pass 2: p = exp2((s - max) * log2e), partial row sum, 16-bit P -> shared (K-major, 32B swizzle) ----
       unsigned long long sum2 = pk2(0.f, 0.f);
@@ -504,11 +558,9 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
           sum2 = fadd2(sum2, pk2(p0, p1));
           packed[t] = at_pack<DT>(p0, p1);
         }
-        if (row_ok) {
-          // keys [8*G, 8*G+8), G = 6*third + g: K step G/2, 16-byte chunk (G&1) of the row's 32 B, XOR row bit 2
-          const int G = 6 * third + g, j16 = G >> 1, ch = (G & 1) ^ ((r >> 2) & 1);
-          ptx::sts128(sP_a + j16 * AT_P_BLOCK + r * 32 + ch * 16, make_uint4(packed[0], packed[1], packed[2], packed[3]));
-        }
+        // keys [8*G, 8*G+8), G = 6*third + g: K step G/2 = 3*third + g/2, 16-byte chunk (g&1) of the row's 32 B XOR row
+        // bit 2 -- two per-thread bases (pbase[g&1]) plus a compile-time offset; predicated, no branch
+        sts128_pred(pbase[g & 1] + (g >> 1) * AT_P_BLOCK, make_uint4(packed[0], packed[1], packed[2], packed[3]), row_ok);
       }
       float sum;
       {
