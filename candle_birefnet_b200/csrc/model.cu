@@ -1012,6 +1012,31 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
     }
   }
   if (prof_on) BRN_CUDA(cudaStreamSynchronize(st));
+  collect_profile();
+  } catch (...) {
+    cudaStreamSynchronize(st);
+    std::swap(arena, lanes[li].arena);
+    release_lane(li);
+    throw;
+  }
+  // host-side state is done with: hand the workspace back to the lane and wait for the device without the lock
+  std::swap(arena, lanes[li].arena);
+  cudaError_t werr = cudaSuccess;
+  if (last_bytes || ((!x_dev || !out_dev) && !prof_on)) {
+    lk.unlock();
+    if (last_bytes) werr = cudaMemcpyAsync(last_dst, last_src, last_bytes, cudaMemcpyDeviceToHost, st);
+    if (werr == cudaSuccess) werr = cudaStreamSynchronize(st);
+    lk.lock();
+  } else {
+    werr = cudaEventRecord(lanes[li].done, st);
+  }
+  release_lane(li);
+  BRN_CHECK(werr == cudaSuccess, 2, std::string("forward: ") + cudaGetErrorString(werr));
+}
+
+// after a profiled pass has completed on the device: per-class sums of the per-launch events, the optional per-launch
+// CSV (BRN_KERNEL_LOG) and the per-stage times
+void Model::collect_profile() {
   if (prof_on >= 2) {
     for (int c = 0; c < KC_COUNT; ++c) { kc_ms[c] = 0; kc_flops[c] = 0; kc_bytes[c] = 0; kc_count[c] = 0; }
     for (auto& r : ktimer.recs) {
@@ -1036,25 +1061,14 @@ void Model::forward(const float* x, int B, int H, int W, bool x_dev, float* out,
       prof_names.push_back(pe.name.c_str()); prof_ms.push_back(ms); prof_flops.push_back(pe.flops);
     }
   }
-  } catch (...) {
-    cudaStreamSynchronize(st);
-    std::swap(arena, lanes[li].arena);
-    release_lane(li);
-    throw;
+}
+// profiled passes of the partial entry points (backbone / features / decoder): same event bookkeeping as forward()
+void Model::begin_profile(LaunchCtx& ctx) {
+  if (prof_on >= 2) { ctx.kt = &ktimer; ktimer.reset(); }
+  if (prof_on) {
+    for (auto& pe : prof) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
+    prof.clear();
   }
-  // host-side state is done with: hand the workspace back to the lane and wait for the device without the lock
-  std::swap(arena, lanes[li].arena);
-  cudaError_t werr = cudaSuccess;
-  if (last_bytes || ((!x_dev || !out_dev) && !prof_on)) {
-    lk.unlock();
-    if (last_bytes) werr = cudaMemcpyAsync(last_dst, last_src, last_bytes, cudaMemcpyDeviceToHost, st);
-    if (werr == cudaSuccess) werr = cudaStreamSynchronize(st);
-    lk.lock();
-  } else {
-    werr = cudaEventRecord(lanes[li].done, st);
-  }
-  release_lane(li);
-  BRN_CHECK(werr == cudaSuccess, 2, std::string("forward: ") + cudaGetErrorString(werr));
 }
 
 void Model::backbone_api(const float* x, int B, int H, int W, bool x_dev, float* const outs[4], bool out_dev,
@@ -1068,6 +1082,7 @@ void Model::backbone_api(const float* x, int B, int H, int W, bool x_dev, float*
   LaunchCtx ctx; ctx.stream = st; ctx.precision = cfg.precision; ctx.force_simt = env_flag("BRN_FORCE_SIMT");
   long long dummy = 0;
   for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) begin_profile(ctx);
     arena.dry = pass == 0; ctx.dry = pass == 0; ctx.launches = pass == 0 ? &dummy : &launches;
     arena.off = 0; if (pass == 0) arena.peak = 0;
     float* din = (float*)arena.alloc((size_t)B * 3 * H * W * 4);
@@ -1091,6 +1106,7 @@ void Model::backbone_api(const float* x, int B, int H, int W, bool x_dev, float*
     if (pass == 0) ensure_arena(arena.peak);
   }
   BRN_CUDA(cudaStreamSynchronize(st));
+  collect_profile();
 }
 
 // x1..x3 and the cxt-concatenated x4 (src/birefnet.rs:412-454) as NCHW fp32: the inputs brn_decoder_forward takes
@@ -1106,6 +1122,7 @@ void Model::features_api(const float* x, int B, int H, int W, bool x_dev, float*
   LaunchCtx ctx; ctx.stream = st; ctx.precision = cfg.precision; ctx.force_simt = env_flag("BRN_FORCE_SIMT");
   long long dummy = 0;
   for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) begin_profile(ctx);
     arena.dry = pass == 0; ctx.dry = pass == 0; ctx.launches = pass == 0 ? &dummy : &launches;
     arena.off = 0; if (pass == 0) arena.peak = 0;
     float* din = (float*)arena.alloc((size_t)B * 3 * H * W * 4);
@@ -1127,6 +1144,7 @@ void Model::features_api(const float* x, int B, int H, int W, bool x_dev, float*
     if (pass == 0) ensure_arena(arena.peak);
   }
   BRN_CUDA(cudaStreamSynchronize(st));
+  collect_profile();
 }
 
 void Model::decoder_api(const float* x, const float* x1, const float* x2, const float* x3, const float* x4, int B,
@@ -1142,6 +1160,7 @@ void Model::decoder_api(const float* x, const float* x1, const float* x2, const 
   const cudaMemcpyKind kin = is_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const float* srcs[4] = {x1, x2, x3, x4};
   for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) begin_profile(ctx);
     arena.dry = pass == 0; ctx.dry = pass == 0; ctx.launches = pass == 0 ? &dummy : &launches;
     arena.off = 0; if (pass == 0) arena.peak = 0;
     float* dimg = (float*)arena.alloc((size_t)B * 3 * H * W * 4);
@@ -1164,6 +1183,7 @@ void Model::decoder_api(const float* x, const float* x1, const float* x2, const 
     if (pass == 0) ensure_arena(arena.peak);
   }
   BRN_CUDA(cudaStreamSynchronize(st));
+  collect_profile();
 }
 
 }  // namespace brn

@@ -180,6 +180,8 @@ struct Model {
   // rate, 3 more mantissa bits -- what IoU >= 0.999 on near-threshold logits needs)
   int bf16_decoder_fp16 = 1;
   int dec_dtype() const;
+  void begin_profile(LaunchCtx& ctx);
+  void collect_profile();
   void prof_begin(LaunchCtx& ctx, const char* name);
   void prof_end(LaunchCtx& ctx);
 
