@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
     L.brn_postprocess_mask.argtypes = [C.c_int, vp, i32, i32, i32, i32, i32, vp]
     L.brn_infer_rgb8.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.brn_ln_linear.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.brn_swin_mlp.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
     L.brn_conv2d.argtypes = [C.c_int, C.c_int, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     L.brn_bench_op.argtypes = [C.c_int, C.c_int, C.c_int] + [i32] * 10 + [fp]
     L.brn_sharded_create.argtypes = [C.POINTER(BrnConfig), C.POINTER(i32), i32, C.POINTER(vp)]

@@ -10,7 +10,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libbirefnet_b200.so"
-SOURCES = ["abi.cu", "model.cu", "kernels_simt.cu", "kernels_glue.cu", "gemm_tcgen05.cu", "attn_tcgen05.cu",
+SOURCES = ["abi.cu", "model.cu", "kernels_simt.cu", "kernels_glue.cu", "gemm_tcgen05.cu", "attn_tcgen05.cu", "mlp_tcgen05.cu",
            "deform_tcgen05.cu", "ln_kernels.cu", "final_kernel.cu", "prepost.cu", "safetensors_loader.cpp", "sharded.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

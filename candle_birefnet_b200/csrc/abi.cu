@@ -353,6 +353,66 @@ brn_status brn_ln_linear(int device, int precision, const float* x, const float*
   });
 }
 
+// Swin MLP sub-block (src/swin.rs:103-107 inside :407): out = x + fc2(gelu_erf(fc1(LayerNorm(x)))) on the tensor-core
+// path with the LayerNorm folded.  fused: 1 = the single-kernel path (mlp_tcgen05.cu; C in {128, 192, 256}, hidden = 4C),
+// 0 = two GEMMs, -1 = whatever the model would run.  out_mean_rstd (optional, [M, 2]): the (mean, rstd) the epilogue's
+// emitted statistics give for the rows of `out` -- what the NEXT block's folded norm1 would consume.
+brn_status brn_swin_mlp(int device, int precision, const float* x, const float* gamma, const float* beta,
+                        const float* w1, const float* b1, const float* w2, const float* b2, int32_t M, int32_t C,
+                        int32_t hidden, int32_t fused, float* out, float* out_mean_rstd) {
+  return guard([&] {
+    BRN_CHECK(x && gamma && beta && w1 && w2 && out && M > 0 && C > 0 && hidden > 0, 1, "brn_swin_mlp: bad argument");
+    BRN_CHECK(precision != BRN_PREC_FP32, 7, "brn_swin_mlp: the LayerNorm fold is a tensor-core-path feature");
+    BRN_CHECK(C % 16 == 0 && hidden % 8 == 0, 5, "brn_swin_mlp: C % 16 == 0 and hidden % 8 == 0");
+    Scratch s(device);
+    LaunchCtx ctx = make_ctx(s, precision);
+    const int AD = precision == BRN_PREC_FP16 ? F16 : BF16;
+    std::vector<float> wf((size_t)hidden * C), bf(hidden);
+    for (int n = 0; n < hidden; ++n) {
+      double acc = b1 ? b1[n] : 0.0;
+      for (int c = 0; c < C; ++c) {
+        wf[(size_t)n * C + c] = (float)((double)w1[(size_t)n * C + c] * gamma[c]);
+        acc += (double)w1[(size_t)n * C + c] * beta[c];
+      }
+      bf[n] = (float)acc;
+    }
+    LayerW L1 = make_layer_standalone(hidden, C, 1, 1, wf.data(), bf.data(), s.ptrs, true);
+    LayerW L2 = make_layer_standalone(C, hidden, 1, 1, w2, b2, s.ptrs);
+    View xt = make_view(s.put(x, (size_t)M * C), F32, 1, 1, M, C);
+    View x16 = make_view(s.alloc((size_t)M * C * 2), AD, 1, 1, M, C);
+    const int parts = tc_gemm_ln_parts(C);
+    float2* stats = (float2*)s.alloc((size_t)parts * M * sizeof(float2));
+    float2* mr = (float2*)s.alloc((size_t)M * sizeof(float2));
+    glue_ln_stats_cast(ctx, xt, x16, stats);
+    glue_ln_finalize(ctx, stats, 1, M, M, C, mr);
+    MlpArgs ml; ml.x16 = x16; ml.mr = mr; ml.fc1 = &L1; ml.fc2 = &L2; ml.xt = xt;
+    ml.lne.stats = stats; ml.lne.stride = M; ml.lne.x16 = x16.p; ml.lne.x16dt = AD; ml.lne.ldx16 = C;
+    const bool can = hidden == 4 * C && tc_mlp_supported(ml);
+    BRN_CHECK(fused != 1 || can, 7, "brn_swin_mlp: the fused kernel needs C in {128, 192, 256} and hidden = 4C");
+    if (fused != 0 && can) {
+      tc_mlp(ctx, ml);
+    } else {
+      View hd = make_view(s.alloc((size_t)M * hidden * 2), AD, 1, 1, M, hidden);
+      GemmArgs g; g.x = x16; g.w = &L1; g.act = ACT_GELU; g.out = hd; g.lnf.mr = mr; g.lnf.C = C;
+      BRN_CHECK(tc_gemm_supported(g), 5, "brn_swin_mlp: fc1 shape unsupported");
+      tc_gemm(ctx, g);
+      GemmArgs g2; g2.x = hd; g2.w = &L2; g2.out = xt; g2.res = xt; g2.lne = ml.lne;
+      BRN_CHECK(tc_gemm_supported(g2), 5, "brn_swin_mlp: fc2 shape unsupported");
+      tc_gemm(ctx, g2);
+    }
+    glue_ln_finalize(ctx, stats, parts, M, M, C, mr);
+    BRN_CUDA(cudaMemcpyAsync(out, xt.p, (size_t)M * C * 4, cudaMemcpyDeviceToHost, s.stream));
+    std::vector<float2> h;
+    if (out_mean_rstd) {
+      h.resize(M);
+      BRN_CUDA(cudaMemcpyAsync(h.data(), mr, (size_t)M * sizeof(float2), cudaMemcpyDeviceToHost, s.stream));
+    }
+    BRN_CUDA(cudaStreamSynchronize(s.stream));
+    if (out_mean_rstd)
+      for (int m = 0; m < M; ++m) { out_mean_rstd[2 * m] = -h[m].x; out_mean_rstd[2 * m + 1] = h[m].y; }
+  });
+}
+
 brn_status brn_conv2d(int device, int precision, const float* x, const float* weight, const float* bias, int32_t B,
                       int32_t C, int32_t H, int32_t W, int32_t O, int32_t k, int32_t act, float* out) {
   return guard([&] {
@@ -578,7 +638,7 @@ brn_status brn_bench_op(int device, int precision, int kind, int32_t B, int32_t 
     cudaEvent_t e0, e1;
     BRN_CUDA(cudaEventCreate(&e0)); BRN_CUDA(cudaEventCreate(&e1));
     std::function<void()> launch;
-    LayerW L{}; GemmArgs g; AttnArgs at; DeformArgs d;
+    LayerW L{}, L2{}; GemmArgs g; AttnArgs at; DeformArgs d; MlpArgs ml; View hd;
     const size_t px = (size_t)B * H * W;
     if (kind == 0 || kind == 2) {
       const int taps = k * k;
@@ -607,6 +667,35 @@ brn_status brn_bench_op(int device, int precision, int kind, int32_t B, int32_t 
         d.om_tiled = (H % 8 == 0 && W % 16 == 0 && precision != BRN_PREC_FP32) ? 1 : 0;
         launch = [&] { op_deform(ctx, d); };
       }
+    } else if (kind == 3) {
+      // Swin MLP half-block on M = B*H*W rows of width C: with_res = 1 the fused kernel, 0 fc1 + fc2 through HBM
+      const int hid = 4 * C;
+      std::vector<float> hw((size_t)hid * C), hb(hid), hw2((size_t)C * hid), hb2(C);
+      for (size_t i = 0; i < hw.size(); ++i) hw[i] = (float)((int)((i * 2654435761u) >> 20 & 1023) - 512) / (512.0f * sqrtf((float)C));
+      for (size_t i = 0; i < hw2.size(); ++i) hw2[i] = (float)((int)((i * 2246822519u) >> 20 & 1023) - 512) / (512.0f * sqrtf((float)hid));
+      for (int i = 0; i < hid; ++i) hb[i] = 0.01f * (i % 7);
+      for (int i = 0; i < C; ++i) hb2[i] = 0.01f * (i % 5);
+      L = make_layer_standalone(hid, C, 1, 1, hw.data(), hb.data(), s.ptrs, true);
+      L2 = make_layer_standalone(C, hid, 1, 1, hw2.data(), hb2.data(), s.ptrs);
+      ml.xt = make_view(s.alloc(px * C * 4), F32, 1, 1, (int)px, C);
+      fill(s, ml.xt.p, F32, (long long)px * C, 2u, 1.0f);
+      ml.x16 = make_view(s.alloc(px * C * 2), AD, 1, 1, (int)px, C);
+      const int parts = tc_gemm_ln_parts(C);
+      float2* stats = (float2*)s.alloc((size_t)parts * px * sizeof(float2));
+      float2* mr = (float2*)s.alloc(px * sizeof(float2));
+      glue_ln_stats_cast(ctx, ml.xt, ml.x16, stats);
+      glue_ln_finalize(ctx, stats, 1, (long long)px, (long long)px, C, mr);
+      ml.mr = mr; ml.fc1 = &L; ml.fc2 = &L2;
+      ml.lne.stats = stats; ml.lne.stride = (long long)px; ml.lne.x16 = ml.x16.p; ml.lne.x16dt = AD; ml.lne.ldx16 = C;
+      hd = make_view(s.alloc(px * hid * 2), AD, 1, 1, (int)px, hid);
+      // (the statistics are not refreshed between iterations: the values drift, the timing does not depend on them)
+      if (with_res) launch = [&] { tc_mlp(ctx, ml); };
+      else launch = [&] {
+        GemmArgs g1; g1.x = ml.x16; g1.w = &L; g1.act = ACT_GELU; g1.out = hd; g1.lnf.mr = ml.mr; g1.lnf.C = C;
+        tc_gemm(ctx, g1);
+        GemmArgs g2; g2.x = hd; g2.w = &L2; g2.out = ml.xt; g2.res = ml.xt; g2.lne = ml.lne;
+        tc_gemm(ctx, g2);
+      };
     } else {
       const int heads = C, Cc = heads * 32, nwin = B;
       const size_t rows = (size_t)nwin * 144;

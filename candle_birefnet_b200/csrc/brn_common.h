@@ -144,6 +144,18 @@ struct GemmArgs {
   double flops = 0;
 };
 
+// Fused Swin MLP on the tensor-core path (mlp_tcgen05.cu): xt <- xt + fc2(gelu(fc1(LN(xt)))) with the LayerNorm folded
+// (x16 = raw 16-bit copy of xt, mr = its row statistics) and the next block's statistics emitted (lne; lne.x16 may be
+// x16 itself: a tile's rows are read before they are rewritten).  src/swin.rs:103-107,407.
+struct MlpArgs {
+  View x16;                      // [rows, C] 16-bit
+  const float2* mr = nullptr;    // [rows] (-mean, rstd)
+  const LayerW* fc1 = nullptr;   // gamma-folded, with column sums
+  const LayerW* fc2 = nullptr;
+  View xt;                       // [rows, C] fp32 residual stream, updated in place
+  LnEmit lne;
+};
+
 struct DeformArgs {
   View x;                 // [B,H,W,C] input
   View om;                // [B,H,W,3*taps] fp32: 2*taps offsets (dy,dx interleaved) then taps modulators
@@ -230,6 +242,8 @@ bool tc_gemm_supported(const GemmArgs&);
 void tc_gemm(const LaunchCtx&, const GemmArgs&);
 size_t tc_gemm_splitk_scratch_bytes(int batch);   // LaunchCtx::splitk size that every split-K launch of a batch fits in
 void tc_attention(const LaunchCtx&, const AttnArgs&);
+bool tc_mlp_supported(const MlpArgs&);
+void tc_mlp(const LaunchCtx&, const MlpArgs&);
 bool tc_deform_supported(const DeformArgs&);
 void tc_deform(const LaunchCtx&, const DeformArgs&);
 

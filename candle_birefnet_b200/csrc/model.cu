@@ -677,17 +677,25 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
         if (!fold) { g.rowmap = wmap; g.rowmap.enabled = 1; }
         emit_gemm(g); }
       // x + fc2(gelu(fc1(norm2(x))))  (src/swin.rs:407)
-      View hd = make_view(arena.alloc((size_t)Tt * cfg.mlp_ratio * Ci * dsize(AD)), AD, 1, 1, (int)Tt, cfg.mlp_ratio * Ci);
-      if (fold) {
-        GemmArgs g; g.x = x16; g.w = &bw.fc1_f; g.act = ACT_GELU; g.out = hd; folded(g);
-        BRN_CHECK(tc_gemm_supported(g), 5, "folded fc1: tcgen05 path unavailable");
-        tc_gemm(ctx, g);
+      // Early stages (C <= 256, mlp_ratio 4): one fused kernel, the hidden activations stay on the SM (mlp_tcgen05.cu)
+      MlpArgs ml; ml.x16 = x16; ml.mr = mr; ml.fc1 = &bw.fc1_f; ml.fc2 = &bw.fc2; ml.xt = xt;
+      ml.lne.stats = stats; ml.lne.stride = Tt; ml.lne.x16 = x16.p; ml.lne.x16dt = AD; ml.lne.ldx16 = Ci;
+      if (fold && cfg.mlp_ratio == 4 && !env_flag("BRN_MLP_UNFUSED") && tc_mlp_supported(ml)) {
+        tc_mlp(ctx, ml);
+        glue_ln_finalize(ctx, stats, parts, Tt, Tt, Ci, mr);
       } else {
-        View xn = make_view(arena.alloc((size_t)Tt * Ci * dsize(AD)), AD, 1, 1, (int)Tt, Ci);
-        { LnArgs l; l.x = xt; l.gamma = bw.n2g; l.beta = bw.n2b; l.out = xn; l.mode = LN_PLAIN; glue_layernorm(ctx, l); }
-        GemmArgs g; g.x = xn; g.w = &bw.fc1; g.act = ACT_GELU; g.out = hd; op_gemm(ctx, g);
+        View hd = make_view(arena.alloc((size_t)Tt * cfg.mlp_ratio * Ci * dsize(AD)), AD, 1, 1, (int)Tt, cfg.mlp_ratio * Ci);
+        if (fold) {
+          GemmArgs g; g.x = x16; g.w = &bw.fc1_f; g.act = ACT_GELU; g.out = hd; folded(g);
+          BRN_CHECK(tc_gemm_supported(g), 5, "folded fc1: tcgen05 path unavailable");
+          tc_gemm(ctx, g);
+        } else {
+          View xn = make_view(arena.alloc((size_t)Tt * Ci * dsize(AD)), AD, 1, 1, (int)Tt, Ci);
+          { LnArgs l; l.x = xt; l.gamma = bw.n2g; l.beta = bw.n2b; l.out = xn; l.mode = LN_PLAIN; glue_layernorm(ctx, l); }
+          GemmArgs g; g.x = xn; g.w = &bw.fc1; g.act = ACT_GELU; g.out = hd; op_gemm(ctx, g);
+        }
+        { GemmArgs g; g.x = hd; g.w = &bw.fc2; g.out = xt; g.res = xt; emit_gemm(g); }
       }
-      { GemmArgs g; g.x = hd; g.w = &bw.fc2; g.out = xt; g.res = xt; emit_gemm(g); }
       have_stats = fold;
       arena.release(mb);
     }

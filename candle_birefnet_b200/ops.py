@@ -42,6 +42,23 @@ def ln_linear(x, gamma, beta, w, bias=None, act: int = 0, precision: str = "fp16
     return out
 
 
+def swin_mlp(x, gamma, beta, w1, b1, w2, b2, precision: str = "fp16", fused: int = -1, device: int = 0,
+             with_stats: bool = False):
+    """x + fc2(gelu_erf(fc1(LayerNorm(x)))): `Mlp::forward` inside the Swin block (src/swin.rs:103-107,407).
+
+    fused=1 demands the single-kernel path (C in {128, 192, 256}, hidden = 4C), 0 the two-GEMM path, -1 the model's own
+    choice.  with_stats: also return the [M, 2] (mean, rstd) the epilogue emits for the next block's folded norm1."""
+    x, gamma, beta, w1, b1, w2, b2 = (_f32(t) for t in (x, gamma, beta, w1, b1, w2, b2))
+    M, Cc = x.shape
+    hidden = w1.shape[0]
+    assert w1.shape == (hidden, Cc) and w2.shape == (Cc, hidden)
+    out = np.empty((M, Cc), dtype=np.float32)
+    st = np.empty((M, 2), dtype=np.float32) if with_stats else None
+    check(lib().brn_swin_mlp(device, _PREC[precision], _p(x), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), M, Cc,
+                             hidden, fused, _p(out), _p(st)))
+    return (out, st) if with_stats else out
+
+
 def conv2d(x, weight, bias=None, act: int = 0, precision: str = "bf16", device: int = 0) -> np.ndarray:
     """candle_nn::conv2d, stride 1, padding k//2, NCHW."""
     x, weight, bias = _f32(x), _f32(weight), _f32(bias)
@@ -147,9 +164,10 @@ def postprocess_mask(logits: np.ndarray, orig_h: int, orig_w: int, device: int =
 
 def bench_op(kind: str, B: int, H: int, W: int, Cin: int, N: int = 0, k: int = 1, act: int = 0, with_res: bool = False,
              out_f32: bool = False, iters: int = 20, precision: str = "fp16", device: int = 0) -> float:
-    """Mean device ms per launch of one kernel on synthetic device-resident data (kind: gemm | attn | deform)."""
+    """Mean device ms per launch of one kernel on synthetic device-resident data (kind: gemm | attn | deform | mlp;
+    mlp: M = B*H*W rows of width Cin, with_res = the fused kernel, else fc1 + fc2)."""
     ms = C_float()
-    kid = {"gemm": 0, "attn": 1, "deform": 2}[kind]
+    kid = {"gemm": 0, "attn": 1, "deform": 2, "mlp": 3}[kind]
     check(lib().brn_bench_op(device, _PREC[precision], kid, B, H, W, Cin, N, k, act, int(with_res), int(out_f32), iters,
                              C.byref(ms)))
     return float(ms.value)

@@ -255,13 +255,24 @@ BRN_API brn_status brn_linear(int device, int precision, const float* a, const f
 BRN_API brn_status brn_ln_linear(int device, int precision, const float* x, const float* gamma, const float* beta,
                          const float* w, const float* bias, int32_t M, int32_t N, int32_t K, int32_t act, float* out);
 
+/* The MLP half of a Swin block, out = x + fc2(gelu_erf(fc1(LayerNorm(x; gamma, beta, eps 1e-5)))): Mlp::forward
+ * (src/swin.rs:103-107) as SwinTransformerBlock::forward calls it (src/swin.rs:407).  x, out: HOST fp32 [M, C];
+ * w1 [hidden, C], b1 [hidden], w2 [C, hidden], b2 [C] (b1 / b2 may be NULL).  precision BRN_PREC_BF16 / BRN_PREC_FP16.
+ * fused: 1 = the single-kernel path of the early stages (C in {128, 192, 256}, hidden = 4C: hidden activations stay in
+ * shared / tensor memory), 0 = two GEMMs through HBM, -1 = what the model itself would run for this shape.
+ * out_mean_rstd (optional, HOST [M, 2]): per-row (mean, rstd) of `out` as emitted for the next block's folded norm1. */
+BRN_API brn_status brn_swin_mlp(int device, int precision, const float* x, const float* gamma, const float* beta,
+                        const float* w1, const float* b1, const float* w2, const float* b2, int32_t M, int32_t C,
+                        int32_t hidden, int32_t fused, float* out, float* out_mean_rstd);
+
 /* conv2d, stride 1, zero padding k/2, NCHW fp32 HOST tensors (candle_nn::conv2d; src/decoder.rs:44-45,104,113). */
 BRN_API brn_status brn_conv2d(int device, int precision, const float* x, const float* weight, const float* bias, int32_t B,
                       int32_t C, int32_t H, int32_t W, int32_t O, int32_t k, int32_t act, float* out);
 
 /* Kernel micro-benchmark on device-resident synthetic data: mean device ms per launch over `iters` back-to-back
  * launches.  kind 0: conv / linear implicit GEMM x[B,H,W,C] * w[N,k,k,C]; kind 1: window attention (B = windows,
- * C = heads, H,W = windows per image side, k = shift); kind 2: deformable conv (C must be 64). */
+ * C = heads, H,W = windows per image side, k = shift); kind 2: deformable conv (C must be 64);
+ * kind 3: the MLP half of a Swin block on B*H*W rows of width C (with_res = 1: fused kernel, 0: fc1 + fc2). */
 BRN_API brn_status brn_bench_op(int device, int precision, int kind, int32_t B, int32_t H, int32_t W, int32_t C, int32_t N,
                                 int32_t k, int32_t act, int32_t with_res, int32_t out_f32, int32_t iters, float* ms_out);
 

@@ -122,6 +122,9 @@ extern "C" {
                       residual: *const f32, m: i32, n: i32, k: i32, act: i32, out: *mut f32) -> brn_status;
     pub fn brn_ln_linear(device: c_int, precision: c_int, x: *const f32, gamma: *const f32, beta: *const f32,
                          w: *const f32, bias: *const f32, m: i32, n: i32, k: i32, act: i32, out: *mut f32) -> brn_status;
+    pub fn brn_swin_mlp(device: c_int, precision: c_int, x: *const f32, gamma: *const f32, beta: *const f32,
+                        w1: *const f32, b1: *const f32, w2: *const f32, b2: *const f32, m: i32, c: i32, hidden: i32,
+                        fused: i32, out: *mut f32, out_mean_rstd: *mut f32) -> brn_status;
     pub fn brn_conv2d(device: c_int, precision: c_int, x: *const f32, weight: *const f32, bias: *const f32, b: i32,
                       c: i32, h: i32, w: i32, o: i32, k: i32, act: i32, out: *mut f32) -> brn_status;
     pub fn brn_bench_op(device: c_int, precision: c_int, kind: c_int, b: i32, h: i32, w: i32, c: i32, n: i32, k: i32,

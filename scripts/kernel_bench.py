@@ -83,6 +83,16 @@ def main():
                 print(f"attn windows={nw:5d} heads={heads:2d} shift={shift} pad={pad}: window-order {ms0*1e3:8.1f} us {nw*heads/ms0/1e3:6.1f} units/us | "
                       f"token-order+pads {ms1*1e3:8.1f} us {nw*heads/ms1/1e3:6.1f} units/us", flush=True)
         return
+    if which == "mlp":     # the MLP half of a Swin block at the model's stage-0 / stage-1 row counts (batch 16, merged grids)
+        for (M, Cc) in ((1310720, 192), (327680, 128), (327680, 256)):
+            for prec in ("fp16", "bf16"):
+                ms0 = ops.bench_op("mlp", 1, 1, M, Cc, with_res=False, precision=prec)
+                ms1 = ops.bench_op("mlp", 1, 1, M, Cc, with_res=True, precision=prec)
+                fl = 16.0 * M * Cc * Cc
+                gb = 12.0 * M * Cc
+                print(f"mlp M={M} C={Cc} {prec}: fc1+fc2 {ms0*1e3:8.1f} us {fl/ms0/1e9:6.1f} TF/s | fused {ms1*1e3:8.1f} us "
+                      f"{fl/ms1/1e9:6.1f} TF/s {gb/ms1/1e6:6.0f} GB/s compulsory", flush=True)
+        return
     if which == "attn1":   # attn1 <windows> <heads> <side> <shift>
         nw, heads, side, shift = [int(v) for v in sys.argv[2:6]]
         ms = ops.bench_op("attn", nw, side, side, heads, 0, shift, precision="fp16")

@@ -155,6 +155,41 @@ def test_ln_linear_fold(M, N, K, mean_over_std, precision, act):
     assert err < tol, (err, tol)
 
 
+@pytest.mark.parametrize("M,C", [(1000, 192), (148 * 128 + 205, 192), (149 * 128, 192), (777, 128), (150 * 128 + 1, 128), (640, 256),
+                                 (148 * 128 + 64, 256)])
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_swin_mlp_fused(M, C, precision):
+    """The fused MLP kernel of the early stages (mlp_tcgen05.cu) against x + fc2(gelu(fc1(LN(x)))) in fp64
+    (src/swin.rs:103-107,407), against the two-GEMM path it replaces, and its emitted row statistics against the
+    statistics of its own output.  Row counts cover partial tiles, one CTA per tile (M < 148 tiles) and 2-CTA clusters
+    with an odd tile count (the second CTA of the last pair has no tile)."""
+    rng = np.random.default_rng(M + C)
+    hid = 4 * C
+    x = (rng.standard_normal((M, C)) * rng.uniform(0.5, 3.0, size=(M, 1)) + rng.uniform(-2.0, 2.0, size=(M, 1))).astype(np.float32)
+    gamma = (1.0 + 0.1 * rng.standard_normal(C)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    w1 = (rng.standard_normal((hid, C)) / np.sqrt(C)).astype(np.float32)
+    b1 = (0.5 * rng.standard_normal(hid)).astype(np.float32)
+    w2 = (rng.standard_normal((C, hid)) / np.sqrt(hid)).astype(np.float32)
+    b2 = (0.5 * rng.standard_normal(C)).astype(np.float32)
+    got, st = cb.ops.swin_mlp(x, gamma, beta, w1, b1, w2, b2, precision=precision, fused=1, with_stats=True)
+    two = cb.ops.swin_mlp(x, gamma, beta, w1, b1, w2, b2, precision=precision, fused=0)
+    xd = torch.from_numpy(x).double()
+    ln = F.layer_norm(xd, (C,), torch.from_numpy(gamma).double(), torch.from_numpy(beta).double(), 1e-5)
+    h = F.gelu(ln @ torch.from_numpy(w1).double().T + torch.from_numpy(b1).double())
+    exp = (xd + h @ torch.from_numpy(w2).double().T + torch.from_numpy(b2).double()).numpy()
+    eps = 2.0 ** -11 if precision == "fp16" else 2.0 ** -8
+    scale = max(1.0, np.abs(exp).max())
+    err = np.abs(got - exp).max() / scale
+    assert err < 12.0 * eps, (err, eps)
+    # same operands, same roundings (hidden activations rounded to the operand type on both paths); fp32 accumulation
+    # order over the hidden dimension differs (one 4C-long chain vs 128-wide chunks): a few fp32 ulps
+    assert np.abs(got - two).max() / scale < 1e-5, np.abs(got - two).max()
+    mean, rstd = got.astype(np.float64).mean(1), 1.0 / np.sqrt(got.astype(np.float64).var(1) + 1e-5)
+    assert np.abs(st[:, 0] - mean).max() < 1e-4 * scale
+    assert np.abs(st[:, 1] / rstd - 1.0).max() < 1e-3
+
+
 def test_preprocess_matches_image_crate_restatement():
     """examples/infer_image.rs:44-67 on the device: Triangle resize_exact + ImageNet normalise of the reference's own
     test photo, against oracle/imageops_ref.py (restatement of the `image` 0.25.9 sampling code).  Triangle weights are
