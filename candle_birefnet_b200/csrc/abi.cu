@@ -354,7 +354,7 @@ brn_status brn_ln_linear(int device, int precision, const float* x, const float*
 }
 
 // Swin MLP sub-block (src/swin.rs:103-107 inside :407): out = x + fc2(gelu_erf(fc1(LayerNorm(x)))) on the tensor-core
-// path with the LayerNorm folded.  fused: 1 = the single-kernel path (mlp_tcgen05.cu; C in {128, 192, 256}, hidden = 4C),
+// path with the LayerNorm folded.  fused: 1 = the single-kernel path (mlp_tcgen05.cu; C in {128, 192}, hidden = 4C),
 // 0 = two GEMMs, -1 = whatever the model would run.  out_mean_rstd (optional, [M, 2]): the (mean, rstd) the epilogue's
 // emitted statistics give for the rows of `out` -- what the NEXT block's folded norm1 would consume.
 brn_status brn_swin_mlp(int device, int precision, const float* x, const float* gamma, const float* beta,
@@ -386,9 +386,9 @@ brn_status brn_swin_mlp(int device, int precision, const float* x, const float* 
     glue_ln_stats_cast(ctx, xt, x16, stats);
     glue_ln_finalize(ctx, stats, 1, M, M, C, mr);
     MlpArgs ml; ml.x16 = x16; ml.mr = mr; ml.fc1 = &L1; ml.fc2 = &L2; ml.xt = xt;
-    ml.lne.stats = stats; ml.lne.stride = M; ml.lne.x16 = x16.p; ml.lne.x16dt = AD; ml.lne.ldx16 = C;
+    ml.lne.stats = stats; ml.lne.stride = M; ml.lne.x16 = x16.p; ml.lne.x16dt = AD; ml.lne.ldx16 = C; ml.mr_out = mr;
     const bool can = hidden == 4 * C && tc_mlp_supported(ml);
-    BRN_CHECK(fused != 1 || can, 7, "brn_swin_mlp: the fused kernel needs C in {128, 192, 256} and hidden = 4C");
+    BRN_CHECK(fused != 1 || can, 7, "brn_swin_mlp: the fused kernel needs C in {128, 192} and hidden = 4C");
     if (fused != 0 && can) {
       tc_mlp(ctx, ml);
     } else {
@@ -399,8 +399,8 @@ brn_status brn_swin_mlp(int device, int precision, const float* x, const float* 
       GemmArgs g2; g2.x = hd; g2.w = &L2; g2.out = xt; g2.res = xt; g2.lne = ml.lne;
       BRN_CHECK(tc_gemm_supported(g2), 5, "brn_swin_mlp: fc2 shape unsupported");
       tc_gemm(ctx, g2);
+      glue_ln_finalize(ctx, stats, parts, M, M, C, mr);
     }
-    glue_ln_finalize(ctx, stats, parts, M, M, C, mr);
     BRN_CUDA(cudaMemcpyAsync(out, xt.p, (size_t)M * C * 4, cudaMemcpyDeviceToHost, s.stream));
     std::vector<float2> h;
     if (out_mean_rstd) {
@@ -687,6 +687,7 @@ brn_status brn_bench_op(int device, int precision, int kind, int32_t B, int32_t 
       glue_ln_finalize(ctx, stats, 1, (long long)px, (long long)px, C, mr);
       ml.mr = mr; ml.fc1 = &L; ml.fc2 = &L2;
       ml.lne.stats = stats; ml.lne.stride = (long long)px; ml.lne.x16 = ml.x16.p; ml.lne.x16dt = AD; ml.lne.ldx16 = C;
+      ml.mr_out = mr;
       hd = make_view(s.alloc(px * hid * 2), AD, 1, 1, (int)px, hid);
       // (the statistics are not refreshed between iterations: the values drift, the timing does not depend on them)
       if (with_res) launch = [&] { tc_mlp(ctx, ml); };

@@ -145,8 +145,9 @@ struct GemmArgs {
 };
 
 // Fused Swin MLP on the tensor-core path (mlp_tcgen05.cu): xt <- xt + fc2(gelu(fc1(LN(xt)))) with the LayerNorm folded
-// (x16 = raw 16-bit copy of xt, mr = its row statistics) and the next block's statistics emitted (lne; lne.x16 may be
-// x16 itself: a tile's rows are read before they are rewritten).  src/swin.rs:103-107,407.
+// (x16 = raw 16-bit copy of xt, mr = its row statistics).  The kernel writes the updated rows' raw copy to lne.x16 (may
+// be x16 itself) and their (-mean, rstd) to mr_out (may be mr): a tile's rows are read before they are rewritten, and a
+// warp holds whole rows, so there are no partials (lne.stats unused) and no finalize pass.  src/swin.rs:103-107,407.
 struct MlpArgs {
   View x16;                      // [rows, C] 16-bit
   const float2* mr = nullptr;    // [rows] (-mean, rstd)
@@ -154,6 +155,7 @@ struct MlpArgs {
   const LayerW* fc2 = nullptr;
   View xt;                       // [rows, C] fp32 residual stream, updated in place
   LnEmit lne;
+  float2* mr_out = nullptr;
 };
 
 struct DeformArgs {

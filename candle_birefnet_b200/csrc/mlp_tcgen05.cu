@@ -1,23 +1,26 @@
 // Fused Swin MLP (sm_100a):  x <- x + fc2(gelu(fc1(LayerNorm(x))))   (src/swin.rs:103-107 Mlp::forward, :407 the block)
 //
-// for the early stages (C <= 256), where the two GEMMs are bound by their epilogues and by the 4C-wide hidden matrix
+// for the early stages (C <= 192), where the two GEMMs are bound by their epilogues and by the 4C-wide hidden matrix
 // they exchange through HBM (stage 0 of Swin-L at 1024^2, batch 16: 2.0 GB written by fc1 and read again by fc2 per
 // block, for 0.77 TFLOP of work).  One persistent CTA owns a 128-row tile of the token matrix from the raw 16-bit copy
 // of the residual stream to the updated fp32 stream; the hidden activations never leave the SM:
 //
 //   A tile [128 x C] (TMA, resident for the whole tile)
 //   for each 128-wide chunk j of the hidden dimension:
-//     G1: H[j%2] (TMEM, 128 fp32 columns)  = A x W1'[chunk j]^T                     (tcgen05.mma, N = 128, K = C)
-//     E1: H -> registers -> LayerNorm fold (rstd * (acc - mean * colsum) + bias') -> erf-GELU -> 16-bit ->
-//         Hs[j%2] (shared memory, the 128B-swizzled K-major layout TMA would have produced: an A operand)
-//     G2: O (TMEM, C fp32 columns)        += Hs[j%2] x W2[:, chunk j]^T             (tcgen05.mma, N = C, K = 128)
-//   E2: O + bias2 + residual -> fp32 stream, raw 16-bit copy and LayerNorm partials for the next block
-//       (the RES32 + LnEmit epilogue of tc_epilogue.cuh, unchanged)
+//     G1: H (TMEM, 128 fp32 columns)       = A x W1'[chunk j]^T                     (tcgen05.mma, N = 128, K = C)
+//     E1: H -> registers (H is free again) -> LayerNorm fold (rstd * (acc - mean * colsum) + bias') -> erf-GELU ->
+//         16-bit -> Hs[j%2] (shared memory, the 128B-swizzled K-major layout TMA would have produced: an A operand)
+//     G2: O[tile%2] (TMEM, C fp32 columns) += Hs[j%2] x W2[:, chunk j]^T            (tcgen05.mma, N = C, K = 128)
+//   E2: O + bias2 + residual -> fp32 stream, its raw 16-bit copy, and (-mean, rstd) of the new rows for the next
+//       block's folded norm1 (a warp holds whole rows, so the statistics need no partials and no finalize pass)
 //
-// Warp roles: warp 0 = TMA producer (A tile; W1 / W2 K blocks through one mbarrier ring, each CTA of a 2-CTA cluster
-// loading half of every weight block and multicasting it), warp 1 = MMA issuer, warps 2-9 = epilogue (two per TMEM lane
-// quadrant, 64 hidden columns each per chunk).  The issuer runs G1 one chunk ahead of G2, so the tensor pipe works on
-// chunk j+1 while the epilogue warps run GELU on chunk j.
+// Warp roles: warp 0 = TMA producer (A tile; W1 / W2 K blocks into per-block slots, each CTA of a 2-CTA cluster
+// loading half of every weight block and multicasting it), warp 1 = MMA issuer, warps 2-9 = E1 (two per TMEM lane
+// quadrant, 64 hidden columns each per chunk), warps 10-13 = E2 (one per lane quadrant).  The issuer runs G1 one chunk
+// ahead of G2, so the tensor pipe works on chunk j+1 while the E1 warps run GELU on chunk j; O is double buffered, so E2
+// of tile t (latency-bound: fp32 residual from HBM, staging round trip -- as many stall samples as E1 for a quarter of
+// the elements when the same warps ran both, ncu r02) overlaps E1 of tile t+1 on its own warps, with the residual of a
+// 16-column granule requested two granules ahead.
 // Roofline: HBM (A + residual in + residual out + 16-bit copy = 12 C bytes per row) and epilogue issue (4C GELUs per
 // row); tensor time is 16 C^2 flop per row.
 #include <cuda.h>
@@ -37,39 +40,51 @@ CUtensorMap make_tmap_16(const void* base, int dt, int rank, const uint64_t* dim
 int device_sm_count();
 
 constexpr int ML_BM = 128, ML_BK = 64, ML_HC = 128;
-constexpr int ML_EPI_WARPS = 8;
-constexpr int ML_THREADS = 64 + 32 * ML_EPI_WARPS;
+constexpr int ML_E1_WARPS = 8, ML_E2_WARPS = 4;
+constexpr int ML_THREADS = 64 + 32 * (ML_E1_WARPS + ML_E2_WARPS);
 constexpr int ML_AKB = ML_BM * ML_BK * 2;        // 16 KB: 128 rows x one 64-wide K block, 128B swizzle
 constexpr int ML_HS_BYTES = (ML_HC / ML_BK) * ML_AKB;   // one hidden chunk as an A operand (two K blocks)
+constexpr int ML_STAGING = ML_E2_WARPS * EPI_STAGE_BYTES;
 constexpr int ML_SMEM_MAX = 227 * 1024;
+constexpr int ML_RES_DEPTH = 2;                  // residual granules in flight per E2 warp
 
 template <int C>
 struct MlpCfg {
-  static_assert(C % 64 == 0 && C >= 128 && C <= 256, "fused MLP: C in {128, 192, 256}");
+  static_assert(C % 64 == 0 && C >= 128 && C <= 192, "fused MLP: C in {128, 192}");
   static constexpr int KB1 = C / ML_BK, HID = 4 * C, NCH = HID / ML_HC;
-  static constexpr int STAGE = C * ML_BK * 2;     // ring slot: a W2 K block [C x 64]; a W1 block [128 x 64] uses its first 16 KB
-  static constexpr int FIXED = KB1 * ML_AKB + 2 * ML_HS_BYTES + (2 * HID + C) * 4 + 256;
-  static constexpr int NST_FIT = (ML_SMEM_MAX - 1024 - FIXED) / STAGE;
-  static constexpr int NST = NST_FIT > 6 ? 6 : NST_FIT;
-  static constexpr int SMEM = 1024 + FIXED + NST * STAGE;
-  static constexpr int TMEM_O = 2 * ML_HC;        // accumulator columns: H[0], H[1], then O (C columns)
-  static_assert(NST >= 2 && TMEM_O + C <= 512 && NCH % 2 == 0, "fused MLP: shared / tensor memory budget");
+  // weight blocks in flight: one chunk's worth in DEDICATED slots -- KB1 slots of 16 KB for the K blocks of W1[chunk]
+  // ([128 x 64]) and two of C x 128 B for those of W2[:, chunk] ([C x 64]).  Every slot is used once per chunk, so its
+  // refill is requested a whole chunk period before the next use (a 4-deep uniform ring held less than one chunk: the
+  // last W1 block of every chunk was requested only when the first W2 block of the previous one retired, ~1 us of
+  // exposed TMA latency per chunk)
+  static constexpr int W1_SLOT = ML_HC * ML_BK * 2, W2_SLOT = C * ML_BK * 2;
+  static constexpr int NSLOT = KB1 + ML_HC / ML_BK;
+  static constexpr int RING = KB1 * W1_SLOT + (ML_HC / ML_BK) * W2_SLOT;
+  static constexpr int FIXED = KB1 * ML_AKB + 2 * ML_HS_BYTES + ML_STAGING + (2 * HID + C) * 4 + 256;
+  static constexpr int SMEM = 1024 + FIXED + RING;
+  static constexpr int TMEM_O = ML_HC;            // accumulator columns: H, then O[0] and O[1] (C columns each)
+  static_assert(SMEM <= ML_SMEM_MAX && TMEM_O + 2 * C <= 512 && NSLOT <= 6, "fused MLP: shared / tensor memory budget");
 };
 
 struct MlpP {
   long long rows;
   int m_tiles;
-  int in_bf16;
   const float* bias1;     // [4C] fc1 bias with W1 beta folded in
   const float* colsum1;   // [4C] column sums of the rounded gamma-folded W1
   const float* bias2;     // [C]
-  const float2* mr;       // [rows] (-mean, rstd)
-  EpiP epi;               // E2: fp32 residual in place + LnEmit
+  const float2* mr;       // [rows] (-mean, rstd) of the input rows
+  float* xt; int ldx;     // fp32 residual stream, updated in place
+  void* x16; int ldx16;   // raw 16-bit copy of the updated rows
+  float2* mr_out;         // [rows] (-mean, rstd) of the updated rows (may alias mr: a tile's rows are read before E2 writes them)
 };
 
+template <bool BF>
+__device__ __forceinline__ uint32_t mlp_pack(float a, float b) { return BF ? pack_bf16x2(a, b) : pack_f16x2(a, b); }
+
 // eight hidden columns of this thread's row: fold + bias + GELU -> 16-bit, one 16-byte chunk of the A operand
+template <bool BF>
 __device__ __forceinline__ uint4 mlp_gelu8(const uint32_t* v, uint32_t sb, uint32_t scs, unsigned long long nmu2,
-                                           unsigned long long rstd2, int bf16) {
+                                           unsigned long long rstd2) {
   float f[8];
 #pragma unroll
   for (int j = 0; j < 8; j += 4) {
@@ -85,47 +100,46 @@ __device__ __forceinline__ uint4 mlp_gelu8(const uint32_t* v, uint32_t sb, uint3
   }
 #pragma unroll
   for (int j = 0; j < 8; j += 2) gelu_fast2(f[j], f[j + 1]);
-  if (bf16)
-    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-  return make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+  return make_uint4(mlp_pack<BF>(f[0], f[1]), mlp_pack<BF>(f[2], f[3]), mlp_pack<BF>(f[4], f[5]), mlp_pack<BF>(f[6], f[7]));
 }
 
-template <int C, int CL>
+template <int C, int CL, bool BF>
 __global__ void __launch_bounds__(ML_THREADS, 1)
 tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
               const __grid_constant__ CUtensorMap tmW2, const MlpP p) {
   using K = MlpCfg<C>;
-  constexpr int KB1 = K::KB1, HID = K::HID, NCH = K::NCH, NST = K::NST, STAGE = K::STAGE;
+  constexpr int KB1 = K::KB1, HID = K::HID, NCH = K::NCH, NSLOT = K::NSLOT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sHs = sA + KB1 * ML_AKB;
   uint8_t* ring = sHs + 2 * ML_HS_BYTES;
-  float* sB1 = (float*)(ring + NST * STAGE);
+  uint8_t* sStage = ring + K::RING;
+  float* sB1 = (float*)(sStage + ML_STAGING);
   float* sCs1 = sB1 + HID;
   float* sB2 = sCs1 + HID;
   uint64_t* full = (uint64_t*)(sB2 + C);
-  uint64_t* empty = full + NST;
-  uint64_t* afull = empty + NST;
+  uint64_t* empty = full + NSLOT;
+  uint64_t* afull = empty + NSLOT;
   uint64_t* aempty = afull + 1;
-  uint64_t* hfull = aempty + 1;      // [2] G1 of a chunk complete
-  uint64_t* hfree = hfull + 2;       // [2] every epilogue thread holds its part of H in registers
-  uint64_t* hsfull = hfree + 2;      // [2] the 16-bit chunk is in shared memory
+  uint64_t* hfull = aempty + 1;      // G1 of a chunk complete
+  uint64_t* hfree = hfull + 1;       // every E1 thread holds its part of H in registers
+  uint64_t* hsfull = hfree + 1;      // [2] the 16-bit chunk is in shared memory
   uint64_t* hsempty = hsfull + 2;    // [2] G2 has read it
-  uint64_t* ofull = hsempty + 2;
-  uint64_t* ofree = ofull + 1;
-  uint32_t* tmem_slot = (uint32_t*)(ofree + 1);
+  uint64_t* ofull = hsempty + 2;     // [2] all G2 of a tile complete
+  uint64_t* ofree = ofull + 2;       // [2] E2 has read the accumulator
+  uint32_t* tmem_slot = (uint32_t*)(ofree + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NST; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], CL); }
+    for (int s = 0; s < NSLOT; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], CL); }
     ptx::mbar_init(afull, 1); ptx::mbar_init(aempty, 1);
+    ptx::mbar_init(hfull, 1); ptx::mbar_init(hfree, 32 * ML_E1_WARPS);
     for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(&hfull[a], 1); ptx::mbar_init(&hfree[a], 32 * ML_EPI_WARPS);
-      ptx::mbar_init(&hsfull[a], 32 * ML_EPI_WARPS); ptx::mbar_init(&hsempty[a], 1);
+      ptx::mbar_init(&hsfull[a], 32 * ML_E1_WARPS); ptx::mbar_init(&hsempty[a], 1);
+      ptx::mbar_init(&ofull[a], 1); ptx::mbar_init(&ofree[a], 32 * ML_E2_WARPS);
     }
-    ptx::mbar_init(ofull, 1); ptx::mbar_init(ofree, 32 * ML_EPI_WARPS);
     ptx::fence_barrier_init();
   }
   for (int t = threadIdx.x; t < HID; t += ML_THREADS) { sB1[t] = __ldg(p.bias1 + t); sCs1[t] = __ldg(p.colsum1 + t); }
@@ -144,11 +158,16 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
   const int n_iter = cid < pairs ? (pairs - cid + ncl - 1) / ncl : 0;
   const int G = n_iter * NCH;
+  // global row of tile-row `row` of this CTA's tile `it` (-1: past the end)
+  auto grow_of = [&](int it, int row) -> long long {
+    if (it >= n_iter) return -1;
+    const long long r = (long long)((cid + it * ncl) * CL + rank) * ML_BM + row;
+    return r < p.rows ? r : -1;
+  };
 
   if (warp == 0) {
     if (ptx::elect_one()) {
       // ===== TMA producer: per global chunk g the K blocks of W1[chunk g], then those of W2[:, chunk g-1] =====
-      int stage = 0; uint32_t phase = 0;
       constexpr int w1_rows = ML_HC / CL, w2_rows = C / CL;
       for (int g = 0; g <= G; ++g) {
         if (g < G) {
@@ -160,24 +179,25 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
             for (int kb = 0; kb < KB1; ++kb) ptx::tma_load_2d(sA + kb * ML_AKB, &tmA, afull, kb * ML_BK, m_tile * ML_BM);
           }
+#pragma unroll
           for (int kb = 0; kb < KB1; ++kb) {
-            ptx::mbar_wait(&empty[stage], phase ^ 1);
-            ptx::mbar_expect_tx(&full[stage], ML_HC * ML_BK * 2);
-            uint8_t* dst = ring + stage * STAGE + rank * w1_rows * (ML_BK * 2);
-            if (CL > 1) ptx::tma_load_2d_mc(dst, &tmW1, &full[stage], kb * ML_BK, j * ML_HC + rank * w1_rows, (uint16_t)((1u << CL) - 1));
-            else ptx::tma_load_2d(dst, &tmW1, &full[stage], kb * ML_BK, j * ML_HC);
-            if (++stage == NST) { stage = 0; phase ^= 1; }
+            ptx::mbar_wait(&empty[kb], (g & 1) ^ 1);
+            ptx::mbar_expect_tx(&full[kb], K::W1_SLOT);
+            uint8_t* dst = ring + kb * K::W1_SLOT + rank * w1_rows * (ML_BK * 2);
+            if (CL > 1) ptx::tma_load_2d_mc(dst, &tmW1, &full[kb], kb * ML_BK, j * ML_HC + rank * w1_rows, (uint16_t)((1u << CL) - 1));
+            else ptx::tma_load_2d(dst, &tmW1, &full[kb], kb * ML_BK, j * ML_HC);
           }
         }
         if (g >= 1) {
           const int jp = (g - 1) % NCH;
+#pragma unroll
           for (int kb = 0; kb < ML_HC / ML_BK; ++kb) {
-            ptx::mbar_wait(&empty[stage], phase ^ 1);
-            ptx::mbar_expect_tx(&full[stage], C * ML_BK * 2);
-            uint8_t* dst = ring + stage * STAGE + rank * w2_rows * (ML_BK * 2);
-            if (CL > 1) ptx::tma_load_2d_mc(dst, &tmW2, &full[stage], jp * ML_HC + kb * ML_BK, rank * w2_rows, (uint16_t)((1u << CL) - 1));
-            else ptx::tma_load_2d(dst, &tmW2, &full[stage], jp * ML_HC + kb * ML_BK, 0);
-            if (++stage == NST) { stage = 0; phase ^= 1; }
+            const int slot = KB1 + kb;
+            ptx::mbar_wait(&empty[slot], ((g - 1) & 1) ^ 1);
+            ptx::mbar_expect_tx(&full[slot], K::W2_SLOT);
+            uint8_t* dst = ring + KB1 * K::W1_SLOT + kb * K::W2_SLOT + rank * w2_rows * (ML_BK * 2);
+            if (CL > 1) ptx::tma_load_2d_mc(dst, &tmW2, &full[slot], jp * ML_HC + kb * ML_BK, rank * w2_rows, (uint16_t)((1u << CL) - 1));
+            else ptx::tma_load_2d(dst, &tmW2, &full[slot], jp * ML_HC + kb * ML_BK, 0);
           }
         }
       }
@@ -185,116 +205,185 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     if (ptx::elect_one()) {
       // ===== MMA issuer =====
-      const uint32_t idesc1 = ptx::make_idesc_16(ML_BM, ML_HC, 0, 0, p.in_bf16);
-      const uint32_t idesc2 = ptx::make_idesc_16(ML_BM, C, 0, 0, p.in_bf16);
-      int stage = 0; uint32_t phase = 0;
-      auto next_stage = [&] { if (++stage == NST) { stage = 0; phase ^= 1; } };
+      const uint32_t idesc1 = ptx::make_idesc_16(ML_BM, ML_HC, 0, 0, BF ? 1 : 0);
+      const uint32_t idesc2 = ptx::make_idesc_16(ML_BM, C, 0, 0, BF ? 1 : 0);
       auto release = [&](uint64_t* bar) {
         if (CL > 1) ptx::umma_commit_mc(bar, (uint16_t)((1u << CL) - 1)); else ptx::umma_commit(bar);
       };
       for (int g = 0; g <= G; ++g) {
         if (g < G) {
-          // G1(g): H[g & 1] = A x W1[chunk]^T
-          const int it = g / NCH, j = g - it * NCH, hb = g & 1;
-          const uint32_t ph = (g >> 1) & 1;
+          // G1(g): H = A x W1[chunk]^T, as soon as the E1 warps hold chunk g-1 in registers
+          const int it = g / NCH, j = g - it * NCH;
           if (j == 0) ptx::mbar_wait(afull, it & 1);
-          ptx::mbar_wait(&hfree[hb], ph ^ 1);
+          ptx::mbar_wait(hfree, (g & 1) ^ 1);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + hb * ML_HC;
+#pragma unroll
           for (int kb = 0; kb < KB1; ++kb) {
-            ptx::mbar_wait(&full[stage], phase);
+            ptx::mbar_wait(&full[kb], g & 1);
             ptx::tc_fence_after();
             const uint64_t a_desc = ptx::make_smem_desc(ptx::smem_u32(sA + kb * ML_AKB), 16, 1024, ptx::SW_128B);
-            const uint64_t b_desc = ptx::make_smem_desc(ptx::smem_u32(ring + stage * STAGE), 16, 1024, ptx::SW_128B);
+            const uint64_t b_desc = ptx::make_smem_desc(ptx::smem_u32(ring + kb * K::W1_SLOT), 16, 1024, ptx::SW_128B);
 #pragma unroll
-            for (int k = 0; k < ML_BK / 16; ++k) ptx::umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc1, (kb | k) != 0);
-            release(&empty[stage]);
-            next_stage();
+            for (int k = 0; k < ML_BK / 16; ++k) ptx::umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc1, (kb | k) != 0);
+            release(&empty[kb]);
           }
-          ptx::umma_commit(&hfull[hb]);
+          ptx::umma_commit(hfull);
           if (j == NCH - 1) ptx::umma_commit(aempty);       // the A tile may be overwritten by the next one
         }
         if (g >= 1) {
-          // G2(g - 1): O += Hs[(g - 1) & 1] x W2[:, chunk]^T
-          const int gp = g - 1, itp = gp / NCH, jp = gp - itp * NCH, hb = gp & 1;
-          const uint32_t ph = (gp >> 1) & 1;
-          if (jp == 0) ptx::mbar_wait(ofree, (itp & 1) ^ 1);   // E2 of the previous tile has read O
-          ptx::mbar_wait(&hsfull[hb], ph);
+          // G2(g - 1): O[tile & 1] += Hs[(g - 1) & 1] x W2[:, chunk]^T
+          const int gp = g - 1, itp = gp / NCH, jp = gp - itp * NCH, hb = gp & 1, ob = itp & 1;
+          if (jp == 0) ptx::mbar_wait(&ofree[ob], ((itp >> 1) & 1) ^ 1);   // E2 of tile itp - 2 has read O[ob]
+          ptx::mbar_wait(&hsfull[hb], (gp >> 1) & 1);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + K::TMEM_O;
+          const uint32_t d_tmem = tmem_base + K::TMEM_O + ob * C;
+#pragma unroll
           for (int kb = 0; kb < ML_HC / ML_BK; ++kb) {
-            ptx::mbar_wait(&full[stage], phase);
+            const int slot = KB1 + kb;
+            ptx::mbar_wait(&full[slot], gp & 1);
             ptx::tc_fence_after();
             const uint64_t a_desc = ptx::make_smem_desc(ptx::smem_u32(sHs + hb * ML_HS_BYTES + kb * ML_AKB), 16, 1024, ptx::SW_128B);
-            const uint64_t b_desc = ptx::make_smem_desc(ptx::smem_u32(ring + stage * STAGE), 16, 1024, ptx::SW_128B);
+            const uint64_t b_desc = ptx::make_smem_desc(ptx::smem_u32(ring + KB1 * K::W1_SLOT + kb * K::W2_SLOT), 16, 1024, ptx::SW_128B);
 #pragma unroll
             for (int k = 0; k < ML_BK / 16; ++k) ptx::umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc2, (jp | kb | k) != 0);
-            release(&empty[stage]);
-            next_stage();
+            release(&empty[slot]);
           }
           ptx::umma_commit(&hsempty[hb]);
-          if (jp == NCH - 1) ptx::umma_commit(ofull);
+          if (jp == NCH - 1) ptx::umma_commit(&ofull[ob]);
         }
       }
     }
-  } else {
-    // ===== epilogue warps: warp % 4 = TMEM lane quadrant, (warp - 2) / 4 = column half =====
+  } else if (warp < 2 + ML_E1_WARPS) {
+    // ===== E1 warps: warp % 4 = TMEM lane quadrant, (warp - 2) / 4 = half of the chunk's 128 hidden columns =====
     const int q = warp & 3;
     const int part = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int sw = row & 7;
     // this thread's row inside K block `part` of a hidden chunk (128-byte rows, 8-row swizzle atoms of 1 KB)
     const uint32_t hs_row = ptx::smem_u32(sHs) + part * ML_AKB + (row >> 3) * 1024 + (row & 7) * 128;
-    // E2 staging block: the first 2 KB of this warp's OWN 4 KB of Hs[0] (both hidden buffers are idle while O is drained,
-    // and nobody else ever touches these rows)
-    const uint32_t stage = ptx::smem_u32(sHs) + part * ML_AKB + q * 4096;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    constexpr int nch = C / 16, per = (nch + 1) / 2;
-    const int c0 = min(part * per, nch) * 16, c1 = min((part + 1) * per, nch) * 16;
-    auto grow_of = [&](int it) -> long long {
-      if (it >= n_iter) return -1;
-      const long long r = (long long)((cid + it * ncl) * CL + rank) * ML_BM + row;
-      return r < p.rows ? r : -1;
-    };
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + part * 64;
     float2 mr_next = make_float2(0.f, 1.f);
-    { const long long r0 = grow_of(0); if (r0 >= 0) mr_next = __ldg(p.mr + r0); }
+    { const long long r0 = grow_of(0, row); if (r0 >= 0) mr_next = __ldg(p.mr + r0); }
     for (int it = 0; it < n_iter; ++it) {
-      const long long grow = grow_of(it);
       const unsigned long long nmu2 = pk2(mr_next.x, mr_next.x), rstd2 = pk2(mr_next.y, mr_next.y);
-      { const long long rn = grow_of(it + 1); if (rn >= 0) mr_next = __ldg(p.mr + rn); }
+      { const long long rn = grow_of(it + 1, row); if (rn >= 0) mr_next = __ldg(p.mr + rn); }
       for (int j = 0; j < NCH; ++j) {
         const int g = it * NCH + j, hb = g & 1;
-        const uint32_t ph = (g >> 1) & 1;
-        ptx::mbar_wait(&hfull[hb], ph);
+        ptx::mbar_wait(hfull, g & 1);
         ptx::tc_fence_after();
         uint32_t va[32], vb[32];
-        const uint32_t taddr = lane_base + hb * ML_HC + part * 64;
         ptx::tmem_ld32(taddr, va);
         ptx::tmem_ld32(taddr + 32, vb);
         tmem_wait_dep(va);
         tmem_wait_dep(vb);
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&hfree[hb]);                   // G1 of chunk g + 2 may overwrite H[hb]
-        ptx::mbar_wait(&hsempty[hb], ph ^ 1);           // G2 of chunk g - 2 has read Hs[hb]
+        ptx::mbar_arrive(hfree);                            // G1 of chunk g + 1 may overwrite H
+        ptx::mbar_wait(&hsempty[hb], ((g >> 1) & 1) ^ 1);   // G2 of chunk g - 2 has read Hs[hb]
         const uint32_t cb = (uint32_t)(j * ML_HC + part * 64) * 4;
         const uint32_t sb = ptx::smem_u32(sB1) + cb, scs = ptx::smem_u32(sCs1) + cb;
         const uint32_t dst = hs_row + hb * ML_HS_BYTES;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          ptx::sts128(dst + ((c ^ sw) << 4), mlp_gelu8(va + 8 * c, sb + c * 32, scs + c * 32, nmu2, rstd2, p.in_bf16));
+          ptx::sts128(dst + ((c ^ sw) << 4), mlp_gelu8<BF>(va + 8 * c, sb + c * 32, scs + c * 32, nmu2, rstd2));
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          ptx::sts128(dst + (((4 + c) ^ sw) << 4), mlp_gelu8(vb + 8 * c, sb + (4 + c) * 32, scs + (4 + c) * 32, nmu2, rstd2, p.in_bf16));
-        ptx::fence_proxy_async_smem();                  // generic-proxy stores -> visible to the MMA's operand reads
+          ptx::sts128(dst + (((4 + c) ^ sw) << 4), mlp_gelu8<BF>(vb + 8 * c, sb + (4 + c) * 32, scs + (4 + c) * 32, nmu2, rstd2));
+        ptx::fence_proxy_async_smem();                      // generic-proxy stores -> visible to the MMA's operand reads
         ptx::mbar_arrive(&hsfull[hb]);
       }
-      // E2: O + bias2 + residual -> fp32 stream (+ 16-bit copy + LayerNorm partials)
-      ptx::mbar_wait(ofull, it & 1);
+    }
+  } else {
+    // ===== E2 warps: one per TMEM lane quadrant, all C columns of its 32 rows in 16-column granules =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t stage = ptx::smem_u32(sStage) + (warp - 2 - ML_E1_WARPS) * EPI_STAGE_BYTES;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + K::TMEM_O;
+    const int kb4 = lane & 3, sw_a = (lane >> 1) & 3;
+    constexpr int NG = C / 16, D = ML_RES_DEPTH;
+    // phase-B rows of this lane (instruction i covers tile rows q*32 + i*8 + lane/4), current and next tile
+    // (32-bit row indices: the host checks rows < 2^31)
+    int orow_b[4], orow_n[4];
+    auto rows_of = [&](int it, int (&o)[4]) {
+      const int gr = (int)grow_of(it, row);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = __shfl_sync(0xffffffffu, gr, i * 8 + (lane >> 2));
+    };
+    uint4 rq[D][4];
+    auto res_issue = [&](int gran, const int (&o)[4], uint4 (&r)[4]) {      // 8 rows x 64 B per instruction
+      const int col = gran * 16 + kb4 * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = o[i] >= 0 ? ldg_l2_256(p.xt + (long long)o[i] * p.ldx + col) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    rows_of(0, orow_b);
+#pragma unroll
+    for (int d = 0; d < D; ++d) res_issue(d, orow_b, rq[d]);
+    for (int it = 0; it < n_iter; ++it) {
+      rows_of(it + 1, orow_n);
+      float es[4], eq[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { es[i] = 0.f; eq[i] = 0.f; }
+      const uint32_t o_addr = lane_base + (it & 1) * C;
+      ptx::mbar_wait(&ofull[it & 1], (it >> 1) & 1);
       ptx::tc_fence_after();
-      epi_warp<ACT_NONE, true, 1, false, false, true>(p.epi, lane_base + K::TMEM_O, 0, c0, c1, grow, ptx::smem_u32(sB2),
-                                                      stage, lane, 0.f, 1.f, 0, part);
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(ofree);
+      uint32_t vo[16];
+      tmem_ld16_raw(o_addr, vo);
+#pragma unroll
+      for (int gran = 0; gran < NG; ++gran) {
+        const int c = gran * 16;
+        tmem_wait_dep(vo);
+        // phase A: this thread's row, + bias2, into the XOR-swizzled staging block
+        const uint32_t my_row = stage + lane * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint4 bv = ptx::lds128(ptx::smem_u32(sB2) + (c + 4 * k) * 4);
+          float f0 = __uint_as_float(vo[4 * k]), f1 = __uint_as_float(vo[4 * k + 1]), f2 = __uint_as_float(vo[4 * k + 2]), f3 = __uint_as_float(vo[4 * k + 3]);
+          add2(f0, f1, __uint_as_float(bv.x), __uint_as_float(bv.y));
+          add2(f2, f3, __uint_as_float(bv.z), __uint_as_float(bv.w));
+          ptx::sts128(my_row + ((k ^ sw_a) << 4), make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)));
+        }
+        if (gran + 1 < NG) {
+          tmem_ld16_raw(o_addr + c + 16, vo);
+        } else {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&ofree[it & 1]);      // the accumulator is in registers / staged: G2 of tile it + 2 may start
+        }
+        __syncwarp();
+        // phase B: 8 rows x 64 bytes per instruction: + residual, statistics, 16-bit copy, fp32 store
+        uint4 (&r)[4] = rq[gran % D];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2);
+          uint4 val = ptx::lds128(stage + rr * 64 + ((kb4 ^ ((rr >> 1) & 3)) << 4));
+          float4* fv = reinterpret_cast<float4*>(&val);
+          const float4* rv = reinterpret_cast<const float4*>(&r[i]);
+          add2(fv->x, fv->y, rv->x, rv->y); add2(fv->z, fv->w, rv->z, rv->w);
+          es[i] += (fv->x + fv->y) + (fv->z + fv->w);
+          eq[i] = fmaf(fv->x, fv->x, fmaf(fv->y, fv->y, fmaf(fv->z, fv->z, fmaf(fv->w, fv->w, eq[i]))));
+          if (orow_b[i] >= 0) {
+            *reinterpret_cast<uint2*>((uint16_t*)p.x16 + (long long)orow_b[i] * p.ldx16 + c + kb4 * 4) =
+                make_uint2(mlp_pack<BF>(fv->x, fv->y), mlp_pack<BF>(fv->z, fv->w));
+            *reinterpret_cast<uint4*>(p.xt + (long long)orow_b[i] * p.ldx + c + kb4 * 4) = val;
+          }
+        }
+        // this slot's next granule: D granules ahead, rolling over into the next tile's rows
+        if (gran + D < NG) res_issue(gran + D, orow_b, r);
+        else res_issue(gran + D - NG, orow_n, r);
+        __syncwarp();      // the staging block is rewritten only after every lane has read it
+      }
+      // the four lanes of a row hold its partial sums: fixed-order butterfly, then (-mean, rstd) exactly as
+      // ln_finalize_kernel forms them
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        es[i] += __shfl_xor_sync(0xffffffffu, es[i], 1); eq[i] += __shfl_xor_sync(0xffffffffu, eq[i], 1);
+        es[i] += __shfl_xor_sync(0xffffffffu, es[i], 2); eq[i] += __shfl_xor_sync(0xffffffffu, eq[i], 2);
+        if (kb4 == 0 && orow_b[i] >= 0) {
+          const float mu = es[i] * (1.0f / (float)C);
+          const float var = fmaxf(fmaf(-mu, mu, eq[i] * (1.0f / (float)C)), 0.f);
+          p.mr_out[orow_b[i]] = make_float2(-mu, rsqrtf(var + 1e-5f));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) orow_b[i] = orow_n[i];
     }
   }
   ptx::tc_fence_before();
@@ -307,15 +396,16 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // host side
 // ------------------------------------------------------------------------------------------------
 bool tc_mlp_supported(const MlpArgs& a) {
-  if (!a.fc1 || !a.fc2 || !a.mr || !a.lne.stats || !a.lne.x16) return false;
+  if (!a.fc1 || !a.fc2 || !a.mr || !a.mr_out || !a.lne.x16) return false;
   const int C = a.x16.C;
-  if (C != 128 && C != 192 && C != 256) return false;
+  if (C != 128 && C != 192) return false;
   if (a.x16.dt != BF16 && a.x16.dt != F16) return false;
   const LayerW &w1 = *a.fc1, &w2 = *a.fc2;
   if (w1.taps() != 1 || w2.taps() != 1 || w1.Cin != C || w1.cin_pad != C || w1.N != 4 * C || w2.Cin != 4 * C ||
       w2.cin_pad != 4 * C || w2.N != C)
     return false;
   if (!w1.w16(a.x16.dt) || !w2.w16(a.x16.dt) || !w1.colsum(a.x16.dt) || !w1.bias) return false;
+  if (a.x16.rows() >= (1ll << 31) - 256) return false;
   if (a.x16.B != 1 || a.x16.H != 1 || a.x16.ld % 8 != 0 || ((uintptr_t)a.x16.p & 15)) return false;
   if (a.xt.dt != F32 || a.xt.rows() != a.x16.rows() || a.xt.C != C || a.xt.ld % 4 != 0 || ((uintptr_t)a.xt.p & 15)) return false;
   if (a.lne.x16dt != a.x16.dt || a.lne.ldx16 % 4 != 0 || ((uintptr_t)a.lne.x16 & 7)) return false;
@@ -355,7 +445,8 @@ static void launch_mlp(const LaunchCtx& ctx, const MlpArgs& a, MlpP& p) {
     cfg.attrs = attr; cfg.numAttrs = 1;
     BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW1, tmW2, p));
   };
-  if (CL == 2) launch(tc_mlp_kernel<C, 2>); else launch(tc_mlp_kernel<C, 1>);
+  if (dt == BF16) { if (CL == 2) launch(tc_mlp_kernel<C, 2, true>); else launch(tc_mlp_kernel<C, 1, true>); }
+  else { if (CL == 2) launch(tc_mlp_kernel<C, 2, false>); else launch(tc_mlp_kernel<C, 1, false>); }
   BRN_CUDA(cudaGetLastError());
 }
 
@@ -367,24 +458,17 @@ void tc_mlp(const LaunchCtx& ctx, const MlpArgs& a) {
   MlpP p{};
   p.rows = a.x16.rows();
   p.m_tiles = (int)((p.rows + ML_BM - 1) / ML_BM);
-  p.in_bf16 = a.x16.dt == BF16 ? 1 : 0;
   p.bias1 = a.fc1->bias; p.colsum1 = a.fc1->colsum(a.x16.dt); p.bias2 = a.fc2->bias;
   p.mr = a.mr;
-  EpiP e{};
-  e.N = C; e.act = ACT_NONE;
-  e.res = a.xt.p; e.resdt = F32; e.ldres = a.xt.ld;
-  e.out = a.xt.p; e.odt = F32; e.ldo = a.xt.ld;
-  e.vec = 1;
-  e.lne_stats = a.lne.stats; e.lne_stride = a.lne.stride; e.x16 = a.lne.x16; e.x16dt = a.lne.x16dt; e.ldx16 = a.lne.ldx16;
-  p.epi = e;
+  p.xt = (float*)a.xt.p; p.ldx = a.xt.ld;
+  p.x16 = a.lne.x16; p.ldx16 = a.lne.ldx16; p.mr_out = a.mr_out;
   const double rows = (double)p.rows;
   char desc[96] = "";
   if (ctx.kt) snprintf(desc, sizeof desc, "mlp M=%lld C=%d hid=%d tiles=%d", (long long)p.rows, C, 4 * C, p.m_tiles);
   KScope ks(ctx, KC_GEMM_TC, 2.0 * rows * C * 4 * C * 2, rows * C * (2 + 4 + 4 + 2) + 2.0 * 4 * C * C * 2, desc);
   switch (C) {
     case 128: launch_mlp<128>(ctx, a, p); break;
-    case 192: launch_mlp<192>(ctx, a, p); break;
-    default: launch_mlp<256>(ctx, a, p); break;
+    default: launch_mlp<192>(ctx, a, p); break;
   }
 }
 

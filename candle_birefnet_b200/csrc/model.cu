@@ -679,10 +679,9 @@ void Model::run_backbone(LaunchCtx& ctx, const float* img, int B, int H, int W, 
       // x + fc2(gelu(fc1(norm2(x))))  (src/swin.rs:407)
       // Early stages (C <= 256, mlp_ratio 4): one fused kernel, the hidden activations stay on the SM (mlp_tcgen05.cu)
       MlpArgs ml; ml.x16 = x16; ml.mr = mr; ml.fc1 = &bw.fc1_f; ml.fc2 = &bw.fc2; ml.xt = xt;
-      ml.lne.stats = stats; ml.lne.stride = Tt; ml.lne.x16 = x16.p; ml.lne.x16dt = AD; ml.lne.ldx16 = Ci;
+      ml.lne.x16 = x16.p; ml.lne.x16dt = AD; ml.lne.ldx16 = Ci; ml.mr_out = mr;
       if (fold && cfg.mlp_ratio == 4 && !env_flag("BRN_MLP_UNFUSED") && tc_mlp_supported(ml)) {
-        tc_mlp(ctx, ml);
-        glue_ln_finalize(ctx, stats, parts, Tt, Tt, Ci, mr);
+        tc_mlp(ctx, ml);       // writes the next block's (-mean, rstd) itself
       } else {
         View hd = make_view(arena.alloc((size_t)Tt * cfg.mlp_ratio * Ci * dsize(AD)), AD, 1, 1, (int)Tt, cfg.mlp_ratio * Ci);
         if (fold) {

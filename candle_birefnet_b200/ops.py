@@ -46,7 +46,7 @@ def swin_mlp(x, gamma, beta, w1, b1, w2, b2, precision: str = "fp16", fused: int
              with_stats: bool = False):
     """x + fc2(gelu_erf(fc1(LayerNorm(x)))): `Mlp::forward` inside the Swin block (src/swin.rs:103-107,407).
 
-    fused=1 demands the single-kernel path (C in {128, 192, 256}, hidden = 4C), 0 the two-GEMM path, -1 the model's own
+    fused=1 demands the single-kernel path (C in {128, 192}, hidden = 4C), 0 the two-GEMM path, -1 the model's own
     choice.  with_stats: also return the [M, 2] (mean, rstd) the epilogue emits for the next block's folded norm1."""
     x, gamma, beta, w1, b1, w2, b2 = (_f32(t) for t in (x, gamma, beta, w1, b1, w2, b2))
     M, Cc = x.shape

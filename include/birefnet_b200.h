@@ -258,7 +258,7 @@ BRN_API brn_status brn_ln_linear(int device, int precision, const float* x, cons
 /* The MLP half of a Swin block, out = x + fc2(gelu_erf(fc1(LayerNorm(x; gamma, beta, eps 1e-5)))): Mlp::forward
  * (src/swin.rs:103-107) as SwinTransformerBlock::forward calls it (src/swin.rs:407).  x, out: HOST fp32 [M, C];
  * w1 [hidden, C], b1 [hidden], w2 [C, hidden], b2 [C] (b1 / b2 may be NULL).  precision BRN_PREC_BF16 / BRN_PREC_FP16.
- * fused: 1 = the single-kernel path of the early stages (C in {128, 192, 256}, hidden = 4C: hidden activations stay in
+ * fused: 1 = the single-kernel path of the early stages (C in {128, 192}, hidden = 4C: hidden activations stay in
  * shared / tensor memory), 0 = two GEMMs through HBM, -1 = what the model itself would run for this shape.
  * out_mean_rstd (optional, HOST [M, 2]): per-row (mean, rstd) of `out` as emitted for the next block's folded norm1. */
 BRN_API brn_status brn_swin_mlp(int device, int precision, const float* x, const float* gamma, const float* beta,

@@ -155,8 +155,8 @@ def test_ln_linear_fold(M, N, K, mean_over_std, precision, act):
     assert err < tol, (err, tol)
 
 
-@pytest.mark.parametrize("M,C", [(1000, 192), (148 * 128 + 205, 192), (149 * 128, 192), (777, 128), (150 * 128 + 1, 128), (640, 256),
-                                 (148 * 128 + 64, 256)])
+@pytest.mark.parametrize("M,C", [(1000, 192), (148 * 128 + 205, 192), (149 * 128, 192), (777, 128), (150 * 128 + 1, 128), (100, 192),
+                                 (3 * 148 * 128 + 5, 192)])
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 def test_swin_mlp_fused(M, C, precision):
     """The fused MLP kernel of the early stages (mlp_tcgen05.cu) against x + fc2(gelu(fc1(LN(x)))) in fp64
