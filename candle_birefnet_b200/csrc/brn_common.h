@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -84,6 +85,9 @@ struct LayerW {
   float* colsum_bf16 = nullptr;
   float* colsum_fp16 = nullptr;
   const float* colsum(int dt) const { return dt == F16 ? colsum_fp16 : colsum_bf16; }
+  // host copies for the folded layers: [colsum_bf16 (N) | colsum_fp16 (N) | bias (N)] -- the fused MLP kernel takes its
+  // per-column constants as kernel parameters (constant bank) instead of reading them through the shared-memory pipe
+  std::shared_ptr<std::vector<float>> h_fold;
   int taps() const { return kh * kw; }
 };
 

@@ -60,17 +60,23 @@ struct MlpCfg {
   static constexpr int W1_SLOT = ML_HC * ML_BK * 2, W2_SLOT = C * ML_BK * 2;
   static constexpr int NSLOT = KB1 + ML_HC / ML_BK;
   static constexpr int RING = KB1 * W1_SLOT + (ML_HC / ML_BK) * W2_SLOT;
-  static constexpr int FIXED = KB1 * ML_AKB + 2 * ML_HS_BYTES + ML_STAGING + (2 * HID + C) * 4 + 256;
+  static constexpr int FIXED = KB1 * ML_AKB + 2 * ML_HS_BYTES + ML_STAGING + C * 4 + 256;
   static constexpr int SMEM = 1024 + FIXED + RING;
   static constexpr int TMEM_O = ML_HC;            // accumulator columns: H, then O[0] and O[1] (C columns each)
   static_assert(SMEM <= ML_SMEM_MAX && TMEM_O + 2 * C <= 512 && NSLOT <= 6, "fused MLP: shared / tensor memory budget");
 };
 
+// fc1's per-column constants as a kernel parameter (constant bank): every thread needs every column's pair once per
+// chunk, and as broadcast LDS.128 those reads were 57 % of the kernel's shared-memory wavefronts on a shared-memory pipe
+// that the MMA operand reads and the TMA fills already keep busy (ncu r02: 77 % LSU data-pipe + 25 % tensor reads).
+// cb[i] = (colsum[2i], colsum[2i+1], bias'[2i], bias'[2i+1]): column sums of the rounded gamma-folded W1; fc1 bias with
+// W1 beta folded in.
+template <int C>
+struct MlpConst { float4 cb[2 * C]; };
+
 struct MlpP {
   long long rows;
   int m_tiles;
-  const float* bias1;     // [4C] fc1 bias with W1 beta folded in
-  const float* colsum1;   // [4C] column sums of the rounded gamma-folded W1
   const float* bias2;     // [C]
   const float2* mr;       // [rows] (-mean, rstd) of the input rows
   float* xt; int ldx;     // fp32 residual stream, updated in place
@@ -81,32 +87,65 @@ struct MlpP {
 template <bool BF>
 __device__ __forceinline__ uint32_t mlp_pack(float a, float b) { return BF ? pack_bf16x2(a, b) : pack_f16x2(a, b); }
 
-// eight hidden columns of this thread's row: fold + bias + GELU -> 16-bit, one 16-byte chunk of the A operand
-template <bool BF>
-__device__ __forceinline__ uint4 mlp_gelu8(const uint32_t* v, uint32_t sb, uint32_t scs, unsigned long long nmu2,
-                                           unsigned long long rstd2) {
-  float f[8];
+// Eight hidden columns of this thread's row: fold + bias + GELU -> 16-bit, one 16-byte chunk of the A operand -- in
+// three steps, so that the caller can put the polynomial of the NEXT eight columns between the exponentials of a group
+// and their first use (with two E1 warps per scheduler the MUFU latency was the largest single stall, ncu r02: a third
+// of the E1 samples sat on the FFMA2 right after the four MUFU.EX2).
+struct MlpG8 {
+  unsigned long long na[4], l[4];     // -|x| pairs; log2 q(|x|) pairs (gelu_fast2, tc_epilogue.cuh)
+  float relu[8];
+};
+__device__ __forceinline__ void mlp_g8_poly(MlpG8& g, const uint32_t* v, const float4* cb, unsigned long long nmu2,
+                                            unsigned long long rstd2) {
 #pragma unroll
-  for (int j = 0; j < 8; j += 4) {
-    const uint4 bv = ptx::lds128(sb + j * 4), cv = ptx::lds128(scs + j * 4);
-    unsigned long long t0 = fma2(nmu2, pk2(__uint_as_float(cv.x), __uint_as_float(cv.y)),
-                                 pk2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
-    unsigned long long t1 = fma2(nmu2, pk2(__uint_as_float(cv.z), __uint_as_float(cv.w)),
-                                 pk2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
-    t0 = fma2(rstd2, t0, pk2(__uint_as_float(bv.x), __uint_as_float(bv.y)));
-    t1 = fma2(rstd2, t1, pk2(__uint_as_float(bv.z), __uint_as_float(bv.w)));
-    upk2(t0, f[j], f[j + 1]);
-    upk2(t1, f[j + 2], f[j + 3]);
+  for (int j = 0; j < 2; ++j) {
+    const float4 ca = cb[2 * j], cc = cb[2 * j + 1];      // (colsum pair, bias pair) of columns 4j..4j+1, 4j+2..4j+3
+    unsigned long long t0 = fma2(nmu2, pk2(ca.x, ca.y), pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])));
+    unsigned long long t1 = fma2(nmu2, pk2(cc.x, cc.y), pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+    t0 = fma2(rstd2, t0, pk2(ca.z, ca.w));
+    t1 = fma2(rstd2, t1, pk2(cc.z, cc.w));
+    float x0, x1, x2, x3;
+    upk2(t0, x0, x1);
+    upk2(t1, x2, x3);
+    g.na[2 * j] = pk2(-fabsf(x0), -fabsf(x1));
+    g.na[2 * j + 1] = pk2(-fabsf(x2), -fabsf(x3));
+    g.relu[4 * j] = fmaxf(x0, 0.f); g.relu[4 * j + 1] = fmaxf(x1, 0.f);
+    g.relu[4 * j + 2] = fmaxf(x2, 0.f); g.relu[4 * j + 3] = fmaxf(x3, 0.f);
   }
 #pragma unroll
-  for (int j = 0; j < 8; j += 2) gelu_fast2(f[j], f[j + 1]);
-  return make_uint4(mlp_pack<BF>(f[0], f[1]), mlp_pack<BF>(f[2], f[3]), mlp_pack<BF>(f[4], f[5]), mlp_pack<BF>(f[6], f[7]));
+  for (int i = 0; i < 4; ++i) {
+    unsigned long long l = fma2(g.na[i], pk2(0.0004732935631182045f, 0.0004732935631182045f),
+                                pk2(0.007084455341100693f, 0.007084455341100693f));
+    l = fma2(g.na[i], l, pk2(0.05182714760303497f, 0.05182714760303497f));
+    l = fma2(g.na[i], l, pk2(-0.4599926769733429f, -0.4599926769733429f));
+    l = fma2(g.na[i], l, pk2(1.1507877111434937f, 1.1507877111434937f));
+    g.l[i] = fma2(g.na[i], l, pk2(-1.000037670135498f, -1.000037670135498f));
+  }
+}
+__device__ __forceinline__ void mlp_g8_exp(const MlpG8& g, float (&e)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float l0, l1;
+    upk2(g.l[i], l0, l1);
+    e[2 * i] = ex2_approx(l0); e[2 * i + 1] = ex2_approx(l1);
+  }
+}
+template <bool BF>
+__device__ __forceinline__ uint4 mlp_g8_pack(const MlpG8& g, const float (&e)[8]) {
+  uint32_t h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float r0, r1;
+    upk2(fma2(g.na[i], pk2(e[2 * i], e[2 * i + 1]), pk2(g.relu[2 * i], g.relu[2 * i + 1])), r0, r1);
+    h[i] = mlp_pack<BF>(r0, r1);
+  }
+  return make_uint4(h[0], h[1], h[2], h[3]);
 }
 
 template <int C, int CL, bool BF>
 __global__ void __launch_bounds__(ML_THREADS, 1)
 tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
-              const __grid_constant__ CUtensorMap tmW2, const MlpP p) {
+              const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ MlpConst<C> cst, const MlpP p) {
   using K = MlpCfg<C>;
   constexpr int KB1 = K::KB1, HID = K::HID, NCH = K::NCH, NSLOT = K::NSLOT;
   extern __shared__ uint8_t smem_raw[];
@@ -115,9 +154,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint8_t* sHs = sA + KB1 * ML_AKB;
   uint8_t* ring = sHs + 2 * ML_HS_BYTES;
   uint8_t* sStage = ring + K::RING;
-  float* sB1 = (float*)(sStage + ML_STAGING);
-  float* sCs1 = sB1 + HID;
-  float* sB2 = sCs1 + HID;
+  float* sB2 = (float*)(sStage + ML_STAGING);
   uint64_t* full = (uint64_t*)(sB2 + C);
   uint64_t* empty = full + NSLOT;
   uint64_t* afull = empty + NSLOT;
@@ -142,7 +179,6 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     ptx::fence_barrier_init();
   }
-  for (int t = threadIdx.x; t < HID; t += ML_THREADS) { sB1[t] = __ldg(p.bias1 + t); sCs1[t] = __ldg(p.colsum1 + t); }
   for (int t = threadIdx.x; t < C; t += ML_THREADS) sB2[t] = p.bias2 ? __ldg(p.bias2 + t) : 0.f;
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmW1); ptx::prefetch_tmap(&tmW2); }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -279,15 +315,21 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         ptx::tc_fence_before();
         ptx::mbar_arrive(hfree);                            // G1 of chunk g + 1 may overwrite H
         ptx::mbar_wait(&hsempty[hb], ((g >> 1) & 1) ^ 1);   // G2 of chunk g - 2 has read Hs[hb]
-        const uint32_t cb = (uint32_t)(j * ML_HC + part * 64) * 4;
-        const uint32_t sb = ptx::smem_u32(sB1) + cb, scs = ptx::smem_u32(sCs1) + cb;
+        const float4* cb = cst.cb + (j * ML_HC + part * 64) / 2;     // warp-uniform index: constant-cache loads
         const uint32_t dst = hs_row + hb * ML_HS_BYTES;
+        // eight groups of eight columns, software-pipelined: exp(k) issued, poly(k+1) computed, then pack(k)
+        MlpG8 ga, gb;
+        mlp_g8_poly(ga, va, cb, nmu2, rstd2);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          ptx::sts128(dst + ((c ^ sw) << 4), mlp_gelu8<BF>(va + 8 * c, sb + c * 32, scs + c * 32, nmu2, rstd2));
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          ptx::sts128(dst + (((4 + c) ^ sw) << 4), mlp_gelu8<BF>(vb + 8 * c, sb + (4 + c) * 32, scs + (4 + c) * 32, nmu2, rstd2));
+        for (int c = 0; c < 8; c += 2) {
+          float e[8];
+          mlp_g8_exp(ga, e);
+          mlp_g8_poly(gb, (c + 1 < 4 ? va : vb) + 8 * ((c + 1) & 3), cb + (c + 1) * 4, nmu2, rstd2);
+          ptx::sts128(dst + ((c ^ sw) << 4), mlp_g8_pack<BF>(ga, e));
+          mlp_g8_exp(gb, e);
+          if (c + 2 < 8) mlp_g8_poly(ga, (c + 2 < 4 ? va : vb) + 8 * ((c + 2) & 3), cb + (c + 2) * 4, nmu2, rstd2);
+          ptx::sts128(dst + (((c + 1) ^ sw) << 4), mlp_g8_pack<BF>(gb, e));
+        }
         ptx::fence_proxy_async_smem();                      // generic-proxy stores -> visible to the MMA's operand reads
         ptx::mbar_arrive(&hsfull[hb]);
       }
@@ -404,7 +446,7 @@ bool tc_mlp_supported(const MlpArgs& a) {
   if (w1.taps() != 1 || w2.taps() != 1 || w1.Cin != C || w1.cin_pad != C || w1.N != 4 * C || w2.Cin != 4 * C ||
       w2.cin_pad != 4 * C || w2.N != C)
     return false;
-  if (!w1.w16(a.x16.dt) || !w2.w16(a.x16.dt) || !w1.colsum(a.x16.dt) || !w1.bias) return false;
+  if (!w1.w16(a.x16.dt) || !w2.w16(a.x16.dt) || !w1.h_fold || w1.h_fold->size() != (size_t)3 * w1.N) return false;
   if (a.x16.rows() >= (1ll << 31) - 256) return false;
   if (a.x16.B != 1 || a.x16.H != 1 || a.x16.ld % 8 != 0 || ((uintptr_t)a.x16.p & 15)) return false;
   if (a.xt.dt != F32 || a.xt.rows() != a.x16.rows() || a.xt.C != C || a.xt.ld % 4 != 0 || ((uintptr_t)a.xt.p & 15)) return false;
@@ -431,6 +473,13 @@ static void launch_mlp(const LaunchCtx& ctx, const MlpArgs& a, MlpP& p) {
   uint64_t w2str[1] = {(uint64_t)K::HID * 2};
   uint32_t w2box[2] = {(uint32_t)ML_BK, (uint32_t)(C / CL)};
   CUtensorMap tmW2 = make_tmap_16(a.fc2->w16(dt), dt, 2, w2dims, w2str, w2box, CU_TENSOR_MAP_SWIZZLE_128B);
+  MlpConst<C> cst;
+  {
+    const std::vector<float>& hf = *a.fc1->h_fold;
+    const float* cs = hf.data() + (dt == F16 ? K::HID : 0);
+    const float* b1 = hf.data() + 2 * K::HID;
+    for (int i = 0; i < 2 * C; ++i) cst.cb[i] = make_float4(cs[2 * i], cs[2 * i + 1], b1[2 * i], b1[2 * i + 1]);
+  }
   auto launch = [&](auto kern) {
     BRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
     const int pairs = (p.m_tiles + CL - 1) / CL;
@@ -443,7 +492,7 @@ static void launch_mlp(const LaunchCtx& ctx, const MlpArgs& a, MlpP& p) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW1, tmW2, p));
+    BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW1, tmW2, cst, p));
   };
   if (dt == BF16) { if (CL == 2) launch(tc_mlp_kernel<C, 2, true>); else launch(tc_mlp_kernel<C, 1, true>); }
   else { if (CL == 2) launch(tc_mlp_kernel<C, 2, false>); else launch(tc_mlp_kernel<C, 1, false>); }
@@ -458,7 +507,7 @@ void tc_mlp(const LaunchCtx& ctx, const MlpArgs& a) {
   MlpP p{};
   p.rows = a.x16.rows();
   p.m_tiles = (int)((p.rows + ML_BM - 1) / ML_BM);
-  p.bias1 = a.fc1->bias; p.colsum1 = a.fc1->colsum(a.x16.dt); p.bias2 = a.fc2->bias;
+  p.bias2 = a.fc2->bias;
   p.mr = a.mr;
   p.xt = (float*)a.xt.p; p.ldx = a.xt.ld;
   p.x16 = a.lne.x16; p.ldx16 = a.lne.ldx16; p.mr_out = a.mr_out;

@@ -257,6 +257,11 @@ LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w, con
     BRN_CUDA(cudaMemcpy(L.colsum_bf16, cb.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
     BRN_CUDA(cudaMalloc(&L.colsum_fp16, (size_t)N * 4)); allocs.push_back(L.colsum_fp16);
     BRN_CUDA(cudaMemcpy(L.colsum_fp16, cf.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+    L.h_fold = std::make_shared<std::vector<float>>((size_t)3 * N, 0.f);
+    for (int n = 0; n < N; ++n) {
+      (*L.h_fold)[n] = cb[n]; (*L.h_fold)[(size_t)N + n] = cf[n];
+      if (bias) (*L.h_fold)[(size_t)2 * N + n] = bias[n];
+    }
   }
   BRN_CUDA(cudaMalloc(&L.w_bf16, wbf.size() * 2)); allocs.push_back(L.w_bf16);
   BRN_CUDA(cudaMemcpy(L.w_bf16, wbf.data(), wbf.size() * 2, cudaMemcpyHostToDevice));
