@@ -88,6 +88,7 @@ struct LayerW {
   // host copies for the folded layers: [colsum_bf16 (N) | colsum_fp16 (N) | bias (N)] -- the fused MLP kernel takes its
   // per-column constants as kernel parameters (constant bank) instead of reading them through the shared-memory pipe
   std::shared_ptr<std::vector<float>> h_fold;
+  std::shared_ptr<std::vector<float>> h_bias;     // host copy of `bias` (layers with N <= 1024)
   int taps() const { return kh * kw; }
 };
 

@@ -400,7 +400,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// rank-`rank` bf16/fp16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides[0] is implicit.
+// rank-`rank` bf16 / fp16 / fp32 tensor map, zero OOB fill.  dims/strides innermost first; strides[0] is implicit.
 CUtensorMap make_tmap_16(const void* base, int dt, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                          const uint32_t* box, CUtensorMapSwizzle swz) {
   CUtensorMap m;
@@ -408,7 +408,8 @@ CUtensorMap make_tmap_16(const void* base, int dt, int rank, const uint64_t* dim
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = get_encode()(&m, dt == F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+  const CUtensorMapDataType cdt = dt == F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : dt == F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = get_encode()(&m, cdt, rank, const_cast<void*>(base), gd, gs, bx, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BRN_CHECK(r == CUDA_SUCCESS, 2, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));

@@ -18,9 +18,12 @@
 // loading half of every weight block and multicasting it), warp 1 = MMA issuer, warps 2-9 = E1 (two per TMEM lane
 // quadrant, 64 hidden columns each per chunk), warps 10-13 = E2 (one per lane quadrant).  The issuer runs G1 one chunk
 // ahead of G2, so the tensor pipe works on chunk j+1 while the E1 warps run GELU on chunk j; O is double buffered, so E2
-// of tile t (latency-bound: fp32 residual from HBM, staging round trip -- as many stall samples as E1 for a quarter of
-// the elements when the same warps ran both, ncu r02) overlaps E1 of tile t+1 on its own warps, with the residual of a
-// 16-column granule requested two granules ahead.
+// of tile t overlaps E1 of tile t+1 on its own warps.  E2 is one latency chain per warp, so everything that can be
+// asynchronous is: the fp32 residual of a 16-column granule (32 rows x 64 B) arrives by TMA in a three-deep ring, the
+// updated rows and their 16-bit copy leave by TMA store from double-buffered blocks, and the thread = row layout of
+// tcgen05.ld is kept end to end (the TMA engine does the transposition the staging round trip used to do; row
+// statistics are per thread).  A/B r02: with register loads / STG.128 stores and one LDS round trip per granule the E2
+// warps set the kernel's pace (E2 without its global traffic 960 -> 652 us; GELU math removed only 993 -> 960 us).
 // Roofline: HBM (A + residual in + residual out + 16-bit copy = 12 C bytes per row) and epilogue issue (4C GELUs per
 // row); tensor time is 16 C^2 flop per row.
 #include <cuda.h>
@@ -44,9 +47,11 @@ constexpr int ML_E1_WARPS = 8, ML_E2_WARPS = 4;
 constexpr int ML_THREADS = 64 + 32 * (ML_E1_WARPS + ML_E2_WARPS);
 constexpr int ML_AKB = ML_BM * ML_BK * 2;        // 16 KB: 128 rows x one 64-wide K block, 128B swizzle
 constexpr int ML_HS_BYTES = (ML_HC / ML_BK) * ML_AKB;   // one hidden chunk as an A operand (two K blocks)
-constexpr int ML_STAGING = ML_E2_WARPS * EPI_STAGE_BYTES;
 constexpr int ML_SMEM_MAX = 227 * 1024;
-constexpr int ML_RES_DEPTH = 2;                  // residual granules in flight per E2 warp
+constexpr int ML_RES_DEPTH = 3;                  // residual granules in flight per E2 warp
+// per E2 warp: residual ring (32 rows x 64 B each), two fp32 output blocks, two 16-bit output blocks (32 rows x 32 B)
+constexpr int ML_E2_WARP_BYTES = ML_RES_DEPTH * 2048 + 2 * 2048 + 2 * 1024;
+constexpr int ML_E2_BYTES = ML_E2_WARPS * ML_E2_WARP_BYTES;
 
 template <int C>
 struct MlpCfg {
@@ -60,7 +65,7 @@ struct MlpCfg {
   static constexpr int W1_SLOT = ML_HC * ML_BK * 2, W2_SLOT = C * ML_BK * 2;
   static constexpr int NSLOT = KB1 + ML_HC / ML_BK;
   static constexpr int RING = KB1 * W1_SLOT + (ML_HC / ML_BK) * W2_SLOT;
-  static constexpr int FIXED = KB1 * ML_AKB + 2 * ML_HS_BYTES + ML_STAGING + C * 4 + 256;
+  static constexpr int FIXED = KB1 * ML_AKB + ML_HS_BYTES + ML_E2_BYTES + 512;
   static constexpr int SMEM = 1024 + FIXED + RING;
   static constexpr int TMEM_O = ML_HC;            // accumulator columns: H, then O[0] and O[1] (C columns each)
   static_assert(SMEM <= ML_SMEM_MAX && TMEM_O + 2 * C <= 512 && NSLOT <= 6, "fused MLP: shared / tensor memory budget");
@@ -72,15 +77,13 @@ struct MlpCfg {
 // cb[i] = (colsum[2i], colsum[2i+1], bias'[2i], bias'[2i+1]): column sums of the rounded gamma-folded W1; fc1 bias with
 // W1 beta folded in.
 template <int C>
-struct MlpConst { float4 cb[2 * C]; };
+struct MlpConst { float4 cb[2 * C]; float b2[C]; };     // + fc2 bias
 
 struct MlpP {
   long long rows;
   int m_tiles;
-  const float* bias2;     // [C]
   const float2* mr;       // [rows] (-mean, rstd) of the input rows
-  float* xt; int ldx;     // fp32 residual stream, updated in place
-  void* x16; int ldx16;   // raw 16-bit copy of the updated rows
+  const float* xt;        // fp32 residual stream (L2 prefetch only; E2 goes through the tensor maps)
   float2* mr_out;         // [rows] (-mean, rstd) of the updated rows (may alias mr: a tile's rows are read before E2 writes them)
 };
 
@@ -112,6 +115,11 @@ __device__ __forceinline__ void mlp_g8_poly(MlpG8& g, const uint32_t* v, const f
     g.relu[4 * j] = fmaxf(x0, 0.f); g.relu[4 * j + 1] = fmaxf(x1, 0.f);
     g.relu[4 * j + 2] = fmaxf(x2, 0.f); g.relu[4 * j + 3] = fmaxf(x3, 0.f);
   }
+#if defined(BRN_MLP_EXP) && BRN_MLP_EXP >= 1      // A/B experiment builds (scripts/r02_gpu_p.sh): no polynomial
+#pragma unroll
+  for (int i = 0; i < 4; ++i) g.l[i] = g.na[i];
+  return;
+#endif
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     unsigned long long l = fma2(g.na[i], pk2(0.0004732935631182045f, 0.0004732935631182045f),
@@ -123,6 +131,11 @@ __device__ __forceinline__ void mlp_g8_poly(MlpG8& g, const uint32_t* v, const f
   }
 }
 __device__ __forceinline__ void mlp_g8_exp(const MlpG8& g, float (&e)[8]) {
+#if defined(BRN_MLP_EXP) && BRN_MLP_EXP >= 1      // ... and no exponential
+#pragma unroll
+  for (int i = 0; i < 4; ++i) upk2(g.l[i], e[2 * i], e[2 * i + 1]);
+  return;
+#endif
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float l0, l1;
@@ -145,27 +158,28 @@ __device__ __forceinline__ uint4 mlp_g8_pack(const MlpG8& g, const float (&e)[8]
 template <int C, int CL, bool BF>
 __global__ void __launch_bounds__(ML_THREADS, 1)
 tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
-              const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ MlpConst<C> cst, const MlpP p) {
+              const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
+              const __grid_constant__ CUtensorMap tmX16, const __grid_constant__ MlpConst<C> cst, const MlpP p) {
   using K = MlpCfg<C>;
   constexpr int KB1 = K::KB1, HID = K::HID, NCH = K::NCH, NSLOT = K::NSLOT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sHs = sA + KB1 * ML_AKB;
-  uint8_t* ring = sHs + 2 * ML_HS_BYTES;
-  uint8_t* sStage = ring + K::RING;
-  float* sB2 = (float*)(sStage + ML_STAGING);
-  uint64_t* full = (uint64_t*)(sB2 + C);
+  uint8_t* ring = sHs + ML_HS_BYTES;
+  uint8_t* sE2 = ring + K::RING;
+  uint64_t* full = (uint64_t*)(sE2 + ML_E2_BYTES);
   uint64_t* empty = full + NSLOT;
   uint64_t* afull = empty + NSLOT;
   uint64_t* aempty = afull + 1;
   uint64_t* hfull = aempty + 1;      // G1 of a chunk complete
   uint64_t* hfree = hfull + 1;       // every E1 thread holds its part of H in registers
-  uint64_t* hsfull = hfree + 1;      // [2] the 16-bit chunk is in shared memory
-  uint64_t* hsempty = hsfull + 2;    // [2] G2 has read it
-  uint64_t* ofull = hsempty + 2;     // [2] all G2 of a tile complete
+  uint64_t* hsfull = hfree + 1;      // the 16-bit chunk is in shared memory
+  uint64_t* hsempty = hsfull + 1;    // G2 has read it
+  uint64_t* ofull = hsempty + 1;     // [2] all G2 of a tile complete
   uint64_t* ofree = ofull + 2;       // [2] E2 has read the accumulator
-  uint32_t* tmem_slot = (uint32_t*)(ofree + 2);
+  uint64_t* rfull = ofree + 2;       // [E2 warps][ML_RES_DEPTH] residual granule landed
+  uint32_t* tmem_slot = (uint32_t*)(rfull + ML_E2_WARPS * ML_RES_DEPTH);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
@@ -173,14 +187,14 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     for (int s = 0; s < NSLOT; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], CL); }
     ptx::mbar_init(afull, 1); ptx::mbar_init(aempty, 1);
     ptx::mbar_init(hfull, 1); ptx::mbar_init(hfree, 32 * ML_E1_WARPS);
-    for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(&hsfull[a], 32 * ML_E1_WARPS); ptx::mbar_init(&hsempty[a], 1);
-      ptx::mbar_init(&ofull[a], 1); ptx::mbar_init(&ofree[a], 32 * ML_E2_WARPS);
-    }
+    ptx::mbar_init(hsfull, 32 * ML_E1_WARPS); ptx::mbar_init(hsempty, 1);
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&ofull[a], 1); ptx::mbar_init(&ofree[a], 32 * ML_E2_WARPS); }
+    for (int a = 0; a < ML_E2_WARPS * ML_RES_DEPTH; ++a) ptx::mbar_init(&rfull[a], 1);
     ptx::fence_barrier_init();
   }
-  for (int t = threadIdx.x; t < C; t += ML_THREADS) sB2[t] = p.bias2 ? __ldg(p.bias2 + t) : 0.f;
-  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmW1); ptx::prefetch_tmap(&tmW2); }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmW1); ptx::prefetch_tmap(&tmW2); ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmX16);
+  }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
   ptx::tc_fence_before();
   __syncthreads();
@@ -214,6 +228,11 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             ptx::mbar_expect_tx(afull, KB1 * ML_AKB);
 #pragma unroll
             for (int kb = 0; kb < KB1; ++kb) ptx::tma_load_2d(sA + kb * ML_AKB, &tmA, afull, kb * ML_BK, m_tile * ML_BM);
+            // the tile's fp32 residual rows (contiguous) -> L2 now: E2 reads them a tile period later with two granules
+            // in flight per warp, which covers an L2 hit but not an HBM miss (A/B r02: E2 without its global traffic
+            // 960 -> 652 us, GELU math removed 993 -> 960 us)
+            const long long r0 = (long long)m_tile * ML_BM, nr = min((long long)ML_BM, p.rows - r0);
+            if (p.xt && nr > 0) ptx::bulk_prefetch_l2(p.xt + r0 * C, (uint32_t)(nr * C * 4));
           }
 #pragma unroll
           for (int kb = 0; kb < KB1; ++kb) {
@@ -267,10 +286,10 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (j == NCH - 1) ptx::umma_commit(aempty);       // the A tile may be overwritten by the next one
         }
         if (g >= 1) {
-          // G2(g - 1): O[tile & 1] += Hs[(g - 1) & 1] x W2[:, chunk]^T
-          const int gp = g - 1, itp = gp / NCH, jp = gp - itp * NCH, hb = gp & 1, ob = itp & 1;
+          // G2(g - 1): O[tile & 1] += Hs x W2[:, chunk]^T
+          const int gp = g - 1, itp = gp / NCH, jp = gp - itp * NCH, ob = itp & 1;
           if (jp == 0) ptx::mbar_wait(&ofree[ob], ((itp >> 1) & 1) ^ 1);   // E2 of tile itp - 2 has read O[ob]
-          ptx::mbar_wait(&hsfull[hb], (gp >> 1) & 1);
+          ptx::mbar_wait(hsfull, gp & 1);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + K::TMEM_O + ob * C;
 #pragma unroll
@@ -278,13 +297,13 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const int slot = KB1 + kb;
             ptx::mbar_wait(&full[slot], gp & 1);
             ptx::tc_fence_after();
-            const uint64_t a_desc = ptx::make_smem_desc(ptx::smem_u32(sHs + hb * ML_HS_BYTES + kb * ML_AKB), 16, 1024, ptx::SW_128B);
+            const uint64_t a_desc = ptx::make_smem_desc(ptx::smem_u32(sHs + kb * ML_AKB), 16, 1024, ptx::SW_128B);
             const uint64_t b_desc = ptx::make_smem_desc(ptx::smem_u32(ring + KB1 * K::W1_SLOT + kb * K::W2_SLOT), 16, 1024, ptx::SW_128B);
 #pragma unroll
             for (int k = 0; k < ML_BK / 16; ++k) ptx::umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc2, (jp | kb | k) != 0);
             release(&empty[slot]);
           }
-          ptx::umma_commit(&hsempty[hb]);
+          ptx::umma_commit(hsempty);
           if (jp == NCH - 1) ptx::umma_commit(&ofull[ob]);
         }
       }
@@ -304,7 +323,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const unsigned long long nmu2 = pk2(mr_next.x, mr_next.x), rstd2 = pk2(mr_next.y, mr_next.y);
       { const long long rn = grow_of(it + 1, row); if (rn >= 0) mr_next = __ldg(p.mr + rn); }
       for (int j = 0; j < NCH; ++j) {
-        const int g = it * NCH + j, hb = g & 1;
+        const int g = it * NCH + j;
         ptx::mbar_wait(hfull, g & 1);
         ptx::tc_fence_after();
         uint32_t va[32], vb[32];
@@ -314,10 +333,11 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tmem_wait_dep(vb);
         ptx::tc_fence_before();
         ptx::mbar_arrive(hfree);                            // G1 of chunk g + 1 may overwrite H
-        ptx::mbar_wait(&hsempty[hb], ((g >> 1) & 1) ^ 1);   // G2 of chunk g - 2 has read Hs[hb]
         const float4* cb = cst.cb + (j * ML_HC + part * 64) / 2;     // warp-uniform index: constant-cache loads
-        const uint32_t dst = hs_row + hb * ML_HS_BYTES;
-        // eight groups of eight columns, software-pipelined: exp(k) issued, poly(k+1) computed, then pack(k)
+        // eight groups of eight columns, software-pipelined: exp(k) issued, poly(k+1) computed, then pack(k).  The
+        // packed chunk stays in registers until G2 of the PREVIOUS chunk has read the (single) hidden buffer -- that
+        // MMA runs while this math does.
+        uint4 out[8];
         MlpG8 ga, gb;
         mlp_g8_poly(ga, va, cb, nmu2, rstd2);
 #pragma unroll
@@ -325,108 +345,104 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           float e[8];
           mlp_g8_exp(ga, e);
           mlp_g8_poly(gb, (c + 1 < 4 ? va : vb) + 8 * ((c + 1) & 3), cb + (c + 1) * 4, nmu2, rstd2);
-          ptx::sts128(dst + ((c ^ sw) << 4), mlp_g8_pack<BF>(ga, e));
+          out[c] = mlp_g8_pack<BF>(ga, e);
           mlp_g8_exp(gb, e);
           if (c + 2 < 8) mlp_g8_poly(ga, (c + 2 < 4 ? va : vb) + 8 * ((c + 2) & 3), cb + (c + 2) * 4, nmu2, rstd2);
-          ptx::sts128(dst + (((c + 1) ^ sw) << 4), mlp_g8_pack<BF>(gb, e));
+          out[c + 1] = mlp_g8_pack<BF>(gb, e);
         }
+        ptx::mbar_wait(hsempty, (g & 1) ^ 1);               // G2 of chunk g - 1 has read Hs
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ptx::sts128(hs_row + ((c ^ sw) << 4), out[c]);
         ptx::fence_proxy_async_smem();                      // generic-proxy stores -> visible to the MMA's operand reads
-        ptx::mbar_arrive(&hsfull[hb]);
+        ptx::mbar_arrive(hsfull);
       }
     }
   } else {
-    // ===== E2 warps: one per TMEM lane quadrant, all C columns of its 32 rows in 16-column granules =====
-    const int q = warp & 3;
+    // ===== E2 warps: one per TMEM lane quadrant, all C columns of its 32 rows in 16-column granules, thread = row =====
+    const int q = warp & 3, ew = warp - 2 - ML_E1_WARPS;
     const int row = q * 32 + lane;
-    const uint32_t stage = ptx::smem_u32(sStage) + (warp - 2 - ML_E1_WARPS) * EPI_STAGE_BYTES;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + K::TMEM_O;
-    const int kb4 = lane & 3, sw_a = (lane >> 1) & 3;
+    const uint32_t base = ptx::smem_u32(sE2) + ew * ML_E2_WARP_BYTES;
     constexpr int NG = C / 16, D = ML_RES_DEPTH;
-    // phase-B rows of this lane (instruction i covers tile rows q*32 + i*8 + lane/4), current and next tile
-    // (32-bit row indices: the host checks rows < 2^31)
-    int orow_b[4], orow_n[4];
-    auto rows_of = [&](int it, int (&o)[4]) {
-      const int gr = (int)grow_of(it, row);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = __shfl_sync(0xffffffffu, gr, i * 8 + (lane >> 2));
+    // residual slot d: base + d * 2 KB; fp32 output block b: base + (D + b) * 2 KB; 16-bit block b: base + (D + 2) * 2 KB + b * 1 KB.
+    // fp32 blocks are [32 rows][64 B] with CU_TENSOR_MAP_SWIZZLE_64B (16-byte chunk k of row r at (k ^ ((r >> 1) & 3)) * 16:
+    // conflict-free for thread = row), 16-bit blocks [32 rows][32 B] unswizzled.
+    const uint32_t sw_a = (lane >> 1) & 3;
+    const uint32_t res_row = base + lane * 64, out_row = base + D * 2048 + lane * 64, x16_row = base + (D + 2) * 2048 + lane * 32;
+    uint64_t* rf = rfull + ew * D;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + K::TMEM_O;
+    auto tile_row0 = [&](int it) { return ((cid + it * ncl) * CL + rank) * ML_BM + q * 32; };   // past-the-end tiles: TMA zero-fills / clips
+    const int NT = n_iter * NG;            // granules of this warp
+    // residual of granule n -> slot n % D (lane 0)
+    auto res_issue = [&](int n) {
+      if (n >= NT) return;
+      const int it = n / NG, gran = n - it * NG, d = n % D;
+      ptx::mbar_expect_tx(&rf[d], 2048);
+      ptx::tma_load_2d((void*)(sE2 + ew * ML_E2_WARP_BYTES + d * 2048), &tmX, &rf[d], gran * 16, tile_row0(it));
     };
-    uint4 rq[D][4];
-    auto res_issue = [&](int gran, const int (&o)[4], uint4 (&r)[4]) {      // 8 rows x 64 B per instruction
-      const int col = gran * 16 + kb4 * 4;
+    if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = o[i] >= 0 ? ldg_l2_256(p.xt + (long long)o[i] * p.ldx + col) : make_uint4(0u, 0u, 0u, 0u);
-    };
-    rows_of(0, orow_b);
-#pragma unroll
-    for (int d = 0; d < D; ++d) res_issue(d, orow_b, rq[d]);
+      for (int d = 0; d < D; ++d) res_issue(d);
+    }
+    int n = 0;
     for (int it = 0; it < n_iter; ++it) {
-      rows_of(it + 1, orow_n);
-      float es[4], eq[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { es[i] = 0.f; eq[i] = 0.f; }
+      float es = 0.f, eq = 0.f;
       const uint32_t o_addr = lane_base + (it & 1) * C;
+      const int row0 = tile_row0(it);
       ptx::mbar_wait(&ofull[it & 1], (it >> 1) & 1);
       ptx::tc_fence_after();
       uint32_t vo[16];
       tmem_ld16_raw(o_addr, vo);
 #pragma unroll
-      for (int gran = 0; gran < NG; ++gran) {
-        const int c = gran * 16;
+      for (int gran = 0; gran < NG; ++gran, ++n) {
+        const int c = gran * 16, d = n % D, b = n & 1;
+        // the TMA stores issued two granules ago have read output blocks b
+        if (lane == 0) ptx::tma_store_wait_read_n<1>();
+        __syncwarp();
+        ptx::mbar_wait(&rf[d], (n / D) & 1);
         tmem_wait_dep(vo);
-        // phase A: this thread's row, + bias2, into the XOR-swizzled staging block
-        const uint32_t my_row = stage + lane * 64;
+        float f[16];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint4 bv = ptx::lds128(ptx::smem_u32(sB2) + (c + 4 * k) * 4);
-          float f0 = __uint_as_float(vo[4 * k]), f1 = __uint_as_float(vo[4 * k + 1]), f2 = __uint_as_float(vo[4 * k + 2]), f3 = __uint_as_float(vo[4 * k + 3]);
-          add2(f0, f1, __uint_as_float(bv.x), __uint_as_float(bv.y));
-          add2(f2, f3, __uint_as_float(bv.z), __uint_as_float(bv.w));
-          ptx::sts128(my_row + ((k ^ sw_a) << 4), make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)));
+          const uint4 r = ptx::lds128(res_row + d * 2048 + ((k ^ sw_a) << 4));
+          f[4 * k] = __uint_as_float(vo[4 * k]) + cst.b2[c + 4 * k] + __uint_as_float(r.x);
+          f[4 * k + 1] = __uint_as_float(vo[4 * k + 1]) + cst.b2[c + 4 * k + 1] + __uint_as_float(r.y);
+          f[4 * k + 2] = __uint_as_float(vo[4 * k + 2]) + cst.b2[c + 4 * k + 2] + __uint_as_float(r.z);
+          f[4 * k + 3] = __uint_as_float(vo[4 * k + 3]) + cst.b2[c + 4 * k + 3] + __uint_as_float(r.w);
         }
         if (gran + 1 < NG) {
           tmem_ld16_raw(o_addr + c + 16, vo);
         } else {
           ptx::tc_fence_before();
-          ptx::mbar_arrive(&ofree[it & 1]);      // the accumulator is in registers / staged: G2 of tile it + 2 may start
+          ptx::mbar_arrive(&ofree[it & 1]);      // the accumulator is in registers: G2 of tile it + 2 may start
         }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { es += f[k]; eq = fmaf(f[k], f[k], eq); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::sts128(out_row + b * 2048 + ((k ^ sw_a) << 4), make_uint4(__float_as_uint(f[4 * k]), __float_as_uint(f[4 * k + 1]),
+                                                                           __float_as_uint(f[4 * k + 2]), __float_as_uint(f[4 * k + 3])));
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          ptx::sts128(x16_row + b * 1024 + k * 16, make_uint4(mlp_pack<BF>(f[8 * k], f[8 * k + 1]), mlp_pack<BF>(f[8 * k + 2], f[8 * k + 3]),
+                                                               mlp_pack<BF>(f[8 * k + 4], f[8 * k + 5]), mlp_pack<BF>(f[8 * k + 6], f[8 * k + 7])));
+        ptx::fence_proxy_async_smem();       // staged blocks -> visible to the TMA engine; residual slot d: reads done
         __syncwarp();
-        // phase B: 8 rows x 64 bytes per instruction: + residual, statistics, 16-bit copy, fp32 store
-        uint4 (&r)[4] = rq[gran % D];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = i * 8 + (lane >> 2);
-          uint4 val = ptx::lds128(stage + rr * 64 + ((kb4 ^ ((rr >> 1) & 3)) << 4));
-          float4* fv = reinterpret_cast<float4*>(&val);
-          const float4* rv = reinterpret_cast<const float4*>(&r[i]);
-          add2(fv->x, fv->y, rv->x, rv->y); add2(fv->z, fv->w, rv->z, rv->w);
-          es[i] += (fv->x + fv->y) + (fv->z + fv->w);
-          eq[i] = fmaf(fv->x, fv->x, fmaf(fv->y, fv->y, fmaf(fv->z, fv->z, fmaf(fv->w, fv->w, eq[i]))));
-          if (orow_b[i] >= 0) {
-            *reinterpret_cast<uint2*>((uint16_t*)p.x16 + (long long)orow_b[i] * p.ldx16 + c + kb4 * 4) =
-                make_uint2(mlp_pack<BF>(fv->x, fv->y), mlp_pack<BF>(fv->z, fv->w));
-            *reinterpret_cast<uint4*>(p.xt + (long long)orow_b[i] * p.ldx + c + kb4 * 4) = val;
-          }
-        }
-        // this slot's next granule: D granules ahead, rolling over into the next tile's rows
-        if (gran + D < NG) res_issue(gran + D, orow_b, r);
-        else res_issue(gran + D - NG, orow_n, r);
-        __syncwarp();      // the staging block is rewritten only after every lane has read it
-      }
-      // the four lanes of a row hold its partial sums: fixed-order butterfly, then (-mean, rstd) exactly as
-      // ln_finalize_kernel forms them
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        es[i] += __shfl_xor_sync(0xffffffffu, es[i], 1); eq[i] += __shfl_xor_sync(0xffffffffu, eq[i], 1);
-        es[i] += __shfl_xor_sync(0xffffffffu, es[i], 2); eq[i] += __shfl_xor_sync(0xffffffffu, eq[i], 2);
-        if (kb4 == 0 && orow_b[i] >= 0) {
-          const float mu = es[i] * (1.0f / (float)C);
-          const float var = fmaxf(fmaf(-mu, mu, eq[i] * (1.0f / (float)C)), 0.f);
-          p.mr_out[orow_b[i]] = make_float2(-mu, rsqrtf(var + 1e-5f));
+        if (lane == 0) {
+          ptx::tma_store_2d(&tmX, base + (D + b) * 2048, c, row0);
+          ptx::tma_store_2d(&tmX16, base + (D + 2) * 2048 + b * 1024, c, row0);
+          ptx::tma_store_commit();
+          res_issue(n + D);                  // slot d again, D granules ahead (rolls over into the next tile)
         }
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) orow_b[i] = orow_n[i];
+      // (-mean, rstd) of the updated row exactly as ln_finalize_kernel forms them
+      const long long gr = grow_of(it, row);
+      if (gr >= 0) {
+        const float mu = es * (1.0f / (float)C);
+        const float var = fmaxf(fmaf(-mu, mu, eq * (1.0f / (float)C)), 0.f);
+        p.mr_out[gr] = make_float2(-mu, rsqrtf(var + 1e-5f));
+      }
     }
+    if (lane == 0) ptx::tma_store_wait_all();      // this warp's bulk stores are performed before the CTA retires
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -449,8 +465,9 @@ bool tc_mlp_supported(const MlpArgs& a) {
   if (!w1.w16(a.x16.dt) || !w2.w16(a.x16.dt) || !w1.h_fold || w1.h_fold->size() != (size_t)3 * w1.N) return false;
   if (a.x16.rows() >= (1ll << 31) - 256) return false;
   if (a.x16.B != 1 || a.x16.H != 1 || a.x16.ld % 8 != 0 || ((uintptr_t)a.x16.p & 15)) return false;
+  if (w2.bias && (!w2.h_bias || w2.h_bias->size() != (size_t)C)) return false;
   if (a.xt.dt != F32 || a.xt.rows() != a.x16.rows() || a.xt.C != C || a.xt.ld % 4 != 0 || ((uintptr_t)a.xt.p & 15)) return false;
-  if (a.lne.x16dt != a.x16.dt || a.lne.ldx16 % 4 != 0 || ((uintptr_t)a.lne.x16 & 7)) return false;
+  if (a.lne.x16dt != a.x16.dt || a.lne.ldx16 % 8 != 0 || ((uintptr_t)a.lne.x16 & 15)) return false;
   return true;
 }
 
@@ -479,7 +496,15 @@ static void launch_mlp(const LaunchCtx& ctx, const MlpArgs& a, MlpP& p) {
     const float* cs = hf.data() + (dt == F16 ? K::HID : 0);
     const float* b1 = hf.data() + 2 * K::HID;
     for (int i = 0; i < 2 * C; ++i) cst.cb[i] = make_float4(cs[2 * i], cs[2 * i + 1], b1[2 * i], b1[2 * i + 1]);
+    for (int i = 0; i < C; ++i) cst.b2[i] = a.fc2->bias ? (*a.fc2->h_bias)[i] : 0.f;
   }
+  // E2: the fp32 stream (load + store) and the 16-bit copy (store) as 32-row x 16-column boxes
+  uint64_t xdims[2] = {(uint64_t)C, (uint64_t)p.rows};
+  uint64_t xstr[1] = {(uint64_t)a.xt.ld * 4};
+  uint32_t xbox[2] = {16, 32};
+  CUtensorMap tmX = make_tmap_16(a.xt.p, F32, 2, xdims, xstr, xbox, CU_TENSOR_MAP_SWIZZLE_64B);
+  uint64_t x16str[1] = {(uint64_t)a.lne.ldx16 * 2};
+  CUtensorMap tmX16 = make_tmap_16(a.lne.x16, dt, 2, xdims, x16str, xbox, CU_TENSOR_MAP_SWIZZLE_NONE);
   auto launch = [&](auto kern) {
     BRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
     const int pairs = (p.m_tiles + CL - 1) / CL;
@@ -492,7 +517,7 @@ static void launch_mlp(const LaunchCtx& ctx, const MlpArgs& a, MlpP& p) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW1, tmW2, cst, p));
+    BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW1, tmW2, tmX, tmX16, cst, p));
   };
   if (dt == BF16) { if (CL == 2) launch(tc_mlp_kernel<C, 2, true>); else launch(tc_mlp_kernel<C, 1, true>); }
   else { if (CL == 2) launch(tc_mlp_kernel<C, 2, false>); else launch(tc_mlp_kernel<C, 1, false>); }
@@ -507,10 +532,9 @@ void tc_mlp(const LaunchCtx& ctx, const MlpArgs& a) {
   MlpP p{};
   p.rows = a.x16.rows();
   p.m_tiles = (int)((p.rows + ML_BM - 1) / ML_BM);
-  p.bias2 = a.fc2->bias;
   p.mr = a.mr;
-  p.xt = (float*)a.xt.p; p.ldx = a.xt.ld;
-  p.x16 = a.lne.x16; p.ldx16 = a.lne.ldx16; p.mr_out = a.mr_out;
+  p.xt = a.xt.ld == C ? (const float*)a.xt.p : nullptr;
+  p.mr_out = a.mr_out;
   const double rows = (double)p.rows;
   char desc[96] = "";
   if (ctx.kt) snprintf(desc, sizeof desc, "mlp M=%lld C=%d hid=%d tiles=%d", (long long)p.rows, C, 4 * C, p.m_tiles);

@@ -270,6 +270,7 @@ LayerW make_layer_standalone(int N, int Cin, int kh, int kw, const float* w, con
   if (bias) {
     BRN_CUDA(cudaMalloc(&L.bias, (size_t)N * 4)); allocs.push_back(L.bias);
     BRN_CUDA(cudaMemcpy(L.bias, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+    if (N <= 1024) L.h_bias = std::make_shared<std::vector<float>>(bias, bias + N);
   }
   return L;
 }
