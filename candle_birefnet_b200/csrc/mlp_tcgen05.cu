@@ -161,7 +161,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
               const __grid_constant__ CUtensorMap tmX16, const __grid_constant__ MlpConst<C> cst, const MlpP p) {
   using K = MlpCfg<C>;
-  constexpr int KB1 = K::KB1, HID = K::HID, NCH = K::NCH, NSLOT = K::NSLOT;
+  constexpr int KB1 = K::KB1, NCH = K::NCH, NSLOT = K::NSLOT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -374,6 +374,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int NT = n_iter * NG;            // granules of this warp
     // residual of granule n -> slot n % D (lane 0)
     auto res_issue = [&](int n) {
+#if defined(BRN_MLP_EXP) && BRN_MLP_EXP >= 2      // A/B experiment build: E2 without its HBM traffic
+      return;
+#endif
       if (n >= NT) return;
       const int it = n / NG, gran = n - it * NG, d = n % D;
       ptx::mbar_expect_tx(&rf[d], 2048);
@@ -398,7 +401,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         // the TMA stores issued two granules ago have read output blocks b
         if (lane == 0) ptx::tma_store_wait_read_n<1>();
         __syncwarp();
+#if !(defined(BRN_MLP_EXP) && BRN_MLP_EXP >= 2)
         ptx::mbar_wait(&rf[d], (n / D) & 1);
+#endif
         tmem_wait_dep(vo);
         float f[16];
 #pragma unroll
@@ -428,9 +433,11 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         ptx::fence_proxy_async_smem();       // staged blocks -> visible to the TMA engine; residual slot d: reads done
         __syncwarp();
         if (lane == 0) {
+#if !(defined(BRN_MLP_EXP) && BRN_MLP_EXP >= 2)
           ptx::tma_store_2d(&tmX, base + (D + b) * 2048, c, row0);
           ptx::tma_store_2d(&tmX16, base + (D + 2) * 2048 + b * 1024, c, row0);
           ptx::tma_store_commit();
+#endif
           res_issue(n + D);                  // slot d again, D granules ahead (rolls over into the next tile)
         }
       }
