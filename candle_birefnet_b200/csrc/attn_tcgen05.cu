@@ -227,6 +227,7 @@ __device__ __forceinline__ uint32_t at_pack(float a, float b) { return DT == BF1
 template <int DT>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
+  ptx::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sBias = smem;
@@ -264,6 +265,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnP p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();       // above: barriers, TMEM, the head's qkv bias (a weight)
 
   if (warp == AT_SOFT_WARPS) {
     if (n_units > 0) {
@@ -614,8 +616,15 @@ void tc_attention(const LaunchCtx& ctx, const AttnArgs& a) {
   if (ctx.kt) snprintf(desc, sizeof desc, "windows=%d heads=%d shift=%d grid=%d", a.n_windows, a.heads, a.shift, a.heads * per_head);
   KScope ks(ctx, KC_ATTN_TC, 4.0 * 144 * 144 * 32 * (double)a.n_windows * a.heads,
             (double)a.n_windows * a.heads * 144 * 32 * 4 * dsize(a.qkv.dt), desc);   // q, k, v in + o out
-  if (a.qkv.dt == BF16) tc_attn_kernel<BF16><<<a.heads * per_head, AT_THREADS, AT_SMEM, ctx.stream>>>(tm, p);
-  else tc_attn_kernel<F16><<<a.heads * per_head, AT_THREADS, AT_SMEM, ctx.stream>>>(tm, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(a.heads * per_head);
+  cfg.blockDim = dim3(AT_THREADS);
+  cfg.dynamicSmemBytes = AT_SMEM;
+  cfg.stream = ctx.stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr; cfg.numAttrs = pdl_attr(attr, 0);
+  if (a.qkv.dt == BF16) BRN_CUDA(cudaLaunchKernelEx(&cfg, tc_attn_kernel<BF16>, tm, p));
+  else BRN_CUDA(cudaLaunchKernelEx(&cfg, tc_attn_kernel<F16>, tm, p));
   BRN_CUDA(cudaGetLastError());
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -243,6 +244,15 @@ struct KScope {
 void simt_gemm(const LaunchCtx&, const GemmArgs&);
 void simt_deform(const LaunchCtx&, const DeformArgs&);
 void simt_attention(const LaunchCtx&, const AttnArgs&);
+
+// Programmatic dependent launch (tc_ptx.cuh pdl_*): appends the stream-serialization attribute unless BRN_PDL=0
+inline int pdl_attr(cudaLaunchAttribute* attr, int n) {
+  static const bool off = [] { const char* v = getenv("BRN_PDL"); return v && v[0] == '0'; }();
+  if (off) return n;
+  attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[n].val.programmaticStreamSerializationAllowed = 1;
+  return n + 1;
+}
 
 // ---- tcgen05 kernels ----
 bool tc_gemm_supported(const GemmArgs&);

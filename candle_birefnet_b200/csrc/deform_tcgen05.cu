@@ -100,6 +100,7 @@ __device__ __forceinline__ uint4 blend_h2(const uint4 (&v)[4], const uint32_t (&
 template <int CL, int DT>
 __global__ void __launch_bounds__(DF_THREADS, 1)
 tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
+  ptx::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -126,6 +127,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
   if (CL > 1) ptx::cluster_sync_all();     // peers' barriers are initialised before any multicast can land
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   // work items: this CTA's M tile of item i is i * CL + rank (may be >= m_tiles for the odd tail: all rows masked)
   const int rank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
@@ -381,10 +383,10 @@ void tc_deform(const LaunchCtx& ctx, const DeformArgs& a) {
     cfg.blockDim = dim3(DF_THREADS);
     cfg.dynamicSmemBytes = DF_SMEM;
     cfg.stream = ctx.stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_attr(attr, 1);
     BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmB, p));
   };
   if (CL == 2) { if (a.x.dt == BF16) launch(tc_deform_kernel<2, BF16>); else launch(tc_deform_kernel<2, F16>); }

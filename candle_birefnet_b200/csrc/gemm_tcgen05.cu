@@ -124,6 +124,7 @@ template <int CL, int EPI, bool U2 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcGemmP p) {
+  ptx::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -155,6 +156,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CL > 1) ptx::cluster_sync_all();     // peers' barriers are initialised before any multicast can land
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();       // everything above touched only this CTA's shared / tensor memory and kernel parameters
 
   // work items: (m_group, n_tile); this CTA's M tile is m_group * CL + rank
   const int m_groups = (p.m_tiles + CL - 1) / CL;
@@ -646,10 +648,10 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = TC_SMEM;
     cfg.stream = ctx.stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_attr(attr, 1);
     BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, p));
   };
 #define TC_EK_CASE(E) case E: if (CL == 2) launch(tc_gemm_kernel<2, E>); else launch(tc_gemm_kernel<1, E>); break

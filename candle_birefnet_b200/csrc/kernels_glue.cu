@@ -365,6 +365,8 @@ void glue_ln_stats_cast(const LaunchCtx& ctx, View x, View x16, float2* stats) {
 // path of every tile: +30 % on the epilogue-bound stage-0 qkv GEMM, r02 run B).
 __global__ void __launch_bounds__(256) ln_finalize_kernel(const float2* __restrict__ stats, int parts, long long stride,
                                                           long long rows, float invC, float2* __restrict__ mr) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // programmatic dependent launch, tc_ptx.cuh pdl_*
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long m = (long long)blockIdx.x * 256 + threadIdx.x;
   if (m >= rows) return;
   float s = 0.f, q = 0.f;
@@ -381,7 +383,13 @@ void glue_ln_finalize(const LaunchCtx& ctx, const float2* stats, int parts, long
   if (ctx.launches) ++*ctx.launches;
   if (ctx.dry) return;
   KScope ks(ctx, KC_LN, 0.0, (double)rows * (parts + 1) * 8, "ln_finalize");
-  ln_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx.stream>>>(stats, parts, stride, rows, 1.0f / (float)C, mr);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((rows + 255) / 256));
+  cfg.blockDim = dim3(256);
+  cfg.stream = ctx.stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr; cfg.numAttrs = pdl_attr(attr, 0);
+  BRN_CUDA(cudaLaunchKernelEx(&cfg, ln_finalize_kernel, stats, parts, stride, rows, 1.0f / (float)C, mr));
   BRN_CUDA(cudaGetLastError());
 }
 

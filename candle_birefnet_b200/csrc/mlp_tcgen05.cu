@@ -162,6 +162,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               const __grid_constant__ CUtensorMap tmX16, const __grid_constant__ MlpConst<C> cst, const MlpP p) {
   using K = MlpCfg<C>;
   constexpr int KB1 = K::KB1, NCH = K::NCH, NSLOT = K::NSLOT;
+  ptx::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -201,6 +202,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (CL > 1) ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();
 
   // work: cluster `cid` owns tile pairs cid, cid + ncl, ...; this CTA's tile of a pair is pair * CL + rank.  Both CTAs of
   // a cluster run the same number of iterations (the weight ring is shared); a tile past the end loads zeros and stores nothing.
@@ -520,10 +522,10 @@ static void launch_mlp(const LaunchCtx& ctx, const MlpArgs& a, MlpP& p) {
     cfg.blockDim = dim3(ML_THREADS);
     cfg.dynamicSmemBytes = K::SMEM;
     cfg.stream = ctx.stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_attr(attr, 1);
     BRN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW1, tmW2, tmX, tmX16, cst, p));
   };
   if (dt == BF16) { if (CL == 2) launch(tc_mlp_kernel<C, 2, true>); else launch(tc_mlp_kernel<C, 1, true>); }

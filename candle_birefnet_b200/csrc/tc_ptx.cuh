@@ -216,6 +216,14 @@ __device__ __forceinline__ void bulk_load(void* smem, const void* gmem, uint32_t
 }
 
 // ---- tcgen05 ----
+// Programmatic dependent launch.  Every hot kernel signals at its very top that the next kernel in the stream may be
+// launched (its CTAs become resident as this kernel's CTAs retire and run their prologue: barrier init, TMEM allocation,
+// tensor-map prefetch), and waits here -- before its first access to global memory that an earlier kernel may still
+// be writing or reading -- for the preceding kernel to have completed and flushed.  Without the launch attribute
+// (BRN_PDL=0, or a predecessor that is not a kernel) both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // asynchronous L2 prefetch of a contiguous global range (multiple of 16 bytes): no destination, no completion to wait for
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
