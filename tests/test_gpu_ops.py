@@ -190,6 +190,30 @@ def test_swin_mlp_fused(M, C, precision):
     assert np.abs(st[:, 1] / rstd - 1.0).max() < 1e-3
 
 
+@pytest.mark.parametrize("M,C,hid", [(500, 384, 1536), (300, 192, 384), (260, 96, 384)])
+def test_swin_mlp_two_gemm_path(M, C, hid):
+    """Shapes the fused kernel does not take (C = 384: the A tile + one chunk of weights exceed shared memory; mlp_ratio
+    != 4; C = 96) run as folded fc1 + fc2 GEMMs behind the same entry point; fused=1 must refuse them loudly."""
+    rng = np.random.default_rng(M + C + hid)
+    x = rng.standard_normal((M, C)).astype(np.float32)
+    gamma = (1.0 + 0.1 * rng.standard_normal(C)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    w1 = (rng.standard_normal((hid, C)) / np.sqrt(C)).astype(np.float32)
+    b1 = (0.5 * rng.standard_normal(hid)).astype(np.float32)
+    w2 = (rng.standard_normal((C, hid)) / np.sqrt(hid)).astype(np.float32)
+    b2 = (0.5 * rng.standard_normal(C)).astype(np.float32)
+    got, st = cb.ops.swin_mlp(x, gamma, beta, w1, b1, w2, b2, precision="fp16", fused=-1, with_stats=True)
+    xd = torch.from_numpy(x).double()
+    ln = F.layer_norm(xd, (C,), torch.from_numpy(gamma).double(), torch.from_numpy(beta).double(), 1e-5)
+    h = F.gelu(ln @ torch.from_numpy(w1).double().T + torch.from_numpy(b1).double())
+    exp = (xd + h @ torch.from_numpy(w2).double().T + torch.from_numpy(b2).double()).numpy()
+    scale = max(1.0, np.abs(exp).max())
+    assert np.abs(got - exp).max() / scale < 12.0 * 2.0 ** -11
+    assert np.abs(st[:, 0] - got.astype(np.float64).mean(1)).max() < 1e-4 * scale
+    with pytest.raises(cb._lib.BrnError):
+        cb.ops.swin_mlp(x, gamma, beta, w1, b1, w2, b2, precision="fp16", fused=1)
+
+
 def test_preprocess_matches_image_crate_restatement():
     """examples/infer_image.rs:44-67 on the device: Triangle resize_exact + ImageNet normalise of the reference's own
     test photo, against oracle/imageops_ref.py (restatement of the `image` 0.25.9 sampling code).  Triangle weights are
