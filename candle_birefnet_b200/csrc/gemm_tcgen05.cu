@@ -37,6 +37,12 @@ constexpr int TC_B_BYTES = 256 * TC_BK * 2;     // 32 KB (BN <= 256)
 constexpr int TC_BIAS_LD = 288;                                // floats per accumulator stage (BN <= 256, padded to 32)
 constexpr int TC_EPI_BYTES = TC_EPI_WARPS * EPI_STAGE_BYTES + 4 * TC_BIAS_LD * 4;   // bias + LnFold column sums, x2 accumulator stages
 constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_EPI_BYTES + 256 + 1024;
+#ifndef BRN_GEMM_U2_STAGES
+#define BRN_GEMM_U2_STAGES 6
+#endif
+constexpr int TC_STAGES_U2 = BRN_GEMM_U2_STAGES;               // CTA-pair instances (half a B tile per CTA and stage)
+constexpr int TC_SMEM_U2 = TC_STAGES_U2 * (TC_A_BYTES + TC_B_BYTES / 2) + TC_EPI_BYTES + 256 + 1024;
+static_assert(TC_SMEM <= 232448 && TC_SMEM_U2 <= 232448, "shared memory per CTA");
 
 struct TcGemmP {
   int B, H, W;
@@ -125,16 +131,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcGemmP p) {
   ptx::pdl_launch_dependents();
+  // CTA pairs keep HALF of the B tile per CTA: 34 KB per stage instead of 50 KB, so the ring is six stages deep (2,560
+  // instead of 1,536 tensor-pipe cycles of look-ahead for the TMA round trip)
+  constexpr int NST = U2 ? TC_STAGES_U2 : TC_STAGES;
+  constexpr int BBYTES = U2 ? TC_B_BYTES / 2 : TC_B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + TC_STAGES * TC_A_BYTES;
-  uint8_t* sStage = sB + TC_STAGES * TC_B_BYTES;                 // epilogue staging, 2 KB per epilogue warp
+  uint8_t* sB = smem + NST * TC_A_BYTES;
+  uint8_t* sStage = sB + NST * BBYTES;                 // epilogue staging, 2 KB per epilogue warp
   float* sBias = (float*)(sStage + TC_EPI_WARPS * EPI_STAGE_BYTES);
   float* sCs = sBias + 2 * TC_BIAS_LD;                           // LnFold column sums, staged like the bias
   uint64_t* full = (uint64_t*)((uint8_t*)sBias + 4 * TC_BIAS_LD * 4);
-  uint64_t* empty = full + TC_STAGES;
-  uint64_t* tfull = empty + TC_STAGES;
+  uint64_t* empty = full + NST;
+  uint64_t* tfull = empty + NST;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
@@ -142,7 +152,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int rank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
   if (threadIdx.x == 0) {
     constexpr bool u2i = U2;
-    for (int s = 0; s < TC_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], u2i ? 1 : CL); }
+    for (int s = 0; s < NST; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], u2i ? 1 : CL); }
     // pair mode: one elected lane per epilogue warp of BOTH CTAs arrives on the leader's accumulator-empty barrier
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], u2i ? 2 * TC_EPI_WARPS : 32 * TC_EPI_WARPS); }
     ptx::fence_barrier_init();
@@ -173,31 +183,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tx_bytes = p.tg ? TC_A_BYTES + 3 * p.BN * TC_BK * 2 : TC_BM * TC_BK * 2 + p.BN * TC_BK * 2;
       const int b_rows = p.BN / CL;                           // rows of B this CTA loads (and multicasts)
       for (int item = item0; item < num_items; item += item_step) {
-        const int it2 = item / p.ksplit, ks = item - it2 * p.ksplit;
+        // work-item decode by multiply-high, K-block decode by counters: the producer sits on the refill path of every
+        // stage (it wakes when a stage is released), so an integer division here is tensor-pipe idle time
+        const int it2 = (int)p.fd_ks.div((uint32_t)item), ks = item - it2 * p.ksplit;
         const int kb0 = ks * p.kb_per, kb1 = min(kblocks, kb0 + p.kb_per);
-        const int m_tile = (it2 / p.n_tiles) * CL + rank, n_tile = it2 % p.n_tiles;
-        const int b = m_tile / tiles_per_img, r = m_tile - b * tiles_per_img;   // b >= B for the odd tail: TMA zero-fills
-        const int y0 = (r / p.tiles_x) * TH, x0 = (r % p.tiles_x) * TW;
+        const int mg = (int)p.fd_nt.div((uint32_t)it2);
+        const int m_tile = mg * CL + rank, n_tile = it2 - mg * p.n_tiles;
+        const int b = (int)p.fd_tpi.div((uint32_t)m_tile), r = m_tile - b * tiles_per_img;   // b >= B for the odd tail: TMA zero-fills
+        const int ty = (int)p.fd_tx.div((uint32_t)r);
+        const int y0 = ty * TH, x0 = (r - ty * p.tiles_x) * TW;
+        int tap = 0, cb = kb0, ky = 0, kx = 0;
+        if (kb0 != 0) { tap = kb0 / p.cblocks; cb = kb0 - tap * p.cblocks; if (!p.tg) { ky = tap / p.kw; kx = tap - ky * p.kw; } }
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait_backoff(&empty[stage], phase ^ 1);
           if (!u2) ptx::mbar_expect_tx(&full[stage], tx_bytes);
           else if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * (TC_BM * TC_BK * 2 + b_rows * TC_BK * 2));
-          const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+          // (tap, cb, ky, kx) of this K block; `next_kb` advances them
+          auto next_kb = [&] {
+            if (++cb == p.cblocks) { cb = 0; ++tap; if (++kx == p.kw) { kx = 0; ++ky; } }
+            if (++stage == NST) { stage = 0; phase ^= 1; }
+          };
           if (p.tg) {
             // `tap` is the kernel column kx: the (TH+2) x TW box holds the input rows of all three vertical taps
             ptx::tma_load_4d(sA + stage * TC_A_BYTES, &tmA, &full[stage], cb * TC_BK, x0 + tap - 1, y0 - 1, b);
             const int bn = n_tile * p.BN + rank * b_rows;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
-              uint8_t* bdst = sB + stage * TC_B_BYTES + ky * p.BN * (TC_BK * 2) + rank * b_rows * (TC_BK * 2);
+              uint8_t* bdst = sB + stage * BBYTES + ky * p.BN * (TC_BK * 2) + rank * b_rows * (TC_BK * 2);
               const int bk = (ky * 3 + tap) * p.cin_pad + cb * TC_BK;
               if (CL > 1) ptx::tma_load_2d_mc(bdst, &tmB, &full[stage], bk, bn, (uint16_t)((1u << CL) - 1));
               else ptx::tma_load_2d(bdst, &tmB, &full[stage], bk, bn);
             }
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            next_kb();
             continue;
           }
-          const int ky = tap / p.kw, kx = tap - ky * p.kw;
           if (u2) {
             // CTA pair: both CTAs' boxes are counted on the LEADER's barrier (it expects the bytes of both); B is not
             // multicast -- this CTA keeps rows [rank * BN/2, (rank + 1) * BN/2) of the tile at offset 0 of its B stage
@@ -205,16 +224,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // expects twice the per-CTA bytes and the follower's own barrier is simply not used in this mode)
             const uint32_t lbar = ptx::mapa_shared(ptx::smem_u32(&full[stage]), 0);
             ptx::tma_load_4d_2sm(sA + stage * TC_A_BYTES, &tmA, lbar, cb * TC_BK, x0 + kx - p.pad, y0 + ky - p.pad, b);
-            ptx::tma_load_2d_2sm(sB + stage * TC_B_BYTES, &tmB, lbar, tap * p.cin_pad + cb * TC_BK, n_tile * p.BN + rank * b_rows);
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            ptx::tma_load_2d_2sm(sB + stage * BBYTES, &tmB, lbar, tap * p.cin_pad + cb * TC_BK, n_tile * p.BN + rank * b_rows);
+            next_kb();
             continue;
           }
           ptx::tma_load_4d(sA + stage * TC_A_BYTES, &tmA, &full[stage], cb * TC_BK, x0 + kx - p.pad, y0 + ky - p.pad, b);
-          uint8_t* bdst = sB + stage * TC_B_BYTES + rank * b_rows * (TC_BK * 2);
+          uint8_t* bdst = sB + stage * BBYTES + rank * b_rows * (TC_BK * 2);
           const int bk = tap * p.cin_pad + cb * TC_BK, bn = n_tile * p.BN + rank * b_rows;
           if (CL > 1) ptx::tma_load_2d_mc(bdst, &tmB, &full[stage], bk, bn, (uint16_t)((1u << CL) - 1));
           else ptx::tma_load_2d(bdst, &tmB, &full[stage], bk, bn);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          next_kb();
         }
       }
     }
@@ -224,17 +243,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc = ptx::make_idesc_16(u2 ? 2 * TC_BM : TC_BM, p.BN, 0, 0, p.in_bf16);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+#ifdef BRN_GEMM_TIMING
+      long long tm_empty = 0, tm_full = 0, tm_t0 = clock64(), tm_a;
+#endif
       for (int item = item0; item < num_items; item += item_step) {
+#ifdef BRN_GEMM_TIMING
+        tm_a = clock64();
+#endif
         ptx::mbar_wait_backoff(&tempty[acc], acc_phase ^ 1);
+#ifdef BRN_GEMM_TIMING
+        tm_empty += clock64() - tm_a;
+#endif
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        const int ks = item % p.ksplit;
+        const int ks = item - (int)p.fd_ks.div((uint32_t)item) * p.ksplit;
         const int kbn = min(kblocks, (ks + 1) * p.kb_per) - ks * p.kb_per;     // K blocks of this work item
         for (int kb = 0; kb < kbn; ++kb) {
+#ifdef BRN_GEMM_TIMING
+          tm_a = clock64();
+#endif
           ptx::mbar_wait(&full[stage], phase);
+#ifdef BRN_GEMM_TIMING
+          tm_full += clock64() - tm_a;
+#endif
           ptx::tc_fence_after();
           const uint64_t a_desc = ptx::make_smem_desc(ptx::smem_u32(sA + stage * TC_A_BYTES), 16, 1024, ptx::SW_128B);
-          const uint64_t b_desc = ptx::make_smem_desc(ptx::smem_u32(sB + stage * TC_B_BYTES), 16, 1024, ptx::SW_128B);
+          const uint64_t b_desc = ptx::make_smem_desc(ptx::smem_u32(sB + stage * BBYTES), 16, 1024, ptx::SW_128B);
           if (p.tg) {
             // vertical tap ky = the same box read one pixel row (8 pixels = one 1024-byte swizzle atom) further down
             const uint32_t b_step = (uint32_t)(p.BN * TC_BK * 2) >> 4;
@@ -256,12 +290,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (u2) ptx::umma_commit_2sm(&empty[stage], (uint16_t)3);
           else if (CL > 1) ptx::umma_commit_mc(&empty[stage], (uint16_t)((1u << CL) - 1));
           else ptx::umma_commit(&empty[stage]);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
         if (u2) ptx::umma_commit_2sm(&tfull[acc], (uint16_t)3);     // both CTAs' epilogues
         else ptx::umma_commit(&tfull[acc]);
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
+#ifdef BRN_GEMM_TIMING
+      if (blockIdx.x == 0 || blockIdx.x == 77)
+        printf("[gemm timing] cta %d EPI %d items %d: total %lld clk, mma waits: acc-empty %lld, smem-full %lld\n", (int)blockIdx.x, EPI,
+               (num_items - item0 + item_step - 1) / item_step, clock64() - tm_t0, tm_empty, tm_full);
+#endif
     }
   } else {
     // ===== epilogue: warp % 4 selects the TMEM lane quadrant, (warp - 2) / 4 the column part =====
@@ -285,6 +324,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (!(m_tile < p.m_tiles && y < p.H && x < p.W)) return -1;
       return ((long long)b * p.H + y) * p.W + x;
     };
+#ifdef BRN_GEMM_TIMING
+    long long tm_ewait = 0; const long long tm_es = clock64();
+#endif
     float2 mr_next = make_float2(0.f, 1.f);
     if (EPI == EK_LNF_NONE16 || EPI == EK_LNF_GELU16) {
       const long long a0 = a_row_of(item0);
@@ -327,7 +369,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
       }
+#ifdef BRN_GEMM_TIMING
+      const long long tm_e0 = clock64();
+#endif
       ptx::mbar_wait(&tfull[acc], acc_phase);
+#ifdef BRN_GEMM_TIMING
+      tm_ewait += clock64() - tm_e0;
+#endif
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
       const uint32_t sbb = sb;
@@ -373,6 +421,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
+#ifdef BRN_GEMM_TIMING
+    if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && (warp == 2 || warp == 9))
+      printf("[gemm timing] cta %d epilogue warp %d: total %lld clk, waits on acc-full %lld\n", (int)blockIdx.x, warp, clock64() - tm_es, tm_ewait);
+#endif
     if ((EPI == EK_NONE16 || EPI == EK_GELU16 || EPI == EK_LNF_GELU16) && p.tma_store && lane == 0)
       ptx::tma_store_wait_all();           // this warp's bulk stores are performed before the CTA retires
   }
@@ -628,7 +680,8 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   static const bool no_u2 = [] { const char* v = getenv("BRN_GEMM_UMMA2"); return v && v[0] == '0'; }();
   // (K >= 1536 only: the pair couples the two CTAs' epilogues, which costs 20-40 % on the epilogue-bound short-K shapes
   //  and gains 1-2 % on the long-K ones -- kernel_bench A/B, r02 run G)
-  p.u2 = (!no_u2 && CL == 2 && !tg && S == 1 && p.BN == 256 && kblocks >= 24 &&
+  static const int u2_minkb = [] { const char* v = getenv("BRN_GEMM_U2_MINKB"); return v ? atoi(v) : 24; }();
+  p.u2 = (!no_u2 && CL == 2 && !tg && S == 1 && p.BN == 256 && kblocks >= u2_minkb &&
           (ek == EK_RES32_EMIT || ek == EK_NONE32_EMIT || ek == EK_LNF_GELU16 || ek == EK_LNF_NONE16)) ? 1 : 0;
   CUtensorMap tmO = tmA;                 // placeholder when unused (never dereferenced)
   p.tma_store = 0;
@@ -641,6 +694,7 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
     p.tma_store = 1;
   }
   auto launch = [&](auto kern) {
+    const int TC_SMEM = p.u2 ? brn::TC_SMEM_U2 : brn::TC_SMEM;
     BRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     const int items = ((p.m_tiles + CL - 1) / CL) * p.n_tiles * p.ksplit;
     cudaLaunchConfig_t cfg{};

@@ -38,6 +38,15 @@ def main():
         gemm("dec1 conv1 1024->64", 0, 64, 1024, k=1, act=1, B=16, H=256, W=256)
         gemm("dec1 conv_out 64->192", 0, 192, 64, k=3, f32=True, B=16, H=256, W=256)
         gemm("lat2 384->384 res", 0, 384, 384, k=1, res=True, B=16, H=256, W=256)
+    if which == "s2":     # the four GEMMs of a stage-2 block + the stage-1 / stage-3 MLP pair
+        gemm("s2 fc1 gelu", 65536, 3072, 768, act=2)
+        gemm("s2 qkv", 82944, 2304, 768)
+        gemm("s2 fc2 res", 65536, 768, 3072, res=True, f32=True)
+        gemm("s2 proj res", 82944, 768, 768, res=True, f32=True)
+        gemm("s1 fc1 gelu", 262144, 1536, 384, act=2)
+        gemm("s1 fc2 res", 262144, 384, 1536, res=True, f32=True)
+        gemm("s3 fc1 gelu", 16384, 6144, 1536, act=2)
+        gemm("s3 fc2 res", 16384, 1536, 6144, res=True, f32=True)
     if which == "tg":
         gemm("dec1 conv_in 480->64", 0, 64, 480, k=3, act=1, B=16, H=256, W=256)
         gemm("dec2 conv_in 960->64", 0, 64, 960, k=3, act=1, B=16, H=128, W=128)
@@ -92,6 +101,12 @@ def main():
                 gb = 12.0 * M * Cc
                 print(f"mlp M={M} C={Cc} {prec}: fc1+fc2 {ms0*1e3:8.1f} us {fl/ms0/1e9:6.1f} TF/s | fused {ms1*1e3:8.1f} us "
                       f"{fl/ms1/1e9:6.1f} TF/s {gb/ms1/1e6:6.0f} GB/s compulsory", flush=True)
+        return
+    if which == "mlp2":    # fc1 (LayerNorm fold + GELU) and fc2 (fp32 residual + emit) as the model launches them, stage 2 / 3 rows
+        for (M, Cc) in ((81920, 768), (20480, 1536), (327680, 384)):
+            ms0 = ops.bench_op("mlp", 1, 1, M, Cc, with_res=False, precision="fp16")
+            fl = 16.0 * M * Cc * Cc
+            print(f"mlp2 M={M} C={Cc}: fc1+fc2 {ms0*1e3:8.1f} us {fl/ms0/1e9:6.1f} TF/s", flush=True)
         return
     if which == "attn1":   # attn1 <windows> <heads> <side> <shift>
         nw, heads, side, shift = [int(v) for v in sys.argv[2:6]]
