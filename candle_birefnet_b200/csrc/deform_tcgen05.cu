@@ -154,7 +154,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
     const long long img_elems = (long long)p.H * p.W * p.ldx;
 
     // position in the tap sequence: local item `it`, tap (ky, kx); per-pixel data of the parameter role
-    int it = 0, tap = q, ky = 0, kx = 0, y = 0, x = 0, tile = 0;
+    int it = 0, tap = q, ky = 0, kx = 0, y = 0, x = 0, tile = 0, img = 0;
     bool row_ok = false;
     const float* o = p.om; long long os1 = 1;
     auto enter_tile = [&]() {
@@ -163,6 +163,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
       const int t = (item0 + it * item_step) * CL + rank;
       tile = min(t, p.m_tiles - 1);
       const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
+      img = b;
       y = (t2 / p.tiles_x) * DF_TH + (pr >> 4); x = (t2 % p.tiles_x) * DF_TW + (pr & 15);
       row_ok = t < p.m_tiles && y < p.H && x < p.W;
       ky = tap / p.k; kx = tap - ky * p.k;
@@ -201,7 +202,7 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
     if (it < n_my_items) params(0, ldg_stream(o + 2 * tap * os1), ldg_stream(o + (2 * tap + 1) * os1), ldg_stream(o + (2 * p.taps + tap) * os1));
     asm volatile("bar.sync %0, 256;" ::"r"(2 + q) : "memory");
     for (int k = 0; it < n_my_items; ++k) {
-      const uint16_t* xb = p.x + (long long)(tile / tiles_per_img) * img_elems + l8 * 8;   // image of the CURRENT tap's tile
+      const uint16_t* xb = p.x + (long long)img * img_elems + l8 * 8;   // image of the CURRENT tap's tile (no division per tap)
       // step to the group's next tap and fetch its offsets now; its parameters are computed below, while the second
       // half of this tap's corners is in flight
       advance2();
@@ -263,11 +264,13 @@ tc_deform_kernel(const __grid_constant__ CUtensorMap tmB, const DeformP p) {
       const long long total = (long long)n_my_tiles * p.taps;
       // the B loads run DF_STAGES ahead of the MMAs (same ring, same stage order)
       long long issued = 0;
+      int btap = 0;                                            // tap of the next B load (issued % taps without the 64-bit division)
       int lstage = 0; uint32_t lphase = 0;
       auto issue_b = [&]() {
         ptx::mbar_wait(&empty[lstage], lphase ^ 1);
         ptx::mbar_expect_tx(&full[lstage], b_bytes);
-        const int tap = (int)(issued % p.taps);
+        const int tap = btap;
+        if (++btap == p.taps) btap = 0;
         uint8_t* bdst = sB + lstage * DF_B_BYTES + rank * b_rows * 128;
         if (CL > 1) ptx::tma_load_2d_mc(bdst, &tmB, &full[lstage], tap * 64, rank * b_rows, (uint16_t)((1u << CL) - 1));
         else ptx::tma_load_2d(bdst, &tmB, &full[lstage], tap * 64, 0);

@@ -327,6 +327,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef BRN_GEMM_TIMING
     long long tm_ewait = 0; const long long tm_es = clock64();
 #endif
+    // Bias (and LnFold column sums) of ALL N columns staged once per kernel when they fit the staging area (N <= 576 with, N <= 1152 without
+    // LnFold; one bias vector for every image): the per-tile staging below is an L2 round trip + a barrier of the eight epilogue
+    // warps in front of every tile, which the epilogue-bound short-K GEMMs (200 tiles per SM at stage 0) cannot hide
+    constexpr bool kLnfK = EPI == EK_LNF_NONE16 || EPI == EK_LNF_GELU16;
+    // (without LnFold the column-sum half of the area is free: N <= 1152)
+    constexpr int kOnceCap = (kLnfK ? 2 : 4) * TC_BIAS_LD;
+    const bool bias_once = p.epi.bias_bstride == 0 && p.epi.N <= kOnceCap;
+    if (bias_once) {
+      for (int t = eth; t < kOnceCap; t += 32 * TC_EPI_WARPS) {
+        ptx::sts32(ptx::smem_u32(sBias) + t * 4, (p.epi.bias && t < p.epi.N) ? __ldg(p.epi.bias + t) : 0.f);
+        if (kLnfK) ptx::sts32(ptx::smem_u32(sCs) + t * 4, t < p.epi.N ? __ldg(p.epi.lnf_colsum + t) : 0.f);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+    }
+    // otherwise: per tile, double buffered with the accumulator stage -- but fetched into registers one tile ahead, so
+    // the L2 latency of the loads overlaps the previous tile's epilogue (thread t holds elements t and t + 256)
+    float pb0 = 0.f, pb1 = 0.f, pc0 = 0.f, pc1 = 0.f;
+    auto bias_fetch = [&](int item) {
+      if (item >= num_items) return;
+      const int it2 = (int)p.fd_ks.div((uint32_t)item);
+      const int mg = (int)p.fd_nt.div((uint32_t)it2);
+      const int m_tile = mg * CL + rank, n0 = (it2 - mg * p.n_tiles) * p.BN;
+      const int b = (int)p.fd_tpi.div((uint32_t)m_tile);
+      const float* bias = p.epi.bias ? p.epi.bias + (long long)(m_tile < p.m_tiles ? b : 0) * p.epi.bias_bstride : nullptr;
+      const int t1 = eth + 32 * TC_EPI_WARPS;
+      pb0 = (bias && eth < p.BN && n0 + eth < p.epi.N) ? __ldg(bias + n0 + eth) : 0.f;
+      pb1 = (bias && t1 < p.BN && n0 + t1 < p.epi.N) ? __ldg(bias + n0 + t1) : 0.f;
+      if (kLnfK) {
+        pc0 = (eth < p.BN && n0 + eth < p.epi.N) ? __ldg(p.epi.lnf_colsum + n0 + eth) : 0.f;
+        pc1 = (t1 < p.BN && n0 + t1 < p.epi.N) ? __ldg(p.epi.lnf_colsum + n0 + t1) : 0.f;
+      }
+    };
+    static_assert(TC_BIAS_LD <= 64 * TC_EPI_WARPS, "two staged elements per epilogue thread");
+    if (!bias_once) bias_fetch(item0);
     float2 mr_next = make_float2(0.f, 1.f);
     if (EPI == EK_LNF_NONE16 || EPI == EK_LNF_GELU16) {
       const long long a0 = a_row_of(item0);
@@ -356,18 +390,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int gsz = o32 ? 1 : 2;                           // 16-bit output: keep the split on 32-column granules
       const int per = ((nch + gsz - 1) / gsz + PER_Q - 1) / PER_Q * gsz;
       const int c0 = min(part * per, nch) * 16, c1 = min((part + 1) * per, nch) * 16;
-      const uint32_t sb = ptx::smem_u32(sBias) + acc * TC_BIAS_LD * 4;
-      {
-        // this tile's bias -> shared (double buffered with the accumulator stage; an M tile lies inside one image).
-        // Staged unconditionally (zeros without a bias): an optional add costs a register move per element.
-        const float* bias = p.epi.bias ? p.epi.bias + (long long)(m_tile < p.m_tiles ? b : 0) * p.epi.bias_bstride : nullptr;
-        for (int t = eth; t < TC_BIAS_LD; t += 32 * TC_EPI_WARPS) {
-          ptx::sts32(sb + t * 4, (bias && t < p.BN && n0 + t < p.epi.N) ? __ldg(bias + n0 + t) : 0.f);
-          if (kLnf)
-            ptx::sts32(ptx::smem_u32(sCs) + (acc * TC_BIAS_LD + t) * 4,
-                       (t < p.BN && n0 + t < p.epi.N) ? __ldg(p.epi.lnf_colsum + n0 + t) : 0.f);
+      const uint32_t sb = ptx::smem_u32(sBias) + (bias_once ? n0 : acc * TC_BIAS_LD) * 4;
+      const uint32_t scs_t = ptx::smem_u32(sCs) + (bias_once ? n0 : acc * TC_BIAS_LD) * 4;
+      if (!bias_once) {
+        // this tile's bias (fetched during the previous tile) -> shared; an M tile lies inside one image.  Staged
+        // unconditionally (zeros without a bias): an optional add costs a register move per element.
+        const int t1 = eth + 32 * TC_EPI_WARPS;
+        ptx::sts32(sb + eth * 4, pb0);
+        if (t1 < TC_BIAS_LD) ptx::sts32(sb + t1 * 4, pb1);
+        if (kLnf) {
+          ptx::sts32(scs_t + eth * 4, pc0);
+          if (t1 < TC_BIAS_LD) ptx::sts32(scs_t + t1 * 4, pc1);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        bias_fetch(item + item_step);
       }
 #ifdef BRN_GEMM_TIMING
       const long long tm_e0 = clock64();
@@ -386,7 +422,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         epi_warp<ACT_GELU, false, 0, true, false, false, true>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane, 0.f, 1.f, 0, 0, &tmO, trow0);
       else if (EPI == EK_LNF_GELU16 && p.tma_store)
         epi_warp<ACT_GELU, false, 0, true, true, false, true>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane, nmu, rstd,
-                                                              ptx::smem_u32(sCs) + acc * TC_BIAS_LD * 4, 0, &tmO, trow0);
+                                                              scs_t, 0, &tmO, trow0);
       else if (EPI == EK_NONE16) epi_warp<ACT_NONE, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
       else if (EPI == EK_RELU16) epi_warp<ACT_RELU, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
       else if (EPI == EK_GELU16) epi_warp<ACT_GELU, false, 0>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
@@ -395,10 +431,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       else if (EPI == EK_RES16) epi_warp<ACT_NONE, false, 2>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane);
       else if (EPI == EK_LNF_NONE16)
         epi_warp<ACT_NONE, false, 0, true, true, false>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane, nmu, rstd,
-                                                        ptx::smem_u32(sCs) + acc * TC_BIAS_LD * 4);
+                                                        scs_t);
       else if (EPI == EK_LNF_GELU16)
         epi_warp<ACT_GELU, false, 0, true, true, false>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane, nmu, rstd,
-                                                        ptx::smem_u32(sCs) + acc * TC_BIAS_LD * 4);
+                                                        scs_t);
       else if (EPI == EK_RES32_EMIT)
         epi_warp<ACT_NONE, true, 1, false, false, true>(p.epi, taddr, n0, c0, c1, orow, sbb, stage, lane, 0.f, 1.f, 0,
                                                         n_tile * PER_Q + part);
