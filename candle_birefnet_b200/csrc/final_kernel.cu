@@ -20,14 +20,16 @@ namespace brn {
 constexpr int FIN_TAB = 336;
 constexpr int FT_W = 128, FT_H = 8, FT_PX = 4;          // block = 128 x 8 outputs, FT_PX horizontally adjacent outputs per thread
 constexpr int FT_THREADS = (FT_W / FT_PX) * FT_H;
-constexpr int FT_LD = FT_W + 4;                          // 132 floats: 16-byte aligned rows
+constexpr int FT_LD = FT_W + 8;                          // 136 floats: shared column j holds image column tx0 - 4 + j, so the
+                                                         // tile is filled with aligned 16-byte global loads (halo 2, loaded as 4)
+constexpr int FT_OFF = 2;                                // shared column of image column (tx0 - 2): first tap of output 0
 
 // the 5x5 kernel and its bias travel in the kernel parameter (constant bank): the unrolled FFMAs read them as
 // immediate-offset constant operands instead of one shared-memory load per MAC
 struct FinK5 { float k[76]; };
 
-__device__ __forceinline__ void fin_bilin(int dst, int in, int out, int& i0, int& i1, float& l) {
-  float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+__device__ __forceinline__ float fin_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+__device__ __forceinline__ void fin_bilin(int dst, int in, float scale, int& i0, int& i1, float& l) {
   float s = scale * dst;
   i0 = min((int)s, in - 1);
   i1 = min(i0 + 1, in - 1);
@@ -41,21 +43,34 @@ __global__ void __launch_bounds__(FT_THREADS) final_kernel(const float* __restri
   __shared__ float st[FIN_TAB];
   const int b = blockIdx.z, ty0 = blockIdx.y * FT_H, tx0 = blockIdx.x * FT_W, tid = threadIdx.x;
   for (int i = tid; i < FIN_TAB; i += FT_THREADS) st[i] = tab[i];
-  for (int i = tid; i < 3 * (FT_H + 4) * FT_LD; i += FT_THREADS) {
-    const int c = i / ((FT_H + 4) * FT_LD), r = i % ((FT_H + 4) * FT_LD), yy = r / FT_LD, xx = r % FT_LD;
-    const int gy = ty0 + yy - 2, gx = tx0 + xx - 2;
-    xin[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(x + ((long long)(b * 3 + c) * H + gy) * W + gx) : 0.f;
+  if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // 16-byte loads: a float4 at image column tx0 - 4 + 4 k is either completely inside or completely outside the row
+    constexpr int V = FT_LD / 4;
+    for (int i = tid; i < 3 * (FT_H + 4) * V; i += FT_THREADS) {
+      const int c = i / ((FT_H + 4) * V), r = i % ((FT_H + 4) * V), yy = r / V, k = r % V;
+      const int gy = ty0 + yy - 2, gx = tx0 - 4 + 4 * k;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const float4*>(x + ((long long)(b * 3 + c) * H + gy) * W + gx));
+      *reinterpret_cast<float4*>(&xin[c][yy][4 * k]) = v;
+    }
+  } else {
+    for (int i = tid; i < 3 * (FT_H + 4) * FT_LD; i += FT_THREADS) {
+      const int c = i / ((FT_H + 4) * FT_LD), r = i % ((FT_H + 4) * FT_LD), yy = r / FT_LD, xx = r % FT_LD;
+      const int gy = ty0 + yy - 2, gx = tx0 + xx - 4;
+      xin[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(x + ((long long)(b * 3 + c) * H + gy) * W + gx) : 0.f;
+    }
   }
   __syncthreads();
   const int ly = tid / (FT_W / FT_PX), lx = (tid % (FT_W / FT_PX)) * FT_PX;
   const int gy = ty0 + ly, gx0 = tx0 + lx;
   if (gy >= H || gx0 >= W) return;
   int y0, y1; float fy;
-  fin_bilin(gy, qh, H, y0, y1, fy);
+  const float sc_y = fin_scale(qh, H), sc_x = fin_scale(qw, W);     // one division each per thread, not per output
+  fin_bilin(gy, qh, sc_y, y0, y1, fy);
   const float* qb = q + (long long)b * qh * qw;
   auto finish = [&](int gx, float a) {       // + up(q), optional sigmoid
     int x0, x1; float fx;
-    fin_bilin(gx, qw, W, x0, x1, fx);
+    fin_bilin(gx, qw, sc_x, x0, x1, fx);
     const float up = (1.f - fy) * ((1.f - fx) * __ldg(qb + y0 * qw + x0) + fx * __ldg(qb + y0 * qw + x1)) +
                      fy * ((1.f - fx) * __ldg(qb + y1 * qw + x0) + fx * __ldg(qb + y1 * qw + x1));
     float v = a + up;
@@ -72,9 +87,11 @@ __global__ void __launch_bounds__(FT_THREADS) final_kernel(const float* __restri
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
       for (int u = 0; u < 5; ++u) {
+        // image columns gx0 - 2 .. gx0 + 5 = shared columns lx + 2 .. lx + 9
         const float4 r0 = *reinterpret_cast<const float4*>(&xin[ci][ly + u][lx]);
         const float4 r1 = *reinterpret_cast<const float4*>(&xin[ci][ly + u][lx + 4]);
-        const float row[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const float4 r2 = *reinterpret_cast<const float4*>(&xin[ci][ly + u][lx + 8]);
+        const float row[8] = {r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y};
 #pragma unroll
         for (int v = 0; v < 5; ++v)
 #pragma unroll
@@ -93,7 +110,7 @@ __global__ void __launch_bounds__(FT_THREADS) final_kernel(const float* __restri
       a = st[328];
       for (int ci = 0; ci < 3; ++ci)
         for (int u = 0; u < 5; ++u)
-          for (int v = 0; v < 5; ++v) a = fmaf(st[ci * 25 + u * 5 + v], xin[ci][ly + u][lx + e + v], a);
+          for (int v = 0; v < 5; ++v) a = fmaf(st[ci * 25 + u * 5 + v], xin[ci][ly + u][lx + FT_OFF + e + v], a);
     } else {
       a = st[327];
       for (int i = 0; i < 3; ++i)
@@ -104,7 +121,7 @@ __global__ void __launch_bounds__(FT_THREADS) final_kernel(const float* __restri
           float s = st[318 + i * 3 + j];
           for (int ci = 0; ci < 3; ++ci)
             for (int ky = 0; ky < 3; ++ky)
-              for (int kx = 0; kx < 3; ++kx) s = fmaf(m[ci * 9 + ky * 3 + kx], xin[ci][ly + i + ky][lx + e + j + kx], s);
+              for (int kx = 0; kx < 3; ++kx) s = fmaf(m[ci * 9 + ky * 3 + kx], xin[ci][ly + i + ky][lx + FT_OFF + e + j + kx], s);
           a += s;
         }
     }
