@@ -115,7 +115,7 @@ __device__ __forceinline__ void mlp_g8_poly(MlpG8& g, const uint32_t* v, const f
     g.relu[4 * j] = fmaxf(x0, 0.f); g.relu[4 * j + 1] = fmaxf(x1, 0.f);
     g.relu[4 * j + 2] = fmaxf(x2, 0.f); g.relu[4 * j + 3] = fmaxf(x3, 0.f);
   }
-#if defined(BRN_MLP_EXP) && BRN_MLP_EXP >= 1      // A/B experiment builds (scripts/r02_gpu_p.sh): no polynomial
+#if defined(BRN_MLP_EXP) && BRN_MLP_EXP >= 1      // A/B experiment builds (scripts/history/r02_gpu_p.sh): no polynomial
 #pragma unroll
   for (int i = 0; i < 4; ++i) g.l[i] = g.na[i];
   return;

@@ -37,7 +37,7 @@ def iou(a, b):
 # IoU@0.5 gates.  fp16 operands (the shipped default and what bench.py runs) meet the north-star 0.999 everywhere.
 # bf16 operands (8-bit mantissa) meet it on the photo but NOT on randn inputs, where random-init logits are not
 # bimodal (std 0.56, 0.6 % of the pixels within 5e-3 of the threshold): measured 0.9989 / 0.9975 (A / B) with the
-# bf16 backbone + fp16 decoder policy, 0.9977 / 0.9952 with bf16 everywhere (scripts/r02_exp_parity.py, r02 run A).
+# bf16 backbone + fp16 decoder policy, 0.9977 / 0.9952 with bf16 everywhere (scripts/history/r02_exp_parity.py, r02 run A).
 # The bf16 randn gate below is therefore a regression bound, not a north-star pass -- DESIGN.md section 5 says so.
 MIN_IOU = {("fp16", "randn"): 0.999, ("fp16", "cat"): 0.999, ("bf16", "cat"): 0.999, ("bf16", "randn"): 0.996}
 
