@@ -716,9 +716,15 @@ void tc_gemm(const LaunchCtx& ctx, const GemmArgs& a) {
   static const bool no_u2 = [] { const char* v = getenv("BRN_GEMM_UMMA2"); return v && v[0] == '0'; }();
   // (K >= 1536 only: the pair couples the two CTAs' epilogues, which costs 20-40 % on the epilogue-bound short-K shapes
   //  and gains 1-2 % on the long-K ones -- kernel_bench A/B, r02 run G)
+  // K threshold (in 64-element K blocks) from which the pair form is used, separately for the LayerNorm-fold consumers
+  // (qkv, fc1) and the fp32-stream producers (proj, fc2, merge).  Isolated, the pair form wins from K = 1536 (24 blocks)
+  // and loses ~1 % at K = 768; in the power-capped full-model step 24 / 24, 12 / 24 and 12 / 12 are within the run-to-run
+  // noise of each other (271.4-273.4 images/s, same box, alternating: r02 runs D2 / E2)
   static const int u2_minkb = [] { const char* v = getenv("BRN_GEMM_U2_MINKB"); return v ? atoi(v) : 24; }();
-  p.u2 = (!no_u2 && CL == 2 && !tg && S == 1 && p.BN == 256 && kblocks >= u2_minkb &&
-          (ek == EK_RES32_EMIT || ek == EK_NONE32_EMIT || ek == EK_LNF_GELU16 || ek == EK_LNF_NONE16)) ? 1 : 0;
+  static const int u2_minkb_res = [] { const char* v = getenv("BRN_GEMM_U2_MINKB_RES"); return v ? atoi(v) : 24; }();
+  const bool ek_lnf = ek == EK_LNF_GELU16 || ek == EK_LNF_NONE16, ek_emit = ek == EK_RES32_EMIT || ek == EK_NONE32_EMIT;
+  p.u2 = (!no_u2 && CL == 2 && !tg && S == 1 && p.BN == 256 &&
+          ((ek_lnf && kblocks >= u2_minkb) || (ek_emit && kblocks >= u2_minkb_res))) ? 1 : 0;
   CUtensorMap tmO = tmA;                 // placeholder when unused (never dereferenced)
   p.tma_store = 0;
   if (!no_ts && (ek == EK_NONE16 || ek == EK_GELU16 || ek == EK_LNF_GELU16) && a.x.B == 1 && a.x.H == 1 && !a.rowmap.enabled &&

@@ -34,7 +34,10 @@ def relerr(got, exp):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 192, 192), (1000, 576, 192), (257, 48, 96), (144, 3, 64),
-                                    (5184, 2304, 768)])
+                                    (5184, 2304, 768),
+                                    # several work items per CTA with the N tile changing from item to item: bias staged
+                                    # once per kernel (N <= 1152) / fetched one tile ahead (N > 1152)
+                                    (20000, 768, 256), (20000, 1536, 128)])
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_linear(M, N, K, precision):
     rng = np.random.default_rng(M + N + K)
@@ -122,7 +125,10 @@ def test_window_attention(nimg, hp, wp, heads, shift, precision):
     assert err < {"bf16": 3e-2, "fp16": 4e-3, "fp32": 2e-5}[precision], err
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 576, 192), (1000, 1152, 384), (777, 3072, 768), (200, 4608, 1536)])
+@pytest.mark.parametrize("M,N,K", [(300, 576, 192), (1000, 1152, 384), (777, 3072, 768), (200, 4608, 1536),
+                                    # persistent CTAs walking several (M, N) tiles: column sums + bias staged once
+                                    # (N = 576) / fetched one tile ahead (N = 1536)
+                                    (40000, 576, 192), (20000, 1536, 384)])
 @pytest.mark.parametrize("mean_over_std", [0.0, 3.0, 30.0])
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 @pytest.mark.parametrize("act", [0, 2])
