@@ -327,11 +327,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef BRN_GEMM_TIMING
     long long tm_ewait = 0; const long long tm_es = clock64();
 #endif
-    // Bias (and LnFold column sums) of ALL N columns staged once per kernel when they fit the staging area (N <= 576 with, N <= 1152 without
-    // LnFold; one bias vector for every image): the per-tile staging below is an L2 round trip + a barrier of the eight epilogue
-    // warps in front of every tile, which the epilogue-bound short-K GEMMs (200 tiles per SM at stage 0) cannot hide
+    // Bias (and LnFold column sums) of ALL N columns staged once per kernel when they fit the staging area (N <= 576 with
+    // LnFold, N <= 1152 without: the column-sum half of the area is free then; one bias vector for every image).  The
+    // per-tile staging below is an L2 round trip + a barrier of the eight epilogue warps in front of every tile, which
+    // the epilogue-bound short-K GEMMs (200 tiles per SM at stage 0) cannot hide.
     constexpr bool kLnfK = EPI == EK_LNF_NONE16 || EPI == EK_LNF_GELU16;
-    // (without LnFold the column-sum half of the area is free: N <= 1152)
     constexpr int kOnceCap = (kLnfK ? 2 : 4) * TC_BIAS_LD;
     const bool bias_once = p.epi.bias_bstride == 0 && p.epi.N <= kOnceCap;
     if (bias_once) {
