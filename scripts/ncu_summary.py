@@ -40,4 +40,5 @@ if __name__ == "__main__":
     for m in WANT:
         if any(m in d for d in data):
             unit = next((d[m][1] for d in data if m in d), "")
-            w.writerow([m, unit] + [d.get(m, ("", ""))[0] for d in data])
+            # a capture whose unit differs from the first one's (us vs ms, Mbyte vs Gbyte) carries its unit in the cell
+            w.writerow([m, unit] + [(d[m][0] if d[m][1] == unit else f"{d[m][0]} {d[m][1]}") if m in d else "" for d in data])
