@@ -97,7 +97,13 @@ __device__ __forceinline__ void bilin_coord(int dst, int in, int out, int& i0, i
 __global__ void resize_nchw_kernel(const float* x, int C, int H, int W, float* out, int Ho, int Wo, long long total) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int ox = (int)(i % Wo); long long t = i / Wo; int oy = (int)(t % Ho); long long bc = t / Ho;
+  int ox, oy; long long bc;
+  if (total <= 0x7fffffffll) {          // 32-bit index decode (the 64-bit divisions dominated the instruction count)
+    const uint32_t i32 = (uint32_t)i, t32 = i32 / (uint32_t)Wo, b32 = t32 / (uint32_t)Ho;
+    ox = (int)(i32 - t32 * (uint32_t)Wo); oy = (int)(t32 - b32 * (uint32_t)Ho); bc = b32;
+  } else {
+    ox = (int)(i % Wo); long long t = i / Wo; oy = (int)(t % Ho); bc = t / Ho;
+  }
   int y0, y1, x0, x1; float ly, lx;
   bilin_coord(oy, H, Ho, y0, y1, ly);
   bilin_coord(ox, W, Wo, x0, x1, lx);
@@ -625,7 +631,17 @@ __global__ void __launch_bounds__(256) deform_sample_k1_kernel(const uint16_t* _
   const long long i = FUSED ? min(i0, total - 1) : i0;      // FUSED: every lane takes part in the shuffles
   if (!FUSED && i >= total) return;
   const int l8 = (int)(i & 7); const long long px = i >> 3;
-  const int xx = (int)(px % W); const long long t = px / W; const int y = (int)(t % H); const long long b = t / H;
+  // pixel -> (b, y, x) in 32-bit arithmetic when the pixel count allows it (always, in the model): the four 64-bit
+  // divisions were the larger part of this kernel's instructions
+  int xx, y; long long b;
+  if (total <= 0x7fffffffll * 8) {
+    const uint32_t p32 = (uint32_t)px, t32 = p32 / (uint32_t)W;
+    xx = (int)(p32 - t32 * (uint32_t)W);
+    const uint32_t b32 = t32 / (uint32_t)H;
+    y = (int)(t32 - b32 * (uint32_t)H); b = b32;
+  } else {
+    xx = (int)(px % W); const long long t = px / W; y = (int)(t % H); b = t / H;
+  }
   float dy, dx, mk;
   if (FUSED) {
     const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + px * ldx + l8 * 8));
